@@ -1,0 +1,67 @@
+// Shared host/device helpers for libdlpm_b200.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/dlpm_b200.h"
+
+namespace dlpm {
+
+void set_error(const char* fmt, ...);
+
+inline int cuda_fail(cudaError_t e, const char* what) {
+  set_error("%s: %s", what, cudaGetErrorString(e));
+  return DLPM_ERR_CUDA;
+}
+
+#define DLPM_CHECK_LAUNCH(what)                                  \
+  do {                                                           \
+    cudaError_t e__ = cudaGetLastError();                        \
+    if (e__ != cudaSuccess) return ::dlpm::cuda_fail(e__, what); \
+  } while (0)
+
+#define DLPM_REQUIRE(cond, msg)          \
+  do {                                   \
+    if (!(cond)) {                       \
+      ::dlpm::set_error("%s", msg);      \
+      return DLPM_ERR_ARG;               \
+    }                                    \
+  } while (0)
+
+constexpr int kNumSMs = 148;  // B200
+
+inline int grid_for(int64_t work_items, int threads, int max_waves = 8) {
+  int64_t blocks = (work_items + threads - 1) / threads;
+  const int64_t cap = (int64_t)kNumSMs * max_waves * (2048 / threads);
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// streaming 128-bit accesses (data touched once: bypass L1 allocation)
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_stream(float4* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ float4 ld_rw(const float4* p) {  // plain (the location is rewritten by the same thread)
+  return *p;
+}
+
+__device__ __forceinline__ float4 bf16x4_to_float4(uint2 raw) {
+  const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
+  const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
+  const float2 a = __bfloat1622float2(lo), b = __bfloat1622float2(hi);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+}  // namespace dlpm

@@ -1,0 +1,632 @@
+// K1 (alpha-stable noise), K2 (Sigma scan), K3 (fused reverse steps) and the training-forward
+// helpers.  All of these are HBM-bound streaming kernels: 128-bit accesses, grid = multiples of the
+// SM count, noise generated in registers so the x_t state makes exactly one read + one write per step.
+//
+// Reference behaviour being replaced (file:line relative to the reference tree):
+//   bem/datasets/Distributions.py:33-73        gen_skewed_levy / gen_sas (host scipy + H2D + 3 eager kernels)
+//   dlpm/methods/dlpm.py:226-239               sample_A / compute_Sigmas (T host draws, 4T launches, (T,B,C,H,W) tables)
+//   dlpm/methods/dlpm.py:250-297               Gamma_t, posterior mean/variance, DLIM
+//   dlpm/methods/GenerativeLevyProcess.py:186-239   clip_denoised path, p_sample
+//   dlpm/methods/LIM/functions/sampler.py:81-181    LIM ODE / SDE updates
+// Arithmetic uses explicit round-to-nearest intrinsics in the reference's evaluation order (no FMA
+// contraction), so with injected noise the results are bit-identical to the reference's fp32 CPU path.
+#include <cstdarg>
+
+#include "common.cuh"
+#include "rng.cuh"
+
+namespace dlpm {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static StableParams make_params(float alpha) {
+  StableParams p;
+  p.gaussian = (alpha == 2.0f);
+  const double ap = (double)alpha / 2.0;
+  p.ap = (float)ap;
+  p.inv_ap = (float)(1.0 / ap);
+  p.r = (float)((1.0 - ap) / ap);
+  p.one_m_ap = (float)(1.0 - ap);
+  return p;
+}
+
+__device__ __forceinline__ float clamp_A(float a, float clamp_a) { return clamp_a >= 0.f ? fminf(fmaxf(a, 0.f), clamp_a) : a; }
+__device__ __forceinline__ float clamp_sym(float v, float c) { return c >= 0.f ? fminf(fmaxf(v, -c), c) : v; }
+__device__ __forceinline__ float sel4(const float4& v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w)); }
+
+// per-sample subordinator (one draw per sample; position 0 of the sample's A stream)
+__device__ __forceinline__ float sample_A(const Philox& ph, const StableParams& sp, uint32_t stream, uint64_t offset,
+                                          uint64_t sample) {
+  const uint4 r = philox_at(ph, stream, offset, sample, 0u);
+  return stable_A(sp, r.x, r.y);
+}
+// four per-element subordinators for quad `pos` of a sample (two Philox blocks: positions 2pos, 2pos+1)
+__device__ __forceinline__ float4 element_A4(const Philox& ph, const StableParams& sp, uint32_t stream, uint64_t offset,
+                                             uint64_t sample, uint32_t pos) {
+  const uint4 r0 = philox_at(ph, stream, offset, sample, 2u * pos + 1u);  // +1: position 0 is the per-sample draw
+  const uint4 r1 = philox_at(ph, stream, offset, sample, 2u * pos + 2u);
+  return make_float4(stable_A(sp, r0.x, r0.y), stable_A(sp, r0.z, r0.w), stable_A(sp, r1.x, r1.y),
+                     stable_A(sp, r1.z, r1.w));
+}
+__device__ __forceinline__ float4 normal_quad(const Philox& ph, uint32_t stream, uint64_t offset, uint64_t sample,
+                                              uint32_t pos) {
+  return normal4(philox_at(ph, stream, offset, sample, pos));
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1a  stable_A
+// ------------------------------------------------------------------------------------------------
+template <bool VEC>
+__global__ void __launch_bounds__(256) k_stable_A(float* __restrict__ out, int64_t n_outer, int64_t inner, int mode,
+                                                  StableParams sp, float clamp_a, uint64_t seed, uint64_t offset,
+                                                  int64_t sample_base) {
+  const Philox ph(seed);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  if (mode == DLPM_A_COMPACT) {
+    for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < n_outer; o += stride)
+      out[o] = clamp_A(sample_A(ph, sp, STREAM_A, offset, (uint64_t)(o + sample_base)), clamp_a);
+    return;
+  }
+  if (VEC) {
+    const int64_t qpr = inner >> 2, nq = n_outer * qpr;  // quads per row
+    int64_t last_o = -1;
+    float a_iso = 0.f;
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nq; q += stride) {
+      const int64_t o = q / qpr;
+      const uint32_t pos = (uint32_t)(q - o * qpr);
+      float4 v;
+      if (mode == DLPM_A_ISOTROPIC) {
+        if (o != last_o) { a_iso = clamp_A(sample_A(ph, sp, STREAM_A, offset, (uint64_t)(o + sample_base)), clamp_a); last_o = o; }
+        v = make_float4(a_iso, a_iso, a_iso, a_iso);
+      } else {
+        v = element_A4(ph, sp, STREAM_A, offset, (uint64_t)(o + sample_base), pos);
+        v.x = clamp_A(v.x, clamp_a); v.y = clamp_A(v.y, clamp_a); v.z = clamp_A(v.z, clamp_a); v.w = clamp_A(v.w, clamp_a);
+      }
+      st_stream(reinterpret_cast<float4*>(out) + q, v);
+    }
+  } else {
+    const int64_t n = n_outer * inner;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += stride) {
+      const int64_t o = e / inner;
+      const int64_t i = e - o * inner;
+      float a;
+      if (mode == DLPM_A_ISOTROPIC) a = sample_A(ph, sp, STREAM_A, offset, (uint64_t)(o + sample_base));
+      else a = sel4(element_A4(ph, sp, STREAM_A, offset, (uint64_t)(o + sample_base), (uint32_t)(i >> 2)), (int)(i & 3));
+      out[e] = clamp_A(a, clamp_a);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1b  sas  (and plain normal fill)
+// ------------------------------------------------------------------------------------------------
+// A_MODE: 0 = none (plain normal), 1 = in-kernel isotropic, 2 = in-kernel per element, 3 = A_in compact, 4 = A_in full
+template <bool VEC, int A_MODE>
+__global__ void __launch_bounds__(256) k_sas(float* __restrict__ out, const float* __restrict__ A_in, int64_t n_outer,
+                                             int64_t inner, StableParams sp, float clamp_eps, float scale,
+                                             uint32_t g_stream, uint64_t seed, uint64_t offset, int64_t sample_base) {
+  const Philox ph(seed);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  if (VEC) {
+    const int64_t qpr = inner >> 2, nq = n_outer * qpr;
+    int64_t last_o = -1;
+    float sa_iso = 1.f;
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nq; q += stride) {
+      const int64_t o = q / qpr;
+      const uint32_t pos = (uint32_t)(q - o * qpr);
+      const uint64_t sample = (uint64_t)(o + sample_base);
+      float4 g = normal_quad(ph, g_stream, offset, sample, pos);
+      if (A_MODE == 1 || A_MODE == 3) {
+        if (o != last_o) {
+          sa_iso = __fsqrt_rn(A_MODE == 1 ? sample_A(ph, sp, STREAM_EPS_A, offset, sample) : __ldg(A_in + o));
+          last_o = o;
+        }
+        g.x *= sa_iso; g.y *= sa_iso; g.z *= sa_iso; g.w *= sa_iso;
+      } else if (A_MODE == 2 || A_MODE == 4) {
+        const float4 a = (A_MODE == 2) ? element_A4(ph, sp, STREAM_EPS_A, offset, sample, pos)
+                                       : ld_stream(reinterpret_cast<const float4*>(A_in) + q);
+        g.x *= __fsqrt_rn(a.x); g.y *= __fsqrt_rn(a.y); g.z *= __fsqrt_rn(a.z); g.w *= __fsqrt_rn(a.w);
+      }
+      if (A_MODE != 0) {
+        g.x = scale * clamp_sym(g.x, clamp_eps); g.y = scale * clamp_sym(g.y, clamp_eps);
+        g.z = scale * clamp_sym(g.z, clamp_eps); g.w = scale * clamp_sym(g.w, clamp_eps);
+      }
+      st_stream(reinterpret_cast<float4*>(out) + q, g);
+    }
+  } else {
+    const int64_t n = n_outer * inner;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += stride) {
+      const int64_t o = e / inner;
+      const int64_t i = e - o * inner;
+      const uint64_t sample = (uint64_t)(o + sample_base);
+      const uint32_t pos = (uint32_t)(i >> 2);
+      float g = sel4(normal_quad(ph, g_stream, offset, sample, pos), (int)(i & 3));
+      if (A_MODE != 0) {
+        float a;
+        if (A_MODE == 1) a = sample_A(ph, sp, STREAM_EPS_A, offset, sample);
+        else if (A_MODE == 3) a = A_in[o];
+        else if (A_MODE == 2) a = sel4(element_A4(ph, sp, STREAM_EPS_A, offset, sample, pos), (int)(i & 3));
+        else a = A_in[e];
+        g = scale * clamp_sym(g * __fsqrt_rn(a), clamp_eps);
+      }
+      out[e] = g;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2  Sigma scan: one thread per chain, T sequential steps, coalesced (T, n) stores.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_sigma_scan(float* __restrict__ Sigma, const float* __restrict__ A_in,
+                                                    float* __restrict__ A_out, const float* __restrict__ sched, int T,
+                                                    int64_t n, int64_t inner, int per_element, StableParams sp,
+                                                    float clamp_a, uint64_t seed, uint64_t offset, int64_t sample_base) {
+  const Philox ph(seed);
+  const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  uint64_t sample;
+  uint32_t pos = 0;
+  int lane = 0;
+  if (per_element) {
+    const int64_t o = c / inner, i = c - o * inner;
+    sample = (uint64_t)(o + sample_base);
+    pos = (uint32_t)(i >> 2);
+    lane = (int)(i & 3);
+  } else {
+    sample = (uint64_t)(c + sample_base);
+  }
+  float S = 0.f;
+  for (int t = 0; t < T; ++t) {
+    const float4 row = __ldg(reinterpret_cast<const float4*>(sched) + t);  // (g, bg, s, bs)
+    float a;
+    if (A_in) a = A_in[(int64_t)t * n + c];
+    else if (per_element) a = clamp_A(sel4(element_A4(ph, sp, STREAM_A, offset + (uint64_t)t, sample, pos), lane), clamp_a);
+    else a = clamp_A(sample_A(ph, sp, STREAM_A, offset + (uint64_t)t, sample), clamp_a);
+    // dlpm.py:234,238  s[t]**2 * A_t + g[t]**2 * Sigmas[-1]
+    const float sa = __fmul_rn(__fmul_rn(row.z, row.z), a);
+    S = (t == 0) ? sa : __fadd_rn(sa, __fmul_rn(__fmul_rn(row.x, row.x), S));
+    Sigma[(int64_t)t * n + c] = S;
+    if (A_out) A_out[(int64_t)t * n + c] = a;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3  fused reverse steps
+// ------------------------------------------------------------------------------------------------
+struct StepCoef {  // per-chain scalars of one DLPM step
+  float c1;        // bs_t * Gamma_t
+  float g;         // gamma_t
+  float sd;        // 1[t != 1] * sqrt(Gamma_t * Sigma_{t-1})
+};
+__device__ __forceinline__ StepCoef dlpm_coef(float S1, float St, const float4& row, int t) {
+  // dlpm.py:250-254,272-278
+  const float Gamma = __fsub_rn(1.0f, __fdiv_rn(__fmul_rn(__fmul_rn(row.x, row.x), S1), St));
+  StepCoef c;
+  c.c1 = __fmul_rn(row.w, Gamma);
+  c.g = row.x;
+  c.sd = (t == 1) ? 0.f : __fsqrt_rn(__fmul_rn(Gamma, S1));
+  return c;
+}
+__device__ __forceinline__ float clip_eps1(float x, float e, const float4& row) {
+  // GenerativeLevyProcess.py:186-207 with dlpm.py:191-202
+  const float xs = fminf(fmaxf(__fdiv_rn(__fsub_rn(x, __fmul_rn(e, row.w)), row.y), -1.f), 1.f);
+  return __fdiv_rn(__fsub_rn(x, __fmul_rn(xs, row.y)), row.w);
+}
+__device__ __forceinline__ float dlpm_update1(float x, float e, float z, const StepCoef& c) {
+  const float mean = __fdiv_rn(__fsub_rn(x, __fmul_rn(c.c1, e)), c.g);
+  return __fadd_rn(mean, __fmul_rn(c.sd, z));
+}
+
+template <bool VEC, bool EPS_BF16>
+__device__ __forceinline__ float4 load_eps4(const void* eps, int64_t q) {
+  if (EPS_BF16) return bf16x4_to_float4(__ldg(reinterpret_cast<const uint2*>(eps) + q));
+  return ld_stream(reinterpret_cast<const float4*>(eps) + q);
+}
+template <bool EPS_BF16>
+__device__ __forceinline__ float load_eps1(const void* eps, int64_t e) {
+  if (EPS_BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(eps)[e]);
+  return reinterpret_cast<const float*>(eps)[e];
+}
+
+// MODE 0: DLPM stochastic, MODE 1: DLIM eta=0
+template <bool VEC, bool EPS_BF16, int MODE>
+__global__ void __launch_bounds__(256) k_reverse_step(float* __restrict__ x, const void* __restrict__ eps,
+                                                      const float* __restrict__ Sigma, const float* __restrict__ sched,
+                                                      int t_imm, const int* __restrict__ t_dev, int T, int64_t B,
+                                                      int64_t D, int flags, const float* __restrict__ z,
+                                                      uint64_t seed, uint64_t offset, int64_t sample_base,
+                                                      float* __restrict__ hist) {
+  const int t = t_dev ? *t_dev : t_imm;
+  if (t < 1 || t >= T) return;
+  const Philox ph(seed);
+  const float4 row = __ldg(reinterpret_cast<const float4*>(sched) + t);
+  const float bs_prev = __ldg(sched + 4 * (t - 1) + 3);
+  const bool clip = flags & DLPM_STEP_CLIP_DENOISED;
+  const bool sig_full = flags & DLPM_STEP_SIGMA_FULL;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const uint64_t off_t = offset + (uint64_t)t;
+  if (VEC) {
+    const int64_t qpr = D >> 2, nq = B * qpr;
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nq; q += stride) {
+      const int64_t b = q / qpr;
+      const uint32_t pos = (uint32_t)(q - b * qpr);
+      float4 xv = ld_rw(reinterpret_cast<const float4*>(x) + q);
+      float4 ev = load_eps4<VEC, EPS_BF16>(eps, q);
+      if (clip) {
+        ev.x = clip_eps1(xv.x, ev.x, row); ev.y = clip_eps1(xv.y, ev.y, row);
+        ev.z = clip_eps1(xv.z, ev.z, row); ev.w = clip_eps1(xv.w, ev.w, row);
+      }
+      float4 o;
+      if (MODE == 1) {  // dlpm.py:285-287
+        o.x = __fadd_rn(__fdiv_rn(__fsub_rn(xv.x, __fmul_rn(row.w, ev.x)), row.x), __fmul_rn(bs_prev, ev.x));
+        o.y = __fadd_rn(__fdiv_rn(__fsub_rn(xv.y, __fmul_rn(row.w, ev.y)), row.x), __fmul_rn(bs_prev, ev.y));
+        o.z = __fadd_rn(__fdiv_rn(__fsub_rn(xv.z, __fmul_rn(row.w, ev.z)), row.x), __fmul_rn(bs_prev, ev.z));
+        o.w = __fadd_rn(__fdiv_rn(__fsub_rn(xv.w, __fmul_rn(row.w, ev.w)), row.x), __fmul_rn(bs_prev, ev.w));
+      } else {
+        const float4 zv = z ? ld_stream(reinterpret_cast<const float4*>(z) + q)
+                            : normal_quad(ph, STREAM_Z, off_t, (uint64_t)(b + sample_base), pos);
+        if (!sig_full) {
+          const StepCoef c = dlpm_coef(__ldg(Sigma + (int64_t)(t - 1) * B + b), __ldg(Sigma + (int64_t)t * B + b), row, t);
+          o.x = dlpm_update1(xv.x, ev.x, zv.x, c); o.y = dlpm_update1(xv.y, ev.y, zv.y, c);
+          o.z = dlpm_update1(xv.z, ev.z, zv.z, c); o.w = dlpm_update1(xv.w, ev.w, zv.w, c);
+        } else {
+          const float4 s1 = ld_stream(reinterpret_cast<const float4*>(Sigma + (int64_t)(t - 1) * B * D) + q);
+          const float4 st = ld_stream(reinterpret_cast<const float4*>(Sigma + (int64_t)t * B * D) + q);
+          o.x = dlpm_update1(xv.x, ev.x, zv.x, dlpm_coef(s1.x, st.x, row, t));
+          o.y = dlpm_update1(xv.y, ev.y, zv.y, dlpm_coef(s1.y, st.y, row, t));
+          o.z = dlpm_update1(xv.z, ev.z, zv.z, dlpm_coef(s1.z, st.z, row, t));
+          o.w = dlpm_update1(xv.w, ev.w, zv.w, dlpm_coef(s1.w, st.w, row, t));
+        }
+      }
+      reinterpret_cast<float4*>(x)[q] = o;
+      if (hist) st_stream(reinterpret_cast<float4*>(hist) + q, o);
+    }
+  } else {
+    const int64_t n = B * D;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += stride) {
+      const int64_t b = e / D, i = e - b * D;
+      const float xv = x[e];
+      float ev = load_eps1<EPS_BF16>(eps, e);
+      if (clip) ev = clip_eps1(xv, ev, row);
+      float o;
+      if (MODE == 1) {
+        o = __fadd_rn(__fdiv_rn(__fsub_rn(xv, __fmul_rn(row.w, ev)), row.x), __fmul_rn(bs_prev, ev));
+      } else {
+        const float zv = z ? z[e] : sel4(normal_quad(ph, STREAM_Z, off_t, (uint64_t)(b + sample_base), (uint32_t)(i >> 2)), (int)(i & 3));
+        const float S1 = sig_full ? Sigma[(int64_t)(t - 1) * n + e] : Sigma[(int64_t)(t - 1) * B + b];
+        const float St = sig_full ? Sigma[(int64_t)t * n + e] : Sigma[(int64_t)t * B + b];
+        o = dlpm_update1(xv, ev, zv, dlpm_coef(S1, St, row, t));
+      }
+      x[e] = o;
+      if (hist) hist[e] = o;
+    }
+  }
+}
+
+// LIM step (sampler.py:81-181): x <- a x + c_score (sc * out) [+ c_noise e_L]
+template <bool VEC, bool EPS_BF16>
+__global__ void __launch_bounds__(256) k_lim_step(float* __restrict__ x, const void* __restrict__ mo,
+                                                  const float* __restrict__ coef, int step_imm,
+                                                  const int* __restrict__ step_dev, int64_t B, int64_t D, int ode,
+                                                  int isotropic, StableParams sp, float clamp_eps,
+                                                  const float* __restrict__ e_L, uint64_t seed, uint64_t offset,
+                                                  int64_t sample_base, float* __restrict__ hist) {
+  const int step = step_dev ? *step_dev : step_imm;
+  const Philox ph(seed);
+  const float4 cf = __ldg(reinterpret_cast<const float4*>(coef) + step);  // (score_scale, a, c_score, c_noise)
+  const uint64_t off_s = offset + (uint64_t)step;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  if (VEC) {
+    const int64_t qpr = D >> 2, nq = B * qpr;
+    int64_t last_b = -1;
+    float sa = 1.f;
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nq; q += stride) {
+      const int64_t b = q / qpr;
+      const uint32_t pos = (uint32_t)(q - b * qpr);
+      const uint64_t sample = (uint64_t)(b + sample_base);
+      const float4 xv = ld_rw(reinterpret_cast<const float4*>(x) + q);
+      const float4 mv = load_eps4<VEC, EPS_BF16>(mo, q);
+      float4 o;
+      o.x = __fadd_rn(__fmul_rn(cf.y, xv.x), __fmul_rn(cf.z, __fmul_rn(mv.x, cf.x)));
+      o.y = __fadd_rn(__fmul_rn(cf.y, xv.y), __fmul_rn(cf.z, __fmul_rn(mv.y, cf.x)));
+      o.z = __fadd_rn(__fmul_rn(cf.y, xv.z), __fmul_rn(cf.z, __fmul_rn(mv.z, cf.x)));
+      o.w = __fadd_rn(__fmul_rn(cf.y, xv.w), __fmul_rn(cf.z, __fmul_rn(mv.w, cf.x)));
+      if (!ode) {
+        float4 n4;
+        if (e_L) {
+          n4 = ld_stream(reinterpret_cast<const float4*>(e_L) + q);
+        } else {
+          n4 = normal_quad(ph, STREAM_G, off_s, sample, pos);
+          if (isotropic) {
+            if (b != last_b) { sa = __fsqrt_rn(sample_A(ph, sp, STREAM_EPS_A, off_s, sample)); last_b = b; }
+            n4.x *= sa; n4.y *= sa; n4.z *= sa; n4.w *= sa;
+          } else {
+            const float4 a = element_A4(ph, sp, STREAM_EPS_A, off_s, sample, pos);
+            n4.x *= __fsqrt_rn(a.x); n4.y *= __fsqrt_rn(a.y); n4.z *= __fsqrt_rn(a.z); n4.w *= __fsqrt_rn(a.w);
+          }
+          n4.x = clamp_sym(n4.x, clamp_eps); n4.y = clamp_sym(n4.y, clamp_eps);
+          n4.z = clamp_sym(n4.z, clamp_eps); n4.w = clamp_sym(n4.w, clamp_eps);
+        }
+        o.x = __fadd_rn(o.x, __fmul_rn(cf.w, n4.x)); o.y = __fadd_rn(o.y, __fmul_rn(cf.w, n4.y));
+        o.z = __fadd_rn(o.z, __fmul_rn(cf.w, n4.z)); o.w = __fadd_rn(o.w, __fmul_rn(cf.w, n4.w));
+      }
+      reinterpret_cast<float4*>(x)[q] = o;
+      if (hist) st_stream(reinterpret_cast<float4*>(hist) + q, o);
+    }
+  } else {
+    const int64_t n = B * D;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += stride) {
+      const int64_t b = e / D, i = e - b * D;
+      const uint64_t sample = (uint64_t)(b + sample_base);
+      const float mv = load_eps1<EPS_BF16>(mo, e);
+      float o = __fadd_rn(__fmul_rn(cf.y, x[e]), __fmul_rn(cf.z, __fmul_rn(mv, cf.x)));
+      if (!ode) {
+        float nz;
+        if (e_L) {
+          nz = e_L[e];
+        } else {
+          const uint32_t pos = (uint32_t)(i >> 2);
+          nz = sel4(normal_quad(ph, STREAM_G, off_s, sample, pos), (int)(i & 3));
+          const float a = isotropic ? sample_A(ph, sp, STREAM_EPS_A, off_s, sample)
+                                    : sel4(element_A4(ph, sp, STREAM_EPS_A, off_s, sample, pos), (int)(i & 3));
+          nz = clamp_sym(nz * __fsqrt_rn(a), clamp_eps);
+        }
+        o = __fadd_rn(o, __fmul_rn(cf.w, nz));
+      }
+      x[e] = o;
+      if (hist) hist[e] = o;
+    }
+  }
+}
+
+__global__ void k_advance(int* t, int delta) { *t += delta; }
+
+// ------------------------------------------------------------------------------------------------
+// training forward elements (dlpm.py:384-401)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_training_elements(float* __restrict__ x_t, float* __restrict__ eps_t,
+                                                           const float* __restrict__ x0, const int64_t* __restrict__ t,
+                                                           const float* __restrict__ A, const float* __restrict__ z,
+                                                           const float* __restrict__ sched, int T, int64_t B, int64_t D,
+                                                           StableParams sp, float clamp_a, uint64_t seed,
+                                                           uint64_t offset, int64_t sample_base) {
+  const Philox ph(seed);
+  const int64_t n = B * D, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += stride) {
+    const int64_t b = e / D, i = e - b * D;
+    const uint64_t sample = (uint64_t)(b + sample_base);
+    int64_t tb = t[b];
+    tb = tb < 0 ? 0 : (tb >= T ? T - 1 : tb);
+    const float4 row = __ldg(reinterpret_cast<const float4*>(sched) + tb);
+    const float a = A ? A[b] : clamp_A(sample_A(ph, sp, STREAM_A, offset, sample), clamp_a);
+    const float zz = z ? z[e] : sel4(normal_quad(ph, STREAM_Z, offset, sample, (uint32_t)(i >> 2)), (int)(i & 3));
+    const float Sig = __fmul_rn(a, __fmul_rn(row.w, row.w));        // a_t * bs[t]**2
+    const float xt = __fadd_rn(__fmul_rn(row.y, x0[e]), __fmul_rn(__fsqrt_rn(Sig), zz));
+    x_t[e] = xt;
+    eps_t[e] = __fdiv_rn(__fsub_rn(xt, __fmul_rn(x0[e], row.y)), row.w);
+  }
+}
+
+template <bool PRED_BF16>
+__global__ void __launch_bounds__(256) k_loss_terms(float* __restrict__ out, const void* __restrict__ pred,
+                                                    const float* __restrict__ target, int64_t D, float lploss) {
+  const int64_t b = blockIdx.x;
+  float acc = 0.f;
+  for (int64_t i = threadIdx.x; i < D; i += blockDim.x) {
+    const float d = load_eps1<PRED_BF16>(pred, b * D + i) - target[b * D + i];
+    if (lploss == 1.0f) { const float ad = fabsf(d); acc += ad < 1.f ? 0.5f * d * d : ad - 0.5f; }
+    else acc += d * d;
+  }
+  __shared__ float red[8];
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+    const float m = tot / (float)D;
+    out[b] = (lploss == 2.0f) ? sqrtf(m) : m;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_postprocess(float* __restrict__ out, const float* __restrict__ x, int64_t n,
+                                                     float clamp, int is_image) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += stride) {
+    float v = fminf(fmaxf(x[e], -clamp), clamp);
+    if (is_image) v = __fdiv_rn(__fadd_rn(v, 1.0f), 2.0f);
+    out[e] = v;
+  }
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace dlpm
+
+using namespace dlpm;
+
+// C linkage comes from the declarations in include/dlpm_b200.h
+
+int dlpm_b200_abi_version(void) { return DLPM_B200_ABI_VERSION; }
+const char* dlpm_b200_last_error(void) { return g_err; }
+
+int dlpm_b200_stable_A(float* out, int64_t n_outer, int64_t inner, int mode, float alpha, float clamp_a, uint64_t seed,
+                       uint64_t offset, int64_t sample_base, void* stream) {
+  DLPM_REQUIRE(out != nullptr || n_outer == 0, "stable_A: out is NULL");
+  DLPM_REQUIRE(alpha > 0.f && alpha <= 2.f, "Wrong value of alpha for skewed levy r.v generation");
+  DLPM_REQUIRE(mode >= 0 && mode <= 2 && n_outer >= 0 && inner >= 1, "stable_A: bad mode/size");
+  if (n_outer == 0) return DLPM_OK;
+  const StableParams sp = make_params(alpha);
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool vec = mode != DLPM_A_COMPACT && (inner % 4 == 0) && aligned16(out);
+  const int64_t items = mode == DLPM_A_COMPACT ? n_outer : (vec ? n_outer * inner / 4 : n_outer * inner);
+  const int grid = grid_for(items, 256);
+  if (vec) k_stable_A<true><<<grid, 256, 0, s>>>(out, n_outer, inner, mode, sp, clamp_a, seed, offset, sample_base);
+  else k_stable_A<false><<<grid, 256, 0, s>>>(out, n_outer, inner, mode, sp, clamp_a, seed, offset, sample_base);
+  DLPM_CHECK_LAUNCH("stable_A");
+  return DLPM_OK;
+}
+
+template <int A_MODE>
+static void launch_sas(bool vec, int grid, cudaStream_t s, float* out, const float* A_in, int64_t n_outer, int64_t inner,
+                       const StableParams& sp, float clamp_eps, float scale, uint32_t g_stream, uint64_t seed,
+                       uint64_t offset, int64_t sample_base) {
+  if (vec) k_sas<true, A_MODE><<<grid, 256, 0, s>>>(out, A_in, n_outer, inner, sp, clamp_eps, scale, g_stream, seed, offset, sample_base);
+  else k_sas<false, A_MODE><<<grid, 256, 0, s>>>(out, A_in, n_outer, inner, sp, clamp_eps, scale, g_stream, seed, offset, sample_base);
+}
+
+int dlpm_b200_sas(float* out, const float* A_in, int64_t n_outer, int64_t inner, int isotropic, float alpha,
+                  float clamp_eps, float scale, uint64_t seed, uint64_t offset, int64_t sample_base, void* stream) {
+  DLPM_REQUIRE(out != nullptr || n_outer == 0, "sas: out is NULL");
+  DLPM_REQUIRE(alpha > 0.f && alpha <= 2.f, "Wrong value of alpha for skewed levy r.v generation");
+  DLPM_REQUIRE(n_outer >= 0 && inner >= 1, "sas: bad size");
+  if (n_outer == 0) return DLPM_OK;
+  const StableParams sp = make_params(alpha);
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool vec = (inner % 4 == 0) && aligned16(out) && (A_in == nullptr || isotropic || aligned16(A_in));
+  const int grid = grid_for(vec ? n_outer * inner / 4 : n_outer * inner, 256);
+  const int mode = A_in ? (isotropic ? 3 : 4) : (isotropic ? 1 : 2);
+  switch (mode) {
+    case 1: launch_sas<1>(vec, grid, s, out, A_in, n_outer, inner, sp, clamp_eps, scale, STREAM_G, seed, offset, sample_base); break;
+    case 2: launch_sas<2>(vec, grid, s, out, A_in, n_outer, inner, sp, clamp_eps, scale, STREAM_G, seed, offset, sample_base); break;
+    case 3: launch_sas<3>(vec, grid, s, out, A_in, n_outer, inner, sp, clamp_eps, scale, STREAM_G, seed, offset, sample_base); break;
+    default: launch_sas<4>(vec, grid, s, out, A_in, n_outer, inner, sp, clamp_eps, scale, STREAM_G, seed, offset, sample_base); break;
+  }
+  DLPM_CHECK_LAUNCH("sas");
+  return DLPM_OK;
+}
+
+int dlpm_b200_normal(float* out, int64_t n_outer, int64_t inner, uint64_t seed, uint64_t offset, int64_t sample_base,
+                     void* stream) {
+  DLPM_REQUIRE(out != nullptr || n_outer == 0, "normal: out is NULL");
+  DLPM_REQUIRE(n_outer >= 0 && inner >= 1, "normal: bad size");
+  if (n_outer == 0) return DLPM_OK;
+  StableParams sp = make_params(2.0f);
+  const bool vec = (inner % 4 == 0) && aligned16(out);
+  const int grid = grid_for(vec ? n_outer * inner / 4 : n_outer * inner, 256);
+  launch_sas<0>(vec, grid, (cudaStream_t)stream, out, nullptr, n_outer, inner, sp, -1.f, 1.f, STREAM_Z, seed, offset, sample_base);
+  DLPM_CHECK_LAUNCH("normal");
+  return DLPM_OK;
+}
+
+int dlpm_b200_sigma_scan(float* Sigma, const float* A_in, float* A_out, const float* sched, int T, int64_t n,
+                         int64_t inner, int per_element, float alpha, float clamp_a, uint64_t seed, uint64_t offset,
+                         int64_t sample_base, void* stream) {
+  DLPM_REQUIRE(Sigma && sched && T >= 1 && n >= 0, "sigma_scan: bad arguments");
+  DLPM_REQUIRE(alpha > 0.f && alpha <= 2.f, "Wrong value of alpha for skewed levy r.v generation");
+  DLPM_REQUIRE(!per_element || inner >= 1, "sigma_scan: inner must be >= 1");
+  if (n == 0) return DLPM_OK;
+  const StableParams sp = make_params(alpha);
+  const int grid = (int)((n + 127) / 128);
+  k_sigma_scan<<<grid, 128, 0, (cudaStream_t)stream>>>(Sigma, A_in, A_out, sched, T, n, inner < 1 ? 1 : inner, per_element, sp,
+                                                       clamp_a, seed, offset, sample_base);
+  DLPM_CHECK_LAUNCH("sigma_scan");
+  return DLPM_OK;
+}
+
+template <int MODE>
+static int launch_step(float* x, const void* eps, const float* Sigma, const float* sched, int t, const int* t_dev, int T,
+                       int64_t B, int64_t D, int flags, const float* z, uint64_t seed, uint64_t offset, int64_t sample_base,
+                       float* hist, void* stream) {
+  const bool bf16 = flags & DLPM_STEP_EPS_BF16;
+  const bool vec = (D % 4 == 0) && aligned16(x) && (reinterpret_cast<uintptr_t>(eps) % (bf16 ? 8 : 16) == 0) &&
+                   (!z || aligned16(z)) && (!hist || aligned16(hist)) &&
+                   (!(flags & DLPM_STEP_SIGMA_FULL) || (aligned16(Sigma) && (B * D) % 4 == 0));
+  const int grid = grid_for(vec ? B * D / 4 : B * D, 256);
+  cudaStream_t s = (cudaStream_t)stream;
+#define L(V, H) k_reverse_step<V, H, MODE><<<grid, 256, 0, s>>>(x, eps, Sigma, sched, t, t_dev, T, B, D, flags, z, seed, offset, sample_base, hist)
+  if (vec) { if (bf16) L(true, true); else L(true, false); }
+  else { if (bf16) L(false, true); else L(false, false); }
+#undef L
+  DLPM_CHECK_LAUNCH("reverse_step");
+  return DLPM_OK;
+}
+
+int dlpm_b200_reverse_step(float* x, const void* eps, const float* Sigma, const float* sched, int t, const int* t_dev,
+                           int T, int64_t B, int64_t D, int flags, const float* z, uint64_t seed, uint64_t offset,
+                           int64_t sample_base, float* hist_out, void* stream) {
+  DLPM_REQUIRE(x && eps && Sigma && sched, "reverse_step: NULL tensor");
+  DLPM_REQUIRE(T >= 2 && B >= 0 && D >= 1, "reverse_step: bad sizes");
+  DLPM_REQUIRE(t_dev || (t >= 1 && t < T), "reverse_step: t out of range [1, T)");
+  if (B == 0) return DLPM_OK;
+  return launch_step<0>(x, eps, Sigma, sched, t, t_dev, T, B, D, flags, z, seed, offset, sample_base, hist_out, stream);
+}
+
+int dlpm_b200_dlim_step(float* x, const void* eps, const float* sched, int t, const int* t_dev, int T, int64_t B,
+                        int64_t D, int flags, float* hist_out, void* stream) {
+  DLPM_REQUIRE(x && eps && sched, "dlim_step: NULL tensor");
+  DLPM_REQUIRE(T >= 2 && B >= 0 && D >= 1, "dlim_step: bad sizes");
+  DLPM_REQUIRE(t_dev || (t >= 1 && t < T), "dlim_step: t out of range [1, T)");
+  if (B == 0) return DLPM_OK;
+  return launch_step<1>(x, eps, sched /*unused Sigma*/, sched, t, t_dev, T, B, D, flags & ~DLPM_STEP_SIGMA_FULL, nullptr, 0, 0, 0,
+                        hist_out, stream);
+}
+
+int dlpm_b200_lim_step(float* x, const void* model_out, const float* coef, int step, const int* step_dev, int64_t B,
+                       int64_t D, int flags, int ode, int isotropic, float alpha, float clamp_eps, const float* e_L,
+                       uint64_t seed, uint64_t offset, int64_t sample_base, float* hist_out, void* stream) {
+  DLPM_REQUIRE(x && model_out && coef, "lim_step: NULL tensor");
+  DLPM_REQUIRE(B >= 0 && D >= 1 && (step_dev || step >= 0), "lim_step: bad sizes");
+  DLPM_REQUIRE(alpha > 0.f && alpha < 2.f, "lim_step: heavy-tailed branch only (0 < alpha < 2)");
+  if (B == 0) return DLPM_OK;
+  const StableParams sp = make_params(alpha);
+  const bool bf16 = flags & DLPM_STEP_EPS_BF16;
+  const bool vec = (D % 4 == 0) && aligned16(x) && (reinterpret_cast<uintptr_t>(model_out) % (bf16 ? 8 : 16) == 0) &&
+                   (!e_L || aligned16(e_L)) && (!hist_out || aligned16(hist_out));
+  const int grid = grid_for(vec ? B * D / 4 : B * D, 256);
+  cudaStream_t s = (cudaStream_t)stream;
+#define L(V, H) k_lim_step<V, H><<<grid, 256, 0, s>>>(x, model_out, coef, step, step_dev, B, D, ode, isotropic, sp, clamp_eps, e_L, seed, offset, sample_base, hist_out)
+  if (vec) { if (bf16) L(true, true); else L(true, false); }
+  else { if (bf16) L(false, true); else L(false, false); }
+#undef L
+  DLPM_CHECK_LAUNCH("lim_step");
+  return DLPM_OK;
+}
+
+int dlpm_b200_advance_counter(int* t_dev, int delta, void* stream) {
+  DLPM_REQUIRE(t_dev, "advance_counter: NULL");
+  k_advance<<<1, 1, 0, (cudaStream_t)stream>>>(t_dev, delta);
+  DLPM_CHECK_LAUNCH("advance_counter");
+  return DLPM_OK;
+}
+
+int dlpm_b200_training_elements(float* x_t, float* eps_t, const float* x0, const int64_t* t, const float* A,
+                                const float* z, const float* sched, int T, int64_t B, int64_t D, float alpha,
+                                float clamp_a, uint64_t seed, uint64_t offset, int64_t sample_base, void* stream) {
+  DLPM_REQUIRE(x_t && eps_t && x0 && t && sched, "training_elements: NULL tensor");
+  DLPM_REQUIRE(alpha > 0.f && alpha <= 2.f, "Wrong value of alpha for skewed levy r.v generation");
+  DLPM_REQUIRE(T >= 1 && B >= 0 && D >= 1, "training_elements: bad sizes");
+  if (B == 0) return DLPM_OK;
+  const StableParams sp = make_params(alpha);
+  k_training_elements<<<grid_for(B * D, 256), 256, 0, (cudaStream_t)stream>>>(x_t, eps_t, x0, t, A, z, sched, T, B, D, sp,
+                                                                              clamp_a, seed, offset, sample_base);
+  DLPM_CHECK_LAUNCH("training_elements");
+  return DLPM_OK;
+}
+
+int dlpm_b200_loss_terms(float* out, const void* pred, const float* target, int64_t B, int64_t D, float lploss, int flags,
+                         void* stream) {
+  DLPM_REQUIRE(out && pred && target, "loss_terms: NULL tensor");
+  DLPM_REQUIRE(lploss == 2.0f || lploss == 1.0f || lploss == -1.0f, "loss_terms: lploss must be 2, 1 or -1");
+  DLPM_REQUIRE(B >= 0 && D >= 1 && B < (1ll << 31), "loss_terms: bad sizes");
+  if (B == 0) return DLPM_OK;
+  if (flags & DLPM_STEP_EPS_BF16) k_loss_terms<true><<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>(out, pred, target, D, lploss);
+  else k_loss_terms<false><<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>(out, pred, target, D, lploss);
+  DLPM_CHECK_LAUNCH("loss_terms");
+  return DLPM_OK;
+}
+
+int dlpm_b200_postprocess(float* out, const float* x, int64_t n, float clamp, int is_image, void* stream) {
+  DLPM_REQUIRE((out && x) || n == 0, "postprocess: NULL tensor");
+  if (n <= 0) return DLPM_OK;
+  k_postprocess<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(out, x, n, clamp, is_image);
+  DLPM_CHECK_LAUNCH("postprocess");
+  return DLPM_OK;
+}
+

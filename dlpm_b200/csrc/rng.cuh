@@ -1,0 +1,119 @@
+// Counter-based RNG and alpha-stable transforms (device side).
+//
+// Replaces the reference's host-side scipy draw + H2D copy
+// (bem/datasets/Distributions.py:45-51: scipy.stats.levy_stable.rvs -> Chambers-Mallows-Stuck)
+// and torch.randn (Distributions.py:65, GenerativeLevyProcess.py:236) with a stateless
+// Philox4x32-10 generator: every variate is a pure function of
+//   (seed, stream tag, call offset, GLOBAL sample index, position inside the sample)
+// so results do not depend on grid shape or on how the batch is sharded over GPUs.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace dlpm {
+
+enum : uint32_t { STREAM_A = 0x0Au, STREAM_G = 0x06u, STREAM_Z = 0x5Au, STREAM_EPS_A = 0xEAu };
+
+struct Philox {
+  uint32_t k0, k1;
+  __device__ __forceinline__ Philox(uint64_t seed) : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)) {}
+
+  // 10 rounds, Salmon et al. 2011 constants.
+  __device__ __forceinline__ uint4 operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) const {
+    uint32_t a = k0, b = k1;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+      const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+      c0 = hi1 ^ c1 ^ a;
+      c1 = lo1;
+      c2 = hi0 ^ c3 ^ b;
+      c3 = lo0;
+      a += 0x9E3779B9u;
+      b += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+  }
+};
+
+// Counter layout shared by every kernel (documented in DESIGN.md):
+//   c0 = position inside the sample (in units of 4 variates), c1 = global sample index (low 32),
+//   c2 = call offset / diffusion step (low 32), c3 = stream tag | sample-index bits 32..39 << 8 | offset bits 32..47 << 16
+__device__ __forceinline__ uint4 philox_at(const Philox& ph, uint32_t stream, uint64_t offset, uint64_t sample,
+                                           uint32_t pos) {
+  const uint32_t c3 = stream | ((uint32_t)((sample >> 32) & 0xFFu) << 8) | ((uint32_t)((offset >> 32) & 0xFFFFu) << 16);
+  return ph(pos, (uint32_t)sample, (uint32_t)offset, c3);
+}
+
+// uniform in (0, 1] on the 32-bit lattice, centred: never 0 so log() is finite; small values are
+// exact, which is what the Gaussian tail (|z| up to 6.6) needs.
+__device__ __forceinline__ float u01(uint32_t x) { return fminf(((float)x + 0.5f) * 2.3283064365386963e-10f, 1.0f); }
+
+// uniform in [0, 1) with 23 bits, ALU-only (no I2F on the XU pipe).
+__device__ __forceinline__ float u01_fast(uint32_t x) { return __uint_as_float((x >> 9) | 0x3f800000u) - 1.0f; }
+
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// two N(0,1) from two 32-bit words (Box-Muller: lg2 + sqrt + sin + cos = 4 MUFU ops per pair).
+__device__ __forceinline__ float2 box_muller(uint32_t x, uint32_t y) {
+  const float r = sqrt_approx(-1.3862943611198906f * __log2f(u01(x)));  // sqrt(-2 ln u), ln u = ln2 * lg2 u
+  float s, c;
+  __sincosf(6.28318530717958647692f * u01_fast(y), &s, &c);
+  return make_float2(r * c, r * s);
+}
+
+__device__ __forceinline__ float4 normal4(uint4 r) {
+  const float2 a = box_muller(r.x, r.y), b = box_muller(r.z, r.w);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+// Exp(1) variate from 32 bits, accurate in the W -> 0 tail (which drives the heavy tail of A):
+// W = -log(1 - d), d in (0,1); series for small d, MUFU lg2 otherwise.
+__device__ __forceinline__ float exp1(uint32_t x) {
+  const float d = fminf(((float)x + 0.5f) * 2.3283064365386963e-10f, 0.99999994f);
+  const float series = d * (1.0f + d * (0.5f + d * (0.33333334f + d * 0.25f)));
+  const float full = -0.6931471805599453f * __log2f(1.0f - d);
+  return d < 0.03125f ? series : full;
+}
+
+// sin on (0, pi) with relative accuracy near 0 (MUFU.SIN only promises absolute error).
+__device__ __forceinline__ float sin_0_pi(float x) {
+  const float small = x * (1.0f - x * x * 0.16666667f);
+  return x < 0.0625f ? small : __sinf(x);
+}
+
+// Parameters of the Kanter / CMS transform for alpha' = alpha/2 (precomputed on the host).
+struct StableParams {
+  float ap;        // alpha' = alpha / 2
+  float inv_ap;    // 1 / alpha'
+  float r;         // (1 - alpha') / alpha'
+  float one_m_ap;  // 1 - alpha'
+  int gaussian;    // alpha == 2  ->  A == 2 exactly (Distributions.py:40-42)
+};
+
+// A = 2 K,  K = sin(a'U)/sin(U)^(1/a') * (sin((1-a')U)/W)^((1-a')/a'),  U ~ Unif(0,pi), W ~ Exp(1)
+// (identical pointwise to scipy's _rvs_Z1 'otherwise' branch with beta=1
+//  times scale 2 cos(pi alpha/4)^(2/alpha), see oracle/stable.py).
+// Evaluated in log2 space so that the heavy tail (U -> pi, W -> 0) neither overflows nor
+// loses precision: sin(U) is evaluated on the reflected argument min(u, 1-u) built from the
+// integer so that U -> pi keeps full relative precision.
+__device__ __forceinline__ float stable_A(const StableParams& p, uint32_t xu, uint32_t xw) {
+  if (p.gaussian) return 2.0f;
+  // u in (0,1) on the centred 32-bit lattice; v = min(u, 1-u) is built from the integer so both ends are exact.
+  const uint32_t xr = (xu & 0x80000000u) ? ~xu : xu;            // reflect the upper half
+  const float v = ((float)xr + 0.5f) * 2.3283064365386963e-10f;  // (0, 0.5]
+  const float u = (xu & 0x80000000u) ? 1.0f - v : v;
+  const float PI = 3.14159265358979323846f;
+  const float sinU = sin_0_pi(PI * v);  // sin(pi u) = sin(pi (1-u))
+  const float s1 = sin_0_pi(p.ap * PI * u);
+  const float s2 = sin_0_pi(p.one_m_ap * PI * u);
+  const float w = exp1(xw);
+  const float l2 = __log2f(s1) - p.inv_ap * __log2f(sinU) + p.r * (__log2f(s2) - __log2f(w));
+  return 2.0f * exp2f(l2);
+}
+
+}  // namespace dlpm

@@ -1,0 +1,184 @@
+"""CPU: pin the oracle (oracle/) against the golden vectors generated from the real reference
+(tests/golden/make_golden.py) and, when /root/reference is present, against the live reference."""
+import numpy as np
+import pytest
+import scipy.stats
+import torch
+
+from conftest import load_golden, sub
+from oracle import nets, process, ref_import, stable
+
+ALPHAS = (1.5, 1.7, 1.9)
+
+
+def test_cms_restatement_matches_scipy_on_same_variates():
+    """scipy _rvs_Z1 draws TH then W from random_state (scipy stats/_levy_stable/__init__.py:472-475)."""
+    for alpha in ALPHAS:
+        n = 20000
+        rs = np.random.RandomState(11)
+        ref = scipy.stats.levy_stable.rvs(alpha / 2, 1, loc=0, scale=stable.levy_scale(alpha), size=n, random_state=rs)
+        rs = np.random.RandomState(11)
+        TH = rs.uniform(-np.pi / 2, np.pi / 2, size=n)
+        W = rs.standard_exponential(size=n)
+        mine = stable.levy_scale(alpha) * stable.cms_totally_skewed(alpha / 2, TH, W)
+        np.testing.assert_allclose(mine, ref, rtol=1e-9)
+        # reduced Kanter form used by the CUDA kernel: identical pointwise with U = TH + pi/2
+        np.testing.assert_allclose(stable.kanter_A(alpha, TH + np.pi / 2, W), ref, rtol=1e-7)
+
+
+def test_laplace_transform_closed_form():
+    """E exp(-A/2) = exp(-1) for every alpha (A = 2K, E exp(-sK) = exp(-s^(alpha/2)))."""
+    for alpha in ALPHAS:
+        A = stable.gen_skewed_levy(alpha, (400000,), isotropic=False, rng=np.random.RandomState(3))
+        assert abs(np.exp(-A.astype(np.float64) / 2).mean() - np.exp(-1.0)) < 3e-3
+
+
+def test_noise_golden():
+    g = load_golden("noise")
+    for alpha in (1.5, 1.7, 1.9, 2.0):
+        for iso in (True, False):
+            tag = "a%.1f_%s" % (alpha, "iso" if iso else "full")
+            A = stable.gen_skewed_levy(alpha, (64, 3, 4), isotropic=iso, clamp_a=20.0 if iso else None,
+                                       rng=np.random.RandomState(1234))
+            np.testing.assert_allclose(A, g["A_" + tag], rtol=2e-6)
+            e = stable.gen_sas(alpha, (64, 3, 4), isotropic=iso, clamp_eps=50.0, rng=np.random.RandomState(77),
+                               G=g["G_" + tag])
+            np.testing.assert_allclose(e, g["eps_" + tag], rtol=2e-6, atol=1e-7)
+
+
+def test_schedule_golden_bit_exact():
+    g = load_golden("schedule")
+    for key in g.files:
+        a, T, kind = key.split("_")
+        alpha, T = float(a[1:]), int(T[1:])
+        if kind == "exploding":
+            sched = process.gen_noise_schedule(alpha, T, scale="scale_exploding")
+        else:
+            sched = process.gen_noise_schedule(alpha, T, time_spacing=kind)
+        got = torch.stack(sched).numpy()
+        assert np.array_equal(got, g[key], equal_nan=True), key
+
+
+def _mlp(g):
+    sd = {k: torch.from_numpy(v) for k, v in sub(g, "sd").items()}
+    return lambda x, t: nets.mlp_forward(sd, 4, x, t)
+
+
+def test_mlp_forward_golden():
+    g = load_golden("mlp_chain")
+    f = sub(g, "fwd")
+    y = _mlp(g)(torch.from_numpy(f["x"]), torch.from_numpy(f["t"]))
+    np.testing.assert_allclose(y.numpy(), f["y"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("tag,kw", [("dlpm", {}), ("dlpm_clip", dict(clip_denoised=True)), ("dlpm_clampa", {}),
+                                    ("dlim", dict(deterministic=True))])
+def test_dlpm_chain_golden(tag, kw):
+    g = load_golden("mlp_chain")
+    r = sub(g, tag)
+    T, B = r["A"].shape
+    shape = r["x_init"].shape
+    A = torch.from_numpy(r["A"]).view(T, B, *([1] * (len(shape) - 1))).expand(T, *shape)
+    net = _mlp(g)
+    z = torch.from_numpy(r["z"])
+    # free-running: 1-ulp differences are amplified by the chain, so the bar is the north-star rtol 1e-3 regime
+    final, hist = process.dlpm_sample_loop(net, torch.from_numpy(r["x_init"]), A, z, 1.7, T, **kw)
+    np.testing.assert_allclose(hist.numpy(), r["hist"], rtol=5e-3, atol=1e-3)
+    sched = process.gen_noise_schedule(1.7, T)
+    Sig = process.compute_Sigmas(torch.from_numpy(r["A"]), sched[0], sched[2])
+    np.testing.assert_array_equal(Sig.numpy(), r["Sigmas"])
+    # teacher-forced: feed the reference's x_t, compare x_{t-1} (tight)
+    Sigf = process.compute_Sigmas(A, sched[0], sched[2])
+    ref_hist = torch.from_numpy(r["hist"])
+    for k, t in enumerate(range(T - 1, 0, -1)):
+        x = ref_hist[k]
+        eps = net(x, torch.tensor([t] * B).float() * (1.0 / T))
+        if kw.get("deterministic"):
+            xn = process.dlim_step(x, eps, t, sched, kw.get("clip_denoised", False))
+        else:
+            xn = process.dlpm_step(x, eps, z[k], t, Sigf, sched, kw.get("clip_denoised", False))
+        np.testing.assert_allclose(xn.numpy(), r["hist"][k + 1], rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("tag,ode", [("lim_sde", False), ("lim_ode", True)])
+def test_lim_chain_golden(tag, ode):
+    g = load_golden("mlp_chain")
+    r = sub(g, tag)
+    steps = r["e_L"].shape[0]
+    final, hist = process.lim_sample_loop(_mlp(g), torch.from_numpy(r["x_init"]), torch.from_numpy(r["e_L"]), 1.7, steps,
+                                          ode=ode)
+    np.testing.assert_allclose(hist.numpy(), r["hist"], rtol=5e-3, atol=1e-3)
+
+
+def test_training_loss_golden():
+    g = load_golden("mlp_chain")
+    r = sub(g, "train")
+    x0, t = torch.from_numpy(r["x0"]), torch.from_numpy(r["t"])
+    A = torch.from_numpy(r["A"]).view(-1, 1, 1).expand_as(x0)
+    z = torch.from_numpy(r["z"])
+    gs, bg, s, bs = process.gen_noise_schedule(1.7, 100)
+    x_t, eps_t = process.one_rv_loss_elements(x0, t, A, z, bg, bs)
+    np.testing.assert_allclose(x_t.numpy(), r["x_t"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(eps_t.numpy(), r["eps_t"], rtol=1e-5, atol=1e-6)
+    loss = process.training_loss_dlpm(_mlp(g), x0, t, A, z, 1.7, 100)
+    np.testing.assert_allclose(loss.numpy(), r["loss"], rtol=1e-5)
+
+
+UNET_CFGS = {
+    "mnist": dict(model_channels=32, channel_mult=(1, 2, 2, 2), num_res_blocks=2, attention_resolutions=(2, 4),
+                  num_heads=4, in_ch=1),
+    "cifar_half": dict(model_channels=64, channel_mult=(1, 2, 2, 2), num_res_blocks=2, attention_resolutions=(16,),
+                       num_heads=4, in_ch=3),
+}
+
+
+def unet_state_dict(cfg, seed=21):
+    """Weights from the seed recipe (dlpm_b200.init_utils) on the parameter-container mirror."""
+    from dlpm_b200.init_utils import parameter_checksum, randomize_parameters_
+    from dlpm_b200.score_nets import UNetModel
+    m = UNetModel(in_channels=cfg["in_ch"], model_channels=cfg["model_channels"], out_channels=cfg["in_ch"],
+                  num_res_blocks=cfg["num_res_blocks"], attention_resolutions=cfg["attention_resolutions"],
+                  channel_mult=cfg["channel_mult"], num_heads=cfg["num_heads"], use_scale_shift_norm=True)
+    randomize_parameters_(m, seed)
+    return {k: v.detach() for k, v in m.state_dict().items()}, parameter_checksum(m)
+
+
+@pytest.mark.parametrize("name", ["mnist", "cifar_half"])
+def test_unet_forward_and_chain_golden(name):
+    g = load_golden("unet_" + name)
+    cfg = UNET_CFGS[name]
+    sd, csum = unet_state_dict(cfg)
+    assert abs(csum - float(g["weight_checksum"])) < 1e-6 * max(1.0, abs(csum)), "seed recipe drifted"
+    net = lambda x, t: nets.unet_forward(sd, cfg, x, t)
+    x = torch.from_numpy(g["fwd/x"])
+    np.testing.assert_allclose(net(x, torch.from_numpy(g["fwd/t"])).numpy(), g["fwd/y"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(net(x, torch.from_numpy(g["fwd2/t"])).numpy(), g["fwd2/y"], rtol=1e-4, atol=2e-5)
+    r = sub(g, "dlpm")
+    T, B = r["A"].shape
+    shape = r["x_init"].shape
+    A = torch.from_numpy(r["A"]).view(T, B, 1, 1, 1).expand(T, *shape)
+    final, hist = process.dlpm_sample_loop(net, torch.from_numpy(r["x_init"]), A, torch.from_numpy(r["z"]), 1.7, T)
+    np.testing.assert_allclose(hist.numpy(), r["hist"], rtol=1e-3, atol=1e-3)
+    r = sub(g, "lim_sde")
+    final, hist = process.lim_sample_loop(net, torch.from_numpy(r["x_init"]), torch.from_numpy(r["e_L"]), 1.7,
+                                          r["e_L"].shape[0])
+    np.testing.assert_allclose(hist.numpy(), r["hist"], rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="/root/reference not present (GPU box)")
+def test_oracle_against_live_reference():
+    """Fresh random case straight against the imported reference (build container only)."""
+    ns = ref_import.load()
+    for alpha in ALPHAS:
+        d = ns.dlpm.DLPM(alpha, "cpu", 37)
+        mine = process.gen_noise_schedule(alpha, 37)
+        for a, b in zip(mine, (d.gammas, d.bargammas, d.sigmas, d.barsigmas)):
+            assert torch.equal(a, b)
+        np.random.seed(5)
+        ref_A = ns.Distributions.gen_skewed_levy(alpha, (33, 5), isotropic=False).numpy()
+        np.testing.assert_allclose(stable.gen_skewed_levy(alpha, (33, 5), isotropic=False, rng=np.random.RandomState(5)),
+                                   ref_A, rtol=2e-6)
+    sde_ref, sde = ns.sde.VPSDE(1.7, "cosine"), process.VPSDE(1.7)
+    t = torch.linspace(0.9946, 1e-5, 11)
+    assert torch.equal(sde_ref.marginal_std(t), sde.marginal_std(t))
+    assert torch.equal(sde_ref.diffusion_coeff(t), sde.diffusion_coeff(t))
