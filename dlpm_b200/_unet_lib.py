@@ -1,0 +1,132 @@
+"""ctypes side of the UNet engine (``include/dlpm_b200_unet.h``) and the graph-replayed sampling loop."""
+import ctypes
+
+import torch
+
+from . import _lib
+
+c_i64, c_int, c_f32, c_vp = ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_void_p
+
+UNET_SIGNATURES = {
+    "dlpm_b200_conv2d": [c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_int, c_i64, c_int, c_int, c_int, c_int,
+                         c_int, c_int, c_vp],
+    "dlpm_b200_groupnorm_silu": [c_vp, c_vp, c_int, c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_int, c_i64, c_i64, c_int,
+                                 c_vp],
+    "dlpm_b200_attention": [c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp],
+    "dlpm_b200_conv_in": [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp],
+    "dlpm_b200_upsample2x": [c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp],
+    "dlpm_b200_time_embedding": [c_vp, c_vp, c_vp, c_vp, c_f32, c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "dlpm_b200_unet_create": [ctypes.POINTER(c_vp), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), c_vp,
+                              c_i64, c_vp, c_i64, c_i64],
+    "dlpm_b200_unet_forward": [c_vp, c_vp, c_vp, c_int, c_vp, c_f32, c_vp, c_i64, c_vp],
+    "dlpm_b200_unet_copy_buffer": [c_vp, c_int, c_vp, c_i64, c_vp],
+    "dlpm_b200_unet_num_launches": [c_vp],
+    "dlpm_b200_unet_destroy": [c_vp],
+}
+
+
+def declare(lib):
+    for name, argtypes in UNET_SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = c_int
+    lib.dlpm_b200_unet_workspace_bytes.argtypes = [c_vp]
+    lib.dlpm_b200_unet_workspace_bytes.restype = c_i64
+
+
+class Engine:
+    """Owns one ``dlpm_b200_unet_create`` handle."""
+
+    def __init__(self, prog, max_batch, version):
+        lib = _lib.load()
+        self.prog = prog
+        self.max_batch = int(max_batch)
+        self.version = version
+        self.names = prog["names"]
+        self.bufs = prog["bufs"]
+        header = (c_i64 * 16)(*prog["header"])
+        flat_ops = [v for op in prog["ops"] for v in op]
+        ops = (c_i64 * len(flat_ops))(*flat_ops)
+        bufs = (c_i64 * len(prog["bufs"]))(*prog["bufs"])
+        self.handle = c_vp()
+        wb, wf = prog["wb"], prog["wf"]
+        _lib.call("dlpm_b200_unet_create", ctypes.byref(self.handle), header, ops, bufs, _lib.ptr(wb), wb.numel(), _lib.ptr(wf),
+                  wf.numel(), self.max_batch)
+        torch.cuda.synchronize()
+        self.workspace_bytes = lib.dlpm_b200_unet_workspace_bytes(self.handle)
+
+    def forward(self, x, t, t_dev, inv_T, out, B):
+        _lib.call("dlpm_b200_unet_forward", self.handle, _lib.ptr(x), _lib.ptr(t), 0 if t is None else t.numel(), _lib.ptr(t_dev),
+                  float(inv_T), _lib.ptr(out), B, _lib.stream_ptr())
+
+    def num_launches(self):
+        return _lib.load().dlpm_b200_unet_num_launches(self.handle)
+
+    def read_buffer(self, name_or_id, B, shape_hwc):
+        """Debug: NHWC bf16 activation of the last forward as a float32 NCHW tensor."""
+        bid = self.names[name_or_id] if isinstance(name_or_id, str) else int(name_or_id)
+        H, W, C = shape_hwc
+        dst = torch.empty((B, H, W, C), device="cuda", dtype=torch.bfloat16)
+        assert H * W * C == self.bufs[bid], (H * W * C, self.bufs[bid])
+        _lib.call("dlpm_b200_unet_copy_buffer", self.handle, bid, _lib.ptr(dst), B, _lib.stream_ptr())
+        return dst.float().permute(0, 3, 1, 2).contiguous()
+
+    def close(self):
+        if self.handle:
+            torch.cuda.synchronize()
+            _lib.load().dlpm_b200_unet_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def run_sample_loop(model, x, dlpm, T, mode, flags, hist, seed, z_offset, sample_base, graph_cache=None, progress=False,
+                    use_graph=True):
+    """x: (B, C, H, W) fp32, updated in place to x_0.  One step = UNet forward (t from the device counter) + fused
+    update + counter decrement; captured once as a CUDA graph and replayed T-1 times."""
+    dev = x.device
+    B, C, H, W = x.shape
+    D = C * H * W
+    eng = model.engine(H, W, B)
+    eps = torch.empty((B, model.out_channels, H, W), device=dev, dtype=torch.float32)
+    t_dev = torch.full((1,), T - 1, device=dev, dtype=torch.int32)
+    inv_T = float(torch.tensor(1.0 / T, dtype=torch.float32))
+    stream = torch.cuda.current_stream()
+
+    def one_step(h_ptr):
+        eng.forward(x, None, t_dev, inv_T, eps, B)
+        if mode == 1:
+            _lib.call("dlpm_b200_dlim_step", _lib.ptr(x), _lib.ptr(eps), _lib.ptr(dlpm.sched), 0, _lib.ptr(t_dev), T, B, D, flags,
+                      h_ptr, _lib.stream_ptr())
+        else:
+            _lib.call("dlpm_b200_reverse_step", _lib.ptr(x), _lib.ptr(eps), _lib.ptr(dlpm.Sigmas), _lib.ptr(dlpm.sched), 0,
+                      _lib.ptr(t_dev), T, B, D, flags, None, seed, z_offset, sample_base, h_ptr, _lib.stream_ptr())
+        _lib.call("dlpm_b200_advance_counter", _lib.ptr(t_dev), -1, _lib.stream_ptr())
+
+    if hist is not None or not use_graph:
+        # history needs a different destination every step: run the launches directly
+        for k in range(T - 1):
+            one_step(_lib.ptr(hist[k + 1]) if hist is not None else None)
+        return
+    # warm-up step outside capture builds the per-batch plan (TMA descriptors) -- then rewind
+    x_save = x.clone()
+    one_step(None)
+    x.copy_(x_save)
+    t_dev.fill_(T - 1)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(stream)
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            one_step(None)
+    stream.wait_stream(side)
+    # capture does not execute: state is still (x_{T-1}, t = T-1)
+    for _ in range(T - 1):
+        g.replay()
+    torch.cuda.synchronize()
+    del g

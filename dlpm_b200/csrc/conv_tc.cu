@@ -1,0 +1,355 @@
+// K5: implicit-GEMM 3x3 / 1x1 convolution on 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM,
+// operands staged by TMA), replacing the cuDNN calls behind unet.py:64,96,143,157,164-168,347,435
+// (nn.Conv2d in ResBlock / Upsample / Downsample / AttentionBlock of dlpm/models/unet.py).
+//
+// GEMM view:  D[M = B*H*W pixels, N = C_out] = sum_k A[M, k] * Wt[N, k],  k = (tap, c_in) [+ 1x1 skip-conv channels]
+//   * activations are NHWC bf16; an M tile is 128 pixels = a (Wb x Hb x Nb) box of the 4-D tensor
+//     [B, H, W, C].  For filter tap (dy, dx) the A tile is the SAME box shifted by (dy, dx): one
+//     cp.async.bulk.tensor.4d per (tap, 64-channel block), zero padding comes from TMA out-of-bounds
+//     fill, stride-2 convolutions use the tensor map's element strides.  No im2col buffer exists.
+//   * the TMA writes rows of 128 B (64 bf16 channels) in 128B-swizzled 8-row atoms = the canonical
+//     K-major UMMA operand layout, so the MMA consumes the tile as it lands.
+//   * ResBlock fusion: the 1x1 skip convolution (unet.py:161-168) is appended to the K loop of the
+//     block's second 3x3 conv (extra K blocks reading the raw block input through tmS0/tmS1 = the two
+//     halves of the skip concatenation, unet.py:489) and identity skips are added in the epilogue,
+//     so `skip_connection(x) + h` (unet.py:195) costs no extra pass.
+//   * warp-specialised, persistent: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread),
+//     warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld -> +bias (+residual) -> bf16 -> global).
+//     Two accumulator stages in TMEM let the epilogue of tile i overlap the MMAs of tile i+1.
+#include "../../include/dlpm_b200_unet.h"
+#include "conv_tc.cuh"
+#include "tc_common.cuh"
+
+namespace dlpm {
+
+using namespace tc;
+
+constexpr int kMaxStages = 8;
+constexpr int kConvThreads = 256;
+constexpr int kSmemBudget = 200 * 1024;  // operand ring; barriers + alignment slack come on top
+
+struct ConvKParams {
+  int n_m_tiles, n_n_tiles, stages;
+  int Wb, Hb, Nb, H_out, W_out, tiles_per_img;
+  int stride, taps, cin_blocks, s0_blocks, s1_blocks;
+  int64_t B;
+  int C_out, C_out_real, out_mode;
+  const float* bias;
+  const __nv_bfloat16* residual;
+  void* out;
+};
+
+template <int BLOCK_N, int BLOCK_K>
+__global__ void __launch_bounds__(kConvThreads, 1)
+k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmS0,
+          const __grid_constant__ CUtensorMap tmS1, const __grid_constant__ CUtensorMap tmB, const ConvKParams p) {
+  constexpr int A_BYTES = 128 * BLOCK_K * 2;
+  constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int SWZ = BLOCK_K * 2;  // bytes per operand row = swizzle span (128 or 64)
+  constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
+  constexpr uint32_t IDESC = make_idesc_bf16(128, BLOCK_N);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tfull_bar = empty_bar + kMaxStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int main_blocks = p.taps * p.cin_blocks;
+  const int nkb = main_blocks + p.s0_blocks + p.s1_blocks;
+  const int n_tiles = p.n_m_tiles * p.n_n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    if (p.s0_blocks) prefetch_tmap(&tmS0);
+    if (p.s1_blocks) prefetch_tmap(&tmS1);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar + a, 1); mbar_init(tempty_bar + a, 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_n_tiles, mt = tile / p.n_n_tiles;
+        int n0, h0;
+        if (p.Nb == 1) { n0 = mt / p.tiles_per_img; h0 = (mt - n0 * p.tiles_per_img) * p.Hb; }
+        else { n0 = mt * p.Nb; h0 = 0; }
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(empty_bar + stage, phase ^ 1);
+          uint8_t* a_dst = smem + stage * STAGE_BYTES;
+          uint8_t* b_dst = a_dst + A_BYTES;
+          mbar_expect_tx(full_bar + stage, STAGE_BYTES);
+          if (kb < main_blocks) {
+            const int tap = kb / p.cin_blocks, cblk = kb - tap * p.cin_blocks;
+            const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap - (tap / 3) * 3 - 1 : 0;
+            tma_load_4d(&tmA, full_bar + stage, a_dst, cblk * BLOCK_K, dx, h0 * p.stride + dy, n0);
+          } else if (kb < main_blocks + p.s0_blocks) {
+            tma_load_4d(&tmS0, full_bar + stage, a_dst, (kb - main_blocks) * BLOCK_K, 0, h0, n0);
+          } else {
+            tma_load_4d(&tmS1, full_bar + stage, a_dst, (kb - main_blocks - p.s0_blocks) * BLOCK_K, 0, h0, n0);
+          }
+          tma_load_2d(&tmB, full_bar + stage, b_dst, kb * BLOCK_K, nt * BLOCK_N);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(tempty_bar + acc, acc_phase ^ 1);  // epilogue has drained this accumulator stage
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(full_bar + stage, phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            const uint64_t da = make_smem_desc<SWZ>(a_addr + k * 32);
+            const uint64_t db = make_smem_desc<SWZ>(b_addr + k * 32);
+            umma_bf16(d_tmem, da, db, IDESC, (kb | k) != 0);
+          }
+          umma_commit(empty_bar + stage);  // frees the smem slot when these MMAs retire
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar + acc);  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int m = q * 32 + lane;
+    const int w_in = m % p.Wb, h_in = (m / p.Wb) % p.Hb, n_in = m / (p.Wb * p.Hb);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int nt = tile % p.n_n_tiles, mt = tile / p.n_n_tiles;
+      int n0, h0;
+      if (p.Nb == 1) { n0 = mt / p.tiles_per_img; h0 = (mt - n0 * p.tiles_per_img) * p.Hb; }
+      else { n0 = mt * p.Nb; h0 = 0; }
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(tfull_bar + acc, acc_phase);
+      tc_fence_after();
+      const int64_t nn = (int64_t)n0 + n_in;
+      const bool valid = nn < p.B;
+      const int64_t pix = (nn * p.H_out + h0 + h_in) * p.W_out + w_in;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+      if (p.out_mode == CONV_OUT_BF16_NHWC) {
+        constexpr int CH = BLOCK_N >= 32 ? 32 : 16;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += CH) {
+          uint32_t r[CH];
+          if constexpr (CH == 32) tmem_ld_x32(t_row + c0, r);
+          else tmem_ld_x16(t_row + c0, r);
+          tmem_ld_wait();
+          if (valid) {
+            const int col = nt * BLOCK_N + c0;
+            const float* bias = p.bias + col;
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.C_out + col;
+            const __nv_bfloat16* res = p.residual ? p.residual + pix * p.C_out + col : nullptr;
+#pragma unroll
+            for (int j = 0; j < CH; j += 8) {
+              float v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[j + e]) + __ldg(bias + j + e);
+              if (res) {
+                const uint4 rv = *reinterpret_cast<const uint4*>(res + j);
+                const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(rp[e]); v[2 * e] += f.x; v[2 * e + 1] += f.y; }
+              }
+              uint4 o;
+              __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) op[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+              *reinterpret_cast<uint4*>(dst + j) = o;
+            }
+          }
+        }
+      } else {
+        // fp32 NCHW, first C_out_real channels of the (zero-padded) tile: the network's final conv (unet.py:435)
+        uint32_t r[16];
+        tmem_ld_x16(t_row, r);
+        tmem_ld_wait();
+        if (valid) {
+          float* dst = reinterpret_cast<float*>(p.out);
+          const int64_t hw = (int64_t)p.H_out * p.W_out;
+          const int64_t sp = (int64_t)(h0 + h_in) * p.W_out + w_in;
+#pragma unroll
+          for (int c = 0; c < 16; ++c)
+            if (c < p.C_out_real) dst[(nn * p.C_out_real + c) * hw + sp] = __uint_as_float(r[c]) + __ldg(p.bias + c);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar + acc);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+static int encode_act_map(CUtensorMap* m, const void* base, int64_t B, int H, int W, int C, int block_k, int Wb, int Hb, int Nb,
+                          int stride) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return DLPM_ERR_CUDA; }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)block_k, (cuuint32_t)(Wb * stride), (cuuint32_t)(Hb * stride), (cuuint32_t)Nb};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activation [%lld,%d,%d,%d]) failed: %d", (long long)B, H, W, C, (int)r); return DLPM_ERR_CUDA; }
+  return DLPM_OK;
+}
+
+static int encode_weight_map(CUtensorMap* m, const void* base, int rows, int64_t k_total, int block_n, int block_k) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return DLPM_ERR_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
+  cuuint32_t box[2] = {(cuuint32_t)block_k, (cuuint32_t)block_n};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights [%d,%lld]) failed: %d", rows, (long long)k_total, (int)r); return DLPM_ERR_CUDA; }
+  return DLPM_OK;
+}
+
+int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, const void* skip0, int C_s0, const void* skip1,
+              int C_s1, const void* residual, void* out, int out_mode, int64_t B, int H, int W, int C_in, int C_out, int ksize,
+              int stride) {
+  DLPM_REQUIRE(in && w && bias && out, "conv: NULL tensor");
+  DLPM_REQUIRE(ksize == 3 || ksize == 1, "conv: kernel size must be 1 or 3");
+  DLPM_REQUIRE(stride == 1 || stride == 2, "conv: stride must be 1 or 2");
+  DLPM_REQUIRE(B >= 1 && H >= 1 && W >= 1, "conv: bad shape");
+  DLPM_REQUIRE(H % stride == 0 && W % stride == 0, "conv: H, W must be divisible by the stride");
+  DLPM_REQUIRE((skip0 == nullptr) == (C_s0 == 0) && (skip1 == nullptr) == (C_s1 == 0), "conv: skip source / channel mismatch");
+  DLPM_REQUIRE(!(stride == 2 && (skip0 || skip1 || residual)), "conv: skip fusion needs stride 1");
+  const int H_out = H / stride, W_out = W / stride;
+  DLPM_REQUIRE(W_out <= 128 && (W_out & (W_out - 1)) == 0 && (H_out & (H_out - 1)) == 0,
+               "conv: output H and W must be powers of two with W <= 128");
+  const int bk = (C_in % 64 == 0 && C_s0 % 64 == 0 && C_s1 % 64 == 0) ? 64 : 32;
+  if (C_in % bk || C_s0 % bk || C_s1 % bk) { set_error("conv: channel counts must be multiples of 32 (got %d,%d,%d)", C_in, C_s0, C_s1); return DLPM_ERR_UNSUPPORTED; }
+  const int C_out_pad = out_mode == CONV_OUT_F32_NCHW ? 16 : C_out;
+  int bn;
+  if (out_mode == CONV_OUT_F32_NCHW) { DLPM_REQUIRE(C_out <= 16, "conv: fp32 NCHW output supports <= 16 channels"); bn = 16; }
+  else if (C_out % 256 == 0) bn = 256;
+  else if (C_out % 128 == 0) bn = 128;
+  else if (C_out % 64 == 0) bn = 64;
+  else if (C_out % 32 == 0) bn = 32;
+  else if (C_out % 16 == 0) bn = 16;
+  else { set_error("conv: C_out must be a multiple of 16 (got %d)", C_out); return DLPM_ERR_UNSUPPORTED; }
+  L->block_n = bn; L->block_k = bk;
+  L->Wb = W_out;
+  L->Hb = (128 / W_out) < H_out ? (128 / W_out) : H_out;
+  L->Nb = 128 / (L->Wb * L->Hb);
+  L->H_out = H_out; L->W_out = W_out;
+  L->tiles_per_img = L->Nb == 1 ? H_out / L->Hb : 0;
+  L->n_m_tiles = L->Nb == 1 ? (int)(B * L->tiles_per_img) : (int)((B + L->Nb - 1) / L->Nb);
+  L->n_n_tiles = C_out_pad / bn;
+  L->stride = stride; L->taps = ksize * ksize;
+  L->cin_blocks = C_in / bk; L->s0_blocks = C_s0 / bk; L->s1_blocks = C_s1 / bk;
+  L->B = B; L->C_out = C_out; L->C_out_real = C_out; L->out_mode = out_mode;
+  L->bias = bias; L->residual = reinterpret_cast<const __nv_bfloat16*>(residual); L->out = out;
+  int rc;
+  if ((rc = encode_act_map(&L->tmA, in, B, H, W, C_in, bk, L->Wb, L->Hb, L->Nb, stride))) return rc;
+  L->tmS0 = L->tmA; L->tmS1 = L->tmA;
+  if (skip0 && (rc = encode_act_map(&L->tmS0, skip0, B, H_out, W_out, C_s0, bk, L->Wb, L->Hb, L->Nb, 1))) return rc;
+  if (skip1 && (rc = encode_act_map(&L->tmS1, skip1, B, H_out, W_out, C_s1, bk, L->Wb, L->Hb, L->Nb, 1))) return rc;
+  const int64_t k_total = (int64_t)L->taps * C_in + C_s0 + C_s1;
+  if ((rc = encode_weight_map(&L->tmB, w, C_out_pad, k_total, bn, bk))) return rc;
+  return DLPM_OK;
+}
+
+template <int BN, int BK>
+static int launch_t(const ConvLaunch& L, cudaStream_t stream) {
+  constexpr int STAGE = 128 * BK * 2 + BN * BK * 2;
+  int stages = kSmemBudget / STAGE;
+  if (stages > kMaxStages) stages = kMaxStages;
+  const size_t smem = (size_t)stages * STAGE + 1024 /*align*/ + (2 * kMaxStages + 4) * 8 + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_conv_tc<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemBudget + 2048));
+    if (e != cudaSuccess) return cuda_fail(e, "conv smem attribute");
+    attr_set = true;
+  }
+  ConvKParams p;
+  p.n_m_tiles = L.n_m_tiles; p.n_n_tiles = L.n_n_tiles; p.stages = stages;
+  p.Wb = L.Wb; p.Hb = L.Hb; p.Nb = L.Nb; p.H_out = L.H_out; p.W_out = L.W_out; p.tiles_per_img = L.tiles_per_img;
+  p.stride = L.stride; p.taps = L.taps; p.cin_blocks = L.cin_blocks; p.s0_blocks = L.s0_blocks; p.s1_blocks = L.s1_blocks;
+  p.B = L.B; p.C_out = L.C_out; p.C_out_real = L.C_out_real; p.out_mode = L.out_mode;
+  p.bias = L.bias; p.residual = L.residual; p.out = L.out;
+  const int n_tiles = L.n_m_tiles * L.n_n_tiles;
+  const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
+  k_conv_tc<BN, BK><<<grid, kConvThreads, smem, stream>>>(L.tmA, L.tmS0, L.tmS1, L.tmB, p);
+  DLPM_CHECK_LAUNCH("conv_tc");
+  return DLPM_OK;
+}
+
+int conv_launch(const ConvLaunch& L, cudaStream_t stream) {
+#define CASE(BN, BK) if (L.block_n == BN && L.block_k == BK) return launch_t<BN, BK>(L, stream)
+  CASE(256, 64); CASE(128, 64); CASE(64, 64); CASE(32, 64); CASE(16, 64);
+  CASE(256, 32); CASE(128, 32); CASE(64, 32); CASE(32, 32); CASE(16, 32);
+#undef CASE
+  set_error("conv: no kernel for tile N=%d K=%d", L.block_n, L.block_k);
+  return DLPM_ERR_UNSUPPORTED;
+}
+
+}  // namespace dlpm
+
+using namespace dlpm;
+
+int dlpm_b200_conv2d(const void* in, const void* w, const float* bias, const void* skip0, int C_s0, const void* skip1, int C_s1,
+                     const void* residual, void* out, int out_mode, int64_t B, int H, int W, int C_in, int C_out, int ksize,
+                     int stride, void* stream) {
+  ConvLaunch L;
+  if (int rc = conv_plan(&L, in, w, bias, skip0, C_s0, skip1, C_s1, residual, out, out_mode, B, H, W, C_in, C_out, ksize, stride))
+    return rc;
+  return conv_launch(L, (cudaStream_t)stream);
+}

@@ -1,0 +1,36 @@
+// K5: implicit-GEMM convolution on tcgen05 tensor cores (host-side interface).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace dlpm {
+
+enum ConvOutMode { CONV_OUT_BF16_NHWC = 0, CONV_OUT_F32_NCHW = 1 };
+
+// Everything the launcher needs for one convolution (tensor maps are built once per plan).
+struct ConvLaunch {
+  CUtensorMap tmA, tmS0, tmS1, tmB;  // main activation, two optional 1x1 skip-conv sources, packed weights
+  int block_n, block_k;              // tile N (16..256), K block in channels (64 or 32)
+  int n_m_tiles, n_n_tiles;
+  int Wb, Hb, Nb;                    // pixel box of one M tile: Wb*Hb*Nb == 128
+  int H_out, W_out, tiles_per_img;
+  int stride, taps;
+  int cin_blocks, s0_blocks, s1_blocks;
+  int64_t B;
+  int C_out;       // row stride (channels) of the output / residual tensors
+  int C_out_real;  // channels actually written (conv_out: 3 of the padded 16)
+  int out_mode;
+  const float* bias;                // [n_n_tiles * block_n] fp32
+  const __nv_bfloat16* residual;    // NHWC bf16 [B, H_out, W_out, C_out] or nullptr
+  void* out;
+};
+
+// Fills geometry + tensor maps.  in: NHWC bf16 [B, H, W, C_in]; w: bf16 [C_out_pad][taps*C_in + C_s0 + C_s1] (K contiguous);
+// skip sources NHWC bf16 [B, H_out, W_out, C_s*].  Returns DLPM_OK or an error code (message via set_error).
+int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, const void* skip0, int C_s0, const void* skip1,
+              int C_s1, const void* residual, void* out, int out_mode, int64_t B, int H, int W, int C_in, int C_out, int ksize,
+              int stride);
+int conv_launch(const ConvLaunch& L, cudaStream_t stream);
+
+}  // namespace dlpm

@@ -1,0 +1,183 @@
+// UNet engine: executes the op list built by dlpm_b200/score_nets.py::UNetModel (which walks the
+// reference architecture, dlpm/models/unet.py:343-437 / forward :463-492) with the kernels of
+// conv_tc.cu (K5) and unet_ops.cu (K6/K7).  Owns the packed weights, the NHWC bf16 activation
+// buffers and the TMA descriptors (rebuilt only when the batch size changes).
+#include <cstring>
+#include <map>
+#include <vector>
+
+#include "../../include/dlpm_b200_unet.h"
+#include "conv_tc.cuh"
+
+namespace dlpm {
+
+enum OpCode { OP_CONV_IN = 0, OP_GN = 1, OP_CONV = 2, OP_UP = 3, OP_ATTN = 4 };
+
+struct Op { int64_t f[16]; };
+
+struct Plan {  // per batch size
+  int64_t B = 0;
+  std::vector<ConvLaunch> convs;  // one per OP_CONV, in op order
+};
+
+struct UNetEngine {
+  int64_t header[16];
+  std::vector<Op> ops;
+  std::vector<int64_t> buf_elems;
+  std::vector<int64_t> buf_offset;  // element offset (per sample, bf16) inside the activation slab
+  int64_t elems_per_sample = 0;
+  int64_t max_batch = 0;
+  __nv_bfloat16* wb = nullptr;
+  float* wf = nullptr;
+  __nv_bfloat16* slab = nullptr;
+  float* ss = nullptr;    // [max_batch][ss_total]
+  float* semb = nullptr;  // [max_batch][4*mc]
+  int64_t workspace_bytes = 0;
+  std::map<int64_t, Plan> plans;
+  int n_launches = 0;
+
+  __nv_bfloat16* buf(int64_t id, int64_t B) const { return slab + buf_offset[id] * max_batch; }
+};
+
+static int build_plan(UNetEngine* E, int64_t B, Plan* P) {
+  P->B = B;
+  P->convs.clear();
+  for (const Op& op : E->ops) {
+    if (op.f[0] != OP_CONV) continue;
+    // f: 1 in, 2 out(-1 = external fp32 NCHW), 3 skip0, 4 C_s0, 5 skip1, 6 C_s1, 7 residual, 8 H, 9 W, 10 C_in, 11 C_out, 12 ksize,
+    //    13 stride, 14 w_off (bf16 elems), 15 bias_off (fp32 elems)
+    ConvLaunch L;
+    const void* s0 = op.f[3] >= 0 ? E->buf(op.f[3], B) : nullptr;
+    const void* s1 = op.f[5] >= 0 ? E->buf(op.f[5], B) : nullptr;
+    const void* res = op.f[7] >= 0 ? E->buf(op.f[7], B) : nullptr;
+    const bool ext = op.f[2] < 0;
+    void* out = ext ? reinterpret_cast<void*>(0x10) /*patched at launch*/ : E->buf(op.f[2], B);
+    int rc = conv_plan(&L, E->buf(op.f[1], B), E->wb + op.f[14], E->wf + op.f[15], s0, (int)op.f[4], s1, (int)op.f[6], res, out,
+                       ext ? CONV_OUT_F32_NCHW : CONV_OUT_BF16_NHWC, B, (int)op.f[8], (int)op.f[9], (int)op.f[10], (int)op.f[11],
+                       (int)op.f[12], (int)op.f[13]);
+    if (rc) return rc;
+    P->convs.push_back(L);
+  }
+  return DLPM_OK;
+}
+
+}  // namespace dlpm
+
+using namespace dlpm;
+
+int dlpm_b200_unet_create(void** handle, const int64_t* header, const int64_t* ops, const int64_t* bufs, const void* wb, int64_t n_wb,
+                          const float* wf, int64_t n_wf, int64_t max_batch) {
+  DLPM_REQUIRE(handle && header && ops && bufs && wb && wf, "unet_create: NULL argument");
+  DLPM_REQUIRE(max_batch >= 1 && n_wb >= 0 && n_wf >= 1, "unet_create: bad sizes");
+  UNetEngine* E = new UNetEngine();
+  std::memcpy(E->header, header, sizeof(E->header));
+  const int64_t n_ops = header[0], n_bufs = header[1];
+  E->ops.resize(n_ops);
+  std::memcpy(E->ops.data(), ops, sizeof(Op) * n_ops);
+  E->buf_elems.assign(bufs, bufs + n_bufs);
+  E->buf_offset.resize(n_bufs);
+  int64_t off = 0;
+  for (int64_t i = 0; i < n_bufs; ++i) {
+    E->buf_offset[i] = off;
+    off += (E->buf_elems[i] + 63) & ~63ll;  // keep every buffer 128-byte aligned for any batch
+  }
+  E->elems_per_sample = off;
+  E->max_batch = max_batch;
+  const int64_t mc = header[6], ss_total = header[7];
+  cudaError_t e;
+#define ALLOC(ptr, bytes)                                                     \
+  do {                                                                        \
+    e = cudaMalloc(reinterpret_cast<void**>(&(ptr)), (size_t)(bytes));        \
+    if (e != cudaSuccess) { dlpm_b200_unet_destroy(E); return cuda_fail(e, "unet_create cudaMalloc"); } \
+    E->workspace_bytes += (bytes);                                            \
+  } while (0)
+  ALLOC(E->wb, (n_wb > 0 ? n_wb : 1) * 2);
+  ALLOC(E->wf, n_wf * 4);
+  ALLOC(E->slab, off * max_batch * 2);
+  ALLOC(E->ss, max_batch * ss_total * 4);
+  ALLOC(E->semb, max_batch * 4 * mc * 4);
+#undef ALLOC
+  if ((e = cudaMemcpy(E->wb, wb, (size_t)n_wb * 2, cudaMemcpyDeviceToDevice)) != cudaSuccess ||
+      (e = cudaMemcpy(E->wf, wf, (size_t)n_wf * 4, cudaMemcpyDeviceToDevice)) != cudaSuccess) {
+    dlpm_b200_unet_destroy(E);
+    return cuda_fail(e, "unet_create weight copy");
+  }
+  *handle = E;
+  return DLPM_OK;
+}
+
+int dlpm_b200_unet_forward(void* handle, const float* x, const float* t, int t_rows, const int* t_dev, float inv_T, float* out,
+                           int64_t B, void* stream) {
+  DLPM_REQUIRE(handle && x && out && (t || t_dev), "unet_forward: NULL argument");
+  UNetEngine* E = reinterpret_cast<UNetEngine*>(handle);
+  DLPM_REQUIRE(B >= 1 && B <= E->max_batch, "unet_forward: batch exceeds the engine's max_batch");
+  DLPM_REQUIRE(t_dev || t_rows == 1 || t_rows == B, "unet_forward: t_rows must be 1 or B");
+  auto it = E->plans.find(B);
+  if (it == E->plans.end()) {
+    Plan P;
+    if (int rc = build_plan(E, B, &P)) return rc;
+    it = E->plans.emplace(B, std::move(P)).first;
+  }
+  Plan& P = it->second;
+  const int64_t* h = E->header;
+  const int mc = (int)h[6];
+  const int64_t ss_total = h[7];
+  const int rows = t_dev ? 1 : t_rows;
+  int launches = 0;
+  int rc = dlpm_b200_time_embedding(E->ss, E->semb, t, t_dev, inv_T, rows, mc, ss_total, E->wf + h[8], E->wf + h[9], E->wf + h[10],
+                                    E->wf + h[11], E->wf + h[12], E->wf + h[13], stream);
+  if (rc) return rc;
+  launches += 2;
+  size_t ci = 0;
+  for (const Op& op : E->ops) {
+    const int64_t* f = op.f;
+    switch (f[0]) {
+      case OP_CONV_IN:  // 1 out, 2 C_in, 3 C_out, 4 H, 5 W, 6 w_off(f32), 7 b_off(f32)
+        rc = dlpm_b200_conv_in(E->buf(f[1], B), x, E->wf + f[6], E->wf + f[7], B, (int)f[2], (int)f[3], (int)f[4], (int)f[5], stream);
+        break;
+      case OP_GN:  // 1 in0, 2 in1, 3 out, 4 C0, 5 C1, 6 HW, 7 gamma_off, 8 beta_off, 9 ss_off, 10 silu
+        rc = dlpm_b200_groupnorm_silu(E->buf(f[3], B), E->buf(f[1], B), (int)f[4], f[2] >= 0 ? E->buf(f[2], B) : nullptr, (int)f[5], B,
+                                      (int)f[6], E->wf + f[7], E->wf + f[8], f[9] >= 0 ? E->ss : nullptr, rows, ss_total,
+                                      f[9] >= 0 ? f[9] : 0, (int)f[10], stream);
+        break;
+      case OP_CONV: {
+        ConvLaunch& L = P.convs[ci++];
+        if (f[2] < 0) L.out = out;
+        rc = conv_launch(L, (cudaStream_t)stream);
+      } break;
+      case OP_UP:  // 1 in, 2 out, 3 H, 4 W, 5 C
+        rc = dlpm_b200_upsample2x(E->buf(f[2], B), E->buf(f[1], B), B, (int)f[3], (int)f[4], (int)f[5], stream);
+        break;
+      case OP_ATTN:  // 1 qkv, 2 out, 3 L, 4 C, 5 heads
+        rc = dlpm_b200_attention(E->buf(f[2], B), E->buf(f[1], B), B, (int)f[3], (int)f[4], (int)f[5], stream);
+        break;
+      default:
+        set_error("unet_forward: unknown opcode %lld", (long long)f[0]);
+        return DLPM_ERR_ARG;
+    }
+    if (rc) return rc;
+    ++launches;
+  }
+  E->n_launches = launches;
+  return DLPM_OK;
+}
+
+int dlpm_b200_unet_copy_buffer(void* handle, int buf, void* dst, int64_t B, void* stream) {
+  DLPM_REQUIRE(handle && dst, "unet_copy_buffer: NULL argument");
+  UNetEngine* E = reinterpret_cast<UNetEngine*>(handle);
+  DLPM_REQUIRE(buf >= 0 && buf < (int)E->buf_elems.size() && B >= 1 && B <= E->max_batch, "unet_copy_buffer: bad index");
+  cudaError_t e = cudaMemcpyAsync(dst, E->buf(buf, B), (size_t)(E->buf_elems[buf] * B * 2), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "unet_copy_buffer");
+  return DLPM_OK;
+}
+
+int64_t dlpm_b200_unet_workspace_bytes(void* handle) { return handle ? reinterpret_cast<UNetEngine*>(handle)->workspace_bytes : 0; }
+int dlpm_b200_unet_num_launches(void* handle) { return handle ? reinterpret_cast<UNetEngine*>(handle)->n_launches : 0; }
+
+int dlpm_b200_unet_destroy(void* handle) {
+  if (!handle) return DLPM_OK;
+  UNetEngine* E = reinterpret_cast<UNetEngine*>(handle);
+  cudaFree(E->wb); cudaFree(E->wf); cudaFree(E->slab); cudaFree(E->ss); cudaFree(E->semb);
+  delete E;
+  return DLPM_OK;
+}

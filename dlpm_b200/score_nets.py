@@ -170,5 +170,321 @@ def as_native(model, device):
     return native
 
 
+
+
+# ------------------------------------------------------------------------------------------------
+# UNet (image configs)
+# ------------------------------------------------------------------------------------------------
+OP_CONV_IN, OP_GN, OP_CONV, OP_UP, OP_ATTN = 0, 1, 2, 3, 4
+
+
+def _gn(c):
+    return nn.GroupNorm(min(32, c), c)
+
+
+class _ResBlockParams(nn.Module):
+    """Parameter names of ResBlock (unet.py:105-180) with use_scale_shift_norm=True."""
+
+    def __init__(self, channels, emb_channels, out_channels):
+        super().__init__()
+        self.channels, self.out_channels = channels, out_channels
+        self.in_layers = _seq((0, _gn(channels)), (2, nn.Conv2d(channels, out_channels, 3, padding=1)))
+        self.emb_layers = _seq((1, nn.Linear(emb_channels, 2 * out_channels)))
+        self.out_layers = _seq((0, _gn(out_channels)), (3, nn.Conv2d(out_channels, out_channels, 3, padding=1)))
+        self.skip_connection = nn.Identity() if out_channels == channels else nn.Conv2d(channels, out_channels, 1)
+
+
+class _AttentionParams(nn.Module):
+    """Parameter names of AttentionBlock (unet.py:198-228)."""
+
+    def __init__(self, channels, num_heads):
+        super().__init__()
+        self.channels, self.num_heads = channels, num_heads
+        self.norm = _gn(channels)
+        self.qkv = nn.Conv1d(channels, channels * 3, 1)
+        self.proj_out = nn.Conv1d(channels, channels, 1)
+
+
+class _DownParams(nn.Module):
+    def __init__(self, channels):
+        super().__init__()
+        self.channels = channels
+        self.op = nn.Conv2d(channels, channels, 3, stride=2, padding=1)
+
+
+class _UpParams(nn.Module):
+    def __init__(self, channels):
+        super().__init__()
+        self.channels = channels
+        self.conv = nn.Conv2d(channels, channels, 3, padding=1)
+
+
+class UNetModel(nn.Module):
+    """Improved-DDPM UNet with the constructor of unet.py:298-313 (2-D, unconditional, conv resampling,
+    scale-shift norm -- the only variant ``dlpm_experiment.py:41-56`` builds)."""
+
+    native_kind = "unet"
+
+    def __init__(self, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions, dropout=0,
+                 channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2, num_classes=None, use_checkpoint=False,
+                 num_heads=1, num_heads_upsample=-1, use_scale_shift_norm=False):
+        super().__init__()
+        if dims != 2 or num_classes is not None or not conv_resample or not use_scale_shift_norm:
+            raise NotImplementedError("dlpm_b200 UNetModel covers the variant built by dlpm_experiment.py:41-56 "
+                                      "(dims=2, unconditional, conv_resample, use_scale_shift_norm=True)")
+        if num_heads_upsample not in (-1, num_heads):
+            raise NotImplementedError("num_heads_upsample must equal num_heads")
+        self.in_channels, self.model_channels, self.out_channels = in_channels, model_channels, out_channels
+        self.num_res_blocks = num_res_blocks
+        self.attention_resolutions = tuple(attention_resolutions)
+        self.channel_mult = tuple(channel_mult)
+        self.num_heads = num_heads
+        self.dropout = dropout
+        mc = model_channels
+        ted = mc * 4
+        self.time_embed = _seq((0, nn.Linear(mc, ted)), (2, nn.Linear(ted, ted)))
+        blocks = [_seq((0, nn.Conv2d(in_channels, mc, 3, padding=1)))]
+        chans = [mc]
+        ch, ds = mc, 1
+        for level, mult in enumerate(self.channel_mult):
+            for _ in range(num_res_blocks):
+                layers = [_ResBlockParams(ch, ted, mult * mc)]
+                ch = mult * mc
+                if ds in self.attention_resolutions:
+                    layers.append(_AttentionParams(ch, num_heads))
+                blocks.append(_seq(*enumerate(layers)))
+                chans.append(ch)
+            if level != len(self.channel_mult) - 1:
+                blocks.append(_seq((0, _DownParams(ch))))
+                chans.append(ch)
+                ds *= 2
+        self.input_blocks = nn.ModuleList(blocks)
+        self.middle_block = _seq((0, _ResBlockParams(ch, ted, ch)), (1, _AttentionParams(ch, num_heads)),
+                                 (2, _ResBlockParams(ch, ted, ch)))
+        outs = []
+        for level, mult in list(enumerate(self.channel_mult))[::-1]:
+            for i in range(num_res_blocks + 1):
+                layers = [_ResBlockParams(ch + chans.pop(), ted, mc * mult)]
+                ch = mc * mult
+                if ds in self.attention_resolutions:
+                    layers.append(_AttentionParams(ch, num_heads))
+                if level and i == num_res_blocks:
+                    layers.append(_UpParams(ch))
+                    ds //= 2
+                outs.append(_seq(*enumerate(layers)))
+        self.output_blocks = nn.ModuleList(outs)
+        self.out = _seq((0, _gn(ch)), (2, nn.Conv2d(mc, out_channels, 3, padding=1)))
+        self._engines = {}
+        self._cache = _PackedCache()
+
+    # ------------------------------------------------------------------ architecture walk -> op list
+    def build_program(self, H, W, reuse_scratch=True):
+        """Walk forward() (unet.py:463-492) and emit (header, ops, buffer sizes, bf16 blob, fp32 blob, debug names)."""
+        dev = next(self.parameters()).device
+        mc, nh = self.model_channels, self.num_heads
+        ops, bufs, names = [], [], {}
+        wb_parts, wf_parts = [], []
+        wb_len, wf_len = [0], [0]
+        free_pool = []
+
+        def new_buf(elems, tmp=False):
+            if tmp and reuse_scratch:
+                for k, (bid, sz) in enumerate(free_pool):
+                    if sz >= elems:
+                        free_pool.pop(k)
+                        return bid
+            bufs.append(int(elems))
+            return len(bufs) - 1
+
+        def release(bid):
+            if reuse_scratch:
+                free_pool.append((bid, bufs[bid]))
+
+        def add_f(t):
+            t = t.detach().to(dev, torch.float32).reshape(-1)
+            off = wf_len[0]
+            wf_parts.append(t)
+            wf_len[0] += t.numel()
+            return off
+
+        def add_b(t):
+            t = t.detach().to(dev, torch.float32).reshape(-1)
+            pad = (-t.numel()) % 64
+            if pad:
+                t = torch.cat([t, torch.zeros(pad, device=dev)])
+            off = wb_len[0]
+            wb_parts.append(t.to(torch.bfloat16))
+            wb_len[0] += t.numel()
+            return off
+
+        def op(*f):
+            f = list(f) + [0] * (16 - len(f))
+            ops.append([int(v) for v in f])
+
+        def conv(src, C_in, H_, W_, w, b, out_buf, ksize=3, stride=1, skips=(), skip_w=None, skip_b=None, residual=-1,
+                 C_out_pad=None):
+            C_out = w.shape[0]
+            wk = w.detach().float()
+            wk = wk.permute(0, 2, 3, 1).reshape(C_out, -1) if wk.dim() == 4 else wk.reshape(C_out, -1)
+            bias = b.detach().float()
+            if skips:
+                wk = torch.cat([wk, skip_w.detach().float().reshape(C_out, -1)], dim=1)
+                bias = bias + skip_b.detach().float()
+            if C_out_pad and C_out_pad > C_out:
+                wk = torch.cat([wk, torch.zeros(C_out_pad - C_out, wk.shape[1], device=wk.device)], dim=0)
+                bias = torch.cat([bias, torch.zeros(C_out_pad - C_out, device=bias.device)])
+            s = list(skips) + [(-1, 0)] * (2 - len(skips))
+            op(OP_CONV, src, out_buf, s[0][0], s[0][1], s[1][0], s[1][1], residual, H_, W_, C_in, C_out, ksize, stride,
+               add_b(wk), add_f(bias))
+
+        ss_off = [0]
+        emb_w, emb_b = [], []
+
+        def resblock(rb, parts, H_, W_, tag):
+            C_in = sum(c for _, c in parts)
+            C_out = rb.out_channels
+            hw = H_ * W_
+            p = list(parts) + [(-1, 0)] * (2 - len(parts))
+            a1 = new_buf(hw * C_in, tmp=True)
+            op(OP_GN, p[0][0], p[1][0], a1, p[0][1], p[1][1], hw, add_f(rb.in_layers[0].weight), add_f(rb.in_layers[0].bias), -1, 1)
+            h1 = new_buf(hw * C_out, tmp=True)
+            conv(a1, C_in, H_, W_, rb.in_layers[2].weight, rb.in_layers[2].bias, h1)
+            release(a1)
+            a2 = new_buf(hw * C_out, tmp=True)
+            op(OP_GN, h1, -1, a2, C_out, 0, hw, add_f(rb.out_layers[0].weight), add_f(rb.out_layers[0].bias), ss_off[0], 1)
+            emb_w.append(rb.emb_layers[1].weight)
+            emb_b.append(rb.emb_layers[1].bias)
+            ss_off[0] += 2 * C_out
+            release(h1)
+            out = new_buf(hw * C_out)
+            names[tag] = out
+            if isinstance(rb.skip_connection, nn.Identity):
+                assert len(parts) == 1
+                conv(a2, C_out, H_, W_, rb.out_layers[3].weight, rb.out_layers[3].bias, out, residual=parts[0][0])
+            else:
+                conv(a2, C_out, H_, W_, rb.out_layers[3].weight, rb.out_layers[3].bias, out, skips=parts,
+                     skip_w=rb.skip_connection.weight, skip_b=rb.skip_connection.bias)
+            release(a2)
+            return out, C_out
+
+        def attention(at, src, C, H_, W_, tag):
+            L = H_ * W_
+            xn = new_buf(L * C, tmp=True)
+            op(OP_GN, src, -1, xn, C, 0, L, add_f(at.norm.weight), add_f(at.norm.bias), -1, 0)
+            qkv = new_buf(L * 3 * C, tmp=True)
+            conv(xn, C, H_, W_, at.qkv.weight, at.qkv.bias, qkv, ksize=1)
+            release(xn)
+            ao = new_buf(L * C, tmp=True)
+            op(OP_ATTN, qkv, ao, L, C, nh)
+            release(qkv)
+            out = new_buf(L * C)
+            names[tag] = out
+            conv(ao, C, H_, W_, at.proj_out.weight, at.proj_out.bias, out, ksize=1, residual=src)
+            release(ao)
+            return out
+
+        def run_block(block, parts, H_, W_, tag):
+            h, C = None, None
+            for j in range(len(list(block.children()))):
+                layer = block[j]
+                if isinstance(layer, _ResBlockParams):
+                    h, C = resblock(layer, parts, H_, W_, "%s.%d" % (tag, j))
+                elif isinstance(layer, _AttentionParams):
+                    h = attention(layer, h, C, H_, W_, "%s.%d" % (tag, j))
+                elif isinstance(layer, _DownParams):
+                    (src, C), = parts
+                    h = new_buf((H_ // 2) * (W_ // 2) * C)
+                    names["%s.%d" % (tag, j)] = h
+                    conv(src, C, H_, W_, layer.op.weight, layer.op.bias, h, stride=2)
+                    H_, W_ = H_ // 2, W_ // 2
+                elif isinstance(layer, _UpParams):
+                    up = new_buf(4 * H_ * W_ * C, tmp=True)
+                    op(OP_UP, h, up, H_, W_, C)
+                    H_, W_ = 2 * H_, 2 * W_
+                    h2 = new_buf(H_ * W_ * C)
+                    names["%s.%d" % (tag, j)] = h2
+                    conv(up, C, H_, W_, layer.conv.weight, layer.conv.bias, h2)
+                    release(up)
+                    h = h2
+                else:
+                    raise TypeError(type(layer))
+            return h, C, H_, W_
+
+        # input conv (unet.py:347)
+        c0 = self.input_blocks[0][0]
+        h = new_buf(H * W * mc)
+        names["input_blocks.0"] = h
+        op(OP_CONV_IN, h, self.in_channels, mc, H, W, add_f(c0.weight.reshape(mc, -1)), add_f(c0.bias))
+        C, Hc, Wc = mc, H, W
+        hs = [(h, C)]
+        for i in range(1, len(self.input_blocks)):
+            h, C, Hc, Wc = run_block(self.input_blocks[i], [(h, C)], Hc, Wc, "input_blocks.%d" % i)
+            hs.append((h, C))
+        h, C, Hc, Wc = run_block(self.middle_block, [(h, C)], Hc, Wc, "middle_block")
+        for i, blk in enumerate(self.output_blocks):
+            skip = hs.pop()
+            h, C, Hc, Wc = run_block(blk, [(h, C), skip], Hc, Wc, "output_blocks.%d" % i)
+        a = new_buf(Hc * Wc * C, tmp=True)
+        op(OP_GN, h, -1, a, C, 0, Hc * Wc, add_f(self.out[0].weight), add_f(self.out[0].bias), -1, 1)
+        conv(a, C, Hc, Wc, self.out[2].weight, self.out[2].bias, -1, C_out_pad=16)
+        ss_total = ss_off[0]
+        te = self.time_embed
+        p_w0T, p_b0 = add_f(te[0].weight.detach().float().t().contiguous()), add_f(te[0].bias)
+        p_w2T, p_b2 = add_f(te[2].weight.detach().float().t().contiguous()), add_f(te[2].bias)
+        p_wallT = add_f(torch.cat([w.detach().float() for w in emb_w], dim=0).t().contiguous())
+        p_ball = add_f(torch.cat([b.detach().float() for b in emb_b], dim=0))
+        header = [len(ops), len(bufs), self.in_channels, self.out_channels, H, W, mc, ss_total, p_w0T, p_b0, p_w2T, p_b2,
+                  p_wallT, p_ball, 0, 0]
+        return dict(header=header, ops=ops, bufs=bufs, wb=torch.cat(wb_parts).contiguous(), wf=torch.cat(wf_parts).contiguous(),
+                    names=names)
+
+    # ------------------------------------------------------------------ engine
+    def engine(self, H, W, max_batch, reuse_scratch=True):
+        """Create (or fetch) the CUDA engine for this resolution / batch capacity."""
+        from . import _unet_lib
+        key = (H, W, reuse_scratch)
+        version = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        ent = self._engines.get(key)
+        if ent is not None and (ent.version != version or ent.max_batch < max_batch):
+            ent.close()
+            ent = None
+        if ent is None:
+            prog = self.build_program(H, W, reuse_scratch)
+            ent = _unet_lib.Engine(prog, max_batch, version)
+            self._engines[key] = ent
+        return ent
+
+    def forward(self, x, timesteps, y=None, out=None):
+        """x: (B, C, H, W) CUDA fp32; timesteps: (B,) already-scaled floats (unet.py:463).  Returns fp32 NCHW."""
+        assert y is None, "must specify y if and only if the model is class-conditional"
+        dev = next(self.parameters()).device
+        _lib.require_cuda(dev)
+        B, _, H, W = x.shape
+        eng = self.engine(H, W, B)
+        xin = x.to(dev, torch.float32).contiguous()
+        t = timesteps.to(dev, torch.float32).reshape(-1).contiguous()
+        if t.numel() != B:
+            t = t.expand(B).contiguous()
+        uniform = bool((t == t[0]).all().item()) if B > 1 else True
+        if out is None:
+            out = torch.empty((B, self.out_channels, H, W), device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            eng.forward(xin, t[:1].contiguous() if uniform else t, None, 0.0, out, B)
+        return out
+
+    def sample_loop(self, x, dlpm, T, mode, flags, hist, seed, z_offset, sample_base, graph_cache=None, progress=False):
+        """The image-config hot loop: per step  eps = UNet(x, t/T)  then the fused update (K3), with the step index
+        in a device counter so ONE captured CUDA graph is replayed T-1 times."""
+        from . import _unet_lib
+        _unet_lib.run_sample_loop(self, x, dlpm, T, mode, flags, hist, seed, z_offset, sample_base, graph_cache, progress)
+
+
 def _unet_from_reference(ref, device):
-    raise NotImplementedError("UNet engine not built yet")
+    """Ingest a reference ``UNetModel`` instance (dlpm/models/unet.py) by hyper-parameters + state_dict."""
+    m = UNetModel(in_channels=ref.in_channels, model_channels=ref.model_channels, out_channels=ref.out_channels,
+                  num_res_blocks=ref.num_res_blocks, attention_resolutions=tuple(ref.attention_resolutions),
+                  dropout=ref.dropout, channel_mult=tuple(ref.channel_mult), conv_resample=ref.conv_resample,
+                  num_classes=ref.num_classes, num_heads=ref.num_heads, num_heads_upsample=ref.num_heads_upsample,
+                  use_scale_shift_norm=True)
+    m.load_state_dict(ref.state_dict(), strict=True)
+    return m.to(device).eval()

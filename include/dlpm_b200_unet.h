@@ -1,0 +1,83 @@
+/* dlpm_b200_unet.h -- C ABI of the image score network (K5-K7) in libdlpm_b200.so.
+ *
+ * Replaces UNetModel.forward (dlpm/models/unet.py:463-492) and its sub-modules.  Activations are
+ * NHWC bf16 in HBM, accumulation and normalisation statistics are fp32.  Same conventions as
+ * dlpm_b200.h (device pointers, void* stream, 0 / negative return, dlpm_b200_last_error()).
+ */
+#ifndef DLPM_B200_UNET_H_
+#define DLPM_B200_UNET_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DLPM_CONV_OUT_BF16_NHWC 0
+#define DLPM_CONV_OUT_F32_NCHW 1
+
+/* K5. 3x3 (pad 1) / 1x1 convolution, stride 1 or 2, as an implicit GEMM on tcgen05 tensor cores
+ * (nn.Conv2d at unet.py:64,96,143,157,164-168,214-215,347,435).
+ *   in        NHWC bf16 [B, H, W, C_in]                       (C_in multiple of 32)
+ *   w         bf16 [C_out_pad][ksize*ksize*C_in + C_s0 + C_s1], K index = (ky*ksize+kx)*C_in + c, then the
+ *             1x1 skip-conv weights for skip0 and skip1 (ResBlock.skip_connection fused into the K loop)
+ *   bias      fp32 [C_out_pad]
+ *   skip0/1   optional NHWC bf16 [B, H/stride, W/stride, C_s*] inputs of the fused 1x1 skip conv (or NULL, 0)
+ *   residual  optional NHWC bf16 [B, H/stride, W/stride, C_out] added in the epilogue (identity skip)
+ *   out       DLPM_CONV_OUT_BF16_NHWC: bf16 [B, H/stride, W/stride, C_out] (C_out multiple of 16)
+ *             DLPM_CONV_OUT_F32_NCHW : fp32 [B, C_out, H, W], C_out <= 16 and w/bias zero-padded to 16 rows
+ */
+int dlpm_b200_conv2d(const void* in, const void* w, const float* bias, const void* skip0, int C_s0, const void* skip1,
+                     int C_s1, const void* residual, void* out, int out_mode, int64_t B, int H, int W, int C_in,
+                     int C_out, int ksize, int stride, void* stream);
+
+/* K6. GroupNorm(min(32,C) groups, eps 1e-5) over the virtual concatenation [in0 | in1] of two NHWC bf16
+ * tensors, optional scale-shift conditioning y = GN(x) * (1 + scale) + shift, optional SiLU; bf16 NHWC out
+ * (GroupNorm32 + SiLU + use_scale_shift_norm of unet.py:141-142,153-154,188-191,212,433-434; nn.py:17-19).
+ *   gamma, beta   fp32 [C0 + C1];   ss: NULL or fp32 [ss_rows][ss_stride] with scale at [ss_off, ss_off+C) and
+ *   shift at [ss_off+C, ss_off+2C); ss_rows is 1 (batch-constant timestep) or B. */
+int dlpm_b200_groupnorm_silu(void* out, const void* in0, int C0, const void* in1, int C1, int64_t B, int HW,
+                             const float* gamma, const float* beta, const float* ss, int ss_rows, int64_t ss_stride,
+                             int64_t ss_off, int apply_silu, void* stream);
+
+/* K7. QKVAttention (unet.py:231-250): qkv NHWC bf16 [B, L, 3C] with the reference's channel order (per head:
+ * q, k, v blocks of C/heads channels), out NHWC bf16 [B, L, C].  L <= 1024, C/heads <= 64. */
+int dlpm_b200_attention(void* out, const void* qkv, int64_t B, int L, int C, int heads, void* stream);
+
+/* Input conv (unet.py:347): x NCHW fp32 [B, C_in<=4, H, W] -> NHWC bf16 [B, H, W, C_out]; w fp32 [C_out][C_in*9]. */
+int dlpm_b200_conv_in(void* out, const float* x, const float* w, const float* bias, int64_t B, int C_in, int C_out, int H,
+                      int W, void* stream);
+
+/* Nearest x2 upsample (unet.py:73), NHWC bf16 [B,H,W,C] -> [B,2H,2W,C]. */
+int dlpm_b200_upsample2x(void* out, const void* in, int64_t B, int H, int W, int C, void* stream);
+
+/* Timestep embedding + every ResBlock's emb_layers in two launches (nn.py:103-121; unet.py:335-339,145-151,477):
+ *   semb = SiLU(time_embed(timestep_embedding(t, mc)))  [rows][4mc];  ss = semb @ W_all^T + b_all  [rows][ss_total].
+ * t: device float[rows] or NULL with t_dev (device int*) -> t = *t_dev * inv_T (CUDA-graph replay).
+ * Weights in-major fp32: w0T [mc][4mc], b0, w2T [4mc][4mc], b2, wallT [4mc][ss_total], ball. */
+int dlpm_b200_time_embedding(float* ss, float* semb, const float* t, const int* t_dev, float inv_T, int rows, int mc,
+                             int64_t ss_total, const float* w0T, const float* b0, const float* w2T, const float* b2,
+                             const float* wallT, const float* ball, void* stream);
+
+/* ---- whole network behind one handle ------------------------------------------------------------
+ * The Python host (dlpm_b200/score_nets.py::UNetModel) walks the architecture (unet.py:343-437) and hands
+ * over an op list + two packed weight blobs; the engine owns activation buffers and TMA descriptors.
+ *   header  int64[16] : {n_ops, n_bufs, in_ch, out_ch, H, W, model_channels, ss_total,
+ *                        p_w0T, p_b0, p_w2T, p_b2, p_wallT, p_ball, 0, 0}   (p_* = fp32-blob offsets)
+ *   ops     int64[n_ops][16], bufs int64[n_bufs] = bf16 elements per sample of each activation buffer
+ *   wb      bf16 blob (conv weights, device), wf fp32 blob (everything else, device); both are copied. */
+int dlpm_b200_unet_create(void** handle, const int64_t* header, const int64_t* ops, const int64_t* bufs, const void* wb,
+                          int64_t n_wb, const float* wf, int64_t n_wf, int64_t max_batch);
+/* eps = UNet(x, t): x fp32 NCHW [B,in_ch,H,W]; t device float[t_rows] (t_rows = 1: batch-constant, or B), or
+ * t_dev/inv_T as above; out fp32 NCHW [B,out_ch,H,W]. */
+int dlpm_b200_unet_forward(void* handle, const float* x, const float* t, int t_rows, const int* t_dev, float inv_T,
+                           float* out, int64_t B, void* stream);
+/* debugging / per-layer parity: copy activation buffer `buf` (bf16, B * elems) of the last forward to dst. */
+int dlpm_b200_unet_copy_buffer(void* handle, int buf, void* dst, int64_t B, void* stream);
+int64_t dlpm_b200_unet_workspace_bytes(void* handle);
+int dlpm_b200_unet_num_launches(void* handle);
+int dlpm_b200_unet_destroy(void* handle);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DLPM_B200_UNET_H_ */

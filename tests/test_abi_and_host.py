@@ -1,0 +1,166 @@
+"""CPU: the C-ABI library loads and exports every symbol the headers declare (no compute calls -- there is no GPU
+here), the ctypes table matches the headers, and the host-side logic (schedules, Generator kwargs merging, error
+behaviour, LIM coefficient table, architecture walk) agrees with the oracle / golden vectors."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+
+
+def header_symbols():
+    syms = {}
+    for h in ("dlpm_b200.h", "dlpm_b200_unet.h"):
+        src = open(os.path.join(ROOT, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        for m in re.finditer(r"\b(int|int64_t|const char\*)\s+(dlpm_b200_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+            args = [a.strip() for a in m.group(3).split(",") if a.strip() and a.strip() != "void"]
+            syms[m.group(2)] = len(args)
+    return syms
+
+
+def test_library_exports_every_declared_symbol():
+    from dlpm_b200 import _lib, _unet_lib, build
+    if not os.path.exists(_lib.LIB_PATH):
+        build.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    syms = header_symbols()
+    assert len(syms) >= 27
+    for name in syms:
+        assert hasattr(lib, name), "missing export: " + name
+    lib.dlpm_b200_abi_version.restype = ctypes.c_int
+    assert lib.dlpm_b200_abi_version() == 1
+    # the ctypes signature table covers the headers and agrees on arity
+    table = dict(_lib.SIGNATURES)
+    table.update(_unet_lib.UNET_SIGNATURES)
+    for name, nargs in syms.items():
+        if name in ("dlpm_b200_abi_version", "dlpm_b200_last_error", "dlpm_b200_unet_workspace_bytes"):
+            continue
+        assert name in table, "no ctypes signature for " + name
+        assert len(table[name]) == nargs, (name, len(table[name]), nargs)
+
+
+def test_no_cpu_fallback_and_loud_failures():
+    import dlpm_b200
+    from dlpm_b200 import _lib
+    with pytest.raises(_lib.DlpmB200Error, match="CUDA devices only"):
+        dlpm_b200.gen_skewed_levy(1.7, (4, 4), device="cpu")
+    with pytest.raises(Exception, match="Wrong value of alpha"):
+        dlpm_b200.gen_skewed_levy(0.0, (4, 4), device="cpu")
+    with pytest.raises(_lib.DlpmB200Error):
+        _lib.ptr(torch.zeros(3))
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.DlpmB200Error):
+            _lib.require_cuda("cuda")
+    # the product never imports the oracle
+    import subprocess
+    import sys
+    code = "import sys; import dlpm_b200, dlpm_b200.score_nets, dlpm_b200._unet_lib; assert not any(m.split('.')[0]=='oracle' for m in sys.modules)"
+    assert subprocess.run([sys.executable, "-c", code], cwd=ROOT).returncode == 0
+    for base, _, files in os.walk(os.path.join(ROOT, "dlpm_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                assert "oracle" not in open(os.path.join(base, f)).read().replace("oracle/", ""), f
+
+
+def test_host_schedule_bit_exact_vs_reference_golden():
+    from dlpm_b200.methods.dlpm import DLPM
+    g = load_golden("schedule")
+    for key in g.files:
+        a, T, kind = key.split("_")
+        alpha, T = float(a[1:]), int(T[1:])
+        d = DLPM(alpha, "cpu", T, scale="scale_exploding") if kind == "exploding" else DLPM(alpha, "cpu", T, time_spacing=kind)
+        got = torch.stack([d.gammas, d.bargammas, d.sigmas, d.barsigmas]).numpy()
+        assert np.array_equal(got, g[key], equal_nan=True), key
+        assert np.array_equal(d.sched.numpy(), g[key].T, equal_nan=True)
+    d = DLPM(1.7, "cpu", 50)
+    d.rescale_diffusion(10)
+    assert d.gammas.shape[0] == 10 and d.sched.shape == (10, 4)
+    with pytest.raises(AssertionError):
+        d.rescale_diffusion(10.0)
+
+
+def test_generator_kwargs_semantics():
+    from dlpm_b200 import Generator
+    gen = Generator("skewed_levy", alpha=1.7, device="cpu", isotropic=True, clamp_a=None)
+    gen.setParams(clamp_a=20)
+    assert gen.kwargs["clamp_a"] == 20 and gen.kwargs["alpha"] == 1.7
+    with pytest.raises(Exception, match="Given void parameters"):
+        gen.setParams()
+    with pytest.raises(Exception, match="Unknown distribution"):
+        Generator("gmm_2")
+    with pytest.raises(Exception):  # reaches the kernel wrapper, which refuses non-CUDA devices
+        gen.generate(size=(4, 2))
+    assert "clamp_a" in str(gen.getSignature())
+
+
+def test_glp_constructor_contract():
+    from dlpm_b200 import GenerativeLevyProcess, ModelMeanType
+    glp = GenerativeLevyProcess(1.7, "cpu", 100, rescale_timesteps=True)
+    assert glp.dlpm.gammas.shape == (100,) and glp.reverse_steps == 100 and not glp.LIM
+    assert torch.equal(glp.get_timesteps(5), torch.arange(5, dtype=torch.float32))
+    assert torch.allclose(glp._scale_timesteps(torch.tensor([50])), torch.tensor([0.5]))
+    with pytest.raises(AssertionError):
+        GenerativeLevyProcess(1.7, "cpu", 100, model_mean_type=ModelMeanType.START_X)
+    with pytest.raises(AssertionError):
+        GenerativeLevyProcess(1.7, "cpu", 100, LIM=True, rescale_timesteps=False)
+    lim = GenerativeLevyProcess(1.7, "cpu", 100, LIM=True, rescale_timesteps=True)
+    assert abs(lim.sde.T - 0.9946) < 1e-9
+    with pytest.raises(AssertionError, match="time spacing"):
+        glp.sample({"default": None}, [2, 1, 2], 100, time_spacing="quadratic")
+
+
+def test_lim_table_matches_oracle():
+    from dlpm_b200.methods.lim import VPSDE, lim_step_table
+    from oracle import process
+    for ode in (False, True):
+        ts, coef = lim_step_table(VPSDE(1.7), 25, ode)
+        sde = process.VPSDE(1.7)
+        sc, a, cs, cn = process.lim_coefficients(sde, ts[:-1], ts[1:], ode)
+        assert torch.equal(coef[:, 0], sc) and torch.equal(coef[:, 1], a) and torch.equal(coef[:, 2], cs)
+        if not ode:
+            assert torch.equal(coef[:, 3], cn)
+
+
+def test_unet_program_matches_oracle_block_plan():
+    from dlpm_b200.score_nets import OP_ATTN, OP_CONV, OP_GN, UNetModel
+    from oracle import nets
+    for mc, attn in ((128, (16,)), (32, (2, 4))):
+        m = UNetModel(3, mc, 3, 2, attn, channel_mult=(1, 2, 2, 2), num_heads=4, use_scale_shift_norm=True)
+        prog = m.build_program(32, 32)
+        inp, out = nets.unet_block_plan(mc, (1, 2, 2, 2), 2, attn)
+        n_res = sum(l.count("res") for l in inp + out) + 2
+        n_attn = sum(l.count("attn") for l in inp + out) + 1
+        ops = [o[0] for o in prog["ops"]]
+        assert ops.count(OP_ATTN) == n_attn
+        assert ops.count(OP_GN) == 2 * n_res + n_attn + 1
+        n_updown = sum(l.count("up") + l.count("down") for l in inp + out)
+        assert ops.count(OP_CONV) == 2 * n_res + 2 * n_attn + n_updown + 1
+        assert prog["header"][7] == sum(2 * b.out_channels for b in m.modules() if hasattr(b, "emb_layers"))
+        assert prog["wb"].dtype == torch.bfloat16 and prog["wb"].numel() % 64 == 0
+    # state_dict key set equals the oracle's expectations (keys it reads exist)
+    sd = m.state_dict()
+    for k in ("time_embed.0.weight", "input_blocks.0.0.weight", "middle_block.1.qkv.weight", "out.2.bias",
+              "input_blocks.3.0.op.weight", "output_blocks.2.1.conv.weight", "output_blocks.0.0.skip_connection.weight"):
+        assert k in sd, k
+
+
+def test_mlp_packing_layout():
+    from dlpm_b200.score_nets import MLPModel
+    p = {"data": {"nfeatures": 2}, "method": "dlpm", "dlpm": {"isotropic": True}, "device": "cpu",
+         "model": dict(use_a_t=False, no_a=True, a_pos_emb=False, a_emb_size=32, time_emb_type="learnable", time_emb_size=32,
+                       nblocks=4, nunits=64, skip_connection=True, group_norm=True, dropout_rate=0.0, learn_variance=False)}
+    m = MLPModel(p)
+    w = m.packed_weights()
+    E, U, F, NB = 32, 64, 2, 5
+    main0 = 3 * E + E * E + NB * (E * U + U)
+    assert w.numel() == main0 + F * U + 3 * U + NB * (2 * U * U + 6 * U) + F * U + 4
+    assert torch.equal(w[main0:main0 + F * U].reshape(F, U), m.linear_in.weight.t())
+    with pytest.raises(NotImplementedError):
+        bad = dict(p)
+        bad["model"] = dict(p["model"], time_emb_type="sinusoidal")
+        MLPModel(bad)

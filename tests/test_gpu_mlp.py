@@ -1,0 +1,124 @@
+"""GPU: K4 fused MLP forward and the persistent whole-chain sampler vs golden vectors from the reference."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, sub
+
+pytestmark = pytest.mark.gpu
+
+
+def mlp_params():
+    return {"data": {"nfeatures": 2}, "method": "dlpm", "dlpm": {"isotropic": True}, "device": "cuda",
+            "model": dict(use_a_t=False, no_a=True, a_pos_emb=False, a_emb_size=32, time_emb_type="learnable",
+                          time_emb_size=32, nblocks=4, nunits=64, skip_connection=True, group_norm=True, dropout_rate=0.0,
+                          learn_variance=False)}
+
+
+@pytest.fixture(scope="module")
+def model():
+    from dlpm_b200.score_nets import MLPModel
+    g = load_golden("mlp_chain")
+    m = MLPModel(mlp_params())
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sub(g, "sd").items()}, strict=True)
+    return m.cuda().eval()
+
+
+def test_mlp_forward_golden(model):
+    g = load_golden("mlp_chain")
+    f = sub(g, "fwd")
+    y = model(torch.from_numpy(f["x"]).cuda(), torch.from_numpy(f["t"]).cuda())
+    np.testing.assert_allclose(y.cpu().numpy(), f["y"], rtol=1e-4, atol=1e-5)  # fp32 bar: rtol 1e-3
+    # ragged batch (not a multiple of the 64-sample tile) and a batch spanning several CTAs
+    x = torch.randn(1000, 1, 2).cuda()
+    t = torch.rand(1000).cuda()
+    big = model(x, t)
+    small = model(x[:77], t[:77])
+    assert torch.equal(big[:77], small)
+
+
+@pytest.mark.parametrize("tag,kw", [("dlpm", {}), ("dlpm_clip", dict(clip_denoised=True)), ("dlpm_clampa", {})])
+def test_chain_golden_injected_noise(model, tag, kw):
+    """Free-running T=50 chain with the reference's A, x_T and z injected (north-star tolerance rtol 1e-3 regime;
+    1-ulp differences are amplified along the chain, see tests/test_oracle_golden.py)."""
+    from dlpm_b200 import GenerativeLevyProcess
+    g = load_golden("mlp_chain")
+    r = sub(g, tag)
+    T, B = r["A"].shape
+    glp = GenerativeLevyProcess(1.7, "cuda", T, rescale_timesteps=True, isotropic=True)
+    final, hist = glp.p_sample_loop(model, list(r["x_init"].shape), noise=torch.from_numpy(r["x_init"]),
+                                    injected_A=torch.from_numpy(r["A"]), injected_z=torch.from_numpy(r["z"]),
+                                    get_sample_history=True, **kw)
+    assert hist.shape == r["hist"].shape
+    np.testing.assert_allclose(glp.dlpm.Sigmas.cpu().numpy(), r["Sigmas"], rtol=0, atol=0)
+    np.testing.assert_allclose(hist.cpu().numpy(), r["hist"], rtol=5e-3, atol=2e-3)
+    np.testing.assert_allclose(final.cpu().numpy(), r["final"], rtol=5e-3, atol=2e-3)
+
+
+def test_dlim_chain_golden(model):
+    from dlpm_b200 import GenerativeLevyProcess
+    g = load_golden("mlp_chain")
+    r = sub(g, "dlim")
+    T, B = r["A"].shape
+    glp = GenerativeLevyProcess(1.7, "cuda", T, rescale_timesteps=True, isotropic=True)
+    final, hist = glp.ddim_sample_loop(model, list(r["x_init"].shape), noise=torch.from_numpy(r["x_init"]), eta=0.0,
+                                       injected_A=torch.from_numpy(r["A"]), get_sample_history=True)
+    np.testing.assert_allclose(hist.cpu().numpy(), r["hist"], rtol=5e-3, atol=2e-3)
+    with pytest.raises(NotImplementedError):
+        glp.ddim_sample_loop(model, [4, 1, 2], eta=1.0)
+
+
+@pytest.mark.parametrize("tag,ode", [("lim_sde", False), ("lim_ode", True)])
+def test_lim_chain_golden(model, tag, ode):
+    from dlpm_b200 import GenerativeLevyProcess
+    g = load_golden("mlp_chain")
+    r = sub(g, tag)
+    steps = r["e_L"].shape[0]
+    glp = GenerativeLevyProcess(1.7, "cuda", steps, rescale_timesteps=True, isotropic=True, LIM=True)
+    final, hist = glp.lim_sample(model, list(r["x_init"].shape), ddim=ode, get_sample_history=True,
+                                 injected_x=torch.from_numpy(r["x_init"]), injected_noise=torch.from_numpy(r["e_L"]))
+    np.testing.assert_allclose(hist.cpu().numpy(), r["hist"], rtol=5e-3, atol=2e-3)
+
+
+def test_chain_kernel_equals_stepwise_kernels(model):
+    """The persistent chain (one launch) and the per-step path (forward kernel + K3) draw the same Philox noise
+    and must agree to rounding."""
+    from dlpm_b200 import GenerativeLevyProcess, rng
+    T, B = 30, 300
+    outs = []
+    for force_stepwise in (False, True):
+        glp = GenerativeLevyProcess(1.7, "cuda", T, rescale_timesteps=True, isotropic=True)
+        st = rng.PhiloxState(seed=99, offset=0)
+        m = model
+        if force_stepwise:
+            class Wrap(torch.nn.Module):  # hides native_kind -> generic per-step path
+                def __init__(self, inner):
+                    super().__init__()
+                    self.inner = inner
+
+                def forward(self, x, t):
+                    return self.inner(x, t)
+            m = Wrap(model)
+        x = glp.p_sample_loop(m, [B, 1, 2], state=st)
+        outs.append(x)
+    np.testing.assert_allclose(outs[0].cpu().numpy(), outs[1].cpu().numpy(), rtol=2e-3, atol=2e-3)
+
+
+def test_sample_api_and_training_loss(model):
+    from dlpm_b200 import GenerativeLevyProcess, manual_seed
+    manual_seed(7)
+    glp = GenerativeLevyProcess(1.7, "cuda", 100, rescale_timesteps=True, isotropic=True)
+    x = glp.sample({"default": model}, [512, 1, 2], reverse_steps=100, clamp_a=None, clamp_eps=None)
+    assert x.shape == (512, 1, 2) and x.is_cuda and torch.isfinite(x).all()
+    x2, hist = glp.sample({"default": model}, [64, 1, 2], reverse_steps=20, get_sample_history=True)
+    assert hist.shape == (20, 64, 1, 2) and glp.reverse_steps == 100 and glp.dlpm.gammas.shape[0] == 100
+    xd = glp.sample({"default": model}, [64, 1, 2], reverse_steps=100, deterministic=True, dlim_eta=0.0)
+    assert torch.isfinite(xd).all()
+    # training loss with injected t / A / z vs the reference value
+    g = load_golden("mlp_chain")
+    r = sub(g, "train")
+    loss = glp.training_losses({"default": model}, torch.from_numpy(r["x0"]), loss_type="EPS_LOSS", lploss=2.0,
+                               injected=dict(t=torch.from_numpy(r["t"]), A=torch.from_numpy(r["A"]), z=torch.from_numpy(r["z"])))
+    np.testing.assert_allclose(loss["loss"].item(), float(r["loss"]), rtol=1e-4)
+    free = glp.training_losses({"default": model}, torch.randn(256, 1, 2), loss_type="EPS_LOSS")["loss"]
+    assert torch.isfinite(free) and free.dim() == 0

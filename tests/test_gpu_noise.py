@@ -1,0 +1,110 @@
+"""GPU: K1 alpha-stable noise kernels vs the oracle / scipy (distributional parity: KS + quantiles +
+closed-form Laplace transform), plus determinism and shard invariance of the Philox streams."""
+import numpy as np
+import pytest
+import scipy.stats
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import stable  # noqa: E402
+
+ALPHAS = (1.5, 1.7, 1.9)
+
+
+@pytest.fixture(scope="module")
+def dl():
+    import dlpm_b200
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    dlpm_b200.manual_seed(1234)
+    return dlpm_b200
+
+
+@pytest.mark.parametrize("alpha", ALPHAS)
+def test_skewed_levy_distribution(dl, alpha):
+    n = 400000
+    A = dl.gen_skewed_levy(alpha, (n, 4), device="cuda", isotropic=False).cpu().numpy().astype(np.float64).ravel()
+    ref = stable.gen_skewed_levy(alpha, (A.size,), isotropic=False, rng=np.random.RandomState(7)).astype(np.float64)
+    assert np.all(np.isfinite(A)) and A.min() > 0
+    ks = scipy.stats.ks_2samp(A[:400000], ref[:400000])
+    assert ks.statistic < 0.004, ks  # two-sample KS at n=4e5: 99.9% critical value ~ 0.0044
+    qs = [0.001, 0.01, 0.1, 0.25, 0.5, 0.75, 0.9, 0.99, 0.999, 0.9999]
+    qa, qr = np.quantile(A, qs), np.quantile(ref, qs)
+    np.testing.assert_allclose(qa[:9], qr[:9], rtol=0.04)
+    np.testing.assert_allclose(qa[9], qr[9], rtol=0.25)  # extreme tail: sampling noise dominates
+    # closed form: E exp(-A/2) = exp(-1)
+    assert abs(np.exp(-A / 2).mean() - np.exp(-1.0)) < 2e-3
+
+
+@pytest.mark.parametrize("alpha", ALPHAS)
+def test_sas_distribution_vs_scipy_cdf(dl, alpha):
+    e = dl.gen_sas(alpha, (300000, 4), device="cuda", isotropic=False).cpu().numpy().astype(np.float64).ravel()
+    ref = stable.gen_sas(alpha, (e.size,), isotropic=False, rng=np.random.RandomState(9)).astype(np.float64)
+    ks = scipy.stats.ks_2samp(e, ref)
+    assert ks.statistic < 0.004, ks
+    qs = [0.001, 0.01, 0.1, 0.25, 0.5, 0.75, 0.9, 0.99, 0.999]
+    np.testing.assert_allclose(np.quantile(e, qs), np.quantile(ref, qs), rtol=0.06, atol=0.02)
+    # SaS(alpha, scale 1) cdf from scipy on a subsample (levy_stable.cdf is slow)
+    sub = e[:3000]
+    ks1 = scipy.stats.kstest(sub, lambda v: scipy.stats.levy_stable.cdf(v, alpha, 0))
+    assert ks1.pvalue > 1e-3, ks1
+
+
+def test_alpha_2_is_degenerate(dl):
+    A = dl.gen_skewed_levy(2.0, (1000, 8), device="cuda", isotropic=False)
+    assert torch.all(A == 2.0)
+    e = dl.gen_sas(2.0, (200000, 4), device="cuda", isotropic=True).cpu().numpy().ravel()
+    assert abs(e.var() - 2.0) < 0.03 and abs(e.mean()) < 0.01  # sqrt(2) * N(0,1)
+
+
+def test_isotropic_layout_and_clamps(dl):
+    A = dl.gen_skewed_levy(1.7, (512, 3, 8, 8), device="cuda", isotropic=True, clamp_a=20.0)
+    assert A.shape == (512, 3, 8, 8)
+    flat = A.reshape(512, -1)
+    assert torch.all(flat == flat[:, :1]), "isotropic: one draw per sample, replicated"
+    assert flat.max() <= 20.0 and flat.min() >= 0.0
+    assert (flat[:, 0] == 20.0).float().mean() > 0.001  # the clamp does bite at alpha=1.7
+    e = dl.gen_sas(1.7, (512, 3, 8, 8), device="cuda", isotropic=True, clamp_eps=3.0)
+    assert e.abs().max() <= 3.0
+    # odd inner size -> scalar path
+    e2 = dl.gen_sas(1.7, (1000, 1, 2), device="cuda", isotropic=True)
+    assert e2.shape == (1000, 1, 2) and torch.isfinite(e2).all()
+    # isotropic SaS: within a sample the coordinates share A -> ratio test: e / sqrt(A) is N(0,1)
+    Ac = dl.gen_skewed_levy(1.7, (4096,), device="cuda", isotropic=True, compact=True)
+    e3 = dl.gen_sas(1.7, (4096, 64), a=Ac, device="cuda", isotropic=True)
+    g = (e3 / Ac.sqrt()[:, None]).cpu().numpy().ravel()
+    assert abs(g.mean()) < 0.01 and abs(g.std() - 1) < 0.01
+    assert scipy.stats.kstest(g[:100000], "norm").statistic < 0.006
+
+
+def test_normal_kernel_moments(dl):
+    z = dl.gen_normal((1 << 20, 4), device="cuda").cpu().numpy().ravel().astype(np.float64)
+    assert abs(z.mean()) < 2e-3 and abs(z.std() - 1) < 2e-3
+    assert abs(scipy.stats.kurtosis(z)) < 0.02 and abs(scipy.stats.skew(z)) < 0.01
+    assert scipy.stats.kstest(z[:500000], "norm").statistic < 0.003
+    assert np.abs(z).max() > 4.5
+
+
+def test_determinism_and_shard_invariance(dl):
+    from dlpm_b200 import rng
+    st = rng.PhiloxState(seed=42, offset=100)
+    full = dl.gen_sas(1.7, (64, 3, 32, 32), device="cuda", isotropic=True, state=st)
+    st = rng.PhiloxState(seed=42, offset=100)
+    again = dl.gen_sas(1.7, (64, 3, 32, 32), device="cuda", isotropic=True, state=st)
+    assert torch.equal(full, again)
+    # two "ranks", 32 samples each, sample_base = global index of the first local sample
+    parts = []
+    for r in range(2):
+        st = rng.PhiloxState(seed=42, offset=100, sample_base=32 * r)
+        parts.append(dl.gen_sas(1.7, (32, 3, 32, 32), device="cuda", isotropic=True, state=st))
+    assert torch.equal(torch.cat(parts), full)
+    other = dl.gen_sas(1.7, (64, 3, 32, 32), device="cuda", isotropic=True, state=rng.PhiloxState(seed=43, offset=100))
+    assert not torch.equal(other, full)
+
+
+def test_error_behaviour(dl):
+    with pytest.raises(Exception, match="Wrong value of alpha"):
+        dl.gen_skewed_levy(2.5, (4, 4), device="cuda")
+    with pytest.raises(Exception):
+        dl.gen_skewed_levy(1.7, (4, 4), device="cpu")  # no CPU fallback
+    assert dl.gen_sas(1.7, (0, 4), device="cuda").shape == (0, 4)  # empty input

@@ -1,0 +1,176 @@
+"""GPU: K2 (Sigma scan), K3 (fused DLPM / DLIM / LIM steps) and the training-forward kernels against the
+golden vectors generated from the real reference (teacher-forced: bit-level; free-running: rtol 1e-3)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, sub
+
+pytestmark = pytest.mark.gpu
+
+from oracle import nets, process  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def L():
+    import dlpm_b200
+    from dlpm_b200 import _lib
+    assert torch.cuda.is_available()
+    return _lib
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def sched_dev(alpha, T):
+    s = torch.stack(process.gen_noise_schedule(alpha, T), dim=1).contiguous()
+    return s, s.cuda()
+
+
+def test_sigma_scan_matches_reference_bitwise(L):
+    g = load_golden("mlp_chain")
+    r = sub(g, "dlpm")
+    T, B = r["A"].shape
+    _, sd = sched_dev(1.7, T)
+    A = cu(r["A"])
+    Sig = torch.empty_like(A)
+    L.call("dlpm_b200_sigma_scan", L.ptr(Sig), L.ptr(A), None, L.ptr(sd), T, B, 1, 0, 1.7, -1.0, 0, 0, 0, L.stream_ptr())
+    assert np.array_equal(Sig.cpu().numpy(), r["Sigmas"])  # same fp32 op order as dlpm.py:230-239
+
+
+@pytest.mark.parametrize("tag,clip,det", [("dlpm", False, False), ("dlpm_clip", True, False), ("dlpm_clampa", False, False),
+                                          ("dlim", False, True)])
+def test_reverse_step_teacher_forced(L, tag, clip, det):
+    """Feed the reference's x_t and eps(x_t) (oracle net on CPU), compare x_{t-1} with the reference history."""
+    g = load_golden("mlp_chain")
+    r = sub(g, tag)
+    sdict = {k: torch.from_numpy(v) for k, v in sub(g, "sd").items()}
+    T, B = r["A"].shape
+    D = int(np.prod(r["x_init"].shape[1:]))
+    _, sd = sched_dev(1.7, T)
+    Sig = cu(r["Sigmas"])
+    hist = torch.from_numpy(r["hist"])
+    flags = L.STEP_CLIP_DENOISED if clip else 0
+    worst = 0.0
+    for k, t in enumerate(range(T - 1, 0, -1)):
+        x = hist[k].clone()
+        eps = nets.mlp_forward(sdict, 4, x, torch.tensor([t] * B).float() * (1.0 / T))
+        xd, ed = x.cuda().contiguous(), eps.cuda().contiguous()
+        if det:
+            L.call("dlpm_b200_dlim_step", L.ptr(xd), L.ptr(ed), L.ptr(sd), t, None, T, B, D, flags, None, L.stream_ptr())
+        else:
+            zd = cu(r["z"][k])
+            L.call("dlpm_b200_reverse_step", L.ptr(xd), L.ptr(ed), L.ptr(Sig), L.ptr(sd), t, None, T, B, D, flags, L.ptr(zd), 0, 0, 0,
+                   None, L.stream_ptr())
+        got, want = xd.cpu().numpy(), r["hist"][k + 1]
+        np.testing.assert_allclose(got, want, rtol=2e-5, atol=2e-5)
+        worst = max(worst, float(np.abs(got - want).max()))
+    assert worst < 1e-4
+
+
+def test_reverse_step_variants_agree(L):
+    """vector / scalar paths, bf16 eps, device-side step counter and history output."""
+    torch.manual_seed(0)
+    T, B, D = 20, 37, 48
+    _, sd = sched_dev(1.7, T)
+    A = torch.rand(T, B).cuda() * 3 + 0.1
+    Sig = torch.empty_like(A)
+    L.call("dlpm_b200_sigma_scan", L.ptr(Sig), L.ptr(A), None, L.ptr(sd), T, B, 1, 0, 1.7, -1.0, 0, 0, 0, L.stream_ptr())
+    x0 = torch.randn(B, D).cuda()
+    eps = torch.randn(B, D).cuda()
+    z = torch.randn(B, D).cuda()
+    t = 7
+
+    def run(x, e, flags=0, zz=z, t_dev=None, hist=None, Dd=D, Bb=B):
+        x = x.clone()
+        L.call("dlpm_b200_reverse_step", L.ptr(x), L.ptr(e), L.ptr(Sig), L.ptr(sd), t, L.ptr(t_dev), T, Bb, Dd, flags, L.ptr(zz), 5, 11,
+               3, L.ptr(hist), L.stream_ptr())
+        return x
+    ref = run(x0, eps)
+    # oracle
+    sched = process.gen_noise_schedule(1.7, T)
+    want = process.dlpm_step(x0.cpu(), eps.cpu(), z.cpu(), t, Sig.cpu()[:, :, None], sched)
+    np.testing.assert_allclose(ref.cpu().numpy(), want.numpy(), rtol=1e-6, atol=1e-6)
+    # device counter + history
+    td = torch.tensor([t], dtype=torch.int32).cuda()
+    h = torch.empty_like(x0)
+    out = run(x0, eps, t_dev=td, hist=h)
+    assert torch.equal(out, ref) and torch.equal(h, ref)
+    # scalar path (D not multiple of 4): same numbers on the overlapping layout
+    x1, e1, z1 = x0[:, :47].contiguous(), eps[:, :47].contiguous(), z[:, :47].contiguous()
+    out1 = run(x1, e1, zz=z1, Dd=47)
+    assert torch.equal(out1, ref[:, :47])
+    # bf16 eps
+    eb = eps.to(torch.bfloat16)
+    outb = run(x0, eb, flags=L.STEP_EPS_BF16)
+    refb = run(x0, eb.float())
+    assert torch.equal(outb, refb)
+    # in-kernel noise: deterministic, N(0,1)-driven: (x' - mean)/sd is standard normal
+    a = run(x0, eps, zz=None)
+    b = run(x0, eps, zz=None)
+    assert torch.equal(a, b)
+    mean = run(x0, eps, zz=torch.zeros_like(z))
+    one = run(x0, eps, zz=torch.ones_like(z))
+    zhat = ((a - mean) / (one - mean)).cpu().numpy().ravel()
+    assert abs(zhat.mean()) < 0.1 and abs(zhat.std() - 1) < 0.1
+    # vector and scalar paths draw the same in-kernel noise
+    a47 = run(x1, e1, zz=None, Dd=47)
+    assert torch.equal(a47, a[:, :47])
+
+
+@pytest.mark.parametrize("tag,ode", [("lim_sde", False), ("lim_ode", True)])
+def test_lim_step_teacher_forced(L, tag, ode):
+    from dlpm_b200.methods.lim import VPSDE, lim_step_table
+    g = load_golden("mlp_chain")
+    r = sub(g, tag)
+    sdict = {k: torch.from_numpy(v) for k, v in sub(g, "sd").items()}
+    steps = r["e_L"].shape[0]
+    ts, coef = lim_step_table(VPSDE(1.7), steps, ode)
+    cd = coef.cuda()
+    hist = torch.from_numpy(r["hist"])
+    B = hist.shape[1]
+    D = int(np.prod(hist.shape[2:]))
+    for i in range(steps):
+        x = hist[i].clone()
+        out = nets.mlp_forward(sdict, 4, x, torch.ones(B) * ts[i])
+        xd, od, ed = x.cuda().contiguous(), out.cuda().contiguous(), cu(r["e_L"][i])
+        L.call("dlpm_b200_lim_step", L.ptr(xd), L.ptr(od), L.ptr(cd), i, None, B, D, 0, 1 if ode else 0, 1, 1.7, -1.0, L.ptr(ed), 0, 0,
+               0, None, L.stream_ptr())
+        np.testing.assert_allclose(xd.cpu().numpy(), r["hist"][i + 1], rtol=2e-5, atol=2e-5)
+
+
+def test_training_elements_and_loss(L):
+    g = load_golden("mlp_chain")
+    r = sub(g, "train")
+    _, sd = sched_dev(1.7, 100)
+    B, D = r["x0"].shape[0], int(np.prod(r["x0"].shape[1:]))
+    x_t = torch.empty(B, D).cuda()
+    eps_t = torch.empty(B, D).cuda()
+    L.call("dlpm_b200_training_elements", L.ptr(x_t), L.ptr(eps_t), L.ptr(cu(r["x0"])), L.ptr(cu(r["t"])), L.ptr(cu(r["A"])),
+           L.ptr(cu(r["z"])), L.ptr(sd), 100, B, D, 1.7, -1.0, 0, 0, 0, L.stream_ptr())
+    np.testing.assert_allclose(x_t.cpu().numpy().reshape(r["x_t"].shape), r["x_t"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(eps_t.cpu().numpy().reshape(r["eps_t"].shape), r["eps_t"], rtol=1e-5, atol=1e-6)
+    # loss terms vs oracle for the three supported exponents
+    pred = torch.randn(B, 96).cuda()
+    tgt = torch.randn(B, 96).cuda()
+    for lp in (2.0, 1.0, -1):
+        out = torch.empty(B).cuda()
+        L.call("dlpm_b200_loss_terms", L.ptr(out), L.ptr(pred), L.ptr(tgt), B, 96, float(lp), 0, L.stream_ptr())
+        want = process.compute_loss_terms(pred.cpu(), tgt.cpu(), lp)
+        np.testing.assert_allclose(out.cpu().numpy(), want.numpy(), rtol=1e-5)
+
+
+def test_postprocess(L):
+    x = torch.randn(1000).cuda() * 2
+    y = torch.empty_like(x)
+    L.call("dlpm_b200_postprocess", L.ptr(y), L.ptr(x), x.numel(), 1.0, 1, L.stream_ptr())
+    assert torch.equal(y, (x.clamp(-1, 1) + 1) / 2)
+
+
+def test_argument_errors(L):
+    x = torch.zeros(4, 4).cuda()
+    with pytest.raises(L.DlpmB200Error, match="t out of range"):
+        L.call("dlpm_b200_reverse_step", L.ptr(x), L.ptr(x), L.ptr(x), L.ptr(x), 0, None, 4, 4, 4, 0, None, 0, 0, 0, None, L.stream_ptr())
+    with pytest.raises(L.DlpmB200Error):
+        L.ptr(torch.zeros(3))  # CPU tensor: no fallback

@@ -1,0 +1,193 @@
+"""GPU: the UNet building blocks (K5 tcgen05 conv, K6 GroupNorm, K7 attention, conv_in, upsample, time embedding)
+against plain PyTorch fp32 references of the same op evaluated on the bf16-rounded operands (bf16 bar: rtol 2e-2)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def L():
+    from dlpm_b200 import _lib
+    _lib.load()
+    assert torch.cuda.is_available()
+    return _lib
+
+
+def bf(x):
+    return x.to(torch.bfloat16)
+
+
+def nhwc(x):  # NCHW fp32 -> NHWC bf16 (device)
+    return bf(x.permute(0, 2, 3, 1).contiguous()).cuda()
+
+
+def from_nhwc(y):
+    return y.float().permute(0, 3, 1, 2).cpu()
+
+
+def run_conv(L, x, w, b, stride=1, skips=(), skip_w=None, skip_b=None, residual=None, f32_out=False):
+    """x NCHW fp32 (bf16-representable), w torch conv weight.  Returns NCHW fp32 (cpu)."""
+    B, C_in, H, W = x.shape
+    C_out, _, k, _ = w.shape
+    wk = w.permute(0, 2, 3, 1).reshape(C_out, -1)
+    bias = b.clone()
+    sk = []
+    if skips:
+        wk = torch.cat([wk, skip_w.reshape(C_out, -1)], dim=1)
+        bias = bias + skip_b
+        sk = [(nhwc(s), s.shape[1]) for s in skips]
+    if f32_out:
+        wk = torch.cat([wk, torch.zeros(16 - C_out, wk.shape[1])])
+        bias = torch.cat([bias, torch.zeros(16 - C_out)])
+    wd, bd, xd = bf(wk).contiguous().cuda(), bias.float().cuda(), nhwc(x)
+    Ho, Wo = H // stride, W // stride
+    out = (torch.zeros(B, C_out, Ho, Wo, device="cuda") if f32_out
+           else torch.zeros(B, Ho, Wo, C_out, device="cuda", dtype=torch.bfloat16))
+    rd = nhwc(residual) if residual is not None else None
+    s = sk + [(None, 0)] * (2 - len(sk))
+    L.call("dlpm_b200_conv2d", L.ptr(xd), L.ptr(wd), L.ptr(bd), L.ptr(s[0][0]), s[0][1], L.ptr(s[1][0]), s[1][1], L.ptr(rd),
+           L.ptr(out), 1 if f32_out else 0, B, H, W, C_in, C_out, k, stride, L.stream_ptr())
+    torch.cuda.synchronize()
+    return out.cpu() if f32_out else from_nhwc(out)
+
+
+def rnd(*shape, scale=1.0, seed=0):
+    g = torch.Generator().manual_seed(seed + sum(shape))
+    return bf(torch.randn(*shape, generator=g) * scale).float()
+
+
+CONV_CASES = [
+    # B, H, C_in, C_out, k, stride
+    (3, 32, 128, 128, 3, 1),   # 7x in the CIFAR UNet
+    (2, 16, 256, 256, 3, 1),
+    (5, 8, 256, 256, 3, 1),    # two images per tile, odd batch -> masked tail
+    (11, 4, 256, 256, 3, 1),   # eight images per tile
+    (2, 16, 512, 256, 3, 1),
+    (2, 32, 128, 128, 3, 2),   # Downsample (unet.py:96)
+    (3, 16, 256, 256, 3, 2),
+    (9, 4, 256, 768, 1, 1),    # attention qkv
+    (2, 32, 64, 64, 3, 1),     # tile N = 64
+    (2, 32, 32, 32, 3, 1),     # MNIST width: 64-byte swizzle, K block 32
+    (2, 16, 96, 64, 3, 1),
+    (200, 32, 128, 128, 3, 1),  # > 148 tiles per... persistent loop with several tiles per CTA
+]
+
+
+@pytest.mark.parametrize("B,H,C_in,C_out,k,stride", CONV_CASES)
+def test_conv_matches_torch(L, B, H, C_in, C_out, k, stride):
+    x = rnd(B, C_in, H, H)
+    w = rnd(C_out, C_in, k, k, scale=1.0 / math.sqrt(C_in * k * k))
+    b = torch.randn(C_out) * 0.1
+    got = run_conv(L, x, w, b, stride=stride)
+    want = F.conv2d(x, w, b, stride=stride, padding=k // 2)
+    err = (got - want).abs().max().item()
+    assert got.shape == want.shape
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=2e-2, atol=2e-2, err_msg="max err %g" % err)
+    assert (got - want).abs().mean().item() < 4e-3
+
+
+def test_conv_fused_skip_residual_and_final(L):
+    # second conv of a ResBlock with channel change: 3x3 on h plus the 1x1 skip conv over cat([x1, x2]) (unet.py:161-195,489)
+    B, H, C_out = 2, 32, 128
+    h, x1, x2 = rnd(B, 128, H, H, seed=1), rnd(B, 256, H, H, seed=2), rnd(B, 128, H, H, seed=3)
+    w = rnd(C_out, 128, 3, 3, scale=1 / math.sqrt(1152))
+    sw = rnd(C_out, 384, 1, 1, scale=1 / math.sqrt(384))
+    b, sb = torch.randn(C_out) * 0.1, torch.randn(C_out) * 0.1
+    got = run_conv(L, h, w, b, skips=(x1, x2), skip_w=sw, skip_b=sb)
+    want = F.conv2d(h, w, b, padding=1) + F.conv2d(torch.cat([x1, x2], 1), sw, sb)
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=2e-2, atol=3e-2)
+    # identity skip: residual added in the epilogue
+    res = rnd(B, 128, H, H, seed=4)
+    got = run_conv(L, h, w, b, residual=res)
+    np.testing.assert_allclose(got.numpy(), (F.conv2d(h, w, b, padding=1) + res).numpy(), rtol=2e-2, atol=3e-2)
+    # final conv: 128 -> 3, fp32 NCHW output (unet.py:435)
+    w3 = rnd(3, 128, 3, 3, scale=1 / math.sqrt(1152))
+    b3 = torch.randn(3) * 0.1
+    got = run_conv(L, h, w3, b3, f32_out=True)
+    np.testing.assert_allclose(got.numpy(), F.conv2d(h, w3, b3, padding=1).numpy(), rtol=1e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("C0,C1,HW,ss,silu", [(128, 0, 1024, False, True), (256, 128, 1024, False, True), (256, 256, 64, True, True),
+                                              (256, 0, 16, False, False), (32, 0, 1024, True, True), (64, 32, 256, False, True)])
+def test_groupnorm_silu(L, C0, C1, HW, ss, silu):
+    B, C = 5, C0 + C1
+    H = int(math.isqrt(HW))
+    x0 = rnd(B, C0, H, H, seed=5) * 2 + 0.3
+    x1 = rnd(B, C1, H, H, seed=6) if C1 else None
+    gamma, beta = 1 + 0.1 * torch.randn(C), 0.1 * torch.randn(C)
+    table = torch.randn(B, 3 * C + 7) * 0.3
+    off = 5
+    out = torch.zeros(B, H, H, C, device="cuda", dtype=torch.bfloat16)
+    for rows in ((1, B) if ss else (1,)):
+        tb = table[:rows].contiguous().cuda()
+        L.call("dlpm_b200_groupnorm_silu", L.ptr(out), L.ptr(nhwc(x0)), C0, L.ptr(nhwc(x1)) if C1 else None, C1, B, HW,
+               L.ptr(gamma.cuda()), L.ptr(beta.cuda()), L.ptr(tb) if ss else None, rows, table.shape[1], off, 1 if silu else 0,
+               L.stream_ptr())
+        x = torch.cat([x0, x1], 1) if C1 else x0
+        want = F.group_norm(x, min(32, C), gamma, beta, eps=1e-5)
+        if ss:
+            t = table[:rows]
+            scale, shift = t[:, off:off + C, None, None], t[:, off + C:off + 2 * C, None, None]
+            want = want * (1 + scale) + shift
+        if silu:
+            want = want * torch.sigmoid(want)
+        np.testing.assert_allclose(from_nhwc(out).numpy(), want.numpy(), rtol=1.5e-2, atol=1.5e-2)
+
+
+@pytest.mark.parametrize("L_,C,heads", [(16, 256, 4), (256, 64, 4), (64, 64, 4), (16, 64, 4)])
+def test_attention(L, L_, C, heads):
+    B = 3
+    qkv = rnd(B, 3 * C, L_, seed=7)
+    qd = bf(qkv.permute(0, 2, 1).contiguous()).cuda()  # [B, L, 3C]
+    out = torch.zeros(B, L_, C, device="cuda", dtype=torch.bfloat16)
+    L.call("dlpm_b200_attention", L.ptr(out), L.ptr(qd), B, L_, C, heads, L.stream_ptr())
+    q = qkv.reshape(B * heads, -1, L_)
+    ch = q.shape[1] // 3
+    qq, kk, vv = torch.split(q, ch, dim=1)
+    s = 1 / math.sqrt(math.sqrt(ch))
+    wgt = torch.softmax(torch.einsum("bct,bcs->bts", qq * s, kk * s), dim=-1)
+    want = torch.einsum("bts,bcs->bct", wgt, vv).reshape(B, -1, L_)
+    np.testing.assert_allclose(out.float().permute(0, 2, 1).cpu().numpy(), want.numpy(), rtol=1.5e-2, atol=1.5e-2)
+
+
+def test_conv_in_upsample_time_embedding(L):
+    B, H = 3, 32
+    x = torch.randn(B, 3, H, H)
+    w = torch.randn(128, 3, 3, 3) / math.sqrt(27)
+    b = torch.randn(128) * 0.1
+    out = torch.zeros(B, H, H, 128, device="cuda", dtype=torch.bfloat16)
+    L.call("dlpm_b200_conv_in", L.ptr(out), L.ptr(x.cuda()), L.ptr(w.reshape(128, -1).contiguous().cuda()), L.ptr(b.cuda()), B, 3, 128,
+           H, H, L.stream_ptr())
+    np.testing.assert_allclose(from_nhwc(out).numpy(), F.conv2d(x, w, b, padding=1).numpy(), rtol=1e-2, atol=1e-2)
+    # upsample
+    y = rnd(B, 64, 8, 8, seed=8)
+    up = torch.zeros(B, 16, 16, 64, device="cuda", dtype=torch.bfloat16)
+    L.call("dlpm_b200_upsample2x", L.ptr(up), L.ptr(nhwc(y)), B, 8, 8, 64, L.stream_ptr())
+    assert torch.equal(from_nhwc(up), F.interpolate(y, scale_factor=2, mode="nearest"))
+    # time embedding + emb_layers
+    from oracle import nets
+    mc, sst = 128, 1000
+    w0, b0 = torch.randn(4 * mc, mc) / math.sqrt(mc), torch.randn(4 * mc) * 0.1
+    w2, b2 = torch.randn(4 * mc, 4 * mc) / math.sqrt(4 * mc), torch.randn(4 * mc) * 0.1
+    wa, ba = torch.randn(sst, 4 * mc) / math.sqrt(4 * mc), torch.randn(sst) * 0.1
+    t = torch.tensor([0.731, 0.05, 0.9])
+    ss = torch.zeros(3, sst, device="cuda")
+    semb = torch.zeros(3, 4 * mc, device="cuda")
+    cu = lambda v: v.contiguous().cuda()
+    L.call("dlpm_b200_time_embedding", L.ptr(ss), L.ptr(semb), L.ptr(t.cuda()), None, 0.0, 3, mc, sst, L.ptr(cu(w0.t())), L.ptr(cu(b0)),
+           L.ptr(cu(w2.t())), L.ptr(cu(b2)), L.ptr(cu(wa.t())), L.ptr(cu(ba)), L.stream_ptr())
+    emb = nets.timestep_embedding(t, mc)
+    emb = F.linear(F.silu(F.linear(emb, w0, b0)), w2, b2)
+    want = F.linear(F.silu(emb), wa, ba)
+    np.testing.assert_allclose(ss.cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-4)
+    # device-side step counter: t = *t_dev * inv_T
+    td = torch.tensor([731], dtype=torch.int32).cuda()
+    ss1 = torch.zeros(1, sst, device="cuda")
+    L.call("dlpm_b200_time_embedding", L.ptr(ss1), L.ptr(semb), None, L.ptr(td), 0.001, 1, mc, sst, L.ptr(cu(w0.t())), L.ptr(cu(b0)),
+           L.ptr(cu(w2.t())), L.ptr(cu(b2)), L.ptr(cu(wa.t())), L.ptr(cu(ba)), L.stream_ptr())
+    np.testing.assert_allclose(ss1.cpu().numpy()[0], want.numpy()[0], rtol=1e-4, atol=1e-4)
