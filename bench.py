@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""Benchmark of the DLPM sampling hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A "step" is ONE full pass of the hot path over one batch of synthetic input: `GenerativeLevyProcess.sample()`
+= alpha-stable noise + Sigma chain + 999 score-network evaluations + 999 fused posterior updates, for the
+CIFAR-10-LT configuration (BASELINE.json configs[2]: 32x32x3, UNet ch128 mult (1,2,2,2), alpha=1.7, T=1000,
+clamp_a=20, clamp_eps=200; 4096 samples over 8 GPUs = 512 samples per GPU, weak scaling).  Weights are random
+(every parameter re-randomised, see dlpm_b200/init_utils.py), data is synthetic (there is no input data: the
+sampler starts from in-kernel noise).  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALPHA, T_STEPS, IMG, CH = 1.7, 1000, 32, 3
+UNET = dict(model_channels=128, channel_mult=(1, 2, 2, 2), num_res_blocks=2, attention_resolutions=(16,), num_heads=4)
+GFLOP_PER_SAMPLE_STEP = 11.44  # SURVEY.md section 6 (2*MAC of conv/linear/bmm, torch flop counter on the reference UNet)
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's PyTorch path (the reference itself cannot travel to the GPU box)
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_reference_step(b_cpu, n_sub, seed=0):
+    """One bounded sample of the workload on the host cores: the full A/Sigma set-up for T=1000 at batch b_cpu, then
+    n_sub reverse steps (UNet forward + posterior update), extrapolated linearly to the 999 steps of a full pass.
+    Returns (samples_per_sec, seconds_spent, description)."""
+    import numpy as np
+    import torch
+    from dlpm_b200.init_utils import randomize_parameters_
+    from dlpm_b200.score_nets import UNetModel
+    from oracle import nets, process, stable
+    torch.set_num_threads(os.cpu_count() or 1)
+    m = UNetModel(CH, UNET["model_channels"], CH, UNET["num_res_blocks"], UNET["attention_resolutions"],
+                  channel_mult=UNET["channel_mult"], num_heads=UNET["num_heads"], use_scale_shift_norm=True)
+    randomize_parameters_(m, 0)
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    cfg = dict(UNET)
+    rs = np.random.RandomState(seed)
+    shape = (b_cpu, CH, IMG, IMG)
+    t0 = time.perf_counter()
+    sched = process.gen_noise_schedule(ALPHA, T_STEPS)
+    A = torch.stack([torch.from_numpy(stable.gen_skewed_levy(ALPHA, shape, isotropic=True, clamp_a=20.0, rng=rs)) for _ in range(T_STEPS)])
+    Sig = process.compute_Sigmas(A, sched[0], sched[2])
+    x = sched[3][-1] * torch.from_numpy(stable.gen_sas(ALPHA, shape, isotropic=True, clamp_eps=200.0, rng=rs))
+    t_setup = time.perf_counter() - t0
+    with torch.inference_mode():
+        def one(t):
+            eps = nets.unet_forward(sd, cfg, x, torch.full((b_cpu,), t / T_STEPS))
+            return process.dlpm_step(x, eps, torch.randn(shape), t, Sig, sched)
+        x = one(T_STEPS - 1)  # warm-up (thread pools, allocator)
+        t1 = time.perf_counter()
+        for k in range(n_sub):
+            x = one(T_STEPS - 2 - k)
+        t_step = (time.perf_counter() - t1) / n_sub
+    full = t_setup + t_step * (T_STEPS - 1)
+    desc = ("oracle port of the reference CPU path: batch %d, Sigma set-up for T=%d in full (%.2f s) + %d of 999 reverse steps "
+            "(%.3f s/step), extrapolated linearly to a full pass" % (b_cpu, T_STEPS, t_setup, n_sub, t_step))
+    return b_cpu / full, time.perf_counter() - t0, desc
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    vals, spent = [], 0.0
+    desc = ""
+    for i in range(args.warmup + args.steps):
+        v, s, desc = cpu_reference_step(args.cpu_batch, args.cpu_substeps, seed=i)
+        spent += s
+        if i >= args.warmup:
+            vals.append(v)
+        if spent > 240 and vals:  # keep the whole arm within a few minutes
+            break
+    value = sum(vals) / len(vals)
+    cores = os.cpu_count() or 1
+    line = {"impl": "reference", "metric": "DLPM samples/sec (1000 reverse steps, CIFAR-10 shape)", "value": value, "unit": "samples/s",
+            "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup, "ms_per_step": 1000.0 * args.cpu_batch / value,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, args.cpu_batch, 1),
+            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, batch_per_gpu, n):
+    return {"workload": "CIFAR-10-LT 32x32x3 UNet(ch128, mult 1-2-2-2, 2 res blocks, middle attention) DLPM alpha=1.7, "
+                        "T=1000 (999 network evals), clamp_a=20, clamp_eps=200; BASELINE.json configs[2] = 4096 samples over 8 GPUs",
+            "batch_per_gpu": batch_per_gpu, "global_batch": batch_per_gpu * n, "reverse_steps": args.reverse_steps,
+            "parallelism": "batch-sharded x%d (independent Philox streams keyed by global sample index, one NCCL all_gather)" % n,
+            "l2_note": "per-step working set (activations %.1f GB at batch %d) exceeds the 126 MB L2; no extra flush needed"
+                       % (5.1e-3 * batch_per_gpu, batch_per_gpu)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    import dlpm_b200
+    from dlpm_b200 import GenerativeLevyProcess, _lib, rng
+    from dlpm_b200.init_utils import randomize_parameters_
+    from dlpm_b200.score_nets import UNetModel
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()  # fail loudly if the CUDA library is missing
+    B, T = args.batch_per_gpu, args.reverse_steps
+    model = UNetModel(CH, UNET["model_channels"], CH, UNET["num_res_blocks"], UNET["attention_resolutions"],
+                      channel_mult=UNET["channel_mult"], num_heads=UNET["num_heads"], use_scale_shift_norm=True)
+    randomize_parameters_(model, 0)
+    model = model.to(dev).eval()
+    glp = GenerativeLevyProcess(ALPHA, dev, T, rescale_timesteps=True, isotropic=True)
+    models = {"default": model}
+    shape = [B, CH, IMG, IMG]
+    state = rng.default_state()
+    dlpm_b200.manual_seed(1234)
+    dlpm_b200.set_sample_base(rank * B)  # global sample index of this rank's first sample
+    gathered = torch.empty((world * B, CH, IMG, IMG), device=dev) if world > 1 else None
+    host_out = torch.empty((B, CH, IMG, IMG), dtype=torch.float32).pin_memory()
+    host_sched = glp.dlpm._sched_host.clone().pin_memory()
+
+    def step(e2e=False):
+        if e2e:  # host -> device: the per-call inputs of sample() are the schedule table and the RNG key/offset
+            glp.dlpm.sched.copy_(host_sched, non_blocking=True)
+        x = glp.sample(models, shape, reverse_steps=T, clamp_a=20, clamp_eps=200)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, x)  # the path's only collective
+        if e2e:  # GenerationManager.generate post-processing (clamp, (x+1)/2) + device -> host read of the result
+            _lib.call("dlpm_b200_postprocess", _lib.ptr(x), _lib.ptr(x), x.numel(), 1.0, 1, _lib.stream_ptr())
+            host_out.copy_(x, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return x
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n, e2e):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        e0.record()
+        for _ in range(n):
+            step(e2e)
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - w0
+        ms = torch.tensor([e0.elapsed_time(e1), wall * 1000.0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms[0]), float(ms[1])
+
+    for _ in range(args.warmup):
+        step()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ms_dev, _ = timed(args.steps, e2e=False)
+    clk = clocks.stop() if rank == 0 else None
+    _, ms_e2e_wall = timed(args.e2e_steps, e2e=True)
+    ms_per_step = ms_dev / args.steps
+    value = world * B / (ms_per_step / 1000.0)
+    e2e_value = world * B / (ms_e2e_wall / args.e2e_steps / 1000.0)
+
+    # ---- roofline of the dominant kernel (tcgen05 implicit-GEMM conv), measured live with CUDA events per op
+    eng = model.engine(IMG, IMG, B)
+    xs = torch.randn(shape, device=dev)
+    tt = torch.full((1,), 0.5, device=dev)
+    out = torch.empty_like(xs)
+    eng.profile(xs, tt, out, B)
+    prof = eng.profile(xs, tt, out, B)
+    conv = [(ms, fl) for code, ms, fl in prof if code == 2]
+    conv_ms, conv_fl = sum(m for m, _ in conv), sum(f for _, f in conv)
+    fwd_ms = sum(ms for _, ms, _ in prof)
+    pk, pk_src = peaks()
+    achieved = conv_fl / (conv_ms * 1e-3) / 1e12
+    peak = float(pk.get("bf16_tflops_sustained", pk["bf16_tflops"]))
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "conv_traffic.json"))).get("dram_bytes_per_launch_avg")
+    except Exception:
+        pass
+    roofline = {"bound": "tensor", "kernel": "k_conv_tc (tcgen05 implicit-GEMM conv, %d launches per UNet forward)" % len(conv),
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s)" % pk_src,
+                "flop_per_launch_avg": conv_fl / len(conv), "ms_per_launch_avg": conv_ms / len(conv),
+                "conv_share_of_forward": conv_ms / fwd_ms, "forward_ms_serialised": fwd_ms,
+                "end_to_end_tflops": GFLOP_PER_SAMPLE_STEP * 1e9 * B * (T - 1) / (ms_per_step * 1e-3) / 1e12}
+
+    # ---- HBM-bound kernels: fused reverse step (12 B/element) and SaS noise (4 B/element), timed alone (burst peak)
+    hbm = {}
+    n_el = B * CH * IMG * IMG
+    big = torch.empty(64 * 1024 * 1024, device=dev)  # 256 MB > L2: flushes between timed launches
+    d = glp.dlpm
+    d.sample_A(shape, T)
+    eps = torch.randn(shape, device=dev)
+    xw = torch.randn(shape, device=dev)
+
+    def time_kernel(fn, reps=20):
+        t = 0.0
+        for _ in range(reps):
+            big.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            t += a.elapsed_time(b)
+        return t / reps
+    ms_k3 = time_kernel(lambda: _lib.call("dlpm_b200_reverse_step", _lib.ptr(xw), _lib.ptr(eps), _lib.ptr(d.Sigmas), _lib.ptr(d.sched), 500,
+                                          None, T, B, CH * IMG * IMG, 0, None, 1, 2, 0, None, _lib.stream_ptr()))
+    n_noise = 1 << 28
+    nbuf = torch.empty(n_noise, device=dev)
+    ms_k1 = time_kernel(lambda: _lib.call("dlpm_b200_sas", _lib.ptr(nbuf), None, n_noise // 3072, 3072, 1, ALPHA, 200.0, 1.0, 1, 2, 0,
+                                          _lib.stream_ptr()), reps=5)
+    hbm_peak = float(pk["hbm_gbs"])
+    hbm["reverse_step"] = {"bytes_per_launch": 12 * n_el, "ms": ms_k3, "GB/s": 12 * n_el / ms_k3 / 1e6, "frac": 12 * n_el / ms_k3 / 1e6 / hbm_peak}
+    nn = (n_noise // 3072) * 3072
+    hbm["sas_noise_isotropic"] = {"bytes_per_launch": 4 * nn, "ms": ms_k1, "GB/s": 4 * nn / ms_k1 / 1e6, "frac": 4 * nn / ms_k1 / 1e6 / hbm_peak}
+
+    launches_per_pass = (T - 1) * (eng.num_launches() + 2) + 3
+    if rank == 0:
+        cpu_val, _, cpu_desc = cpu_reference_step(args.cpu_batch, args.cpu_substeps)
+        line = {"metric": "DLPM samples/sec (1000 reverse steps, CIFAR-10 shape)", "value": value, "unit": "samples/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, B, world),
+                "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(host_sched.numel() * 4 * world),
+                        "d2h_bytes_per_step": int(host_out.numel() * 4 * world), "steps": args.e2e_steps,
+                        "api": "GenerativeLevyProcess.sample() + GenerationManager post-processing + pinned D2H"},
+                "gpu_launches": int(launches_per_pass * (args.steps + args.e2e_steps)), "clocks": clk, "roofline": roofline,
+                "hbm_kernels": hbm,
+                "cpu_baseline": {"value": cpu_val, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port", "sample": cpu_desc},
+                "workspace_gb": eng.workspace_bytes / 1e9}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch-per-gpu", type=int, default=512)
+    ap.add_argument("--reverse-steps", type=int, default=T_STEPS)
+    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--cpu-batch", type=int, default=8)
+    ap.add_argument("--cpu-substeps", type=int, default=3)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world == 1 and args.gpus > 1:
+        # not launched through torchrun: re-exec under it (one process per GPU)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus), "--master-addr",
+               "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

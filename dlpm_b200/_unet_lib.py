@@ -20,6 +20,7 @@ UNET_SIGNATURES = {
                               c_i64, c_vp, c_i64, c_i64],
     "dlpm_b200_unet_forward": [c_vp, c_vp, c_vp, c_int, c_vp, c_f32, c_vp, c_i64, c_vp],
     "dlpm_b200_unet_copy_buffer": [c_vp, c_int, c_vp, c_i64, c_vp],
+    "dlpm_b200_unet_profile": [c_vp, c_vp, c_vp, c_int, c_vp, c_i64, ctypes.POINTER(c_f32), ctypes.POINTER(ctypes.c_double), c_vp],
     "dlpm_b200_unet_num_launches": [c_vp],
     "dlpm_b200_unet_destroy": [c_vp],
 }
@@ -58,6 +59,16 @@ class Engine:
     def forward(self, x, t, t_dev, inv_T, out, B):
         _lib.call("dlpm_b200_unet_forward", self.handle, _lib.ptr(x), _lib.ptr(t), 0 if t is None else t.numel(), _lib.ptr(t_dev),
                   float(inv_T), _lib.ptr(out), B, _lib.stream_ptr())
+
+    def profile(self, x, t, out, B):
+        """One forward with per-op CUDA-event timing.  Returns [(opcode, ms, flops)], entry 0 = time embedding."""
+        n = len(self.prog["ops"]) + 1
+        ms = (c_f32 * n)()
+        fl = (ctypes.c_double * n)()
+        _lib.call("dlpm_b200_unet_profile", self.handle, _lib.ptr(x), _lib.ptr(t), t.numel(), _lib.ptr(out), B, ms, fl,
+                  _lib.stream_ptr())
+        codes = [-1] + [op[0] for op in self.prog["ops"]]
+        return [(codes[i], float(ms[i]), float(fl[i])) for i in range(n)]
 
     def num_launches(self):
         return _lib.load().dlpm_b200_unet_num_launches(self.handle)

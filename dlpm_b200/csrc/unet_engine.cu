@@ -35,6 +35,7 @@ struct UNetEngine {
   int64_t workspace_bytes = 0;
   std::map<int64_t, Plan> plans;
   int n_launches = 0;
+  std::vector<cudaEvent_t> prof;  // when non-empty: one event recorded before the first op and after every op
 
   __nv_bfloat16* buf(int64_t id, int64_t B) const { return slab + buf_offset[id] * max_batch; }
 };
@@ -124,11 +125,14 @@ int dlpm_b200_unet_forward(void* handle, const float* x, const float* t, int t_r
   const int64_t ss_total = h[7];
   const int rows = t_dev ? 1 : t_rows;
   int launches = 0;
+  const bool prof = !E->prof.empty();
+  if (prof) cudaEventRecord(E->prof[0], (cudaStream_t)stream);
   int rc = dlpm_b200_time_embedding(E->ss, E->semb, t, t_dev, inv_T, rows, mc, ss_total, E->wf + h[8], E->wf + h[9], E->wf + h[10],
                                     E->wf + h[11], E->wf + h[12], E->wf + h[13], stream);
   if (rc) return rc;
   launches += 2;
-  size_t ci = 0;
+  if (prof) cudaEventRecord(E->prof[1], (cudaStream_t)stream);
+  size_t ci = 0, oi = 0;
   for (const Op& op : E->ops) {
     const int64_t* f = op.f;
     switch (f[0]) {
@@ -157,6 +161,8 @@ int dlpm_b200_unet_forward(void* handle, const float* x, const float* t, int t_r
     }
     if (rc) return rc;
     ++launches;
+    ++oi;
+    if (prof) cudaEventRecord(E->prof[1 + oi], (cudaStream_t)stream);
   }
   E->n_launches = launches;
   return DLPM_OK;
@@ -168,6 +174,36 @@ int dlpm_b200_unet_copy_buffer(void* handle, int buf, void* dst, int64_t B, void
   DLPM_REQUIRE(buf >= 0 && buf < (int)E->buf_elems.size() && B >= 1 && B <= E->max_batch, "unet_copy_buffer: bad index");
   cudaError_t e = cudaMemcpyAsync(dst, E->buf(buf, B), (size_t)(E->buf_elems[buf] * B * 2), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "unet_copy_buffer");
+  return DLPM_OK;
+}
+
+int dlpm_b200_unet_profile(void* handle, const float* x, const float* t, int t_rows, float* out, int64_t B, float* ms_per_op,
+                           double* flops_per_op, void* stream) {
+  DLPM_REQUIRE(handle && ms_per_op && flops_per_op, "unet_profile: NULL argument");
+  UNetEngine* E = reinterpret_cast<UNetEngine*>(handle);
+  const size_t n = E->ops.size();
+  E->prof.resize(n + 2);
+  for (auto& ev : E->prof) cudaEventCreate(&ev);
+  int rc = dlpm_b200_unet_forward(handle, x, t, t_rows, nullptr, 0.f, out, B, stream);
+  cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+  if (!rc && e == cudaSuccess) {
+    cudaEventElapsedTime(&ms_per_op[0], E->prof[0], E->prof[1]);  // time embedding (2 launches)
+    flops_per_op[0] = 0.0;
+    for (size_t i = 0; i < n; ++i) {
+      cudaEventElapsedTime(&ms_per_op[1 + i], E->prof[1 + i], E->prof[2 + i]);
+      const int64_t* f = E->ops[i].f;
+      double fl = 0.0;
+      if (f[0] == OP_CONV) {  // 2 * M * N * K with M = B * H_out * W_out
+        const double M = (double)B * (f[8] / f[13]) * (f[9] / f[13]);
+        fl = 2.0 * M * (double)f[11] * ((double)f[12] * f[12] * f[10] + f[4] + f[6]);
+      }
+      flops_per_op[1 + i] = fl;
+    }
+  }
+  for (auto& ev : E->prof) cudaEventDestroy(ev);
+  E->prof.clear();
+  if (rc) return rc;
+  if (e != cudaSuccess) return cuda_fail(e, "unet_profile");
   return DLPM_OK;
 }
 

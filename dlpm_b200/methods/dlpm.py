@@ -175,14 +175,14 @@ class DLPM:
                       max(inner, 1), 0 if self.isotropic else 1, float(self.alpha), self._clamp_a(), st.seed, st.reserve(T),
                       st.sample_base, _lib.stream_ptr())
         self._shape = shape
-        self._sigma_src = (self.A.data_ptr(), self.A._version)
+        self._sigma_src = self.A
 
-    def compute_Sigmas(self):
+    def compute_Sigmas(self, force=False):
         """Sigma_t = s_t^2 A_t + g_t^2 Sigma_{t-1}.  No-op if ``sample_A`` just produced them; re-runs
-        the scan (K2) when ``self.A`` was replaced or edited (e.g. injected for parity tests)."""
+        the scan (K2) when ``self.A`` was replaced (e.g. injected for parity tests); pass ``force=True`` after editing
+        ``self.A`` in place."""
         assert self.A is not None, "sample_A must be called first"
-        if self.Sigmas is not None and self._sigma_src == (self.A.data_ptr(), self.A._version) \
-                and self.Sigmas.shape == self.A.shape:
+        if not force and self.Sigmas is not None and self._sigma_src is self.A and self.Sigmas.shape == self.A.shape:
             return
         dev = _lib.require_cuda(self.device)
         A = self.A.to(dev, torch.float32).contiguous()
@@ -193,7 +193,7 @@ class DLPM:
             _lib.call("dlpm_b200_sigma_scan", _lib.ptr(self.Sigmas), _lib.ptr(A), None, _lib.ptr(self.sched), T, n, 1, 0,
                       float(self.alpha), -1.0, 0, 0, 0, _lib.stream_ptr())
         self.A = A
-        self._sigma_src = (self.A.data_ptr(), self.A._version)
+        self._sigma_src = self.A
 
     def _full(self, v):
         if v is None or self._shape is None or v.dim() != 2:

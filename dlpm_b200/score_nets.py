@@ -39,6 +39,13 @@ def _seq(*pairs):
     return m
 
 
+def _version_of(p):
+    try:
+        return p._version
+    except RuntimeError:  # inference tensors do not track versions
+        return -1
+
+
 class _PackedCache:
     """Caches a packed device copy of the parameters, invalidated by parameter version bumps."""
 
@@ -47,7 +54,7 @@ class _PackedCache:
         self.value = None
 
     def get(self, module, build):
-        key = tuple((p.data_ptr(), p._version, str(p.device)) for p in module.parameters())
+        key = tuple((p.data_ptr(), _version_of(p), str(p.device)) for p in module.parameters())
         if key != self.key:
             self.value = build()
             self.key = key
@@ -388,7 +395,7 @@ class UNetModel(nn.Module):
             for j in range(len(list(block.children()))):
                 layer = block[j]
                 if isinstance(layer, _ResBlockParams):
-                    h, C = resblock(layer, parts, H_, W_, "%s.%d" % (tag, j))
+                    h, C = resblock(layer, parts if h is None else [(h, C)], H_, W_, "%s.%d" % (tag, j))
                 elif isinstance(layer, _AttentionParams):
                     h = attention(layer, h, C, H_, W_, "%s.%d" % (tag, j))
                 elif isinstance(layer, _DownParams):
@@ -443,7 +450,7 @@ class UNetModel(nn.Module):
         """Create (or fetch) the CUDA engine for this resolution / batch capacity."""
         from . import _unet_lib
         key = (H, W, reuse_scratch)
-        version = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        version = tuple((p.data_ptr(), _version_of(p)) for p in self.parameters())
         ent = self._engines.get(key)
         if ent is not None and (ent.version != version or ent.max_batch < max_batch):
             ent.close()

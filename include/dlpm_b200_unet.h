@@ -73,6 +73,10 @@ int dlpm_b200_unet_forward(void* handle, const float* x, const float* t, int t_r
                            float* out, int64_t B, void* stream);
 /* debugging / per-layer parity: copy activation buffer `buf` (bf16, B * elems) of the last forward to dst. */
 int dlpm_b200_unet_copy_buffer(void* handle, int buf, void* dst, int64_t B, void* stream);
+/* measurement: one forward with a CUDA event after every op; ms_per_op / flops_per_op are HOST arrays of n_ops + 1
+ * entries (entry 0 = the two time-embedding launches); flops = 2*M*N*K of the convolutions, 0 for the other ops. */
+int dlpm_b200_unet_profile(void* handle, const float* x, const float* t, int t_rows, float* out, int64_t B, float* ms_per_op,
+                           double* flops_per_op, void* stream);
 int64_t dlpm_b200_unet_workspace_bytes(void* handle);
 int dlpm_b200_unet_num_launches(void* handle);
 int dlpm_b200_unet_destroy(void* handle);

@@ -1,0 +1,90 @@
+"""Test helper: a plain-PyTorch (CPU fp32) interpreter of the UNet op list emitted by
+``dlpm_b200.score_nets.UNetModel.build_program``.  It validates the architecture walk, the weight packing and the
+offsets independently of the CUDA kernels (the C++ engine executes the very same list)."""
+import math
+
+import torch
+import torch.nn.functional as F
+
+OP_CONV_IN, OP_GN, OP_CONV, OP_UP, OP_ATTN = 0, 1, 2, 3, 4
+
+
+def interpret(prog, x, t, mc, emulate_bf16=False):
+    """x: (B, C, H, W) fp32 NCHW; t: (B,) floats.  Returns (eps NCHW fp32, {buffer id: NHWC tensor})."""
+    hd = prog["header"]
+    wb = prog["wb"].float().cpu()
+    wf = prog["wf"].float().cpu()
+    B = x.shape[0]
+    ss_total = hd[7]
+    E = 4 * mc
+    q = (lambda v: v.to(torch.bfloat16).float()) if emulate_bf16 else (lambda v: v)
+    # time embedding (k_time_embed / k_emb_layers)
+    half = mc // 2
+    freqs = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32) / half)
+    args = t[:, None].float() * freqs[None]
+    e0 = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+    w0T = wf[hd[8]:hd[8] + mc * E].reshape(mc, E)
+    b0 = wf[hd[9]:hd[9] + E]
+    w2T = wf[hd[10]:hd[10] + E * E].reshape(E, E)
+    b2 = wf[hd[11]:hd[11] + E]
+    wallT = wf[hd[12]:hd[12] + E * ss_total].reshape(E, ss_total)
+    ball = wf[hd[13]:hd[13] + ss_total]
+    semb = F.silu(F.silu(e0 @ w0T + b0) @ w2T + b2)
+    ss = semb @ wallT + ball  # [B, ss_total]
+    bufs = {}
+    out = None
+    for f in prog["ops"]:
+        code = f[0]
+        if code == OP_CONV_IN:
+            _, o, cin, cout, H, W, woff, boff = f[:8]
+            w = wf[woff:woff + cout * cin * 9].reshape(cout, cin, 3, 3)
+            b = wf[boff:boff + cout]
+            bufs[o] = q(F.conv2d(x, w, b, padding=1).permute(0, 2, 3, 1))
+        elif code == OP_GN:
+            _, i0, i1, o, C0, C1, HW, goff, boff, ssoff, silu = f[:11]
+            C = C0 + C1
+            v = bufs[i0] if i1 < 0 else torch.cat([bufs[i0], bufs[i1]], dim=-1)
+            v = v.permute(0, 3, 1, 2)
+            y = F.group_norm(v, min(32, C), wf[goff:goff + C], wf[boff:boff + C], eps=1e-5)
+            if ssoff >= 0:
+                y = y * (1 + ss[:, ssoff:ssoff + C, None, None]) + ss[:, ssoff + C:ssoff + 2 * C, None, None]
+            if silu:
+                y = F.silu(y)
+            bufs[o] = q(y.permute(0, 2, 3, 1))
+        elif code == OP_CONV:
+            _, i, o, s0, C0, s1, C1, res, H, W, cin, cout, k, stride, woff, boff = f[:16]
+            rows = 16 if o < 0 else cout
+            K = k * k * cin + C0 + C1
+            wk = wb[woff:woff + rows * K].reshape(rows, K)[:cout]
+            bias = wf[boff:boff + cout]
+            w = wk[:, :k * k * cin].reshape(cout, k, k, cin).permute(0, 3, 1, 2)
+            y = F.conv2d(bufs[i].permute(0, 3, 1, 2), w, None, stride=stride, padding=k // 2)
+            col = k * k * cin
+            for sid, Cs in ((s0, C0), (s1, C1)):
+                if sid >= 0:
+                    y = y + F.conv2d(bufs[sid].permute(0, 3, 1, 2), wk[:, col:col + Cs].reshape(cout, Cs, 1, 1))
+                    col += Cs
+            y = y + bias[None, :, None, None]
+            if res >= 0:
+                y = y + bufs[res].permute(0, 3, 1, 2)
+            if o < 0:
+                out = y
+            else:
+                bufs[o] = q(y.permute(0, 2, 3, 1))
+        elif code == OP_UP:
+            _, i, o, H, W, C = f[:6]
+            bufs[o] = F.interpolate(bufs[i].permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1)
+        elif code == OP_ATTN:
+            _, i, o, L, C, heads = f[:6]
+            qkv = bufs[i].reshape(B, L, 3 * C).permute(0, 2, 1)  # [B, 3C, L]
+            qkv = qkv.reshape(B * heads, -1, L)
+            ch = qkv.shape[1] // 3
+            qq, kk, vv = torch.split(qkv, ch, dim=1)
+            s = 1 / math.sqrt(math.sqrt(ch))
+            wgt = torch.softmax(torch.einsum("bct,bcs->bts", qq * s, kk * s), dim=-1)
+            a = torch.einsum("bts,bcs->bct", wgt, vv).reshape(B, C, L)
+            hh = int(math.isqrt(L))
+            bufs[o] = q(a.permute(0, 2, 1).reshape(B, hh, hh, C))
+        else:
+            raise ValueError(code)
+    return out, bufs

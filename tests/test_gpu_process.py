@@ -147,8 +147,9 @@ def test_training_elements_and_loss(L):
     B, D = r["x0"].shape[0], int(np.prod(r["x0"].shape[1:]))
     x_t = torch.empty(B, D).cuda()
     eps_t = torch.empty(B, D).cuda()
-    L.call("dlpm_b200_training_elements", L.ptr(x_t), L.ptr(eps_t), L.ptr(cu(r["x0"])), L.ptr(cu(r["t"])), L.ptr(cu(r["A"])),
-           L.ptr(cu(r["z"])), L.ptr(sd), 100, B, D, 1.7, -1.0, 0, 0, 0, L.stream_ptr())
+    x0d, td, Ad, zd = cu(r["x0"]), cu(r["t"]), cu(r["A"]), cu(r["z"])
+    L.call("dlpm_b200_training_elements", L.ptr(x_t), L.ptr(eps_t), L.ptr(x0d), L.ptr(td), L.ptr(Ad), L.ptr(zd), L.ptr(sd), 100, B, D,
+           1.7, -1.0, 0, 0, 0, L.stream_ptr())
     np.testing.assert_allclose(x_t.cpu().numpy().reshape(r["x_t"].shape), r["x_t"], rtol=1e-6, atol=1e-7)
     np.testing.assert_allclose(eps_t.cpu().numpy().reshape(r["eps_t"].shape), r["eps_t"], rtol=1e-5, atol=1e-6)
     # loss terms vs oracle for the three supported exponents

@@ -123,12 +123,15 @@ def test_groupnorm_silu(L, C0, C1, HW, ss, silu):
     table = torch.randn(B, 3 * C + 7) * 0.3
     off = 5
     out = torch.zeros(B, H, H, C, device="cuda", dtype=torch.bfloat16)
+    x0d, x1d, gd, bd = nhwc(x0), (nhwc(x1) if C1 else None), gamma.cuda(), beta.cuda()
     for rows in ((1, B) if ss else (1,)):
         tb = table[:rows].contiguous().cuda()
-        L.call("dlpm_b200_groupnorm_silu", L.ptr(out), L.ptr(nhwc(x0)), C0, L.ptr(nhwc(x1)) if C1 else None, C1, B, HW,
-               L.ptr(gamma.cuda()), L.ptr(beta.cuda()), L.ptr(tb) if ss else None, rows, table.shape[1], off, 1 if silu else 0,
+        L.call("dlpm_b200_groupnorm_silu", L.ptr(out), L.ptr(x0d), C0, L.ptr(x1d), C1, B, HW,
+               L.ptr(gd), L.ptr(bd), L.ptr(tb) if ss else None, rows, table.shape[1], off, 1 if silu else 0,
                L.stream_ptr())
-        x = torch.cat([x0, x1], 1) if C1 else x0
+        torch.cuda.synchronize()
+        x = torch.cat([x0d.float().cpu().permute(0, 3, 1, 2), x1d.float().cpu().permute(0, 3, 1, 2)], 1) if C1 \
+            else x0d.float().cpu().permute(0, 3, 1, 2)
         want = F.group_norm(x, min(32, C), gamma, beta, eps=1e-5)
         if ss:
             t = table[:rows]
@@ -161,13 +164,14 @@ def test_conv_in_upsample_time_embedding(L):
     w = torch.randn(128, 3, 3, 3) / math.sqrt(27)
     b = torch.randn(128) * 0.1
     out = torch.zeros(B, H, H, 128, device="cuda", dtype=torch.bfloat16)
-    L.call("dlpm_b200_conv_in", L.ptr(out), L.ptr(x.cuda()), L.ptr(w.reshape(128, -1).contiguous().cuda()), L.ptr(b.cuda()), B, 3, 128,
-           H, H, L.stream_ptr())
+    xd, wd, bd = x.cuda(), w.reshape(128, -1).contiguous().cuda(), b.cuda()
+    L.call("dlpm_b200_conv_in", L.ptr(out), L.ptr(xd), L.ptr(wd), L.ptr(bd), B, 3, 128, H, H, L.stream_ptr())
     np.testing.assert_allclose(from_nhwc(out).numpy(), F.conv2d(x, w, b, padding=1).numpy(), rtol=1e-2, atol=1e-2)
     # upsample
     y = rnd(B, 64, 8, 8, seed=8)
     up = torch.zeros(B, 16, 16, 64, device="cuda", dtype=torch.bfloat16)
-    L.call("dlpm_b200_upsample2x", L.ptr(up), L.ptr(nhwc(y)), B, 8, 8, 64, L.stream_ptr())
+    yd = nhwc(y)
+    L.call("dlpm_b200_upsample2x", L.ptr(up), L.ptr(yd), B, 8, 8, 64, L.stream_ptr())
     assert torch.equal(from_nhwc(up), F.interpolate(y, scale_factor=2, mode="nearest"))
     # time embedding + emb_layers
     from oracle import nets
@@ -179,8 +183,9 @@ def test_conv_in_upsample_time_embedding(L):
     ss = torch.zeros(3, sst, device="cuda")
     semb = torch.zeros(3, 4 * mc, device="cuda")
     cu = lambda v: v.contiguous().cuda()
-    L.call("dlpm_b200_time_embedding", L.ptr(ss), L.ptr(semb), L.ptr(t.cuda()), None, 0.0, 3, mc, sst, L.ptr(cu(w0.t())), L.ptr(cu(b0)),
-           L.ptr(cu(w2.t())), L.ptr(cu(b2)), L.ptr(cu(wa.t())), L.ptr(cu(ba)), L.stream_ptr())
+    td_, w0T, b0d, w2T, b2d, waT, bad = t.cuda(), cu(w0.t()), cu(b0), cu(w2.t()), cu(b2), cu(wa.t()), cu(ba)
+    L.call("dlpm_b200_time_embedding", L.ptr(ss), L.ptr(semb), L.ptr(td_), None, 0.0, 3, mc, sst, L.ptr(w0T), L.ptr(b0d),
+           L.ptr(w2T), L.ptr(b2d), L.ptr(waT), L.ptr(bad), L.stream_ptr())
     emb = nets.timestep_embedding(t, mc)
     emb = F.linear(F.silu(F.linear(emb, w0, b0)), w2, b2)
     want = F.linear(F.silu(emb), wa, ba)
@@ -188,6 +193,6 @@ def test_conv_in_upsample_time_embedding(L):
     # device-side step counter: t = *t_dev * inv_T
     td = torch.tensor([731], dtype=torch.int32).cuda()
     ss1 = torch.zeros(1, sst, device="cuda")
-    L.call("dlpm_b200_time_embedding", L.ptr(ss1), L.ptr(semb), None, L.ptr(td), 0.001, 1, mc, sst, L.ptr(cu(w0.t())), L.ptr(cu(b0)),
-           L.ptr(cu(w2.t())), L.ptr(cu(b2)), L.ptr(cu(wa.t())), L.ptr(cu(ba)), L.stream_ptr())
+    L.call("dlpm_b200_time_embedding", L.ptr(ss1), L.ptr(semb), None, L.ptr(td), 0.001, 1, mc, sst, L.ptr(w0T), L.ptr(b0d),
+           L.ptr(w2T), L.ptr(b2d), L.ptr(waT), L.ptr(bad), L.stream_ptr())
     np.testing.assert_allclose(ss1.cpu().numpy()[0], want.numpy()[0], rtol=1e-4, atol=1e-4)
