@@ -219,6 +219,15 @@ def run_ours(args, rank, local_rank, world):
     out = torch.empty_like(xs)
     eng.profile(xs, tt, out, B)
     prof = eng.profile(xs, tt, out, B)
+    names = {-1: "time_embedding", 0: "conv_in", 1: "groupnorm_silu", 2: "conv_tc", 3: "upsample2x", 4: "attention"}
+    breakdown = {}
+    for code, ms, fl in prof:
+        breakdown[names[code]] = breakdown.get(names[code], 0.0) + ms
+    if rank == 0 and os.path.isdir(os.path.join(ROOT, "gpurun_out")):
+        with open(os.path.join(ROOT, "gpurun_out", "ops_profile.txt"), "w") as fh:
+            for i, (code, ms, fl) in enumerate(prof):
+                op = eng.prog["ops"][i - 1] if i > 0 else []
+                fh.write("%3d %-15s %8.4f ms %8.1f TFLOP/s  %s\n" % (i, names[code], ms, fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0, op))
     conv = [(ms, fl) for code, ms, fl in prof if code == 2]
     conv_ms, conv_fl = sum(m for m, _ in conv), sum(f for _, f in conv)
     fwd_ms = sum(ms for _, ms, _ in prof)
@@ -234,17 +243,19 @@ def run_ours(args, rank, local_rank, world):
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s)" % pk_src,
                 "flop_per_launch_avg": conv_fl / len(conv), "ms_per_launch_avg": conv_ms / len(conv),
-                "conv_share_of_forward": conv_ms / fwd_ms, "forward_ms_serialised": fwd_ms,
+                "conv_share_of_forward": conv_ms / fwd_ms, "forward_ms_serialised": fwd_ms, "forward_ms_by_op": breakdown,
                 "end_to_end_tflops": GFLOP_PER_SAMPLE_STEP * 1e9 * B * (T - 1) / (ms_per_step * 1e-3) / 1e12}
 
     # ---- HBM-bound kernels: fused reverse step (12 B/element) and SaS noise (4 B/element), timed alone (burst peak)
     hbm = {}
-    n_el = B * CH * IMG * IMG
+    Bk = 4096  # BASELINE.json configs[2] full batch: 4096 x 3 x 32 x 32 (151 MB per launch, > L2)
+    kshape = [Bk, CH, IMG, IMG]
+    n_el = Bk * CH * IMG * IMG
     big = torch.empty(64 * 1024 * 1024, device=dev)  # 256 MB > L2: flushes between timed launches
     d = glp.dlpm
-    d.sample_A(shape, T)
-    eps = torch.randn(shape, device=dev)
-    xw = torch.randn(shape, device=dev)
+    d.sample_A(kshape, T)
+    eps = torch.randn(kshape, device=dev)
+    xw = torch.randn(kshape, device=dev)
 
     def time_kernel(fn, reps=20):
         t = 0.0
@@ -255,8 +266,8 @@ def run_ours(args, rank, local_rank, world):
             torch.cuda.synchronize()
             t += a.elapsed_time(b)
         return t / reps
-    ms_k3 = time_kernel(lambda: _lib.call("dlpm_b200_reverse_step", _lib.ptr(xw), _lib.ptr(eps), _lib.ptr(d.Sigmas), _lib.ptr(d.sched), 500,
-                                          None, T, B, CH * IMG * IMG, 0, None, 1, 2, 0, None, _lib.stream_ptr()))
+    ms_k3 = time_kernel(lambda: _lib.call("dlpm_b200_reverse_step", _lib.ptr(xw), _lib.ptr(eps), _lib.ptr(d.Sigmas), _lib.ptr(d.sched), min(500, T - 1),
+                                          None, T, Bk, CH * IMG * IMG, 0, None, 1, 2, 0, None, _lib.stream_ptr()))
     n_noise = 1 << 28
     nbuf = torch.empty(n_noise, device=dev)
     ms_k1 = time_kernel(lambda: _lib.call("dlpm_b200_sas", _lib.ptr(nbuf), None, n_noise // 3072, 3072, 1, ALPHA, 200.0, 1.0, 1, 2, 0,

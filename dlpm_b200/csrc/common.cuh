@@ -40,6 +40,24 @@ inline int grid_for(int64_t work_items, int threads, int max_waves = 8) {
   return (int)blocks;
 }
 
+// Division by a launch-constant via multiply-high (valid for 0 <= n < 2^31): the streaming kernels index
+// (sample, position) from a flat quad index; a 64-bit hardware-emulated divide there costs more than the memory traffic.
+struct FastDiv {
+  uint32_t d, mul, shr;
+  FastDiv() : d(1), mul(0), shr(0) {}
+  explicit FastDiv(uint32_t div) : d(div), mul(0), shr(0) {
+    if (div > 1) {
+      uint32_t lg = 0;
+      while ((1ull << lg) < div) ++lg;
+      const unsigned p = 31 + lg;
+      mul = (uint32_t)(((1ull << p) + div - 1) / div);
+      shr = p - 32;
+    }
+  }
+  __device__ __forceinline__ uint32_t div(uint32_t n) const { return d == 1 ? n : (__umulhi(n, mul) >> shr); }
+  __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const { q = div(n); r = n - q * d; }
+};
+
 // streaming 128-bit accesses (data touched once: bypass L1 allocation)
 __device__ __forceinline__ float4 ld_stream(const float4* p) {
   float4 v;

@@ -285,10 +285,15 @@ int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, c
   else if (C_out % 32 == 0) bn = 32;
   else if (C_out % 16 == 0) bn = 16;
   else { set_error("conv: C_out must be a multiple of 16 (got %d)", C_out); return DLPM_ERR_UNSUPPORTED; }
-  L->block_n = bn; L->block_k = bk;
+  L->block_k = bk;
   L->Wb = W_out;
   L->Hb = (128 / W_out) < H_out ? (128 / W_out) : H_out;
   L->Nb = 128 / (L->Wb * L->Hb);
+  {  // small problems (4x4 / 8x8 feature maps): prefer more, narrower tiles so that every SM gets work
+    const int64_t m_tiles = L->Nb == 1 ? B * (H_out / L->Hb) : (B + L->Nb - 1) / L->Nb;
+    while (bn > 128 && m_tiles * (C_out_pad / bn) < kNumSMs && C_out_pad % (bn / 2) == 0) bn /= 2;
+  }
+  L->block_n = bn;
   L->H_out = H_out; L->W_out = W_out;
   L->tiles_per_img = L->Nb == 1 ? H_out / L->Hb : 0;
   L->n_m_tiles = L->Nb == 1 ? (int)(B * L->tiles_per_img) : (int)((B + L->Nb - 1) / L->Nb);

@@ -36,6 +36,8 @@ static StableParams make_params(float alpha) {
   return p;
 }
 
+constexpr int kChunkQuads = 2048;  // quads per CTA iteration of the streaming kernels (8 per thread)
+
 __device__ __forceinline__ float clamp_A(float a, float clamp_a) { return clamp_a >= 0.f ? fminf(fmaxf(a, 0.f), clamp_a) : a; }
 __device__ __forceinline__ float clamp_sym(float v, float c) { return c >= 0.f ? fminf(fmaxf(v, -c), c) : v; }
 __device__ __forceinline__ float sel4(const float4& v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w)); }
@@ -65,7 +67,7 @@ __device__ __forceinline__ float4 normal_quad(const Philox& ph, uint32_t stream,
 template <bool VEC>
 __global__ void __launch_bounds__(256) k_stable_A(float* __restrict__ out, int64_t n_outer, int64_t inner, int mode,
                                                   StableParams sp, float clamp_a, uint64_t seed, uint64_t offset,
-                                                  int64_t sample_base) {
+                                                  int64_t sample_base, FastDiv fd, int chunk) {
   const Philox ph(seed);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   if (mode == DLPM_A_COMPACT) {
@@ -74,21 +76,35 @@ __global__ void __launch_bounds__(256) k_stable_A(float* __restrict__ out, int64
     return;
   }
   if (VEC) {
+    // block-contiguous chunks: the per-sample draws of a chunk are computed once into shared memory
     const int64_t qpr = inner >> 2, nq = n_outer * qpr;  // quads per row
-    int64_t last_o = -1;
-    float a_iso = 0.f;
-    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nq; q += stride) {
-      const int64_t o = q / qpr;
-      const uint32_t pos = (uint32_t)(q - o * qpr);
-      float4 v;
+    const bool fast = nq < (1ll << 31);
+    __shared__ float s_a[kChunkQuads];
+    for (int64_t q0 = (int64_t)blockIdx.x * chunk; q0 < nq; q0 += (int64_t)gridDim.x * chunk) {
+      const int64_t q1 = q0 + chunk < nq ? q0 + chunk : nq;
+      const int64_t o_first = fast ? (int64_t)fd.div((uint32_t)q0) : q0 / qpr;
       if (mode == DLPM_A_ISOTROPIC) {
-        if (o != last_o) { a_iso = clamp_A(sample_A(ph, sp, STREAM_A, offset, (uint64_t)(o + sample_base)), clamp_a); last_o = o; }
-        v = make_float4(a_iso, a_iso, a_iso, a_iso);
-      } else {
-        v = element_A4(ph, sp, STREAM_A, offset, (uint64_t)(o + sample_base), pos);
-        v.x = clamp_A(v.x, clamp_a); v.y = clamp_A(v.y, clamp_a); v.z = clamp_A(v.z, clamp_a); v.w = clamp_A(v.w, clamp_a);
+        const int64_t o_last = fast ? (int64_t)fd.div((uint32_t)(q1 - 1)) : (q1 - 1) / qpr;
+        __syncthreads();
+        for (int64_t sI = threadIdx.x; sI <= o_last - o_first; sI += blockDim.x)
+          s_a[sI] = clamp_A(sample_A(ph, sp, STREAM_A, offset, (uint64_t)(o_first + sI + sample_base)), clamp_a);
+        __syncthreads();
       }
-      st_stream(reinterpret_cast<float4*>(out) + q, v);
+      for (int64_t q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
+        uint32_t o32, pos;
+        if (fast) fd.divmod((uint32_t)q, o32, pos);
+        const int64_t o = fast ? (int64_t)o32 : q / qpr;
+        if (!fast) pos = (uint32_t)(q - o * qpr);
+        float4 v;
+        if (mode == DLPM_A_ISOTROPIC) {
+          const float a_iso = s_a[o - o_first];
+          v = make_float4(a_iso, a_iso, a_iso, a_iso);
+        } else {
+          v = element_A4(ph, sp, STREAM_A, offset, (uint64_t)(o + sample_base), pos);
+          v.x = clamp_A(v.x, clamp_a); v.y = clamp_A(v.y, clamp_a); v.z = clamp_A(v.z, clamp_a); v.w = clamp_A(v.w, clamp_a);
+        }
+        st_stream(reinterpret_cast<float4*>(out) + q, v);
+      }
     }
   } else {
     const int64_t n = n_outer * inner;
@@ -110,34 +126,46 @@ __global__ void __launch_bounds__(256) k_stable_A(float* __restrict__ out, int64
 template <bool VEC, int A_MODE>
 __global__ void __launch_bounds__(256) k_sas(float* __restrict__ out, const float* __restrict__ A_in, int64_t n_outer,
                                              int64_t inner, StableParams sp, float clamp_eps, float scale,
-                                             uint32_t g_stream, uint64_t seed, uint64_t offset, int64_t sample_base) {
+                                             uint32_t g_stream, uint64_t seed, uint64_t offset, int64_t sample_base,
+                                             FastDiv fd, int chunk) {
   const Philox ph(seed);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   if (VEC) {
     const int64_t qpr = inner >> 2, nq = n_outer * qpr;
-    int64_t last_o = -1;
-    float sa_iso = 1.f;
-    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nq; q += stride) {
-      const int64_t o = q / qpr;
-      const uint32_t pos = (uint32_t)(q - o * qpr);
-      const uint64_t sample = (uint64_t)(o + sample_base);
-      float4 g = normal_quad(ph, g_stream, offset, sample, pos);
+    const bool fast = nq < (1ll << 31);
+    __shared__ float s_sa[kChunkQuads];  // sqrt(A) of the samples touched by this chunk
+    for (int64_t q0 = (int64_t)blockIdx.x * chunk; q0 < nq; q0 += (int64_t)gridDim.x * chunk) {
+      const int64_t q1 = q0 + chunk < nq ? q0 + chunk : nq;
+      const int64_t o_first = fast ? (int64_t)fd.div((uint32_t)q0) : q0 / qpr;
       if (A_MODE == 1 || A_MODE == 3) {
-        if (o != last_o) {
-          sa_iso = __fsqrt_rn(A_MODE == 1 ? sample_A(ph, sp, STREAM_EPS_A, offset, sample) : __ldg(A_in + o));
-          last_o = o;
+        const int64_t o_last = fast ? (int64_t)fd.div((uint32_t)(q1 - 1)) : (q1 - 1) / qpr;
+        __syncthreads();
+        for (int64_t sI = threadIdx.x; sI <= o_last - o_first; sI += blockDim.x)
+          s_sa[sI] = __fsqrt_rn(A_MODE == 1 ? sample_A(ph, sp, STREAM_EPS_A, offset, (uint64_t)(o_first + sI + sample_base))
+                                            : __ldg(A_in + o_first + sI));
+        __syncthreads();
+      }
+      for (int64_t q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
+        uint32_t o32, pos;
+        if (fast) fd.divmod((uint32_t)q, o32, pos);
+        const int64_t o = fast ? (int64_t)o32 : q / qpr;
+        if (!fast) pos = (uint32_t)(q - o * qpr);
+        const uint64_t sample = (uint64_t)(o + sample_base);
+        float4 g = normal_quad(ph, g_stream, offset, sample, pos);
+        if (A_MODE == 1 || A_MODE == 3) {
+          const float sa_iso = s_sa[o - o_first];
+          g.x *= sa_iso; g.y *= sa_iso; g.z *= sa_iso; g.w *= sa_iso;
+        } else if (A_MODE == 2 || A_MODE == 4) {
+          const float4 a = (A_MODE == 2) ? element_A4(ph, sp, STREAM_EPS_A, offset, sample, pos)
+                                         : ld_stream(reinterpret_cast<const float4*>(A_in) + q);
+          g.x *= __fsqrt_rn(a.x); g.y *= __fsqrt_rn(a.y); g.z *= __fsqrt_rn(a.z); g.w *= __fsqrt_rn(a.w);
         }
-        g.x *= sa_iso; g.y *= sa_iso; g.z *= sa_iso; g.w *= sa_iso;
-      } else if (A_MODE == 2 || A_MODE == 4) {
-        const float4 a = (A_MODE == 2) ? element_A4(ph, sp, STREAM_EPS_A, offset, sample, pos)
-                                       : ld_stream(reinterpret_cast<const float4*>(A_in) + q);
-        g.x *= __fsqrt_rn(a.x); g.y *= __fsqrt_rn(a.y); g.z *= __fsqrt_rn(a.z); g.w *= __fsqrt_rn(a.w);
+        if (A_MODE != 0) {
+          g.x = scale * clamp_sym(g.x, clamp_eps); g.y = scale * clamp_sym(g.y, clamp_eps);
+          g.z = scale * clamp_sym(g.z, clamp_eps); g.w = scale * clamp_sym(g.w, clamp_eps);
+        }
+        st_stream(reinterpret_cast<float4*>(out) + q, g);
       }
-      if (A_MODE != 0) {
-        g.x = scale * clamp_sym(g.x, clamp_eps); g.y = scale * clamp_sym(g.y, clamp_eps);
-        g.z = scale * clamp_sym(g.z, clamp_eps); g.w = scale * clamp_sym(g.w, clamp_eps);
-      }
-      st_stream(reinterpret_cast<float4*>(out) + q, g);
     }
   } else {
     const int64_t n = n_outer * inner;
@@ -222,6 +250,11 @@ __device__ __forceinline__ float dlpm_update1(float x, float e, float z, const S
   const float mean = __fdiv_rn(__fsub_rn(x, __fmul_rn(c.c1, e)), c.g);
   return __fadd_rn(mean, __fmul_rn(c.sd, z));
 }
+// Production variant (in-kernel noise, nothing to be bit-compared against): reciprocal + FMAs instead of the IEEE
+// divide; differs from dlpm_update1 by <= 2 ulp.
+__device__ __forceinline__ float dlpm_update1_fast(float x, float e, float z, const StepCoef& c, float inv_g) {
+  return fmaf(c.sd, z, fmaf(-c.c1, e, x) * inv_g);
+}
 
 template <bool VEC, bool EPS_BF16>
 __device__ __forceinline__ float4 load_eps4(const void* eps, int64_t q) {
@@ -241,7 +274,7 @@ __global__ void __launch_bounds__(256) k_reverse_step(float* __restrict__ x, con
                                                       int t_imm, const int* __restrict__ t_dev, int T, int64_t B,
                                                       int64_t D, int flags, const float* __restrict__ z,
                                                       uint64_t seed, uint64_t offset, int64_t sample_base,
-                                                      float* __restrict__ hist) {
+                                                      float* __restrict__ hist, FastDiv fd) {
   const int t = t_dev ? *t_dev : t_imm;
   if (t < 1 || t >= T) return;
   const Philox ph(seed);
@@ -253,9 +286,12 @@ __global__ void __launch_bounds__(256) k_reverse_step(float* __restrict__ x, con
   const uint64_t off_t = offset + (uint64_t)t;
   if (VEC) {
     const int64_t qpr = D >> 2, nq = B * qpr;
+    const bool fast = nq < (1ll << 31);
     for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nq; q += stride) {
-      const int64_t b = q / qpr;
-      const uint32_t pos = (uint32_t)(q - b * qpr);
+      uint32_t b32, pos;
+      if (fast) fd.divmod((uint32_t)q, b32, pos);
+      const int64_t b = fast ? (int64_t)b32 : q / qpr;
+      if (!fast) pos = (uint32_t)(q - b * qpr);
       float4 xv = ld_rw(reinterpret_cast<const float4*>(x) + q);
       float4 ev = load_eps4<VEC, EPS_BF16>(eps, q);
       if (clip) {
@@ -273,8 +309,14 @@ __global__ void __launch_bounds__(256) k_reverse_step(float* __restrict__ x, con
                             : normal_quad(ph, STREAM_Z, off_t, (uint64_t)(b + sample_base), pos);
         if (!sig_full) {
           const StepCoef c = dlpm_coef(__ldg(Sigma + (int64_t)(t - 1) * B + b), __ldg(Sigma + (int64_t)t * B + b), row, t);
-          o.x = dlpm_update1(xv.x, ev.x, zv.x, c); o.y = dlpm_update1(xv.y, ev.y, zv.y, c);
-          o.z = dlpm_update1(xv.z, ev.z, zv.z, c); o.w = dlpm_update1(xv.w, ev.w, zv.w, c);
+          if (z) {  // injected noise (parity tests): reference evaluation order, bit-exact
+            o.x = dlpm_update1(xv.x, ev.x, zv.x, c); o.y = dlpm_update1(xv.y, ev.y, zv.y, c);
+            o.z = dlpm_update1(xv.z, ev.z, zv.z, c); o.w = dlpm_update1(xv.w, ev.w, zv.w, c);
+          } else {
+            const float inv_g = __frcp_rn(c.g);
+            o.x = dlpm_update1_fast(xv.x, ev.x, zv.x, c, inv_g); o.y = dlpm_update1_fast(xv.y, ev.y, zv.y, c, inv_g);
+            o.z = dlpm_update1_fast(xv.z, ev.z, zv.z, c, inv_g); o.w = dlpm_update1_fast(xv.w, ev.w, zv.w, c, inv_g);
+          }
         } else {
           const float4 s1 = ld_stream(reinterpret_cast<const float4*>(Sigma + (int64_t)(t - 1) * B * D) + q);
           const float4 st = ld_stream(reinterpret_cast<const float4*>(Sigma + (int64_t)t * B * D) + q);
@@ -316,7 +358,7 @@ __global__ void __launch_bounds__(256) k_lim_step(float* __restrict__ x, const v
                                                   const int* __restrict__ step_dev, int64_t B, int64_t D, int ode,
                                                   int isotropic, StableParams sp, float clamp_eps,
                                                   const float* __restrict__ e_L, uint64_t seed, uint64_t offset,
-                                                  int64_t sample_base, float* __restrict__ hist) {
+                                                  int64_t sample_base, float* __restrict__ hist, FastDiv fd, int chunk) {
   const int step = step_dev ? *step_dev : step_imm;
   const Philox ph(seed);
   const float4 cf = __ldg(reinterpret_cast<const float4*>(coef) + step);  // (score_scale, a, c_score, c_noise)
@@ -324,40 +366,54 @@ __global__ void __launch_bounds__(256) k_lim_step(float* __restrict__ x, const v
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   if (VEC) {
     const int64_t qpr = D >> 2, nq = B * qpr;
-    int64_t last_b = -1;
-    float sa = 1.f;
-    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nq; q += stride) {
-      const int64_t b = q / qpr;
-      const uint32_t pos = (uint32_t)(q - b * qpr);
-      const uint64_t sample = (uint64_t)(b + sample_base);
-      const float4 xv = ld_rw(reinterpret_cast<const float4*>(x) + q);
-      const float4 mv = load_eps4<VEC, EPS_BF16>(mo, q);
-      float4 o;
-      o.x = __fadd_rn(__fmul_rn(cf.y, xv.x), __fmul_rn(cf.z, __fmul_rn(mv.x, cf.x)));
-      o.y = __fadd_rn(__fmul_rn(cf.y, xv.y), __fmul_rn(cf.z, __fmul_rn(mv.y, cf.x)));
-      o.z = __fadd_rn(__fmul_rn(cf.y, xv.z), __fmul_rn(cf.z, __fmul_rn(mv.z, cf.x)));
-      o.w = __fadd_rn(__fmul_rn(cf.y, xv.w), __fmul_rn(cf.z, __fmul_rn(mv.w, cf.x)));
-      if (!ode) {
-        float4 n4;
-        if (e_L) {
-          n4 = ld_stream(reinterpret_cast<const float4*>(e_L) + q);
-        } else {
-          n4 = normal_quad(ph, STREAM_G, off_s, sample, pos);
-          if (isotropic) {
-            if (b != last_b) { sa = __fsqrt_rn(sample_A(ph, sp, STREAM_EPS_A, off_s, sample)); last_b = b; }
-            n4.x *= sa; n4.y *= sa; n4.z *= sa; n4.w *= sa;
-          } else {
-            const float4 a = element_A4(ph, sp, STREAM_EPS_A, off_s, sample, pos);
-            n4.x *= __fsqrt_rn(a.x); n4.y *= __fsqrt_rn(a.y); n4.z *= __fsqrt_rn(a.z); n4.w *= __fsqrt_rn(a.w);
-          }
-          n4.x = clamp_sym(n4.x, clamp_eps); n4.y = clamp_sym(n4.y, clamp_eps);
-          n4.z = clamp_sym(n4.z, clamp_eps); n4.w = clamp_sym(n4.w, clamp_eps);
-        }
-        o.x = __fadd_rn(o.x, __fmul_rn(cf.w, n4.x)); o.y = __fadd_rn(o.y, __fmul_rn(cf.w, n4.y));
-        o.z = __fadd_rn(o.z, __fmul_rn(cf.w, n4.z)); o.w = __fadd_rn(o.w, __fmul_rn(cf.w, n4.w));
+    const bool fast = nq < (1ll << 31);
+    const bool iso_draw = !ode && !e_L && isotropic;
+    __shared__ float s_sa[kChunkQuads];
+    for (int64_t q0 = (int64_t)blockIdx.x * chunk; q0 < nq; q0 += (int64_t)gridDim.x * chunk) {
+      const int64_t q1 = q0 + chunk < nq ? q0 + chunk : nq;
+      const int64_t b_first = fast ? (int64_t)fd.div((uint32_t)q0) : q0 / qpr;
+      if (iso_draw) {
+        const int64_t b_last = fast ? (int64_t)fd.div((uint32_t)(q1 - 1)) : (q1 - 1) / qpr;
+        __syncthreads();
+        for (int64_t sI = threadIdx.x; sI <= b_last - b_first; sI += blockDim.x)
+          s_sa[sI] = __fsqrt_rn(sample_A(ph, sp, STREAM_EPS_A, off_s, (uint64_t)(b_first + sI + sample_base)));
+        __syncthreads();
       }
-      reinterpret_cast<float4*>(x)[q] = o;
-      if (hist) st_stream(reinterpret_cast<float4*>(hist) + q, o);
+      for (int64_t q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
+        uint32_t b32, pos;
+        if (fast) fd.divmod((uint32_t)q, b32, pos);
+        const int64_t b = fast ? (int64_t)b32 : q / qpr;
+        if (!fast) pos = (uint32_t)(q - b * qpr);
+        const uint64_t sample = (uint64_t)(b + sample_base);
+        const float4 xv = ld_rw(reinterpret_cast<const float4*>(x) + q);
+        const float4 mv = load_eps4<VEC, EPS_BF16>(mo, q);
+        float4 o;
+        o.x = __fadd_rn(__fmul_rn(cf.y, xv.x), __fmul_rn(cf.z, __fmul_rn(mv.x, cf.x)));
+        o.y = __fadd_rn(__fmul_rn(cf.y, xv.y), __fmul_rn(cf.z, __fmul_rn(mv.y, cf.x)));
+        o.z = __fadd_rn(__fmul_rn(cf.y, xv.z), __fmul_rn(cf.z, __fmul_rn(mv.z, cf.x)));
+        o.w = __fadd_rn(__fmul_rn(cf.y, xv.w), __fmul_rn(cf.z, __fmul_rn(mv.w, cf.x)));
+        if (!ode) {
+          float4 n4;
+          if (e_L) {
+            n4 = ld_stream(reinterpret_cast<const float4*>(e_L) + q);
+          } else {
+            n4 = normal_quad(ph, STREAM_G, off_s, sample, pos);
+            if (isotropic) {
+              const float sa = s_sa[b - b_first];
+              n4.x *= sa; n4.y *= sa; n4.z *= sa; n4.w *= sa;
+            } else {
+              const float4 a = element_A4(ph, sp, STREAM_EPS_A, off_s, sample, pos);
+              n4.x *= __fsqrt_rn(a.x); n4.y *= __fsqrt_rn(a.y); n4.z *= __fsqrt_rn(a.z); n4.w *= __fsqrt_rn(a.w);
+            }
+            n4.x = clamp_sym(n4.x, clamp_eps); n4.y = clamp_sym(n4.y, clamp_eps);
+            n4.z = clamp_sym(n4.z, clamp_eps); n4.w = clamp_sym(n4.w, clamp_eps);
+          }
+          o.x = __fadd_rn(o.x, __fmul_rn(cf.w, n4.x)); o.y = __fadd_rn(o.y, __fmul_rn(cf.w, n4.y));
+          o.z = __fadd_rn(o.z, __fmul_rn(cf.w, n4.z)); o.w = __fadd_rn(o.w, __fmul_rn(cf.w, n4.w));
+        }
+        reinterpret_cast<float4*>(x)[q] = o;
+        if (hist) st_stream(reinterpret_cast<float4*>(hist) + q, o);
+      }
     }
   } else {
     const int64_t n = B * D;
@@ -447,6 +503,20 @@ __global__ void __launch_bounds__(256) k_postprocess(float* __restrict__ out, co
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// chunk size (quads per CTA iteration, multiple of 256, <= kChunkQuads) and grid for the chunked streaming kernels:
+// aim for >= 8 CTAs per SM when the problem is large enough, never more CTAs than chunks.
+static inline void chunk_grid(int64_t nq, int* chunk, int* grid) {
+  int64_t c = nq / ((int64_t)kNumSMs * 8);
+  c = (c / 256) * 256;
+  if (c < 256) c = 256;
+  if (c > kChunkQuads) c = kChunkQuads;
+  int64_t g = (nq + c - 1) / c;
+  if (g > (int64_t)kNumSMs * 16) g = (int64_t)kNumSMs * 16;
+  if (g < 1) g = 1;
+  *chunk = (int)c;
+  *grid = (int)g;
+}
+
 }  // namespace dlpm
 
 using namespace dlpm;
@@ -466,19 +536,22 @@ int dlpm_b200_stable_A(float* out, int64_t n_outer, int64_t inner, int mode, flo
   cudaStream_t s = (cudaStream_t)stream;
   const bool vec = mode != DLPM_A_COMPACT && (inner % 4 == 0) && aligned16(out);
   const int64_t items = mode == DLPM_A_COMPACT ? n_outer : (vec ? n_outer * inner / 4 : n_outer * inner);
-  const int grid = grid_for(items, 256);
-  if (vec) k_stable_A<true><<<grid, 256, 0, s>>>(out, n_outer, inner, mode, sp, clamp_a, seed, offset, sample_base);
-  else k_stable_A<false><<<grid, 256, 0, s>>>(out, n_outer, inner, mode, sp, clamp_a, seed, offset, sample_base);
+  int grid = grid_for(items, 256), chunk = 256;
+  if (vec) chunk_grid(items, &chunk, &grid);
+  const FastDiv fd((uint32_t)(vec ? inner / 4 : 1));
+  if (vec) k_stable_A<true><<<grid, 256, 0, s>>>(out, n_outer, inner, mode, sp, clamp_a, seed, offset, sample_base, fd, chunk);
+  else k_stable_A<false><<<grid, 256, 0, s>>>(out, n_outer, inner, mode, sp, clamp_a, seed, offset, sample_base, fd, chunk);
   DLPM_CHECK_LAUNCH("stable_A");
   return DLPM_OK;
 }
 
 template <int A_MODE>
-static void launch_sas(bool vec, int grid, cudaStream_t s, float* out, const float* A_in, int64_t n_outer, int64_t inner,
+static void launch_sas(bool vec, int grid, int chunk, cudaStream_t s, float* out, const float* A_in, int64_t n_outer, int64_t inner,
                        const StableParams& sp, float clamp_eps, float scale, uint32_t g_stream, uint64_t seed,
                        uint64_t offset, int64_t sample_base) {
-  if (vec) k_sas<true, A_MODE><<<grid, 256, 0, s>>>(out, A_in, n_outer, inner, sp, clamp_eps, scale, g_stream, seed, offset, sample_base);
-  else k_sas<false, A_MODE><<<grid, 256, 0, s>>>(out, A_in, n_outer, inner, sp, clamp_eps, scale, g_stream, seed, offset, sample_base);
+  const FastDiv fd((uint32_t)(vec ? inner / 4 : 1));
+  if (vec) k_sas<true, A_MODE><<<grid, 256, 0, s>>>(out, A_in, n_outer, inner, sp, clamp_eps, scale, g_stream, seed, offset, sample_base, fd, chunk);
+  else k_sas<false, A_MODE><<<grid, 256, 0, s>>>(out, A_in, n_outer, inner, sp, clamp_eps, scale, g_stream, seed, offset, sample_base, fd, chunk);
 }
 
 int dlpm_b200_sas(float* out, const float* A_in, int64_t n_outer, int64_t inner, int isotropic, float alpha,
@@ -490,13 +563,14 @@ int dlpm_b200_sas(float* out, const float* A_in, int64_t n_outer, int64_t inner,
   const StableParams sp = make_params(alpha);
   cudaStream_t s = (cudaStream_t)stream;
   const bool vec = (inner % 4 == 0) && aligned16(out) && (A_in == nullptr || isotropic || aligned16(A_in));
-  const int grid = grid_for(vec ? n_outer * inner / 4 : n_outer * inner, 256);
+  int grid = grid_for(n_outer * inner, 256), chunk = 256;
+  if (vec) chunk_grid(n_outer * inner / 4, &chunk, &grid);
   const int mode = A_in ? (isotropic ? 3 : 4) : (isotropic ? 1 : 2);
   switch (mode) {
-    case 1: launch_sas<1>(vec, grid, s, out, A_in, n_outer, inner, sp, clamp_eps, scale, STREAM_G, seed, offset, sample_base); break;
-    case 2: launch_sas<2>(vec, grid, s, out, A_in, n_outer, inner, sp, clamp_eps, scale, STREAM_G, seed, offset, sample_base); break;
-    case 3: launch_sas<3>(vec, grid, s, out, A_in, n_outer, inner, sp, clamp_eps, scale, STREAM_G, seed, offset, sample_base); break;
-    default: launch_sas<4>(vec, grid, s, out, A_in, n_outer, inner, sp, clamp_eps, scale, STREAM_G, seed, offset, sample_base); break;
+    case 1: launch_sas<1>(vec, grid, chunk, s, out, A_in, n_outer, inner, sp, clamp_eps, scale, STREAM_G, seed, offset, sample_base); break;
+    case 2: launch_sas<2>(vec, grid, chunk, s, out, A_in, n_outer, inner, sp, clamp_eps, scale, STREAM_G, seed, offset, sample_base); break;
+    case 3: launch_sas<3>(vec, grid, chunk, s, out, A_in, n_outer, inner, sp, clamp_eps, scale, STREAM_G, seed, offset, sample_base); break;
+    default: launch_sas<4>(vec, grid, chunk, s, out, A_in, n_outer, inner, sp, clamp_eps, scale, STREAM_G, seed, offset, sample_base); break;
   }
   DLPM_CHECK_LAUNCH("sas");
   return DLPM_OK;
@@ -509,8 +583,9 @@ int dlpm_b200_normal(float* out, int64_t n_outer, int64_t inner, uint64_t seed, 
   if (n_outer == 0) return DLPM_OK;
   StableParams sp = make_params(2.0f);
   const bool vec = (inner % 4 == 0) && aligned16(out);
-  const int grid = grid_for(vec ? n_outer * inner / 4 : n_outer * inner, 256);
-  launch_sas<0>(vec, grid, (cudaStream_t)stream, out, nullptr, n_outer, inner, sp, -1.f, 1.f, STREAM_Z, seed, offset, sample_base);
+  int grid = grid_for(n_outer * inner, 256), chunk = 256;
+  if (vec) chunk_grid(n_outer * inner / 4, &chunk, &grid);
+  launch_sas<0>(vec, grid, chunk, (cudaStream_t)stream, out, nullptr, n_outer, inner, sp, -1.f, 1.f, STREAM_Z, seed, offset, sample_base);
   DLPM_CHECK_LAUNCH("normal");
   return DLPM_OK;
 }
@@ -540,7 +615,8 @@ static int launch_step(float* x, const void* eps, const float* Sigma, const floa
                    (!(flags & DLPM_STEP_SIGMA_FULL) || (aligned16(Sigma) && (B * D) % 4 == 0));
   const int grid = grid_for(vec ? B * D / 4 : B * D, 256);
   cudaStream_t s = (cudaStream_t)stream;
-#define L(V, H) k_reverse_step<V, H, MODE><<<grid, 256, 0, s>>>(x, eps, Sigma, sched, t, t_dev, T, B, D, flags, z, seed, offset, sample_base, hist)
+  const FastDiv fd((uint32_t)(vec ? D / 4 : 1));
+#define L(V, H) k_reverse_step<V, H, MODE><<<grid, 256, 0, s>>>(x, eps, Sigma, sched, t, t_dev, T, B, D, flags, z, seed, offset, sample_base, hist, fd)
   if (vec) { if (bf16) L(true, true); else L(true, false); }
   else { if (bf16) L(false, true); else L(false, false); }
 #undef L
@@ -579,9 +655,11 @@ int dlpm_b200_lim_step(float* x, const void* model_out, const float* coef, int s
   const bool bf16 = flags & DLPM_STEP_EPS_BF16;
   const bool vec = (D % 4 == 0) && aligned16(x) && (reinterpret_cast<uintptr_t>(model_out) % (bf16 ? 8 : 16) == 0) &&
                    (!e_L || aligned16(e_L)) && (!hist_out || aligned16(hist_out));
-  const int grid = grid_for(vec ? B * D / 4 : B * D, 256);
+  int grid = grid_for(B * D, 256), chunk = 256;
+  if (vec) chunk_grid(B * D / 4, &chunk, &grid);
   cudaStream_t s = (cudaStream_t)stream;
-#define L(V, H) k_lim_step<V, H><<<grid, 256, 0, s>>>(x, model_out, coef, step, step_dev, B, D, ode, isotropic, sp, clamp_eps, e_L, seed, offset, sample_base, hist_out)
+  const FastDiv fd((uint32_t)(vec ? D / 4 : 1));
+#define L(V, H) k_lim_step<V, H><<<grid, 256, 0, s>>>(x, model_out, coef, step, step_dev, B, D, ode, isotropic, sp, clamp_eps, e_L, seed, offset, sample_base, hist_out, fd, chunk)
   if (vec) { if (bf16) L(true, true); else L(true, false); }
   else { if (bf16) L(false, true); else L(false, false); }
 #undef L

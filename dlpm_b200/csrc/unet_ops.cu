@@ -3,8 +3,12 @@
 //   QKV attention                    unet.py:231-250
 //   input conv 3->C                  unet.py:347          nearest upsample x2   unet.py:73
 //   timestep embedding + emb_layers  nn.py:103-121, unet.py:335-339,145-151,477
+#include <cooperative_groups.h>
+
 #include "../../include/dlpm_b200_unet.h"
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace dlpm {
 
@@ -109,6 +113,113 @@ __global__ void __launch_bounds__(kGnThreads) k_groupnorm(__nv_bfloat16* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
+// K6 (production variant): ONE HBM read + ONE HBM write per GroupNorm.  A thread-block CLUSTER of cs CTAs owns one sample;
+// every CTA keeps its HW/cs pixels (<= 96 KB of bf16) in shared memory, per-channel partial sums are exchanged
+// through distributed shared memory (fixed rank order -> bitwise deterministic), then the data is normalised from
+// shared memory.  No second pass over global memory, no atomics.
+// ------------------------------------------------------------------------------------------------
+constexpr int kGnClusterSmemData = 96 * 1024;
+
+__global__ void __launch_bounds__(kGnThreads) k_groupnorm_cluster(__nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ in0,
+                                                                  int C0, const __nv_bfloat16* __restrict__ in1, int C1, int HW,
+                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                  const float* __restrict__ ss, int ss_rows, int64_t ss_stride,
+                                                                  int64_t ss_off, int apply_silu, int pix_per_cta) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int cs = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+  const int n = blockIdx.x / cs;
+  const int C = C0 + C1, nvec = C >> 3;
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  uint4* data = reinterpret_cast<uint4*>(sm_raw);                                  // [pix_per_cta][nvec] 16-byte vectors
+  float* psum = reinterpret_cast<float*>(sm_raw + (size_t)pix_per_cta * C * 2);     // [C] this CTA's per-channel sums
+  float* psq = psum + C;                                                            // [C]
+  float* coef_a = psq + C;                                                          // [C]
+  float* coef_b = coef_a + C;                                                       // [C]
+  float* part = coef_b + C;                                                         // [parts][C][2] scratch, parts * C <= 512
+  const int slots = kGnThreads / nvec;
+  const int v = threadIdx.x % nvec, slot = threadIdx.x / nvec;
+  const bool active = slot < slots;
+  const int c = v * 8;
+  const int p0 = rank * pix_per_cta;
+  const __nv_bfloat16* src = (c < C0) ? in0 + ((int64_t)n * HW + p0) * C0 + c : in1 + ((int64_t)n * HW + p0) * C1 + (c - C0);
+  const int src_stride = (c < C0) ? C0 : C1;
+  // phase 1: global -> shared (the only read of the tensor)
+  if (active)
+    for (int p = slot; p < pix_per_cta; p += slots) data[p * nvec + v] = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)p * src_stride));
+  __syncthreads();
+  // phase 2: per-channel sums over this CTA's pixels (2-byte shared loads, consecutive threads = consecutive channels)
+  const int parts = kGnThreads / C > 0 ? kGnThreads / C : 1;
+  {
+    const int ch = threadIdx.x % C, pt = threadIdx.x / C;
+    if (pt < parts) {
+      const __nv_bfloat16* col = reinterpret_cast<const __nv_bfloat16*>(sm_raw) + ch;
+      float sA = 0.f, qA = 0.f;
+      for (int p = pt; p < pix_per_cta; p += parts) {
+        const float xv = __bfloat162float(col[p * C]);
+        sA += xv;
+        qA = fmaf(xv, xv, qA);
+      }
+      part[(pt * C + ch) * 2] = sA;
+      part[(pt * C + ch) * 2 + 1] = qA;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float sA = 0.f, qA = 0.f;
+    for (int pt = 0; pt < parts; ++pt) { sA += part[(pt * C + threadIdx.x) * 2]; qA += part[(pt * C + threadIdx.x) * 2 + 1]; }
+    psum[threadIdx.x] = sA;
+    psq[threadIdx.x] = qA;
+  }
+  cluster.sync();
+  // phase 3: totals over the cluster (DSMEM reads, fixed order), group statistics, affine coefficients
+  if (threadIdx.x < C) {
+    float sA = 0.f, qA = 0.f;
+    for (int r = 0; r < cs; ++r) {
+      const float* rs = cluster.map_shared_rank(psum, r);
+      const float* rq = cluster.map_shared_rank(psq, r);
+      sA += rs[threadIdx.x];
+      qA += rq[threadIdx.x];
+    }
+    part[threadIdx.x * 2] = sA;
+    part[threadIdx.x * 2 + 1] = qA;
+  }
+  __syncthreads();
+  if (threadIdx.x < C) {
+    const int G = C < 32 ? C : 32, cpg = C / G, g = threadIdx.x / cpg;
+    float sA = 0.f, qA = 0.f;
+    for (int k = 0; k < cpg; ++k) { sA += part[(g * cpg + k) * 2]; qA += part[(g * cpg + k) * 2 + 1]; }
+    const float inv_n = 1.0f / (float)(cpg * HW);
+    const float mean = sA * inv_n;
+    const float rstd = rsqrtf(fmaxf(qA * inv_n - mean * mean, 0.f) + 1e-5f);
+    float ga = __ldg(gamma + threadIdx.x) * rstd;
+    float be = __ldg(beta + threadIdx.x) - mean * ga;
+    if (ss) {
+      const float* row = ss + (ss_rows == 1 ? 0 : (int64_t)n * ss_stride) + ss_off;
+      const float sc = 1.0f + __ldg(row + threadIdx.x), sh = __ldg(row + C + threadIdx.x);
+      ga *= sc;
+      be = be * sc + sh;
+    }
+    coef_a[threadIdx.x] = ga;
+    coef_b[threadIdx.x] = be;
+  }
+  cluster.sync();  // every CTA has finished reading its peers' shared memory; also orders coef_* for this CTA
+  // phase 4: normalise from shared memory -> global (the only write)
+  if (active) {
+    float a[8], b[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { a[e] = coef_a[c + e]; b[e] = coef_b[c + e]; }
+    __nv_bfloat16* dst = out + ((int64_t)n * HW + p0) * C + c;
+    for (int p = slot; p < pix_per_cta; p += slots) {
+      float x[8];
+      unpack8(data[p * nvec + v], x);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { x[e] = fmaf(x[e], a[e], b[e]); if (apply_silu) x[e] = silu_f(x[e]); }
+      *reinterpret_cast<uint4*>(dst + (int64_t)p * C) = pack8(x);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K7 attention: one CTA per (sample, head); K and V of the head staged in shared memory as fp32;
 // one query row per thread with an online softmax.  L <= 1024, d = C/heads <= 64.
 // ------------------------------------------------------------------------------------------------
@@ -151,39 +262,72 @@ __global__ void __launch_bounds__(256) k_attention(__nv_bfloat16* __restrict__ o
 }
 
 // ------------------------------------------------------------------------------------------------
-// input conv: NCHW fp32 -> NHWC bf16, 3x3 pad 1, C_in <= 4.  Thread = (pixel, 8 output channels).
+// input conv: NCHW fp32 -> NHWC bf16, 3x3 pad 1, C_in <= 4 (fp32 FMA: the network input keeps full precision).
+// One CTA per (image, band of kRows output rows).  Weights arrive pre-transposed [C_in*9][C_out] (in-major) and are
+// copied to shared memory once per CTA; thread = (pixel x, g) owns the 16 channels {32*j + 4*g .. +3, j = 0..3} so the
+// four 16-byte weight reads of a warp are contiguous (conflict-free) and broadcast across pixels.
 // ------------------------------------------------------------------------------------------------
+constexpr int kConvInRows = 4;
+
 __global__ void __launch_bounds__(256) k_conv_in(__nv_bfloat16* __restrict__ out, const float* __restrict__ x,
-                                                 const float* __restrict__ w, const float* __restrict__ bias, int64_t B, int C_in,
-                                                 int C_out, int H, int W) {
-  extern __shared__ float sm[];  // w [C_out][C_in*9], bias [C_out]
+                                                 const float* __restrict__ wT, const float* __restrict__ bias, int C_in, int C_out,
+                                                 int H, int W) {
+  extern __shared__ float sm[];
   const int K = C_in * 9;
-  for (int i = threadIdx.x; i < C_out * K; i += blockDim.x) sm[i] = w[i];
-  for (int i = threadIdx.x; i < C_out; i += blockDim.x) sm[C_out * K + i] = bias[i];
+  float* s_w = sm;                    // [K][C_out]
+  float* s_b = s_w + K * C_out;       // [C_out]
+  float* s_in = s_b + C_out;          // [C_in][kRows + 2][W + 2]
+  const int bands = (H + kConvInRows - 1) / kConvInRows;
+  const int n = blockIdx.x / bands, y0 = (blockIdx.x % bands) * kConvInRows;
+  for (int i = threadIdx.x; i < K * C_out / 4; i += blockDim.x)
+    reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(wT) + i);
+  for (int i = threadIdx.x; i < C_out; i += blockDim.x) s_b[i] = __ldg(bias + i);
+  const int Wp = W + 2, R = kConvInRows + 2;
+  for (int i = threadIdx.x; i < C_in * R * Wp; i += blockDim.x) {
+    const int ci = i / (R * Wp), r = (i / Wp) % R, xx = i % Wp - 1;
+    const int yy = y0 + r - 1;
+    s_in[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(x + (((int64_t)n * C_in + ci) * H + yy) * W + xx) : 0.f;
+  }
   __syncthreads();
-  const int groups = C_out >> 3;
-  const int64_t total = B * H * W * groups;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int g = (int)(idx % groups);
-    const int64_t pix = idx / groups;
-    const int xw = (int)(pix % W), yh = (int)((pix / W) % H);
-    const int64_t n = pix / ((int64_t)W * H);
-    float in[36];
+  const int sets = C_out >> 5;            // 32-channel sets; a thread owns 4 channels of up to 4 sets
+  const int gq = threadIdx.x & 7;         // which 4-channel slice inside each 32-channel set
+  const int items = kConvInRows * W * ((sets + 3) / 4);
+  for (int item = threadIdx.x >> 3; item < items; item += blockDim.x >> 3) {
+    const int sb = item / (kConvInRows * W);  // block of 4 sets (C_out > 128)
+    const int rem = item - sb * kConvInRows * W;
+    const int row = rem / W, px = rem - row * W;
+    if (y0 + row >= H) continue;
+    float acc[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = (sb * 4 + j) * 32 + gq * 4;
+      const float4 bv = (sb * 4 + j) < sets ? *reinterpret_cast<const float4*>(s_b + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      acc[j][0] = bv.x; acc[j][1] = bv.y; acc[j][2] = bv.z; acc[j][3] = bv.w;
+    }
     for (int ci = 0; ci < C_in; ++ci)
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
-        const int yy = yh + t / 3 - 1, xx = xw + t % 3 - 1;
-        in[ci * 9 + t] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(x + ((n * C_in + ci) * H + yy) * W + xx) : 0.f;
-      }
-    float acc[8];
+        const float v = s_in[(ci * R + row + t / 3) * Wp + px + t % 3];
+        const float* wr = s_w + (ci * 9 + t) * C_out + gq * 4;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float* wr = sm + (g * 8 + e) * K;
-      float a = sm[C_out * K + g * 8 + e];
-      for (int k = 0; k < K; ++k) a = fmaf(in[k], wr[k], a);
-      acc[e] = a;
+        for (int j = 0; j < 4; ++j) {
+          if ((sb * 4 + j) < sets) {
+            const float4 wv = *reinterpret_cast<const float4*>(wr + (sb * 4 + j) * 32);
+            acc[j][0] = fmaf(v, wv.x, acc[j][0]); acc[j][1] = fmaf(v, wv.y, acc[j][1]);
+            acc[j][2] = fmaf(v, wv.z, acc[j][2]); acc[j][3] = fmaf(v, wv.w, acc[j][3]);
+          }
+        }
+      }
+    __nv_bfloat16* dst = out + (((int64_t)n * H + y0 + row) * W + px) * C_out + gq * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if ((sb * 4 + j) < sets) {
+        uint2 o;
+        *reinterpret_cast<__nv_bfloat162*>(&o.x) = __floats2bfloat162_rn(acc[j][0], acc[j][1]);
+        *reinterpret_cast<__nv_bfloat162*>(&o.y) = __floats2bfloat162_rn(acc[j][2], acc[j][3]);
+        *reinterpret_cast<uint2*>(dst + (sb * 4 + j) * 32) = o;
+      }
     }
-    *reinterpret_cast<uint4*>(out + pix * C_out + g * 8) = pack8(acc);
   }
 }
 
@@ -200,59 +344,56 @@ __global__ void __launch_bounds__(256) k_upsample2x(uint4* __restrict__ out, con
 }
 
 // ------------------------------------------------------------------------------------------------
-// timestep embedding (one CTA per row) and the concatenated emb_layers GEMV
+// timestep embedding + emb_layers: three launches of one K-split GEMV kernel.
+//   out[r][j] = act( bias[j] + sum_k in[r][k] * WT[k][j] ),  CTA = 32 outputs x 8 K-slices (one warp per slice,
+//   lanes = consecutive outputs -> coalesced in-major weight reads), reduced through shared memory.
+//   input mode 1 builds the sinusoidal embedding of t (nn.py:103-121) on the fly.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512) k_time_embed(float* __restrict__ semb, const float* __restrict__ t,
-                                                    const int* __restrict__ t_dev, float inv_T, int mc,
-                                                    const float* __restrict__ w0T, const float* __restrict__ b0,
-                                                    const float* __restrict__ w2T, const float* __restrict__ b2) {
-  extern __shared__ float sm[];  // e0 [mc], h1 [4mc]
-  float* e0 = sm;
-  float* h1 = sm + mc;
-  const int r = blockIdx.x, E = 4 * mc, half = mc / 2;
-  const float tv = t_dev ? (float)(*t_dev) * inv_T : t[r];
-  for (int i = threadIdx.x; i < mc; i += blockDim.x) {
-    if (i < 2 * half) {
-      const int k = i < half ? i : i - half;
-      const float freq = expf(-9.210340371976184f * (float)k / (float)half);  // exp(-ln(10000) k / half), nn.py:113-115
-      const float arg = tv * freq;
-      e0[i] = i < half ? cosf(arg) : sinf(arg);
-    } else {
-      e0[i] = 0.f;  // odd dim padding (nn.py:118-119)
+__global__ void __launch_bounds__(256) k_gemv_rows(float* __restrict__ out, const float* __restrict__ in, const float* __restrict__ t,
+                                                   const int* __restrict__ t_dev, float inv_T, int sinus, int K, int64_t N,
+                                                   const float* __restrict__ WT, const float* __restrict__ bias, int act_out) {
+  extern __shared__ float sm[];  // in row [K], partial [8][32]
+  float* s_in = sm;
+  float* s_part = sm + K;
+  const int r = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (sinus) {
+    const float tv = t_dev ? (float)(*t_dev) * inv_T : t[r];
+    const int half = K / 2;
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+      if (i < 2 * half) {
+        const int k = i < half ? i : i - half;
+        const float arg = tv * expf(-9.210340371976184f * (float)k / (float)half);  // exp(-ln(10000) k / half)
+        s_in[i] = i < half ? cosf(arg) : sinf(arg);
+      } else {
+        s_in[i] = 0.f;  // odd-dim padding (nn.py:118-119)
+      }
     }
+  } else {
+    for (int i = threadIdx.x; i < K; i += blockDim.x) s_in[i] = in[(int64_t)r * K + i];
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < E; j += blockDim.x) {
-    float a = __ldg(b0 + j);
-    for (int k = 0; k < mc; ++k) a = fmaf(e0[k], __ldg(w0T + (int64_t)k * E + j), a);
-    h1[j] = a / (1.0f + expf(-a));
-  }
-  __syncthreads();
-  for (int j = threadIdx.x; j < E; j += blockDim.x) {
-    float a = __ldg(b2 + j);
-    for (int k = 0; k < E; ++k) a = fmaf(h1[k], __ldg(w2T + (int64_t)k * E + j), a);
-    semb[(int64_t)r * E + j] = a / (1.0f + expf(-a));  // every emb_layers starts with SiLU (unet.py:145-146)
-  }
-}
-
-__global__ void __launch_bounds__(256) k_emb_layers(float* __restrict__ ss, const float* __restrict__ semb, int E, int64_t ss_total,
-                                                    const float* __restrict__ wallT, const float* __restrict__ ball) {
-  extern __shared__ float sm[];  // semb row [E]
-  const int r = blockIdx.y;
-  for (int i = threadIdx.x; i < E; i += blockDim.x) sm[i] = semb[(int64_t)r * E + i];
-  __syncthreads();
-  const int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (o >= ss_total) return;
+  const int64_t j = (int64_t)blockIdx.x * 32 + lane;
+  const int k0 = (K * warp) / 8, k1 = (K * (warp + 1)) / 8;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  int k = 0;
-  for (; k + 3 < E; k += 4) {
-    a0 = fmaf(sm[k], __ldg(wallT + (int64_t)k * ss_total + o), a0);
-    a1 = fmaf(sm[k + 1], __ldg(wallT + (int64_t)(k + 1) * ss_total + o), a1);
-    a2 = fmaf(sm[k + 2], __ldg(wallT + (int64_t)(k + 2) * ss_total + o), a2);
-    a3 = fmaf(sm[k + 3], __ldg(wallT + (int64_t)(k + 3) * ss_total + o), a3);
+  if (j < N) {
+    int k = k0;
+    for (; k + 3 < k1; k += 4) {
+      a0 = fmaf(s_in[k], __ldg(WT + (int64_t)k * N + j), a0);
+      a1 = fmaf(s_in[k + 1], __ldg(WT + (int64_t)(k + 1) * N + j), a1);
+      a2 = fmaf(s_in[k + 2], __ldg(WT + (int64_t)(k + 2) * N + j), a2);
+      a3 = fmaf(s_in[k + 3], __ldg(WT + (int64_t)(k + 3) * N + j), a3);
+    }
+    for (; k < k1; ++k) a0 = fmaf(s_in[k], __ldg(WT + (int64_t)k * N + j), a0);
   }
-  for (; k < E; ++k) a0 = fmaf(sm[k], __ldg(wallT + (int64_t)k * ss_total + o), a0);
-  ss[(int64_t)r * ss_total + o] = __ldg(ball + o) + ((a0 + a1) + (a2 + a3));
+  s_part[warp * 32 + lane] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (warp == 0 && j < N) {
+    float a = __ldg(bias + j);
+#pragma unroll
+    for (int wI = 0; wI < 8; ++wI) a += s_part[wI * 32 + lane];
+    if (act_out) a = a / (1.0f + expf(-a));
+    out[(int64_t)r * N + j] = a;
+  }
 }
 
 }  // namespace dlpm
@@ -270,17 +411,50 @@ int dlpm_b200_groupnorm_silu(void* out, const void* in0, int C0, const void* in1
   DLPM_REQUIRE(B >= 0 && HW >= 1 && B < (1ll << 31), "groupnorm: bad sizes");
   DLPM_REQUIRE(!ss || ss_rows == 1 || ss_rows == B, "groupnorm: ss_rows must be 1 or B");
   if (B == 0) return DLPM_OK;
+  auto* o = reinterpret_cast<__nv_bfloat16*>(out);
+  auto* i0 = reinterpret_cast<const __nv_bfloat16*>(in0);
+  auto* i1 = reinterpret_cast<const __nv_bfloat16*>(in1);
+  // cluster variant: smallest power-of-two cluster (<= 8) whose per-CTA slice fits the 96 KB shared-memory budget
+  int cs = 1;
+  const int64_t bytes = (int64_t)HW * C * 2;
+  while (cs < 8 && bytes / cs > kGnClusterSmemData) cs *= 2;
+  if (bytes / cs <= kGnClusterSmemData && HW % cs == 0 && B * cs < (1ll << 31)) {
+    const int pix = HW / cs;
+    const size_t smem = (size_t)pix * C * 2 + (size_t)(4 * C + 2 * 512) * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+      cudaError_t e = cudaFuncSetAttribute(k_groupnorm_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, kGnClusterSmemData + 16 * 1024);
+      if (e != cudaSuccess) return cuda_fail(e, "groupnorm smem attribute");
+      attr = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(B * cs));
+    cfg.blockDim = dim3(kGnThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)cs;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_groupnorm_cluster, o, i0, C0, i1, C1, HW, gamma, beta, ss, ss_rows, ss_stride, ss_off,
+                                       apply_silu, pix);
+    if (e != cudaSuccess) return cuda_fail(e, "groupnorm cluster launch");
+    return DLPM_OK;
+  }
+  // fallback for shapes the cluster variant cannot hold: two passes over global memory
   const int nvec = C / 8, slots = kGnThreads / nvec;
   const size_t smem = (size_t)(2 * slots * C + 2 * C) * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
+  static bool attr2 = false;
+  if (!attr2) {
     cudaError_t e = cudaFuncSetAttribute(k_groupnorm, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
     if (e != cudaSuccess) return cuda_fail(e, "groupnorm smem attribute");
-    attr = true;
+    attr2 = true;
   }
-  k_groupnorm<<<(unsigned)B, kGnThreads, smem, (cudaStream_t)stream>>>(
-      reinterpret_cast<__nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(in0), C0,
-      reinterpret_cast<const __nv_bfloat16*>(in1), C1, HW, gamma, beta, ss, ss_rows, ss_stride, ss_off, apply_silu);
+  k_groupnorm<<<(unsigned)B, kGnThreads, smem, (cudaStream_t)stream>>>(o, i0, C0, i1, C1, HW, gamma, beta, ss, ss_rows, ss_stride, ss_off,
+                                                                      apply_silu);
   DLPM_CHECK_LAUNCH("groupnorm");
   return DLPM_OK;
 }
@@ -313,21 +487,23 @@ int dlpm_b200_attention(void* out, const void* qkv, int64_t B, int L, int C, int
   return DLPM_OK;
 }
 
-int dlpm_b200_conv_in(void* out, const float* x, const float* w, const float* bias, int64_t B, int C_in, int C_out, int H, int W,
+int dlpm_b200_conv_in(void* out, const float* x, const float* wT, const float* bias, int64_t B, int C_in, int C_out, int H, int W,
                       void* stream) {
-  DLPM_REQUIRE(out && x && w && bias, "conv_in: NULL tensor");
-  DLPM_REQUIRE(C_in >= 1 && C_in <= 4 && C_out % 8 == 0 && C_out <= 512, "conv_in: C_in <= 4, C_out multiple of 8 (<= 512)");
+  DLPM_REQUIRE(out && x && wT && bias, "conv_in: NULL tensor");
+  DLPM_REQUIRE(C_in >= 1 && C_in <= 4 && C_out % 32 == 0 && C_out <= 512, "conv_in: C_in <= 4, C_out multiple of 32 (<= 512)");
+  const int bands = (H + kConvInRows - 1) / kConvInRows;
+  DLPM_REQUIRE(B * bands < (1ll << 31) && W >= 1 && W <= 256, "conv_in: bad shape");
   if (B == 0) return DLPM_OK;
-  const size_t smem = (size_t)(C_out * C_in * 9 + C_out) * sizeof(float);
+  const size_t smem = (size_t)(C_out * C_in * 9 + C_out + C_in * (kConvInRows + 2) * (W + 2)) * sizeof(float);
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(k_conv_in, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     if (e != cudaSuccess) return cuda_fail(e, "conv_in smem attribute");
     attr = true;
   }
-  const int64_t total = B * H * W * (C_out / 8);
-  k_conv_in<<<grid_for(total, 256, 4), 256, smem, (cudaStream_t)stream>>>(reinterpret_cast<__nv_bfloat16*>(out), x, w, bias, B, C_in,
-                                                                         C_out, H, W);
+  DLPM_REQUIRE(smem <= 96 * 1024, "conv_in: weights do not fit in shared memory");
+  k_conv_in<<<(unsigned)(B * bands), 256, smem, (cudaStream_t)stream>>>(reinterpret_cast<__nv_bfloat16*>(out), x, wT, bias, C_in, C_out,
+                                                                      H, W);
   DLPM_CHECK_LAUNCH("conv_in");
   return DLPM_OK;
 }
@@ -348,10 +524,17 @@ int dlpm_b200_time_embedding(float* ss, float* semb, const float* t, const int* 
   DLPM_REQUIRE(ss && semb && (t || t_dev) && w0T && b0 && w2T && b2 && wallT && ball, "time_embedding: NULL tensor");
   DLPM_REQUIRE(rows >= 1 && mc >= 2 && mc <= 1024 && ss_total >= 1, "time_embedding: bad sizes");
   cudaStream_t s = (cudaStream_t)stream;
-  k_time_embed<<<rows, 512, (size_t)5 * mc * sizeof(float), s>>>(semb, t, t_dev, inv_T, mc, w0T, b0, w2T, b2);
-  DLPM_CHECK_LAUNCH("time_embed");
-  dim3 grid((unsigned)((ss_total + 255) / 256), (unsigned)rows);
-  k_emb_layers<<<grid, 256, (size_t)4 * mc * sizeof(float), s>>>(ss, semb, 4 * mc, ss_total, wallT, ball);
+  const int E = 4 * mc;
+  float* h1 = ss;  // hidden layer [rows][E] parked in the ss buffer, which the third launch rewrites completely
+  DLPM_REQUIRE(ss_total >= E, "time_embedding: ss_total must be >= 4*mc");
+  dim3 g1((unsigned)((E + 31) / 32), (unsigned)rows);
+  k_gemv_rows<<<g1, 256, (size_t)(mc + 256) * sizeof(float), s>>>(h1, nullptr, t, t_dev, inv_T, 1, mc, E, w0T, b0, 1);
+  DLPM_CHECK_LAUNCH("time_embed layer 1");
+  // every emb_layers starts with SiLU (unet.py:145-146): semb = SiLU(time_embed(.))
+  k_gemv_rows<<<g1, 256, (size_t)(E + 256) * sizeof(float), s>>>(semb, h1, nullptr, nullptr, 0.f, 0, E, E, w2T, b2, 1);
+  DLPM_CHECK_LAUNCH("time_embed layer 2");
+  dim3 g3((unsigned)((ss_total + 31) / 32), (unsigned)rows);
+  k_gemv_rows<<<g3, 256, (size_t)(E + 256) * sizeof(float), s>>>(ss, semb, nullptr, nullptr, 0.f, 0, E, ss_total, wallT, ball, 0);
   DLPM_CHECK_LAUNCH("emb_layers");
   return DLPM_OK;
 }

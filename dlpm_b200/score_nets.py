@@ -421,7 +421,8 @@ class UNetModel(nn.Module):
         c0 = self.input_blocks[0][0]
         h = new_buf(H * W * mc)
         names["input_blocks.0"] = h
-        op(OP_CONV_IN, h, self.in_channels, mc, H, W, add_f(c0.weight.reshape(mc, -1)), add_f(c0.bias))
+        op(OP_CONV_IN, h, self.in_channels, mc, H, W, add_f(c0.weight.detach().float().reshape(mc, -1).t().contiguous()),
+           add_f(c0.bias))
         C, Hc, Wc = mc, H, W
         hs = [(h, C)]
         for i in range(1, len(self.input_blocks)):

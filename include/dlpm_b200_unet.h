@@ -43,8 +43,9 @@ int dlpm_b200_groupnorm_silu(void* out, const void* in0, int C0, const void* in1
  * q, k, v blocks of C/heads channels), out NHWC bf16 [B, L, C].  L <= 1024, C/heads <= 64. */
 int dlpm_b200_attention(void* out, const void* qkv, int64_t B, int L, int C, int heads, void* stream);
 
-/* Input conv (unet.py:347): x NCHW fp32 [B, C_in<=4, H, W] -> NHWC bf16 [B, H, W, C_out]; w fp32 [C_out][C_in*9]. */
-int dlpm_b200_conv_in(void* out, const float* x, const float* w, const float* bias, int64_t B, int C_in, int C_out, int H,
+/* Input conv (unet.py:347): x NCHW fp32 [B, C_in<=4, H, W] -> NHWC bf16 [B, H, W, C_out] (C_out multiple of 32);
+ * wT fp32 in-major [C_in*9][C_out] (= conv weight [C_out][C_in][3][3] reshaped to [C_out][C_in*9] and transposed). */
+int dlpm_b200_conv_in(void* out, const float* x, const float* wT, const float* bias, int64_t B, int C_in, int C_out, int H,
                       int W, void* stream);
 
 /* Nearest x2 upsample (unet.py:73), NHWC bf16 [B,H,W,C] -> [B,2H,2W,C]. */

@@ -37,7 +37,7 @@ def interpret(prog, x, t, mc, emulate_bf16=False):
         code = f[0]
         if code == OP_CONV_IN:
             _, o, cin, cout, H, W, woff, boff = f[:8]
-            w = wf[woff:woff + cout * cin * 9].reshape(cout, cin, 3, 3)
+            w = wf[woff:woff + cout * cin * 9].reshape(cin * 9, cout).t().reshape(cout, cin, 3, 3)
             b = wf[boff:boff + cout]
             bufs[o] = q(F.conv2d(x, w, b, padding=1).permute(0, 2, 3, 1))
         elif code == OP_GN:

@@ -115,8 +115,8 @@ def test_reverse_step_variants_agree(L):
     zhat = ((a - mean) / (one - mean)).cpu().numpy().ravel()
     assert abs(zhat.mean()) < 0.1 and abs(zhat.std() - 1) < 0.1
     # vector and scalar paths draw the same in-kernel noise
-    a47 = run(x1, e1, zz=None, Dd=47)
-    assert torch.equal(a47, a[:, :47])
+    a47 = run(x1, e1, zz=None, Dd=47)  # scalar path keeps the IEEE divide, the vector path uses reciprocal + FMA (<= 2 ulp)
+    np.testing.assert_allclose(a47.cpu().numpy(), a[:, :47].cpu().numpy(), rtol=2e-6, atol=2e-6)
 
 
 @pytest.mark.parametrize("tag,ode", [("lim_sde", False), ("lim_ode", True)])

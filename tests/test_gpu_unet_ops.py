@@ -164,7 +164,7 @@ def test_conv_in_upsample_time_embedding(L):
     w = torch.randn(128, 3, 3, 3) / math.sqrt(27)
     b = torch.randn(128) * 0.1
     out = torch.zeros(B, H, H, 128, device="cuda", dtype=torch.bfloat16)
-    xd, wd, bd = x.cuda(), w.reshape(128, -1).contiguous().cuda(), b.cuda()
+    xd, wd, bd = x.cuda(), w.reshape(128, -1).t().contiguous().cuda(), b.cuda()
     L.call("dlpm_b200_conv_in", L.ptr(out), L.ptr(xd), L.ptr(wd), L.ptr(bd), B, 3, 128, H, H, L.stream_ptr())
     np.testing.assert_allclose(from_nhwc(out).numpy(), F.conv2d(x, w, b, padding=1).numpy(), rtol=1e-2, atol=1e-2)
     # upsample
