@@ -10,6 +10,7 @@ c_i64, c_int, c_f32, c_vp = ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes
 UNET_SIGNATURES = {
     "dlpm_b200_conv2d": [c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_int, c_i64, c_int, c_int, c_int, c_int,
                          c_int, c_int, c_vp],
+    "dlpm_b200_set_option": [ctypes.c_char_p, c_int],
     "dlpm_b200_groupnorm_silu": [c_vp, c_vp, c_int, c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_int, c_i64, c_i64, c_int,
                                  c_vp],
     "dlpm_b200_attention": [c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp],

@@ -17,6 +17,9 @@
 //     warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld -> +bias (+residual) -> bf16 -> global).
 //     Two accumulator stages in TMEM let the epilogue of tile i overlap the MMAs of tile i+1.
 #include "../../include/dlpm_b200_unet.h"
+#include <cstdlib>
+#include <string>
+
 #include "conv_tc.cuh"
 #include "tc_common.cuh"
 
@@ -39,16 +42,23 @@ struct ConvKParams {
   void* out;
 };
 
-template <int BLOCK_N, int BLOCK_K>
+// CG = 1: one CTA per 128-pixel tile.  CG = 2: a CTA PAIR (cluster of 2 on one TPC) computes two adjacent 128-pixel
+// tiles with tcgen05.mma.cta_group::2 (M = 256): each CTA stages its own 128 activation rows and only HALF of the weight
+// tile (BLOCK_N/2 rows) -- the tensor core reads both halves -- which halves the weight traffic from L2 and the
+// shared-memory operand bandwidth per SM (the limiter of the N = 128 layers).  The leader CTA (rank 0) issues the MMAs;
+// TMA completions of both CTAs are signalled on the leader's "full" barrier, tcgen05.commit multicasts the "empty" /
+// "accumulator ready" arrivals to both CTAs, and both epilogues arrive remotely on the leader's "accumulator free" barrier.
+template <int BLOCK_N, int BLOCK_K, int CG>
 __global__ void __launch_bounds__(kConvThreads, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmS0,
           const __grid_constant__ CUtensorMap tmS1, const __grid_constant__ CUtensorMap tmB, const ConvKParams p) {
   constexpr int A_BYTES = 128 * BLOCK_K * 2;
-  constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  constexpr int B_ROWS = BLOCK_N / CG;
+  constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int SWZ = BLOCK_K * 2;  // bytes per operand row = swizzle span (128 or 64)
   constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
-  constexpr uint32_t IDESC = make_idesc_bf16(128, BLOCK_N);
+  constexpr uint32_t IDESC = make_idesc_bf16(128 * CG, BLOCK_N);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -59,9 +69,13 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
   const int main_blocks = p.taps * p.cin_blocks;
   const int nkb = main_blocks + p.s0_blocks + p.s1_blocks;
-  const int n_tiles = p.n_m_tiles * p.n_n_tiles;
+  const int m_groups = (p.n_m_tiles + CG - 1) / CG;   // a work item = CG adjacent M tiles x one N tile
+  const int n_items = m_groups * p.n_n_tiles;
+  const int first_item = blockIdx.x / CG, item_stride = gridDim.x / CG;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -71,21 +85,25 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar + a, 1); mbar_init(tempty_bar + a, 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar + a, 1); mbar_init(tempty_bar + a, 4 * CG); }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 2) {
+    if (CG == 2) tmem_alloc_pair(tmem_slot, TMEM_COLS);
+    else tmem_alloc(tmem_slot, TMEM_COLS);
+  }
   tc_fence_before();
-  __syncthreads();
+  __syncwarp();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (every CTA loads its own A rows and its share of B) =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_n_tiles, mt = tile / p.n_n_tiles;
+      for (int item = first_item; item < n_items; item += item_stride) {
+        const int nt = item % p.n_n_tiles, mt = (item / p.n_n_tiles) * CG + (int)cta_rank;
         int n0, h0;
         if (p.Nb == 1) { n0 = mt / p.tiles_per_img; h0 = (mt - n0 * p.tiles_per_img) * p.Hb; }
         else { n0 = mt * p.Nb; h0 = 0; }
@@ -93,30 +111,40 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           mbar_wait(empty_bar + stage, phase ^ 1);
           uint8_t* a_dst = smem + stage * STAGE_BYTES;
           uint8_t* b_dst = a_dst + A_BYTES;
-          mbar_expect_tx(full_bar + stage, STAGE_BYTES);
+          int c_a, x_a, y_a;
+          const CUtensorMap* map;
           if (kb < main_blocks) {
             const int tap = kb / p.cin_blocks, cblk = kb - tap * p.cin_blocks;
             const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap - (tap / 3) * 3 - 1 : 0;
-            tma_load_4d(&tmA, full_bar + stage, a_dst, cblk * BLOCK_K, dx, h0 * p.stride + dy, n0);
+            map = &tmA; c_a = cblk * BLOCK_K; x_a = dx; y_a = h0 * p.stride + dy;
           } else if (kb < main_blocks + p.s0_blocks) {
-            tma_load_4d(&tmS0, full_bar + stage, a_dst, (kb - main_blocks) * BLOCK_K, 0, h0, n0);
+            map = &tmS0; c_a = (kb - main_blocks) * BLOCK_K; x_a = 0; y_a = h0;
           } else {
-            tma_load_4d(&tmS1, full_bar + stage, a_dst, (kb - main_blocks - p.s0_blocks) * BLOCK_K, 0, h0, n0);
+            map = &tmS1; c_a = (kb - main_blocks - p.s0_blocks) * BLOCK_K; x_a = 0; y_a = h0;
           }
-          tma_load_2d(&tmB, full_bar + stage, b_dst, kb * BLOCK_K, nt * BLOCK_N);
+          if (CG == 2) {
+            const uint32_t lead_full = mapa_u32(smem_u32(full_bar + stage), 0);
+            if (leader) mbar_expect_tx(full_bar + stage, 2 * STAGE_BYTES);
+            tma_load_4d_pair(map, lead_full, a_dst, c_a, x_a, y_a, n0);
+            tma_load_2d_pair(&tmB, lead_full, b_dst, kb * BLOCK_K, nt * BLOCK_N + (int)cta_rank * B_ROWS);
+          } else {
+            mbar_expect_tx(full_bar + stage, STAGE_BYTES);
+            tma_load_4d(map, full_bar + stage, a_dst, c_a, x_a, y_a, n0);
+            tma_load_2d(&tmB, full_bar + stage, b_dst, kb * BLOCK_K, nt * BLOCK_N);
+          }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && leader) {
       int stage = 0; uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      for (int item = first_item; item < n_items; item += item_stride, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(tempty_bar + acc, acc_phase ^ 1);  // epilogue has drained this accumulator stage
+        mbar_wait(tempty_bar + acc, acc_phase ^ 1);  // epilogues (of both CTAs) have drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
         for (int kb = 0; kb < nkb; ++kb) {
@@ -128,12 +156,13 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           for (int k = 0; k < BLOCK_K / 16; ++k) {
             const uint64_t da = make_smem_desc<SWZ>(a_addr + k * 32);
             const uint64_t db = make_smem_desc<SWZ>(b_addr + k * 32);
-            umma_bf16(d_tmem, da, db, IDESC, (kb | k) != 0);
+            if (CG == 2) umma_bf16_pair(d_tmem, da, db, IDESC, (kb | k) != 0);
+            else umma_bf16(d_tmem, da, db, IDESC, (kb | k) != 0);
           }
-          umma_commit(empty_bar + stage);  // frees the smem slot when these MMAs retire
+          if (CG == 2) umma_commit_pair(empty_bar + stage); else umma_commit(empty_bar + stage);  // frees the smem slot(s)
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(tfull_bar + acc);  // accumulator complete -> epilogue
+        if (CG == 2) umma_commit_pair(tfull_bar + acc); else umma_commit(tfull_bar + acc);  // accumulator complete -> epilogue(s)
       }
     }
   } else if (warp >= 4) {
@@ -142,8 +171,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int m = q * 32 + lane;
     const int w_in = m % p.Wb, h_in = (m / p.Wb) % p.Hb, n_in = m / (p.Wb * p.Hb);
     int it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-      const int nt = tile % p.n_n_tiles, mt = tile / p.n_n_tiles;
+    for (int item = first_item; item < n_items; item += item_stride, ++it) {
+      const int nt = item % p.n_n_tiles, mt = (item / p.n_n_tiles) * CG + (int)cta_rank;
       int n0, h0;
       if (p.Nb == 1) { n0 = mt / p.tiles_per_img; h0 = (mt - n0 * p.tiles_per_img) * p.Hb; }
       else { n0 = mt * p.Nb; h0 = 0; }
@@ -203,14 +232,19 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar + acc);
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(tempty_bar + acc), 0));
+        else mbar_arrive(tempty_bar + acc);
+      }
     }
   }
   tc_fence_before();
-  __syncthreads();
+  __syncwarp();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (CG == 2) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -308,19 +342,33 @@ int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, c
   if (skip0 && (rc = encode_act_map(&L->tmS0, skip0, B, H_out, W_out, C_s0, bk, L->Wb, L->Hb, L->Nb, 1))) return rc;
   if (skip1 && (rc = encode_act_map(&L->tmS1, skip1, B, H_out, W_out, C_s1, bk, L->Wb, L->Hb, L->Nb, 1))) return rc;
   const int64_t k_total = (int64_t)L->taps * C_in + C_s0 + C_s1;
-  if ((rc = encode_weight_map(&L->tmB, w, C_out_pad, k_total, bn, bk))) return rc;
+  // CTA pairs (cta_group::2) when there are enough M tiles to keep all 74 pairs busy
+  L->cta_group = (conv_cta_group_override() == 1) ? 1
+                 : ((bn >= 32 && (int64_t)((L->n_m_tiles + 1) / 2) * L->n_n_tiles >= kNumSMs / 2) ? 2 : 1);
+  if (conv_cta_group_override() == 2 && bn >= 32) L->cta_group = 2;
+  if ((rc = encode_weight_map(&L->tmB, w, C_out_pad, k_total, bn / L->cta_group, bk))) return rc;
   return DLPM_OK;
 }
 
-template <int BN, int BK>
+static int g_cta_group_override = -1;
+int conv_cta_group_override() {
+  if (g_cta_group_override < 0) {
+    const char* e = getenv("DLPM_B200_CTA_GROUP");  // 1 / 2 force the MMA flavour (debugging, A/B measurements); unset = auto
+    g_cta_group_override = e ? atoi(e) : 0;
+  }
+  return g_cta_group_override;
+}
+void conv_set_cta_group_override(int v) { g_cta_group_override = v; }
+
+template <int BN, int BK, int CG>
 static int launch_t(const ConvLaunch& L, cudaStream_t stream) {
-  constexpr int STAGE = 128 * BK * 2 + BN * BK * 2;
+  constexpr int STAGE = 128 * BK * 2 + (BN / CG) * BK * 2;
   int stages = kSmemBudget / STAGE;
   if (stages > kMaxStages) stages = kMaxStages;
   const size_t smem = (size_t)stages * STAGE + 1024 /*align*/ + (2 * kMaxStages + 4) * 8 + 16;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_conv_tc<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemBudget + 2048));
+    cudaError_t e = cudaFuncSetAttribute(k_conv_tc<BN, BK, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemBudget + 2048));
     if (e != cudaSuccess) return cuda_fail(e, "conv smem attribute");
     attr_set = true;
   }
@@ -330,17 +378,41 @@ static int launch_t(const ConvLaunch& L, cudaStream_t stream) {
   p.stride = L.stride; p.taps = L.taps; p.cin_blocks = L.cin_blocks; p.s0_blocks = L.s0_blocks; p.s1_blocks = L.s1_blocks;
   p.B = L.B; p.C_out = L.C_out; p.C_out_real = L.C_out_real; p.out_mode = L.out_mode;
   p.bias = L.bias; p.residual = L.residual; p.out = L.out;
-  const int n_tiles = L.n_m_tiles * L.n_n_tiles;
-  const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
-  k_conv_tc<BN, BK><<<grid, kConvThreads, smem, stream>>>(L.tmA, L.tmS0, L.tmS1, L.tmB, p);
-  DLPM_CHECK_LAUNCH("conv_tc");
+  const int n_items = ((L.n_m_tiles + CG - 1) / CG) * L.n_n_tiles;
+  const int max_groups = kNumSMs / CG;
+  const int grid = (n_items < max_groups ? n_items : max_groups) * CG;
+  if (CG == 1) {
+    k_conv_tc<BN, BK, 1><<<grid, kConvThreads, smem, stream>>>(L.tmA, L.tmS0, L.tmS1, L.tmB, p);
+    DLPM_CHECK_LAUNCH("conv_tc");
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kConvThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_conv_tc<BN, BK, CG>, L.tmA, L.tmS0, L.tmS1, L.tmB, p);
+    if (e != cudaSuccess) return cuda_fail(e, "conv_tc pair launch");
+  }
   return DLPM_OK;
 }
 
 int conv_launch(const ConvLaunch& L, cudaStream_t stream) {
-#define CASE(BN, BK) if (L.block_n == BN && L.block_k == BK) return launch_t<BN, BK>(L, stream)
-  CASE(256, 64); CASE(128, 64); CASE(64, 64); CASE(32, 64); CASE(16, 64);
-  CASE(256, 32); CASE(128, 32); CASE(64, 32); CASE(32, 32); CASE(16, 32);
+#define CASE(BN, BK)                                                          \
+  if (L.block_n == BN && L.block_k == BK) {                                   \
+    if (L.cta_group == 2) {                                                   \
+      if constexpr (BN >= 32) return launch_t<BN, BK, 2>(L, stream);          \
+    }                                                                         \
+    return launch_t<BN, BK, 1>(L, stream);                                    \
+  }
+  CASE(256, 64) CASE(128, 64) CASE(64, 64) CASE(32, 64) CASE(16, 64)
+  CASE(256, 32) CASE(128, 32) CASE(64, 32) CASE(32, 32) CASE(16, 32)
 #undef CASE
   set_error("conv: no kernel for tile N=%d K=%d", L.block_n, L.block_k);
   return DLPM_ERR_UNSUPPORTED;
@@ -349,6 +421,17 @@ int conv_launch(const ConvLaunch& L, cudaStream_t stream) {
 }  // namespace dlpm
 
 using namespace dlpm;
+
+int dlpm_b200_set_option(const char* name, int value) {
+  DLPM_REQUIRE(name != nullptr, "set_option: NULL name");
+  if (std::string(name) == "conv_cta_group") {
+    DLPM_REQUIRE(value >= 0 && value <= 2, "set_option: conv_cta_group must be 0 (auto), 1 or 2");
+    conv_set_cta_group_override(value);
+    return DLPM_OK;
+  }
+  set_error("set_option: unknown option '%s'", name);
+  return DLPM_ERR_ARG;
+}
 
 int dlpm_b200_conv2d(const void* in, const void* w, const float* bias, const void* skip0, int C_s0, const void* skip1, int C_s1,
                      const void* residual, void* out, int out_mode, int64_t B, int H, int W, int C_in, int C_out, int ksize,

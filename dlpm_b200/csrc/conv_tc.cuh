@@ -12,6 +12,7 @@ enum ConvOutMode { CONV_OUT_BF16_NHWC = 0, CONV_OUT_F32_NCHW = 1 };
 struct ConvLaunch {
   CUtensorMap tmA, tmS0, tmS1, tmB;  // main activation, two optional 1x1 skip-conv sources, packed weights
   int block_n, block_k;              // tile N (16..256), K block in channels (64 or 32)
+  int cta_group;                     // 1 = single-CTA MMA, 2 = CTA pairs (tcgen05 cta_group::2, M = 256)
   int n_m_tiles, n_n_tiles;
   int Wb, Hb, Nb;                    // pixel box of one M tile: Wb*Hb*Nb == 128
   int H_out, W_out, tiles_per_img;
@@ -32,5 +33,6 @@ int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, c
               int C_s1, const void* residual, void* out, int out_mode, int64_t B, int H, int W, int C_in, int C_out, int ksize,
               int stride);
 int conv_launch(const ConvLaunch& L, cudaStream_t stream);
+int conv_cta_group_override();
 
 }  // namespace dlpm

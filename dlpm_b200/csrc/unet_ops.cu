@@ -120,6 +120,8 @@ __global__ void __launch_bounds__(kGnThreads) k_groupnorm(__nv_bfloat16* __restr
 // ------------------------------------------------------------------------------------------------
 constexpr int kGnClusterSmemData = 96 * 1024;
 
+__device__ __forceinline__ uint32_t gn_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
 __global__ void __launch_bounds__(kGnThreads) k_groupnorm_cluster(__nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ in0,
                                                                   int C0, const __nv_bfloat16* __restrict__ in1, int C1, int HW,
                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -128,90 +130,109 @@ __global__ void __launch_bounds__(kGnThreads) k_groupnorm_cluster(__nv_bfloat16*
   cg::cluster_group cluster = cg::this_cluster();
   const int cs = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
   const int n = blockIdx.x / cs;
-  const int C = C0 + C1, nvec = C >> 3;
-  extern __shared__ __align__(16) uint8_t sm_raw[];
-  uint4* data = reinterpret_cast<uint4*>(sm_raw);                                  // [pix_per_cta][nvec] 16-byte vectors
+  const int C = C0 + C1, nvec = C >> 3, nvec0 = C0 >> 3;
+  const int nthreads = blockDim.x;
+  extern __shared__ __align__(128) uint8_t sm_raw[];
+  // two planes (one per input tensor) so that each is ONE contiguous bulk copy: plane0 [pix][C0], plane1 [pix][C1]
+  __nv_bfloat16* plane0 = reinterpret_cast<__nv_bfloat16*>(sm_raw);
+  __nv_bfloat16* plane1 = plane0 + (size_t)pix_per_cta * C0;
   float* psum = reinterpret_cast<float*>(sm_raw + (size_t)pix_per_cta * C * 2);     // [C] this CTA's per-channel sums
   float* psq = psum + C;                                                            // [C]
   float* coef_a = psq + C;                                                          // [C]
   float* coef_b = coef_a + C;                                                       // [C]
   float* part = coef_b + C;                                                         // [parts][C][2] scratch, parts * C <= 512
-  const int slots = kGnThreads / nvec;
-  const int v = threadIdx.x % nvec, slot = threadIdx.x / nvec;
-  const bool active = slot < slots;
-  const int c = v * 8;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(part + 1024);
   const int p0 = rank * pix_per_cta;
-  const __nv_bfloat16* src = (c < C0) ? in0 + ((int64_t)n * HW + p0) * C0 + c : in1 + ((int64_t)n * HW + p0) * C1 + (c - C0);
-  const int src_stride = (c < C0) ? C0 : C1;
-  // phase 1: global -> shared (the only read of the tensor)
-  if (active)
-    for (int p = slot; p < pix_per_cta; p += slots) data[p * nvec + v] = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)p * src_stride));
-  __syncthreads();
-  // phase 2: per-channel sums over this CTA's pixels (2-byte shared loads, consecutive threads = consecutive channels)
-  const int parts = kGnThreads / C > 0 ? kGnThreads / C : 1;
+  // phase 1: global -> shared with bulk asynchronous copies (the only read of the tensor)
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(gn_smem_u32(bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t bytes0 = (uint32_t)pix_per_cta * C0 * 2, bytes1 = (uint32_t)pix_per_cta * C1 * 2;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gn_smem_u32(bar)), "r"(bytes0 + bytes1) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(gn_smem_u32(plane0)),
+                 "l"(in0 + ((int64_t)n * HW + p0) * C0), "r"(bytes0), "r"(gn_smem_u32(bar))
+                 : "memory");
+    if (C1)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(gn_smem_u32(plane1)),
+                   "l"(in1 + ((int64_t)n * HW + p0) * C1), "r"(bytes1), "r"(gn_smem_u32(bar))
+                   : "memory");
+  }
+  __syncthreads();  // barrier initialised before anyone polls it
   {
-    const int ch = threadIdx.x % C, pt = threadIdx.x / C;
-    if (pt < parts) {
-      const __nv_bfloat16* col = reinterpret_cast<const __nv_bfloat16*>(sm_raw) + ch;
-      float sA = 0.f, qA = 0.f;
-      for (int p = pt; p < pix_per_cta; p += parts) {
-        const float xv = __bfloat162float(col[p * C]);
-        sA += xv;
-        qA = fmaf(xv, xv, qA);
-      }
-      part[(pt * C + ch) * 2] = sA;
-      part[(pt * C + ch) * 2 + 1] = qA;
+    uint32_t ok = 0, spins = 0;
+    while (!ok) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(ok) : "r"(gn_smem_u32(bar)) : "memory");
+      if (++spins > (1u << 26)) __trap();
     }
   }
-  __syncthreads();
-  if (threadIdx.x < C) {
+  // phase 2: per-channel sums over this CTA's pixels (2-byte shared loads, consecutive threads = consecutive channels)
+  const int parts = nthreads / C > 0 ? nthreads / C : 1;
+  for (int item = threadIdx.x; item < parts * C; item += nthreads) {
+    const int ch = item % C, pt = item / C;
+    const __nv_bfloat16* col = ch < C0 ? plane0 + ch : plane1 + (ch - C0);
+    const int stride = ch < C0 ? C0 : C1;
     float sA = 0.f, qA = 0.f;
-    for (int pt = 0; pt < parts; ++pt) { sA += part[(pt * C + threadIdx.x) * 2]; qA += part[(pt * C + threadIdx.x) * 2 + 1]; }
-    psum[threadIdx.x] = sA;
-    psq[threadIdx.x] = qA;
+    for (int p = pt; p < pix_per_cta; p += parts) {
+      const float xv = __bfloat162float(col[p * stride]);
+      sA += xv;
+      qA = fmaf(xv, xv, qA);
+    }
+    part[(pt * C + ch) * 2] = sA;
+    part[(pt * C + ch) * 2 + 1] = qA;
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < C; ch += nthreads) {
+    float sA = 0.f, qA = 0.f;
+    for (int pt = 0; pt < parts; ++pt) { sA += part[(pt * C + ch) * 2]; qA += part[(pt * C + ch) * 2 + 1]; }
+    psum[ch] = sA;
+    psq[ch] = qA;
   }
   cluster.sync();
   // phase 3: totals over the cluster (DSMEM reads, fixed order), group statistics, affine coefficients
-  if (threadIdx.x < C) {
+  for (int ch = threadIdx.x; ch < C; ch += nthreads) {
     float sA = 0.f, qA = 0.f;
     for (int r = 0; r < cs; ++r) {
-      const float* rs = cluster.map_shared_rank(psum, r);
-      const float* rq = cluster.map_shared_rank(psq, r);
-      sA += rs[threadIdx.x];
-      qA += rq[threadIdx.x];
+      sA += cluster.map_shared_rank(psum, r)[ch];
+      qA += cluster.map_shared_rank(psq, r)[ch];
     }
-    part[threadIdx.x * 2] = sA;
-    part[threadIdx.x * 2 + 1] = qA;
+    part[ch * 2] = sA;
+    part[ch * 2 + 1] = qA;
   }
   __syncthreads();
-  if (threadIdx.x < C) {
-    const int G = C < 32 ? C : 32, cpg = C / G, g = threadIdx.x / cpg;
+  for (int ch = threadIdx.x; ch < C; ch += nthreads) {
+    const int G = C < 32 ? C : 32, cpg = C / G, g = ch / cpg;
     float sA = 0.f, qA = 0.f;
     for (int k = 0; k < cpg; ++k) { sA += part[(g * cpg + k) * 2]; qA += part[(g * cpg + k) * 2 + 1]; }
     const float inv_n = 1.0f / (float)(cpg * HW);
     const float mean = sA * inv_n;
     const float rstd = rsqrtf(fmaxf(qA * inv_n - mean * mean, 0.f) + 1e-5f);
-    float ga = __ldg(gamma + threadIdx.x) * rstd;
-    float be = __ldg(beta + threadIdx.x) - mean * ga;
+    float ga = __ldg(gamma + ch) * rstd;
+    float be = __ldg(beta + ch) - mean * ga;
     if (ss) {
       const float* row = ss + (ss_rows == 1 ? 0 : (int64_t)n * ss_stride) + ss_off;
-      const float sc = 1.0f + __ldg(row + threadIdx.x), sh = __ldg(row + C + threadIdx.x);
+      const float sc = 1.0f + __ldg(row + ch), sh = __ldg(row + C + ch);
       ga *= sc;
       be = be * sc + sh;
     }
-    coef_a[threadIdx.x] = ga;
-    coef_b[threadIdx.x] = be;
+    coef_a[ch] = ga;
+    coef_b[ch] = be;
   }
   cluster.sync();  // every CTA has finished reading its peers' shared memory; also orders coef_* for this CTA
   // phase 4: normalise from shared memory -> global (the only write)
-  if (active) {
+  const int slots = nthreads / nvec;
+  const int v = threadIdx.x % nvec, slot = threadIdx.x / nvec;
+  if (slot < slots) {
+    const int c = v * 8;
     float a[8], b[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) { a[e] = coef_a[c + e]; b[e] = coef_b[c + e]; }
+    const uint4* srcv = c < C0 ? reinterpret_cast<const uint4*>(plane0) + v : reinterpret_cast<const uint4*>(plane1) + (v - nvec0);
+    const int sstride = c < C0 ? nvec0 : nvec - nvec0;
     __nv_bfloat16* dst = out + ((int64_t)n * HW + p0) * C + c;
     for (int p = slot; p < pix_per_cta; p += slots) {
       float x[8];
-      unpack8(data[p * nvec + v], x);
+      unpack8(srcv[p * sstride], x);
 #pragma unroll
       for (int e = 0; e < 8; ++e) { x[e] = fmaf(x[e], a[e], b[e]); if (apply_silu) x[e] = silu_f(x[e]); }
       *reinterpret_cast<uint4*>(dst + (int64_t)p * C) = pack8(x);
@@ -420,7 +441,10 @@ int dlpm_b200_groupnorm_silu(void* out, const void* in0, int C0, const void* in1
   while (cs < 8 && bytes / cs > kGnClusterSmemData) cs *= 2;
   if (bytes / cs <= kGnClusterSmemData && HW % cs == 0 && B * cs < (1ll << 31)) {
     const int pix = HW / cs;
-    const size_t smem = (size_t)pix * C * 2 + (size_t)(4 * C + 2 * 512) * sizeof(float);
+    const size_t smem = (size_t)pix * C * 2 + (size_t)(4 * C + 2 * 512) * sizeof(float) + 16;
+    // small slices: 256-thread CTAs so that more of them are co-resident (the kernel is then pure latency)
+    int threads = ((int64_t)pix * (C / 8) <= 2048) ? 256 : kGnThreads;
+    if (threads < C / 8) threads = kGnThreads;
     static bool attr = false;
     if (!attr) {
       cudaError_t e = cudaFuncSetAttribute(k_groupnorm_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, kGnClusterSmemData + 16 * 1024);
@@ -429,7 +453,7 @@ int dlpm_b200_groupnorm_silu(void* out, const void* in0, int C0, const void* in1
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(B * cs));
-    cfg.blockDim = dim3(kGnThreads);
+    cfg.blockDim = dim3((unsigned)threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute at[1];

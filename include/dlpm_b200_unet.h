@@ -30,6 +30,10 @@ int dlpm_b200_conv2d(const void* in, const void* w, const float* bias, const voi
                      int C_s1, const void* residual, void* out, int out_mode, int64_t B, int H, int W, int C_in,
                      int C_out, int ksize, int stride, void* stream);
 
+/* Tuning / debugging knobs.  "conv_cta_group": 0 = automatic (CTA pairs with tcgen05 cta_group::2 when the problem has
+ * enough tiles), 1 = always single-CTA MMAs, 2 = always CTA pairs.  Takes effect for descriptors built afterwards. */
+int dlpm_b200_set_option(const char* name, int value);
+
 /* K6. GroupNorm(min(32,C) groups, eps 1e-5) over the virtual concatenation [in0 | in1] of two NHWC bf16
  * tensors, optional scale-shift conditioning y = GN(x) * (1 + scale) + shift, optional SiLU; bf16 NHWC out
  * (GroupNorm32 + SiLU + use_scale_shift_norm of unet.py:141-142,153-154,188-191,212,433-434; nn.py:17-19).

@@ -78,8 +78,16 @@ CONV_CASES = [
 ]
 
 
+@pytest.fixture(params=[1, 2], ids=["cta1", "cta_pair"])
+def cta_group(request, L):
+    """Run the conv tests with single-CTA MMAs and with CTA pairs (tcgen05 cta_group::2)."""
+    L.call("dlpm_b200_set_option", b"conv_cta_group", request.param)
+    yield request.param
+    L.call("dlpm_b200_set_option", b"conv_cta_group", 0)
+
+
 @pytest.mark.parametrize("B,H,C_in,C_out,k,stride", CONV_CASES)
-def test_conv_matches_torch(L, B, H, C_in, C_out, k, stride):
+def test_conv_matches_torch(L, cta_group, B, H, C_in, C_out, k, stride):
     x = rnd(B, C_in, H, H)
     w = rnd(C_out, C_in, k, k, scale=1.0 / math.sqrt(C_in * k * k))
     b = torch.randn(C_out) * 0.1
@@ -91,7 +99,7 @@ def test_conv_matches_torch(L, B, H, C_in, C_out, k, stride):
     assert (got - want).abs().mean().item() < 4e-3
 
 
-def test_conv_fused_skip_residual_and_final(L):
+def test_conv_fused_skip_residual_and_final(L, cta_group):
     # second conv of a ResBlock with channel change: 3x3 on h plus the 1x1 skip conv over cat([x1, x2]) (unet.py:161-195,489)
     B, H, C_out = 2, 32, 128
     h, x1, x2 = rnd(B, 128, H, H, seed=1), rnd(B, 256, H, H, seed=2), rnd(B, 128, H, H, seed=3)
