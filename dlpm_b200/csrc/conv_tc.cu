@@ -29,12 +29,14 @@ using namespace tc;
 
 constexpr int kMaxStages = 8;
 constexpr int kConvThreads = 256;
-constexpr int kSmemBudget = 200 * 1024;  // operand ring; barriers + alignment slack come on top
+constexpr int kSmemBudget = 220 * 1024;  // operand ring; barriers + alignment slack come on top (227 KB per CTA)
 
 struct ConvKParams {
   int n_m_tiles, n_n_tiles, stages;
   int Wb, Hb, Nb, H_out, W_out, tiles_per_img;
   int stride, taps, cin_blocks, s0_blocks, s1_blocks;
+  int tap_cols, dy0, dx0, out_scale, out_oy, out_ox, H_full, W_full;
+  int tall, stage_bytes;  // tall: one (Hb+2)-row activation box per (channel block, dx) serves the three dy taps
   int64_t B;
   int C_out, C_out_real, out_mode;
   const float* bias;
@@ -48,14 +50,19 @@ struct ConvKParams {
 // shared-memory operand bandwidth per SM (the limiter of the N = 128 layers).  The leader CTA (rank 0) issues the MMAs;
 // TMA completions of both CTAs are signalled on the leader's "full" barrier, tcgen05.commit multicasts the "empty" /
 // "accumulator ready" arrivals to both CTAs, and both epilogues arrive remotely on the leader's "accumulator free" barrier.
-template <int BLOCK_N, int BLOCK_K, int CG>
+template <int BLOCK_N, int BLOCK_K, int CG, int KS>
 __global__ void __launch_bounds__(kConvThreads, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmS0,
           const __grid_constant__ CUtensorMap tmS1, const __grid_constant__ CUtensorMap tmB, const ConvKParams p) {
   constexpr int A_BYTES = 128 * BLOCK_K * 2;
   constexpr int B_ROWS = BLOCK_N / CG;
   constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
-  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int SUB_BYTES = A_BYTES + B_BYTES;      // one K block (BLOCK_K channels) of both operands
+  // A pipeline stage carries KS K blocks (narrow tiles need fewer barrier round trips per MMA cycle), or -- "tall" mode,
+  // 3x3 stride-1 convs whose tile lies inside one image -- ONE activation box of Hb+2 image rows plus the three weight
+  // tiles of the taps dy = -1, 0, +1: a dy shift is a whole number of 8-row swizzle atoms (Wb rows), so the three MMAs
+  // read the same box at row offsets 0, Wb, 2*Wb and the activation traffic from L2 drops from 9 to 3*(Hb+2)/Hb tiles.
+  const int STAGE_BYTES = p.stage_bytes;
   constexpr int SWZ = BLOCK_K * 2;  // bytes per operand row = swizzle span (128 or 64)
   constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
   constexpr uint32_t IDESC = make_idesc_bf16(128 * CG, BLOCK_N);
@@ -107,30 +114,85 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         int n0, h0;
         if (p.Nb == 1) { n0 = mt / p.tiles_per_img; h0 = (mt - n0 * p.tiles_per_img) * p.Hb; }
         else { n0 = mt * p.Nb; h0 = 0; }
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(empty_bar + stage, phase ^ 1);
-          uint8_t* a_dst = smem + stage * STAGE_BYTES;
-          uint8_t* b_dst = a_dst + A_BYTES;
-          int c_a, x_a, y_a;
-          const CUtensorMap* map;
-          if (kb < main_blocks) {
-            const int tap = kb / p.cin_blocks, cblk = kb - tap * p.cin_blocks;
-            const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap - (tap / 3) * 3 - 1 : 0;
-            map = &tmA; c_a = cblk * BLOCK_K; x_a = dx; y_a = h0 * p.stride + dy;
-          } else if (kb < main_blocks + p.s0_blocks) {
-            map = &tmS0; c_a = (kb - main_blocks) * BLOCK_K; x_a = 0; y_a = h0;
-          } else {
-            map = &tmS1; c_a = (kb - main_blocks - p.s0_blocks) * BLOCK_K; x_a = 0; y_a = h0;
+        if (p.tall) {
+          const int a_tall_bytes = (p.Hb + 2) * p.Wb * BLOCK_K * 2;
+          const int n_sb = 3 * p.cin_blocks + p.s0_blocks + p.s1_blocks;
+          for (int sb = 0; sb < n_sb; ++sb) {
+            mbar_wait(empty_bar + stage, phase ^ 1);
+            uint8_t* a_dst = smem + stage * STAGE_BYTES;
+            uint8_t* b_dst = a_dst + a_tall_bytes;
+            const bool main_part = sb < 3 * p.cin_blocks;
+            const int bytes = main_part ? a_tall_bytes + 3 * B_BYTES : SUB_BYTES;
+            uint32_t lead_full = 0;
+            if (CG == 2) {
+              lead_full = mapa_u32(smem_u32(full_bar + stage), 0);
+              if (leader) mbar_expect_tx(full_bar + stage, 2 * bytes);
+            } else {
+              mbar_expect_tx(full_bar + stage, bytes);
+            }
+            const int brow = nt * BLOCK_N + (int)cta_rank * B_ROWS;
+            if (main_part) {
+              const int cblk = sb / 3, dxi = sb - cblk * 3;
+              if (CG == 2) tma_load_4d_pair(&tmA, lead_full, a_dst, cblk * BLOCK_K, dxi - 1, h0 - 1, n0);
+              else tma_load_4d(&tmA, full_bar + stage, a_dst, cblk * BLOCK_K, dxi - 1, h0 - 1, n0);
+#pragma unroll
+              for (int j = 0; j < 3; ++j) {
+                const int kcol = ((j * 3 + dxi) * p.cin_blocks + cblk) * BLOCK_K;
+                if (CG == 2) tma_load_2d_pair(&tmB, lead_full, b_dst + j * B_BYTES, kcol, brow);
+                else tma_load_2d(&tmB, full_bar + stage, b_dst + j * B_BYTES, kcol, brow);
+              }
+            } else {
+              const int e = sb - 3 * p.cin_blocks;
+              const CUtensorMap* map = e < p.s0_blocks ? &tmS0 : &tmS1;
+              const int c_a = (e < p.s0_blocks ? e : e - p.s0_blocks) * BLOCK_K;
+              const int kcol = (main_blocks + e) * BLOCK_K;
+              if (CG == 2) {
+                tma_load_4d_pair(map, lead_full, a_dst, c_a, 0, h0, n0);
+                tma_load_2d_pair(&tmB, lead_full, b_dst, kcol, brow);
+              } else {
+                tma_load_4d(map, full_bar + stage, a_dst, c_a, 0, h0, n0);
+                tma_load_2d(&tmB, full_bar + stage, b_dst, kcol, brow);
+              }
+            }
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
+          continue;
+        }
+        for (int kb0 = 0; kb0 < nkb; kb0 += KS) {
+          mbar_wait(empty_bar + stage, phase ^ 1);
+          const int cnt = (nkb - kb0) < KS ? (nkb - kb0) : KS;
+          uint32_t lead_full = 0;
           if (CG == 2) {
-            const uint32_t lead_full = mapa_u32(smem_u32(full_bar + stage), 0);
-            if (leader) mbar_expect_tx(full_bar + stage, 2 * STAGE_BYTES);
-            tma_load_4d_pair(map, lead_full, a_dst, c_a, x_a, y_a, n0);
-            tma_load_2d_pair(&tmB, lead_full, b_dst, kb * BLOCK_K, nt * BLOCK_N + (int)cta_rank * B_ROWS);
+            lead_full = mapa_u32(smem_u32(full_bar + stage), 0);
+            if (leader) mbar_expect_tx(full_bar + stage, 2 * cnt * SUB_BYTES);
           } else {
-            mbar_expect_tx(full_bar + stage, STAGE_BYTES);
-            tma_load_4d(map, full_bar + stage, a_dst, c_a, x_a, y_a, n0);
-            tma_load_2d(&tmB, full_bar + stage, b_dst, kb * BLOCK_K, nt * BLOCK_N);
+            mbar_expect_tx(full_bar + stage, cnt * SUB_BYTES);
+          }
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks) {
+            if (ks >= cnt) break;
+            const int kb = kb0 + ks;
+            uint8_t* a_dst = smem + stage * STAGE_BYTES + ks * SUB_BYTES;
+            uint8_t* b_dst = a_dst + A_BYTES;
+            int c_a, x_a, y_a;
+            const CUtensorMap* map;
+            if (kb < main_blocks) {
+              const int tap = kb / p.cin_blocks, cblk = kb - tap * p.cin_blocks;
+              const int trow = tap / p.tap_cols;
+              const int dy = p.dy0 + trow, dx = p.dx0 + tap - trow * p.tap_cols;
+              map = &tmA; c_a = cblk * BLOCK_K; x_a = dx; y_a = h0 * p.stride + dy;
+            } else if (kb < main_blocks + p.s0_blocks) {
+              map = &tmS0; c_a = (kb - main_blocks) * BLOCK_K; x_a = 0; y_a = h0;
+            } else {
+              map = &tmS1; c_a = (kb - main_blocks - p.s0_blocks) * BLOCK_K; x_a = 0; y_a = h0;
+            }
+            if (CG == 2) {
+              tma_load_4d_pair(map, lead_full, a_dst, c_a, x_a, y_a, n0);
+              tma_load_2d_pair(&tmB, lead_full, b_dst, kb * BLOCK_K, nt * BLOCK_N + (int)cta_rank * B_ROWS);
+            } else {
+              tma_load_4d(map, full_bar + stage, a_dst, c_a, x_a, y_a, n0);
+              tma_load_2d(&tmB, full_bar + stage, b_dst, kb * BLOCK_K, nt * BLOCK_N);
+            }
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
@@ -147,17 +209,47 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         mbar_wait(tempty_bar + acc, acc_phase ^ 1);  // epilogues (of both CTAs) have drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
-        for (int kb = 0; kb < nkb; ++kb) {
+        if (p.tall) {
+          const int a_tall_bytes = (p.Hb + 2) * p.Wb * BLOCK_K * 2;
+          const int n_sb = 3 * p.cin_blocks + p.s0_blocks + p.s1_blocks;
+          for (int sb = 0; sb < n_sb; ++sb) {
+            mbar_wait(full_bar + stage, phase);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
+            const uint32_t b_addr = a_addr + a_tall_bytes;
+            const int n_j = sb < 3 * p.cin_blocks ? 3 : 1;
+            for (int j = 0; j < n_j; ++j) {
+              const uint32_t a_j = a_addr + (uint32_t)(j * p.Wb * BLOCK_K * 2);  // dy = j - 1: shift by Wb rows (whole swizzle atoms)
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / 16; ++k) {
+                const uint64_t da = make_smem_desc<SWZ>(a_j + k * 32);
+                const uint64_t db = make_smem_desc<SWZ>(b_addr + j * B_BYTES + k * 32);
+                if (CG == 2) umma_bf16_pair(d_tmem, da, db, IDESC, (sb | j | k) != 0);
+                else umma_bf16(d_tmem, da, db, IDESC, (sb | j | k) != 0);
+              }
+            }
+            if (CG == 2) umma_commit_pair(empty_bar + stage); else umma_commit(empty_bar + stage);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+          if (CG == 2) umma_commit_pair(tfull_bar + acc); else umma_commit(tfull_bar + acc);
+          continue;
+        }
+        for (int kb0 = 0; kb0 < nkb; kb0 += KS) {
           mbar_wait(full_bar + stage, phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
-          const uint32_t b_addr = a_addr + A_BYTES;
+          const int cnt = (nkb - kb0) < KS ? (nkb - kb0) : KS;
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {
-            const uint64_t da = make_smem_desc<SWZ>(a_addr + k * 32);
-            const uint64_t db = make_smem_desc<SWZ>(b_addr + k * 32);
-            if (CG == 2) umma_bf16_pair(d_tmem, da, db, IDESC, (kb | k) != 0);
-            else umma_bf16(d_tmem, da, db, IDESC, (kb | k) != 0);
+          for (int ks = 0; ks < KS; ++ks) {
+            if (ks >= cnt) break;
+            const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES + ks * SUB_BYTES);
+            const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / 16; ++k) {
+              const uint64_t da = make_smem_desc<SWZ>(a_addr + k * 32);
+              const uint64_t db = make_smem_desc<SWZ>(b_addr + k * 32);
+              if (CG == 2) umma_bf16_pair(d_tmem, da, db, IDESC, (kb0 | ks | k) != 0);
+              else umma_bf16(d_tmem, da, db, IDESC, (kb0 | ks | k) != 0);
+            }
           }
           if (CG == 2) umma_commit_pair(empty_bar + stage); else umma_commit(empty_bar + stage);  // frees the smem slot(s)
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -182,7 +274,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       tc_fence_after();
       const int64_t nn = (int64_t)n0 + n_in;
       const bool valid = nn < p.B;
-      const int64_t pix = (nn * p.H_out + h0 + h_in) * p.W_out + w_in;
+      const int64_t pix = (nn * p.H_full + p.out_scale * (h0 + h_in) + p.out_oy) * p.W_full + p.out_scale * w_in + p.out_ox;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
       if (p.out_mode == CONV_OUT_BF16_NHWC) {
         constexpr int CH = BLOCK_N >= 32 ? 32 : 16;
@@ -223,8 +315,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         tmem_ld_wait();
         if (valid) {
           float* dst = reinterpret_cast<float*>(p.out);
-          const int64_t hw = (int64_t)p.H_out * p.W_out;
-          const int64_t sp = (int64_t)(h0 + h_in) * p.W_out + w_in;
+          const int64_t hw = (int64_t)p.H_full * p.W_full;
+          const int64_t sp = (int64_t)(p.out_scale * (h0 + h_in) + p.out_oy) * p.W_full + p.out_scale * w_in + p.out_ox;
 #pragma unroll
           for (int c = 0; c < 16; ++c)
             if (c < p.C_out_real) dst[(nn * p.C_out_real + c) * hw + sp] = __uint_as_float(r[c]) + __ldg(p.bias + c);
@@ -296,10 +388,12 @@ static int encode_weight_map(CUtensorMap* m, const void* base, int rows, int64_t
 }
 
 int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, const void* skip0, int C_s0, const void* skip1,
-              int C_s1, const void* residual, void* out, int out_mode, int64_t B, int H, int W, int C_in, int C_out, int ksize,
+              int C_s1, const void* residual, void* out, int out_mode, int64_t B, int H, int W, int C_in, int C_out, ConvGeom geom,
               int stride) {
   DLPM_REQUIRE(in && w && bias && out, "conv: NULL tensor");
-  DLPM_REQUIRE(ksize == 3 || ksize == 1, "conv: kernel size must be 1 or 3");
+  DLPM_REQUIRE(geom.tap_rows >= 1 && geom.tap_rows <= 3 && geom.tap_cols >= 1 && geom.tap_cols <= 3, "conv: 1..3 taps per dimension");
+  DLPM_REQUIRE(geom.out_scale == 1 || (geom.out_scale == 2 && stride == 1 && !skip0 && !skip1 && !residual &&
+                                        out_mode == CONV_OUT_BF16_NHWC), "conv: strided output only for plain stride-1 convs");
   DLPM_REQUIRE(stride == 1 || stride == 2, "conv: stride must be 1 or 2");
   DLPM_REQUIRE(B >= 1 && H >= 1 && W >= 1, "conv: bad shape");
   DLPM_REQUIRE(H % stride == 0 && W % stride == 0, "conv: H, W must be divisible by the stride");
@@ -332,12 +426,17 @@ int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, c
   L->tiles_per_img = L->Nb == 1 ? H_out / L->Hb : 0;
   L->n_m_tiles = L->Nb == 1 ? (int)(B * L->tiles_per_img) : (int)((B + L->Nb - 1) / L->Nb);
   L->n_n_tiles = C_out_pad / bn;
-  L->stride = stride; L->taps = ksize * ksize;
+  L->stride = stride; L->taps = geom.tap_rows * geom.tap_cols;
+  L->tap_cols = geom.tap_cols; L->dy0 = geom.dy0; L->dx0 = geom.dx0;
+  L->out_scale = geom.out_scale; L->out_oy = geom.out_oy; L->out_ox = geom.out_ox;
+  L->H_full = H_out * geom.out_scale; L->W_full = W_out * geom.out_scale;
   L->cin_blocks = C_in / bk; L->s0_blocks = C_s0 / bk; L->s1_blocks = C_s1 / bk;
   L->B = B; L->C_out = C_out; L->C_out_real = C_out; L->out_mode = out_mode;
   L->bias = bias; L->residual = reinterpret_cast<const __nv_bfloat16*>(residual); L->out = out;
+  L->tall = (L->Nb == 1 && geom.tap_rows == 3 && geom.tap_cols == 3 && geom.dy0 == -1 && geom.dx0 == -1 && stride == 1 &&
+             geom.out_scale == 1 && bn <= 128 && bn >= 32 && L->Wb % 8 == 0 && conv_tall_enabled()) ? 1 : 0;
   int rc;
-  if ((rc = encode_act_map(&L->tmA, in, B, H, W, C_in, bk, L->Wb, L->Hb, L->Nb, stride))) return rc;
+  if ((rc = encode_act_map(&L->tmA, in, B, H, W, C_in, bk, L->Wb, L->tall ? L->Hb + 2 : L->Hb, L->Nb, stride))) return rc;
   L->tmS0 = L->tmA; L->tmS1 = L->tmA;
   if (skip0 && (rc = encode_act_map(&L->tmS0, skip0, B, H_out, W_out, C_s0, bk, L->Wb, L->Hb, L->Nb, 1))) return rc;
   if (skip1 && (rc = encode_act_map(&L->tmS1, skip1, B, H_out, W_out, C_s1, bk, L->Wb, L->Hb, L->Nb, 1))) return rc;
@@ -350,6 +449,8 @@ int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, c
   return DLPM_OK;
 }
 
+static int g_tall_enabled = 1;
+int conv_tall_enabled() { return g_tall_enabled; }
 static int g_cta_group_override = -1;
 int conv_cta_group_override() {
   if (g_cta_group_override < 0) {
@@ -362,13 +463,15 @@ void conv_set_cta_group_override(int v) { g_cta_group_override = v; }
 
 template <int BN, int BK, int CG>
 static int launch_t(const ConvLaunch& L, cudaStream_t stream) {
-  constexpr int STAGE = 128 * BK * 2 + (BN / CG) * BK * 2;
+  constexpr int KS = BN <= 128 ? 2 : 1;
+  const int B_BYTES = (BN / CG) * BK * 2;
+  const int STAGE = L.tall ? (L.Hb + 2) * L.Wb * BK * 2 + 3 * B_BYTES : KS * (128 * BK * 2 + B_BYTES);
   int stages = kSmemBudget / STAGE;
   if (stages > kMaxStages) stages = kMaxStages;
   const size_t smem = (size_t)stages * STAGE + 1024 /*align*/ + (2 * kMaxStages + 4) * 8 + 16;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_conv_tc<BN, BK, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemBudget + 2048));
+    cudaError_t e = cudaFuncSetAttribute(k_conv_tc<BN, BK, CG, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemBudget + 2048));
     if (e != cudaSuccess) return cuda_fail(e, "conv smem attribute");
     attr_set = true;
   }
@@ -376,13 +479,16 @@ static int launch_t(const ConvLaunch& L, cudaStream_t stream) {
   p.n_m_tiles = L.n_m_tiles; p.n_n_tiles = L.n_n_tiles; p.stages = stages;
   p.Wb = L.Wb; p.Hb = L.Hb; p.Nb = L.Nb; p.H_out = L.H_out; p.W_out = L.W_out; p.tiles_per_img = L.tiles_per_img;
   p.stride = L.stride; p.taps = L.taps; p.cin_blocks = L.cin_blocks; p.s0_blocks = L.s0_blocks; p.s1_blocks = L.s1_blocks;
+  p.tap_cols = L.tap_cols; p.dy0 = L.dy0; p.dx0 = L.dx0; p.out_scale = L.out_scale; p.out_oy = L.out_oy; p.out_ox = L.out_ox;
+  p.H_full = L.H_full; p.W_full = L.W_full;
+  p.tall = L.tall; p.stage_bytes = STAGE;
   p.B = L.B; p.C_out = L.C_out; p.C_out_real = L.C_out_real; p.out_mode = L.out_mode;
   p.bias = L.bias; p.residual = L.residual; p.out = L.out;
   const int n_items = ((L.n_m_tiles + CG - 1) / CG) * L.n_n_tiles;
   const int max_groups = kNumSMs / CG;
   const int grid = (n_items < max_groups ? n_items : max_groups) * CG;
   if (CG == 1) {
-    k_conv_tc<BN, BK, 1><<<grid, kConvThreads, smem, stream>>>(L.tmA, L.tmS0, L.tmS1, L.tmB, p);
+    k_conv_tc<BN, BK, 1, KS><<<grid, kConvThreads, smem, stream>>>(L.tmA, L.tmS0, L.tmS1, L.tmB, p);
     DLPM_CHECK_LAUNCH("conv_tc");
   } else {
     cudaLaunchConfig_t cfg = {};
@@ -397,7 +503,7 @@ static int launch_t(const ConvLaunch& L, cudaStream_t stream) {
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, k_conv_tc<BN, BK, CG>, L.tmA, L.tmS0, L.tmS1, L.tmB, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_conv_tc<BN, BK, CG, KS>, L.tmA, L.tmS0, L.tmS1, L.tmB, p);
     if (e != cudaSuccess) return cuda_fail(e, "conv_tc pair launch");
   }
   return DLPM_OK;
@@ -424,6 +530,10 @@ using namespace dlpm;
 
 int dlpm_b200_set_option(const char* name, int value) {
   DLPM_REQUIRE(name != nullptr, "set_option: NULL name");
+  if (std::string(name) == "conv_tall") {
+    g_tall_enabled = value != 0;
+    return DLPM_OK;
+  }
   if (std::string(name) == "conv_cta_group") {
     DLPM_REQUIRE(value >= 0 && value <= 2, "set_option: conv_cta_group must be 0 (auto), 1 or 2");
     conv_set_cta_group_override(value);
@@ -436,8 +546,10 @@ int dlpm_b200_set_option(const char* name, int value) {
 int dlpm_b200_conv2d(const void* in, const void* w, const float* bias, const void* skip0, int C_s0, const void* skip1, int C_s1,
                      const void* residual, void* out, int out_mode, int64_t B, int H, int W, int C_in, int C_out, int ksize,
                      int stride, void* stream) {
+  DLPM_REQUIRE(ksize == 3 || ksize == 1, "conv: kernel size must be 1 or 3");
   ConvLaunch L;
-  if (int rc = conv_plan(&L, in, w, bias, skip0, C_s0, skip1, C_s1, residual, out, out_mode, B, H, W, C_in, C_out, ksize, stride))
+  if (int rc = conv_plan(&L, in, w, bias, skip0, C_s0, skip1, C_s1, residual, out, out_mode, B, H, W, C_in, C_out,
+                         conv_geom_default(ksize), stride))
     return rc;
   return conv_launch(L, (cudaStream_t)stream);
 }

@@ -12,11 +12,15 @@ enum ConvOutMode { CONV_OUT_BF16_NHWC = 0, CONV_OUT_F32_NCHW = 1 };
 struct ConvLaunch {
   CUtensorMap tmA, tmS0, tmS1, tmB;  // main activation, two optional 1x1 skip-conv sources, packed weights
   int block_n, block_k;              // tile N (16..256), K block in channels (64 or 32)
+  int tall;                          // 1 = one (Hb+2)-row activation box per (channel block, dx) feeds the three dy taps
   int cta_group;                     // 1 = single-CTA MMA, 2 = CTA pairs (tcgen05 cta_group::2, M = 256)
   int n_m_tiles, n_n_tiles;
   int Wb, Hb, Nb;                    // pixel box of one M tile: Wb*Hb*Nb == 128
   int H_out, W_out, tiles_per_img;
   int stride, taps;
+  int tap_cols, dy0, dx0;            // tap t reads the input shifted by (dy0 + t / tap_cols, dx0 + t % tap_cols)
+  int out_scale, out_oy, out_ox;     // output pixel of tile pixel (h, w): (out_scale*h + out_oy, out_scale*w + out_ox)
+  int H_full, W_full;                // spatial size of the output TENSOR (= out_scale * H_out, W_out)
   int cin_blocks, s0_blocks, s1_blocks;
   int64_t B;
   int C_out;       // row stride (channels) of the output / residual tensors
@@ -29,10 +33,20 @@ struct ConvLaunch {
 
 // Fills geometry + tensor maps.  in: NHWC bf16 [B, H, W, C_in]; w: bf16 [C_out_pad][taps*C_in + C_s0 + C_s1] (K contiguous);
 // skip sources NHWC bf16 [B, H_out, W_out, C_s*].  Returns DLPM_OK or an error code (message via set_error).
+// Tap geometry.  Default (ksize x ksize taps centred on the pixel, dense output) = a plain convolution; the UNet's
+// "nearest-upsample x2 then conv3x3" (unet.py:73-75) is run as four 2x2-tap convolutions on the LOW-resolution input,
+// one per output parity (out_scale = 2, out_oy/out_ox = parity), with pre-summed weights: 2.25x fewer FLOPs and no
+// upsampled tensor in memory.
+struct ConvGeom {
+  int tap_rows, tap_cols, dy0, dx0, out_scale, out_oy, out_ox;
+};
+inline ConvGeom conv_geom_default(int ksize) { return ConvGeom{ksize, ksize, -(ksize / 2), -(ksize / 2), 1, 0, 0}; }
+
 int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, const void* skip0, int C_s0, const void* skip1,
-              int C_s1, const void* residual, void* out, int out_mode, int64_t B, int H, int W, int C_in, int C_out, int ksize,
+              int C_s1, const void* residual, void* out, int out_mode, int64_t B, int H, int W, int C_in, int C_out, ConvGeom geom,
               int stride);
 int conv_launch(const ConvLaunch& L, cudaStream_t stream);
 int conv_cta_group_override();
+int conv_tall_enabled();
 
 }  // namespace dlpm

@@ -13,7 +13,8 @@ namespace dlpm {
 
 enum OpCode { OP_CONV_IN = 0, OP_GN = 1, OP_CONV = 2, OP_UP = 3, OP_ATTN = 4 };
 
-struct Op { int64_t f[16]; };
+constexpr int kOpFields = 24;
+struct Op { int64_t f[kOpFields]; };
 
 struct Plan {  // per batch size
   int64_t B = 0;
@@ -46,7 +47,8 @@ static int build_plan(UNetEngine* E, int64_t B, Plan* P) {
   for (const Op& op : E->ops) {
     if (op.f[0] != OP_CONV) continue;
     // f: 1 in, 2 out(-1 = external fp32 NCHW), 3 skip0, 4 C_s0, 5 skip1, 6 C_s1, 7 residual, 8 H, 9 W, 10 C_in, 11 C_out, 12 ksize,
-    //    13 stride, 14 w_off (bf16 elems), 15 bias_off (fp32 elems)
+    //    13 stride, 14 w_off (bf16 elems), 15 bias_off (fp32 elems), 16 tap_rows, 17 tap_cols, 18 dy0, 19 dx0, 20 out_scale, 21 out_oy,
+    //    22 out_ox
     ConvLaunch L;
     const void* s0 = op.f[3] >= 0 ? E->buf(op.f[3], B) : nullptr;
     const void* s1 = op.f[5] >= 0 ? E->buf(op.f[5], B) : nullptr;
@@ -55,7 +57,8 @@ static int build_plan(UNetEngine* E, int64_t B, Plan* P) {
     void* out = ext ? reinterpret_cast<void*>(0x10) /*patched at launch*/ : E->buf(op.f[2], B);
     int rc = conv_plan(&L, E->buf(op.f[1], B), E->wb + op.f[14], E->wf + op.f[15], s0, (int)op.f[4], s1, (int)op.f[6], res, out,
                        ext ? CONV_OUT_F32_NCHW : CONV_OUT_BF16_NHWC, B, (int)op.f[8], (int)op.f[9], (int)op.f[10], (int)op.f[11],
-                       (int)op.f[12], (int)op.f[13]);
+                       ConvGeom{(int)op.f[16], (int)op.f[17], (int)op.f[18], (int)op.f[19], (int)op.f[20], (int)op.f[21], (int)op.f[22]},
+                       (int)op.f[13]);
     if (rc) return rc;
     P->convs.push_back(L);
   }
@@ -195,7 +198,7 @@ int dlpm_b200_unet_profile(void* handle, const float* x, const float* t, int t_r
       double fl = 0.0;
       if (f[0] == OP_CONV) {  // 2 * M * N * K with M = B * H_out * W_out
         const double M = (double)B * (f[8] / f[13]) * (f[9] / f[13]);
-        fl = 2.0 * M * (double)f[11] * ((double)f[12] * f[12] * f[10] + f[4] + f[6]);
+        fl = 2.0 * M * (double)f[11] * ((double)f[16] * f[17] * f[10] + f[4] + f[6]);
       }
       flops_per_op[1 + i] = fl;
     }

@@ -12,7 +12,8 @@ namespace cg = cooperative_groups;
 
 namespace dlpm {
 
-__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
+// x * sigmoid(x) with MUFU.EX2 + MUFU.RCP (an IEEE divide costs ~20 instructions and made GroupNorm issue-bound)
+__device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
 __device__ __forceinline__ void unpack8(const uint4& raw, float (&v)[8]) {
   const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&raw);
@@ -140,8 +141,8 @@ __global__ void __launch_bounds__(kGnThreads) k_groupnorm_cluster(__nv_bfloat16*
   float* psq = psum + C;                                                            // [C]
   float* coef_a = psq + C;                                                          // [C]
   float* coef_b = coef_a + C;                                                       // [C]
-  float* part = coef_b + C;                                                         // [parts][C][2] scratch, parts * C <= 512
-  uint64_t* bar = reinterpret_cast<uint64_t*>(part + 1024);
+  float* part = coef_b + C;                                                         // [parts][C/2][4] scratch, parts * C/2 <= 512
+  uint64_t* bar = reinterpret_cast<uint64_t*>(part + 2048);
   const int p0 = rank * pix_per_cta;
   // phase 1: global -> shared with bulk asynchronous copies (the only read of the tensor)
   if (threadIdx.x == 0) {
@@ -167,24 +168,31 @@ __global__ void __launch_bounds__(kGnThreads) k_groupnorm_cluster(__nv_bfloat16*
     }
   }
   // phase 2: per-channel sums over this CTA's pixels (2-byte shared loads, consecutive threads = consecutive channels)
-  const int parts = nthreads / C > 0 ? nthreads / C : 1;
-  for (int item = threadIdx.x; item < parts * C; item += nthreads) {
-    const int ch = item % C, pt = item / C;
-    const __nv_bfloat16* col = ch < C0 ? plane0 + ch : plane1 + (ch - C0);
-    const int stride = ch < C0 ? C0 : C1;
-    float sA = 0.f, qA = 0.f;
+  // (channel PAIRS: one 4-byte shared load feeds two channels; consecutive threads = consecutive pairs, conflict-free)
+  const int C2 = C >> 1;
+  const int parts = nthreads / C2 > 0 ? nthreads / C2 : 1;  // pixel phases per channel pair; parts * C2 <= 512
+  for (int item = threadIdx.x; item < parts * C2; item += nthreads) {
+    const int cp = item % C2, pt = item / C2, ch = cp * 2;
+    const __nv_bfloat162* col = reinterpret_cast<const __nv_bfloat162*>(ch < C0 ? plane0 + ch : plane1 + (ch - C0));
+    const int stride2 = (ch < C0 ? C0 : C1) >> 1;
+    float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+#pragma unroll 4
     for (int p = pt; p < pix_per_cta; p += parts) {
-      const float xv = __bfloat162float(col[p * stride]);
-      sA += xv;
-      qA = fmaf(xv, xv, qA);
+      const float2 xv = __bfloat1622float2(col[p * stride2]);
+      s0 += xv.x; q0 = fmaf(xv.x, xv.x, q0);
+      s1 += xv.y; q1 = fmaf(xv.y, xv.y, q1);
     }
-    part[(pt * C + ch) * 2] = sA;
-    part[(pt * C + ch) * 2 + 1] = qA;
+    float4* dstp = reinterpret_cast<float4*>(part) + (pt * C2 + cp);
+    *dstp = make_float4(s0, q0, s1, q1);
   }
   __syncthreads();
   for (int ch = threadIdx.x; ch < C; ch += nthreads) {
     float sA = 0.f, qA = 0.f;
-    for (int pt = 0; pt < parts; ++pt) { sA += part[(pt * C + ch) * 2]; qA += part[(pt * C + ch) * 2 + 1]; }
+    for (int pt = 0; pt < parts; ++pt) {
+      const float* e = part + ((pt * C2 + (ch >> 1)) * 4) + (ch & 1) * 2;
+      sA += e[0];
+      qA += e[1];
+    }
     psum[ch] = sA;
     psq[ch] = qA;
   }
@@ -441,7 +449,7 @@ int dlpm_b200_groupnorm_silu(void* out, const void* in0, int C0, const void* in1
   while (cs < 8 && bytes / cs > kGnClusterSmemData) cs *= 2;
   if (bytes / cs <= kGnClusterSmemData && HW % cs == 0 && B * cs < (1ll << 31)) {
     const int pix = HW / cs;
-    const size_t smem = (size_t)pix * C * 2 + (size_t)(4 * C + 2 * 512) * sizeof(float) + 16;
+    const size_t smem = (size_t)pix * C * 2 + (size_t)(4 * C + 4 * 512) * sizeof(float) + 16;
     // small slices: 256-thread CTAs so that more of them are co-resident (the kernel is then pure latency)
     int threads = ((int64_t)pix * (C / 8) <= 2048) ? 256 : kGnThreads;
     if (threads < C / 8) threads = kGnThreads;

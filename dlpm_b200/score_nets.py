@@ -183,6 +183,7 @@ def as_native(model, device):
 # UNet (image configs)
 # ------------------------------------------------------------------------------------------------
 OP_CONV_IN, OP_GN, OP_CONV, OP_UP, OP_ATTN = 0, 1, 2, 3, 4
+OP_FIELDS = 24  # int64 fields per op record (unet_engine.cu: kOpFields)
 
 
 def _gn(c):
@@ -325,14 +326,17 @@ class UNetModel(nn.Module):
             return off
 
         def op(*f):
-            f = list(f) + [0] * (16 - len(f))
+            f = list(f) + [0] * (OP_FIELDS - len(f))
             ops.append([int(v) for v in f])
 
         def conv(src, C_in, H_, W_, w, b, out_buf, ksize=3, stride=1, skips=(), skip_w=None, skip_b=None, residual=-1,
-                 C_out_pad=None):
+                 C_out_pad=None, geom=None):
+            """geom = (tap_rows, tap_cols, dy0, dx0, out_scale, out_oy, out_ox); default: centred ksize x ksize taps."""
             C_out = w.shape[0]
             wk = w.detach().float()
             wk = wk.permute(0, 2, 3, 1).reshape(C_out, -1) if wk.dim() == 4 else wk.reshape(C_out, -1)
+            if geom is None:
+                geom = (ksize, ksize, -(ksize // 2), -(ksize // 2), 1, 0, 0)
             bias = b.detach().float()
             if skips:
                 wk = torch.cat([wk, skip_w.detach().float().reshape(C_out, -1)], dim=1)
@@ -342,7 +346,7 @@ class UNetModel(nn.Module):
                 bias = torch.cat([bias, torch.zeros(C_out_pad - C_out, device=bias.device)])
             s = list(skips) + [(-1, 0)] * (2 - len(skips))
             op(OP_CONV, src, out_buf, s[0][0], s[0][1], s[1][0], s[1][1], residual, H_, W_, C_in, C_out, ksize, stride,
-               add_b(wk), add_f(bias))
+               add_b(wk), add_f(bias), *geom)
 
         ss_off = [0]
         emb_w, emb_b = [], []
@@ -405,13 +409,18 @@ class UNetModel(nn.Module):
                     conv(src, C, H_, W_, layer.op.weight, layer.op.bias, h, stride=2)
                     H_, W_ = H_ // 2, W_ // 2
                 elif isinstance(layer, _UpParams):
-                    up = new_buf(4 * H_ * W_ * C, tmp=True)
-                    op(OP_UP, h, up, H_, W_, C)
-                    H_, W_ = 2 * H_, 2 * W_
-                    h2 = new_buf(H_ * W_ * C)
+                    # nearest x2 + conv3x3 (unet.py:73-75) == four 2x2-tap convs on the low-res tensor, one per output
+                    # parity, with the 3x3 weights that hit the same source pixel pre-summed (2.25x fewer FLOPs)
+                    h2 = new_buf(4 * H_ * W_ * C)
                     names["%s.%d" % (tag, j)] = h2
-                    conv(up, C, H_, W_, layer.conv.weight, layer.conv.bias, h2)
-                    release(up)
+                    w3 = layer.conv.weight.detach().float()  # [C_out, C_in, 3, 3]
+                    rows = {0: ((0,), (1, 2)), 1: ((0, 1), (2,))}  # parity -> 3x3 taps merged into 2x2 tap a = 0, 1
+                    for py in (0, 1):
+                        for px in (0, 1):
+                            w2 = torch.stack([torch.stack([w3[:, :, list(rows[py][a])][:, :, :, list(rows[px][bb])].sum(dim=(2, 3))
+                                                           for bb in (0, 1)], dim=-1) for a in (0, 1)], dim=-2)  # [C_out, C_in, 2, 2]
+                            conv(h, C, H_, W_, w2, layer.conv.bias, h2, ksize=2, geom=(2, 2, py - 1, px - 1, 2, py, px))
+                    H_, W_ = 2 * H_, 2 * W_
                     h = h2
                 else:
                     raise TypeError(type(layer))

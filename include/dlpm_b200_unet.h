@@ -31,7 +31,9 @@ int dlpm_b200_conv2d(const void* in, const void* w, const float* bias, const voi
                      int C_out, int ksize, int stride, void* stream);
 
 /* Tuning / debugging knobs.  "conv_cta_group": 0 = automatic (CTA pairs with tcgen05 cta_group::2 when the problem has
- * enough tiles), 1 = always single-CTA MMAs, 2 = always CTA pairs.  Takes effect for descriptors built afterwards. */
+ * enough tiles), 1 = always single-CTA MMAs, 2 = always CTA pairs.  "conv_tall": 1 (default) lets 3x3 stride-1 convs with
+ * narrow output tiles load one (rows+2)-tall activation box per horizontal tap and reuse it for the three vertical taps,
+ * 0 loads one box per tap.  Takes effect for descriptors built afterwards. */
 int dlpm_b200_set_option(const char* name, int value);
 
 /* K6. GroupNorm(min(32,C) groups, eps 1e-5) over the virtual concatenation [in0 | in1] of two NHWC bf16
@@ -68,7 +70,7 @@ int dlpm_b200_time_embedding(float* ss, float* semb, const float* t, const int* 
  * over an op list + two packed weight blobs; the engine owns activation buffers and TMA descriptors.
  *   header  int64[16] : {n_ops, n_bufs, in_ch, out_ch, H, W, model_channels, ss_total,
  *                        p_w0T, p_b0, p_w2T, p_b2, p_wallT, p_ball, 0, 0}   (p_* = fp32-blob offsets)
- *   ops     int64[n_ops][16], bufs int64[n_bufs] = bf16 elements per sample of each activation buffer
+ *   ops     int64[n_ops][24], bufs int64[n_bufs] = bf16 elements per sample of each activation buffer
  *   wb      bf16 blob (conv weights, device), wf fp32 blob (everything else, device); both are copied. */
 int dlpm_b200_unet_create(void** handle, const int64_t* header, const int64_t* ops, const int64_t* bufs, const void* wb,
                           int64_t n_wb, const float* wf, int64_t n_wf, int64_t max_batch);
