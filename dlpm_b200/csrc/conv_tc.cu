@@ -270,15 +270,23 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       else { n0 = mt * p.Nb; h0 = 0; }
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(tfull_bar + acc, acc_phase);
-      tc_fence_after();
       const int64_t nn = (int64_t)n0 + n_in;
       const bool valid = nn < p.B;
       const int64_t pix = (nn * p.H_full + p.out_scale * (h0 + h_in) + p.out_oy) * p.W_full + p.out_scale * w_in + p.out_ox;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
       if (p.out_mode == CONV_OUT_BF16_NHWC) {
         constexpr int CH = BLOCK_N >= 32 ? 32 : 16;
-#pragma unroll 1
+        // identity-skip rows are fetched BEFORE waiting for the accumulator so their HBM latency hides behind the MMAs
+        uint4 resv[BLOCK_N / 8];
+        const bool has_res = p.residual != nullptr && valid;
+        if (has_res) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.C_out + nt * BLOCK_N);
+#pragma unroll
+          for (int j = 0; j < BLOCK_N / 8; ++j) resv[j] = __ldg(rp + j);
+        }
+        mbar_wait(tfull_bar + acc, acc_phase);
+        tc_fence_after();
+#pragma unroll
         for (int c0 = 0; c0 < BLOCK_N; c0 += CH) {
           uint32_t r[CH];
           if constexpr (CH == 32) tmem_ld_x32(t_row + c0, r);
@@ -288,14 +296,13 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const int col = nt * BLOCK_N + c0;
             const float* bias = p.bias + col;
             __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.C_out + col;
-            const __nv_bfloat16* res = p.residual ? p.residual + pix * p.C_out + col : nullptr;
 #pragma unroll
             for (int j = 0; j < CH; j += 8) {
               float v[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[j + e]) + __ldg(bias + j + e);
-              if (res) {
-                const uint4 rv = *reinterpret_cast<const uint4*>(res + j);
+              if (has_res) {
+                const uint4 rv = resv[(c0 + j) / 8];
                 const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(rp[e]); v[2 * e] += f.x; v[2 * e + 1] += f.y; }
@@ -310,6 +317,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
       } else {
         // fp32 NCHW, first C_out_real channels of the (zero-padded) tile: the network's final conv (unet.py:435)
+        mbar_wait(tfull_bar + acc, acc_phase);
+        tc_fence_after();
         uint32_t r[16];
         tmem_ld_x16(t_row, r);
         tmem_ld_wait();
@@ -434,7 +443,7 @@ int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, c
   L->B = B; L->C_out = C_out; L->C_out_real = C_out; L->out_mode = out_mode;
   L->bias = bias; L->residual = reinterpret_cast<const __nv_bfloat16*>(residual); L->out = out;
   L->tall = (L->Nb == 1 && geom.tap_rows == 3 && geom.tap_cols == 3 && geom.dy0 == -1 && geom.dx0 == -1 && stride == 1 &&
-             geom.out_scale == 1 && bn <= 128 && bn >= 32 && L->Wb % 8 == 0 && conv_tall_enabled()) ? 1 : 0;
+             geom.out_scale == 1 && bn <= 128 && L->Wb % 8 == 0 && conv_tall_enabled()) ? 1 : 0;
   int rc;
   if ((rc = encode_act_map(&L->tmA, in, B, H, W, C_in, bk, L->Wb, L->tall ? L->Hb + 2 : L->Hb, L->Nb, stride))) return rc;
   L->tmS0 = L->tmA; L->tmS1 = L->tmA;
@@ -443,7 +452,7 @@ int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, c
   const int64_t k_total = (int64_t)L->taps * C_in + C_s0 + C_s1;
   // CTA pairs (cta_group::2) when there are enough M tiles to keep all 74 pairs busy
   L->cta_group = (conv_cta_group_override() == 1) ? 1
-                 : ((bn >= 32 && (int64_t)((L->n_m_tiles + 1) / 2) * L->n_n_tiles >= kNumSMs / 2) ? 2 : 1);
+                 : ((bn >= 32 && (int64_t)((L->n_m_tiles + 1) / 2) * L->n_n_tiles >= 32) ? 2 : 1);
   if (conv_cta_group_override() == 2 && bn >= 32) L->cta_group = 2;
   if ((rc = encode_weight_map(&L->tmB, w, C_out_pad, k_total, bn / L->cta_group, bk))) return rc;
   return DLPM_OK;
