@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(kGnThreads) k_groupnorm(__nv_bfloat16* __restr
 // through distributed shared memory (fixed rank order -> bitwise deterministic), then the data is normalised from
 // shared memory.  No second pass over global memory, no atomics.
 // ------------------------------------------------------------------------------------------------
-constexpr int kGnClusterSmemData = 80 * 1024;  // per-CTA slice of the sample: two CTAs (+ 16 KB scratch each) fit one SM
+constexpr int kGnClusterSmemData = 96 * 1024;
 
 __device__ __forceinline__ uint32_t gn_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -141,8 +141,8 @@ __global__ void __launch_bounds__(kGnThreads) k_groupnorm_cluster(__nv_bfloat16*
   float* psq = psum + C;                                                            // [C]
   float* coef_a = psq + C;                                                          // [C]
   float* coef_b = coef_a + C;                                                       // [C]
-  float* part = coef_b + C;                                                         // 16 KB scratch (slot merge, then totals)
-  uint64_t* bar = reinterpret_cast<uint64_t*>(part + 4096);
+  float* part = coef_b + C;                                                         // [parts][C/2][4] scratch, parts * C/2 <= 512
+  uint64_t* bar = reinterpret_cast<uint64_t*>(part + 2048);
   const int p0 = rank * pix_per_cta;
   // phase 1: global -> shared with bulk asynchronous copies (the only read of the tensor)
   if (threadIdx.x == 0) {
@@ -167,56 +167,34 @@ __global__ void __launch_bounds__(kGnThreads) k_groupnorm_cluster(__nv_bfloat16*
       if (++spins > (1u << 26)) __trap();
     }
   }
-  // phase 2: per-channel sums over this CTA's pixels.  Thread (v, slot) accumulates its 8 channels over the pixels
-  // p = slot, slot + slots, ... with 16-byte shared loads; the slots are then merged through a <= 16 KB scratch in a
-  // fixed order (bitwise deterministic): rows [0, R) are written first, rows [R, 2R) ... are added on top, round by round.
-  const int slots = nthreads / nvec;
-  const int v = threadIdx.x % nvec, slot = threadIdx.x / nvec;
-  const bool active = slot < slots;
-  const int c = v * 8;
-  const uint4* srcv = c < C0 ? reinterpret_cast<const uint4*>(plane0) + v : reinterpret_cast<const uint4*>(plane1) + (v - nvec0);
-  const int sstride = c < C0 ? nvec0 : nvec - nvec0;
-  {
-    float sA[8], qA[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) { sA[e] = 0.f; qA[e] = 0.f; }
-    if (active) {
-#pragma unroll 2
-      for (int p = slot; p < pix_per_cta; p += slots) {
-        float x[8];
-        unpack8(srcv[p * sstride], x);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { sA[e] += x[e]; qA[e] = fmaf(x[e], x[e], qA[e]); }
-      }
+  // phase 2: per-channel sums over this CTA's pixels (2-byte shared loads, consecutive threads = consecutive channels)
+  // (channel PAIRS: one 4-byte shared load feeds two channels; consecutive threads = consecutive pairs, conflict-free)
+  const int C2 = C >> 1;
+  const int parts = nthreads / C2 > 0 ? nthreads / C2 : 1;  // pixel phases per channel pair; parts * C2 <= 512
+  for (int item = threadIdx.x; item < parts * C2; item += nthreads) {
+    const int cp = item % C2, pt = item / C2, ch = cp * 2;
+    const __nv_bfloat162* col = reinterpret_cast<const __nv_bfloat162*>(ch < C0 ? plane0 + ch : plane1 + (ch - C0));
+    const int stride2 = (ch < C0 ? C0 : C1) >> 1;
+    float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+#pragma unroll 4
+    for (int p = pt; p < pix_per_cta; p += parts) {
+      const float2 xv = __bfloat1622float2(col[p * stride2]);
+      s0 += xv.x; q0 = fmaf(xv.x, xv.x, q0);
+      s1 += xv.y; q1 = fmaf(xv.y, xv.y, q1);
     }
-    int R = 2048 / C;  // scratch rows: R * C * 2 floats <= 16 KB
-    if (R < 1) R = 1;
-    if (R > slots) R = slots;
-    float* redS = part;          // [R][C]
-    float* redQ = part + R * C;  // [R][C]
-    for (int base = 0; base < slots; base += R) {
-      if (active && slot >= base && slot < base + R) {
-        float4* ps = reinterpret_cast<float4*>(redS + (slot - base) * C + c);
-        float4* pq = reinterpret_cast<float4*>(redQ + (slot - base) * C + c);
-        if (base == 0) {
-          ps[0] = make_float4(sA[0], sA[1], sA[2], sA[3]); ps[1] = make_float4(sA[4], sA[5], sA[6], sA[7]);
-          pq[0] = make_float4(qA[0], qA[1], qA[2], qA[3]); pq[1] = make_float4(qA[4], qA[5], qA[6], qA[7]);
-        } else {
-          float4 a0 = ps[0], a1 = ps[1], b0 = pq[0], b1 = pq[1];
-          a0.x += sA[0]; a0.y += sA[1]; a0.z += sA[2]; a0.w += sA[3]; a1.x += sA[4]; a1.y += sA[5]; a1.z += sA[6]; a1.w += sA[7];
-          b0.x += qA[0]; b0.y += qA[1]; b0.z += qA[2]; b0.w += qA[3]; b1.x += qA[4]; b1.y += qA[5]; b1.z += qA[6]; b1.w += qA[7];
-          ps[0] = a0; ps[1] = a1; pq[0] = b0; pq[1] = b1;
-        }
-      }
-      __syncthreads();
+    float4* dstp = reinterpret_cast<float4*>(part) + (pt * C2 + cp);
+    *dstp = make_float4(s0, q0, s1, q1);
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < C; ch += nthreads) {
+    float sA = 0.f, qA = 0.f;
+    for (int pt = 0; pt < parts; ++pt) {
+      const float* e = part + ((pt * C2 + (ch >> 1)) * 4) + (ch & 1) * 2;
+      sA += e[0];
+      qA += e[1];
     }
-    for (int ch = threadIdx.x; ch < C; ch += nthreads) {
-      float ts = 0.f, tq = 0.f;
-      for (int r = 0; r < R; ++r) { ts += redS[r * C + ch]; tq += redQ[r * C + ch]; }
-      psum[ch] = ts;
-      psq[ch] = tq;
-    }
-    __syncthreads();  // scratch is reused by phase 3
+    psum[ch] = sA;
+    psq[ch] = qA;
   }
   cluster.sync();
   // phase 3: totals over the cluster (DSMEM reads, fixed order), group statistics, affine coefficients
@@ -250,10 +228,15 @@ __global__ void __launch_bounds__(kGnThreads) k_groupnorm_cluster(__nv_bfloat16*
   }
   cluster.sync();  // every CTA has finished reading its peers' shared memory; also orders coef_* for this CTA
   // phase 4: normalise from shared memory -> global (the only write)
-  if (active) {
+  const int slots = nthreads / nvec;
+  const int v = threadIdx.x % nvec, slot = threadIdx.x / nvec;
+  if (slot < slots) {
+    const int c = v * 8;
     float a[8], b[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) { a[e] = coef_a[c + e]; b[e] = coef_b[c + e]; }
+    const uint4* srcv = c < C0 ? reinterpret_cast<const uint4*>(plane0) + v : reinterpret_cast<const uint4*>(plane1) + (v - nvec0);
+    const int sstride = c < C0 ? nvec0 : nvec - nvec0;
     __nv_bfloat16* dst = out + ((int64_t)n * HW + p0) * C + c;
     for (int p = slot; p < pix_per_cta; p += slots) {
       float x[8];
@@ -335,43 +318,56 @@ __global__ void __launch_bounds__(256) k_conv_in(__nv_bfloat16* __restrict__ out
     s_in[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(x + (((int64_t)n * C_in + ci) * H + yy) * W + xx) : 0.f;
   }
   __syncthreads();
+  // thread = (pixel column px, 4-channel slice gq, block of 4 channel sets) and computes ALL kRows rows of the band:
+  // every 16-byte weight read (4 shared-memory wavefronts) feeds 16 FMAs, so the kernel is FMA- not LDS-bound
   const int sets = C_out >> 5;            // 32-channel sets; a thread owns 4 channels of up to 4 sets
   const int gq = threadIdx.x & 7;         // which 4-channel slice inside each 32-channel set
-  const int items = kConvInRows * W * ((sets + 3) / 4);
-  for (int item = threadIdx.x >> 3; item < items; item += blockDim.x >> 3) {
-    const int sb = item / (kConvInRows * W);  // block of 4 sets (C_out > 128)
-    const int rem = item - sb * kConvInRows * W;
-    const int row = rem / W, px = rem - row * W;
-    if (y0 + row >= H) continue;
-    float acc[4][4];
+  const int nsb = (sets + 3) / 4;
+  for (int item = threadIdx.x >> 3; item < W * nsb; item += blockDim.x >> 3) {
+    const int sb = item / W, px = item - sb * W;
+    float acc[kConvInRows][4][4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int c = (sb * 4 + j) * 32 + gq * 4;
       const float4 bv = (sb * 4 + j) < sets ? *reinterpret_cast<const float4*>(s_b + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-      acc[j][0] = bv.x; acc[j][1] = bv.y; acc[j][2] = bv.z; acc[j][3] = bv.w;
+#pragma unroll
+      for (int r = 0; r < kConvInRows; ++r) { acc[r][j][0] = bv.x; acc[r][j][1] = bv.y; acc[r][j][2] = bv.z; acc[r][j][3] = bv.w; }
     }
-    for (int ci = 0; ci < C_in; ++ci)
+    for (int ci = 0; ci < C_in; ++ci) {
+      float win[kConvInRows + 2][3];
+#pragma unroll
+      for (int r = 0; r < kConvInRows + 2; ++r)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) win[r][dx] = s_in[(ci * R + r) * Wp + px + dx];
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
-        const float v = s_in[(ci * R + row + t / 3) * Wp + px + t % 3];
         const float* wr = s_w + (ci * 9 + t) * C_out + gq * 4;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           if ((sb * 4 + j) < sets) {
             const float4 wv = *reinterpret_cast<const float4*>(wr + (sb * 4 + j) * 32);
-            acc[j][0] = fmaf(v, wv.x, acc[j][0]); acc[j][1] = fmaf(v, wv.y, acc[j][1]);
-            acc[j][2] = fmaf(v, wv.z, acc[j][2]); acc[j][3] = fmaf(v, wv.w, acc[j][3]);
+#pragma unroll
+            for (int r = 0; r < kConvInRows; ++r) {
+              const float v = win[r + t / 3][t % 3];
+              acc[r][j][0] = fmaf(v, wv.x, acc[r][j][0]); acc[r][j][1] = fmaf(v, wv.y, acc[r][j][1]);
+              acc[r][j][2] = fmaf(v, wv.z, acc[r][j][2]); acc[r][j][3] = fmaf(v, wv.w, acc[r][j][3]);
+            }
           }
         }
       }
-    __nv_bfloat16* dst = out + (((int64_t)n * H + y0 + row) * W + px) * C_out + gq * 4;
+    }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if ((sb * 4 + j) < sets) {
-        uint2 o;
-        *reinterpret_cast<__nv_bfloat162*>(&o.x) = __floats2bfloat162_rn(acc[j][0], acc[j][1]);
-        *reinterpret_cast<__nv_bfloat162*>(&o.y) = __floats2bfloat162_rn(acc[j][2], acc[j][3]);
-        *reinterpret_cast<uint2*>(dst + (sb * 4 + j) * 32) = o;
+    for (int r = 0; r < kConvInRows; ++r) {
+      if (y0 + r >= H) continue;
+      __nv_bfloat16* dst = out + (((int64_t)n * H + y0 + r) * W + px) * C_out + gq * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if ((sb * 4 + j) < sets) {
+          uint2 o;
+          *reinterpret_cast<__nv_bfloat162*>(&o.x) = __floats2bfloat162_rn(acc[r][j][0], acc[r][j][1]);
+          *reinterpret_cast<__nv_bfloat162*>(&o.y) = __floats2bfloat162_rn(acc[r][j][2], acc[r][j][3]);
+          *reinterpret_cast<uint2*>(dst + (sb * 4 + j) * 32) = o;
+        }
       }
     }
   }
@@ -466,7 +462,7 @@ int dlpm_b200_groupnorm_silu(void* out, const void* in0, int C0, const void* in1
   while (cs < 8 && bytes / cs > kGnClusterSmemData) cs *= 2;
   if (bytes / cs <= 112 * 1024 /* one CTA per SM in the worst case */ && HW % cs == 0 && B * cs < (1ll << 31)) {
     const int pix = HW / cs;
-    const size_t smem = (size_t)pix * C * 2 + (size_t)(4 * C + 4096) * sizeof(float) + 16;
+    const size_t smem = (size_t)pix * C * 2 + (size_t)(4 * C + 4 * 512) * sizeof(float) + 16;
     // small slices: 256-thread CTAs so that more of them are co-resident (the kernel is then pure latency)
     int threads = ((int64_t)pix * (C / 8) <= 2048) ? 256 : kGnThreads;
     if (threads < C / 8) threads = kGnThreads;
