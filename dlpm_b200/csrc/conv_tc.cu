@@ -36,6 +36,7 @@ struct ConvKParams {
   int Wb, Hb, Nb, H_out, W_out, tiles_per_img;
   int stride, taps, cin_blocks, s0_blocks, s1_blocks;
   int tap_cols, dy0, dx0, out_scale, out_oy, out_ox, H_full, W_full;
+  int n_par, c_out_pad;   // n_par = 4: the four output-parity 2x2 convs of a folded upsample+conv3x3 share one launch
   int tall, stage_bytes;  // tall: one (Hb+2)-row activation box per (channel block, dx) serves the three dy taps
   int64_t B;
   int C_out, C_out_real, out_mode;
@@ -81,7 +82,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const int main_blocks = p.taps * p.cin_blocks;
   const int nkb = main_blocks + p.s0_blocks + p.s1_blocks;
   const int m_groups = (p.n_m_tiles + CG - 1) / CG;   // a work item = CG adjacent M tiles x one N tile
-  const int n_items = m_groups * p.n_n_tiles;
+  const int items_per_par = m_groups * p.n_n_tiles;
+  const int n_items = items_per_par * p.n_par;
   const int first_item = blockIdx.x / CG, item_stride = gridDim.x / CG;
 
   if (warp == 0 && lane == 0) {
@@ -110,7 +112,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int item = first_item; item < n_items; item += item_stride) {
-        const int nt = item % p.n_n_tiles, mt = (item / p.n_n_tiles) * CG + (int)cta_rank;
+        const int par = item / items_per_par, it_in = item - par * items_per_par;
+        const int nt = it_in % p.n_n_tiles, mt = (it_in / p.n_n_tiles) * CG + (int)cta_rank;
+        const int dy_base = p.dy0 + (p.n_par == 4 ? (par >> 1) : 0), dx_base = p.dx0 + (p.n_par == 4 ? (par & 1) : 0);
+        const int brow0 = par * p.c_out_pad + nt * BLOCK_N + (int)cta_rank * B_ROWS;
         int n0, h0;
         if (p.Nb == 1) { n0 = mt / p.tiles_per_img; h0 = (mt - n0 * p.tiles_per_img) * p.Hb; }
         else { n0 = mt * p.Nb; h0 = 0; }
@@ -130,7 +135,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             } else {
               mbar_expect_tx(full_bar + stage, bytes);
             }
-            const int brow = nt * BLOCK_N + (int)cta_rank * B_ROWS;
+            const int brow = brow0;
             if (main_part) {
               const int cblk = sb / 3, dxi = sb - cblk * 3;
               if (CG == 2) tma_load_4d_pair(&tmA, lead_full, a_dst, cblk * BLOCK_K, dxi - 1, h0 - 1, n0);
@@ -179,7 +184,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             if (kb < main_blocks) {
               const int tap = kb / p.cin_blocks, cblk = kb - tap * p.cin_blocks;
               const int trow = tap / p.tap_cols;
-              const int dy = p.dy0 + trow, dx = p.dx0 + tap - trow * p.tap_cols;
+              const int dy = dy_base + trow, dx = dx_base + tap - trow * p.tap_cols;
               map = &tmA; c_a = cblk * BLOCK_K; x_a = dx; y_a = h0 * p.stride + dy;
             } else if (kb < main_blocks + p.s0_blocks) {
               map = &tmS0; c_a = (kb - main_blocks) * BLOCK_K; x_a = 0; y_a = h0;
@@ -188,10 +193,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
             if (CG == 2) {
               tma_load_4d_pair(map, lead_full, a_dst, c_a, x_a, y_a, n0);
-              tma_load_2d_pair(&tmB, lead_full, b_dst, kb * BLOCK_K, nt * BLOCK_N + (int)cta_rank * B_ROWS);
+              tma_load_2d_pair(&tmB, lead_full, b_dst, kb * BLOCK_K, brow0);
             } else {
               tma_load_4d(map, full_bar + stage, a_dst, c_a, x_a, y_a, n0);
-              tma_load_2d(&tmB, full_bar + stage, b_dst, kb * BLOCK_K, nt * BLOCK_N);
+              tma_load_2d(&tmB, full_bar + stage, b_dst, kb * BLOCK_K, brow0);
             }
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -264,7 +269,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int w_in = m % p.Wb, h_in = (m / p.Wb) % p.Hb, n_in = m / (p.Wb * p.Hb);
     int it = 0;
     for (int item = first_item; item < n_items; item += item_stride, ++it) {
-      const int nt = item % p.n_n_tiles, mt = (item / p.n_n_tiles) * CG + (int)cta_rank;
+      const int par = item / items_per_par, it_in = item - par * items_per_par;
+      const int nt = it_in % p.n_n_tiles, mt = (it_in / p.n_n_tiles) * CG + (int)cta_rank;
+      const int out_oy = p.n_par == 4 ? (par >> 1) : p.out_oy, out_ox = p.n_par == 4 ? (par & 1) : p.out_ox;
       int n0, h0;
       if (p.Nb == 1) { n0 = mt / p.tiles_per_img; h0 = (mt - n0 * p.tiles_per_img) * p.Hb; }
       else { n0 = mt * p.Nb; h0 = 0; }
@@ -272,7 +279,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const uint32_t acc_phase = (it >> 1) & 1;
       const int64_t nn = (int64_t)n0 + n_in;
       const bool valid = nn < p.B;
-      const int64_t pix = (nn * p.H_full + p.out_scale * (h0 + h_in) + p.out_oy) * p.W_full + p.out_scale * w_in + p.out_ox;
+      const int64_t pix = (nn * p.H_full + p.out_scale * (h0 + h_in) + out_oy) * p.W_full + p.out_scale * w_in + out_ox;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
       if (p.out_mode == CONV_OUT_BF16_NHWC) {
         constexpr int CH = BLOCK_N >= 32 ? 32 : 16;
@@ -325,7 +332,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (valid) {
           float* dst = reinterpret_cast<float*>(p.out);
           const int64_t hw = (int64_t)p.H_full * p.W_full;
-          const int64_t sp = (int64_t)(p.out_scale * (h0 + h_in) + p.out_oy) * p.W_full + p.out_scale * w_in + p.out_ox;
+          const int64_t sp = (int64_t)(p.out_scale * (h0 + h_in) + out_oy) * p.W_full + p.out_scale * w_in + out_ox;
 #pragma unroll
           for (int c = 0; c < 16; ++c)
             if (c < p.C_out_real) dst[(nn * p.C_out_real + c) * hw + sp] = __uint_as_float(r[c]) + __ldg(p.bias + c);
@@ -427,7 +434,7 @@ int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, c
   L->Hb = (128 / W_out) < H_out ? (128 / W_out) : H_out;
   L->Nb = 128 / (L->Wb * L->Hb);
   {  // small problems (4x4 / 8x8 feature maps): prefer more, narrower tiles so that every SM gets work
-    const int64_t m_tiles = L->Nb == 1 ? B * (H_out / L->Hb) : (B + L->Nb - 1) / L->Nb;
+    const int64_t m_tiles = (L->Nb == 1 ? B * (H_out / L->Hb) : (B + L->Nb - 1) / L->Nb) * (geom.n_par == 4 ? 4 : 1);
     while (bn > 128 && m_tiles * (C_out_pad / bn) < kNumSMs && C_out_pad % (bn / 2) == 0) bn /= 2;
   }
   L->block_n = bn;
@@ -439,6 +446,9 @@ int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, c
   L->tap_cols = geom.tap_cols; L->dy0 = geom.dy0; L->dx0 = geom.dx0;
   L->out_scale = geom.out_scale; L->out_oy = geom.out_oy; L->out_ox = geom.out_ox;
   L->H_full = H_out * geom.out_scale; L->W_full = W_out * geom.out_scale;
+  L->n_par = geom.n_par == 4 ? 4 : 1;
+  DLPM_REQUIRE(L->n_par == 1 || (geom.out_scale == 2 && geom.tap_rows == 2 && geom.tap_cols == 2),
+               "conv: parity batching is for folded upsample convs (2x2 taps, output scale 2)");
   L->cin_blocks = C_in / bk; L->s0_blocks = C_s0 / bk; L->s1_blocks = C_s1 / bk;
   L->B = B; L->C_out = C_out; L->C_out_real = C_out; L->out_mode = out_mode;
   L->bias = bias; L->residual = reinterpret_cast<const __nv_bfloat16*>(residual); L->out = out;
@@ -452,9 +462,10 @@ int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, c
   const int64_t k_total = (int64_t)L->taps * C_in + C_s0 + C_s1;
   // CTA pairs (cta_group::2) when there are enough M tiles to keep all 74 pairs busy
   L->cta_group = (conv_cta_group_override() == 1) ? 1
-                 : ((bn >= 32 && (int64_t)((L->n_m_tiles + 1) / 2) * L->n_n_tiles >= 32) ? 2 : 1);
+                 : ((bn >= 32 && (int64_t)((L->n_m_tiles + 1) / 2) * L->n_n_tiles * L->n_par >= 32) ? 2 : 1);
   if (conv_cta_group_override() == 2 && bn >= 32) L->cta_group = 2;
-  if ((rc = encode_weight_map(&L->tmB, w, C_out_pad, k_total, bn / L->cta_group, bk))) return rc;
+  L->c_out_pad = C_out_pad;
+  if ((rc = encode_weight_map(&L->tmB, w, C_out_pad * L->n_par, k_total, bn / L->cta_group, bk))) return rc;
   return DLPM_OK;
 }
 
@@ -490,10 +501,10 @@ static int launch_t(const ConvLaunch& L, cudaStream_t stream) {
   p.stride = L.stride; p.taps = L.taps; p.cin_blocks = L.cin_blocks; p.s0_blocks = L.s0_blocks; p.s1_blocks = L.s1_blocks;
   p.tap_cols = L.tap_cols; p.dy0 = L.dy0; p.dx0 = L.dx0; p.out_scale = L.out_scale; p.out_oy = L.out_oy; p.out_ox = L.out_ox;
   p.H_full = L.H_full; p.W_full = L.W_full;
-  p.tall = L.tall; p.stage_bytes = STAGE;
+  p.tall = L.tall; p.stage_bytes = STAGE; p.n_par = L.n_par; p.c_out_pad = L.c_out_pad;
   p.B = L.B; p.C_out = L.C_out; p.C_out_real = L.C_out_real; p.out_mode = L.out_mode;
   p.bias = L.bias; p.residual = L.residual; p.out = L.out;
-  const int n_items = ((L.n_m_tiles + CG - 1) / CG) * L.n_n_tiles;
+  const int n_items = ((L.n_m_tiles + CG - 1) / CG) * L.n_n_tiles * L.n_par;
   const int max_groups = kNumSMs / CG;
   const int grid = (n_items < max_groups ? n_items : max_groups) * CG;
   if (CG == 1) {

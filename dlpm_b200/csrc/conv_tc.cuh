@@ -21,6 +21,7 @@ struct ConvLaunch {
   int tap_cols, dy0, dx0;            // tap t reads the input shifted by (dy0 + t / tap_cols, dx0 + t % tap_cols)
   int out_scale, out_oy, out_ox;     // output pixel of tile pixel (h, w): (out_scale*h + out_oy, out_scale*w + out_ox)
   int H_full, W_full;                // spatial size of the output TENSOR (= out_scale * H_out, W_out)
+  int n_par, c_out_pad;              // parity batching (folded upsample): 4 weight matrices stacked along rows
   int cin_blocks, s0_blocks, s1_blocks;
   int64_t B;
   int C_out;       // row stride (channels) of the output / residual tensors
@@ -39,8 +40,10 @@ struct ConvLaunch {
 // upsampled tensor in memory.
 struct ConvGeom {
   int tap_rows, tap_cols, dy0, dx0, out_scale, out_oy, out_ox;
+  int n_par;  // 4: run the four parity convs of a folded upsample in one launch (weights stacked [4][C_out][4*C_in]; parity
+              // (py, px) uses taps (dy0 + py + a, dx0 + px + b) and writes output pixels (2h + py, 2w + px)); else 1
 };
-inline ConvGeom conv_geom_default(int ksize) { return ConvGeom{ksize, ksize, -(ksize / 2), -(ksize / 2), 1, 0, 0}; }
+inline ConvGeom conv_geom_default(int ksize) { return ConvGeom{ksize, ksize, -(ksize / 2), -(ksize / 2), 1, 0, 0, 1}; }
 
 int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, const void* skip0, int C_s0, const void* skip1,
               int C_s1, const void* residual, void* out, int out_mode, int64_t B, int H, int W, int C_in, int C_out, ConvGeom geom,

@@ -48,7 +48,7 @@ static int build_plan(UNetEngine* E, int64_t B, Plan* P) {
     if (op.f[0] != OP_CONV) continue;
     // f: 1 in, 2 out(-1 = external fp32 NCHW), 3 skip0, 4 C_s0, 5 skip1, 6 C_s1, 7 residual, 8 H, 9 W, 10 C_in, 11 C_out, 12 ksize,
     //    13 stride, 14 w_off (bf16 elems), 15 bias_off (fp32 elems), 16 tap_rows, 17 tap_cols, 18 dy0, 19 dx0, 20 out_scale, 21 out_oy,
-    //    22 out_ox
+    //    22 out_ox, 23 n_par
     ConvLaunch L;
     const void* s0 = op.f[3] >= 0 ? E->buf(op.f[3], B) : nullptr;
     const void* s1 = op.f[5] >= 0 ? E->buf(op.f[5], B) : nullptr;
@@ -57,7 +57,8 @@ static int build_plan(UNetEngine* E, int64_t B, Plan* P) {
     void* out = ext ? reinterpret_cast<void*>(0x10) /*patched at launch*/ : E->buf(op.f[2], B);
     int rc = conv_plan(&L, E->buf(op.f[1], B), E->wb + op.f[14], E->wf + op.f[15], s0, (int)op.f[4], s1, (int)op.f[6], res, out,
                        ext ? CONV_OUT_F32_NCHW : CONV_OUT_BF16_NHWC, B, (int)op.f[8], (int)op.f[9], (int)op.f[10], (int)op.f[11],
-                       ConvGeom{(int)op.f[16], (int)op.f[17], (int)op.f[18], (int)op.f[19], (int)op.f[20], (int)op.f[21], (int)op.f[22]},
+                       ConvGeom{(int)op.f[16], (int)op.f[17], (int)op.f[18], (int)op.f[19], (int)op.f[20], (int)op.f[21], (int)op.f[22],
+                                (int)op.f[23]},
                        (int)op.f[13]);
     if (rc) return rc;
     P->convs.push_back(L);
@@ -198,7 +199,7 @@ int dlpm_b200_unet_profile(void* handle, const float* x, const float* t, int t_r
       double fl = 0.0;
       if (f[0] == OP_CONV) {  // 2 * M * N * K with M = B * H_out * W_out
         const double M = (double)B * (f[8] / f[13]) * (f[9] / f[13]);
-        fl = 2.0 * M * (double)f[11] * ((double)f[16] * f[17] * f[10] + f[4] + f[6]);
+        fl = 2.0 * M * (double)f[11] * ((double)f[16] * f[17] * f[10] + f[4] + f[6]) * (f[23] == 4 ? 4.0 : 1.0);
       }
       flops_per_op[1 + i] = fl;
     }

@@ -336,7 +336,9 @@ class UNetModel(nn.Module):
             wk = w.detach().float()
             wk = wk.permute(0, 2, 3, 1).reshape(C_out, -1) if wk.dim() == 4 else wk.reshape(C_out, -1)
             if geom is None:
-                geom = (ksize, ksize, -(ksize // 2), -(ksize // 2), 1, 0, 0)
+                geom = (ksize, ksize, -(ksize // 2), -(ksize // 2), 1, 0, 0, 1)
+            n_par = geom[7]
+            C_out //= n_par  # parity-stacked weights: rows = n_par * C_out
             bias = b.detach().float()
             if skips:
                 wk = torch.cat([wk, skip_w.detach().float().reshape(C_out, -1)], dim=1)
@@ -415,11 +417,14 @@ class UNetModel(nn.Module):
                     names["%s.%d" % (tag, j)] = h2
                     w3 = layer.conv.weight.detach().float()  # [C_out, C_in, 3, 3]
                     rows = {0: ((0,), (1, 2)), 1: ((0, 1), (2,))}  # parity -> 3x3 taps merged into 2x2 tap a = 0, 1
+                    stacked = []
                     for py in (0, 1):
                         for px in (0, 1):
-                            w2 = torch.stack([torch.stack([w3[:, :, list(rows[py][a])][:, :, :, list(rows[px][bb])].sum(dim=(2, 3))
-                                                           for bb in (0, 1)], dim=-1) for a in (0, 1)], dim=-2)  # [C_out, C_in, 2, 2]
-                            conv(h, C, H_, W_, w2, layer.conv.bias, h2, ksize=2, geom=(2, 2, py - 1, px - 1, 2, py, px))
+                            stacked.append(torch.stack(
+                                [torch.stack([w3[:, :, list(rows[py][a])][:, :, :, list(rows[px][bb])].sum(dim=(2, 3))
+                                              for bb in (0, 1)], dim=-1) for a in (0, 1)], dim=-2))  # [C_out, C_in, 2, 2]
+                    # ONE launch for the four parities: weights stacked along rows [4*C_out, C_in, 2, 2], parity p = 2*py + px
+                    conv(h, C, H_, W_, torch.cat(stacked, dim=0), layer.conv.bias, h2, ksize=2, geom=(2, 2, -1, -1, 2, 0, 0, 4))
                     H_, W_ = 2 * H_, 2 * W_
                     h = h2
                 else:

@@ -53,36 +53,41 @@ def interpret(prog, x, t, mc, emulate_bf16=False):
             bufs[o] = q(y.permute(0, 2, 3, 1))
         elif code == OP_CONV:
             _, i, o, s0, C0, s1, C1, res, H, W, cin, cout, k, stride, woff, boff = f[:16]
-            tr, tc_, dy0, dx0, oscale, oy, ox = f[16:23]
+            tr, tc_, dy0b, dx0b, oscale, oyb, oxb, n_par = f[16:24]
+            n_par = 4 if n_par == 4 else 1
             rows = 16 if o < 0 else cout
             ntap = tr * tc_
             K = ntap * cin + C0 + C1
-            wk = wb[woff:woff + rows * K].reshape(rows, K)[:cout]
+            wall = wb[woff:woff + n_par * rows * K].reshape(n_par, rows, K)
             bias = wf[boff:boff + cout]
             xin = bufs[i].permute(0, 3, 1, 2)
             Ho, Wo = H // stride, W // stride
-            y = torch.zeros(B, cout, Ho, Wo)
             xp = F.pad(xin, (2, 2, 2, 2))
-            for tI in range(ntap):
-                dy, dx = dy0 + tI // tc_, dx0 + tI % tc_
-                sl = xp[:, :, 2 + dy:2 + dy + H:stride, 2 + dx:2 + dx + W:stride]
-                y = y + torch.einsum("bchw,oc->bohw", sl, wk[:, tI * cin:(tI + 1) * cin])
-            col = ntap * cin
-            for sid, Cs in ((s0, C0), (s1, C1)):
-                if sid >= 0:
-                    y = y + F.conv2d(bufs[sid].permute(0, 3, 1, 2), wk[:, col:col + Cs].reshape(cout, Cs, 1, 1))
-                    col += Cs
-            y = y + bias[None, :, None, None]
-            if res >= 0:
-                y = y + bufs[res].permute(0, 3, 1, 2)
-            if o < 0:
-                out = y
-            elif oscale == 1:
-                bufs[o] = q(y.permute(0, 2, 3, 1))
-            else:
-                if o not in bufs or bufs[o].shape[1] != Ho * oscale:
-                    bufs[o] = torch.zeros(B, Ho * oscale, Wo * oscale, cout)
-                bufs[o][:, oy::oscale, ox::oscale, :] = q(y.permute(0, 2, 3, 1))
+            for par in range(n_par):
+                wk = wall[par][:cout]
+                dy0, dx0 = (dy0b + (par >> 1), dx0b + (par & 1)) if n_par == 4 else (dy0b, dx0b)
+                oy, ox = ((par >> 1), (par & 1)) if n_par == 4 else (oyb, oxb)
+                y = torch.zeros(B, cout, Ho, Wo)
+                for tI in range(ntap):
+                    dy, dx = dy0 + tI // tc_, dx0 + tI % tc_
+                    sl = xp[:, :, 2 + dy:2 + dy + H:stride, 2 + dx:2 + dx + W:stride]
+                    y = y + torch.einsum("bchw,oc->bohw", sl, wk[:, tI * cin:(tI + 1) * cin])
+                col = ntap * cin
+                for sid, Cs in ((s0, C0), (s1, C1)):
+                    if sid >= 0:
+                        y = y + F.conv2d(bufs[sid].permute(0, 3, 1, 2), wk[:, col:col + Cs].reshape(cout, Cs, 1, 1))
+                        col += Cs
+                y = y + bias[None, :, None, None]
+                if res >= 0:
+                    y = y + bufs[res].permute(0, 3, 1, 2)
+                if o < 0:
+                    out = y
+                elif oscale == 1:
+                    bufs[o] = q(y.permute(0, 2, 3, 1))
+                else:
+                    if o not in bufs or bufs[o].shape[1] != Ho * oscale or bufs[o].shape[3] != cout:
+                        bufs[o] = torch.zeros(B, Ho * oscale, Wo * oscale, cout)
+                    bufs[o][:, oy::oscale, ox::oscale, :] = q(y.permute(0, 2, 3, 1))
         elif code == OP_UP:
             _, i, o, H, W, C = f[:6]
             bufs[o] = F.interpolate(bufs[i].permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1)
