@@ -40,6 +40,45 @@ inline int grid_for(int64_t work_items, int threads, int max_waves = 8) {
   return (int)blocks;
 }
 
+// Programmatic dependent launch (PDL): every kernel of the per-step chain is launched with the programmatic-stream-
+// serialization attribute; it lets its successor start launching right away (pdl_launch_dependents) and blocks
+// (pdl_wait) until its predecessor has fully completed before it touches global memory.  The successor's launch
+// latency and prologue (barrier init, TMEM allocation, descriptor prefetch, weight staging) overlap the predecessor's
+// tail.  Both instructions are no-ops for kernels launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();
+void pdl_set_enabled(bool on);
+
+// cudaLaunchKernelEx wrapper: optional thread-block cluster (x dimension) and the PDL attribute.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x,
+                             Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  int n = 0;
+  if (cluster_x > 1) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = (unsigned)cluster_x;
+    at[n].val.clusterDim.y = 1;
+    at[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // Division by a launch-constant via multiply-high (valid for 0 <= n < 2^31): the streaming kernels index
 // (sample, position) from a flat quad index; a 64-bit hardware-emulated divide there costs more than the memory traffic.
 struct FastDiv {

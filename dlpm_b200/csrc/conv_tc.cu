@@ -106,6 +106,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: the prologue above overlapped the previous kernel's tail; its outputs may only be touched from here on
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer (every CTA loads its own A rows and its share of B) =====================
@@ -508,22 +511,10 @@ static int launch_t(const ConvLaunch& L, cudaStream_t stream) {
   const int max_groups = kNumSMs / CG;
   const int grid = (n_items < max_groups ? n_items : max_groups) * CG;
   if (CG == 1) {
-    k_conv_tc<BN, BK, 1, KS><<<grid, kConvThreads, smem, stream>>>(L.tmA, L.tmS0, L.tmS1, L.tmB, p);
-    DLPM_CHECK_LAUNCH("conv_tc");
+    cudaError_t e = launch_ex(k_conv_tc<BN, BK, 1, KS>, dim3(grid), dim3(kConvThreads), smem, stream, 1, L.tmA, L.tmS0, L.tmS1, L.tmB, p);
+    if (e != cudaSuccess) return cuda_fail(e, "conv_tc launch");
   } else {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(kConvThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, k_conv_tc<BN, BK, CG, KS>, L.tmA, L.tmS0, L.tmS1, L.tmB, p);
+    cudaError_t e = launch_ex(k_conv_tc<BN, BK, CG, KS>, dim3(grid), dim3(kConvThreads), smem, stream, 2, L.tmA, L.tmS0, L.tmS1, L.tmB, p);
     if (e != cudaSuccess) return cuda_fail(e, "conv_tc pair launch");
   }
   return DLPM_OK;
@@ -550,6 +541,10 @@ using namespace dlpm;
 
 int dlpm_b200_set_option(const char* name, int value) {
   DLPM_REQUIRE(name != nullptr, "set_option: NULL name");
+  if (std::string(name) == "pdl") {
+    pdl_set_enabled(value != 0);
+    return DLPM_OK;
+  }
   if (std::string(name) == "conv_tall") {
     g_tall_enabled = value != 0;
     return DLPM_OK;

@@ -11,6 +11,7 @@
 // Arithmetic uses explicit round-to-nearest intrinsics in the reference's evaluation order (no FMA
 // contraction), so with injected noise the results are bit-identical to the reference's fp32 CPU path.
 #include <cstdarg>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "rng.cuh"
@@ -24,6 +25,16 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+static int g_pdl = -1;  // -1: not initialised -> DLPM_B200_PDL environment variable (default on)
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("DLPM_B200_PDL");
+    g_pdl = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl != 0;
+}
+void pdl_set_enabled(bool on) { g_pdl = on ? 1 : 0; }
 
 static StableParams make_params(float alpha) {
   StableParams p;
@@ -275,6 +286,8 @@ __global__ void __launch_bounds__(256) k_reverse_step(float* __restrict__ x, con
                                                       int64_t D, int flags, const float* __restrict__ z,
                                                       uint64_t seed, uint64_t offset, int64_t sample_base,
                                                       float* __restrict__ hist, FastDiv fd) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int t = t_dev ? *t_dev : t_imm;
   if (t < 1 || t >= T) return;
   const Philox ph(seed);
@@ -441,7 +454,11 @@ __global__ void __launch_bounds__(256) k_lim_step(float* __restrict__ x, const v
   }
 }
 
-__global__ void k_advance(int* t, int delta) { *t += delta; }
+__global__ void k_advance(int* t, int delta) {
+  pdl_launch_dependents();
+  pdl_wait();
+  *t += delta;
+}
 
 // ------------------------------------------------------------------------------------------------
 // training forward elements (dlpm.py:384-401)
@@ -616,7 +633,7 @@ static int launch_step(float* x, const void* eps, const float* Sigma, const floa
   const int grid = grid_for(vec ? B * D / 4 : B * D, 256);
   cudaStream_t s = (cudaStream_t)stream;
   const FastDiv fd((uint32_t)(vec ? D / 4 : 1));
-#define L(V, H) k_reverse_step<V, H, MODE><<<grid, 256, 0, s>>>(x, eps, Sigma, sched, t, t_dev, T, B, D, flags, z, seed, offset, sample_base, hist, fd)
+#define L(V, H) launch_ex(k_reverse_step<V, H, MODE>, dim3(grid), dim3(256), 0, s, 1, x, eps, Sigma, sched, t, t_dev, T, B, D, flags, z, seed, offset, sample_base, hist, fd)
   if (vec) { if (bf16) L(true, true); else L(true, false); }
   else { if (bf16) L(false, true); else L(false, false); }
 #undef L
@@ -669,7 +686,7 @@ int dlpm_b200_lim_step(float* x, const void* model_out, const float* coef, int s
 
 int dlpm_b200_advance_counter(int* t_dev, int delta, void* stream) {
   DLPM_REQUIRE(t_dev, "advance_counter: NULL");
-  k_advance<<<1, 1, 0, (cudaStream_t)stream>>>(t_dev, delta);
+  launch_ex(k_advance, dim3(1), dim3(1), 0, (cudaStream_t)stream, 1, t_dev, delta);
   DLPM_CHECK_LAUNCH("advance_counter");
   return DLPM_OK;
 }

@@ -40,6 +40,8 @@ __global__ void __launch_bounds__(kGnThreads) k_groupnorm(__nv_bfloat16* __restr
                                                           const float* __restrict__ ss, int ss_rows, int64_t ss_stride,
                                                           int64_t ss_off, int apply_silu) {
   extern __shared__ float sm[];
+  pdl_launch_dependents();
+  pdl_wait();
   const int C = C0 + C1, nvec = C >> 3;
   const int slots = kGnThreads / nvec;
   const int n = blockIdx.x;
@@ -145,6 +147,8 @@ __global__ void __launch_bounds__(kGnThreads) k_groupnorm_cluster(__nv_bfloat16*
   uint64_t* bar = reinterpret_cast<uint64_t*>(part + 2048);
   const int p0 = rank * pix_per_cta;
   // phase 1: global -> shared with bulk asynchronous copies (the only read of the tensor)
+  pdl_launch_dependents();
+  pdl_wait();
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(gn_smem_u32(bar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -256,6 +260,8 @@ template <int D>
 __global__ void __launch_bounds__(256) k_attention(__nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ qkv, int L,
                                                    int C, int heads) {
   extern __shared__ float sm[];
+  pdl_launch_dependents();
+  pdl_wait();
   float* Ks = sm;            // [L][D]
   float* Vs = sm + L * D;    // [L][D]
   const int n = blockIdx.x / heads, h = blockIdx.x % heads;
@@ -311,6 +317,8 @@ __global__ void __launch_bounds__(256) k_conv_in(__nv_bfloat16* __restrict__ out
   for (int i = threadIdx.x; i < K * C_out / 4; i += blockDim.x)
     reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(wT) + i);
   for (int i = threadIdx.x; i < C_out; i += blockDim.x) s_b[i] = __ldg(bias + i);
+  pdl_launch_dependents();
+  pdl_wait();  // weights are constants (staged above, overlapping the previous kernel); x is produced upstream
   const int Wp = W + 2, R = kConvInRows + 2;
   for (int i = threadIdx.x; i < C_in * R * Wp; i += blockDim.x) {
     const int ci = i / (R * Wp), r = (i / Wp) % R, xx = i % Wp - 1;
@@ -375,6 +383,8 @@ __global__ void __launch_bounds__(256) k_conv_in(__nv_bfloat16* __restrict__ out
 
 __global__ void __launch_bounds__(256) k_upsample2x(uint4* __restrict__ out, const uint4* __restrict__ in, int64_t B, int H, int W,
                                                     int C8) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t total = B * (2 * H) * (2 * W) * C8;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(idx % C8);
@@ -398,6 +408,8 @@ __global__ void __launch_bounds__(256) k_gemv_rows(float* __restrict__ out, cons
   float* s_in = sm;
   float* s_part = sm + K;
   const int r = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  pdl_launch_dependents();
+  pdl_wait();
   if (sinus) {
     const float tv = t_dev ? (float)(*t_dev) * inv_T : t[r];
     const int half = K / 2;
@@ -472,20 +484,8 @@ int dlpm_b200_groupnorm_silu(void* out, const void* in0, int C0, const void* in1
       if (e != cudaSuccess) return cuda_fail(e, "groupnorm smem attribute");
       attr = true;
     }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(B * cs));
-    cfg.blockDim = dim3((unsigned)threads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = (unsigned)cs;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, k_groupnorm_cluster, o, i0, C0, i1, C1, HW, gamma, beta, ss, ss_rows, ss_stride, ss_off,
-                                       apply_silu, pix);
+    cudaError_t e = launch_ex(k_groupnorm_cluster, dim3((unsigned)(B * cs)), dim3((unsigned)threads), smem, (cudaStream_t)stream, cs, o, i0,
+                              C0, i1, C1, HW, gamma, beta, ss, ss_rows, ss_stride, ss_off, apply_silu, pix);
     if (e != cudaSuccess) return cuda_fail(e, "groupnorm cluster launch");
     return DLPM_OK;
   }
@@ -498,9 +498,9 @@ int dlpm_b200_groupnorm_silu(void* out, const void* in0, int C0, const void* in1
     if (e != cudaSuccess) return cuda_fail(e, "groupnorm smem attribute");
     attr2 = true;
   }
-  k_groupnorm<<<(unsigned)B, kGnThreads, smem, (cudaStream_t)stream>>>(o, i0, C0, i1, C1, HW, gamma, beta, ss, ss_rows, ss_stride, ss_off,
-                                                                      apply_silu);
-  DLPM_CHECK_LAUNCH("groupnorm");
+  cudaError_t e2 = launch_ex(k_groupnorm, dim3((unsigned)B), dim3(kGnThreads), smem, (cudaStream_t)stream, 1, o, i0, C0, i1, C1, HW, gamma,
+                             beta, ss, ss_rows, ss_stride, ss_off, apply_silu);
+  if (e2 != cudaSuccess) return cuda_fail(e2, "groupnorm launch");
   return DLPM_OK;
 }
 
@@ -521,7 +521,8 @@ int dlpm_b200_attention(void* out, const void* qkv, int64_t B, int L, int C, int
   case DD: {                                                                                               \
     cudaError_t e = cudaFuncSetAttribute(k_attention<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) return cuda_fail(e, "attention smem attribute");                                 \
-    k_attention<DD><<<grid, threads, smem, s>>>(o, q, L, C, heads);                                        \
+    cudaError_t e2 = launch_ex(k_attention<DD>, dim3(grid), dim3(threads), smem, s, 1, o, q, L, C, heads);  \
+    if (e2 != cudaSuccess) return cuda_fail(e2, "attention launch");                                       \
   } break
   switch (D) {
     ATT(8); ATT(16); ATT(32); ATT(64);
@@ -547,9 +548,9 @@ int dlpm_b200_conv_in(void* out, const float* x, const float* wT, const float* b
     attr = true;
   }
   DLPM_REQUIRE(smem <= 96 * 1024, "conv_in: weights do not fit in shared memory");
-  k_conv_in<<<(unsigned)(B * bands), 256, smem, (cudaStream_t)stream>>>(reinterpret_cast<__nv_bfloat16*>(out), x, wT, bias, C_in, C_out,
-                                                                      H, W);
-  DLPM_CHECK_LAUNCH("conv_in");
+  cudaError_t e2 = launch_ex(k_conv_in, dim3((unsigned)(B * bands)), dim3(256), smem, (cudaStream_t)stream, 1,
+                             reinterpret_cast<__nv_bfloat16*>(out), x, wT, bias, C_in, C_out, H, W);
+  if (e2 != cudaSuccess) return cuda_fail(e2, "conv_in launch");
   return DLPM_OK;
 }
 
@@ -573,13 +574,16 @@ int dlpm_b200_time_embedding(float* ss, float* semb, const float* t, const int* 
   float* h1 = ss;  // hidden layer [rows][E] parked in the ss buffer, which the third launch rewrites completely
   DLPM_REQUIRE(ss_total >= E, "time_embedding: ss_total must be >= 4*mc");
   dim3 g1((unsigned)((E + 31) / 32), (unsigned)rows);
-  k_gemv_rows<<<g1, 256, (size_t)(mc + 256) * sizeof(float), s>>>(h1, nullptr, t, t_dev, inv_T, 1, mc, E, w0T, b0, 1);
-  DLPM_CHECK_LAUNCH("time_embed layer 1");
+  cudaError_t e = launch_ex(k_gemv_rows, g1, dim3(256), (size_t)(mc + 256) * sizeof(float), s, 1, h1, (const float*)nullptr, t, t_dev, inv_T,
+                            1, mc, (int64_t)E, w0T, b0, 1);
+  if (e != cudaSuccess) return cuda_fail(e, "time_embed layer 1");
   // every emb_layers starts with SiLU (unet.py:145-146): semb = SiLU(time_embed(.))
-  k_gemv_rows<<<g1, 256, (size_t)(E + 256) * sizeof(float), s>>>(semb, h1, nullptr, nullptr, 0.f, 0, E, E, w2T, b2, 1);
-  DLPM_CHECK_LAUNCH("time_embed layer 2");
+  e = launch_ex(k_gemv_rows, g1, dim3(256), (size_t)(E + 256) * sizeof(float), s, 1, semb, (const float*)h1, (const float*)nullptr,
+                (const int*)nullptr, 0.f, 0, E, (int64_t)E, w2T, b2, 1);
+  if (e != cudaSuccess) return cuda_fail(e, "time_embed layer 2");
   dim3 g3((unsigned)((ss_total + 31) / 32), (unsigned)rows);
-  k_gemv_rows<<<g3, 256, (size_t)(E + 256) * sizeof(float), s>>>(ss, semb, nullptr, nullptr, 0.f, 0, E, ss_total, wallT, ball, 0);
-  DLPM_CHECK_LAUNCH("emb_layers");
+  e = launch_ex(k_gemv_rows, g3, dim3(256), (size_t)(E + 256) * sizeof(float), s, 1, ss, (const float*)semb, (const float*)nullptr,
+                (const int*)nullptr, 0.f, 0, E, ss_total, wallT, ball, 0);
+  if (e != cudaSuccess) return cuda_fail(e, "emb_layers");
   return DLPM_OK;
 }
