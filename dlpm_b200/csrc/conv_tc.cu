@@ -36,6 +36,8 @@ struct ConvKParams {
   int Wb, Hb, Nb, H_out, W_out, tiles_per_img;
   int stride, taps, cin_blocks, s0_blocks, s1_blocks;
   int tap_cols, dy0, dx0, out_scale, out_oy, out_ox, H_full, W_full;
+  int msub;               // 2: a CTA owns two vertically adjacent 128-pixel sub-tiles fed by ONE (2*Hb+2)-row box and the same
+                          //    weight tiles (tall mode only): weight traffic per pixel halves, halo overhead 1.5x -> 1.25x
   int n_par, c_out_pad;   // n_par = 4: the four output-parity 2x2 convs of a folded upsample+conv3x3 share one launch
   int tall, stage_bytes;  // tall: one (Hb+2)-row activation box per (channel block, dx) serves the three dy taps
   int64_t B;
@@ -65,7 +67,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   // read the same box at row offsets 0, Wb, 2*Wb and the activation traffic from L2 drops from 9 to 3*(Hb+2)/Hb tiles.
   const int STAGE_BYTES = p.stage_bytes;
   constexpr int SWZ = BLOCK_K * 2;  // bytes per operand row = swizzle span (128 or 64)
-  constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
+  constexpr int MS_MAX = BLOCK_N <= 128 ? 2 : 1;  // sub-tiles per CTA the accumulator space allows (2 stages x MS_MAX x N <= 512)
+  constexpr int ACC_COLS = 2 * MS_MAX * BLOCK_N;
+  constexpr uint32_t TMEM_COLS = ACC_COLS <= 32 ? 32 : (ACC_COLS <= 64 ? 64 : (ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512)));
   constexpr uint32_t IDESC = make_idesc_bf16(128 * CG, BLOCK_N);
 
   extern __shared__ uint8_t smem_raw[];
@@ -81,7 +85,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const bool leader = cta_rank == 0;
   const int main_blocks = p.taps * p.cin_blocks;
   const int nkb = main_blocks + p.s0_blocks + p.s1_blocks;
-  const int m_groups = (p.n_m_tiles + CG - 1) / CG;   // a work item = CG adjacent M tiles x one N tile
+  const int msub = p.msub;
+  const int m_units = p.n_m_tiles / msub;             // a unit = msub vertically adjacent 128-pixel tiles of one image
+  const int m_groups = (m_units + CG - 1) / CG;        // a work item = CG adjacent units x one N tile
   const int items_per_par = m_groups * p.n_n_tiles;
   const int n_items = items_per_par * p.n_par;
   const int first_item = blockIdx.x / CG, item_stride = gridDim.x / CG;
@@ -116,21 +122,21 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       int stage = 0; uint32_t phase = 0;
       for (int item = first_item; item < n_items; item += item_stride) {
         const int par = item / items_per_par, it_in = item - par * items_per_par;
-        const int nt = it_in % p.n_n_tiles, mt = (it_in / p.n_n_tiles) * CG + (int)cta_rank;
+        const int nt = it_in % p.n_n_tiles, mt = ((it_in / p.n_n_tiles) * CG + (int)cta_rank) * msub;
         const int dy_base = p.dy0 + (p.n_par == 4 ? (par >> 1) : 0), dx_base = p.dx0 + (p.n_par == 4 ? (par & 1) : 0);
         const int brow0 = par * p.c_out_pad + nt * BLOCK_N + (int)cta_rank * B_ROWS;
         int n0, h0;
         if (p.Nb == 1) { n0 = mt / p.tiles_per_img; h0 = (mt - n0 * p.tiles_per_img) * p.Hb; }
         else { n0 = mt * p.Nb; h0 = 0; }
         if (p.tall) {
-          const int a_tall_bytes = (p.Hb + 2) * p.Wb * BLOCK_K * 2;
+          const int a_tall_bytes = (msub * p.Hb + 2) * p.Wb * BLOCK_K * 2;
           const int n_sb = 3 * p.cin_blocks + p.s0_blocks + p.s1_blocks;
           for (int sb = 0; sb < n_sb; ++sb) {
             mbar_wait(empty_bar + stage, phase ^ 1);
             uint8_t* a_dst = smem + stage * STAGE_BYTES;
             uint8_t* b_dst = a_dst + a_tall_bytes;
             const bool main_part = sb < 3 * p.cin_blocks;
-            const int bytes = main_part ? a_tall_bytes + 3 * B_BYTES : SUB_BYTES;
+            const int bytes = main_part ? a_tall_bytes + 3 * B_BYTES : msub * A_BYTES + B_BYTES;
             uint32_t lead_full = 0;
             if (CG == 2) {
               lead_full = mapa_u32(smem_u32(full_bar + stage), 0);
@@ -216,24 +222,29 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(tempty_bar + acc, acc_phase ^ 1);  // epilogues (of both CTAs) have drained this accumulator stage
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * msub * BLOCK_N);
         if (p.tall) {
-          const int a_tall_bytes = (p.Hb + 2) * p.Wb * BLOCK_K * 2;
+          const int a_tall_bytes = (msub * p.Hb + 2) * p.Wb * BLOCK_K * 2;
           const int n_sb = 3 * p.cin_blocks + p.s0_blocks + p.s1_blocks;
           for (int sb = 0; sb < n_sb; ++sb) {
             mbar_wait(full_bar + stage, phase);
             tc_fence_after();
             const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
             const uint32_t b_addr = a_addr + a_tall_bytes;
-            const int n_j = sb < 3 * p.cin_blocks ? 3 : 1;
+            const bool main_part = sb < 3 * p.cin_blocks;
+            const int n_j = main_part ? 3 : 1;
             for (int j = 0; j < n_j; ++j) {
-              const uint32_t a_j = a_addr + (uint32_t)(j * p.Wb * BLOCK_K * 2);  // dy = j - 1: shift by Wb rows (whole swizzle atoms)
+              for (int sub = 0; sub < msub; ++sub) {
+                // dy = j - 1: shift by Wb rows (whole swizzle atoms); sub-tile `sub` starts Hb image rows further down
+                const uint32_t a_j = main_part ? a_addr + (uint32_t)((sub * p.Hb + j) * p.Wb * BLOCK_K * 2) : a_addr + (uint32_t)(sub * A_BYTES);
+                const uint32_t d_sub = d_tmem + (uint32_t)(sub * BLOCK_N);
 #pragma unroll
-              for (int k = 0; k < BLOCK_K / 16; ++k) {
-                const uint64_t da = make_smem_desc<SWZ>(a_j + k * 32);
-                const uint64_t db = make_smem_desc<SWZ>(b_addr + j * B_BYTES + k * 32);
-                if (CG == 2) umma_bf16_pair(d_tmem, da, db, IDESC, (sb | j | k) != 0);
-                else umma_bf16(d_tmem, da, db, IDESC, (sb | j | k) != 0);
+                for (int k = 0; k < BLOCK_K / 16; ++k) {
+                  const uint64_t da = make_smem_desc<SWZ>(a_j + k * 32);
+                  const uint64_t db = make_smem_desc<SWZ>(b_addr + j * B_BYTES + k * 32);
+                  if (CG == 2) umma_bf16_pair(d_sub, da, db, IDESC, (sb | j | k) != 0);
+                  else umma_bf16(d_sub, da, db, IDESC, (sb | j | k) != 0);
+                }
               }
             }
             if (CG == 2) umma_commit_pair(empty_bar + stage); else umma_commit(empty_bar + stage);
@@ -273,7 +284,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     int it = 0;
     for (int item = first_item; item < n_items; item += item_stride, ++it) {
       const int par = item / items_per_par, it_in = item - par * items_per_par;
-      const int nt = it_in % p.n_n_tiles, mt = (it_in / p.n_n_tiles) * CG + (int)cta_rank;
+      const int nt = it_in % p.n_n_tiles, mt = ((it_in / p.n_n_tiles) * CG + (int)cta_rank) * msub;
       const int out_oy = p.n_par == 4 ? (par >> 1) : p.out_oy, out_ox = p.n_par == 4 ? (par & 1) : p.out_ox;
       int n0, h0;
       if (p.Nb == 1) { n0 = mt / p.tiles_per_img; h0 = (mt - n0 * p.tiles_per_img) * p.Hb; }
@@ -282,46 +293,58 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const uint32_t acc_phase = (it >> 1) & 1;
       const int64_t nn = (int64_t)n0 + n_in;
       const bool valid = nn < p.B;
-      const int64_t pix = (nn * p.H_full + p.out_scale * (h0 + h_in) + out_oy) * p.W_full + p.out_scale * w_in + out_ox;
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+      const uint32_t t_row0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * msub * BLOCK_N);
       if (p.out_mode == CONV_OUT_BF16_NHWC) {
         constexpr int CH = BLOCK_N >= 32 ? 32 : 16;
         // identity-skip rows are fetched BEFORE waiting for the accumulator so their HBM latency hides behind the MMAs
-        uint4 resv[BLOCK_N / 8];
+        uint4 resv[MS_MAX][BLOCK_N / 8];
         const bool has_res = p.residual != nullptr && valid;
         if (has_res) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.C_out + nt * BLOCK_N);
 #pragma unroll
-          for (int j = 0; j < BLOCK_N / 8; ++j) resv[j] = __ldg(rp + j);
+          for (int sub = 0; sub < MS_MAX; ++sub) {
+            if (sub < msub) {
+              const int64_t pix = (nn * p.H_full + p.out_scale * (h0 + sub * p.Hb + h_in) + out_oy) * p.W_full + p.out_scale * w_in + out_ox;
+              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.C_out + nt * BLOCK_N);
+#pragma unroll
+              for (int j = 0; j < BLOCK_N / 8; ++j) resv[sub][j] = __ldg(rp + j);
+            }
+          }
         }
         mbar_wait(tfull_bar + acc, acc_phase);
         tc_fence_after();
 #pragma unroll
-        for (int c0 = 0; c0 < BLOCK_N; c0 += CH) {
-          uint32_t r[CH];
-          if constexpr (CH == 32) tmem_ld_x32(t_row + c0, r);
-          else tmem_ld_x16(t_row + c0, r);
-          tmem_ld_wait();
-          if (valid) {
-            const int col = nt * BLOCK_N + c0;
-            const float* bias = p.bias + col;
-            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.C_out + col;
+        for (int sub = 0; sub < MS_MAX; ++sub) {
+          if (sub < msub) {
+            const int64_t pix = (nn * p.H_full + p.out_scale * (h0 + sub * p.Hb + h_in) + out_oy) * p.W_full + p.out_scale * w_in + out_ox;
+            const uint32_t t_row = t_row0 + (uint32_t)(sub * BLOCK_N);
 #pragma unroll
-            for (int j = 0; j < CH; j += 8) {
-              float v[8];
+            for (int c0 = 0; c0 < BLOCK_N; c0 += CH) {
+              uint32_t r[CH];
+              if constexpr (CH == 32) tmem_ld_x32(t_row + c0, r);
+              else tmem_ld_x16(t_row + c0, r);
+              tmem_ld_wait();
+              if (valid) {
+                const int col = nt * BLOCK_N + c0;
+                const float* bias = p.bias + col;
+                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.C_out + col;
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[j + e]) + __ldg(bias + j + e);
-              if (has_res) {
-                const uint4 rv = resv[(c0 + j) / 8];
-                const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rv);
+                for (int j = 0; j < CH; j += 8) {
+                  float v[8];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(rp[e]); v[2 * e] += f.x; v[2 * e + 1] += f.y; }
+                  for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[j + e]) + __ldg(bias + j + e);
+                  if (has_res) {
+                    const uint4 rv = resv[sub][(c0 + j) / 8];
+                    const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(rp[e]); v[2 * e] += f.x; v[2 * e + 1] += f.y; }
+                  }
+                  uint4 o;
+                  __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) op[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+                  *reinterpret_cast<uint4*>(dst + j) = o;
+                }
               }
-              uint4 o;
-              __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) op[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-              *reinterpret_cast<uint4*>(dst + j) = o;
             }
           }
         }
@@ -329,16 +352,21 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         // fp32 NCHW, first C_out_real channels of the (zero-padded) tile: the network's final conv (unet.py:435)
         mbar_wait(tfull_bar + acc, acc_phase);
         tc_fence_after();
-        uint32_t r[16];
-        tmem_ld_x16(t_row, r);
-        tmem_ld_wait();
-        if (valid) {
-          float* dst = reinterpret_cast<float*>(p.out);
-          const int64_t hw = (int64_t)p.H_full * p.W_full;
-          const int64_t sp = (int64_t)(p.out_scale * (h0 + h_in) + out_oy) * p.W_full + p.out_scale * w_in + out_ox;
 #pragma unroll
-          for (int c = 0; c < 16; ++c)
-            if (c < p.C_out_real) dst[(nn * p.C_out_real + c) * hw + sp] = __uint_as_float(r[c]) + __ldg(p.bias + c);
+        for (int sub = 0; sub < MS_MAX; ++sub) {
+          if (sub < msub) {
+            uint32_t r[16];
+            tmem_ld_x16(t_row0 + (uint32_t)(sub * BLOCK_N), r);
+            tmem_ld_wait();
+            if (valid) {
+              float* dst = reinterpret_cast<float*>(p.out);
+              const int64_t hw = (int64_t)p.H_full * p.W_full;
+              const int64_t sp = (int64_t)(p.out_scale * (h0 + sub * p.Hb + h_in) + out_oy) * p.W_full + p.out_scale * w_in + out_ox;
+#pragma unroll
+              for (int c = 0; c < 16; ++c)
+                if (c < p.C_out_real) dst[(nn * p.C_out_real + c) * hw + sp] = __uint_as_float(r[c]) + __ldg(p.bias + c);
+            }
+          }
         }
       }
       tc_fence_before();
@@ -457,15 +485,17 @@ int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, c
   L->bias = bias; L->residual = reinterpret_cast<const __nv_bfloat16*>(residual); L->out = out;
   L->tall = (L->Nb == 1 && geom.tap_rows == 3 && geom.tap_cols == 3 && geom.dy0 == -1 && geom.dx0 == -1 && stride == 1 &&
              geom.out_scale == 1 && bn <= 128 && L->Wb % 8 == 0 && conv_tall_enabled()) ? 1 : 0;
+  // two vertically adjacent sub-tiles per CTA when the image has an even number of tiles and TMEM has room (N <= 128)
+  L->msub = (L->tall && L->tiles_per_img % 2 == 0 && bn <= 128 && conv_msub_enabled()) ? 2 : 1;
   int rc;
-  if ((rc = encode_act_map(&L->tmA, in, B, H, W, C_in, bk, L->Wb, L->tall ? L->Hb + 2 : L->Hb, L->Nb, stride))) return rc;
+  if ((rc = encode_act_map(&L->tmA, in, B, H, W, C_in, bk, L->Wb, L->tall ? L->msub * L->Hb + 2 : L->Hb, L->Nb, stride))) return rc;
   L->tmS0 = L->tmA; L->tmS1 = L->tmA;
-  if (skip0 && (rc = encode_act_map(&L->tmS0, skip0, B, H_out, W_out, C_s0, bk, L->Wb, L->Hb, L->Nb, 1))) return rc;
-  if (skip1 && (rc = encode_act_map(&L->tmS1, skip1, B, H_out, W_out, C_s1, bk, L->Wb, L->Hb, L->Nb, 1))) return rc;
+  if (skip0 && (rc = encode_act_map(&L->tmS0, skip0, B, H_out, W_out, C_s0, bk, L->Wb, L->msub * L->Hb, L->Nb, 1))) return rc;
+  if (skip1 && (rc = encode_act_map(&L->tmS1, skip1, B, H_out, W_out, C_s1, bk, L->Wb, L->msub * L->Hb, L->Nb, 1))) return rc;
   const int64_t k_total = (int64_t)L->taps * C_in + C_s0 + C_s1;
   // CTA pairs (cta_group::2) when there are enough M tiles to keep all 74 pairs busy
   L->cta_group = (conv_cta_group_override() == 1) ? 1
-                 : ((bn >= 32 && (int64_t)((L->n_m_tiles + 1) / 2) * L->n_n_tiles * L->n_par >= 32) ? 2 : 1);
+                 : ((bn >= 32 && (int64_t)((L->n_m_tiles / L->msub + 1) / 2) * L->n_n_tiles * L->n_par >= 32) ? 2 : 1);
   if (conv_cta_group_override() == 2 && bn >= 32) L->cta_group = 2;
   L->c_out_pad = C_out_pad;
   if ((rc = encode_weight_map(&L->tmB, w, C_out_pad * L->n_par, k_total, bn / L->cta_group, bk))) return rc;
@@ -474,6 +504,8 @@ int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, c
 
 static int g_tall_enabled = 1;
 int conv_tall_enabled() { return g_tall_enabled; }
+static int g_msub_enabled = 1;
+int conv_msub_enabled() { return g_msub_enabled; }
 static int g_cta_group_override = -1;
 int conv_cta_group_override() {
   if (g_cta_group_override < 0) {
@@ -488,7 +520,7 @@ template <int BN, int BK, int CG>
 static int launch_t(const ConvLaunch& L, cudaStream_t stream) {
   constexpr int KS = BN <= 128 ? 2 : 1;
   const int B_BYTES = (BN / CG) * BK * 2;
-  const int STAGE = L.tall ? (L.Hb + 2) * L.Wb * BK * 2 + 3 * B_BYTES : KS * (128 * BK * 2 + B_BYTES);
+  const int STAGE = L.tall ? (L.msub * L.Hb + 2) * L.Wb * BK * 2 + 3 * B_BYTES : KS * (128 * BK * 2 + B_BYTES);
   int stages = kSmemBudget / STAGE;
   if (stages > kMaxStages) stages = kMaxStages;
   const size_t smem = (size_t)stages * STAGE + 1024 /*align*/ + (2 * kMaxStages + 4) * 8 + 16;
@@ -504,10 +536,10 @@ static int launch_t(const ConvLaunch& L, cudaStream_t stream) {
   p.stride = L.stride; p.taps = L.taps; p.cin_blocks = L.cin_blocks; p.s0_blocks = L.s0_blocks; p.s1_blocks = L.s1_blocks;
   p.tap_cols = L.tap_cols; p.dy0 = L.dy0; p.dx0 = L.dx0; p.out_scale = L.out_scale; p.out_oy = L.out_oy; p.out_ox = L.out_ox;
   p.H_full = L.H_full; p.W_full = L.W_full;
-  p.tall = L.tall; p.stage_bytes = STAGE; p.n_par = L.n_par; p.c_out_pad = L.c_out_pad;
+  p.tall = L.tall; p.stage_bytes = STAGE; p.n_par = L.n_par; p.c_out_pad = L.c_out_pad; p.msub = L.msub;
   p.B = L.B; p.C_out = L.C_out; p.C_out_real = L.C_out_real; p.out_mode = L.out_mode;
   p.bias = L.bias; p.residual = L.residual; p.out = L.out;
-  const int n_items = ((L.n_m_tiles + CG - 1) / CG) * L.n_n_tiles * L.n_par;
+  const int n_items = ((L.n_m_tiles / L.msub + CG - 1) / CG) * L.n_n_tiles * L.n_par;
   const int max_groups = kNumSMs / CG;
   const int grid = (n_items < max_groups ? n_items : max_groups) * CG;
   if (CG == 1) {
@@ -543,6 +575,10 @@ int dlpm_b200_set_option(const char* name, int value) {
   DLPM_REQUIRE(name != nullptr, "set_option: NULL name");
   if (std::string(name) == "pdl") {
     pdl_set_enabled(value != 0);
+    return DLPM_OK;
+  }
+  if (std::string(name) == "conv_msub") {
+    g_msub_enabled = value != 0;
     return DLPM_OK;
   }
   if (std::string(name) == "conv_tall") {

@@ -12,6 +12,7 @@ enum ConvOutMode { CONV_OUT_BF16_NHWC = 0, CONV_OUT_F32_NCHW = 1 };
 struct ConvLaunch {
   CUtensorMap tmA, tmS0, tmS1, tmB;  // main activation, two optional 1x1 skip-conv sources, packed weights
   int block_n, block_k;              // tile N (16..256), K block in channels (64 or 32)
+  int msub;                          // sub-tiles (128 pixels each) per CTA: 2 in tall mode when the image has an even tile count
   int tall;                          // 1 = one (Hb+2)-row activation box per (channel block, dx) feeds the three dy taps
   int cta_group;                     // 1 = single-CTA MMA, 2 = CTA pairs (tcgen05 cta_group::2, M = 256)
   int n_m_tiles, n_n_tiles;
@@ -51,5 +52,6 @@ int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, c
 int conv_launch(const ConvLaunch& L, cudaStream_t stream);
 int conv_cta_group_override();
 int conv_tall_enabled();
+int conv_msub_enabled();
 
 }  // namespace dlpm

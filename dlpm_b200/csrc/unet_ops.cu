@@ -162,6 +162,23 @@ __global__ void __launch_bounds__(kGnThreads) k_groupnorm_cluster(__nv_bfloat16*
                    "l"(in1 + ((int64_t)n * HW + p0) * C1), "r"(bytes1), "r"(gn_smem_u32(bar))
                    : "memory");
   }
+  // affine parameters of (up to) two channels per thread are fetched while the bulk copy is in flight
+  float pg[2], pb[2], psc[2], psh[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int ch = threadIdx.x + k * nthreads;
+    pg[k] = pb[k] = psh[k] = 0.f;
+    psc[k] = 1.f;
+    if (ch < C) {
+      pg[k] = __ldg(gamma + ch);
+      pb[k] = __ldg(beta + ch);
+      if (ss) {
+        const float* row = ss + (ss_rows == 1 ? 0 : (int64_t)n * ss_stride) + ss_off;
+        psc[k] = 1.0f + __ldg(row + ch);
+        psh[k] = __ldg(row + C + ch);
+      }
+    }
+  }
   __syncthreads();  // barrier initialised before anyone polls it
   {
     uint32_t ok = 0, spins = 0;
@@ -200,7 +217,7 @@ __global__ void __launch_bounds__(kGnThreads) k_groupnorm_cluster(__nv_bfloat16*
     psum[ch] = sA;
     psq[ch] = qA;
   }
-  cluster.sync();
+  if (cs > 1) cluster.sync(); else __syncthreads();
   // phase 3: totals over the cluster (DSMEM reads, fixed order), group statistics, affine coefficients
   for (int ch = threadIdx.x; ch < C; ch += nthreads) {
     float sA = 0.f, qA = 0.f;
@@ -212,25 +229,23 @@ __global__ void __launch_bounds__(kGnThreads) k_groupnorm_cluster(__nv_bfloat16*
     part[ch * 2 + 1] = qA;
   }
   __syncthreads();
-  for (int ch = threadIdx.x; ch < C; ch += nthreads) {
-    const int G = C < 32 ? C : 32, cpg = C / G, g = ch / cpg;
-    float sA = 0.f, qA = 0.f;
-    for (int k = 0; k < cpg; ++k) { sA += part[(g * cpg + k) * 2]; qA += part[(g * cpg + k) * 2 + 1]; }
-    const float inv_n = 1.0f / (float)(cpg * HW);
-    const float mean = sA * inv_n;
-    const float rstd = rsqrtf(fmaxf(qA * inv_n - mean * mean, 0.f) + 1e-5f);
-    float ga = __ldg(gamma + ch) * rstd;
-    float be = __ldg(beta + ch) - mean * ga;
-    if (ss) {
-      const float* row = ss + (ss_rows == 1 ? 0 : (int64_t)n * ss_stride) + ss_off;
-      const float sc = 1.0f + __ldg(row + ch), sh = __ldg(row + C + ch);
-      ga *= sc;
-      be = be * sc + sh;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int ch = threadIdx.x + k * nthreads;
+    if (ch < C) {
+      const int G = C < 32 ? C : 32, cpg = C / G, g = ch / cpg;
+      float sA = 0.f, qA = 0.f;
+      for (int kk = 0; kk < cpg; ++kk) { sA += part[(g * cpg + kk) * 2]; qA += part[(g * cpg + kk) * 2 + 1]; }
+      const float inv_n = 1.0f / (float)(cpg * HW);
+      const float mean = sA * inv_n;
+      const float rstd = rsqrtf(fmaxf(qA * inv_n - mean * mean, 0.f) + 1e-5f);
+      const float ga = pg[k] * rstd;
+      const float be = pb[k] - mean * ga;
+      coef_a[ch] = ga * psc[k];
+      coef_b[ch] = be * psc[k] + psh[k];
     }
-    coef_a[ch] = ga;
-    coef_b[ch] = be;
   }
-  cluster.sync();  // every CTA has finished reading its peers' shared memory; also orders coef_* for this CTA
+  if (cs > 1) cluster.sync(); else __syncthreads();  // peers done reading this CTA's shared memory; orders coef_*
   // phase 4: normalise from shared memory -> global (the only write)
   const int slots = nthreads / nvec;
   const int v = threadIdx.x % nvec, slot = threadIdx.x / nvec;
