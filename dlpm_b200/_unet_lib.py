@@ -96,6 +96,47 @@ class Engine:
             pass
 
 
+def run_lim_loop(model, x, coef_d, t_table, steps, ode, isotropic, alpha, clamp_eps, hist, seed, offset, sample_base,
+                 use_graph=True):
+    """LIM reverse loop (sampler.py:218-258) for the image net: per step UNet forward at the continuous time
+    t_table[step] (device table, device step counter) + fused LIM update; one CUDA graph replayed `steps` times."""
+    dev = x.device
+    B, C, H, W = x.shape
+    D = C * H * W
+    eng = model.engine(H, W, B)
+    out = torch.empty((B, model.out_channels, H, W), device=dev, dtype=torch.float32)
+    step_dev = torch.zeros((1,), device=dev, dtype=torch.int32)
+    stream = torch.cuda.current_stream()
+
+    def one_step(h_ptr):
+        eng.forward(x, t_table, step_dev, 0.0, out, B)
+        _lib.call("dlpm_b200_lim_step", _lib.ptr(x), _lib.ptr(out), _lib.ptr(coef_d), 0, _lib.ptr(step_dev), B, D, 0, 1 if ode else 0,
+                  1 if isotropic else 0, float(alpha), -1.0 if clamp_eps is None else float(clamp_eps), None, seed, offset,
+                  sample_base, h_ptr, _lib.stream_ptr())
+        _lib.call("dlpm_b200_advance_counter", _lib.ptr(step_dev), 1, _lib.stream_ptr())
+
+    if hist is not None or not use_graph:
+        for k in range(steps):
+            one_step(_lib.ptr(hist[k + 1]) if hist is not None else None)
+        return
+    x_save = x.clone()
+    one_step(None)  # builds the per-batch plan outside capture
+    x.copy_(x_save)
+    step_dev.zero_()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(stream)
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            one_step(None)
+    stream.wait_stream(side)
+    for _ in range(steps):
+        g.replay()
+    torch.cuda.synchronize()
+    del g
+
+
 def run_sample_loop(model, x, dlpm, T, mode, flags, hist, seed, z_offset, sample_base, graph_cache=None, progress=False,
                     use_graph=True):
     """x: (B, C, H, W) fp32, updated in place to x_0.  One step = UNet forward (t from the device counter) + fused

@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(256) k_gemv_rows(float* __restrict__ out, cons
   pdl_launch_dependents();
   pdl_wait();
   if (sinus) {
-    const float tv = t_dev ? (float)(*t_dev) * inv_T : t[r];
+    const float tv = t_dev ? (t ? t[*t_dev] : (float)(*t_dev) * inv_T) : t[r];
     const int half = K / 2;
     for (int i = threadIdx.x; i < K; i += blockDim.x) {
       if (i < 2 * half) {

@@ -83,6 +83,13 @@ def LIM_sampler(ddim, x, y, model, sde, levy, isotropic, steps, gen_a, gen_eps, 
         hist = torch.empty((steps + 1, *x.shape), device=dev, dtype=torch.float32)
         hist[0].copy_(x)
     call = net_call or (lambda xx, tt: model(xx, tt))
+    if getattr(model, "native_kind", None) == "unet" and injected_noise is None and x.dim() == 4:
+        # image nets: one CUDA graph per step, replayed `steps` times (times come from a device table)
+        from .. import _unet_lib
+        with torch.no_grad(), torch.cuda.device(dev):
+            _unet_lib.run_lim_loop(model, x, coef_d, timesteps[:-1].contiguous().to(dev), steps, bool(ddim), bool(isotropic),
+                                   float(sde.alpha), clamp_eps, hist, st.seed, offset, st.sample_base)
+        return (x, hist) if get_sample_history else x
     with torch.no_grad(), torch.cuda.device(dev):
         for i in range(steps):
             vec_s = torch.full((B,), float(timesteps[i]), device=dev, dtype=torch.float32)

@@ -59,7 +59,8 @@ int dlpm_b200_upsample2x(void* out, const void* in, int64_t B, int H, int W, int
 
 /* Timestep embedding + every ResBlock's emb_layers in two launches (nn.py:103-121; unet.py:335-339,145-151,477):
  *   semb = SiLU(time_embed(timestep_embedding(t, mc)))  [rows][4mc];  ss = semb @ W_all^T + b_all  [rows][ss_total].
- * t: device float[rows] or NULL with t_dev (device int*) -> t = *t_dev * inv_T (CUDA-graph replay).
+ * t: device float[rows]; or NULL with t_dev (device int*): t = *t_dev * inv_T when inv_T > 0 (discrete DLPM steps), or
+ * t = t[*t_dev] when t is non-NULL as well (table of continuous times, LIM) -- both for CUDA-graph replay.
  * Weights in-major fp32: w0T [mc][4mc], b0, w2T [4mc][4mc], b2, wallT [4mc][ss_total], ball. */
 int dlpm_b200_time_embedding(float* ss, float* semb, const float* t, const int* t_dev, float inv_T, int rows, int mc,
                              int64_t ss_total, const float* w0T, const float* b0, const float* w2T, const float* b2,
@@ -75,7 +76,7 @@ int dlpm_b200_time_embedding(float* ss, float* semb, const float* t, const int* 
 int dlpm_b200_unet_create(void** handle, const int64_t* header, const int64_t* ops, const int64_t* bufs, const void* wb,
                           int64_t n_wb, const float* wf, int64_t n_wf, int64_t max_batch);
 /* eps = UNet(x, t): x fp32 NCHW [B,in_ch,H,W]; t device float[t_rows] (t_rows = 1: batch-constant, or B), or
- * t_dev/inv_T as above; out fp32 NCHW [B,out_ch,H,W]. */
+ * t_dev (+ inv_T, or + t as a time table) as above; out fp32 NCHW [B,out_ch,H,W]. */
 int dlpm_b200_unet_forward(void* handle, const float* x, const float* t, int t_rows, const int* t_dev, float inv_T,
                            float* out, int64_t B, void* stream);
 /* debugging / per-layer parity: copy activation buffer `buf` (bf16, B * elems) of the last forward to dst. */

@@ -138,3 +138,27 @@ def test_graph_replayed_sampling_matches_direct_launches():
     x = GenerativeLevyProcess(1.7, "cuda", 1000, rescale_timesteps=True, isotropic=True).sample(
         {"default": m}, [2, 3, 32, 32], reverse_steps=6, clamp_a=20, clamp_eps=200)
     assert x.shape == (2, 3, 32, 32)
+
+
+def test_lim_image_chain_golden_and_graph():
+    """LIM SDE sampler on the image net: injected-noise chain vs the reference history, and the graph-replayed loop
+    (times from a device table) vs direct launches."""
+    from dlpm_b200 import GenerativeLevyProcess, rng
+    g = load_golden("unet_cifar_half")
+    m, _ = make("cifar_half")
+    r = sub(g, "lim_sde")
+    steps = r["e_L"].shape[0]
+    glp = GenerativeLevyProcess(1.7, "cuda", steps, rescale_timesteps=True, isotropic=True, LIM=True)
+    final, hist = glp.lim_sample(m, list(r["x_init"].shape), get_sample_history=True, injected_x=torch.from_numpy(r["x_init"]),
+                                 injected_noise=torch.from_numpy(r["e_L"]))
+    want = torch.from_numpy(r["hist"])
+    assert rel_err(hist.cpu(), want) < 3e-2, rel_err(hist.cpu(), want)
+    outs = []
+    for with_hist in (False, True):  # False: captured graph; True: direct launches
+        glp = GenerativeLevyProcess(1.7, "cuda", 6, rescale_timesteps=True, isotropic=True, LIM=True)
+        o = glp.lim_sample(m, [4, 3, 32, 32], get_sample_history=with_hist, state=rng.PhiloxState(seed=11, offset=0))
+        outs.append(o[0] if with_hist else o)
+    assert torch.isfinite(outs[0]).all() and torch.equal(outs[0], outs[1])
+    ode = GenerativeLevyProcess(1.7, "cuda", 6, rescale_timesteps=True, isotropic=True, LIM=True).sample(
+        {"default": m}, [2, 3, 32, 32], reverse_steps=6, deterministic=True)
+    assert ode.shape == (2, 3, 32, 32) and torch.isfinite(ode).all()
