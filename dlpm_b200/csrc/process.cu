@@ -56,12 +56,14 @@ __device__ __forceinline__ float sel4(const float4& v, int k) { return k == 0 ? 
 // per-sample subordinator (one draw per sample; position 0 of the sample's A stream)
 __device__ __forceinline__ float sample_A(const Philox& ph, const StableParams& sp, uint32_t stream, uint64_t offset,
                                           uint64_t sample) {
+  if (sp.gaussian) return 2.0f;  // alpha == 2: A == 2, no variates consumed (Distributions.py:40-42)
   const uint4 r = philox_at(ph, stream, offset, sample, 0u);
   return stable_A(sp, r.x, r.y);
 }
 // four per-element subordinators for quad `pos` of a sample (two Philox blocks: positions 2pos, 2pos+1)
 __device__ __forceinline__ float4 element_A4(const Philox& ph, const StableParams& sp, uint32_t stream, uint64_t offset,
                                              uint64_t sample, uint32_t pos) {
+  if (sp.gaussian) return make_float4(2.0f, 2.0f, 2.0f, 2.0f);
   const uint4 r0 = philox_at(ph, stream, offset, sample, 2u * pos + 1u);  // +1: position 0 is the per-sample draw
   const uint4 r1 = philox_at(ph, stream, offset, sample, 2u * pos + 2u);
   return make_float4(stable_A(sp, r0.x, r0.y), stable_A(sp, r0.z, r0.w), stable_A(sp, r1.x, r1.y),
@@ -364,6 +366,68 @@ __global__ void __launch_bounds__(256) k_reverse_step(float* __restrict__ x, con
   }
 }
 
+// Production variant of the stochastic DLPM step (isotropic, compact Sigma, in-kernel noise, no clipping): the hot loop
+// of image sampling.  Block-contiguous chunks; the per-sample coefficients (bs*Gamma, sqrt(Gamma*Sigma_{t-1})) of the
+// samples touched by a chunk are computed once into shared memory with the reference's exact arithmetic; every thread
+// then streams UNROLL quads with all loads issued before the math (memory-level parallelism), z drawn in registers.
+template <bool EPS_BF16>
+__global__ void __launch_bounds__(256) k_reverse_step_fast(float* __restrict__ x, const void* __restrict__ eps,
+                                                           const float* __restrict__ Sigma, const float* __restrict__ sched,
+                                                           int t_imm, const int* __restrict__ t_dev, int T, int64_t B, int64_t D,
+                                                           uint64_t seed, uint64_t offset, int64_t sample_base,
+                                                           float* __restrict__ hist, FastDiv fd, int chunk) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int t = t_dev ? *t_dev : t_imm;
+  if (t < 1 || t >= T) return;
+  const Philox ph(seed);
+  const float4 row = __ldg(reinterpret_cast<const float4*>(sched) + t);
+  const float inv_g = __frcp_rn(row.x);
+  const uint64_t off_t = offset + (uint64_t)t;
+  const int64_t qpr = D >> 2, nq = B * qpr;
+  __shared__ float2 s_coef[kChunkQuads];  // (bs*Gamma, 1[t != 1] sqrt(Gamma*Sigma_{t-1})) per sample of the chunk
+  constexpr int UNROLL = 4;
+  for (int64_t q0 = (int64_t)blockIdx.x * chunk; q0 < nq; q0 += (int64_t)gridDim.x * chunk) {
+    const int64_t q1 = q0 + chunk < nq ? q0 + chunk : nq;
+    const int64_t b_first = (int64_t)fd.div((uint32_t)q0), b_last = (int64_t)fd.div((uint32_t)(q1 - 1));
+    __syncthreads();
+    for (int64_t sI = threadIdx.x; sI <= b_last - b_first; sI += blockDim.x) {
+      const int64_t b = b_first + sI;
+      const StepCoef c = dlpm_coef(__ldg(Sigma + (int64_t)(t - 1) * B + b), __ldg(Sigma + (int64_t)t * B + b), row, t);
+      s_coef[sI] = make_float2(c.c1, c.sd);
+    }
+    __syncthreads();
+    for (int64_t qb = q0 + threadIdx.x; qb < q1; qb += (int64_t)blockDim.x * UNROLL) {
+      float4 xv[UNROLL], ev[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int64_t q = qb + (int64_t)u * blockDim.x;
+        if (q < q1) {
+          xv[u] = ld_rw(reinterpret_cast<const float4*>(x) + q);
+          ev[u] = load_eps4<true, EPS_BF16>(eps, q);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int64_t q = qb + (int64_t)u * blockDim.x;
+        if (q < q1) {
+          uint32_t b32, pos;
+          fd.divmod((uint32_t)q, b32, pos);
+          const float2 cf = s_coef[(int64_t)b32 - b_first];
+          const float4 zv = normal_quad(ph, STREAM_Z, off_t, (uint64_t)((int64_t)b32 + sample_base), pos);
+          float4 o;
+          o.x = fmaf(cf.y, zv.x, fmaf(-cf.x, ev[u].x, xv[u].x) * inv_g);
+          o.y = fmaf(cf.y, zv.y, fmaf(-cf.x, ev[u].y, xv[u].y) * inv_g);
+          o.z = fmaf(cf.y, zv.z, fmaf(-cf.x, ev[u].z, xv[u].z) * inv_g);
+          o.w = fmaf(cf.y, zv.w, fmaf(-cf.x, ev[u].w, xv[u].w) * inv_g);
+          reinterpret_cast<float4*>(x)[q] = o;
+          if (hist) st_stream(reinterpret_cast<float4*>(hist) + q, o);
+        }
+      }
+    }
+  }
+}
+
 // LIM step (sampler.py:81-181): x <- a x + c_score (sc * out) [+ c_noise e_L]
 template <bool VEC, bool EPS_BF16>
 __global__ void __launch_bounds__(256) k_lim_step(float* __restrict__ x, const void* __restrict__ mo,
@@ -633,6 +697,14 @@ static int launch_step(float* x, const void* eps, const float* Sigma, const floa
   const int grid = grid_for(vec ? B * D / 4 : B * D, 256);
   cudaStream_t s = (cudaStream_t)stream;
   const FastDiv fd((uint32_t)(vec ? D / 4 : 1));
+  if (MODE == 0 && vec && !z && !(flags & (DLPM_STEP_CLIP_DENOISED | DLPM_STEP_SIGMA_FULL)) && B * D / 4 < (1ll << 31)) {
+    int fgrid, chunk;
+    chunk_grid(B * D / 4, &chunk, &fgrid);
+    if (bf16) launch_ex(k_reverse_step_fast<true>, dim3(fgrid), dim3(256), 0, s, 1, x, eps, Sigma, sched, t, t_dev, T, B, D, seed, offset, sample_base, hist, fd, chunk);
+    else launch_ex(k_reverse_step_fast<false>, dim3(fgrid), dim3(256), 0, s, 1, x, eps, Sigma, sched, t, t_dev, T, B, D, seed, offset, sample_base, hist, fd, chunk);
+    DLPM_CHECK_LAUNCH("reverse_step");
+    return DLPM_OK;
+  }
 #define L(V, H) launch_ex(k_reverse_step<V, H, MODE>, dim3(grid), dim3(256), 0, s, 1, x, eps, Sigma, sched, t, t_dev, T, B, D, flags, z, seed, offset, sample_base, hist, fd)
   if (vec) { if (bf16) L(true, true); else L(true, false); }
   else { if (bf16) L(false, true); else L(false, false); }
