@@ -16,7 +16,8 @@
 
 namespace dlpm {
 
-constexpr int S_TILE = 64;   // samples per CTA
+// samples per CTA: 64 (256 threads) for the stand-alone forward, 80 (320 threads) for the persistent chain -- the largest
+// tile whose activations fit next to the 173 KB of weights, so that 10 000 samples (config C1) are ONE wave of 125 CTAs
 constexpr int U = 64;        // hidden width (nunits)
 constexpr int ROW = 68;      // padded activation row stride (floats): conflict-free column reads
 constexpr int MAX_F = 4;
@@ -45,7 +46,7 @@ struct MlpLayout {
   __host__ __device__ int total() const { return main0() + main_size(); }
 };
 
-__device__ __forceinline__ float silu(float v) { return v / (1.0f + expf(-v)); }
+__device__ __forceinline__ float silu(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
 // acc[i][j] += sum_k act[4ty+i][k] * WT[k][4tx+j]
 template <int K>
@@ -102,28 +103,29 @@ __device__ __forceinline__ void store_tile(float* __restrict__ act, const float 
 
 struct MlpSmem {
   float* w;      // main weights (MlpLayout::main_size floats)
-  float* actA;   // [S_TILE][ROW]
-  float* actB;   // [S_TILE][ROW]
-  float* temb;   // [S_TILE][ROW] per-sample time embedding (columns 0..E-1) -- per-sample-t mode
+  float* actA;   // [ST][ROW]
+  float* actB;   // [ST][ROW]
+  float* temb;   // [ST][ROW] per-sample time embedding (columns 0..E-1) -- per-sample-t mode
   float* tvec;   // [NB][U] SiLU(t_proj) for a batch-constant t
-  float* xs;     // [S_TILE][MAX_F] current x
-  float* es;     // [S_TILE][MAX_F] network output
+  float* xs;     // [ST][MAX_F] current x
+  float* es;     // [ST][MAX_F] network output
 };
 
+template <int ST>
 __device__ __forceinline__ MlpSmem carve(float* base, const MlpLayout& L, bool per_sample_t) {
   MlpSmem m;
   m.w = base;
   float* p = base + ((L.main_size() + 3) & ~3);
-  m.actA = p; p += S_TILE * ROW;
-  m.actB = p; p += S_TILE * ROW;
+  m.actA = p; p += ST * ROW;
+  m.actB = p; p += ST * ROW;
   m.tvec = p; p += L.NB * U;
-  m.xs = p; p += S_TILE * MAX_F;
-  m.es = p; p += S_TILE * MAX_F;
+  m.xs = p; p += ST * MAX_F;
+  m.es = p; p += ST * MAX_F;
   m.temb = per_sample_t ? p : nullptr;
   return m;
 }
-static size_t mlp_smem_bytes(const MlpLayout& L, bool per_sample_t) {
-  size_t f = ((L.main_size() + 3) & ~3) + 2 * S_TILE * ROW + L.NB * U + 2 * S_TILE * MAX_F + (per_sample_t ? S_TILE * ROW : 0);
+static size_t mlp_smem_bytes(const MlpLayout& L, bool per_sample_t, int ST) {
+  size_t f = ((L.main_size() + 3) & ~3) + 2 * ST * ROW + L.NB * U + 2 * ST * MAX_F + (per_sample_t ? ST * ROW : 0);
   return f * sizeof(float);
 }
 
@@ -152,8 +154,10 @@ __device__ void time_path_uniform(const float* __restrict__ gw, const MlpLayout&
 }
 
 // per-sample time embedding temb[s][0..E) for t[s]
+template <int ST>
 __device__ void time_embed_per_sample(const float* __restrict__ gw, const MlpLayout& L, const MlpSmem& m,
                                       const float* __restrict__ t, int64_t s0, int64_t B) {
+  constexpr int S_TILE = ST;
   float* e1 = m.actB;  // [S][ROW] scratch
   for (int o = threadIdx.x; o < S_TILE * L.E; o += blockDim.x) {
     const int s = o / L.E, j = o - s * L.E;
@@ -171,8 +175,9 @@ __device__ void time_embed_per_sample(const float* __restrict__ gw, const MlpLay
 }
 
 // One full forward for the CTA's 64 samples: reads m.xs, writes m.es.  All threads must call.
-template <bool PER_SAMPLE_T>
+template <bool PER_SAMPLE_T, int ST>
 __device__ void mlp_forward_tile(const float* __restrict__ gw, const MlpLayout& L, const MlpSmem& m) {
+  constexpr int S_TILE = ST;
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   const float* w = m.w;
   float acc[4][4], skip[4][4];
@@ -284,11 +289,14 @@ __device__ __forceinline__ void load_main_weights(const float* __restrict__ gw, 
   for (int i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = __ldg(src + i);
 }
 
-__global__ void __launch_bounds__(256, 1) k_mlp_forward(float* __restrict__ out, const float* __restrict__ x,
-                                                        const float* __restrict__ t, const float* __restrict__ gw,
-                                                        int64_t B, MlpLayout L) {
+constexpr int kFwdTile = 64, kChainTile = 80;
+
+__global__ void __launch_bounds__(kFwdTile * 4, 1) k_mlp_forward(float* __restrict__ out, const float* __restrict__ x,
+                                                                 const float* __restrict__ t, const float* __restrict__ gw,
+                                                                 int64_t B, MlpLayout L) {
+  constexpr int S_TILE = kFwdTile;
   extern __shared__ __align__(16) float smem[];
-  const MlpSmem m = carve(smem, L, true);
+  const MlpSmem m = carve<S_TILE>(smem, L, true);
   load_main_weights(gw, L, m);
   for (int64_t s0 = (int64_t)blockIdx.x * S_TILE; s0 < B; s0 += (int64_t)gridDim.x * S_TILE) {
     __syncthreads();
@@ -297,8 +305,8 @@ __global__ void __launch_bounds__(256, 1) k_mlp_forward(float* __restrict__ out,
       m.xs[s * MAX_F + f] = (s0 + s < B) ? x[(s0 + s) * L.F + f] : 0.f;
     }
     __syncthreads();
-    time_embed_per_sample(gw, L, m, t, s0, B);
-    mlp_forward_tile<true>(gw, L, m);
+    time_embed_per_sample<S_TILE>(gw, L, m, t, s0, B);
+    mlp_forward_tile<true, S_TILE>(gw, L, m);
     for (int o = threadIdx.x; o < S_TILE * L.F; o += blockDim.x) {
       const int s = o / L.F, f = o - s * L.F;
       if (s0 + s < B) out[(s0 + s) * L.F + f] = m.es[s * MAX_F + f];
@@ -320,13 +328,14 @@ __device__ __forceinline__ float chain_update(float xv, float ev, float zv, floa
   return __fadd_rn(mean, __fmul_rn(sd, zv));
 }
 
-__global__ void __launch_bounds__(256, 1) k_mlp_chain(float* __restrict__ x, const float* __restrict__ gw,
+__global__ void __launch_bounds__(kChainTile * 4, 1) k_mlp_chain(float* __restrict__ x, const float* __restrict__ gw,
                                                       const float* __restrict__ Sigma, const float* __restrict__ sched,
                                                       int T, int64_t B, MlpLayout L, int mode, int flags,
                                                       const float* __restrict__ z, float* __restrict__ hist,
                                                       uint64_t seed, uint64_t offset, int64_t sample_base) {
+  constexpr int S_TILE = kChainTile;
   extern __shared__ __align__(16) float smem[];
-  const MlpSmem m = carve(smem, L, false);
+  const MlpSmem m = carve<S_TILE>(smem, L, false);
   const Philox ph(seed);
   const bool clip = flags & DLPM_STEP_CLIP_DENOISED;
   load_main_weights(gw, L, m);
@@ -344,7 +353,7 @@ __global__ void __launch_bounds__(256, 1) k_mlp_chain(float* __restrict__ x, con
     __syncthreads();
     for (int t = T - 1; t >= 1; --t) {
       time_path_uniform(gw, L, m, (float)t * inv_T);
-      mlp_forward_tile<false>(gw, L, m);
+      mlp_forward_tile<false, S_TILE>(gw, L, m);
       if (owner) {
         const float ev = m.es[s * MAX_F + f];
         if (live) {
@@ -392,13 +401,14 @@ int dlpm_b200_mlp_forward(float* out, const float* x, const float* t, const floa
   if (int rc = check_mlp_dims(F, U_, E, nblocks_total)) return rc;
   if (B == 0) return DLPM_OK;
   MlpLayout L{F, E, nblocks_total};
-  const size_t smem = mlp_smem_bytes(L, true);
+  constexpr int S_TILE = kFwdTile;
+  const size_t smem = mlp_smem_bytes(L, true, S_TILE);
   DLPM_REQUIRE(smem <= 227 * 1024, "mlp_forward: network does not fit in shared memory");
   cudaError_t e = cudaFuncSetAttribute(k_mlp_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_fail(e, "mlp_forward smem attr");
   int64_t tiles = (B + S_TILE - 1) / S_TILE;
   const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-  k_mlp_forward<<<grid, 256, smem, (cudaStream_t)stream>>>(out, x, t, weights, B, L);
+  k_mlp_forward<<<grid, S_TILE * 4, smem, (cudaStream_t)stream>>>(out, x, t, weights, B, L);
   DLPM_CHECK_LAUNCH("mlp_forward");
   return DLPM_OK;
 }
@@ -413,13 +423,14 @@ int dlpm_b200_mlp_sample_chain(float* x, const float* weights, const float* Sigm
   if (int rc = check_mlp_dims(F, U_, E, nblocks_total)) return rc;
   if (B == 0) return DLPM_OK;
   MlpLayout L{F, E, nblocks_total};
-  const size_t smem = mlp_smem_bytes(L, false);
+  constexpr int S_TILE = kChainTile;
+  const size_t smem = mlp_smem_bytes(L, false, S_TILE);
   DLPM_REQUIRE(smem <= 227 * 1024, "mlp_sample_chain: network does not fit in shared memory");
   cudaError_t e = cudaFuncSetAttribute(k_mlp_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_fail(e, "mlp_sample_chain smem attr");
   int64_t tiles = (B + S_TILE - 1) / S_TILE;
   const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-  k_mlp_chain<<<grid, 256, smem, (cudaStream_t)stream>>>(x, weights, Sigma, sched, T, B, L, mode, flags, z, hist, seed, offset,
+  k_mlp_chain<<<grid, S_TILE * 4, smem, (cudaStream_t)stream>>>(x, weights, Sigma, sched, T, B, L, mode, flags, z, hist, seed, offset,
                                                         sample_base);
   DLPM_CHECK_LAUNCH("mlp_sample_chain");
   return DLPM_OK;
