@@ -434,6 +434,8 @@ static int encode_weight_map(CUtensorMap* m, const void* base, int rows, int64_t
   return DLPM_OK;
 }
 
+static int g_tall256_enabled = 1;
+
 int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, const void* skip0, int C_s0, const void* skip1,
               int C_s1, const void* residual, void* out, int out_mode, int64_t B, int H, int W, int C_in, int C_out, ConvGeom geom,
               int stride) {
@@ -483,20 +485,23 @@ int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, c
   L->cin_blocks = C_in / bk; L->s0_blocks = C_s0 / bk; L->s1_blocks = C_s1 / bk;
   L->B = B; L->C_out = C_out; L->C_out_real = C_out; L->out_mode = out_mode;
   L->bias = bias; L->residual = reinterpret_cast<const __nv_bfloat16*>(residual); L->out = out;
-  L->tall = (L->Nb == 1 && geom.tap_rows == 3 && geom.tap_cols == 3 && geom.dy0 == -1 && geom.dx0 == -1 && stride == 1 &&
-             geom.out_scale == 1 && bn <= 128 && L->Wb % 8 == 0 && conv_tall_enabled()) ? 1 : 0;
+  // "tall" activation boxes: 3x3 stride-1 convs whose tile lies inside one image.  N = 256 tiles only fit the shared-memory
+  // budget as CTA pairs (each CTA stages half of the three weight tiles), so the flavour is decided before the tensor maps.
+  const bool tall_geom = L->Nb == 1 && geom.tap_rows == 3 && geom.tap_cols == 3 && geom.dy0 == -1 && geom.dx0 == -1 && stride == 1 &&
+                         geom.out_scale == 1 && L->Wb % 8 == 0 && conv_tall_enabled();
   // two vertically adjacent sub-tiles per CTA when the image has an even number of tiles and TMEM has room (N <= 128)
-  L->msub = (L->tall && L->tiles_per_img % 2 == 0 && bn <= 128 && conv_msub_enabled()) ? 2 : 1;
+  L->msub = (tall_geom && L->tiles_per_img % 2 == 0 && bn <= 128 && conv_msub_enabled()) ? 2 : 1;
+  // CTA pairs (cta_group::2) when there are enough M tiles to keep all 74 pairs busy
+  L->cta_group = (conv_cta_group_override() == 1) ? 1
+                 : ((bn >= 32 && (int64_t)((L->n_m_tiles / L->msub + 1) / 2) * L->n_n_tiles * L->n_par >= 32) ? 2 : 1);
+  if (conv_cta_group_override() == 2 && bn >= 32) L->cta_group = 2;
+  L->tall = (tall_geom && (bn <= 128 || (L->cta_group == 2 && g_tall256_enabled))) ? 1 : 0;
   int rc;
   if ((rc = encode_act_map(&L->tmA, in, B, H, W, C_in, bk, L->Wb, L->tall ? L->msub * L->Hb + 2 : L->Hb, L->Nb, stride))) return rc;
   L->tmS0 = L->tmA; L->tmS1 = L->tmA;
   if (skip0 && (rc = encode_act_map(&L->tmS0, skip0, B, H_out, W_out, C_s0, bk, L->Wb, L->msub * L->Hb, L->Nb, 1))) return rc;
   if (skip1 && (rc = encode_act_map(&L->tmS1, skip1, B, H_out, W_out, C_s1, bk, L->Wb, L->msub * L->Hb, L->Nb, 1))) return rc;
   const int64_t k_total = (int64_t)L->taps * C_in + C_s0 + C_s1;
-  // CTA pairs (cta_group::2) when there are enough M tiles to keep all 74 pairs busy
-  L->cta_group = (conv_cta_group_override() == 1) ? 1
-                 : ((bn >= 32 && (int64_t)((L->n_m_tiles / L->msub + 1) / 2) * L->n_n_tiles * L->n_par >= 32) ? 2 : 1);
-  if (conv_cta_group_override() == 2 && bn >= 32) L->cta_group = 2;
   L->c_out_pad = C_out_pad;
   if ((rc = encode_weight_map(&L->tmB, w, C_out_pad * L->n_par, k_total, bn / L->cta_group, bk))) return rc;
   return DLPM_OK;
@@ -579,6 +584,10 @@ int dlpm_b200_set_option(const char* name, int value) {
   }
   if (std::string(name) == "conv_msub") {
     g_msub_enabled = value != 0;
+    return DLPM_OK;
+  }
+  if (std::string(name) == "conv_tall256") {
+    g_tall256_enabled = value != 0;
     return DLPM_OK;
   }
   if (std::string(name) == "conv_tall") {

@@ -175,3 +175,32 @@ def test_argument_errors(L):
         L.call("dlpm_b200_reverse_step", L.ptr(x), L.ptr(x), L.ptr(x), L.ptr(x), 0, None, 4, 4, 4, 0, None, 0, 0, 0, None, L.stream_ptr())
     with pytest.raises(L.DlpmB200Error):
         L.ptr(torch.zeros(3))  # CPU tensor: no fallback
+
+
+def test_non_isotropic_sigma_chain_and_step(L):
+    """isotropic=False: per-element A / Sigma tables (the reference's full-tensor layout, dlpm.py:226-239) and the fused
+    step with DLPM_STEP_SIGMA_FULL, against the oracle on the A table the kernel drew."""
+    from dlpm_b200.methods.dlpm import DLPM
+    from dlpm_b200 import rng
+    T, shape = 12, (5, 3, 4, 4)
+    d = DLPM(1.7, "cuda", T, isotropic=False)
+    d.gen_a.setParams(clamp_a=20.0)
+    d.sample_A(shape, T, state=rng.PhiloxState(seed=3, offset=0))
+    assert d.A.shape == (T, *shape) and d.Sigmas.shape == (T, *shape)
+    A = d.A.cpu()
+    assert float(A.max()) <= 20.0 and float(A.min()) >= 0.0 and A[0].flatten().unique().numel() > 100  # per-element draws
+    sched = process.gen_noise_schedule(1.7, T)
+    want = process.compute_Sigmas(A, sched[0], sched[2])
+    assert torch.equal(d.Sigmas.cpu(), want)
+    x, eps, z = (torch.randn(shape) for _ in range(3))
+    t = 5
+    xd, ed, zd = x.cuda().contiguous(), eps.cuda().contiguous(), z.cuda().contiguous()
+    B, D = shape[0], 48
+    L.call("dlpm_b200_reverse_step", L.ptr(xd), L.ptr(ed), L.ptr(d.Sigmas), L.ptr(d.sched), t, None, T, B, D, L.STEP_SIGMA_FULL,
+           L.ptr(zd), 0, 0, 0, None, L.stream_ptr())
+    ref = process.dlpm_step(x, eps, z, t, want, sched)
+    np.testing.assert_allclose(xd.cpu().numpy(), ref.numpy(), rtol=1e-6, atol=1e-6)
+    # replacing A by hand re-runs the scan (compute_Sigmas) on the injected table
+    d.A = (A * 0.5).cuda()
+    d.compute_Sigmas()
+    assert torch.equal(d.Sigmas.cpu(), process.compute_Sigmas(A * 0.5, sched[0], sched[2]))

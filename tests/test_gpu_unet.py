@@ -162,3 +162,27 @@ def test_lim_image_chain_golden_and_graph():
     ode = GenerativeLevyProcess(1.7, "cuda", 6, rescale_timesteps=True, isotropic=True, LIM=True).sample(
         {"default": m}, [2, 3, 32, 32], reverse_steps=6, deterministic=True)
     assert ode.shape == (2, 3, 32, 32) and torch.isfinite(ode).all()
+
+
+def test_training_loss_forward_with_unet():
+    """Training-loss forward path (Prop. 9, GenerativeLevyProcess.py:612-677) through the UNet engine with per-sample
+    timesteps, against the oracle on the same injected (t, A, z)."""
+    from dlpm_b200 import GenerativeLevyProcess
+    from oracle import nets, process, stable
+    m, _ = make("cifar_half")
+    c = CFGS["cifar_half"]
+    cfg = dict(model_channels=c["model_channels"], channel_mult=c["channel_mult"], num_res_blocks=c["num_res_blocks"],
+               attention_resolutions=c["attention_resolutions"], num_heads=c["num_heads"])
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    B, T = 6, 100
+    g = torch.Generator().manual_seed(4)
+    x0 = torch.randn(B, 3, 32, 32, generator=g).clamp(-1, 1)
+    t = torch.randint(1, T, size=[B], generator=g)
+    A = torch.from_numpy(stable.gen_skewed_levy(1.7, (B,), isotropic=True, clamp_a=20.0, rng=np.random.RandomState(4)).copy())
+    z = torch.randn(B, 3, 32, 32, generator=g)
+    glp = GenerativeLevyProcess(1.7, "cuda", T, rescale_timesteps=True, isotropic=True)
+    got = glp.training_losses({"default": m}, x0, loss_type="EPS_LOSS", lploss=2.0, clamp_a=20.0,
+                              injected=dict(t=t, A=A, z=z))["loss"].item()
+    want = process.training_loss_dlpm(lambda xx, tt: nets.unet_forward(sd, cfg, xx, tt), x0, t,
+                                      A.view(B, 1, 1, 1).expand(B, 3, 32, 32), z, 1.7, T).item()
+    assert abs(got - want) < 2e-2 * abs(want), (got, want)
