@@ -10,11 +10,18 @@ c_i64, c_int, c_f32, c_vp = ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes
 UNET_SIGNATURES = {
     "dlpm_b200_conv2d": [c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_int, c_i64, c_int, c_int, c_int, c_int,
                          c_int, c_int, c_vp],
+    "dlpm_b200_conv2d_stats": [c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_int, c_i64, c_int, c_int, c_int, c_int,
+                               c_int, c_int, c_vp, ctypes.POINTER(c_int), c_vp],
+    "dlpm_b200_groupnorm_from_stats": [c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_int, c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp,
+                                       c_int, c_i64, c_i64, c_int, c_vp],
+    "dlpm_b200_groupnorm_fold": [c_vp, c_int, c_vp, c_int, c_int, c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_int, c_i64, c_i64,
+                                 c_vp],
     "dlpm_b200_set_option": [ctypes.c_char_p, c_int],
     "dlpm_b200_groupnorm_silu": [c_vp, c_vp, c_int, c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_int, c_i64, c_i64, c_int,
                                  c_vp],
     "dlpm_b200_attention": [c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp],
     "dlpm_b200_conv_in": [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp],
+    "dlpm_b200_conv_in_stats": [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp, ctypes.POINTER(c_int), c_vp],
     "dlpm_b200_upsample2x": [c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp],
     "dlpm_b200_time_embedding": [c_vp, c_vp, c_vp, c_vp, c_f32, c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "dlpm_b200_unet_create": [ctypes.POINTER(c_vp), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), c_vp,

@@ -110,6 +110,11 @@ __device__ __forceinline__ void st_stream(float4* p, const float4& v) {
                "f"(v.w)
                : "memory");
 }
+__device__ __forceinline__ uint4 ld_stream_u4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ float4 ld_rw(const float4* p) {  // plain (the location is rewritten by the same thread)
   return *p;
 }

@@ -45,6 +45,8 @@ struct ConvKParams {
   const float* bias;
   const __nv_bfloat16* residual;
   void* out;
+  float* stats;           // GroupNorm partial sums of the output [B][stats_parts][C_out/4][2], or nullptr
+  int stats_parts, units_per_img, stats_wpi;  // rows per image, work units per image, epilogue warps per image and unit
 };
 
 // CG = 1: one CTA per 128-pixel tile.  CG = 2: a CTA PAIR (cluster of 2 on one TPC) computes two adjacent 128-pixel
@@ -312,13 +314,22 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
         mbar_wait(tfull_bar + acc, acc_phase);
         tc_fence_after();
+        int64_t pixs[MS_MAX];
 #pragma unroll
-        for (int sub = 0; sub < MS_MAX; ++sub) {
-          if (sub < msub) {
-            const int64_t pix = (nn * p.H_full + p.out_scale * (h0 + sub * p.Hb + h_in) + out_oy) * p.W_full + p.out_scale * w_in + out_ox;
-            const uint32_t t_row = t_row0 + (uint32_t)(sub * BLOCK_N);
+        for (int sub = 0; sub < MS_MAX; ++sub)
+          pixs[sub] = (nn * p.H_full + p.out_scale * (h0 + sub * p.Hb + h_in) + out_oy) * p.W_full + p.out_scale * w_in + out_ox;
+        // GroupNorm statistics of the tensor being written (consumed by k_gn_apply / the fold kernel): per warp, per
+        // channel QUAD, (sum, sum of squares) over the warp's 32 pixels (x msub sub-tiles) -- no second pass over the output
+        const bool do_stats = CH == 32 && p.stats != nullptr && valid;
 #pragma unroll
-            for (int c0 = 0; c0 < BLOCK_N; c0 += CH) {
+        for (int c0 = 0; c0 < BLOCK_N; c0 += CH) {
+          float st[CH / 2];
+#pragma unroll
+          for (int i = 0; i < CH / 2; ++i) st[i] = 0.f;
+#pragma unroll
+          for (int sub = 0; sub < MS_MAX; ++sub) {
+            if (sub < msub) {
+              const uint32_t t_row = t_row0 + (uint32_t)(sub * BLOCK_N);
               uint32_t r[CH];
               if constexpr (CH == 32) tmem_ld_x32(t_row + c0, r);
               else tmem_ld_x16(t_row + c0, r);
@@ -326,7 +337,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               if (valid) {
                 const int col = nt * BLOCK_N + c0;
                 const float* bias = p.bias + col;
-                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.C_out + col;
+                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + pixs[sub] * p.C_out + col;
 #pragma unroll
                 for (int j = 0; j < CH; j += 8) {
                   float v[8];
@@ -343,7 +354,36 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
                   for (int e = 0; e < 4; ++e) op[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
                   *reinterpret_cast<uint4*>(dst + j) = o;
+                  if (do_stats) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                      const int qi = (j / 4 + h) * 2;
+                      st[qi] += (v[4 * h] + v[4 * h + 1]) + (v[4 * h + 2] + v[4 * h + 3]);
+                      st[qi + 1] += fmaf(v[4 * h], v[4 * h], v[4 * h + 1] * v[4 * h + 1]) + fmaf(v[4 * h + 2], v[4 * h + 2], v[4 * h + 3] * v[4 * h + 3]);
+                    }
+                  }
                 }
+              }
+            }
+          }
+          if constexpr (CH == 32) {
+            if (p.stats != nullptr) {  // warp-uniform (so is valid: a warp's 32 pixels belong to one image)
+              // transposing butterfly: 16 values over 32 lanes in 8+4+2+1+1 shuffles; lane l ends with the total of value l>>1
+#pragma unroll
+              for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
+                const bool up = (lane & off) != 0;
+#pragma unroll
+                for (int k = 0; k < half; ++k) {
+                  const float send = up ? st[k] : st[k + half];
+                  const float keep = up ? st[k + half] : st[k];
+                  st[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+              }
+              st[0] += __shfl_xor_sync(0xffffffffu, st[0], 1);
+              if (do_stats && (lane & 1) == 0) {
+                const int unit = (mt / msub) % p.units_per_img;
+                const int64_t row = (nn * p.stats_parts + (int64_t)(par * p.units_per_img + unit) * p.stats_wpi + (q % p.stats_wpi));
+                p.stats[(row * (p.C_out >> 2) + ((nt * BLOCK_N + c0) >> 2)) * 2 + (lane >> 1)] = st[0];
               }
             }
           }
@@ -503,8 +543,18 @@ int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, c
   if (skip1 && (rc = encode_act_map(&L->tmS1, skip1, B, H_out, W_out, C_s1, bk, L->Wb, L->msub * L->Hb, L->Nb, 1))) return rc;
   const int64_t k_total = (int64_t)L->taps * C_in + C_s0 + C_s1;
   L->c_out_pad = C_out_pad;
+  L->stats = nullptr;
   if ((rc = encode_weight_map(&L->tmB, w, C_out_pad * L->n_par, k_total, bn / L->cta_group, bk))) return rc;
   return DLPM_OK;
+}
+
+// Partial-statistics rows per image this conv can emit for the GroupNorm that consumes its output (0 = not supported):
+// one row per epilogue warp (4) per work unit of the image per output parity.
+int conv_stats_parts(const ConvLaunch& L) {
+  if (L.out_mode != CONV_OUT_BF16_NHWC || L.block_n < 32 || L.C_out % 4) return 0;
+  if (L.Nb == 1) return 4 * (L.tiles_per_img / L.msub) * L.n_par;
+  // several images per tile: every epilogue warp (32 pixels) must lie inside one image
+  return (L.Wb * L.Hb) % 32 == 0 ? ((L.Wb * L.Hb) / 32) * L.n_par : 0;
 }
 
 static int g_tall_enabled = 1;
@@ -544,6 +594,8 @@ static int launch_t(const ConvLaunch& L, cudaStream_t stream) {
   p.tall = L.tall; p.stage_bytes = STAGE; p.n_par = L.n_par; p.c_out_pad = L.c_out_pad; p.msub = L.msub;
   p.B = L.B; p.C_out = L.C_out; p.C_out_real = L.C_out_real; p.out_mode = L.out_mode;
   p.bias = L.bias; p.residual = L.residual; p.out = L.out;
+  p.stats = L.stats; p.stats_parts = conv_stats_parts(L); p.units_per_img = L.tiles_per_img > 0 ? L.tiles_per_img / L.msub : 1;
+  p.stats_wpi = L.Nb == 1 ? 4 : (L.Wb * L.Hb) / 32;
   const int n_items = ((L.n_m_tiles / L.msub + CG - 1) / CG) * L.n_n_tiles * L.n_par;
   const int max_groups = kNumSMs / CG;
   const int grid = (n_items < max_groups ? n_items : max_groups) * CG;
@@ -574,12 +626,17 @@ int conv_launch(const ConvLaunch& L, cudaStream_t stream) {
 
 }  // namespace dlpm
 
+namespace dlpm { void engine_set_gn_stats(bool on); }
 using namespace dlpm;
 
 int dlpm_b200_set_option(const char* name, int value) {
   DLPM_REQUIRE(name != nullptr, "set_option: NULL name");
   if (std::string(name) == "pdl") {
     pdl_set_enabled(value != 0);
+    return DLPM_OK;
+  }
+  if (std::string(name) == "gn_stats") {
+    engine_set_gn_stats(value != 0);
     return DLPM_OK;
   }
   if (std::string(name) == "conv_msub") {
@@ -611,5 +668,21 @@ int dlpm_b200_conv2d(const void* in, const void* w, const float* bias, const voi
   if (int rc = conv_plan(&L, in, w, bias, skip0, C_s0, skip1, C_s1, residual, out, out_mode, B, H, W, C_in, C_out,
                          conv_geom_default(ksize), stride))
     return rc;
+  return conv_launch(L, (cudaStream_t)stream);
+}
+
+int dlpm_b200_conv2d_stats(const void* in, const void* w, const float* bias, const void* skip0, int C_s0, const void* skip1, int C_s1,
+                           const void* residual, void* out, int out_mode, int64_t B, int H, int W, int C_in, int C_out, int ksize,
+                           int stride, float* stats, int* stats_parts, void* stream) {
+  DLPM_REQUIRE(ksize == 3 || ksize == 1, "conv: kernel size must be 1 or 3");
+  ConvLaunch L;
+  if (int rc = conv_plan(&L, in, w, bias, skip0, C_s0, skip1, C_s1, residual, out, out_mode, B, H, W, C_in, C_out,
+                         conv_geom_default(ksize), stride))
+    return rc;
+  const int parts = conv_stats_parts(L);
+  if (stats_parts) *stats_parts = parts;
+  if (stats == nullptr) return stats_parts ? DLPM_OK : conv_launch(L, (cudaStream_t)stream);
+  DLPM_REQUIRE(parts > 0, "conv2d_stats: this shape cannot emit GroupNorm statistics");
+  L.stats = stats;
   return conv_launch(L, (cudaStream_t)stream);
 }

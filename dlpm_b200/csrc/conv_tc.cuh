@@ -31,6 +31,7 @@ struct ConvLaunch {
   const float* bias;                // [n_n_tiles * block_n] fp32
   const __nv_bfloat16* residual;    // NHWC bf16 [B, H_out, W_out, C_out] or nullptr
   void* out;
+  float* stats;                     // optional GroupNorm partial sums of the output (see conv_stats_parts), set by the caller
 };
 
 // Fills geometry + tensor maps.  in: NHWC bf16 [B, H, W, C_in]; w: bf16 [C_out_pad][taps*C_in + C_s0 + C_s1] (K contiguous);
@@ -50,6 +51,7 @@ int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, c
               int C_s1, const void* residual, void* out, int out_mode, int64_t B, int H, int W, int C_in, int C_out, ConvGeom geom,
               int stride);
 int conv_launch(const ConvLaunch& L, cudaStream_t stream);
+int conv_stats_parts(const ConvLaunch& L);
 int conv_cta_group_override();
 int conv_tall_enabled();
 int conv_msub_enabled();

@@ -16,9 +16,20 @@ enum OpCode { OP_CONV_IN = 0, OP_GN = 1, OP_CONV = 2, OP_UP = 3, OP_ATTN = 4 };
 constexpr int kOpFields = 24;
 struct Op { int64_t f[kOpFields]; };
 
+// GroupNorm whose inputs were all written by convolutions that left partial statistics (conv_tc.cu epilogue): no
+// statistics pass, the tensor is streamed once (unet_ops.cu: k_gn_apply).  Otherwise the cluster kernel runs.
+struct GnLaunch {
+  const float* st0 = nullptr; int parts0 = 0;
+  const float* st1 = nullptr; int parts1 = 0;
+  bool from_stats = false;
+};
+
 struct Plan {  // per batch size
   int64_t B = 0;
   std::vector<ConvLaunch> convs;  // one per OP_CONV, in op order
+  std::vector<GnLaunch> gns;      // one per OP_GN, in op order
+  std::vector<float*> stats_bufs; // owned (one per statistics-emitting convolution)
+  std::vector<float*> conv_in_stats;  // one per OP_CONV_IN (nullptr = no statistics)
 };
 
 struct UNetEngine {
@@ -41,11 +52,55 @@ struct UNetEngine {
   __nv_bfloat16* buf(int64_t id, int64_t B) const { return slab + buf_offset[id] * max_batch; }
 };
 
+static int alloc_stats(UNetEngine* E, Plan* P, int64_t B, int parts, int C, float** st) {
+  const size_t bytes = (size_t)B * parts * (C / 4) * 2 * sizeof(float);
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(st), bytes);
+  if (e != cudaSuccess) return cuda_fail(e, "unet plan: statistics buffer");
+  P->stats_bufs.push_back(*st);
+  E->workspace_bytes += (int64_t)bytes;
+  return DLPM_OK;
+}
+
+static bool g_gn_stats_enabled = true;
+void engine_set_gn_stats(bool on) { g_gn_stats_enabled = on; }
+
 static int build_plan(UNetEngine* E, int64_t B, Plan* P) {
   P->B = B;
   P->convs.clear();
+  P->gns.clear();
+  P->conv_in_stats.clear();
+  struct BufStats { const float* st = nullptr; int parts = 0; int C = 0; };
+  std::vector<BufStats> bstats(E->buf_elems.size());  // statistics of the CURRENT content of every activation buffer
+  auto writes = [&](int64_t id) { if (id >= 0) bstats[id] = BufStats(); };
   for (const Op& op : E->ops) {
-    if (op.f[0] != OP_CONV) continue;
+    const int64_t* f = op.f;
+    if (f[0] == OP_CONV_IN) {  // 1 out, 2 C_in, 3 C_out, 4 H, 5 W
+      writes(f[1]);
+      int parts = 0;
+      dlpm_b200_conv_in_stats(nullptr, nullptr, nullptr, nullptr, B, (int)f[2], (int)f[3], (int)f[4], (int)f[5], nullptr, &parts, nullptr);
+      float* st = nullptr;
+      if (parts > 0 && g_gn_stats_enabled && f[3] % 128 == 0) {
+        if (int rc = alloc_stats(E, P, B, parts, (int)f[3], &st)) return rc;
+        bstats[f[1]].st = st; bstats[f[1]].parts = parts; bstats[f[1]].C = (int)f[3];
+      }
+      P->conv_in_stats.push_back(st);
+    }
+    if (f[0] == OP_UP || f[0] == OP_ATTN) writes(f[2]);
+    if (f[0] == OP_GN) {
+      // 1 in0, 2 in1, 3 out, 4 C0, 5 C1, 6 HW
+      GnLaunch G;
+      const BufStats& s0 = bstats[f[1]];
+      const bool two = f[2] >= 0;
+      const int C = (int)(f[4] + f[5]);
+      if (g_gn_stats_enabled && s0.st && s0.C == f[4] && (!two || (bstats[f[2]].st && bstats[f[2]].C == f[5])) && C % 128 == 0 && C <= 512) {
+        G.from_stats = true;
+        G.st0 = s0.st; G.parts0 = s0.parts;
+        if (two) { G.st1 = bstats[f[2]].st; G.parts1 = bstats[f[2]].parts; }
+      }
+      P->gns.push_back(G);
+      writes(f[3]);
+    }
+    if (f[0] != OP_CONV) continue;
     // f: 1 in, 2 out(-1 = external fp32 NCHW), 3 skip0, 4 C_s0, 5 skip1, 6 C_s1, 7 residual, 8 H, 9 W, 10 C_in, 11 C_out, 12 ksize,
     //    13 stride, 14 w_off (bf16 elems), 15 bias_off (fp32 elems), 16 tap_rows, 17 tap_cols, 18 dy0, 19 dx0, 20 out_scale, 21 out_oy,
     //    22 out_ox, 23 n_par
@@ -61,6 +116,16 @@ static int build_plan(UNetEngine* E, int64_t B, Plan* P) {
                                 (int)op.f[23]},
                        (int)op.f[13]);
     if (rc) return rc;
+    if (!ext) {
+      writes(f[2]);
+      const int parts = conv_stats_parts(L);
+      if (parts > 0 && g_gn_stats_enabled && L.C_out % 128 == 0) {
+        float* st = nullptr;
+        if (int rc2 = alloc_stats(E, P, B, parts, L.C_out, &st)) return rc2;
+        L.stats = st;
+        bstats[f[2]].st = st; bstats[f[2]].parts = parts; bstats[f[2]].C = L.C_out;
+      }
+    }
     P->convs.push_back(L);
   }
   return DLPM_OK;
@@ -136,18 +201,27 @@ int dlpm_b200_unet_forward(void* handle, const float* x, const float* t, int t_r
   if (rc) return rc;
   launches += 2;
   if (prof) cudaEventRecord(E->prof[1], (cudaStream_t)stream);
-  size_t ci = 0, oi = 0;
+  size_t ci = 0, oi = 0, gi = 0, cii = 0;
   for (const Op& op : E->ops) {
     const int64_t* f = op.f;
     switch (f[0]) {
       case OP_CONV_IN:  // 1 out, 2 C_in, 3 C_out, 4 H, 5 W, 6 w_off(f32), 7 b_off(f32)
-        rc = dlpm_b200_conv_in(E->buf(f[1], B), x, E->wf + f[6], E->wf + f[7], B, (int)f[2], (int)f[3], (int)f[4], (int)f[5], stream);
+        rc = dlpm_b200_conv_in_stats(E->buf(f[1], B), x, E->wf + f[6], E->wf + f[7], B, (int)f[2], (int)f[3], (int)f[4], (int)f[5],
+                                     P.conv_in_stats[cii++], nullptr, stream);
         break;
-      case OP_GN:  // 1 in0, 2 in1, 3 out, 4 C0, 5 C1, 6 HW, 7 gamma_off, 8 beta_off, 9 ss_off, 10 silu
+      case OP_GN: {  // 1 in0, 2 in1, 3 out, 4 C0, 5 C1, 6 HW, 7 gamma_off, 8 beta_off, 9 ss_off, 10 silu
+        const GnLaunch& G = P.gns[gi++];
+        if (G.from_stats) {
+          rc = dlpm_b200_groupnorm_from_stats(E->buf(f[3], B), E->buf(f[1], B), (int)f[4], G.st0, G.parts0,
+                                              f[2] >= 0 ? E->buf(f[2], B) : nullptr, (int)f[5], G.st1, G.parts1, B, (int)f[6],
+                                              E->wf + f[7], E->wf + f[8], f[9] >= 0 ? E->ss : nullptr, rows, ss_total,
+                                              f[9] >= 0 ? f[9] : 0, (int)f[10], stream);
+          break;
+        }
         rc = dlpm_b200_groupnorm_silu(E->buf(f[3], B), E->buf(f[1], B), (int)f[4], f[2] >= 0 ? E->buf(f[2], B) : nullptr, (int)f[5], B,
                                       (int)f[6], E->wf + f[7], E->wf + f[8], f[9] >= 0 ? E->ss : nullptr, rows, ss_total,
                                       f[9] >= 0 ? f[9] : 0, (int)f[10], stream);
-        break;
+      } break;
       case OP_CONV: {
         ConvLaunch& L = P.convs[ci++];
         if (f[2] < 0) L.out = out;
@@ -218,6 +292,8 @@ int dlpm_b200_unet_destroy(void* handle) {
   if (!handle) return DLPM_OK;
   UNetEngine* E = reinterpret_cast<UNetEngine*>(handle);
   cudaFree(E->wb); cudaFree(E->wf); cudaFree(E->slab); cudaFree(E->ss); cudaFree(E->semb);
+  for (auto& kv : E->plans)
+    for (float* st : kv.second.stats_bufs) cudaFree(st);
   delete E;
   return DLPM_OK;
 }

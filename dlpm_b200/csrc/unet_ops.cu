@@ -121,6 +121,125 @@ __global__ void __launch_bounds__(kGnThreads) k_groupnorm(__nv_bfloat16* __restr
 // through distributed shared memory (fixed rank order -> bitwise deterministic), then the data is normalised from
 // shared memory.  No second pass over global memory, no atomics.
 // ------------------------------------------------------------------------------------------------
+// K6 (fused-statistics variant).  When the tensor was written by k_conv_tc, its epilogue already left per-image partial
+// sums per channel QUAD ([B][parts][C/4][2] fp32: sum, sum of squares; conv_tc.cu).  GroupNorm then needs no statistics
+// pass and no cluster: gn_fold turns the partials of ONE sample into per-channel affine coefficients
+//   y = a[c] * x + b[c],  a = gamma*rstd*(1+scale),  b = (beta - mean*gamma*rstd)*(1+scale) + shift
+// (fixed summation order -> bitwise deterministic), and k_gn_apply streams the tensor once (read + write).
+// Group boundaries are multiples of 4 channels for every C that is a multiple of 128 (32 groups).
+// ------------------------------------------------------------------------------------------------
+struct GnFoldArgs {
+  const float* st0; int parts0, C0;
+  const float* st1; int parts1, C1;
+  int HW;
+  const float* gamma; const float* beta;
+  const float* ss; int ss_rows; int64_t ss_stride, ss_off;
+};
+
+// block-wide; quad: shared scratch [C/4][2]; coef_a / coef_b: [C] (shared or global); ends with __syncthreads when SYNC
+__device__ __forceinline__ void gn_fold(const GnFoldArgs& g, int n, float* quad, float* coef_a, float* coef_b, int a_stride) {
+  const int C = g.C0 + g.C1, nq = C >> 2, nq0 = g.C0 >> 2;
+  const int pl = threadIdx.x & 7;
+  for (int qd = threadIdx.x >> 3; qd < nq; qd += blockDim.x >> 3) {
+    const bool first = qd < nq0;
+    const float* st = first ? g.st0 : g.st1;
+    const int parts = first ? g.parts0 : g.parts1, cq = first ? nq0 : nq - nq0, ql = first ? qd : qd - nq0;
+    const float2* row = reinterpret_cast<const float2*>(st) + (int64_t)n * parts * cq + ql;
+    float s = 0.f, q = 0.f;
+    for (int pp = pl; pp < parts; pp += 8) { const float2 v = __ldg(row + (int64_t)pp * cq); s += v.x; q += v.y; }
+#pragma unroll
+    for (int off = 4; off >= 1; off >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, off); q += __shfl_xor_sync(0xffffffffu, q, off); }
+    if (pl == 0) { quad[2 * qd] = s; quad[2 * qd + 1] = q; }
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+    const int cpg = C >> 5, gq0 = ((ch / cpg) * cpg) >> 2;
+    float sA = 0.f, qA = 0.f;
+    for (int k = 0; k < (cpg >> 2); ++k) { sA += quad[2 * (gq0 + k)]; qA += quad[2 * (gq0 + k) + 1]; }
+    const float inv_n = 1.0f / (float)(cpg * g.HW);
+    const float mean = sA * inv_n;
+    const float rstd = rsqrtf(fmaxf(qA * inv_n - mean * mean, 0.f) + 1e-5f);
+    float ga = __ldg(g.gamma + ch) * rstd;
+    float be = __ldg(g.beta + ch) - mean * ga;
+    if (g.ss) {
+      const float* row = g.ss + (g.ss_rows == 1 ? 0 : (int64_t)n * g.ss_stride) + g.ss_off;
+      const float sc = 1.0f + __ldg(row + ch), sh = __ldg(row + C + ch);
+      ga *= sc;
+      be = be * sc + sh;
+    }
+    coef_a[ch * a_stride] = ga;
+    coef_b[ch * a_stride] = be;
+  }
+}
+
+constexpr int kGnApplyThreads = 512;
+
+__global__ void __launch_bounds__(kGnApplyThreads) k_gn_apply(__nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ in0,
+                                                              const __nv_bfloat16* __restrict__ in1, GnFoldArgs g, int apply_silu,
+                                                              int pix_per_cta, int slices) {
+  __shared__ float quad[256];
+  __shared__ float coef_a[512], coef_b[512];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int n = blockIdx.x / slices, p0 = (blockIdx.x - n * slices) * pix_per_cta;
+  const int C = g.C0 + g.C1, nvec = C >> 3, nvec0 = g.C0 >> 3;
+  const int slots = kGnApplyThreads / nvec;
+  const int v = threadIdx.x % nvec, slot = threadIdx.x / nvec;
+  const int c = v * 8;
+  const bool first = c < g.C0;
+  const int sstride = first ? nvec0 : nvec - nvec0;
+  const uint4* src = first ? reinterpret_cast<const uint4*>(in0) + ((int64_t)n * g.HW + p0) * nvec0 + v
+                           : reinterpret_cast<const uint4*>(in1) + ((int64_t)n * g.HW + p0) * (nvec - nvec0) + (v - nvec0);
+  uint4* dst = reinterpret_cast<uint4*>(out) + ((int64_t)n * g.HW + p0) * nvec + v;
+  constexpr int U = 4;
+  int p = slot;
+  // the first batch of loads does not depend on the coefficients: issue it before the fold so HBM latency overlaps it
+  uint4 raw[U];
+  const bool pre = slot < slots && p + (U - 1) * slots < pix_per_cta;
+  if (pre) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) raw[u] = ld_stream_u4(src + (int64_t)(p + u * slots) * sstride);
+  }
+  gn_fold(g, n, quad, coef_a, coef_b, 1);
+  __syncthreads();
+  if (slot >= slots) return;
+  float a[8], b[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { a[e] = coef_a[c + e]; b[e] = coef_b[c + e]; }
+  for (bool have = pre; p + (U - 1) * slots < pix_per_cta; p += U * slots, have = false) {
+    if (!have) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) raw[u] = ld_stream_u4(src + (int64_t)(p + u * slots) * sstride);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float x[8];
+      unpack8(raw[u], x);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { x[e] = fmaf(x[e], a[e], b[e]); if (apply_silu) x[e] = silu_f(x[e]); }
+      dst[(int64_t)(p + u * slots) * nvec] = pack8(x);
+    }
+  }
+  for (; p < pix_per_cta; p += slots) {
+    float x[8];
+    unpack8(ld_stream_u4(src + (int64_t)p * sstride), x);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { x[e] = fmaf(x[e], a[e], b[e]); if (apply_silu) x[e] = silu_f(x[e]); }
+    dst[(int64_t)p * nvec] = pack8(x);
+  }
+}
+
+// coefficient table only ([B][C] float2 = (a, b)), for convolutions that normalise their input on load
+__global__ void __launch_bounds__(256) k_gn_fold(float2* __restrict__ ab, GnFoldArgs g) {
+  __shared__ float quad[256];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int C = g.C0 + g.C1;
+  float* base = reinterpret_cast<float*>(ab + (int64_t)blockIdx.x * C);
+  gn_fold(g, blockIdx.x, quad, base, base + 1, 2);
+}
+
+// ------------------------------------------------------------------------------------------------
 constexpr int kGnClusterSmemData = 96 * 1024;
 
 __device__ __forceinline__ uint32_t gn_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -321,8 +440,9 @@ constexpr int kConvInRows = 4;
 
 __global__ void __launch_bounds__(256) k_conv_in(__nv_bfloat16* __restrict__ out, const float* __restrict__ x,
                                                  const float* __restrict__ wT, const float* __restrict__ bias, int C_in, int C_out,
-                                                 int H, int W) {
+                                                 int H, int W, float* __restrict__ stats) {
   extern __shared__ float sm[];
+  __shared__ float s_red[8][32][2];  // per warp, per channel quad: (sum, sum of squares) -- GroupNorm statistics of the output
   const int K = C_in * 9;
   float* s_w = sm;                    // [K][C_out]
   float* s_b = s_w + K * C_out;       // [C_out]
@@ -379,6 +499,22 @@ __global__ void __launch_bounds__(256) k_conv_in(__nv_bfloat16* __restrict__ out
         }
       }
     }
+    if (stats) {  // launch guarantees a single pass of this loop (W * nsb <= 32): quad index = j * 8 + gq
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float sA = 0.f, qA = 0.f;
+#pragma unroll
+        for (int r = 0; r < kConvInRows; ++r) {
+          if (y0 + r < H) {
+            sA += (acc[r][j][0] + acc[r][j][1]) + (acc[r][j][2] + acc[r][j][3]);
+            qA += fmaf(acc[r][j][0], acc[r][j][0], acc[r][j][1] * acc[r][j][1]) + fmaf(acc[r][j][2], acc[r][j][2], acc[r][j][3] * acc[r][j][3]);
+          }
+        }
+        sA += __shfl_xor_sync(0xffffffffu, sA, 8); qA += __shfl_xor_sync(0xffffffffu, qA, 8);
+        sA += __shfl_xor_sync(0xffffffffu, sA, 16); qA += __shfl_xor_sync(0xffffffffu, qA, 16);
+        if ((threadIdx.x & 31) < 8) { s_red[threadIdx.x >> 5][j * 8 + gq][0] = sA; s_red[threadIdx.x >> 5][j * 8 + gq][1] = qA; }
+      }
+    }
 #pragma unroll
     for (int r = 0; r < kConvInRows; ++r) {
       if (y0 + r >= H) continue;
@@ -392,6 +528,16 @@ __global__ void __launch_bounds__(256) k_conv_in(__nv_bfloat16* __restrict__ out
           *reinterpret_cast<uint2*>(dst + (sb * 4 + j) * 32) = o;
         }
       }
+    }
+  }
+  if (stats) {
+    __syncthreads();
+    const int nq = C_out >> 2, warps_used = (W * 8) >> 5;
+    if ((int)threadIdx.x < 2 * nq) {
+      const int qd = threadIdx.x >> 1, which = threadIdx.x & 1;
+      float a = 0.f;
+      for (int w = 0; w < warps_used; ++w) a += s_red[w][qd][which];
+      stats[(((int64_t)n * bands + (blockIdx.x % bands)) * nq + qd) * 2 + which] = a;
     }
   }
 }
@@ -519,6 +665,41 @@ int dlpm_b200_groupnorm_silu(void* out, const void* in0, int C0, const void* in1
   return DLPM_OK;
 }
 
+int dlpm_b200_groupnorm_from_stats(void* out, const void* in0, int C0, const float* stats0, int parts0, const void* in1, int C1,
+                                   const float* stats1, int parts1, int64_t B, int HW, const float* gamma, const float* beta,
+                                   const float* ss, int ss_rows, int64_t ss_stride, int64_t ss_off, int apply_silu, void* stream) {
+  DLPM_REQUIRE(out && in0 && stats0 && gamma && beta && parts0 >= 1, "groupnorm_from_stats: NULL tensor");
+  DLPM_REQUIRE((in1 == nullptr) == (C1 == 0) && (in1 == nullptr) == (stats1 == nullptr), "groupnorm_from_stats: in1 / C1 / stats1 mismatch");
+  const int C = C0 + C1;
+  DLPM_REQUIRE(C0 % 8 == 0 && C1 % 8 == 0 && C % 128 == 0 && C <= 512, "groupnorm_from_stats: total channels must be a multiple of 128 (<= 512)");
+  DLPM_REQUIRE(B >= 0 && HW >= 1 && B < (1ll << 24), "groupnorm_from_stats: bad sizes");
+  DLPM_REQUIRE(!ss || ss_rows == 1 || ss_rows == B, "groupnorm_from_stats: ss_rows must be 1 or B");
+  if (B == 0) return DLPM_OK;
+  int slices = 1;
+  while (slices * 2 <= 64 && HW % (slices * 2) == 0 && (int64_t)(HW / (slices * 2)) * C >= 32768) slices *= 2;
+  GnFoldArgs g{stats0, parts0, C0, stats1, parts1, C1, HW, gamma, beta, ss, ss_rows, ss_stride, ss_off};
+  cudaError_t e = launch_ex(k_gn_apply, dim3((unsigned)(B * slices)), dim3(kGnApplyThreads), 0, (cudaStream_t)stream, 1,
+                            reinterpret_cast<__nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(in0),
+                            reinterpret_cast<const __nv_bfloat16*>(in1), g, apply_silu, HW / slices, slices);
+  if (e != cudaSuccess) return cuda_fail(e, "groupnorm_from_stats launch");
+  return DLPM_OK;
+}
+
+int dlpm_b200_groupnorm_fold(float* ab, int C0, const float* stats0, int parts0, int C1, const float* stats1, int parts1, int64_t B,
+                             int HW, const float* gamma, const float* beta, const float* ss, int ss_rows, int64_t ss_stride,
+                             int64_t ss_off, void* stream) {
+  DLPM_REQUIRE(ab && stats0 && gamma && beta && parts0 >= 1, "groupnorm_fold: NULL tensor");
+  DLPM_REQUIRE((C1 == 0) == (stats1 == nullptr), "groupnorm_fold: C1 / stats1 mismatch");
+  const int C = C0 + C1;
+  DLPM_REQUIRE(C0 % 8 == 0 && C1 % 8 == 0 && C % 128 == 0 && C <= 512, "groupnorm_fold: total channels must be a multiple of 128 (<= 512)");
+  DLPM_REQUIRE(B >= 0 && HW >= 1 && B < (1ll << 31), "groupnorm_fold: bad sizes");
+  if (B == 0) return DLPM_OK;
+  GnFoldArgs g{stats0, parts0, C0, stats1, parts1, C1, HW, gamma, beta, ss, ss_rows, ss_stride, ss_off};
+  cudaError_t e = launch_ex(k_gn_fold, dim3((unsigned)B), dim3(256), 0, (cudaStream_t)stream, 1, reinterpret_cast<float2*>(ab), g);
+  if (e != cudaSuccess) return cuda_fail(e, "groupnorm_fold launch");
+  return DLPM_OK;
+}
+
 int dlpm_b200_attention(void* out, const void* qkv, int64_t B, int L, int C, int heads, void* stream) {
   DLPM_REQUIRE(out && qkv, "attention: NULL tensor");
   DLPM_REQUIRE(heads >= 1 && C % heads == 0 && L >= 1 && L <= 1024, "attention: bad shape");
@@ -550,6 +731,14 @@ int dlpm_b200_attention(void* out, const void* qkv, int64_t B, int L, int C, int
 
 int dlpm_b200_conv_in(void* out, const float* x, const float* wT, const float* bias, int64_t B, int C_in, int C_out, int H, int W,
                       void* stream) {
+  return dlpm_b200_conv_in_stats(out, x, wT, bias, B, C_in, C_out, H, W, nullptr, nullptr, stream);
+}
+
+int dlpm_b200_conv_in_stats(void* out, const float* x, const float* wT, const float* bias, int64_t B, int C_in, int C_out, int H, int W,
+                            float* stats, int* stats_parts, void* stream) {
+  if (stats_parts) *stats_parts = (W <= 32 && W % 4 == 0 && C_out <= 128) ? (H + kConvInRows - 1) / kConvInRows : 0;
+  if (stats_parts && !stats) return DLPM_OK;
+  DLPM_REQUIRE(!stats || (W <= 32 && W % 4 == 0 && C_out <= 128), "conv_in_stats: this shape cannot emit GroupNorm statistics");
   DLPM_REQUIRE(out && x && wT && bias, "conv_in: NULL tensor");
   DLPM_REQUIRE(C_in >= 1 && C_in <= 4 && C_out % 32 == 0 && C_out <= 512, "conv_in: C_in <= 4, C_out multiple of 32 (<= 512)");
   const int bands = (H + kConvInRows - 1) / kConvInRows;
@@ -564,7 +753,7 @@ int dlpm_b200_conv_in(void* out, const float* x, const float* wT, const float* b
   }
   DLPM_REQUIRE(smem <= 96 * 1024, "conv_in: weights do not fit in shared memory");
   cudaError_t e2 = launch_ex(k_conv_in, dim3((unsigned)(B * bands)), dim3(256), smem, (cudaStream_t)stream, 1,
-                             reinterpret_cast<__nv_bfloat16*>(out), x, wT, bias, C_in, C_out, H, W);
+                             reinterpret_cast<__nv_bfloat16*>(out), x, wT, bias, C_in, C_out, H, W, stats);
   if (e2 != cudaSuccess) return cuda_fail(e2, "conv_in launch");
   return DLPM_OK;
 }

@@ -30,6 +30,18 @@ int dlpm_b200_conv2d(const void* in, const void* w, const float* bias, const voi
                      int C_s1, const void* residual, void* out, int out_mode, int64_t B, int H, int W, int C_in,
                      int C_out, int ksize, int stride, void* stream);
 
+/* K5 with the GroupNorm fusion hooks the UNet engine uses.  Same convolution as dlpm_b200_conv2d, plus:
+ *   stats_parts  if non-NULL, receives the number of partial-statistics rows per image this shape emits (0 = the shape
+ *                cannot emit statistics: tiles spanning several images, fp32 output, C_out < 32)
+ *   stats        NULL, or fp32 [B][*stats_parts][C_out/4][2]: the epilogue writes, per row and per QUAD of output
+ *                channels, (sum, sum of squares) of the fp32 results it is storing -- the input of
+ *                dlpm_b200_groupnorm_from_stats / dlpm_b200_groupnorm_fold, so that the GroupNorm that follows the
+ *                convolution (unet.py:141,153,433) needs no statistics pass over the tensor.
+ * Call once with stats == NULL to size the buffer. */
+int dlpm_b200_conv2d_stats(const void* in, const void* w, const float* bias, const void* skip0, int C_s0, const void* skip1,
+                           int C_s1, const void* residual, void* out, int out_mode, int64_t B, int H, int W, int C_in,
+                           int C_out, int ksize, int stride, float* stats, int* stats_parts, void* stream);
+
 /* Tuning / debugging knobs.  "conv_cta_group": 0 = automatic (CTA pairs with tcgen05 cta_group::2 when the problem has
  * enough tiles), 1 = always single-CTA MMAs, 2 = always CTA pairs.  "conv_tall": 1 (default) lets 3x3 stride-1 convs with
  * narrow output tiles load one (rows+2)-tall activation box per horizontal tap and reuse it for the three vertical taps,
@@ -45,6 +57,18 @@ int dlpm_b200_groupnorm_silu(void* out, const void* in0, int C0, const void* in1
                              const float* gamma, const float* beta, const float* ss, int ss_rows, int64_t ss_stride,
                              int64_t ss_off, int apply_silu, void* stream);
 
+/* K6 from convolution-epilogue statistics (dlpm_b200_conv2d_stats): same result as dlpm_b200_groupnorm_silu over
+ * [in0 | in1], but the statistics come from stats0 / stats1 (partial rows of the two producers, parts0 / parts1 rows per
+ * image) and the tensor is streamed exactly once.  Total channels must be a multiple of 128 (group = multiple of 4). */
+int dlpm_b200_groupnorm_from_stats(void* out, const void* in0, int C0, const float* stats0, int parts0, const void* in1, int C1,
+                                   const float* stats1, int parts1, int64_t B, int HW, const float* gamma, const float* beta,
+                                   const float* ss, int ss_rows, int64_t ss_stride, int64_t ss_off, int apply_silu, void* stream);
+
+/* Coefficient table only: ab fp32 [B][C0+C1][2] with GN(x)*(1+scale)+shift == ab[.,c,0] * x + ab[.,c,1]. */
+int dlpm_b200_groupnorm_fold(float* ab, int C0, const float* stats0, int parts0, int C1, const float* stats1, int parts1, int64_t B,
+                             int HW, const float* gamma, const float* beta, const float* ss, int ss_rows, int64_t ss_stride,
+                             int64_t ss_off, void* stream);
+
 /* K7. QKVAttention (unet.py:231-250): qkv NHWC bf16 [B, L, 3C] with the reference's channel order (per head:
  * q, k, v blocks of C/heads channels), out NHWC bf16 [B, L, C].  L <= 1024, C/heads <= 64. */
 int dlpm_b200_attention(void* out, const void* qkv, int64_t B, int L, int C, int heads, void* stream);
@@ -53,6 +77,11 @@ int dlpm_b200_attention(void* out, const void* qkv, int64_t B, int L, int C, int
  * wT fp32 in-major [C_in*9][C_out] (= conv weight [C_out][C_in][3][3] reshaped to [C_out][C_in*9] and transposed). */
 int dlpm_b200_conv_in(void* out, const float* x, const float* wT, const float* bias, int64_t B, int C_in, int C_out, int H,
                       int W, void* stream);
+
+/* Input conv that also leaves GroupNorm partial statistics of its output (same layout and protocol as
+ * dlpm_b200_conv2d_stats: fp32 [B][*stats_parts][C_out/4][2]; stats == NULL with stats_parts != NULL only sizes). */
+int dlpm_b200_conv_in_stats(void* out, const float* x, const float* wT, const float* bias, int64_t B, int C_in, int C_out,
+                            int H, int W, float* stats, int* stats_parts, void* stream);
 
 /* Nearest x2 upsample (unet.py:73), NHWC bf16 [B,H,W,C] -> [B,2H,2W,C]. */
 int dlpm_b200_upsample2x(void* out, const void* in, int64_t B, int H, int W, int C, void* stream);

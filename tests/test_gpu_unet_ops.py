@@ -175,6 +175,18 @@ def test_conv_in_upsample_time_embedding(L):
     xd, wd, bd = x.cuda(), w.reshape(128, -1).t().contiguous().cuda(), b.cuda()
     L.call("dlpm_b200_conv_in", L.ptr(out), L.ptr(xd), L.ptr(wd), L.ptr(bd), B, 3, 128, H, H, L.stream_ptr())
     np.testing.assert_allclose(from_nhwc(out).numpy(), F.conv2d(x, w, b, padding=1).numpy(), rtol=1e-2, atol=1e-2)
+    # the same conv leaving GroupNorm partial statistics (per 4-row band, per channel quad)
+    import ctypes
+    parts = ctypes.c_int(0)
+    L.call("dlpm_b200_conv_in_stats", None, None, None, None, B, 3, 128, H, H, None, ctypes.byref(parts), L.stream_ptr())
+    assert parts.value == H // 4
+    st = torch.full((B, parts.value, 32, 2), float("nan"), device="cuda")
+    out2 = torch.zeros_like(out)
+    L.call("dlpm_b200_conv_in_stats", L.ptr(out2), L.ptr(xd), L.ptr(wd), L.ptr(bd), B, 3, 128, H, H, L.ptr(st), None, L.stream_ptr())
+    assert torch.equal(out, out2)
+    ref = F.conv2d(x, w, b, padding=1).permute(0, 2, 3, 1).reshape(B, H * H, 32, 4)
+    np.testing.assert_allclose(st.sum(1)[..., 0].cpu().numpy(), ref.sum((1, 3)).numpy(), rtol=1e-3, atol=1e-2)
+    np.testing.assert_allclose(st.sum(1)[..., 1].cpu().numpy(), (ref * ref).sum((1, 3)).numpy(), rtol=1e-3, atol=1e-2)
     # upsample
     y = rnd(B, 64, 8, 8, seed=8)
     up = torch.zeros(B, 16, 16, 64, device="cuda", dtype=torch.bfloat16)
@@ -204,3 +216,69 @@ def test_conv_in_upsample_time_embedding(L):
     L.call("dlpm_b200_time_embedding", L.ptr(ss1), L.ptr(semb), None, L.ptr(td), 0.001, 1, mc, sst, L.ptr(w0T), L.ptr(b0d),
            L.ptr(w2T), L.ptr(b2d), L.ptr(waT), L.ptr(bad), L.stream_ptr())
     np.testing.assert_allclose(ss1.cpu().numpy()[0], want.numpy()[0], rtol=1e-4, atol=1e-4)
+
+
+STATS_CASES = [
+    # B, H, C_in, C_out, stride, C1 (second GroupNorm source: a plain tensor through its own conv), ss
+    (3, 32, 128, 128, 1, 0, True),     # tall, two sub-tiles per CTA
+    (5, 16, 256, 256, 1, 0, False),    # tall N = 256 pairs / single CTAs
+    (2, 32, 128, 128, 2, 0, True),     # Downsample conv emits statistics too
+    (3, 32, 128, 256, 1, 128, True),   # concat 256 + 128 -> groups of 12 channels straddle the two sources
+    (2, 16, 256, 256, 1, 256, False),
+    (5, 8, 256, 256, 1, 0, True),      # two images per tile (odd batch: masked tail): one statistics row per epilogue warp
+    (3, 8, 256, 256, 1, 256, False),
+]
+
+
+@pytest.mark.parametrize("B,H,C_in,C_out,stride,C1,ss", STATS_CASES)
+def test_conv_epilogue_statistics_feed_groupnorm(L, cta_group, B, H, C_in, C_out, stride, C1, ss):
+    """conv2d_stats leaves per-quad (sum, sum of squares) partial rows; groupnorm_from_stats / groupnorm_fold must
+    reproduce GroupNorm32 (+ scale-shift, SiLU) of the stored tensor without a statistics pass."""
+    import ctypes
+
+    def conv_with_stats(x, C_o, seed):
+        Bc, Ci, Hc, _ = x.shape
+        w = rnd(C_o, Ci, 3, 3, scale=1.0 / math.sqrt(Ci * 9), seed=seed)
+        b = torch.randn(C_o) * 0.1
+        wd, bd, xd = bf(w.permute(0, 2, 3, 1).reshape(C_o, -1)).contiguous().cuda(), b.cuda(), nhwc(x)
+        Ho = Hc // stride
+        out = torch.zeros(Bc, Ho, Ho, C_o, device="cuda", dtype=torch.bfloat16)
+        parts = ctypes.c_int(0)
+        args = (L.ptr(xd), L.ptr(wd), L.ptr(bd), None, 0, None, 0, None, L.ptr(out), 0, Bc, Hc, Hc, Ci, C_o, 3, stride)
+        L.call("dlpm_b200_conv2d_stats", *args, None, ctypes.byref(parts), L.stream_ptr())
+        assert parts.value > 0
+        st = torch.full((Bc, parts.value, C_o // 4, 2), float("nan"), device="cuda")
+        L.call("dlpm_b200_conv2d_stats", *args, L.ptr(st), ctypes.byref(parts), L.stream_ptr())
+        torch.cuda.synchronize()
+        return out, st, parts.value
+
+    x = rnd(B, C_in, H, H, seed=11)
+    y0, st0, p0 = conv_with_stats(x, C_out, 1)
+    Ho = H // stride
+    # the partial rows add up to the per-quad sums of the stored tensor (fp32 values before the bf16 rounding)
+    yq = y0.float().reshape(B, Ho * Ho, C_out // 4, 4)
+    tot = st0.sum(1).cpu()
+    assert torch.isfinite(tot).all()
+    np.testing.assert_allclose(tot[..., 0].numpy(), yq.sum((1, 3)).cpu().numpy(), rtol=2e-2, atol=0.02 * Ho * Ho ** 0.5)
+    np.testing.assert_allclose(tot[..., 1].numpy(), (yq * yq).sum((1, 3)).cpu().numpy(), rtol=2e-2, atol=1.0)
+    y1 = st1 = None
+    p1 = 0
+    if C1:
+        y1, st1, p1 = conv_with_stats(rnd(B, 128 if H > 8 else 256, H, H, seed=12) * 1.7, C1, 2)
+    C = C_out + C1
+    gamma, beta = (1 + 0.1 * torch.randn(C)).cuda(), (0.1 * torch.randn(C)).cuda()
+    table = (torch.randn(B, 2 * C + 3) * 0.3).cuda()
+    want = torch.zeros(B, Ho, Ho, C, device="cuda", dtype=torch.bfloat16)
+    got = torch.zeros_like(want)
+    tail = (L.ptr(gamma), L.ptr(beta), L.ptr(table) if ss else None, B, table.shape[1], 2)
+    L.call("dlpm_b200_groupnorm_silu", L.ptr(want), L.ptr(y0), C_out, L.ptr(y1), C1, B, Ho * Ho, *tail, 1, L.stream_ptr())
+    L.call("dlpm_b200_groupnorm_from_stats", L.ptr(got), L.ptr(y0), C_out, L.ptr(st0), p0, L.ptr(y1), C1, L.ptr(st1), p1, B,
+           Ho * Ho, *tail, 1, L.stream_ptr())
+    ab = torch.zeros(B, C, 2, device="cuda")
+    L.call("dlpm_b200_groupnorm_fold", L.ptr(ab), C_out, L.ptr(st0), p0, C1, L.ptr(st1), p1, B, Ho * Ho, *tail, L.stream_ptr())
+    torch.cuda.synchronize()
+    # statistics of the unrounded fp32 conv results vs statistics of the bf16 tensor: well inside the bf16 bar
+    np.testing.assert_allclose(got.float().cpu().numpy(), want.float().cpu().numpy(), rtol=1.5e-2, atol=1.5e-2)
+    yc = torch.cat([y0, y1], -1).float() if C1 else y0.float()
+    z = yc * ab[:, None, None, :, 0] + ab[:, None, None, :, 1]
+    np.testing.assert_allclose((z * torch.sigmoid(z)).cpu().numpy(), want.float().cpu().numpy(), rtol=1.5e-2, atol=1.5e-2)
