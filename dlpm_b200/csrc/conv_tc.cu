@@ -29,6 +29,8 @@ using namespace tc;
 
 constexpr int kMaxStages = 8;
 constexpr int kConvThreads = 256;
+constexpr int kConvThreadsXF = 512;  // + warps 8-15: the eight transform warps (two per SM sub-partition)
+constexpr int kXfWarps = 8;
 constexpr int kSmemBudget = 220 * 1024;  // operand ring; barriers + alignment slack come on top (227 KB per CTA)
 
 struct ConvKParams {
@@ -39,12 +41,15 @@ struct ConvKParams {
   int msub;               // 2: a CTA owns two vertically adjacent 128-pixel sub-tiles fed by ONE (2*Hb+2)-row box and the same
                           //    weight tiles (tall mode only): weight traffic per pixel halves, halo overhead 1.5x -> 1.25x
   int n_par, c_out_pad;   // n_par = 4: the four output-parity 2x2 convs of a folded upsample+conv3x3 share one launch
+  int l2_prefetch, xf_dbg;
   int tall, stage_bytes;  // tall: one (Hb+2)-row activation box per (channel block, dx) serves the three dy taps
   int64_t B;
   int C_out, C_out_real, out_mode;
   const float* bias;
   const __nv_bfloat16* residual;
   void* out;
+  const float2* ab;       // XF kernels: GroupNorm coefficients of the main input, [B][c_in_total] (a/2, b/2) pairs
+  int c0_blocks, c_in_total;  // XF: channel blocks served by the first main source (tmA), the rest come from tmA2
   float* stats;           // GroupNorm partial sums of the output [B][stats_parts][C_out/4][2], or nullptr
   int stats_parts, units_per_img, stats_wpi;  // rows per image, work units per image, epilogue warps per image and unit
 };
@@ -55,9 +60,17 @@ struct ConvKParams {
 // shared-memory operand bandwidth per SM (the limiter of the N = 128 layers).  The leader CTA (rank 0) issues the MMAs;
 // TMA completions of both CTAs are signalled on the leader's "full" barrier, tcgen05.commit multicasts the "empty" /
 // "accumulator ready" arrivals to both CTAs, and both epilogues arrive remotely on the leader's "accumulator free" barrier.
-template <int BLOCK_N, int BLOCK_K, int CG, int KS>
-__global__ void __launch_bounds__(kConvThreads, 1)
-k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmS0,
+//
+// XF = true ("normalise on load", tall mode only): the activation tensor is the RAW input of GroupNorm + SiLU
+// (unet.py:141-143,153-157,433-435) and the normalised tensor never exists in memory.  Eight extra warps rewrite every
+// activation box in shared memory between its TMA arrival and its MMAs:  x -> silu(a[n,c] * x + b[n,c])  (coefficients
+// from the conv-epilogue statistics, unet_ops.cu k_gn_fold), forcing the zero padding back to zero.  The main input may
+// be the virtual concatenation of two tensors (tmA | tmA2).  Barrier chain per stage:
+//   TMA(A) -> fullA (local) -> transform warps -> xf (leader, 8 x CG arrivals) -+-> MMA -> empty
+//   TMA(B) -> full (leader) ----------------------------------------------------+
+template <int BLOCK_N, int BLOCK_K, int CG, int KS, bool XF>
+__global__ void __launch_bounds__(XF ? kConvThreadsXF : kConvThreads, 1)
+k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmS0,
           const __grid_constant__ CUtensorMap tmS1, const __grid_constant__ CUtensorMap tmB, const ConvKParams p) {
   constexpr int A_BYTES = 128 * BLOCK_K * 2;
   constexpr int B_ROWS = BLOCK_N / CG;
@@ -78,7 +91,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + kMaxStages;
-  uint64_t* tfull_bar = empty_bar + kMaxStages;
+  uint64_t* fullA_bar = empty_bar + kMaxStages;  // XF only
+  uint64_t* xf_bar = fullA_bar + kMaxStages;     // XF only
+  uint64_t* tfull_bar = xf_bar + kMaxStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
@@ -97,11 +112,16 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    if (XF && p.c0_blocks < p.cin_blocks) prefetch_tmap(&tmA2);
     if (p.s0_blocks) prefetch_tmap(&tmS0);
     if (p.s1_blocks) prefetch_tmap(&tmS1);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, 1);
+      if (XF) { mbar_init(fullA_bar + s, 1); mbar_init(xf_bar + s, kXfWarps * CG); }
+    }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar + a, 1); mbar_init(tempty_bar + a, 4 * CG); }
     fence_barrier_init();
   }
@@ -133,12 +153,26 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (p.tall) {
           const int a_tall_bytes = (msub * p.Hb + 2) * p.Wb * BLOCK_K * 2;
           const int n_sb = 3 * p.cin_blocks + p.s0_blocks + p.s1_blocks;
+          if (p.l2_prefetch && item + item_stride < n_items) {
+            // pull the NEXT work item's activation boxes from HBM into L2 now: its TMA loads then see L2 latency only
+            const int it2 = (item + item_stride) % items_per_par;
+            const int mt2 = ((it2 / p.n_n_tiles) * CG + (int)cta_rank) * msub;
+            const int n2 = mt2 / p.tiles_per_img, h2 = (mt2 - n2 * p.tiles_per_img) * p.Hb;
+            if (it2 % p.n_n_tiles == 0 || p.n_n_tiles == 1) {
+              for (int cblk = 0; cblk < p.cin_blocks; ++cblk) {
+                const bool src0 = !XF || cblk < p.c0_blocks;
+                tma_prefetch_4d(src0 ? &tmA : &tmA2, (src0 ? cblk : cblk - p.c0_blocks) * BLOCK_K, 0, h2 - 1, n2);
+              }
+            }
+          }
           for (int sb = 0; sb < n_sb; ++sb) {
             mbar_wait(empty_bar + stage, phase ^ 1);
             uint8_t* a_dst = smem + stage * STAGE_BYTES;
             uint8_t* b_dst = a_dst + a_tall_bytes;
             const bool main_part = sb < 3 * p.cin_blocks;
-            const int bytes = main_part ? a_tall_bytes + 3 * B_BYTES : msub * A_BYTES + B_BYTES;
+            const int a_bytes = main_part ? a_tall_bytes : msub * A_BYTES, b_bytes = main_part ? 3 * B_BYTES : B_BYTES;
+            // XF: activations complete on this CTA's own fullA barrier (its transform warps wait there), weights on full
+            const int bytes = XF ? b_bytes : a_bytes + b_bytes;
             uint32_t lead_full = 0;
             if (CG == 2) {
               lead_full = mapa_u32(smem_u32(full_bar + stage), 0);
@@ -146,10 +180,14 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             } else {
               mbar_expect_tx(full_bar + stage, bytes);
             }
+            if (XF) mbar_expect_tx(fullA_bar + stage, a_bytes);
             const int brow = brow0;
             if (main_part) {
               const int cblk = sb / 3, dxi = sb - cblk * 3;
-              if (CG == 2) tma_load_4d_pair(&tmA, lead_full, a_dst, cblk * BLOCK_K, dxi - 1, h0 - 1, n0);
+              if (XF) {
+                const bool src0 = cblk < p.c0_blocks;
+                tma_load_4d(src0 ? &tmA : &tmA2, fullA_bar + stage, a_dst, (src0 ? cblk : cblk - p.c0_blocks) * BLOCK_K, dxi - 1, h0 - 1, n0);
+              } else if (CG == 2) tma_load_4d_pair(&tmA, lead_full, a_dst, cblk * BLOCK_K, dxi - 1, h0 - 1, n0);
               else tma_load_4d(&tmA, full_bar + stage, a_dst, cblk * BLOCK_K, dxi - 1, h0 - 1, n0);
 #pragma unroll
               for (int j = 0; j < 3; ++j) {
@@ -162,13 +200,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               const CUtensorMap* map = e < p.s0_blocks ? &tmS0 : &tmS1;
               const int c_a = (e < p.s0_blocks ? e : e - p.s0_blocks) * BLOCK_K;
               const int kcol = (main_blocks + e) * BLOCK_K;
-              if (CG == 2) {
-                tma_load_4d_pair(map, lead_full, a_dst, c_a, 0, h0, n0);
-                tma_load_2d_pair(&tmB, lead_full, b_dst, kcol, brow);
-              } else {
-                tma_load_4d(map, full_bar + stage, a_dst, c_a, 0, h0, n0);
-                tma_load_2d(&tmB, full_bar + stage, b_dst, kcol, brow);
-              }
+              if (XF) tma_load_4d(map, fullA_bar + stage, a_dst, c_a, 0, h0, n0);
+              else if (CG == 2) tma_load_4d_pair(map, lead_full, a_dst, c_a, 0, h0, n0);
+              else tma_load_4d(map, full_bar + stage, a_dst, c_a, 0, h0, n0);
+              if (CG == 2) tma_load_2d_pair(&tmB, lead_full, b_dst, kcol, brow);
+              else tma_load_2d(&tmB, full_bar + stage, b_dst, kcol, brow);
             }
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
@@ -230,6 +266,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           const int n_sb = 3 * p.cin_blocks + p.s0_blocks + p.s1_blocks;
           for (int sb = 0; sb < n_sb; ++sb) {
             mbar_wait(full_bar + stage, phase);
+            if (XF) mbar_wait(xf_bar + stage, phase);  // activation boxes of both CTAs normalised in place
             tc_fence_after();
             const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
             const uint32_t b_addr = a_addr + a_tall_bytes;
@@ -278,7 +315,68 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (CG == 2) umma_commit_pair(tfull_bar + acc); else umma_commit(tfull_bar + acc);  // accumulator complete -> epilogue(s)
       }
     }
-  } else if (warp >= 4) {
+  } else if (XF && warp >= 8) {
+    // ===================== transform warps: GroupNorm + SiLU applied to the activation box in shared memory =====================
+    const int xt = (warp - 8) * 32 + lane;   // 0 .. 255
+    const int chunk = xt & 7, rl = xt >> 3;  // 16-byte chunk (8 channels) of a 128-byte row; 32 row lanes
+    const int box_rows = (msub * p.Hb + 2) * p.Wb;
+    const int wshift = 31 - __clz(p.Wb);
+    const int n_sb = 3 * p.cin_blocks + p.s0_blocks + p.s1_blocks;
+    const uint32_t xf_remote = CG == 2 ? mapa_u32(smem_u32(xf_bar), 0) : 0u;
+    // a thread's rows are rl, rl + 32, ...: Wb divides 32, so its pixel column and its swizzle phase never change
+    const int x_base = (rl & (p.Wb - 1)) - 1, y_step = 32 >> wshift;
+    const uint32_t row_off = (uint32_t)(rl * 128 + ((chunk ^ (rl & 7)) << 4));
+    int stage = 0; uint32_t phase = 0;
+    for (int item = first_item; item < n_items; item += item_stride) {
+      const int it_in = item % items_per_par;
+      const int mt = ((it_in / p.n_n_tiles) * CG + (int)cta_rank) * msub;
+      const int n0 = mt / p.tiles_per_img, h0 = (mt - n0 * p.tiles_per_img) * p.Hb;
+      const float4* ab_row = reinterpret_cast<const float4*>(p.ab + (int64_t)(n0 < p.B ? n0 : p.B - 1) * p.c_in_total);
+      const int y_first = h0 - 1 + (rl >> wshift);
+      for (int sb = 0; sb < n_sb; ++sb) {
+        const bool main_part = sb < 3 * p.cin_blocks;
+        const int cblk = sb / 3, dxi = sb - cblk * 3;
+        float4 co[4];  // (a, b) of this thread's 8 channels; fetched while the box is still in flight
+        if (main_part) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) co[e] = __ldg(ab_row + (cblk * (BLOCK_K / 2) + chunk * 4 + e));
+        }
+        mbar_wait(fullA_bar + stage, phase);
+        if (main_part && p.xf_dbg != 1) {
+          const bool x_ok = (unsigned)(x_base + dxi) < (unsigned)p.W_out;
+          uint8_t* ptr = smem + stage * STAGE_BYTES + row_off;
+          int y = y_first;
+#pragma unroll 5
+          for (int r = rl; r < box_rows; r += 32, ptr += 32 * 128, y += y_step) {
+            const bool inb = x_ok && (unsigned)y < (unsigned)p.H_out;
+            uint4 v = *reinterpret_cast<uint4*>(ptr);
+            uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              // silu(y) = h + h * tanh(h), h = y / 2 (the fold kernel halves the coefficients); tanh on the packed
+              // bf16x2 MUFU path (one op per two elements -- its 2^-9 error is that of the bf16 result anyway)
+              const float h0v = fmaf(__uint_as_float(w[e] << 16), co[e].x, co[e].y);
+              const float h1v = fmaf(__uint_as_float(w[e] & 0xffff0000u), co[e].z, co[e].w);
+              const __nv_bfloat162 hp = __floats2bfloat162_rn(h0v, h1v);
+              uint32_t tp;
+              asm("tanh.approx.bf16x2 %0, %1;" : "=r"(tp) : "r"(*reinterpret_cast<const uint32_t*>(&hp)));
+              const __nv_bfloat162 o = __floats2bfloat162_rn(fmaf(h0v, __uint_as_float(tp << 16), h0v),
+                                                             fmaf(h1v, __uint_as_float(tp & 0xffff0000u), h1v));
+              w[e] = inb ? *reinterpret_cast<const uint32_t*>(&o) : 0u;
+            }
+            *reinterpret_cast<uint4*>(ptr) = v;
+          }
+          if (p.xf_dbg != 2) fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        }
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_cluster(xf_remote + (uint32_t)(stage * 8));
+          else mbar_arrive(xf_bar + stage);
+        }
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
     // ===================== epilogue =====================
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     const int m = q * 32 + lane;
@@ -299,9 +397,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       if (p.out_mode == CONV_OUT_BF16_NHWC) {
         constexpr int CH = BLOCK_N >= 32 ? 32 : 16;
         // identity-skip rows are fetched BEFORE waiting for the accumulator so their HBM latency hides behind the MMAs
-        uint4 resv[MS_MAX][BLOCK_N / 8];
+        constexpr bool RES_PREFETCH = !XF;  // XF kernels run 512 threads (128 registers each): residual rows are read in place
+        uint4 resv[RES_PREFETCH ? MS_MAX : 1][RES_PREFETCH ? BLOCK_N / 8 : 1];
         const bool has_res = p.residual != nullptr && valid;
-        if (has_res) {
+        if (RES_PREFETCH && has_res) {
 #pragma unroll
           for (int sub = 0; sub < MS_MAX; ++sub) {
             if (sub < msub) {
@@ -344,7 +443,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
                   for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[j + e]) + __ldg(bias + j + e);
                   if (has_res) {
-                    const uint4 rv = resv[sub][(c0 + j) / 8];
+                    uint4 rv;
+                    if constexpr (RES_PREFETCH) rv = resv[sub][(c0 + j) / 8];
+                    else rv = __ldg(reinterpret_cast<const uint4*>(p.residual + pixs[sub] * p.C_out + col + j));
                     const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
                     for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(rp[e]); v[2 * e] += f.x; v[2 * e + 1] += f.y; }
@@ -475,11 +576,17 @@ static int encode_weight_map(CUtensorMap* m, const void* base, int rows, int64_t
 }
 
 static int g_tall256_enabled = 1;
+static int g_xf_dbg = 0;  // timing experiments only: 1 = transform warps skip the math, 2 = skip the proxy fence
+static int g_l2_prefetch = 0;  // measured: no gain (the three-stage ring already covers the HBM latency)
 
 int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, const void* skip0, int C_s0, const void* skip1,
-              int C_s1, const void* residual, void* out, int out_mode, int64_t B, int H, int W, int C_in, int C_out, ConvGeom geom,
-              int stride) {
+              int C_s1, const void* residual, void* out, int out_mode, int64_t B, int H, int W, int C_in0, int C_out, ConvGeom geom,
+              int stride, const ConvFuse* fuse) {
+  const int C_in2 = fuse ? fuse->C_in2 : 0;
+  const int C_in = C_in0 + C_in2;  // K channels per tap: the main input may be the concatenation [in | fuse->in2]
+  DLPM_REQUIRE(!fuse || (fuse->ab != nullptr && (fuse->in2 == nullptr) == (C_in2 == 0)), "conv: bad fusion descriptor");
   DLPM_REQUIRE(in && w && bias && out, "conv: NULL tensor");
+  DLPM_REQUIRE(C_in % 32 == 0 && C_in0 % 32 == 0, "conv: channel counts must be multiples of 32");
   DLPM_REQUIRE(geom.tap_rows >= 1 && geom.tap_rows <= 3 && geom.tap_cols >= 1 && geom.tap_cols <= 3, "conv: 1..3 taps per dimension");
   DLPM_REQUIRE(geom.out_scale == 1 || (geom.out_scale == 2 && stride == 1 && !skip0 && !skip1 && !residual &&
                                         out_mode == CONV_OUT_BF16_NHWC), "conv: strided output only for plain stride-1 convs");
@@ -491,7 +598,7 @@ int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, c
   const int H_out = H / stride, W_out = W / stride;
   DLPM_REQUIRE(W_out <= 128 && (W_out & (W_out - 1)) == 0 && (H_out & (H_out - 1)) == 0,
                "conv: output H and W must be powers of two with W <= 128");
-  const int bk = (C_in % 64 == 0 && C_s0 % 64 == 0 && C_s1 % 64 == 0) ? 64 : 32;
+  const int bk = (C_in0 % 64 == 0 && C_in2 % 64 == 0 && C_s0 % 64 == 0 && C_s1 % 64 == 0) ? 64 : 32;
   if (C_in % bk || C_s0 % bk || C_s1 % bk) { set_error("conv: channel counts must be multiples of 32 (got %d,%d,%d)", C_in, C_s0, C_s1); return DLPM_ERR_UNSUPPORTED; }
   const int C_out_pad = out_mode == CONV_OUT_F32_NCHW ? 16 : C_out;
   int bn;
@@ -536,8 +643,17 @@ int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, c
                  : ((bn >= 32 && (int64_t)((L->n_m_tiles / L->msub + 1) / 2) * L->n_n_tiles * L->n_par >= 32) ? 2 : 1);
   if (conv_cta_group_override() == 2 && bn >= 32) L->cta_group = 2;
   L->tall = (tall_geom && (bn <= 128 || (L->cta_group == 2 && g_tall256_enabled))) ? 1 : 0;
+  L->xf = fuse ? 1 : 0;
+  L->ab = fuse ? fuse->ab : nullptr;
+  L->c0_blocks = C_in0 / bk;
+  if (fuse && !(L->tall && bk == 64 && (bn == 16 || bn == 128 || bn == 256))) {
+    set_error("conv: normalise-on-load needs a 3x3 stride-1 conv with one image per tile row block, 64-channel K blocks, N in {16,128,256}");
+    return DLPM_ERR_UNSUPPORTED;
+  }
   int rc;
-  if ((rc = encode_act_map(&L->tmA, in, B, H, W, C_in, bk, L->Wb, L->tall ? L->msub * L->Hb + 2 : L->Hb, L->Nb, stride))) return rc;
+  if ((rc = encode_act_map(&L->tmA, in, B, H, W, C_in0, bk, L->Wb, L->tall ? L->msub * L->Hb + 2 : L->Hb, L->Nb, stride))) return rc;
+  L->tmA2 = L->tmA;
+  if (C_in2 && (rc = encode_act_map(&L->tmA2, fuse->in2, B, H, W, C_in2, bk, L->Wb, L->msub * L->Hb + 2, L->Nb, stride))) return rc;
   L->tmS0 = L->tmA; L->tmS1 = L->tmA;
   if (skip0 && (rc = encode_act_map(&L->tmS0, skip0, B, H_out, W_out, C_s0, bk, L->Wb, L->msub * L->Hb, L->Nb, 1))) return rc;
   if (skip1 && (rc = encode_act_map(&L->tmS1, skip1, B, H_out, W_out, C_s1, bk, L->Wb, L->msub * L->Hb, L->Nb, 1))) return rc;
@@ -571,17 +687,17 @@ int conv_cta_group_override() {
 }
 void conv_set_cta_group_override(int v) { g_cta_group_override = v; }
 
-template <int BN, int BK, int CG>
+template <int BN, int BK, int CG, bool XF>
 static int launch_t(const ConvLaunch& L, cudaStream_t stream) {
   constexpr int KS = BN <= 128 ? 2 : 1;
   const int B_BYTES = (BN / CG) * BK * 2;
   const int STAGE = L.tall ? (L.msub * L.Hb + 2) * L.Wb * BK * 2 + 3 * B_BYTES : KS * (128 * BK * 2 + B_BYTES);
   int stages = kSmemBudget / STAGE;
   if (stages > kMaxStages) stages = kMaxStages;
-  const size_t smem = (size_t)stages * STAGE + 1024 /*align*/ + (2 * kMaxStages + 4) * 8 + 16;
+  const size_t smem = (size_t)stages * STAGE + 1024 /*align*/ + (4 * kMaxStages + 4) * 8 + 16;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_conv_tc<BN, BK, CG, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemBudget + 2048));
+    cudaError_t e = cudaFuncSetAttribute(k_conv_tc<BN, BK, CG, KS, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemBudget + 2048));
     if (e != cudaSuccess) return cuda_fail(e, "conv smem attribute");
     attr_set = true;
   }
@@ -591,31 +707,40 @@ static int launch_t(const ConvLaunch& L, cudaStream_t stream) {
   p.stride = L.stride; p.taps = L.taps; p.cin_blocks = L.cin_blocks; p.s0_blocks = L.s0_blocks; p.s1_blocks = L.s1_blocks;
   p.tap_cols = L.tap_cols; p.dy0 = L.dy0; p.dx0 = L.dx0; p.out_scale = L.out_scale; p.out_oy = L.out_oy; p.out_ox = L.out_ox;
   p.H_full = L.H_full; p.W_full = L.W_full;
+  p.l2_prefetch = g_l2_prefetch; p.xf_dbg = g_xf_dbg;
   p.tall = L.tall; p.stage_bytes = STAGE; p.n_par = L.n_par; p.c_out_pad = L.c_out_pad; p.msub = L.msub;
   p.B = L.B; p.C_out = L.C_out; p.C_out_real = L.C_out_real; p.out_mode = L.out_mode;
   p.bias = L.bias; p.residual = L.residual; p.out = L.out;
+  p.ab = reinterpret_cast<const float2*>(L.ab); p.c0_blocks = L.c0_blocks; p.c_in_total = L.cin_blocks * BK;
   p.stats = L.stats; p.stats_parts = conv_stats_parts(L); p.units_per_img = L.tiles_per_img > 0 ? L.tiles_per_img / L.msub : 1;
   p.stats_wpi = L.Nb == 1 ? 4 : (L.Wb * L.Hb) / 32;
   const int n_items = ((L.n_m_tiles / L.msub + CG - 1) / CG) * L.n_n_tiles * L.n_par;
   const int max_groups = kNumSMs / CG;
   const int grid = (n_items < max_groups ? n_items : max_groups) * CG;
-  if (CG == 1) {
-    cudaError_t e = launch_ex(k_conv_tc<BN, BK, 1, KS>, dim3(grid), dim3(kConvThreads), smem, stream, 1, L.tmA, L.tmS0, L.tmS1, L.tmB, p);
-    if (e != cudaSuccess) return cuda_fail(e, "conv_tc launch");
-  } else {
-    cudaError_t e = launch_ex(k_conv_tc<BN, BK, CG, KS>, dim3(grid), dim3(kConvThreads), smem, stream, 2, L.tmA, L.tmS0, L.tmS1, L.tmB, p);
-    if (e != cudaSuccess) return cuda_fail(e, "conv_tc pair launch");
-  }
+  const int threads = XF ? kConvThreadsXF : kConvThreads;
+  cudaError_t e = launch_ex(k_conv_tc<BN, BK, CG, KS, XF>, dim3(grid), dim3(threads), smem, stream, CG, L.tmA, L.tmA2, L.tmS0, L.tmS1,
+                            L.tmB, p);
+  if (e != cudaSuccess) return cuda_fail(e, CG == 1 ? "conv_tc launch" : "conv_tc pair launch");
   return DLPM_OK;
 }
 
 int conv_launch(const ConvLaunch& L, cudaStream_t stream) {
-#define CASE(BN, BK)                                                          \
-  if (L.block_n == BN && L.block_k == BK) {                                   \
-    if (L.cta_group == 2) {                                                   \
-      if constexpr (BN >= 32) return launch_t<BN, BK, 2>(L, stream);          \
-    }                                                                         \
-    return launch_t<BN, BK, 1>(L, stream);                                    \
+#define CASE(BN, BK)                                                                \
+  if (L.block_n == BN && L.block_k == BK) {                                         \
+    if (L.xf) {                                                                     \
+      if constexpr (BK == 64 && (BN == 16 || BN == 128 || BN == 256)) {             \
+        if (L.cta_group == 2) {                                                     \
+          if constexpr (BN >= 32) return launch_t<BN, BK, 2, true>(L, stream);      \
+        }                                                                           \
+        return launch_t<BN, BK, 1, true>(L, stream);                                \
+      }                                                                             \
+      set_error("conv: no normalise-on-load kernel for tile N=%d K=%d", BN, BK);   \
+      return DLPM_ERR_UNSUPPORTED;                                                  \
+    }                                                                               \
+    if (L.cta_group == 2) {                                                         \
+      if constexpr (BN >= 32) return launch_t<BN, BK, 2, false>(L, stream);         \
+    }                                                                               \
+    return launch_t<BN, BK, 1, false>(L, stream);                                   \
   }
   CASE(256, 64) CASE(128, 64) CASE(64, 64) CASE(32, 64) CASE(16, 64)
   CASE(256, 32) CASE(128, 32) CASE(64, 32) CASE(32, 32) CASE(16, 32)
@@ -626,7 +751,7 @@ int conv_launch(const ConvLaunch& L, cudaStream_t stream) {
 
 }  // namespace dlpm
 
-namespace dlpm { void engine_set_gn_stats(bool on); }
+namespace dlpm { void engine_set_gn_stats(bool on); void engine_set_gn_fuse(int mode); }
 using namespace dlpm;
 
 int dlpm_b200_set_option(const char* name, int value) {
@@ -635,12 +760,24 @@ int dlpm_b200_set_option(const char* name, int value) {
     pdl_set_enabled(value != 0);
     return DLPM_OK;
   }
+  if (std::string(name) == "gn_fuse") {
+    engine_set_gn_fuse(value);
+    return DLPM_OK;
+  }
   if (std::string(name) == "gn_stats") {
     engine_set_gn_stats(value != 0);
     return DLPM_OK;
   }
   if (std::string(name) == "conv_msub") {
     g_msub_enabled = value != 0;
+    return DLPM_OK;
+  }
+  if (std::string(name) == "xf_dbg") {
+    g_xf_dbg = value;
+    return DLPM_OK;
+  }
+  if (std::string(name) == "conv_l2_prefetch") {
+    g_l2_prefetch = value != 0;
     return DLPM_OK;
   }
   if (std::string(name) == "conv_tall256") {
@@ -666,7 +803,7 @@ int dlpm_b200_conv2d(const void* in, const void* w, const float* bias, const voi
   DLPM_REQUIRE(ksize == 3 || ksize == 1, "conv: kernel size must be 1 or 3");
   ConvLaunch L;
   if (int rc = conv_plan(&L, in, w, bias, skip0, C_s0, skip1, C_s1, residual, out, out_mode, B, H, W, C_in, C_out,
-                         conv_geom_default(ksize), stride))
+                         conv_geom_default(ksize), stride, nullptr))
     return rc;
   return conv_launch(L, (cudaStream_t)stream);
 }
@@ -677,12 +814,30 @@ int dlpm_b200_conv2d_stats(const void* in, const void* w, const float* bias, con
   DLPM_REQUIRE(ksize == 3 || ksize == 1, "conv: kernel size must be 1 or 3");
   ConvLaunch L;
   if (int rc = conv_plan(&L, in, w, bias, skip0, C_s0, skip1, C_s1, residual, out, out_mode, B, H, W, C_in, C_out,
-                         conv_geom_default(ksize), stride))
+                         conv_geom_default(ksize), stride, nullptr))
     return rc;
   const int parts = conv_stats_parts(L);
   if (stats_parts) *stats_parts = parts;
   if (stats == nullptr) return stats_parts ? DLPM_OK : conv_launch(L, (cudaStream_t)stream);
   DLPM_REQUIRE(parts > 0, "conv2d_stats: this shape cannot emit GroupNorm statistics");
   L.stats = stats;
+  return conv_launch(L, (cudaStream_t)stream);
+}
+
+int dlpm_b200_conv2d_gn(const void* in, const void* in2, int C_in2, const float* ab, const void* w, const float* bias, const void* skip0,
+                        int C_s0, const void* skip1, int C_s1, const void* residual, void* out, int out_mode, int64_t B, int H, int W,
+                        int C_in, int C_out, float* stats, int* stats_parts, void* stream) {
+  DLPM_REQUIRE(ab != nullptr, "conv2d_gn: NULL coefficient table");
+  ConvLaunch L;
+  const ConvFuse fuse{in2, C_in2, ab};
+  if (int rc = conv_plan(&L, in, w, bias, skip0, C_s0, skip1, C_s1, residual, out, out_mode, B, H, W, C_in, C_out, conv_geom_default(3), 1,
+                         &fuse))
+    return rc;
+  const int parts = conv_stats_parts(L);
+  if (stats_parts) *stats_parts = parts;
+  if (stats) {
+    DLPM_REQUIRE(parts > 0, "conv2d_gn: this shape cannot emit GroupNorm statistics");
+    L.stats = stats;
+  }
   return conv_launch(L, (cudaStream_t)stream);
 }

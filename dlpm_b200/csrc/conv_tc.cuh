@@ -10,7 +10,8 @@ enum ConvOutMode { CONV_OUT_BF16_NHWC = 0, CONV_OUT_F32_NCHW = 1 };
 
 // Everything the launcher needs for one convolution (tensor maps are built once per plan).
 struct ConvLaunch {
-  CUtensorMap tmA, tmS0, tmS1, tmB;  // main activation, two optional 1x1 skip-conv sources, packed weights
+  CUtensorMap tmA, tmA2, tmS0, tmS1, tmB;  // main activation (+ second half of a concatenated input), two optional 1x1
+                                           // skip-conv sources, packed weights
   int block_n, block_k;              // tile N (16..256), K block in channels (64 or 32)
   int msub;                          // sub-tiles (128 pixels each) per CTA: 2 in tall mode when the image has an even tile count
   int tall;                          // 1 = one (Hb+2)-row activation box per (channel block, dx) feeds the three dy taps
@@ -31,6 +32,8 @@ struct ConvLaunch {
   const float* bias;                // [n_n_tiles * block_n] fp32
   const __nv_bfloat16* residual;    // NHWC bf16 [B, H_out, W_out, C_out] or nullptr
   void* out;
+  int xf, c0_blocks;                // normalise-on-load (GroupNorm + SiLU applied to the activation boxes in shared memory)
+  const float* ab;                  // its coefficient table [B][C_in][2] = (a/2, b/2)
   float* stats;                     // optional GroupNorm partial sums of the output (see conv_stats_parts), set by the caller
 };
 
@@ -47,9 +50,17 @@ struct ConvGeom {
 };
 inline ConvGeom conv_geom_default(int ksize) { return ConvGeom{ksize, ksize, -(ksize / 2), -(ksize / 2), 1, 0, 0, 1}; }
 
+// Normalise-on-load fusion: the conv reads the RAW GroupNorm input(s) [in | in2] and applies silu(a*x+b) per (sample, channel)
+// while the activation boxes sit in shared memory (coefficients from dlpm_b200_groupnorm_fold with half = 1).
+struct ConvFuse {
+  const void* in2;  // second half of the concatenated main input (NHWC bf16) or nullptr
+  int C_in2;
+  const float* ab;  // [B][C_in + C_in2][2]
+};
+
 int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, const void* skip0, int C_s0, const void* skip1,
               int C_s1, const void* residual, void* out, int out_mode, int64_t B, int H, int W, int C_in, int C_out, ConvGeom geom,
-              int stride);
+              int stride, const ConvFuse* fuse = nullptr);
 int conv_launch(const ConvLaunch& L, cudaStream_t stream);
 int conv_stats_parts(const ConvLaunch& L);
 int conv_cta_group_override();

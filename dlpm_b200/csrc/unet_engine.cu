@@ -22,6 +22,7 @@ struct GnLaunch {
   const float* st0 = nullptr; int parts0 = 0;
   const float* st1 = nullptr; int parts1 = 0;
   bool from_stats = false;
+  float* ab = nullptr;  // non-null: only the coefficient table is produced; the consuming conv normalises on load
 };
 
 struct Plan {  // per batch size
@@ -62,7 +63,26 @@ static int alloc_stats(UNetEngine* E, Plan* P, int64_t B, int parts, int C, floa
 }
 
 static bool g_gn_stats_enabled = true;
+static int g_gn_fuse_mode = 0;  // 0 = never (default, see DESIGN.md: the transform does not hide behind the MMAs yet), 1 = final conv only, 2 = all
 void engine_set_gn_stats(bool on) { g_gn_stats_enabled = on; }
+void engine_set_gn_fuse(int mode) { g_gn_fuse_mode = mode; }
+
+static int plan_conv(UNetEngine* E, const Op& op, int64_t B, const ConvFuse* fuse, const void* in_override, int C_in0, ConvLaunch* L) {
+  // f: 1 in, 2 out(-1 = external fp32 NCHW), 3 skip0, 4 C_s0, 5 skip1, 6 C_s1, 7 residual, 8 H, 9 W, 10 C_in, 11 C_out, 12 ksize,
+  //    13 stride, 14 w_off (bf16 elems), 15 bias_off (fp32 elems), 16 tap_rows, 17 tap_cols, 18 dy0, 19 dx0, 20 out_scale, 21 out_oy,
+  //    22 out_ox, 23 n_par
+  const void* s0 = op.f[3] >= 0 ? E->buf(op.f[3], B) : nullptr;
+  const void* s1 = op.f[5] >= 0 ? E->buf(op.f[5], B) : nullptr;
+  const void* res = op.f[7] >= 0 ? E->buf(op.f[7], B) : nullptr;
+  const bool ext = op.f[2] < 0;
+  void* out = ext ? reinterpret_cast<void*>(0x10) /*patched at launch*/ : E->buf(op.f[2], B);
+  return conv_plan(L, in_override ? in_override : E->buf(op.f[1], B), E->wb + op.f[14], E->wf + op.f[15], s0, (int)op.f[4], s1,
+                   (int)op.f[6], res, out, ext ? CONV_OUT_F32_NCHW : CONV_OUT_BF16_NHWC, B, (int)op.f[8], (int)op.f[9],
+                   in_override ? C_in0 : (int)op.f[10], (int)op.f[11],
+                   ConvGeom{(int)op.f[16], (int)op.f[17], (int)op.f[18], (int)op.f[19], (int)op.f[20], (int)op.f[21], (int)op.f[22],
+                            (int)op.f[23]},
+                   (int)op.f[13], fuse);
+}
 
 static int build_plan(UNetEngine* E, int64_t B, Plan* P) {
   P->B = B;
@@ -72,7 +92,9 @@ static int build_plan(UNetEngine* E, int64_t B, Plan* P) {
   struct BufStats { const float* st = nullptr; int parts = 0; int C = 0; };
   std::vector<BufStats> bstats(E->buf_elems.size());  // statistics of the CURRENT content of every activation buffer
   auto writes = [&](int64_t id) { if (id >= 0) bstats[id] = BufStats(); };
-  for (const Op& op : E->ops) {
+  bool conv_planned = false;  // the next OP_CONV was already planned (fused with the GroupNorm in front of it)
+  for (size_t oi = 0; oi < E->ops.size(); ++oi) {
+    const Op& op = E->ops[oi];
     const int64_t* f = op.f;
     if (f[0] == OP_CONV_IN) {  // 1 out, 2 C_in, 3 C_out, 4 H, 5 W
       writes(f[1]);
@@ -87,7 +109,7 @@ static int build_plan(UNetEngine* E, int64_t B, Plan* P) {
     }
     if (f[0] == OP_UP || f[0] == OP_ATTN) writes(f[2]);
     if (f[0] == OP_GN) {
-      // 1 in0, 2 in1, 3 out, 4 C0, 5 C1, 6 HW
+      // 1 in0, 2 in1, 3 out, 4 C0, 5 C1, 6 HW, 10 silu
       GnLaunch G;
       const BufStats& s0 = bstats[f[1]];
       const bool two = f[2] >= 0;
@@ -96,26 +118,39 @@ static int build_plan(UNetEngine* E, int64_t B, Plan* P) {
         G.from_stats = true;
         G.st0 = s0.st; G.parts0 = s0.parts;
         if (two) { G.st1 = bstats[f[2]].st; G.parts1 = bstats[f[2]].parts; }
+        // normalise-on-load: the conv that consumes this GroupNorm + SiLU reads the raw tensor(s) instead
+        if (g_gn_fuse_mode > 0 && f[10] == 1 && oi + 1 < E->ops.size()) {
+          const Op& nx = E->ops[oi + 1];
+          if (nx.f[0] == OP_CONV && nx.f[1] == f[3] && nx.f[10] == C && nx.f[12] == 3 && nx.f[13] == 1 && nx.f[20] == 1 &&
+              (nx.f[2] < 0 || (nx.f[2] != f[1] && nx.f[2] != f[2])) /* the conv must not overwrite the raw tensors it now reads */ &&
+              (g_gn_fuse_mode == 2 || nx.f[11] <= 16) /* measured: only the thin final conv hides the transform */) {
+            float* ab = nullptr;
+            cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ab), (size_t)B * C * 2 * sizeof(float));
+            if (e != cudaSuccess) return cuda_fail(e, "unet plan: coefficient table");
+            P->stats_bufs.push_back(ab);
+            E->workspace_bytes += (int64_t)B * C * 2 * sizeof(float);
+            const ConvFuse fuse{two ? E->buf(f[2], B) : nullptr, (int)f[5], ab};
+            ConvLaunch L;
+            if (plan_conv(E, nx, B, &fuse, E->buf(f[1], B), (int)f[4], &L) == DLPM_OK) {
+              G.ab = ab;
+              P->convs.push_back(L);
+              conv_planned = true;
+            }
+          }
+        }
       }
       P->gns.push_back(G);
       writes(f[3]);
     }
     if (f[0] != OP_CONV) continue;
-    // f: 1 in, 2 out(-1 = external fp32 NCHW), 3 skip0, 4 C_s0, 5 skip1, 6 C_s1, 7 residual, 8 H, 9 W, 10 C_in, 11 C_out, 12 ksize,
-    //    13 stride, 14 w_off (bf16 elems), 15 bias_off (fp32 elems), 16 tap_rows, 17 tap_cols, 18 dy0, 19 dx0, 20 out_scale, 21 out_oy,
-    //    22 out_ox, 23 n_par
-    ConvLaunch L;
-    const void* s0 = op.f[3] >= 0 ? E->buf(op.f[3], B) : nullptr;
-    const void* s1 = op.f[5] >= 0 ? E->buf(op.f[5], B) : nullptr;
-    const void* res = op.f[7] >= 0 ? E->buf(op.f[7], B) : nullptr;
     const bool ext = op.f[2] < 0;
-    void* out = ext ? reinterpret_cast<void*>(0x10) /*patched at launch*/ : E->buf(op.f[2], B);
-    int rc = conv_plan(&L, E->buf(op.f[1], B), E->wb + op.f[14], E->wf + op.f[15], s0, (int)op.f[4], s1, (int)op.f[6], res, out,
-                       ext ? CONV_OUT_F32_NCHW : CONV_OUT_BF16_NHWC, B, (int)op.f[8], (int)op.f[9], (int)op.f[10], (int)op.f[11],
-                       ConvGeom{(int)op.f[16], (int)op.f[17], (int)op.f[18], (int)op.f[19], (int)op.f[20], (int)op.f[21], (int)op.f[22],
-                                (int)op.f[23]},
-                       (int)op.f[13]);
-    if (rc) return rc;
+    if (!conv_planned) {
+      ConvLaunch L0;
+      if (int rc = plan_conv(E, op, B, nullptr, nullptr, 0, &L0)) return rc;
+      P->convs.push_back(L0);
+    }
+    conv_planned = false;
+    ConvLaunch& L = P->convs.back();
     if (!ext) {
       writes(f[2]);
       const int parts = conv_stats_parts(L);
@@ -126,7 +161,6 @@ static int build_plan(UNetEngine* E, int64_t B, Plan* P) {
         bstats[f[2]].st = st; bstats[f[2]].parts = parts; bstats[f[2]].C = L.C_out;
       }
     }
-    P->convs.push_back(L);
   }
   return DLPM_OK;
 }
@@ -211,6 +245,11 @@ int dlpm_b200_unet_forward(void* handle, const float* x, const float* t, int t_r
         break;
       case OP_GN: {  // 1 in0, 2 in1, 3 out, 4 C0, 5 C1, 6 HW, 7 gamma_off, 8 beta_off, 9 ss_off, 10 silu
         const GnLaunch& G = P.gns[gi++];
+        if (G.ab) {
+          rc = dlpm_b200_groupnorm_fold(G.ab, (int)f[4], G.st0, G.parts0, (int)f[5], G.st1, G.parts1, B, (int)f[6], E->wf + f[7],
+                                        E->wf + f[8], f[9] >= 0 ? E->ss : nullptr, rows, ss_total, f[9] >= 0 ? f[9] : 0, 1, stream);
+          break;
+        }
         if (G.from_stats) {
           rc = dlpm_b200_groupnorm_from_stats(E->buf(f[3], B), E->buf(f[1], B), (int)f[4], G.st0, G.parts0,
                                               f[2] >= 0 ? E->buf(f[2], B) : nullptr, (int)f[5], G.st1, G.parts1, B, (int)f[6],

@@ -134,6 +134,7 @@ struct GnFoldArgs {
   int HW;
   const float* gamma; const float* beta;
   const float* ss; int ss_rows; int64_t ss_stride, ss_off;
+  float out_scale;  // 1, or 0.5 for consumers that evaluate silu(y) as h + h*tanh(h) with h = y/2
 };
 
 // block-wide; quad: shared scratch [C/4][2]; coef_a / coef_b: [C] (shared or global); ends with __syncthreads when SYNC
@@ -167,8 +168,8 @@ __device__ __forceinline__ void gn_fold(const GnFoldArgs& g, int n, float* quad,
       ga *= sc;
       be = be * sc + sh;
     }
-    coef_a[ch * a_stride] = ga;
-    coef_b[ch * a_stride] = be;
+    coef_a[ch * a_stride] = ga * g.out_scale;
+    coef_b[ch * a_stride] = be * g.out_scale;
   }
 }
 
@@ -677,7 +678,7 @@ int dlpm_b200_groupnorm_from_stats(void* out, const void* in0, int C0, const flo
   if (B == 0) return DLPM_OK;
   int slices = 1;
   while (slices * 2 <= 64 && HW % (slices * 2) == 0 && (int64_t)(HW / (slices * 2)) * C >= 32768) slices *= 2;
-  GnFoldArgs g{stats0, parts0, C0, stats1, parts1, C1, HW, gamma, beta, ss, ss_rows, ss_stride, ss_off};
+  GnFoldArgs g{stats0, parts0, C0, stats1, parts1, C1, HW, gamma, beta, ss, ss_rows, ss_stride, ss_off, 1.0f};
   cudaError_t e = launch_ex(k_gn_apply, dim3((unsigned)(B * slices)), dim3(kGnApplyThreads), 0, (cudaStream_t)stream, 1,
                             reinterpret_cast<__nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(in0),
                             reinterpret_cast<const __nv_bfloat16*>(in1), g, apply_silu, HW / slices, slices);
@@ -687,14 +688,14 @@ int dlpm_b200_groupnorm_from_stats(void* out, const void* in0, int C0, const flo
 
 int dlpm_b200_groupnorm_fold(float* ab, int C0, const float* stats0, int parts0, int C1, const float* stats1, int parts1, int64_t B,
                              int HW, const float* gamma, const float* beta, const float* ss, int ss_rows, int64_t ss_stride,
-                             int64_t ss_off, void* stream) {
+                             int64_t ss_off, int half, void* stream) {
   DLPM_REQUIRE(ab && stats0 && gamma && beta && parts0 >= 1, "groupnorm_fold: NULL tensor");
   DLPM_REQUIRE((C1 == 0) == (stats1 == nullptr), "groupnorm_fold: C1 / stats1 mismatch");
   const int C = C0 + C1;
   DLPM_REQUIRE(C0 % 8 == 0 && C1 % 8 == 0 && C % 128 == 0 && C <= 512, "groupnorm_fold: total channels must be a multiple of 128 (<= 512)");
   DLPM_REQUIRE(B >= 0 && HW >= 1 && B < (1ll << 31), "groupnorm_fold: bad sizes");
   if (B == 0) return DLPM_OK;
-  GnFoldArgs g{stats0, parts0, C0, stats1, parts1, C1, HW, gamma, beta, ss, ss_rows, ss_stride, ss_off};
+  GnFoldArgs g{stats0, parts0, C0, stats1, parts1, C1, HW, gamma, beta, ss, ss_rows, ss_stride, ss_off, half ? 0.5f : 1.0f};
   cudaError_t e = launch_ex(k_gn_fold, dim3((unsigned)B), dim3(256), 0, (cudaStream_t)stream, 1, reinterpret_cast<float2*>(ab), g);
   if (e != cudaSuccess) return cuda_fail(e, "groupnorm_fold launch");
   return DLPM_OK;

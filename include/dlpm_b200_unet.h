@@ -64,10 +64,23 @@ int dlpm_b200_groupnorm_from_stats(void* out, const void* in0, int C0, const flo
                                    const float* stats1, int parts1, int64_t B, int HW, const float* gamma, const float* beta,
                                    const float* ss, int ss_rows, int64_t ss_stride, int64_t ss_off, int apply_silu, void* stream);
 
-/* Coefficient table only: ab fp32 [B][C0+C1][2] with GN(x)*(1+scale)+shift == ab[.,c,0] * x + ab[.,c,1]. */
+/* Coefficient table only: ab fp32 [B][C0+C1][2] with GN(x)*(1+scale)+shift == ab[.,c,0] * x + ab[.,c,1]; half != 0
+ * stores both coefficients multiplied by 1/2 (the form dlpm_b200_conv2d_gn consumes). */
 int dlpm_b200_groupnorm_fold(float* ab, int C0, const float* stats0, int parts0, int C1, const float* stats1, int parts1, int64_t B,
                              int HW, const float* gamma, const float* beta, const float* ss, int ss_rows, int64_t ss_stride,
-                             int64_t ss_off, void* stream);
+                             int64_t ss_off, int half, void* stream);
+
+/* K5 + K6 fused ("normalise on load"): out = conv3x3(SiLU(GroupNorm([in | in2]))) (+ fused 1x1 skip conv / residual / statistics
+ * as in dlpm_b200_conv2d_stats) without materialising the normalised tensor: the activation boxes are rewritten in shared
+ * memory between their TMA arrival and the MMAs (unet.py:141-143,153-157,188-191,433-435).
+ *   in, in2   RAW GroupNorm inputs, NHWC bf16 [B, H, W, C_in] and [B, H, W, C_in2] (in2 may be NULL / 0)
+ *   ab        fp32 [B][C_in + C_in2][2] from dlpm_b200_groupnorm_fold(..., half = 1)
+ *   w         bf16 [C_out_pad][9*(C_in + C_in2) + C_s0 + C_s1]
+ * Only 3x3 stride-1 convolutions whose 128-pixel tiles lie inside one image (H*W >= 128, W a multiple of 8), channel
+ * counts multiples of 64 and C_out in {<=16 (fp32 NCHW out), multiples of 128}; DLPM_ERR_UNSUPPORTED otherwise. */
+int dlpm_b200_conv2d_gn(const void* in, const void* in2, int C_in2, const float* ab, const void* w, const float* bias,
+                        const void* skip0, int C_s0, const void* skip1, int C_s1, const void* residual, void* out, int out_mode,
+                        int64_t B, int H, int W, int C_in, int C_out, float* stats, int* stats_parts, void* stream);
 
 /* K7. QKVAttention (unet.py:231-250): qkv NHWC bf16 [B, L, 3C] with the reference's channel order (per head:
  * q, k, v blocks of C/heads channels), out NHWC bf16 [B, L, C].  L <= 1024, C/heads <= 64. */

@@ -275,10 +275,76 @@ def test_conv_epilogue_statistics_feed_groupnorm(L, cta_group, B, H, C_in, C_out
     L.call("dlpm_b200_groupnorm_from_stats", L.ptr(got), L.ptr(y0), C_out, L.ptr(st0), p0, L.ptr(y1), C1, L.ptr(st1), p1, B,
            Ho * Ho, *tail, 1, L.stream_ptr())
     ab = torch.zeros(B, C, 2, device="cuda")
-    L.call("dlpm_b200_groupnorm_fold", L.ptr(ab), C_out, L.ptr(st0), p0, C1, L.ptr(st1), p1, B, Ho * Ho, *tail, L.stream_ptr())
+    L.call("dlpm_b200_groupnorm_fold", L.ptr(ab), C_out, L.ptr(st0), p0, C1, L.ptr(st1), p1, B, Ho * Ho, *tail, 0, L.stream_ptr())
     torch.cuda.synchronize()
     # statistics of the unrounded fp32 conv results vs statistics of the bf16 tensor: well inside the bf16 bar
     np.testing.assert_allclose(got.float().cpu().numpy(), want.float().cpu().numpy(), rtol=1.5e-2, atol=1.5e-2)
     yc = torch.cat([y0, y1], -1).float() if C1 else y0.float()
     z = yc * ab[:, None, None, :, 0] + ab[:, None, None, :, 1]
     np.testing.assert_allclose((z * torch.sigmoid(z)).cpu().numpy(), want.float().cpu().numpy(), rtol=1.5e-2, atol=1.5e-2)
+
+
+GN_CONV_CASES = [
+    # B, H, C0, C1 (second raw source), C_out, residual, f32_out
+    (3, 32, 128, 0, 128, True, False),
+    (2, 32, 256, 128, 128, False, False),   # concat 256 + 128: groups straddle the sources, two activation maps
+    (5, 16, 256, 0, 256, True, False),      # N = 256 (CTA pairs in auto mode; single CTAs fall back to ... see below)
+    (2, 16, 256, 256, 256, False, False),
+    (3, 32, 128, 0, 3, False, True),        # final GroupNorm + SiLU + conv to 3 fp32 channels
+    (150, 32, 128, 0, 128, False, False),   # several work items per CTA: barrier phases wrap
+]
+
+
+@pytest.mark.parametrize("B,H,C0,C1,C_out,residual,f32_out", GN_CONV_CASES)
+def test_conv_normalise_on_load(L, B, H, C0, C1, C_out, residual, f32_out):
+    """conv2d_gn == conv3x3(SiLU(GroupNorm32([x0 | x1]) * (1 + scale) + shift)): the normalised tensor only ever exists in
+    shared memory.  Statistics come from the epilogues of the convs that produced x0 / x1."""
+    import ctypes
+
+    def produce(Ci, Co, seed, scale):
+        x = rnd(B, Ci, H, H, seed=seed)
+        w = rnd(Co, Ci, 3, 3, scale=scale / math.sqrt(Ci * 9), seed=seed + 1)
+        b = torch.randn(Co) * 0.3
+        wd, bd, xd = bf(w.permute(0, 2, 3, 1).reshape(Co, -1)).contiguous().cuda(), b.cuda(), nhwc(x)
+        out = torch.zeros(B, H, H, Co, device="cuda", dtype=torch.bfloat16)
+        parts = ctypes.c_int(0)
+        args = (L.ptr(xd), L.ptr(wd), L.ptr(bd), None, 0, None, 0, None, L.ptr(out), 0, B, H, H, Ci, Co, 3, 1)
+        L.call("dlpm_b200_conv2d_stats", *args, None, ctypes.byref(parts), L.stream_ptr())
+        st = torch.zeros(B, parts.value, Co // 4, 2, device="cuda")
+        L.call("dlpm_b200_conv2d_stats", *args, L.ptr(st), ctypes.byref(parts), L.stream_ptr())
+        return out, st, parts.value
+
+    y0, st0, p0 = produce(128, C0, 21, 2.0)
+    y1, st1, p1 = produce(128, C1, 23, 1.0) if C1 else (None, None, 0)
+    C = C0 + C1
+    gamma, beta = (1 + 0.1 * torch.randn(C)).cuda(), (0.1 * torch.randn(C)).cuda()
+    table = (torch.randn(B, 2 * C + 3) * 0.3).cuda()
+    ab = torch.zeros(B, C, 2, device="cuda")
+    L.call("dlpm_b200_groupnorm_fold", L.ptr(ab), C0, L.ptr(st0), p0, C1, L.ptr(st1), p1, B, H * H, L.ptr(gamma), L.ptr(beta),
+           L.ptr(table), B, table.shape[1], 2, 1, L.stream_ptr())
+    w = rnd(C_out, C, 3, 3, scale=1.0 / math.sqrt(C * 9), seed=31)
+    b = torch.randn(C_out) * 0.1
+    wk = w.permute(0, 2, 3, 1).reshape(C_out, -1)
+    bias = b.clone()
+    if f32_out:
+        wk = torch.cat([wk, torch.zeros(16 - C_out, wk.shape[1])])
+        bias = torch.cat([bias, torch.zeros(16 - C_out)])
+    wd, bd = bf(wk).contiguous().cuda(), bias.cuda()
+    res = rnd(B, C_out, H, H, seed=33) if residual else None
+    rd = nhwc(res) if residual else None
+    out = (torch.zeros(B, C_out, H, H, device="cuda") if f32_out else torch.zeros(B, H, H, C_out, device="cuda", dtype=torch.bfloat16))
+    L.call("dlpm_b200_conv2d_gn", L.ptr(y0), L.ptr(y1), C1, L.ptr(ab), L.ptr(wd), L.ptr(bd), None, 0, None, 0, L.ptr(rd), L.ptr(out),
+           1 if f32_out else 0, B, H, H, C0, C_out, None, None, L.stream_ptr())
+    torch.cuda.synchronize()
+    got = out.cpu() if f32_out else from_nhwc(out)
+    # reference: fp32 GroupNorm of the bf16 tensors, SiLU, rounded to bf16 like the operand the tensor core sees
+    x = torch.cat([y0, y1], -1).float().cpu() if C1 else y0.float().cpu()
+    x = x.permute(0, 3, 1, 2)
+    t = table.cpu()
+    gn = F.group_norm(x, 32, gamma.cpu(), beta.cpu(), eps=1e-5) * (1 + t[:, 2:2 + C, None, None]) + t[:, 2 + C:2 + 2 * C, None, None]
+    act = bf(gn * torch.sigmoid(gn)).float()
+    want = F.conv2d(act, bf(w).float(), b, padding=1)
+    if residual:
+        want = want + res
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=2e-2, atol=3e-2)
+    assert (got - want).abs().mean().item() < 5e-3
