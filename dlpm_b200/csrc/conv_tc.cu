@@ -97,7 +97,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // provably warp-uniform (see tc::elect_one)
+  const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
   const int main_blocks = p.taps * p.cin_blocks;
@@ -140,7 +141,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
   if (warp == 0) {
     // ===================== TMA producer (every CTA loads its own A rows and its share of B) =====================
-    if (lane == 0) {
+    {
+      const bool elected = elect_one();
       int stage = 0; uint32_t phase = 0;
       for (int item = first_item; item < n_items; item += item_stride) {
         const int par = item / items_per_par, it_in = item - par * items_per_par;
@@ -161,7 +163,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             if (it2 % p.n_n_tiles == 0 || p.n_n_tiles == 1) {
               for (int cblk = 0; cblk < p.cin_blocks; ++cblk) {
                 const bool src0 = !XF || cblk < p.c0_blocks;
-                tma_prefetch_4d(src0 ? &tmA : &tmA2, (src0 ? cblk : cblk - p.c0_blocks) * BLOCK_K, 0, h2 - 1, n2);
+                tma_prefetch_4d_e(elected, src0 ? &tmA : &tmA2, (src0 ? cblk : cblk - p.c0_blocks) * BLOCK_K, 0, h2 - 1, n2);
               }
             }
           }
@@ -176,35 +178,35 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             uint32_t lead_full = 0;
             if (CG == 2) {
               lead_full = mapa_u32(smem_u32(full_bar + stage), 0);
-              if (leader) mbar_expect_tx(full_bar + stage, 2 * bytes);
+              if (leader) mbar_expect_tx_e(elected, full_bar + stage, 2 * bytes);
             } else {
-              mbar_expect_tx(full_bar + stage, bytes);
+              mbar_expect_tx_e(elected, full_bar + stage, bytes);
             }
-            if (XF) mbar_expect_tx(fullA_bar + stage, a_bytes);
+            if (XF) mbar_expect_tx_e(elected, fullA_bar + stage, a_bytes);
             const int brow = brow0;
             if (main_part) {
               const int cblk = sb / 3, dxi = sb - cblk * 3;
               if (XF) {
                 const bool src0 = cblk < p.c0_blocks;
-                tma_load_4d(src0 ? &tmA : &tmA2, fullA_bar + stage, a_dst, (src0 ? cblk : cblk - p.c0_blocks) * BLOCK_K, dxi - 1, h0 - 1, n0);
-              } else if (CG == 2) tma_load_4d_pair(&tmA, lead_full, a_dst, cblk * BLOCK_K, dxi - 1, h0 - 1, n0);
-              else tma_load_4d(&tmA, full_bar + stage, a_dst, cblk * BLOCK_K, dxi - 1, h0 - 1, n0);
+                tma_load_4d_e(elected, src0 ? &tmA : &tmA2, fullA_bar + stage, a_dst, (src0 ? cblk : cblk - p.c0_blocks) * BLOCK_K, dxi - 1, h0 - 1, n0);
+              } else if (CG == 2) tma_load_4d_pair_e(elected, &tmA, lead_full, a_dst, cblk * BLOCK_K, dxi - 1, h0 - 1, n0);
+              else tma_load_4d_e(elected, &tmA, full_bar + stage, a_dst, cblk * BLOCK_K, dxi - 1, h0 - 1, n0);
 #pragma unroll
               for (int j = 0; j < 3; ++j) {
                 const int kcol = ((j * 3 + dxi) * p.cin_blocks + cblk) * BLOCK_K;
-                if (CG == 2) tma_load_2d_pair(&tmB, lead_full, b_dst + j * B_BYTES, kcol, brow);
-                else tma_load_2d(&tmB, full_bar + stage, b_dst + j * B_BYTES, kcol, brow);
+                if (CG == 2) tma_load_2d_pair_e(elected, &tmB, lead_full, b_dst + j * B_BYTES, kcol, brow);
+                else tma_load_2d_e(elected, &tmB, full_bar + stage, b_dst + j * B_BYTES, kcol, brow);
               }
             } else {
               const int e = sb - 3 * p.cin_blocks;
               const CUtensorMap* map = e < p.s0_blocks ? &tmS0 : &tmS1;
               const int c_a = (e < p.s0_blocks ? e : e - p.s0_blocks) * BLOCK_K;
               const int kcol = (main_blocks + e) * BLOCK_K;
-              if (XF) tma_load_4d(map, fullA_bar + stage, a_dst, c_a, 0, h0, n0);
-              else if (CG == 2) tma_load_4d_pair(map, lead_full, a_dst, c_a, 0, h0, n0);
-              else tma_load_4d(map, full_bar + stage, a_dst, c_a, 0, h0, n0);
-              if (CG == 2) tma_load_2d_pair(&tmB, lead_full, b_dst, kcol, brow);
-              else tma_load_2d(&tmB, full_bar + stage, b_dst, kcol, brow);
+              if (XF) tma_load_4d_e(elected, map, fullA_bar + stage, a_dst, c_a, 0, h0, n0);
+              else if (CG == 2) tma_load_4d_pair_e(elected, map, lead_full, a_dst, c_a, 0, h0, n0);
+              else tma_load_4d_e(elected, map, full_bar + stage, a_dst, c_a, 0, h0, n0);
+              if (CG == 2) tma_load_2d_pair_e(elected, &tmB, lead_full, b_dst, kcol, brow);
+              else tma_load_2d_e(elected, &tmB, full_bar + stage, b_dst, kcol, brow);
             }
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
@@ -216,9 +218,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           uint32_t lead_full = 0;
           if (CG == 2) {
             lead_full = mapa_u32(smem_u32(full_bar + stage), 0);
-            if (leader) mbar_expect_tx(full_bar + stage, 2 * cnt * SUB_BYTES);
+            if (leader) mbar_expect_tx_e(elected, full_bar + stage, 2 * cnt * SUB_BYTES);
           } else {
-            mbar_expect_tx(full_bar + stage, cnt * SUB_BYTES);
+            mbar_expect_tx_e(elected, full_bar + stage, cnt * SUB_BYTES);
           }
 #pragma unroll
           for (int ks = 0; ks < KS; ++ks) {
@@ -239,11 +241,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               map = &tmS1; c_a = (kb - main_blocks - p.s0_blocks) * BLOCK_K; x_a = 0; y_a = h0;
             }
             if (CG == 2) {
-              tma_load_4d_pair(map, lead_full, a_dst, c_a, x_a, y_a, n0);
-              tma_load_2d_pair(&tmB, lead_full, b_dst, kb * BLOCK_K, brow0);
+              tma_load_4d_pair_e(elected, map, lead_full, a_dst, c_a, x_a, y_a, n0);
+              tma_load_2d_pair_e(elected, &tmB, lead_full, b_dst, kb * BLOCK_K, brow0);
             } else {
-              tma_load_4d(map, full_bar + stage, a_dst, c_a, x_a, y_a, n0);
-              tma_load_2d(&tmB, full_bar + stage, b_dst, kb * BLOCK_K, brow0);
+              tma_load_4d_e(elected, map, full_bar + stage, a_dst, c_a, x_a, y_a, n0);
+              tma_load_2d_e(elected, &tmB, full_bar + stage, b_dst, kb * BLOCK_K, brow0);
             }
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -252,7 +254,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (lane == 0 && leader) {
+    if (leader) {
+      const bool elected = elect_one();
       int stage = 0; uint32_t phase = 0;
       int it = 0;
       for (int item = first_item; item < n_items; item += item_stride, ++it) {
@@ -277,19 +280,19 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 // dy = j - 1: shift by Wb rows (whole swizzle atoms); sub-tile `sub` starts Hb image rows further down
                 const uint32_t a_j = main_part ? a_addr + (uint32_t)((sub * p.Hb + j) * p.Wb * BLOCK_K * 2) : a_addr + (uint32_t)(sub * A_BYTES);
                 const uint32_t d_sub = d_tmem + (uint32_t)(sub * BLOCK_N);
+                // a K step of 16 elements = 32 bytes inside the swizzled row: the descriptor's address field (>> 4) moves by 2
+                const uint64_t da0 = make_smem_desc<SWZ>(a_j), db0 = make_smem_desc<SWZ>(b_addr + j * B_BYTES);
 #pragma unroll
                 for (int k = 0; k < BLOCK_K / 16; ++k) {
-                  const uint64_t da = make_smem_desc<SWZ>(a_j + k * 32);
-                  const uint64_t db = make_smem_desc<SWZ>(b_addr + j * B_BYTES + k * 32);
-                  if (CG == 2) umma_bf16_pair(d_sub, da, db, IDESC, (sb | j | k) != 0);
-                  else umma_bf16(d_sub, da, db, IDESC, (sb | j | k) != 0);
+                  if (CG == 2) umma_bf16_pair_e(elected, d_sub, da0 + 2 * k, db0 + 2 * k, IDESC, (sb | j | k) != 0);
+                  else umma_bf16_e(elected, d_sub, da0 + 2 * k, db0 + 2 * k, IDESC, (sb | j | k) != 0);
                 }
               }
             }
-            if (CG == 2) umma_commit_pair(empty_bar + stage); else umma_commit(empty_bar + stage);
+            if (CG == 2) umma_commit_pair_e(elected, empty_bar + stage); else umma_commit_e(elected, empty_bar + stage);
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
-          if (CG == 2) umma_commit_pair(tfull_bar + acc); else umma_commit(tfull_bar + acc);
+          if (CG == 2) umma_commit_pair_e(elected, tfull_bar + acc); else umma_commit_e(elected, tfull_bar + acc);
           continue;
         }
         for (int kb0 = 0; kb0 < nkb; kb0 += KS) {
@@ -301,18 +304,17 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             if (ks >= cnt) break;
             const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES + ks * SUB_BYTES);
             const uint32_t b_addr = a_addr + A_BYTES;
+            const uint64_t da0 = make_smem_desc<SWZ>(a_addr), db0 = make_smem_desc<SWZ>(b_addr);
 #pragma unroll
             for (int k = 0; k < BLOCK_K / 16; ++k) {
-              const uint64_t da = make_smem_desc<SWZ>(a_addr + k * 32);
-              const uint64_t db = make_smem_desc<SWZ>(b_addr + k * 32);
-              if (CG == 2) umma_bf16_pair(d_tmem, da, db, IDESC, (kb0 | ks | k) != 0);
-              else umma_bf16(d_tmem, da, db, IDESC, (kb0 | ks | k) != 0);
+              if (CG == 2) umma_bf16_pair_e(elected, d_tmem, da0 + 2 * k, db0 + 2 * k, IDESC, (kb0 | ks | k) != 0);
+              else umma_bf16_e(elected, d_tmem, da0 + 2 * k, db0 + 2 * k, IDESC, (kb0 | ks | k) != 0);
             }
           }
-          if (CG == 2) umma_commit_pair(empty_bar + stage); else umma_commit(empty_bar + stage);  // frees the smem slot(s)
+          if (CG == 2) umma_commit_pair_e(elected, empty_bar + stage); else umma_commit_e(elected, empty_bar + stage);  // frees the smem slot(s)
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        if (CG == 2) umma_commit_pair(tfull_bar + acc); else umma_commit(tfull_bar + acc);  // accumulator complete -> epilogue(s)
+        if (CG == 2) umma_commit_pair_e(elected, tfull_bar + acc); else umma_commit_e(elected, tfull_bar + acc);  // accumulator complete -> epilogue(s)
       }
     }
   } else if (XF && warp >= 8) {

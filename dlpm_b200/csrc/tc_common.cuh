@@ -43,6 +43,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// One lane of a fully converged warp (the same lane every time).  Issue loops run warp-uniformly -- every lane executes
+// the address / descriptor arithmetic, only the elected lane executes the TMA / MMA instruction -- so that the compiler
+// keeps the operands in uniform registers; under `if (lane == 0)` it cannot prove uniformity and wraps every
+// UTMALDG / UTCHMMA in an ELECT + R2UR "waterfall" loop (~16 extra instructions per MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ------------------------------------------------------------------ TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -176,6 +186,19 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&r)[16]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+
+// predicated forms for warp-uniform issue loops (see elect_one)
+__device__ __forceinline__ void mbar_expect_tx_e(bool e, uint64_t* bar, uint32_t bytes) { if (e) mbar_expect_tx(bar, bytes); }
+__device__ __forceinline__ void tma_load_2d_e(bool e, const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1) { if (e) tma_load_2d(m, bar, dst, c0, c1); }
+__device__ __forceinline__ void tma_load_4d_e(bool e, const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) { if (e) tma_load_4d(m, bar, dst, c0, c1, c2, c3); }
+__device__ __forceinline__ void tma_prefetch_4d_e(bool e, const CUtensorMap* m, int c0, int c1, int c2, int c3) { if (e) tma_prefetch_4d(m, c0, c1, c2, c3); }
+__device__ __forceinline__ void tma_load_2d_pair_e(bool e, const CUtensorMap* m, uint32_t bar, void* dst, int c0, int c1) { if (e) tma_load_2d_pair(m, bar, dst, c0, c1); }
+__device__ __forceinline__ void tma_load_4d_pair_e(bool e, const CUtensorMap* m, uint32_t bar, void* dst, int c0, int c1, int c2, int c3) { if (e) tma_load_4d_pair(m, bar, dst, c0, c1, c2, c3); }
+__device__ __forceinline__ void umma_bf16_e(bool e, uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) { if (e) umma_bf16(d, a, b, idesc, acc); }
+__device__ __forceinline__ void umma_bf16_pair_e(bool e, uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) { if (e) umma_bf16_pair(d, a, b, idesc, acc); }
+__device__ __forceinline__ void umma_commit_e(bool e, uint64_t* bar) { if (e) umma_commit(bar); }
+__device__ __forceinline__ void umma_commit_pair_e(bool e, uint64_t* bar) { if (e) umma_commit_pair(bar); }
 
 // ------------------------------------------------------------------ descriptors
 // Shared-memory matrix descriptor, K-major operand, rows of (SWIZZLE_BYTES) bytes, 8-row swizzle atoms.
