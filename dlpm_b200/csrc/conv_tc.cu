@@ -29,6 +29,7 @@ using namespace tc;
 
 constexpr int kMaxStages = 8;
 constexpr int kConvThreads = 256;
+constexpr int kConvThreadsEpi2 = 384;  // + warps 8-11: a second epilogue warp per TMEM lane quadrant (tiles with >= 2 column chunks)
 constexpr int kConvThreadsXF = 512;  // + warps 8-15: the eight transform warps (two per SM sub-partition)
 constexpr int kXfWarps = 8;
 constexpr int kSmemBudget = 220 * 1024;  // operand ring; barriers + alignment slack come on top (227 KB per CTA)
@@ -68,8 +69,13 @@ struct ConvKParams {
 // be the virtual concatenation of two tensors (tmA | tmA2).  Barrier chain per stage:
 //   TMA(A) -> fullA (local) -> transform warps -> xf (leader, 8 x CG arrivals) -+-> MMA -> empty
 //   TMA(B) -> full (leader) ----------------------------------------------------+
+template <int BLOCK_N, bool XF>
+__host__ __device__ constexpr int conv_epi_groups() { return (BLOCK_N >= 64 && !XF) ? 2 : 1; }
+template <int BLOCK_N, bool XF>
+__host__ __device__ constexpr int conv_threads() { return XF ? kConvThreadsXF : (conv_epi_groups<BLOCK_N, XF>() == 2 ? kConvThreadsEpi2 : kConvThreads); }
+
 template <int BLOCK_N, int BLOCK_K, int CG, int KS, bool XF>
-__global__ void __launch_bounds__(XF ? kConvThreadsXF : kConvThreads, 1)
+__global__ void __launch_bounds__(conv_threads<BLOCK_N, XF>(), 1)
 k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmS0,
           const __grid_constant__ CUtensorMap tmS1, const __grid_constant__ CUtensorMap tmB, const ConvKParams p) {
   constexpr int A_BYTES = 128 * BLOCK_K * 2;
@@ -86,6 +92,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   constexpr int ACC_COLS = 2 * MS_MAX * BLOCK_N;
   constexpr uint32_t TMEM_COLS = ACC_COLS <= 32 ? 32 : (ACC_COLS <= 64 ? 64 : (ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512)));
   constexpr uint32_t IDESC = make_idesc_bf16(128 * CG, BLOCK_N);
+  // short-K layers are epilogue-bound with one warp per quadrant (TMEM load -> bias/residual/statistics -> store is a long
+  // dependent chain): two warps per quadrant split the tile's column chunks and interleave on the same sub-partition
+  constexpr int EG = conv_epi_groups<BLOCK_N, XF>();
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -123,7 +132,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       mbar_init(empty_bar + s, 1);
       if (XF) { mbar_init(fullA_bar + s, 1); mbar_init(xf_bar + s, kXfWarps * CG); }
     }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar + a, 1); mbar_init(tempty_bar + a, 4 * CG); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar + a, 1); mbar_init(tempty_bar + a, 4 * EG * CG); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -378,9 +387,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp >= 4 && warp < 4 + 4 * EG) {
     // ===================== epilogue =====================
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int eg = (warp - 4) >> 2;  // which half of the column chunks (EG == 2)
     const int m = q * 32 + lane;
     const int w_in = m % p.Wb, h_in = (m / p.Wb) % p.Hb, n_in = m / (p.Wb * p.Hb);
     int it = 0;
@@ -400,7 +410,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         constexpr int CH = BLOCK_N >= 32 ? 32 : 16;
         // identity-skip rows are fetched BEFORE waiting for the accumulator so their HBM latency hides behind the MMAs
         constexpr bool RES_PREFETCH = !XF;  // XF kernels run 512 threads (128 registers each): residual rows are read in place
-        uint4 resv[RES_PREFETCH ? MS_MAX : 1][RES_PREFETCH ? BLOCK_N / 8 : 1];
+        constexpr int NCH = BLOCK_N / CH;  // column chunks of the tile; this warp owns chunks eg, eg + EG, ...
+        uint4 resv[RES_PREFETCH ? MS_MAX : 1][RES_PREFETCH ? BLOCK_N / 8 / EG : 1];
         const bool has_res = p.residual != nullptr && valid;
         if (RES_PREFETCH && has_res) {
 #pragma unroll
@@ -409,7 +420,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               const int64_t pix = (nn * p.H_full + p.out_scale * (h0 + sub * p.Hb + h_in) + out_oy) * p.W_full + p.out_scale * w_in + out_ox;
               const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.C_out + nt * BLOCK_N);
 #pragma unroll
-              for (int j = 0; j < BLOCK_N / 8; ++j) resv[sub][j] = __ldg(rp + j);
+              for (int ci = 0; ci < NCH / EG; ++ci)
+#pragma unroll
+                for (int j = 0; j < CH / 8; ++j) resv[sub][ci * (CH / 8) + j] = __ldg(rp + (ci * EG + eg) * (CH / 8) + j);
             }
           }
         }
@@ -423,7 +436,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         // channel QUAD, (sum, sum of squares) over the warp's 32 pixels (x msub sub-tiles) -- no second pass over the output
         const bool do_stats = CH == 32 && p.stats != nullptr && valid;
 #pragma unroll
-        for (int c0 = 0; c0 < BLOCK_N; c0 += CH) {
+        for (int ci = 0; ci < NCH / EG; ++ci) {
+          const int c0 = (ci * EG + eg) * CH;
           float st[CH / 2];
 #pragma unroll
           for (int i = 0; i < CH / 2; ++i) st[i] = 0.f;
@@ -446,7 +460,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                   for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[j + e]) + __ldg(bias + j + e);
                   if (has_res) {
                     uint4 rv;
-                    if constexpr (RES_PREFETCH) rv = resv[sub][(c0 + j) / 8];
+                    if constexpr (RES_PREFETCH) rv = resv[sub][ci * (CH / 8) + j / 8];
                     else rv = __ldg(reinterpret_cast<const uint4*>(p.residual + pixs[sub] * p.C_out + col + j));
                     const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
@@ -719,7 +733,7 @@ static int launch_t(const ConvLaunch& L, cudaStream_t stream) {
   const int n_items = ((L.n_m_tiles / L.msub + CG - 1) / CG) * L.n_n_tiles * L.n_par;
   const int max_groups = kNumSMs / CG;
   const int grid = (n_items < max_groups ? n_items : max_groups) * CG;
-  const int threads = XF ? kConvThreadsXF : kConvThreads;
+  const int threads = conv_threads<BN, XF>();
   cudaError_t e = launch_ex(k_conv_tc<BN, BK, CG, KS, XF>, dim3(grid), dim3(threads), smem, stream, CG, L.tmA, L.tmA2, L.tmS0, L.tmS1,
                             L.tmB, p);
   if (e != cudaSuccess) return cuda_fail(e, CG == 1 ? "conv_tc launch" : "conv_tc pair launch");
