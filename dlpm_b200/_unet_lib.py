@@ -24,6 +24,7 @@ UNET_SIGNATURES = {
     "dlpm_b200_attention": [c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp],
     "dlpm_b200_conv_in": [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp],
     "dlpm_b200_conv_in_stats": [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp, ctypes.POINTER(c_int), c_vp],
+    "dlpm_b200_split_input": [c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp],
     "dlpm_b200_upsample2x": [c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp],
     "dlpm_b200_time_embedding": [c_vp, c_vp, c_vp, c_vp, c_f32, c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "dlpm_b200_unet_create": [ctypes.POINTER(c_vp), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), c_vp,

@@ -11,7 +11,7 @@
 
 namespace dlpm {
 
-enum OpCode { OP_CONV_IN = 0, OP_GN = 1, OP_CONV = 2, OP_UP = 3, OP_ATTN = 4 };
+enum OpCode { OP_CONV_IN = 0, OP_GN = 1, OP_CONV = 2, OP_UP = 3, OP_ATTN = 4, OP_SPLIT = 5 };
 
 constexpr int kOpFields = 24;
 struct Op { int64_t f[kOpFields]; };
@@ -108,6 +108,7 @@ static int build_plan(UNetEngine* E, int64_t B, Plan* P) {
       P->conv_in_stats.push_back(st);
     }
     if (f[0] == OP_UP || f[0] == OP_ATTN) writes(f[2]);
+    if (f[0] == OP_SPLIT) writes(f[1]);
     if (f[0] == OP_GN) {
       // 1 in0, 2 in1, 3 out, 4 C0, 5 C1, 6 HW, 10 silu
       GnLaunch G;
@@ -268,6 +269,9 @@ int dlpm_b200_unet_forward(void* handle, const float* x, const float* t, int t_r
       } break;
       case OP_UP:  // 1 in, 2 out, 3 H, 4 W, 5 C
         rc = dlpm_b200_upsample2x(E->buf(f[2], B), E->buf(f[1], B), B, (int)f[3], (int)f[4], (int)f[5], stream);
+        break;
+      case OP_SPLIT:  // 1 out, 2 C_in, 3 H, 4 W
+        rc = dlpm_b200_split_input(E->buf(f[1], B), x, B, (int)f[2], (int)f[3], (int)f[4], stream);
         break;
       case OP_ATTN:  // 1 qkv, 2 out, 3 L, 4 C, 5 heads
         rc = dlpm_b200_attention(E->buf(f[2], B), E->buf(f[1], B), B, (int)f[3], (int)f[4], (int)f[5], stream);

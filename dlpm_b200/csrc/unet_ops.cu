@@ -439,6 +439,34 @@ __global__ void __launch_bounds__(256) k_attention(__nv_bfloat16* __restrict__ o
 }
 
 // ------------------------------------------------------------------------------------------------
+// Network input for the tensor-core input conv: NCHW fp32 [B, C, H, W] -> NHWC bf16 [B, H, W, 32] holding the bf16
+// SPLIT of every value, x = hi + lo (+ O(2^-17 |x|)):  channels [0,C) = hi, [C,2C) = lo, [2C,3C) = hi, rest 0.
+// With weights packed as (w_hi, w_hi, w_lo) the 3x3 conv over these 32 channels computes
+// x_hi*w_hi + x_lo*w_hi + x_hi*w_lo = x*w up to 2^-16 relative -- fp32-grade accuracy for the heavy-tailed x_t on
+// the bf16 tensor cores (the fp32 FMA kernel k_conv_in took 2.8 % of the forward).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_split_input(__nv_bfloat16* __restrict__ out, const float* __restrict__ x, int C, int64_t HW,
+                                                     int64_t total_px) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (int64_t px = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; px < total_px; px += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = px / HW, sp = px - n * HW;
+    __align__(16) __nv_bfloat16 row[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) row[j] = __float2bfloat16(0.f);
+    for (int c = 0; c < C; ++c) {
+      const float v = __ldg(x + (n * C + c) * HW + sp);
+      const __nv_bfloat16 hi = __float2bfloat16(v);
+      const __nv_bfloat16 lo = __float2bfloat16(v - __bfloat162float(hi));
+      row[c] = hi; row[C + c] = lo; row[2 * C + c] = hi;
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out + px * 32);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dst[j] = reinterpret_cast<const uint4*>(row)[j];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // input conv: NCHW fp32 -> NHWC bf16, 3x3 pad 1, C_in <= 4 (fp32 FMA: the network input keeps full precision).
 // One CTA per (image, band of kRows output rows).  Weights arrive pre-transposed [C_in*9][C_out] (in-major) and are
 // copied to shared memory once per CTA; thread = (pixel x, g) owns the 16 channels {32*j + 4*g .. +3, j = 0..3} so the
@@ -763,6 +791,17 @@ int dlpm_b200_conv_in_stats(void* out, const float* x, const float* wT, const fl
   cudaError_t e2 = launch_ex(k_conv_in, dim3((unsigned)(B * bands)), dim3(256), smem, (cudaStream_t)stream, 1,
                              reinterpret_cast<__nv_bfloat16*>(out), x, wT, bias, C_in, C_out, H, W, stats);
   if (e2 != cudaSuccess) return cuda_fail(e2, "conv_in launch");
+  return DLPM_OK;
+}
+
+int dlpm_b200_split_input(void* out, const float* x, int64_t B, int C, int H, int W, void* stream) {
+  DLPM_REQUIRE(out && x, "split_input: NULL tensor");
+  DLPM_REQUIRE(C >= 1 && 3 * C <= 32 && H >= 1 && W >= 1 && B >= 0, "split_input: needs 3*C <= 32");
+  if (B == 0) return DLPM_OK;
+  const int64_t total = B * H * W;
+  cudaError_t e = launch_ex(k_split_input, dim3((unsigned)grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, 1,
+                            reinterpret_cast<__nv_bfloat16*>(out), x, C, (int64_t)H * W, total);
+  if (e != cudaSuccess) return cuda_fail(e, "split_input launch");
   return DLPM_OK;
 }
 

@@ -182,7 +182,7 @@ def as_native(model, device):
 # ------------------------------------------------------------------------------------------------
 # UNet (image configs)
 # ------------------------------------------------------------------------------------------------
-OP_CONV_IN, OP_GN, OP_CONV, OP_UP, OP_ATTN = 0, 1, 2, 3, 4
+OP_CONV_IN, OP_GN, OP_CONV, OP_UP, OP_ATTN, OP_SPLIT = 0, 1, 2, 3, 4, 5
 OP_FIELDS = 24  # int64 fields per op record (unet_engine.cu: kOpFields)
 
 
@@ -435,8 +435,21 @@ class UNetModel(nn.Module):
         c0 = self.input_blocks[0][0]
         h = new_buf(H * W * mc)
         names["input_blocks.0"] = h
-        op(OP_CONV_IN, h, self.in_channels, mc, H, W, add_f(c0.weight.detach().float().reshape(mc, -1).t().contiguous()),
-           add_f(c0.bias))
+        cin = self.in_channels
+        if 3 * cin <= 32 and mc % 32 == 0 and H * W >= 128:
+            # tensor-core input conv: x is split into bf16 (hi, lo, hi) channel groups (k_split_input) and the weights into
+            # (w_hi, w_hi, w_lo), so the bf16 MMAs sum x_hi*w_hi + x_lo*w_hi + x_hi*w_lo = x*w to 2^-16 relative
+            xs = new_buf(H * W * 32, tmp=True)
+            op(OP_SPLIT, xs, cin, H, W)
+            w0 = c0.weight.detach().float()
+            w_hi = w0.to(torch.bfloat16).float()
+            w_lo = (w0 - w_hi).to(torch.bfloat16).float()
+            w32 = torch.zeros(mc, 32, 3, 3, device=w0.device)
+            w32[:, 0:cin], w32[:, cin:2 * cin], w32[:, 2 * cin:3 * cin] = w_hi, w_hi, w_lo
+            conv(xs, 32, H, W, w32, c0.bias, h)
+            release(xs)
+        else:
+            op(OP_CONV_IN, h, cin, mc, H, W, add_f(c0.weight.detach().float().reshape(mc, -1).t().contiguous()), add_f(c0.bias))
         C, Hc, Wc = mc, H, W
         hs = [(h, C)]
         for i in range(1, len(self.input_blocks)):

@@ -91,6 +91,11 @@ int dlpm_b200_attention(void* out, const void* qkv, int64_t B, int L, int C, int
 int dlpm_b200_conv_in(void* out, const float* x, const float* wT, const float* bias, int64_t B, int C_in, int C_out, int H,
                       int W, void* stream);
 
+/* Tensor-core form of the input conv (unet.py:347), step 1: x NCHW fp32 [B, C, H, W] (3*C <= 32) -> NHWC bf16
+ * [B, H, W, 32] with channels [0,C) = bf16(x), [C,2C) = bf16(x - bf16(x)), [2C,3C) = bf16(x), rest 0.  Step 2 is
+ * dlpm_b200_conv2d over these 32 channels with weights packed (w_hi, w_hi, w_lo): x*w to 2^-16 relative. */
+int dlpm_b200_split_input(void* out, const float* x, int64_t B, int C, int H, int W, void* stream);
+
 /* Input conv that also leaves GroupNorm partial statistics of its output (same layout and protocol as
  * dlpm_b200_conv2d_stats: fp32 [B][*stats_parts][C_out/4][2]; stats == NULL with stats_parts != NULL only sizes). */
 int dlpm_b200_conv_in_stats(void* out, const float* x, const float* wT, const float* bias, int64_t B, int C_in, int C_out,

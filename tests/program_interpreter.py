@@ -6,7 +6,7 @@ import math
 import torch
 import torch.nn.functional as F
 
-OP_CONV_IN, OP_GN, OP_CONV, OP_UP, OP_ATTN = 0, 1, 2, 3, 4
+OP_CONV_IN, OP_GN, OP_CONV, OP_UP, OP_ATTN, OP_SPLIT = 0, 1, 2, 3, 4, 5
 
 
 def interpret(prog, x, t, mc, emulate_bf16=False):
@@ -88,6 +88,13 @@ def interpret(prog, x, t, mc, emulate_bf16=False):
                     if o not in bufs or bufs[o].shape[1] != Ho * oscale or bufs[o].shape[3] != cout:
                         bufs[o] = torch.zeros(B, Ho * oscale, Wo * oscale, cout)
                     bufs[o][:, oy::oscale, ox::oscale, :] = q(y.permute(0, 2, 3, 1))
+        elif code == OP_SPLIT:
+            _, o, cin, H, W = f[:5]
+            hi = x.to(torch.bfloat16).float()
+            lo = (x - hi).to(torch.bfloat16).float()
+            v = torch.zeros(B, 32, H, W)
+            v[:, 0:cin], v[:, cin:2 * cin], v[:, 2 * cin:3 * cin] = hi, lo, hi
+            bufs[o] = v.permute(0, 2, 3, 1)
         elif code == OP_UP:
             _, i, o, H, W, C = f[:6]
             bufs[o] = F.interpolate(bufs[i].permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1)

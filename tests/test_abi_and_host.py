@@ -127,7 +127,7 @@ def test_lim_table_matches_oracle():
 
 
 def test_unet_program_matches_oracle_block_plan():
-    from dlpm_b200.score_nets import OP_ATTN, OP_CONV, OP_GN, UNetModel
+    from dlpm_b200.score_nets import OP_ATTN, OP_CONV, OP_CONV_IN, OP_GN, OP_SPLIT, UNetModel
     from oracle import nets
     for mc, attn in ((128, (16,)), (32, (2, 4))):
         m = UNetModel(3, mc, 3, 2, attn, channel_mult=(1, 2, 2, 2), num_heads=4, use_scale_shift_norm=True)
@@ -140,7 +140,9 @@ def test_unet_program_matches_oracle_block_plan():
         assert ops.count(OP_GN) == 2 * n_res + n_attn + 1
         n_up = sum(l.count("up") for l in inp + out)
         n_down = sum(l.count("down") for l in inp + out)
-        assert ops.count(OP_CONV) == 2 * n_res + 2 * n_attn + n_down + n_up + 1  # an upsample+conv = ONE parity-batched launch
+        # an upsample+conv = ONE parity-batched launch; the input conv = bf16 split + ONE tensor-core conv
+        assert ops.count(OP_SPLIT) == 1 and ops.count(OP_CONV_IN) == 0
+        assert ops.count(OP_CONV) == 2 * n_res + 2 * n_attn + n_down + n_up + 2
         assert prog["header"][7] == sum(2 * b.out_channels for b in m.modules() if hasattr(b, "emb_layers"))
         assert prog["wb"].dtype == torch.bfloat16 and prog["wb"].numel() % 64 == 0
     # state_dict key set equals the oracle's expectations (keys it reads exist)
