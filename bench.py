@@ -219,15 +219,15 @@ def run_ours(args, rank, local_rank, world):
     out = torch.empty_like(xs)
     eng.profile(xs, tt, out, B)
     prof = eng.profile(xs, tt, out, B)
-    names = {-1: "time_embedding", 0: "conv_in", 1: "groupnorm_silu", 2: "conv_tc", 3: "upsample2x", 4: "attention"}
+    names = {-1: "time_embedding", 0: "conv_in", 1: "groupnorm_silu", 2: "conv_tc", 3: "upsample2x", 4: "attention", 5: "conv_in_split"}
     breakdown = {}
     for code, ms, fl in prof:
-        breakdown[names[code]] = breakdown.get(names[code], 0.0) + ms
+        breakdown[names.get(code, "op%d" % code)] = breakdown.get(names.get(code, "op%d" % code), 0.0) + ms
     if rank == 0 and os.path.isdir(os.path.join(ROOT, "gpurun_out")):
         with open(os.path.join(ROOT, "gpurun_out", "ops_profile.txt"), "w") as fh:
             for i, (code, ms, fl) in enumerate(prof):
                 op = eng.prog["ops"][i - 1] if i > 0 else []
-                fh.write("%3d %-15s %8.4f ms %8.1f TFLOP/s  %s\n" % (i, names[code], ms, fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0, op))
+                fh.write("%3d %-15s %8.4f ms %8.1f TFLOP/s  %s\n" % (i, names.get(code, "op%d" % code), ms, fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0, op))
     conv = [(ms, fl) for code, ms, fl in prof if code == 2]
     conv_ms, conv_fl = sum(m for m, _ in conv), sum(f for _, f in conv)
     fwd_ms = sum(ms for _, ms, _ in prof)
