@@ -28,6 +28,9 @@ SIGNATURES = {
     "dlpm_b200_advance_counter": [c_vp, c_int, c_vp],
     "dlpm_b200_training_elements": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_i64, c_f32, c_f32, c_u64,
                                     c_u64, c_i64, c_vp],
+    "dlpm_b200_scale_by_step": [c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_i64, c_i64, c_vp],
+    "dlpm_b200_lim_training_elements": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, c_int, c_f32, c_u64, c_u64, c_i64,
+                                        c_vp],
     "dlpm_b200_loss_terms": [c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, c_int, c_vp],
     "dlpm_b200_postprocess": [c_vp, c_vp, c_i64, c_f32, c_int, c_vp],
     "dlpm_b200_mlp_forward": [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp],

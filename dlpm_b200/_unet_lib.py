@@ -148,7 +148,7 @@ def run_lim_loop(model, x, coef_d, t_table, steps, ode, isotropic, alpha, clamp_
 
 
 def run_sample_loop(model, x, dlpm, T, mode, flags, hist, seed, z_offset, sample_base, graph_cache=None, progress=False,
-                    use_graph=True):
+                    use_graph=True, input_scale=None):
     """x: (B, C, H, W) fp32, updated in place to x_0.  One step = UNet forward (t from the device counter) + fused
     update + counter decrement; captured once as a CUDA graph and replayed T-1 times."""
     dev = x.device
@@ -160,8 +160,13 @@ def run_sample_loop(model, x, dlpm, T, mode, flags, hist, seed, z_offset, sample
     inv_T = float(torch.tensor(1.0 / T, dtype=torch.float32))
     stream = torch.cuda.current_stream()
 
+    x_in = x if input_scale is None else torch.empty_like(x)  # scale_exploding + input_scaling: net sees x / (1 + barsigma_t)
+
     def one_step(h_ptr):
-        eng.forward(x, None, t_dev, inv_T, eps, B)
+        if input_scale is not None:
+            _lib.call("dlpm_b200_scale_by_step", _lib.ptr(x_in), _lib.ptr(x), _lib.ptr(input_scale), None, 0, _lib.ptr(t_dev), T, B, D,
+                      _lib.stream_ptr())
+        eng.forward(x_in, None, t_dev, inv_T, eps, B)
         if mode == 1:
             _lib.call("dlpm_b200_dlim_step", _lib.ptr(x), _lib.ptr(eps), _lib.ptr(dlpm.sched), 0, _lib.ptr(t_dev), T, B, D, flags,
                       h_ptr, _lib.stream_ptr())

@@ -767,7 +767,7 @@ int conv_launch(const ConvLaunch& L, cudaStream_t stream) {
 
 }  // namespace dlpm
 
-namespace dlpm { void engine_set_gn_stats(bool on); void engine_set_gn_fuse(int mode); }
+namespace dlpm { void engine_set_gn_stats(bool on); void engine_set_gn_fuse(int mode); bool process_set_option(const char* name, int value); }
 using namespace dlpm;
 
 int dlpm_b200_set_option(const char* name, int value) {
@@ -809,6 +809,7 @@ int dlpm_b200_set_option(const char* name, int value) {
     conv_set_cta_group_override(value);
     return DLPM_OK;
   }
+  if (process_set_option(name, value)) return DLPM_OK;
   set_error("set_option: unknown option '%s'", name);
   return DLPM_ERR_ARG;
 }

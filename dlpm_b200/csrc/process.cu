@@ -12,6 +12,7 @@
 // contraction), so with injected noise the results are bit-identical to the reference's fp32 CPU path.
 #include <cstdarg>
 #include <cstdlib>
+#include <string>
 
 #include "common.cuh"
 #include "rng.cuh"
@@ -54,14 +55,16 @@ __device__ __forceinline__ float clamp_sym(float v, float c) { return c >= 0.f ?
 __device__ __forceinline__ float sel4(const float4& v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w)); }
 
 // per-sample subordinator (one draw per sample; position 0 of the sample's A stream)
-__device__ __forceinline__ float sample_A(const Philox& ph, const StableParams& sp, uint32_t stream, uint64_t offset,
+template <class P>
+__device__ __forceinline__ float sample_A(const P& ph, const StableParams& sp, uint32_t stream, uint64_t offset,
                                           uint64_t sample) {
   if (sp.gaussian) return 2.0f;  // alpha == 2: A == 2, no variates consumed (Distributions.py:40-42)
   const uint4 r = philox_at(ph, stream, offset, sample, 0u);
   return stable_A(sp, r.x, r.y);
 }
 // four per-element subordinators for quad `pos` of a sample (two Philox blocks: positions 2pos, 2pos+1)
-__device__ __forceinline__ float4 element_A4(const Philox& ph, const StableParams& sp, uint32_t stream, uint64_t offset,
+template <class P>
+__device__ __forceinline__ float4 element_A4(const P& ph, const StableParams& sp, uint32_t stream, uint64_t offset,
                                              uint64_t sample, uint32_t pos) {
   if (sp.gaussian) return make_float4(2.0f, 2.0f, 2.0f, 2.0f);
   const uint4 r0 = philox_at(ph, stream, offset, sample, 2u * pos + 1u);  // +1: position 0 is the per-sample draw
@@ -69,9 +72,49 @@ __device__ __forceinline__ float4 element_A4(const Philox& ph, const StableParam
   return make_float4(stable_A(sp, r0.x, r0.y), stable_A(sp, r0.z, r0.w), stable_A(sp, r1.x, r1.y),
                      stable_A(sp, r1.z, r1.w));
 }
-__device__ __forceinline__ float4 normal_quad(const Philox& ph, uint32_t stream, uint64_t offset, uint64_t sample,
+template <class P>
+__device__ __forceinline__ float4 normal_quad(const P& ph, uint32_t stream, uint64_t offset, uint64_t sample,
                                               uint32_t pos) {
   return normal4(philox_at(ph, stream, offset, sample, pos));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Skeleton of the vectorised streaming kernels (K1, K3, LIM).  The flat index space of float4 "quads" is cut into
+// 32-quad granules (512 B) and every CTA owns ONE contiguous share of them, equal to within a granule, with
+// grid = SMs x resident CTAs: a single full wave, no tail.  A thread walks its share in strides of 256 quads and
+// carries (sample, position) incrementally -- no per-quad division.  Per-sample scalars (sqrt(A), step coefficients)
+// of a sub-chunk of <= kChunkQuads quads are computed once into shared memory.  32-bit indices: nq < 2^31.
+// ------------------------------------------------------------------------------------------------
+struct QuadSpan {
+  uint32_t nq;        // total quads = n_outer * inner / 4
+  uint32_t qpr;       // quads per sample row = inner / 4
+  uint32_t step_o;    // 256 quads expressed as (samples, quads): 256 = step_o * qpr + step_pos
+  uint32_t step_pos;
+  uint32_t sub;       // sub-chunk length in quads: touches <= kChunkQuads samples (size of the per-sample smem tables)
+  FastDiv fd;         // division by qpr
+};
+static QuadSpan make_span(int64_t n_outer, int64_t inner) {
+  QuadSpan s;
+  s.qpr = (uint32_t)(inner / 4);
+  s.nq = (uint32_t)(n_outer * (inner / 4));
+  s.step_o = 256u / s.qpr;
+  s.step_pos = 256u % s.qpr;
+  s.fd = FastDiv(s.qpr);
+  const uint64_t sub = (uint64_t)(kChunkQuads - 2) * s.qpr;
+  s.sub = sub < (uint64_t)kChunkQuads ? (uint32_t)kChunkQuads : (sub > (1u << 30) ? (1u << 30) : (uint32_t)(sub & ~31ull));
+  return s;
+}
+__device__ __forceinline__ void span_advance(const QuadSpan& s, uint32_t& o, uint32_t& pos) {
+  pos += s.step_pos;
+  o += s.step_o;
+  if (pos >= s.qpr) { pos -= s.qpr; ++o; }
+}
+__device__ __forceinline__ void cta_share(uint32_t nq, uint32_t& q_lo, uint32_t& q_hi) {
+  const uint32_t ngran = (nq + 31u) >> 5;
+  const uint32_t g0 = (uint32_t)(((uint64_t)ngran * blockIdx.x) / gridDim.x);
+  const uint32_t g1 = (uint32_t)(((uint64_t)ngran * (blockIdx.x + 1)) / gridDim.x);
+  q_lo = g0 << 5;
+  q_hi = (g1 << 5) < nq ? (g1 << 5) : nq;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -197,6 +240,91 @@ __global__ void __launch_bounds__(256) k_sas(float* __restrict__ out, const floa
         g = scale * clamp_sym(g * __fsqrt_rn(a), clamp_eps);
       }
       out[e] = g;
+    }
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// K1 vectorised production kernels (QuadSpan skeleton above)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_stable_A_vec(float* __restrict__ out, const QuadSpan span, int mode, StableParams sp,
+                                                      float clamp_a, const __grid_constant__ PhiloxKeys keys, uint64_t offset,
+                                                      int64_t sample_base) {
+  const PhiloxRef ph(keys);
+  __shared__ float s_a[kChunkQuads];
+  uint32_t q_lo, q_hi;
+  cta_share(span.nq, q_lo, q_hi);
+  for (uint32_t q0 = q_lo; q0 < q_hi; q0 += span.sub) {
+    const uint32_t q1 = q0 + span.sub < q_hi ? q0 + span.sub : q_hi;
+    const uint32_t o_first = span.fd.div(q0);
+    if (mode == DLPM_A_ISOTROPIC) {
+      const uint32_t o_last = span.fd.div(q1 - 1);
+      __syncthreads();
+      for (uint32_t sI = threadIdx.x; sI <= o_last - o_first; sI += 256)
+        s_a[sI] = clamp_A(sample_A(ph, sp, STREAM_A, offset, (uint64_t)((int64_t)(o_first + sI) + sample_base)), clamp_a);
+      __syncthreads();
+    }
+    uint32_t q = q0 + threadIdx.x, o, pos;
+    span.fd.divmod(q, o, pos);
+    for (; q < q1; q += 256) {
+      float4 v;
+      if (mode == DLPM_A_ISOTROPIC) {
+        const float a_iso = s_a[o - o_first];
+        v = make_float4(a_iso, a_iso, a_iso, a_iso);
+      } else {
+        v = element_A4(ph, sp, STREAM_A, offset, (uint64_t)((int64_t)o + sample_base), pos);
+        v.x = clamp_A(v.x, clamp_a); v.y = clamp_A(v.y, clamp_a); v.z = clamp_A(v.z, clamp_a); v.w = clamp_A(v.w, clamp_a);
+      }
+      st_stream(reinterpret_cast<float4*>(out) + q, v);
+      span_advance(span, o, pos);
+    }
+  }
+}
+
+// A_MODE as in k_sas
+template <int A_MODE, bool SCALED>
+__global__ void __launch_bounds__(256) k_sas_vec(float* __restrict__ out, const float* __restrict__ A_in, const QuadSpan span,
+                                                 StableParams sp, float clamp_eps, float scale, uint32_t g_stream,
+                                                 const __grid_constant__ PhiloxKeys keys, uint64_t offset, int64_t sample_base) {
+  const PhiloxRef ph(keys);
+  __shared__ float s_sa[(A_MODE == 1 || A_MODE == 3) ? kChunkQuads : 1];  // sqrt(A) of the samples touched by a sub-chunk
+  uint32_t q_lo, q_hi;
+  cta_share(span.nq, q_lo, q_hi);
+  for (uint32_t q0 = q_lo; q0 < q_hi; q0 += span.sub) {
+    const uint32_t q1 = q0 + span.sub < q_hi ? q0 + span.sub : q_hi;
+    const uint32_t o_first = span.fd.div(q0);
+    if (A_MODE == 1 || A_MODE == 3) {
+      const uint32_t o_last = span.fd.div(q1 - 1);
+      __syncthreads();
+      for (uint32_t sI = threadIdx.x; sI <= o_last - o_first; sI += 256)
+        s_sa[sI] = __fsqrt_rn(A_MODE == 1 ? sample_A(ph, sp, STREAM_EPS_A, offset, (uint64_t)((int64_t)(o_first + sI) + sample_base))
+                                          : __ldg(A_in + o_first + sI));
+      __syncthreads();
+    }
+    uint32_t q = q0 + threadIdx.x, o, pos;
+    span.fd.divmod(q, o, pos);
+    for (; q < q1; q += 256) {
+      const uint64_t sample = (uint64_t)((int64_t)o + sample_base);
+      float4 g = normal_quad(ph, g_stream, offset, sample, pos);
+      bool may_clamp = A_MODE != 0;
+      if (A_MODE == 1 || A_MODE == 3) {
+        const float sa_iso = s_sa[o - o_first];
+        g.x *= sa_iso; g.y *= sa_iso; g.z *= sa_iso; g.w *= sa_iso;
+        // |G| <= sqrt(-2 ln 2^-33) = 6.77 on this lattice: the clamp can only bite when 6.77 sqrt(A) exceeds it
+        may_clamp = sa_iso * 6.77f > clamp_eps;
+      } else if (A_MODE == 2 || A_MODE == 4) {
+        const float4 a = (A_MODE == 2) ? element_A4(ph, sp, STREAM_EPS_A, offset, sample, pos)
+                                       : ld_stream(reinterpret_cast<const float4*>(A_in) + q);
+        g.x *= __fsqrt_rn(a.x); g.y *= __fsqrt_rn(a.y); g.z *= __fsqrt_rn(a.z); g.w *= __fsqrt_rn(a.w);
+      }
+      if (may_clamp) {
+        g.x = clamp_sym(g.x, clamp_eps); g.y = clamp_sym(g.y, clamp_eps);
+        g.z = clamp_sym(g.z, clamp_eps); g.w = clamp_sym(g.w, clamp_eps);
+      }
+      if (SCALED && A_MODE != 0) { g.x *= scale; g.y *= scale; g.z *= scale; g.w *= scale; }
+      st_stream(reinterpret_cast<float4*>(out) + q, g);
+      span_advance(span, o, pos);
     }
   }
 }
@@ -367,41 +495,43 @@ __global__ void __launch_bounds__(256) k_reverse_step(float* __restrict__ x, con
 }
 
 // Production variant of the stochastic DLPM step (isotropic, compact Sigma, in-kernel noise, no clipping): the hot loop
-// of image sampling.  Block-contiguous chunks; the per-sample coefficients (bs*Gamma, sqrt(Gamma*Sigma_{t-1})) of the
-// samples touched by a chunk are computed once into shared memory with the reference's exact arithmetic; every thread
-// then streams UNROLL quads with all loads issued before the math (memory-level parallelism), z drawn in registers.
-template <bool EPS_BF16>
-__global__ void __launch_bounds__(256) k_reverse_step_fast(float* __restrict__ x, const void* __restrict__ eps,
-                                                           const float* __restrict__ Sigma, const float* __restrict__ sched,
-                                                           int t_imm, const int* __restrict__ t_dev, int T, int64_t B, int64_t D,
-                                                           uint64_t seed, uint64_t offset, int64_t sample_base,
-                                                           float* __restrict__ hist, FastDiv fd, int chunk) {
+// of image sampling, on the QuadSpan skeleton.  The per-sample coefficients (bs*Gamma, sqrt(Gamma*Sigma_{t-1})) of the
+// samples touched by a sub-chunk are computed once into shared memory with the reference's exact arithmetic; every
+// thread then streams UNROLL quads with all loads issued before the math (memory-level parallelism), z drawn in registers.
+template <bool EPS_BF16, int UNROLL, int OCC>
+__global__ void __launch_bounds__(256, OCC) k_reverse_step_fast(float* __restrict__ x, const void* __restrict__ eps,
+                                                              const float* __restrict__ Sigma, const float* __restrict__ sched,
+                                                              int t_imm, const int* __restrict__ t_dev, int T, int64_t B,
+                                                              const QuadSpan span, const __grid_constant__ PhiloxKeys keys,
+                                                              uint64_t offset, int64_t sample_base, float* __restrict__ hist) {
   pdl_launch_dependents();
   pdl_wait();
   const int t = t_dev ? *t_dev : t_imm;
   if (t < 1 || t >= T) return;
-  const Philox ph(seed);
+  const PhiloxRef ph(keys);
   const float4 row = __ldg(reinterpret_cast<const float4*>(sched) + t);
   const float inv_g = __frcp_rn(row.x);
   const uint64_t off_t = offset + (uint64_t)t;
-  const int64_t qpr = D >> 2, nq = B * qpr;
-  __shared__ float2 s_coef[kChunkQuads];  // (bs*Gamma, 1[t != 1] sqrt(Gamma*Sigma_{t-1})) per sample of the chunk
-  constexpr int UNROLL = 4;
-  for (int64_t q0 = (int64_t)blockIdx.x * chunk; q0 < nq; q0 += (int64_t)gridDim.x * chunk) {
-    const int64_t q1 = q0 + chunk < nq ? q0 + chunk : nq;
-    const int64_t b_first = (int64_t)fd.div((uint32_t)q0), b_last = (int64_t)fd.div((uint32_t)(q1 - 1));
+  __shared__ float2 s_coef[kChunkQuads];  // (bs*Gamma, 1[t != 1] sqrt(Gamma*Sigma_{t-1})) per sample of the sub-chunk
+  uint32_t q_lo, q_hi;
+  cta_share(span.nq, q_lo, q_hi);
+  for (uint32_t q0 = q_lo; q0 < q_hi; q0 += span.sub) {
+    const uint32_t q1 = q0 + span.sub < q_hi ? q0 + span.sub : q_hi;
+    const uint32_t b_first = span.fd.div(q0), b_last = span.fd.div(q1 - 1);
     __syncthreads();
-    for (int64_t sI = threadIdx.x; sI <= b_last - b_first; sI += blockDim.x) {
-      const int64_t b = b_first + sI;
+    for (uint32_t sI = threadIdx.x; sI <= b_last - b_first; sI += 256) {
+      const int64_t b = (int64_t)(b_first + sI);
       const StepCoef c = dlpm_coef(__ldg(Sigma + (int64_t)(t - 1) * B + b), __ldg(Sigma + (int64_t)t * B + b), row, t);
       s_coef[sI] = make_float2(c.c1, c.sd);
     }
     __syncthreads();
-    for (int64_t qb = q0 + threadIdx.x; qb < q1; qb += (int64_t)blockDim.x * UNROLL) {
+    uint32_t qb = q0 + threadIdx.x, o, pos;
+    span.fd.divmod(qb, o, pos);
+    for (; qb < q1; qb += 256 * UNROLL) {
       float4 xv[UNROLL], ev[UNROLL];
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
-        const int64_t q = qb + (int64_t)u * blockDim.x;
+        const uint32_t q = qb + (uint32_t)u * 256u;
         if (q < q1) {
           xv[u] = ld_rw(reinterpret_cast<const float4*>(x) + q);
           ev[u] = load_eps4<true, EPS_BF16>(eps, q);
@@ -409,20 +539,19 @@ __global__ void __launch_bounds__(256) k_reverse_step_fast(float* __restrict__ x
       }
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
-        const int64_t q = qb + (int64_t)u * blockDim.x;
+        const uint32_t q = qb + (uint32_t)u * 256u;
         if (q < q1) {
-          uint32_t b32, pos;
-          fd.divmod((uint32_t)q, b32, pos);
-          const float2 cf = s_coef[(int64_t)b32 - b_first];
-          const float4 zv = normal_quad(ph, STREAM_Z, off_t, (uint64_t)((int64_t)b32 + sample_base), pos);
-          float4 o;
-          o.x = fmaf(cf.y, zv.x, fmaf(-cf.x, ev[u].x, xv[u].x) * inv_g);
-          o.y = fmaf(cf.y, zv.y, fmaf(-cf.x, ev[u].y, xv[u].y) * inv_g);
-          o.z = fmaf(cf.y, zv.z, fmaf(-cf.x, ev[u].z, xv[u].z) * inv_g);
-          o.w = fmaf(cf.y, zv.w, fmaf(-cf.x, ev[u].w, xv[u].w) * inv_g);
-          reinterpret_cast<float4*>(x)[q] = o;
-          if (hist) st_stream(reinterpret_cast<float4*>(hist) + q, o);
+          const float2 cf = s_coef[o - b_first];
+          const float4 zv = normal_quad(ph, STREAM_Z, off_t, (uint64_t)((int64_t)o + sample_base), pos);
+          float4 r;
+          r.x = fmaf(cf.y, zv.x, fmaf(-cf.x, ev[u].x, xv[u].x) * inv_g);
+          r.y = fmaf(cf.y, zv.y, fmaf(-cf.x, ev[u].y, xv[u].y) * inv_g);
+          r.z = fmaf(cf.y, zv.z, fmaf(-cf.x, ev[u].z, xv[u].z) * inv_g);
+          r.w = fmaf(cf.y, zv.w, fmaf(-cf.x, ev[u].w, xv[u].w) * inv_g);
+          reinterpret_cast<float4*>(x)[q] = r;
+          if (hist) st_stream(reinterpret_cast<float4*>(hist) + q, r);
         }
+        span_advance(span, o, pos);
       }
     }
   }
@@ -518,6 +647,69 @@ __global__ void __launch_bounds__(256) k_lim_step(float* __restrict__ x, const v
   }
 }
 
+// LIM step on the QuadSpan skeleton (nq < 2^31, 16-byte aligned tensors)
+template <bool EPS_BF16>
+__global__ void __launch_bounds__(256) k_lim_step_vec(float* __restrict__ x, const void* __restrict__ mo,
+                                                      const float* __restrict__ coef, int step_imm,
+                                                      const int* __restrict__ step_dev, const QuadSpan span, int ode,
+                                                      int isotropic, StableParams sp, float clamp_eps,
+                                                      const float* __restrict__ e_L, const __grid_constant__ PhiloxKeys keys,
+                                                      uint64_t offset, int64_t sample_base, float* __restrict__ hist) {
+  const int step = step_dev ? *step_dev : step_imm;
+  const PhiloxRef ph(keys);
+  const float4 cf = __ldg(reinterpret_cast<const float4*>(coef) + step);  // (score_scale, a, c_score, c_noise)
+  const uint64_t off_s = offset + (uint64_t)step;
+  const bool iso_draw = !ode && !e_L && isotropic;
+  __shared__ float s_sa[kChunkQuads];
+  uint32_t q_lo, q_hi;
+  cta_share(span.nq, q_lo, q_hi);
+  for (uint32_t q0 = q_lo; q0 < q_hi; q0 += span.sub) {
+    const uint32_t q1 = q0 + span.sub < q_hi ? q0 + span.sub : q_hi;
+    const uint32_t b_first = span.fd.div(q0);
+    if (iso_draw) {
+      const uint32_t b_last = span.fd.div(q1 - 1);
+      __syncthreads();
+      for (uint32_t sI = threadIdx.x; sI <= b_last - b_first; sI += 256)
+        s_sa[sI] = __fsqrt_rn(sample_A(ph, sp, STREAM_EPS_A, off_s, (uint64_t)((int64_t)(b_first + sI) + sample_base)));
+      __syncthreads();
+    }
+    uint32_t q = q0 + threadIdx.x, b, pos;
+    span.fd.divmod(q, b, pos);
+    for (; q < q1; q += 256) {
+      const uint64_t sample = (uint64_t)((int64_t)b + sample_base);
+      const float4 xv = ld_rw(reinterpret_cast<const float4*>(x) + q);
+      const float4 mv = load_eps4<true, EPS_BF16>(mo, q);
+      float4 o;
+      o.x = __fadd_rn(__fmul_rn(cf.y, xv.x), __fmul_rn(cf.z, __fmul_rn(mv.x, cf.x)));
+      o.y = __fadd_rn(__fmul_rn(cf.y, xv.y), __fmul_rn(cf.z, __fmul_rn(mv.y, cf.x)));
+      o.z = __fadd_rn(__fmul_rn(cf.y, xv.z), __fmul_rn(cf.z, __fmul_rn(mv.z, cf.x)));
+      o.w = __fadd_rn(__fmul_rn(cf.y, xv.w), __fmul_rn(cf.z, __fmul_rn(mv.w, cf.x)));
+      if (!ode) {
+        float4 n4;
+        if (e_L) {
+          n4 = ld_stream(reinterpret_cast<const float4*>(e_L) + q);
+        } else {
+          n4 = normal_quad(ph, STREAM_G, off_s, sample, pos);
+          if (isotropic) {
+            const float sa = s_sa[b - b_first];
+            n4.x *= sa; n4.y *= sa; n4.z *= sa; n4.w *= sa;
+          } else {
+            const float4 a = element_A4(ph, sp, STREAM_EPS_A, off_s, sample, pos);
+            n4.x *= __fsqrt_rn(a.x); n4.y *= __fsqrt_rn(a.y); n4.z *= __fsqrt_rn(a.z); n4.w *= __fsqrt_rn(a.w);
+          }
+          n4.x = clamp_sym(n4.x, clamp_eps); n4.y = clamp_sym(n4.y, clamp_eps);
+          n4.z = clamp_sym(n4.z, clamp_eps); n4.w = clamp_sym(n4.w, clamp_eps);
+        }
+        o.x = __fadd_rn(o.x, __fmul_rn(cf.w, n4.x)); o.y = __fadd_rn(o.y, __fmul_rn(cf.w, n4.y));
+        o.z = __fadd_rn(o.z, __fmul_rn(cf.w, n4.z)); o.w = __fadd_rn(o.w, __fmul_rn(cf.w, n4.w));
+      }
+      reinterpret_cast<float4*>(x)[q] = o;
+      if (hist) st_stream(reinterpret_cast<float4*>(hist) + q, o);
+      span_advance(span, b, pos);
+    }
+  }
+}
+
 __global__ void k_advance(int* t, int delta) {
   pdl_launch_dependents();
   pdl_wait();
@@ -547,6 +739,51 @@ __global__ void __launch_bounds__(256) k_training_elements(float* __restrict__ x
     const float xt = __fadd_rn(__fmul_rn(row.y, x0[e]), __fmul_rn(__fsqrt_rn(Sig), zz));
     x_t[e] = xt;
     eps_t[e] = __fdiv_rn(__fsub_rn(xt, __fmul_rn(x0[e], row.y)), row.w);
+  }
+}
+
+// model-input scaling of the exploding schedule: one CTA column per sample row
+__global__ void __launch_bounds__(256) k_scale_by_step(float* __restrict__ out, const float* __restrict__ x,
+                                                       const float* __restrict__ table, const int64_t* __restrict__ t_vec,
+                                                       int t_imm, const int* __restrict__ t_dev, int T, int64_t B, int64_t D) {
+  const int64_t n = B * D, stride = (int64_t)gridDim.x * blockDim.x;
+  const int t_const = t_dev ? *t_dev : t_imm;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += stride) {
+    int64_t tb = t_vec ? t_vec[e / D] : (int64_t)t_const;
+    tb = tb < 0 ? 0 : (tb >= T ? T - 1 : tb);
+    out[e] = __fmul_rn(x[e], __ldg(table + tb));
+  }
+}
+
+// LIM training elements: one CTA per sample; the per-sample VPSDE coefficients use the precise libm functions
+__global__ void __launch_bounds__(256) k_lim_training_elements(float* __restrict__ x_t, float* __restrict__ score,
+                                                               const float* __restrict__ x0, const float* __restrict__ t,
+                                                               const float* __restrict__ e_in, int64_t D, float alpha,
+                                                               int isotropic, StableParams sp, float clamp_eps, uint64_t seed,
+                                                               uint64_t offset, int64_t sample_base) {
+  const Philox ph(seed);
+  const int64_t b = blockIdx.x;
+  const uint64_t sample = (uint64_t)(b + sample_base);
+  const float s = 0.008f;
+  const float HALF_PI = 1.57079632679489661923f;
+  // sde.py:41-47 in the reference's op order: log(cos((t + s) / (1 + s) * pi / 2)) - log_alpha_0
+  const float l0 = (float)log(cos((double)0.008 / (1.0 + 0.008) * 3.14159265358979323846 / 2.0));
+  const float la = __fsub_rn(logf(cosf(__fmul_rn(__fdiv_rn(__fadd_rn(t[b], s), 1.008f), HALF_PI))), l0);
+  const float x_coeff = expf(la);
+  const float sigma = powf(__fsub_rn(1.0f, expf(__fmul_rn(la, alpha))), 1.0f / alpha);
+  const float sa_iso = (!e_in && isotropic) ? __fsqrt_rn(sample_A(ph, sp, STREAM_EPS_A, offset, sample)) : 0.f;
+  for (int64_t i = threadIdx.x; i < D; i += blockDim.x) {
+    float ev;
+    if (e_in) {
+      ev = e_in[b * D + i];
+    } else {
+      const uint32_t pos = (uint32_t)(i >> 2);
+      const float g = sel4(normal_quad(ph, STREAM_G, offset, sample, pos), (int)(i & 3));
+      const float sa = isotropic ? sa_iso : __fsqrt_rn(sel4(element_A4(ph, sp, STREAM_EPS_A, offset, sample, pos), (int)(i & 3)));
+      ev = clamp_sym(g * sa, clamp_eps);
+    }
+    x_t[b * D + i] = __fadd_rn(__fmul_rn(x0[b * D + i], x_coeff), __fmul_rn(ev, sigma));
+    score[b * D + i] = __fdiv_rn(-ev, alpha);
   }
 }
 
@@ -598,6 +835,24 @@ static inline void chunk_grid(int64_t nq, int* chunk, int* grid) {
   *grid = (int)g;
 }
 
+static int g_k3_variant = 0;   // experiment switches (dlpm_b200_set_option): K3 unroll/occupancy variant,
+static int g_stream_ctas = 0;  // CTAs per SM override for the QuadSpan kernels (0 = per-kernel default)
+bool process_set_option(const char* name, int value) {
+  const std::string n(name);
+  if (n == "k3_variant") { g_k3_variant = value; return true; }
+  if (n == "stream_ctas") { g_stream_ctas = value; return true; }
+  return false;
+}
+
+// one full wave for the QuadSpan kernels: SMs x resident CTAs, never more CTAs than 256-quad tiles
+static inline int span_grid(const QuadSpan& sp, int ctas_per_sm) {
+  int64_t tiles = ((int64_t)sp.nq + 255) / 256;
+  int64_t g = (int64_t)kNumSMs * (g_stream_ctas > 0 ? g_stream_ctas : ctas_per_sm);
+  if (g > tiles) g = tiles;
+  return (int)(g < 1 ? 1 : g);
+}
+static inline bool span_ok(int64_t n_outer, int64_t inner) { return inner % 4 == 0 && n_outer * (inner / 4) < (1ll << 31); }
+
 }  // namespace dlpm
 
 using namespace dlpm;
@@ -620,7 +875,10 @@ int dlpm_b200_stable_A(float* out, int64_t n_outer, int64_t inner, int mode, flo
   int grid = grid_for(items, 256), chunk = 256;
   if (vec) chunk_grid(items, &chunk, &grid);
   const FastDiv fd((uint32_t)(vec ? inner / 4 : 1));
-  if (vec) k_stable_A<true><<<grid, 256, 0, s>>>(out, n_outer, inner, mode, sp, clamp_a, seed, offset, sample_base, fd, chunk);
+  if (vec && span_ok(n_outer, inner)) {
+    const QuadSpan span = make_span(n_outer, inner);
+    k_stable_A_vec<<<span_grid(span, 8), 256, 0, s>>>(out, span, mode, sp, clamp_a, make_philox_keys(seed), offset, sample_base);
+  } else if (vec) k_stable_A<true><<<grid, 256, 0, s>>>(out, n_outer, inner, mode, sp, clamp_a, seed, offset, sample_base, fd, chunk);
   else k_stable_A<false><<<grid, 256, 0, s>>>(out, n_outer, inner, mode, sp, clamp_a, seed, offset, sample_base, fd, chunk);
   DLPM_CHECK_LAUNCH("stable_A");
   return DLPM_OK;
@@ -631,7 +889,11 @@ static void launch_sas(bool vec, int grid, int chunk, cudaStream_t s, float* out
                        const StableParams& sp, float clamp_eps, float scale, uint32_t g_stream, uint64_t seed,
                        uint64_t offset, int64_t sample_base) {
   const FastDiv fd((uint32_t)(vec ? inner / 4 : 1));
-  if (vec) k_sas<true, A_MODE><<<grid, 256, 0, s>>>(out, A_in, n_outer, inner, sp, clamp_eps, scale, g_stream, seed, offset, sample_base, fd, chunk);
+  if (vec && span_ok(n_outer, inner)) {
+    const QuadSpan span = make_span(n_outer, inner);
+    if (scale == 1.0f) k_sas_vec<A_MODE, false><<<span_grid(span, 8), 256, 0, s>>>(out, A_in, span, sp, clamp_eps, scale, g_stream, make_philox_keys(seed), offset, sample_base);
+    else k_sas_vec<A_MODE, true><<<span_grid(span, 8), 256, 0, s>>>(out, A_in, span, sp, clamp_eps, scale, g_stream, make_philox_keys(seed), offset, sample_base);
+  } else if (vec) k_sas<true, A_MODE><<<grid, 256, 0, s>>>(out, A_in, n_outer, inner, sp, clamp_eps, scale, g_stream, seed, offset, sample_base, fd, chunk);
   else k_sas<false, A_MODE><<<grid, 256, 0, s>>>(out, A_in, n_outer, inner, sp, clamp_eps, scale, g_stream, seed, offset, sample_base, fd, chunk);
 }
 
@@ -697,11 +959,22 @@ static int launch_step(float* x, const void* eps, const float* Sigma, const floa
   const int grid = grid_for(vec ? B * D / 4 : B * D, 256);
   cudaStream_t s = (cudaStream_t)stream;
   const FastDiv fd((uint32_t)(vec ? D / 4 : 1));
-  if (MODE == 0 && vec && !z && !(flags & (DLPM_STEP_CLIP_DENOISED | DLPM_STEP_SIGMA_FULL)) && B * D / 4 < (1ll << 31)) {
-    int fgrid, chunk;
-    chunk_grid(B * D / 4, &chunk, &fgrid);
-    if (bf16) launch_ex(k_reverse_step_fast<true>, dim3(fgrid), dim3(256), 0, s, 1, x, eps, Sigma, sched, t, t_dev, T, B, D, seed, offset, sample_base, hist, fd, chunk);
-    else launch_ex(k_reverse_step_fast<false>, dim3(fgrid), dim3(256), 0, s, 1, x, eps, Sigma, sched, t, t_dev, T, B, D, seed, offset, sample_base, hist, fd, chunk);
+  if (MODE == 0 && vec && !z && !(flags & (DLPM_STEP_CLIP_DENOISED | DLPM_STEP_SIGMA_FULL)) && span_ok(B, D)) {
+    const QuadSpan span = make_span(B, D);
+    const PhiloxKeys keys = make_philox_keys(seed);
+#define LF(U, O)                                                                                                              \
+  do {                                                                                                                        \
+    const int fgrid = span_grid(span, g_stream_ctas > 0 ? g_stream_ctas : O);                                                 \
+    if (bf16) launch_ex(k_reverse_step_fast<true, U, O>, dim3(fgrid), dim3(256), 0, s, 1, x, eps, Sigma, sched, t, t_dev, T, B, span, keys, offset, sample_base, hist); \
+    else launch_ex(k_reverse_step_fast<false, U, O>, dim3(fgrid), dim3(256), 0, s, 1, x, eps, Sigma, sched, t, t_dev, T, B, span, keys, offset, sample_base, hist);     \
+  } while (0)
+    switch (g_k3_variant) {  // measured within 4 % of each other at B = 4096 (tools/bench_stream.py); (2, 6) is the default
+      case 1: LF(4, 4); break;
+      case 2: LF(2, 8); break;
+      case 3: LF(1, 8); break;
+      default: LF(2, 6); break;
+    }
+#undef LF
     DLPM_CHECK_LAUNCH("reverse_step");
     return DLPM_OK;
   }
@@ -749,7 +1022,13 @@ int dlpm_b200_lim_step(float* x, const void* model_out, const float* coef, int s
   cudaStream_t s = (cudaStream_t)stream;
   const FastDiv fd((uint32_t)(vec ? D / 4 : 1));
 #define L(V, H) k_lim_step<V, H><<<grid, 256, 0, s>>>(x, model_out, coef, step, step_dev, B, D, ode, isotropic, sp, clamp_eps, e_L, seed, offset, sample_base, hist_out, fd, chunk)
-  if (vec) { if (bf16) L(true, true); else L(true, false); }
+  if (vec && span_ok(B, D)) {
+    const QuadSpan span = make_span(B, D);
+    const PhiloxKeys keys = make_philox_keys(seed);
+    const int g = span_grid(span, 6);
+    if (bf16) k_lim_step_vec<true><<<g, 256, 0, s>>>(x, model_out, coef, step, step_dev, span, ode, isotropic, sp, clamp_eps, e_L, keys, offset, sample_base, hist_out);
+    else k_lim_step_vec<false><<<g, 256, 0, s>>>(x, model_out, coef, step, step_dev, span, ode, isotropic, sp, clamp_eps, e_L, keys, offset, sample_base, hist_out);
+  } else if (vec) { if (bf16) L(true, true); else L(true, false); }
   else { if (bf16) L(false, true); else L(false, false); }
 #undef L
   DLPM_CHECK_LAUNCH("lim_step");
@@ -774,6 +1053,30 @@ int dlpm_b200_training_elements(float* x_t, float* eps_t, const float* x0, const
   k_training_elements<<<grid_for(B * D, 256), 256, 0, (cudaStream_t)stream>>>(x_t, eps_t, x0, t, A, z, sched, T, B, D, sp,
                                                                               clamp_a, seed, offset, sample_base);
   DLPM_CHECK_LAUNCH("training_elements");
+  return DLPM_OK;
+}
+
+int dlpm_b200_scale_by_step(float* out, const float* x, const float* table, const int64_t* t_vec, int t, const int* t_dev,
+                            int T, int64_t B, int64_t D, void* stream) {
+  DLPM_REQUIRE(out && x && table, "scale_by_step: NULL tensor");
+  DLPM_REQUIRE(T >= 1 && B >= 0 && D >= 1, "scale_by_step: bad sizes");
+  DLPM_REQUIRE(t_vec || t_dev || (t >= 0 && t < T), "scale_by_step: t out of range [0, T)");
+  if (B == 0) return DLPM_OK;
+  k_scale_by_step<<<grid_for(B * D, 256), 256, 0, (cudaStream_t)stream>>>(out, x, table, t_vec, t, t_dev, T, B, D);
+  DLPM_CHECK_LAUNCH("scale_by_step");
+  return DLPM_OK;
+}
+
+int dlpm_b200_lim_training_elements(float* x_t, float* score, const float* x0, const float* t, const float* e, int64_t B,
+                                    int64_t D, float alpha, int isotropic, float clamp_eps, uint64_t seed, uint64_t offset,
+                                    int64_t sample_base, void* stream) {
+  DLPM_REQUIRE(x_t && score && x0 && t, "lim_training_elements: NULL tensor");
+  DLPM_REQUIRE(alpha > 0.f && alpha < 2.f, "lim_training_elements: heavy-tailed branch only (0 < alpha < 2)");
+  DLPM_REQUIRE(B >= 0 && B < (1ll << 31) && D >= 1, "lim_training_elements: bad sizes");
+  if (B == 0) return DLPM_OK;
+  k_lim_training_elements<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>(x_t, score, x0, t, e, D, alpha, isotropic, make_params(alpha),
+                                                                         clamp_eps, seed, offset, sample_base);
+  DLPM_CHECK_LAUNCH("lim_training_elements");
   return DLPM_OK;
 }
 

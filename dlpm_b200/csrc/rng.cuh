@@ -14,44 +14,75 @@ namespace dlpm {
 
 enum : uint32_t { STREAM_A = 0x0Au, STREAM_G = 0x06u, STREAM_Z = 0x5Au, STREAM_EPS_A = 0xEAu };
 
-struct Philox {
-  uint32_t k0, k1;
-  __device__ __forceinline__ Philox(uint64_t seed) : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)) {}
+// The ten round keys (k + r * Weyl constant).  The hot streaming kernels take them precomputed on the host as a
+// __grid_constant__ parameter, so every round's key is a constant-bank operand of the LOP3 (no per-iteration
+// UIADD3 key schedule); the other kernels build them in registers from the seed.  Both give the same stream.
+struct PhiloxKeys {
+  uint32_t a[10], b[10];
+};
+__host__ __device__ __forceinline__ PhiloxKeys make_philox_keys(uint64_t seed) {
+  PhiloxKeys k;
+  uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+  for (int r = 0; r < 10; ++r) {
+    k.a[r] = a;
+    k.b[r] = b;
+    a += 0x9E3779B9u;
+    b += 0xBB67AE85u;
+  }
+  return k;
+}
 
-  // 10 rounds, Salmon et al. 2011 constants.
-  __device__ __forceinline__ uint4 operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) const {
-    uint32_t a = k0, b = k1;
+// 10 rounds, Salmon et al. 2011 constants.  One round = 2 IMAD.WIDE + 2 three-input XORs.
+__device__ __forceinline__ uint4 philox_rounds(const PhiloxKeys& k, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
-      const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-      const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-      c0 = hi1 ^ c1 ^ a;
-      c1 = lo1;
-      c2 = hi0 ^ c3 ^ b;
-      c3 = lo0;
-      a += 0x9E3779B9u;
-      b += 0xBB67AE85u;
-    }
-    return make_uint4(c0, c1, c2, c3);
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    c0 = (uint32_t)(p1 >> 32) ^ c1 ^ k.a[r];
+    c1 = (uint32_t)p1;
+    c2 = (uint32_t)(p0 >> 32) ^ c3 ^ k.b[r];
+    c3 = (uint32_t)p0;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+struct Philox {  // keys in registers, built from the seed
+  PhiloxKeys k;
+  __device__ __forceinline__ Philox(uint64_t seed) : k(make_philox_keys(seed)) {}
+  __device__ __forceinline__ uint4 operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) const {
+    return philox_rounds(k, c0, c1, c2, c3);
+  }
+};
+struct PhiloxRef {  // keys in the kernel's parameter space (constant bank)
+  const PhiloxKeys& k;
+  __device__ __forceinline__ PhiloxRef(const PhiloxKeys& keys) : k(keys) {}
+  __device__ __forceinline__ uint4 operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) const {
+    return philox_rounds(k, c0, c1, c2, c3);
   }
 };
 
 // Counter layout shared by every kernel (documented in DESIGN.md):
 //   c0 = position inside the sample (in units of 4 variates), c1 = global sample index (low 32),
 //   c2 = call offset / diffusion step (low 32), c3 = stream tag | sample-index bits 32..39 << 8 | offset bits 32..47 << 16
-__device__ __forceinline__ uint4 philox_at(const Philox& ph, uint32_t stream, uint64_t offset, uint64_t sample,
-                                           uint32_t pos) {
+template <class P>
+__device__ __forceinline__ uint4 philox_at(const P& ph, uint32_t stream, uint64_t offset, uint64_t sample, uint32_t pos) {
   const uint32_t c3 = stream | ((uint32_t)((sample >> 32) & 0xFFu) << 8) | ((uint32_t)((offset >> 32) & 0xFFFFu) << 16);
   return ph(pos, (uint32_t)sample, (uint32_t)offset, c3);
 }
 
 // uniform in (0, 1] on the 32-bit lattice, centred: never 0 so log() is finite; small values are
 // exact, which is what the Gaussian tail (|z| up to 6.6) needs.
-__device__ __forceinline__ float u01(uint32_t x) { return fminf(((float)x + 0.5f) * 2.3283064365386963e-10f, 1.0f); }
+// ((float)x + 0.5f) * 2^-32 is at most exactly 1.0f (x rounds up to 2^32), so no clamp is needed.
+__device__ __forceinline__ float u01(uint32_t x) { return ((float)x + 0.5f) * 2.3283064365386963e-10f; }
 
 // uniform in [0, 1) with 23 bits, ALU-only (no I2F on the XU pipe).
 __device__ __forceinline__ float u01_fast(uint32_t x) { return __uint_as_float((x >> 9) | 0x3f800000u) - 1.0f; }
 
+// MUFU.LG2 without the denormal pre-scaling sequence of __log2f (3 extra instructions): arguments here are >= 2^-33.
+__device__ __forceinline__ float lg2_ftz(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float sqrt_approx(float x) {
   float y;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -60,9 +91,10 @@ __device__ __forceinline__ float sqrt_approx(float x) {
 
 // two N(0,1) from two 32-bit words (Box-Muller: lg2 + sqrt + sin + cos = 4 MUFU ops per pair).
 __device__ __forceinline__ float2 box_muller(uint32_t x, uint32_t y) {
-  const float r = sqrt_approx(-1.3862943611198906f * __log2f(u01(x)));  // sqrt(-2 ln u), ln u = ln2 * lg2 u
+  const float r = sqrt_approx(-1.3862943611198906f * lg2_ftz(u01(x)));  // sqrt(-2 ln u), ln u = ln2 * lg2 u
   float s, c;
-  __sincosf(6.28318530717958647692f * u01_fast(y), &s, &c);
+  // angle 2 pi m with m in [1, 2): one turn ahead of 2 pi (m - 1), same sine / cosine, saves the subtraction
+  __sincosf(6.28318530717958647692f * __uint_as_float((y >> 9) | 0x3f800000u), &s, &c);
   return make_float2(r * c, r * s);
 }
 
@@ -76,7 +108,7 @@ __device__ __forceinline__ float4 normal4(uint4 r) {
 __device__ __forceinline__ float exp1(uint32_t x) {
   const float d = fminf(((float)x + 0.5f) * 2.3283064365386963e-10f, 0.99999994f);
   const float series = d * (1.0f + d * (0.5f + d * (0.33333334f + d * 0.25f)));
-  const float full = -0.6931471805599453f * __log2f(1.0f - d);
+  const float full = -0.6931471805599453f * lg2_ftz(1.0f - d);
   return d < 0.03125f ? series : full;
 }
 
@@ -112,7 +144,7 @@ __device__ __forceinline__ float stable_A(const StableParams& p, uint32_t xu, ui
   const float s1 = sin_0_pi(p.ap * PI * u);
   const float s2 = sin_0_pi(p.one_m_ap * PI * u);
   const float w = exp1(xw);
-  const float l2 = __log2f(s1) - p.inv_ap * __log2f(sinU) + p.r * (__log2f(s2) - __log2f(w));
+  const float l2 = lg2_ftz(s1) - p.inv_ap * lg2_ftz(sinU) + p.r * (lg2_ftz(s2) - lg2_ftz(w));
   return 2.0f * exp2f(l2);
 }
 

@@ -72,8 +72,6 @@ class GenerativeLevyProcess:
                 "LIM only supports epsilon prediction, fixed variance and rescaled timesteps"  # noqa: E712
             self.sde = VPSDE(alpha, "cosine")
             self.levy = None  # the reference instantiates torchlevy.LevyStable here but never calls it
-        if input_scaling and scale == "scale_exploding":
-            raise NotImplementedError("input_scaling with the scale_exploding schedule is a 'next' row (SURVEY.md 8f-4)")
         self.dlpm = DLPM(alpha, device, diffusion_steps=reverse_steps, time_spacing=time_spacing, isotropic=isotropic,
                          scale=scale)
         self.graph_cache = {}
@@ -82,6 +80,23 @@ class GenerativeLevyProcess:
         if self.rescale_timesteps:
             return t.float() * (1.0 / self.reverse_steps)
         return t
+
+    def _input_scale_table(self):
+        """1 / (1 + barsigma_t) as a device (T,) table when the reference scales the model input
+        (GenerativeLevyProcess.py:177-180, :651-654: ``input_scaling`` with the 'scale_exploding' schedule), else None."""
+        if not (self.input_scaling and self.dlpm.scale == "scale_exploding"):
+            return None
+        return (1 / (1 + self.dlpm._sched_host[:, 3])).contiguous().to(self.device)
+
+    def _scaled_input(self, x, table, t_vec=None, t=0):
+        """x * table[t] (per-sample t_vec, or one batch-constant step) through dlpm_b200_scale_by_step."""
+        x = x.contiguous()
+        out = torch.empty_like(x)
+        B = x.shape[0]
+        _lib.call("dlpm_b200_scale_by_step", _lib.ptr(out), _lib.ptr(x), _lib.ptr(table),
+                  None if t_vec is None else _lib.ptr(t_vec.to(torch.int64).contiguous()), int(t), None, self.reverse_steps, B,
+                  x[0].numel(), _lib.stream_ptr())
+        return out
 
     def get_timesteps(self, N, **kwargs):
         return self.dlpm.get_timesteps(N)
@@ -96,7 +111,9 @@ class GenerativeLevyProcess:
         B = x.shape[0]
         assert t.shape == (B,)
         net = _Net(model, self.device)
-        eps = net(x, self._scale_timesteps(t), **(model_kwargs or {})).to(torch.float32).reshape(x.shape)
+        table = self._input_scale_table()
+        x_in = x if table is None else self._scaled_input(x.to(torch.float32), table, t_vec=t)
+        eps = net(x_in, self._scale_timesteps(t), **(model_kwargs or {})).to(torch.float32).reshape(x.shape)
         if clip_denoised:
             eps = self.dlpm.predict_eps(x, t, self.dlpm.predict_xstart(x, t, eps).clamp(-1, 1))
         mean, var = self.dlpm.anterior_mean_variance_dlpm(x, t[0], eps)
@@ -141,8 +158,9 @@ class GenerativeLevyProcess:
             flags = (_lib.STEP_CLIP_DENOISED if clip_denoised else 0) | (0 if d.isotropic else _lib.STEP_SIGMA_FULL)
             z_offset = st.reserve(T)
             mode = 1 if deterministic else 0
+            in_scale = self._input_scale_table()
             # (d) the hot loop
-            if net.kind == "mlp" and not model_kwargs and d.isotropic and self.rescale_timesteps:
+            if net.kind == "mlp" and not model_kwargs and d.isotropic and self.rescale_timesteps and in_scale is None:
                 m = net.model
                 _lib.call("dlpm_b200_mlp_sample_chain", _lib.ptr(x), _lib.ptr(m.packed_weights()), _lib.ptr(d.Sigmas),
                           _lib.ptr(d.sched), T, B, m.nfeatures, m.nunits, m.time_emb_size, m.nblocks_total, mode,
@@ -150,7 +168,7 @@ class GenerativeLevyProcess:
                           st.sample_base, _lib.stream_ptr())
             elif net.kind == "unet" and not model_kwargs and z is None and self.rescale_timesteps:
                 net.model.sample_loop(x, d, T, mode, flags, hist, st.seed, z_offset, st.sample_base,
-                                      graph_cache=self.graph_cache, progress=progress)
+                                      graph_cache=self.graph_cache, progress=progress, input_scale=in_scale)
             else:
                 bar = None
                 if progress:
@@ -158,7 +176,8 @@ class GenerativeLevyProcess:
                     bar = tqdm(total=T)
                 for k, t in enumerate(range(T - 1, 0, -1)):
                     tv = torch.full((B,), t, device=dev, dtype=torch.int64)
-                    eps = net(x.view(shape), self._scale_timesteps(tv), **(model_kwargs or {}))
+                    x_in = x if in_scale is None else self._scaled_input(x, in_scale, t=t)
+                    eps = net(x_in.view(shape), self._scale_timesteps(tv), **(model_kwargs or {}))
                     fl = flags | (_lib.STEP_EPS_BF16 if eps.dtype == torch.bfloat16 else 0)
                     eps = eps.contiguous() if eps.dtype == torch.bfloat16 else eps.to(torch.float32).contiguous()
                     h = _lib.ptr(hist[k + 1]) if hist is not None else None
@@ -280,7 +299,9 @@ class GenerativeLevyProcess:
             A_ext = A.repeat(monte_carlo_inner)
         x_t, eps_t = self.dlpm.get_one_rv_loss_elements(t_ext, x_ext, A_ext, inj.get("z"), state=st)
         net = _Net(model, dev)
-        model_eps = net(x_t, self._scale_timesteps(t_ext), **model_kwargs)
+        table = self._input_scale_table()
+        x_in = x_t if table is None else self._scaled_input(x_t, table, t_vec=t_ext)
+        model_eps = net(x_in, self._scale_timesteps(t_ext), **model_kwargs)
         losses = compute_loss_terms(model_eps.reshape(x_t.shape), eps_t, lploss)
         assert not torch.isnan(losses).any(), "Nan in losses"
         if loss_monte_carlo == "mean":
@@ -291,5 +312,33 @@ class GenerativeLevyProcess:
             return losses.mean()
         raise NotImplementedError(loss_monte_carlo)
 
-    def training_losses_lim(self, model, x_start, y=None, clamp_a=None, clamp_eps=None):
-        raise NotImplementedError("the LIM training loss (LIM/functions/loss.py) is a 'next' row (SURVEY.md 2.1 #3)")
+    def training_losses_lim(self, model, x_start, y=None, clamp_a=None, clamp_eps=None, injected=None, state=None):
+        """:680-709 + LIM/functions/loss.py:13-39 (forward + loss): t ~ U(1e-5, T_max), e ~ SaS drawn in-kernel,
+        x_t = x0 exp(l_t) + e sigma_t, target score = -e / alpha, loss = mean smooth-L1(model(x_t, t), score).
+        ``injected`` = dict(u, e) (the uniform variates and the noise) for parity tests."""
+        if self.sde.alpha == 2.0:
+            raise NotImplementedError("LIM with alpha == 2 (plain Gaussian VPSDE branch) is out of scope")
+        assert y is None, "class-conditional LIM training is not on the hot path"
+        dev = _lib.require_cuda(self.device)
+        self.dlpm.gen_a.setParams(clamp_a=clamp_a)
+        self.dlpm.gen_eps.setParams(clamp_eps=clamp_eps)
+        st = state or rng.default_state()
+        inj = injected or {}
+        x0 = x_start.to(dev, torch.float32).contiguous()
+        n = x0.size(0)
+        D = x0[0].numel()
+        start_eps = 1e-5
+        u = inj["u"].to(dev, torch.float32) if "u" in inj else torch.rand(n).to(dev)
+        t = (u * (self.sde.T - start_eps) + start_eps).contiguous()
+        e = inj["e"].to(dev, torch.float32).contiguous() if "e" in inj else None
+        x_t = torch.empty_like(x0)
+        score = torch.empty_like(x0)
+        with torch.cuda.device(dev):
+            _lib.call("dlpm_b200_lim_training_elements", _lib.ptr(x_t), _lib.ptr(score), _lib.ptr(x0), _lib.ptr(t), _lib.ptr(e), n, D,
+                      float(self.sde.alpha), 1 if self.isotropic else 0, -1.0 if clamp_eps is None else float(clamp_eps), st.seed,
+                      st.reserve(1), st.sample_base, _lib.stream_ptr())
+        net = _Net(model, dev)
+        output = net(x_t, t)
+        losses = compute_loss_terms(output.reshape(x_t.shape), score, 1.0)  # per-sample mean smooth-L1 (beta = 1)
+        assert not torch.isnan(losses).any(), "Nan in losses"
+        return losses.mean()  # all samples have D elements: mean of per-sample means == F.smooth_l1_loss(..., 'mean')

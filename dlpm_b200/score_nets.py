@@ -507,11 +507,13 @@ class UNetModel(nn.Module):
             eng.forward(xin, t[:1].contiguous() if uniform else t, None, 0.0, out, B)
         return out
 
-    def sample_loop(self, x, dlpm, T, mode, flags, hist, seed, z_offset, sample_base, graph_cache=None, progress=False):
+    def sample_loop(self, x, dlpm, T, mode, flags, hist, seed, z_offset, sample_base, graph_cache=None, progress=False,
+                    input_scale=None):
         """The image-config hot loop: per step  eps = UNet(x, t/T)  then the fused update (K3), with the step index
         in a device counter so ONE captured CUDA graph is replayed T-1 times."""
         from . import _unet_lib
-        _unet_lib.run_sample_loop(self, x, dlpm, T, mode, flags, hist, seed, z_offset, sample_base, graph_cache, progress)
+        _unet_lib.run_sample_loop(self, x, dlpm, T, mode, flags, hist, seed, z_offset, sample_base, graph_cache, progress,
+                                  input_scale=input_scale)
 
 
 def _unet_from_reference(ref, device):

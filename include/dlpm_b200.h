@@ -104,6 +104,21 @@ int dlpm_b200_training_elements(float* x_t, float* eps_t, const float* x0, const
                                 const float* z, const float* sched, int T, int64_t B, int64_t D, float alpha,
                                 float clamp_a, uint64_t seed, uint64_t offset, int64_t sample_base, void* stream);
 
+/* Model-input scaling of the scale_exploding schedule (GenerativeLevyProcess.py:177-180, :651-654):
+ *   out[b, :] = x[b, :] * table[t_b],   table = 1 / (1 + barsigma) (device float[T], host-computed).
+ * t_b = t_vec[b] (device int64[B], training) when t_vec != NULL; else the batch-constant *t_dev (graph replay) or t. */
+int dlpm_b200_scale_by_step(float* out, const float* x, const float* table, const int64_t* t_vec, int t, const int* t_dev,
+                            int T, int64_t B, int64_t D, void* stream);
+
+/* LIM training elements (LIM/functions/loss.py:13-31, GenerativeLevyProcess.py:680-709) for alpha < 2:
+ *   x_t = x0 * exp(l_b) + e * (1 - exp(alpha l_b))^(1/alpha),   score = -e / alpha,
+ *   l_b = log cos((t_b + s)/(1 + s) pi/2) - log cos(s/(1 + s) pi/2), s = 0.008   (sde.py:35-47, cosine VPSDE)
+ * t: device float[B] continuous times; e: injected SaS noise (B, D) or NULL -> clamp(sqrt(A) G) drawn in-kernel with the
+ * same streams as dlpm_b200_sas (isotropic: one A per sample). */
+int dlpm_b200_lim_training_elements(float* x_t, float* score, const float* x0, const float* t, const float* e, int64_t B,
+                                    int64_t D, float alpha, int isotropic, float clamp_eps, uint64_t seed, uint64_t offset,
+                                    int64_t sample_base, void* stream);
+
 /* Per-sample loss terms compute_loss_terms (GenerativeLevyProcess.py:19-31): lploss 2 -> sqrt(mean sq),
  * 1 -> mean smooth-L1(beta=1), -1 -> mean sq.  out[B]. pred may be bf16 (flag DLPM_STEP_EPS_BF16). */
 int dlpm_b200_loss_terms(float* out, const void* pred, const float* target, int64_t B, int64_t D, float lploss,

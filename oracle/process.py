@@ -107,14 +107,16 @@ def dlim_step(x_t, eps, t, sched, clip_denoised=False):
 
 
 def dlpm_sample_loop(model, x_init, A, z, alpha, T, time_spacing="linear",
-                     clip_denoised=False, deterministic=False, rescale_timesteps=True):
+                     clip_denoised=False, deterministic=False, rescale_timesteps=True, scale="scale_preserving",
+                     input_scaling=False):
     """p_sample_loop_progressive (GenerativeLevyProcess.py:291-330) / ddim loop (:413-452)
     with injected noise.
 
     x_init: the already-scaled x_{T-1} = barsigma_{T-1} * eps_init (:313);  A: (T, B, ...)
     full-shape subordinators (dlpm.py:226-227);  z: (T-1, B, ...) Gaussians, z[k] is used at
-    the k-th loop iteration (t = T-1-k).  Returns (final, history[T, B, ...])."""
-    sched = gen_noise_schedule(alpha, T, time_spacing)
+    the k-th loop iteration (t = T-1-k).  ``input_scaling`` with the 'scale_exploding' schedule feeds the network
+    x / (1 + barsigma_t) (GenerativeLevyProcess.py:177-180).  Returns (final, history[T, B, ...])."""
+    sched = gen_noise_schedule(alpha, T, time_spacing, scale)
     g, bg, s, bs = sched
     Sigmas = compute_Sigmas(A, g, s)
     x = x_init
@@ -123,7 +125,10 @@ def dlpm_sample_loop(model, x_init, A, z, alpha, T, time_spacing="linear",
     for k, t in enumerate(range(T - 1, 0, -1)):
         tt = torch.tensor([t] * B)
         tin = tt.float() * (1.0 / T) if rescale_timesteps else tt
-        eps = model(x, tin)
+        x_in = x
+        if input_scaling and scale == "scale_exploding":
+            x_in = x * _bc(1 / (1 + bs[tt]), x)
+        eps = model(x_in, tin)
         if deterministic:
             x = dlim_step(x, eps, t, sched, clip_denoised)
         else:
@@ -221,10 +226,30 @@ def one_rv_loss_elements(x0, t, A, z, bargammas, barsigmas):
     return x_t, eps_t
 
 
-def training_loss_dlpm(model, x0, t, A, z, alpha, T, lploss=2.0, rescale_timesteps=True):
+def training_loss_dlpm(model, x0, t, A, z, alpha, T, lploss=2.0, rescale_timesteps=True, scale="scale_preserving",
+                       input_scaling=False):
     """training_losses_dlpm with mean aggregation and M=1 (GenerativeLevyProcess.py:612-677)."""
-    g, bg, s, bs = gen_noise_schedule(alpha, T)
+    g, bg, s, bs = gen_noise_schedule(alpha, T, scale=scale)
     x_t, eps_t = one_rv_loss_elements(x0, t, A, z, bg, bs)
     tin = t.float() * (1.0 / T) if rescale_timesteps else t
-    model_eps = model(x_t, tin)
+    x_in = x_t
+    if input_scaling and scale == "scale_exploding":  # :651-654
+        x_in = x_t * _bc(1 / (1 + bs[t]), x_t)
+    model_eps = model(x_in, tin)
     return compute_loss_terms(model_eps, eps_t, lploss).mean()
+
+
+def lim_training_elements(x0, t, e, alpha):
+    """LIM/functions/loss.py:21-31: x_t = x0 * diffusion_coeff(t) + e * marginal_std(t);  score = -e / alpha (alpha != 2)."""
+    sde = VPSDE(alpha)
+    x_t = x0 * _bc(sde.diffusion_coeff(t), x0) + e * _bc(sde.marginal_std(t), x0)
+    return x_t, -e / alpha
+
+
+def training_loss_lim(model, x0, u, e, alpha):
+    """training_losses_lim (GenerativeLevyProcess.py:680-709) + loss_fn (LIM/functions/loss.py:13-39): t = u (T - 1e-5) + 1e-5,
+    loss = mean smooth-L1(model(x_t, t), score), beta = 1."""
+    sde = VPSDE(alpha)
+    t = u * (sde.T - 1e-5) + 1e-5
+    x_t, score = lim_training_elements(x0, t, e, alpha)
+    return torch.nn.functional.smooth_l1_loss(model(x_t, t), score, beta=1, reduction="mean")

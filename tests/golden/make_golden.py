@@ -50,10 +50,11 @@ def make_unet(cfg, in_ch):
 class TorchProxy(types.ModuleType):
     """Stands in for ``torch``/``th`` inside the reference module: pops injected tensors."""
 
-    def __init__(self, randn_list=None, randint_list=None):
+    def __init__(self, randn_list=None, randint_list=None, rand_list=None):
         super().__init__("torch_proxy")
         self._randn = list(randn_list or [])
         self._randint = list(randint_list or [])
+        self._rand = list(rand_list or [])
 
     def __getattr__(self, name):
         return getattr(torch, name)
@@ -63,6 +64,9 @@ class TorchProxy(types.ModuleType):
 
     def randint(self, *a, **kw):
         return self._randint.pop(0)
+
+    def rand(self, *a, **kw):
+        return self._rand.pop(0)
 
 
 def save(name, **arrays):
@@ -229,9 +233,75 @@ def golden_unet_full():
          nparams=np.int64(sum(p.numel() for p in model.parameters())))
 
 
+def golden_next_rows():
+    """scale_exploding schedule with input_scaling (sampling chain + training loss) and the LIM
+    training loss (GenerativeLevyProcess.py:177-180, :651-654, :680-709; LIM/functions/loss.py)."""
+    from oracle import stable
+    torch.manual_seed(0)
+    model = rerandomize_(ns.Model.MLPModel(mlp_params()), 11).eval()
+    out = sd_np(model)
+    alpha, T, B = 1.7, 30, 8
+    shape = (B, 1, 2)
+    # (1) sampling chain, exploding schedule, input scaling 1 / (1 + barsigma_t)
+    g = torch.Generator().manual_seed(15)
+    rs = np.random.RandomState(15)
+    A_compact = torch.stack([torch.from_numpy(stable.gen_skewed_levy(alpha, (B,), isotropic=True, rng=rs).copy()) for _ in range(T)])
+    eps_init = torch.from_numpy(stable.gen_sas(alpha, shape, isotropic=True, rng=rs))
+    z = torch.randn((T - 1,) + shape, generator=g)
+    glp = ns.glp.GenerativeLevyProcess(alpha, "cpu", T, rescale_timesteps=True, isotropic=True, scale="scale_exploding",
+                                       input_scaling=True)
+    A_list = [a.view(B, 1, 1).expand(*shape).contiguous() for a in A_compact]
+    glp.dlpm.gen_a.generate = lambda *a, **k: A_list.pop(0)
+    glp.dlpm.gen_eps.generate = lambda *a, **k: eps_init
+    ns.glp.th = TorchProxy(randn_list=list(z))
+    try:
+        final, hist = glp.p_sample_loop(model, shape, get_sample_history=True)
+    finally:
+        ns.glp.th = torch
+    out.update({"expl/A": A_compact.numpy(), "expl/eps_init": eps_init.numpy(), "expl/x_init": (glp.dlpm.barsigmas[-1] * eps_init).numpy(),
+                "expl/z": z.numpy(), "expl/final": final.numpy(), "expl/hist": hist.numpy(),
+                "expl/sched": torch.stack([glp.dlpm.gammas, glp.dlpm.bargammas, glp.dlpm.sigmas, glp.dlpm.barsigmas]).numpy()})
+    # (2) DLPM training loss with input scaling
+    Bt = 32
+    g = torch.Generator().manual_seed(19)
+    x0 = torch.randn(Bt, 1, 2, generator=g)
+    tt = torch.randint(1, T, size=[Bt], generator=g)
+    A = torch.from_numpy(stable.gen_skewed_levy(alpha, (Bt, 1, 2), isotropic=True, rng=np.random.RandomState(19)))
+    zz = torch.randn(Bt, 1, 2, generator=g)
+    glp.dlpm.gen_a.generate = lambda *a, **k: A
+    ns.glp.torch = TorchProxy(randn_list=[zz], randint_list=[tt])
+    try:
+        with torch.no_grad():
+            loss = glp.training_losses({"default": model}, x0, loss_type="EPS_LOSS", lploss=2.0)["loss"]
+    finally:
+        ns.glp.torch = torch
+    out.update({"expl_train/x0": x0.numpy(), "expl_train/t": tt.numpy(), "expl_train/A": A[:, 0, 0].numpy(), "expl_train/z": zz.numpy(),
+                "expl_train/loss": loss.numpy()})
+    # (3) LIM training loss: injected e (SaS) and t = rand * (T - 1e-5) + 1e-5
+    lim = ns.glp.GenerativeLevyProcess(alpha, "cpu", 50, rescale_timesteps=True, isotropic=True, LIM=True)
+    e = torch.from_numpy(stable.gen_sas(alpha, (Bt, 1, 2), isotropic=True, rng=np.random.RandomState(23)))
+    u = torch.rand(Bt, generator=torch.Generator().manual_seed(23))
+    lim.dlpm.gen_eps.generate = lambda *a, **k: e
+    ns.glp.torch = TorchProxy(rand_list=[u])
+    try:
+        with torch.no_grad():
+            lim_loss = lim.training_losses({"default": model}, x0, clamp_eps=None)["loss"]
+    finally:
+        ns.glp.torch = torch
+    t_c = u * (lim.sde.T - 1e-5) + 1e-5
+    out.update({"lim_train/x0": x0.numpy(), "lim_train/e": e.numpy(), "lim_train/u": u.numpy(), "lim_train/t": t_c.numpy(),
+                "lim_train/loss": lim_loss.numpy(), "lim_train/x_coeff": lim.sde.diffusion_coeff(t_c).numpy(),
+                "lim_train/sigma": lim.sde.marginal_std(t_c).numpy()})
+    save("next_rows", **out)
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["next_rows"]:
+        golden_next_rows()
+        sys.exit(0)
     golden_noise()
     golden_schedule()
     golden_mlp_chain()
     golden_unet()
     golden_unet_full()
+    golden_next_rows()

@@ -122,3 +122,55 @@ def test_sample_api_and_training_loss(model):
     np.testing.assert_allclose(loss["loss"].item(), float(r["loss"]), rtol=1e-4)
     free = glp.training_losses({"default": model}, torch.randn(256, 1, 2), loss_type="EPS_LOSS")["loss"]
     assert torch.isfinite(free) and free.dim() == 0
+
+
+def test_exploding_schedule_input_scaling_golden(model):
+    """'scale_exploding' schedule with input_scaling = x / (1 + barsigma_t) fed to the network
+    (GenerativeLevyProcess.py:177-180, :651-654): free-running chain and training loss vs the reference."""
+    from dlpm_b200 import GenerativeLevyProcess
+    g = load_golden("next_rows")
+    r = sub(g, "expl")
+    T, B = r["A"].shape
+    glp = GenerativeLevyProcess(1.7, "cuda", T, rescale_timesteps=True, isotropic=True, scale="scale_exploding", input_scaling=True)
+    np.testing.assert_array_equal(glp.dlpm._sched_host.t().numpy(), r["sched"])
+    final, hist = glp.p_sample_loop(model, list(r["x_init"].shape), noise=torch.from_numpy(r["x_init"]),
+                                    injected_A=torch.from_numpy(r["A"]), injected_z=torch.from_numpy(r["z"]), get_sample_history=True)
+    np.testing.assert_allclose(hist.cpu().numpy(), r["hist"], rtol=5e-3, atol=2e-3)
+    # without the scaling the chain must differ (the flag is really applied)
+    glp0 = GenerativeLevyProcess(1.7, "cuda", T, rescale_timesteps=True, isotropic=True, scale="scale_exploding", input_scaling=False)
+    _, hist0 = glp0.p_sample_loop(model, list(r["x_init"].shape), noise=torch.from_numpy(r["x_init"]),
+                                  injected_A=torch.from_numpy(r["A"]), injected_z=torch.from_numpy(r["z"]), get_sample_history=True)
+    assert not np.allclose(hist0.cpu().numpy(), r["hist"], rtol=5e-2, atol=2e-2)
+    tr = sub(g, "expl_train")
+    loss = glp.training_losses({"default": model}, torch.from_numpy(tr["x0"]), loss_type="EPS_LOSS", lploss=2.0,
+                               injected=dict(t=torch.from_numpy(tr["t"]), A=torch.from_numpy(tr["A"]), z=torch.from_numpy(tr["z"])))
+    np.testing.assert_allclose(loss["loss"].item(), float(tr["loss"]), rtol=1e-4)
+    # p_mean_variance API parity with per-sample scaling
+    x = torch.from_numpy(r["hist"][3]).cuda()
+    t = torch.full((B,), T - 4, device="cuda", dtype=torch.int64)
+    out = glp.p_mean_variance(model, x, t)
+    assert out["mean"].shape == x.shape and torch.isfinite(out["mean"]).all()
+
+
+def test_lim_training_loss_golden(model):
+    """LIM training loss (GenerativeLevyProcess.py:680-709, LIM/functions/loss.py) with injected (u, e) vs the reference,
+    in-kernel elements vs the oracle, and a free-running draw."""
+    from dlpm_b200 import GenerativeLevyProcess, _lib
+    from oracle import process
+    g = load_golden("next_rows")
+    r = sub(g, "lim_train")
+    glp = GenerativeLevyProcess(1.7, "cuda", 50, rescale_timesteps=True, isotropic=True, LIM=True)
+    x0, u, e = (torch.from_numpy(r[k]) for k in ("x0", "u", "e"))
+    loss = glp.training_losses({"default": model}, x0, injected=dict(u=u, e=e))["loss"]
+    np.testing.assert_allclose(loss.item(), float(r["loss"]), rtol=1e-4)
+    # elements kernel vs oracle
+    t = torch.from_numpy(r["t"])
+    x_t_o, score_o = process.lim_training_elements(x0, t, e, 1.7)
+    x_t, score = torch.empty_like(x0).cuda(), torch.empty_like(x0).cuda()
+    x0d, td, ed = x0.cuda(), t.cuda(), e.cuda()  # keep the device tensors alive across the call
+    _lib.call("dlpm_b200_lim_training_elements", _lib.ptr(x_t), _lib.ptr(score), _lib.ptr(x0d), _lib.ptr(td), _lib.ptr(ed),
+              x0.shape[0], 2, 1.7, 1, -1.0, 0, 0, 0, _lib.stream_ptr())
+    np.testing.assert_allclose(x_t.cpu().numpy(), x_t_o.numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(score.cpu().numpy(), score_o.numpy(), rtol=1e-6)
+    free = glp.training_losses({"default": model}, torch.randn(256, 1, 2), clamp_eps=20.0)["loss"]
+    assert torch.isfinite(free) and free.dim() == 0

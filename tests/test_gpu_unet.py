@@ -152,6 +152,36 @@ def test_graph_replayed_sampling_matches_direct_launches():
     assert x.shape == (2, 3, 32, 32)
 
 
+def test_exploding_input_scaling_image_loop():
+    """scale_exploding + input_scaling on the image net: the graph-replayed loop (scale kernel inside the
+    captured step, step index from the device counter), direct launches and the generic per-step path (the network called
+    as an opaque module on x * 1/(1+barsigma_t)) agree; and the scaling is really applied."""
+    from dlpm_b200 import GenerativeLevyProcess, rng
+    m, _ = make("cifar_half")
+
+    class Opaque(torch.nn.Module):  # hides native_kind -> generic per-step path of _reverse_loop
+        def __init__(self, inner):
+            super().__init__()
+            self.inner = inner
+
+        def forward(self, x, t):
+            return self.inner(x, t)
+
+    outs = {}
+    for tag, model, hist, scaling in (("graph", m, False, True), ("direct", m, True, True), ("generic", Opaque(m), False, True),
+                                      ("unscaled", m, False, False)):
+        glp = GenerativeLevyProcess(1.7, "cuda", 8, rescale_timesteps=True, isotropic=True, scale="scale_exploding",
+                                    input_scaling=scaling)
+        glp.dlpm.gen_a.setParams(clamp_a=20.0)
+        glp.dlpm.gen_eps.setParams(clamp_eps=200.0)
+        o = glp.p_sample_loop(model, [4, 3, 32, 32], get_sample_history=hist, state=rng.PhiloxState(seed=5, offset=0))
+        outs[tag] = o[0] if hist else o
+    assert torch.isfinite(outs["graph"]).all()
+    assert torch.equal(outs["graph"], outs["direct"])
+    np.testing.assert_allclose(outs["graph"].cpu().numpy(), outs["generic"].cpu().numpy(), rtol=2e-2, atol=2e-2)
+    assert not torch.allclose(outs["graph"], outs["unscaled"], rtol=1e-2, atol=1e-2)
+
+
 def test_lim_image_chain_golden_and_graph():
     """LIM SDE sampler on the image net: injected-noise chain vs the reference history, and the graph-replayed loop
     (times from a device table) vs direct launches."""

@@ -124,6 +124,38 @@ def test_training_loss_golden():
     np.testing.assert_allclose(loss.numpy(), r["loss"], rtol=1e-5)
 
 
+def test_exploding_schedule_input_scaling_golden():
+    """scale_exploding schedule + input_scaling, sampling chain and training loss vs the reference."""
+    g = load_golden("next_rows")
+    r = sub(g, "expl")
+    T, B = r["A"].shape
+    shape = r["x_init"].shape
+    sched = process.gen_noise_schedule(1.7, T, scale="scale_exploding")
+    np.testing.assert_array_equal(torch.stack(sched).numpy(), r["sched"])
+    A = torch.from_numpy(r["A"]).view(T, B, 1, 1).expand(T, *shape)
+    final, hist = process.dlpm_sample_loop(_mlp(g), torch.from_numpy(r["x_init"]), A, torch.from_numpy(r["z"]), 1.7, T,
+                                           scale="scale_exploding", input_scaling=True)
+    np.testing.assert_allclose(hist.numpy(), r["hist"], rtol=5e-3, atol=1e-3)
+    tr = sub(g, "expl_train")
+    x0 = torch.from_numpy(tr["x0"])
+    loss = process.training_loss_dlpm(_mlp(g), x0, torch.from_numpy(tr["t"]), torch.from_numpy(tr["A"]).view(-1, 1, 1).expand_as(x0),
+                                      torch.from_numpy(tr["z"]), 1.7, T, scale="scale_exploding", input_scaling=True)
+    np.testing.assert_allclose(loss.numpy(), tr["loss"], rtol=1e-5)
+
+
+def test_lim_training_loss_golden():
+    g = load_golden("next_rows")
+    r = sub(g, "lim_train")
+    x0, u, e = (torch.from_numpy(r[k]) for k in ("x0", "u", "e"))
+    sde = process.VPSDE(1.7)
+    t = u * (sde.T - 1e-5) + 1e-5
+    np.testing.assert_array_equal(t.numpy(), r["t"])
+    np.testing.assert_allclose(sde.diffusion_coeff(t).numpy(), r["x_coeff"], rtol=1e-6)
+    np.testing.assert_allclose(sde.marginal_std(t).numpy(), r["sigma"], rtol=1e-6)
+    loss = process.training_loss_lim(_mlp(g), x0, u, e, 1.7)
+    np.testing.assert_allclose(loss.numpy(), r["loss"], rtol=1e-5)
+
+
 UNET_CFGS = {
     "mnist": dict(model_channels=32, channel_mult=(1, 2, 2, 2), num_res_blocks=2, attention_resolutions=(2, 4),
                   num_heads=4, in_ch=1),

@@ -37,7 +37,7 @@ acc = None
 for _ in range(args.reps):
     prof = eng.profile(x, t, out, B)
     acc = [p[1] for p in prof] if acc is None else [min(a, p[1]) for a, p in zip(acc, prof)]
-names = {-1: "time_embedding", 0: "conv_in", 1: "groupnorm_silu", 2: "conv_tc", 3: "upsample2x", 4: "attention"}
+names = {-1: "time_embedding", 0: "conv_in", 1: "groupnorm_silu", 2: "conv_tc", 3: "upsample2x", 4: "attention", 5: "conv_in_split"}
 tot, flops = {}, {}
 for i, ((code, _, fl), ms) in enumerate(zip(prof, acc)):
     tot[names[code]] = tot.get(names[code], 0.0) + ms
