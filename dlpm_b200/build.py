@@ -22,7 +22,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr",
     "-I", os.path.join(ROOT, "include"),
-]
+] + os.environ.get("DLPM_B200_NVCC_EXTRA", "").split()  # e.g. -DDLPM_CONV_COALESCED_STORES=1 for A/B builds
 
 
 def _nvcc():

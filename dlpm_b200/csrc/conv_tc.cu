@@ -32,7 +32,13 @@ constexpr int kConvThreads = 256;
 constexpr int kConvThreadsEpi2 = 384;  // + warps 8-11: a second epilogue warp per TMEM lane quadrant (tiles with >= 2 column chunks)
 constexpr int kConvThreadsXF = 512;  // + warps 8-15: the eight transform warps (two per SM sub-partition)
 constexpr int kXfWarps = 8;
-constexpr int kSmemBudget = 220 * 1024;  // operand ring; barriers + alignment slack come on top (227 KB per CTA)
+constexpr int kSmemBudget = 204 * 1024;  // operand ring; epilogue staging, barriers, bias and alignment slack come on top (227 KB per CTA)
+constexpr int kEpiStageBytes = 2048;     // per epilogue warp: one 32-pixel x 32-channel bf16 chunk (64-byte rows, SWIZZLE_64B) for TMA stores
+constexpr int kEpiStageTotal = 8 * kEpiStageBytes;
+constexpr int kBiasSmemFloats = 1024;    // the layer's bias vector lives in shared memory: with the whole carve-out given to shared
+                                         // memory there is no L1 left and every bias load of every chunk went to L2
+constexpr int kSmemExtra = 1024 /*base alignment*/ + 1024 /*staging alignment*/ + kEpiStageTotal + (4 * kMaxStages + 4) * 8 + 16 +
+                           kBiasSmemFloats * 4;
 
 struct ConvKParams {
   int n_m_tiles, n_n_tiles, stages;
@@ -44,6 +50,7 @@ struct ConvKParams {
   int n_par, c_out_pad;   // n_par = 4: the four output-parity 2x2 convs of a folded upsample+conv3x3 share one launch
   int l2_prefetch, xf_dbg;
   int tall, stage_bytes;  // tall: one (Hb+2)-row activation box per (channel block, dx) serves the three dy taps
+  int tma_store;          // bf16 NHWC output through shared memory + cp.async.bulk.tensor stores (one 32 x 32 box per warp and chunk)
   int64_t B;
   int C_out, C_out_real, out_mode;
   const float* bias;
@@ -77,7 +84,8 @@ __host__ __device__ constexpr int conv_threads() { return XF ? kConvThreadsXF : 
 template <int BLOCK_N, int BLOCK_K, int CG, int KS, bool XF>
 __global__ void __launch_bounds__(conv_threads<BLOCK_N, XF>(), 1)
 k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmS0,
-          const __grid_constant__ CUtensorMap tmS1, const __grid_constant__ CUtensorMap tmB, const ConvKParams p) {
+          const __grid_constant__ CUtensorMap tmS1, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
+          const ConvKParams p) {
   constexpr int A_BYTES = 128 * BLOCK_K * 2;
   constexpr int B_ROWS = BLOCK_N / CG;
   constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
@@ -98,13 +106,16 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * STAGE_BYTES);
+  uint8_t* epi_stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem + p.stages * STAGE_BYTES) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + kEpiStageTotal);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* fullA_bar = empty_bar + kMaxStages;  // XF only
   uint64_t* xf_bar = fullA_bar + kMaxStages;     // XF only
   uint64_t* tfull_bar = xf_bar + kMaxStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);  // 16-byte aligned (the barrier block is a multiple of 16 bytes)
+  for (int i = threadIdx.x; i < p.c_out_pad; i += blockDim.x) s_bias[i] = __ldg(p.bias + i);  // weights: safe before pdl_wait
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // provably warp-uniform (see tc::elect_one)
   const int lane = threadIdx.x & 31;
@@ -125,6 +136,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     if (XF && p.c0_blocks < p.cin_blocks) prefetch_tmap(&tmA2);
     if (p.s0_blocks) prefetch_tmap(&tmS0);
     if (p.s1_blocks) prefetch_tmap(&tmS1);
+    if (p.tma_store) prefetch_tmap(&tmO);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -393,6 +405,14 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int eg = (warp - 4) >> 2;  // which half of the column chunks (EG == 2)
     const int m = q * 32 + lane;
     const int w_in = m % p.Wb, h_in = (m / p.Wb) % p.Hb, n_in = m / (p.Wb * p.Hb);
+    // TMA-store path: the warp's packed bf16 chunk (32 pixels x 64 bytes) is staged in shared memory in the SWIZZLE_64B
+    // pattern (16-byte granule ^= (row >> 1) & 3: conflict-free st.shared.v4) and leaves as ONE cp.async.bulk.tensor box.
+    // Measured (xf_dbg ablation, B = 512): per-lane 16-byte STG cost 0.55 ms of the 4.45 ms of convolutions per forward --
+    // 32 half-filled sectors per instruction on the SM -> L2 write path, with the epilogue on the critical path.
+    const uint32_t my_stage = smem_u32(epi_stage) + (uint32_t)(warp - 4) * kEpiStageBytes;
+    const uint32_t my_row = my_stage + (uint32_t)lane * 64u;
+    const int m0 = q * 32;  // first tile row of this warp: coordinates of the store box
+    const int w_box = m0 % p.Wb, h_box = (m0 / p.Wb) % p.Hb, n_box = m0 / (p.Wb * p.Hb);
     int it = 0;
     for (int item = first_item; item < n_items; item += item_stride, ++it) {
       const int par = item / items_per_par, it_in = item - par * items_per_par;
@@ -449,15 +469,22 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               if constexpr (CH == 32) tmem_ld_x32(t_row + c0, r);
               else tmem_ld_x16(t_row + c0, r);
               tmem_ld_wait();
+              if (CH == 32 && p.tma_store) {  // the staging buffer is free once the previous box has been read out
+                if (lane == 0) bulk_wait_read0();
+                __syncwarp();
+              }
               if (valid) {
                 const int col = nt * BLOCK_N + c0;
-                const float* bias = p.bias + col;
+                const uint32_t bias_s = smem_u32(s_bias) + (uint32_t)col * 4u;  // explicit shared-space address: LDS.128
                 __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + pixs[sub] * p.C_out + col;
 #pragma unroll
                 for (int j = 0; j < CH; j += 8) {
                   float v[8];
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[j + e]) + __ldg(bias + j + e);
+                  const float4 b0 = lds_f4(bias_s + j * 4), b1 = lds_f4(bias_s + j * 4 + 16);
+                  v[0] = __uint_as_float(r[j + 0]) + b0.x; v[1] = __uint_as_float(r[j + 1]) + b0.y;
+                  v[2] = __uint_as_float(r[j + 2]) + b0.z; v[3] = __uint_as_float(r[j + 3]) + b0.w;
+                  v[4] = __uint_as_float(r[j + 4]) + b1.x; v[5] = __uint_as_float(r[j + 5]) + b1.y;
+                  v[6] = __uint_as_float(r[j + 6]) + b1.z; v[7] = __uint_as_float(r[j + 7]) + b1.w;
                   if (has_res) {
                     uint4 rv;
                     if constexpr (RES_PREFETCH) rv = resv[sub][ci * (CH / 8) + j / 8];
@@ -470,7 +497,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                   __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
                   for (int e = 0; e < 4; ++e) op[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-                  *reinterpret_cast<uint4*>(dst + j) = o;
+                  if (CH == 32 && p.tma_store) sts_u4(my_row + (uint32_t)(((j >> 3) ^ ((lane >> 1) & 3)) << 4), o);
+                  else *reinterpret_cast<uint4*>(dst + j) = o;
                   if (do_stats) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
@@ -479,6 +507,15 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                       st[qi + 1] += fmaf(v[4 * h], v[4 * h], v[4 * h + 1] * v[4 * h + 1]) + fmaf(v[4 * h + 2], v[4 * h + 2], v[4 * h + 3] * v[4 * h + 3]);
                     }
                   }
+                }
+              }
+              if (CH == 32 && p.tma_store) {
+                fence_proxy_async_smem();  // generic-proxy st.shared -> visible to the TMA (async proxy) read
+                __syncwarp();
+                if (lane == 0) {  // rows of images beyond the batch are clipped by the tensor map bounds
+                  tma_store_4d(&tmO, reinterpret_cast<const void*>(epi_stage + (warp - 4) * kEpiStageBytes), nt * BLOCK_N + c0, w_box,
+                               h0 + sub * p.Hb + h_box, n0 + n_box);
+                  bulk_commit();
                 }
               }
             }
@@ -529,11 +566,14 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(tempty_bar + acc), 0));
+        // relaxed: the barrier only hands the TMEM stage back (tcgen05.fence above); a release here would wait for every
+        // outstanding global store of the warp to be acknowledged by L2, on the critical path of short-K layers
+        if (CG == 2) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(tempty_bar + acc), 0));
         else mbar_arrive(tempty_bar + acc);
       }
     }
   }
+  if (p.tma_store && warp >= 4 && warp < 4 + 4 * EG && lane == 0) bulk_wait0();  // this thread's TMA stores have completed
   tc_fence_before();
   __syncwarp();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
@@ -591,6 +631,20 @@ static int encode_weight_map(CUtensorMap* m, const void* base, int rows, int64_t
   return DLPM_OK;
 }
 
+static int encode_out_map(CUtensorMap* m, void* base, int64_t B, int H, int W, int C, int bw, int bh, int bi) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return DLPM_ERR_CUDA; }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bi};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(output [%lld,%d,%d,%d]) failed: %d", (long long)B, H, W, C, (int)r); return DLPM_ERR_CUDA; }
+  return DLPM_OK;
+}
+
+static int g_tma_store_enabled = 1;
 static int g_tall256_enabled = 1;
 static int g_xf_dbg = 0;  // timing experiments only: 1 = transform warps skip the math, 2 = skip the proxy fence
 static int g_l2_prefetch = 0;  // measured: no gain (the three-stage ring already covers the HBM latency)
@@ -602,6 +656,7 @@ int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, c
   const int C_in = C_in0 + C_in2;  // K channels per tap: the main input may be the concatenation [in | fuse->in2]
   DLPM_REQUIRE(!fuse || (fuse->ab != nullptr && (fuse->in2 == nullptr) == (C_in2 == 0)), "conv: bad fusion descriptor");
   DLPM_REQUIRE(in && w && bias && out, "conv: NULL tensor");
+  DLPM_REQUIRE(C_out <= kBiasSmemFloats, "conv: C_out must be <= 1024 (the bias vector is staged in shared memory)");
   DLPM_REQUIRE(C_in % 32 == 0 && C_in0 % 32 == 0, "conv: channel counts must be multiples of 32");
   DLPM_REQUIRE(geom.tap_rows >= 1 && geom.tap_rows <= 3 && geom.tap_cols >= 1 && geom.tap_cols <= 3, "conv: 1..3 taps per dimension");
   DLPM_REQUIRE(geom.out_scale == 1 || (geom.out_scale == 2 && stride == 1 && !skip0 && !skip1 && !residual &&
@@ -677,6 +732,14 @@ int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, c
   L->c_out_pad = C_out_pad;
   L->stats = nullptr;
   if ((rc = encode_weight_map(&L->tmB, w, C_out_pad * L->n_par, k_total, bn / L->cta_group, bk))) return rc;
+  // TMA-store epilogue: dense bf16 NHWC outputs with 32-channel chunks; an epilogue warp's 32 tile rows are a (bw, bh, bn) pixel box
+  L->tmO = L->tmB;
+  L->tma_store = (out_mode == CONV_OUT_BF16_NHWC && bn >= 32 && geom.out_scale == 1 && !fuse && g_tma_store_enabled &&
+                  (reinterpret_cast<uintptr_t>(out) & 15u) == 0) ? 1 : 0;
+  if (L->tma_store) {
+    const int bw = L->Wb < 32 ? L->Wb : 32, bh = L->Hb < 32 / bw ? L->Hb : 32 / bw, bi = 32 / (bw * bh);
+    if ((rc = encode_out_map(&L->tmO, out, B, H_out, W_out, C_out, bw, bh, bi))) return rc;
+  }
   return DLPM_OK;
 }
 
@@ -710,10 +773,10 @@ static int launch_t(const ConvLaunch& L, cudaStream_t stream) {
   const int STAGE = L.tall ? (L.msub * L.Hb + 2) * L.Wb * BK * 2 + 3 * B_BYTES : KS * (128 * BK * 2 + B_BYTES);
   int stages = kSmemBudget / STAGE;
   if (stages > kMaxStages) stages = kMaxStages;
-  const size_t smem = (size_t)stages * STAGE + 1024 /*align*/ + (4 * kMaxStages + 4) * 8 + 16;
+  const size_t smem = (size_t)stages * STAGE + kSmemExtra;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_conv_tc<BN, BK, CG, KS, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemBudget + 2048));
+    cudaError_t e = cudaFuncSetAttribute(k_conv_tc<BN, BK, CG, KS, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemBudget + kSmemExtra));
     if (e != cudaSuccess) return cuda_fail(e, "conv smem attribute");
     attr_set = true;
   }
@@ -724,6 +787,7 @@ static int launch_t(const ConvLaunch& L, cudaStream_t stream) {
   p.tap_cols = L.tap_cols; p.dy0 = L.dy0; p.dx0 = L.dx0; p.out_scale = L.out_scale; p.out_oy = L.out_oy; p.out_ox = L.out_ox;
   p.H_full = L.H_full; p.W_full = L.W_full;
   p.l2_prefetch = g_l2_prefetch; p.xf_dbg = g_xf_dbg;
+  p.tma_store = L.tma_store;
   p.tall = L.tall; p.stage_bytes = STAGE; p.n_par = L.n_par; p.c_out_pad = L.c_out_pad; p.msub = L.msub;
   p.B = L.B; p.C_out = L.C_out; p.C_out_real = L.C_out_real; p.out_mode = L.out_mode;
   p.bias = L.bias; p.residual = L.residual; p.out = L.out;
@@ -735,7 +799,7 @@ static int launch_t(const ConvLaunch& L, cudaStream_t stream) {
   const int grid = (n_items < max_groups ? n_items : max_groups) * CG;
   const int threads = conv_threads<BN, XF>();
   cudaError_t e = launch_ex(k_conv_tc<BN, BK, CG, KS, XF>, dim3(grid), dim3(threads), smem, stream, CG, L.tmA, L.tmA2, L.tmS0, L.tmS1,
-                            L.tmB, p);
+                            L.tmB, L.tmO, p);
   if (e != cudaSuccess) return cuda_fail(e, CG == 1 ? "conv_tc launch" : "conv_tc pair launch");
   return DLPM_OK;
 }
@@ -794,6 +858,10 @@ int dlpm_b200_set_option(const char* name, int value) {
   }
   if (std::string(name) == "conv_l2_prefetch") {
     g_l2_prefetch = value != 0;
+    return DLPM_OK;
+  }
+  if (std::string(name) == "conv_tma_store") {
+    g_tma_store_enabled = value != 0;
     return DLPM_OK;
   }
   if (std::string(name) == "conv_tall256") {

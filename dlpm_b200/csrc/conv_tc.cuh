@@ -12,6 +12,8 @@ enum ConvOutMode { CONV_OUT_BF16_NHWC = 0, CONV_OUT_F32_NCHW = 1 };
 struct ConvLaunch {
   CUtensorMap tmA, tmA2, tmS0, tmS1, tmB;  // main activation (+ second half of a concatenated input), two optional 1x1
                                            // skip-conv sources, packed weights
+  CUtensorMap tmO;                   // output tensor, box = one epilogue warp's 32 pixels x 32 channels (tma_store)
+  int tma_store;                     // 1 = the epilogue stages bf16 chunks in shared memory and stores them with TMA
   int block_n, block_k;              // tile N (16..256), K block in channels (64 or 32)
   int msub;                          // sub-tiles (128 pixels each) per CTA: 2 in tall mode when the image has an even tile count
   int tall;                          // 1 = one (Hb+2)-row activation box per (channel block, dx) feeds the three dy taps

@@ -304,7 +304,8 @@ __global__ void __launch_bounds__(256) k_sas_vec(float* __restrict__ out, const 
     }
     uint32_t q = q0 + threadIdx.x, o, pos;
     span.fd.divmod(q, o, pos);
-    for (; q < q1; q += 256) {
+    float4* optr = reinterpret_cast<float4*>(out) + q;  // running pointer: no per-iteration IMAD.WIDE on the fmaheavy pipe
+    for (; q < q1; q += 256, optr += 256) {
       const uint64_t sample = (uint64_t)((int64_t)o + sample_base);
       float4 g = normal_quad(ph, g_stream, offset, sample, pos);
       bool may_clamp = A_MODE != 0;
@@ -323,7 +324,7 @@ __global__ void __launch_bounds__(256) k_sas_vec(float* __restrict__ out, const 
         g.z = clamp_sym(g.z, clamp_eps); g.w = clamp_sym(g.w, clamp_eps);
       }
       if (SCALED && A_MODE != 0) { g.x *= scale; g.y *= scale; g.z *= scale; g.w *= scale; }
-      st_stream(reinterpret_cast<float4*>(out) + q, g);
+      st_stream(optr, g);
       span_advance(span, o, pos);
     }
   }

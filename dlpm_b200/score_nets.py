@@ -310,6 +310,9 @@ class UNetModel(nn.Module):
 
         def add_f(t):
             t = t.detach().to(dev, torch.float32).reshape(-1)
+            pad = (-t.numel()) % 4  # every fp32 parameter block starts 16-byte aligned (float4 reads in the epilogues)
+            if pad:
+                t = torch.cat([t, torch.zeros(pad, device=dev)])
             off = wf_len[0]
             wf_parts.append(t)
             wf_len[0] += t.numel()
