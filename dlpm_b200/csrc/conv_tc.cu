@@ -513,8 +513,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 fence_proxy_async_smem();  // generic-proxy st.shared -> visible to the TMA (async proxy) read
                 __syncwarp();
                 if (lane == 0) {  // rows of images beyond the batch are clipped by the tensor map bounds
-                  tma_store_4d(&tmO, reinterpret_cast<const void*>(epi_stage + (warp - 4) * kEpiStageBytes), nt * BLOCK_N + c0, w_box,
-                               h0 + sub * p.Hb + h_box, n0 + n_box);
+                  const void* src = reinterpret_cast<const void*>(epi_stage + (warp - 4) * kEpiStageBytes);
+                  if (p.out_scale == 2)  // folded upsample: the output seen as [B*H_out][py][W_out][px][C], one parity per box
+                    tma_store_5d(&tmO, src, nt * BLOCK_N + c0, out_ox, w_box, out_oy, (n0 + n_box) * p.H_out + h0 + sub * p.Hb + h_box);
+                  else
+                    tma_store_4d(&tmO, src, nt * BLOCK_N + c0, w_box, h0 + sub * p.Hb + h_box, n0 + n_box);
                   bulk_commit();
                 }
               }
@@ -644,6 +647,21 @@ static int encode_out_map(CUtensorMap* m, void* base, int64_t B, int H, int W, i
   return DLPM_OK;
 }
 
+// Output of a folded upsample conv (pixels (2h + py, 2w + px)) as the 5-D view [B*H_out][py][W_out][px][C] of the dense
+// [B][2 H_out][2 W_out][C] tensor: a parity's 32-pixel warp box is (32 ch, 1, bw, 1, rows) -- no element strides needed.
+static int encode_out_map_up(CUtensorMap* m, void* base, int64_t B, int H_out, int W_out, int C, int bw, int rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return DLPM_ERR_CUDA; }
+  cuuint64_t dims[5] = {(cuuint64_t)C, 2, (cuuint64_t)W_out, 2, (cuuint64_t)(B * H_out)};
+  cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)C * 4, (cuuint64_t)W_out * C * 4, (cuuint64_t)W_out * C * 8};
+  cuuint32_t box[5] = {32, 1, (cuuint32_t)bw, 1, (cuuint32_t)rows};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(upsampled output [%lld,%d,%d,%d]) failed: %d", (long long)B, H_out, W_out, C, (int)r); return DLPM_ERR_CUDA; }
+  return DLPM_OK;
+}
+
 static int g_tma_store_enabled = 1;
 static int g_tall256_enabled = 1;
 static int g_xf_dbg = 0;  // timing experiments only: 1 = transform warps skip the math, 2 = skip the proxy fence
@@ -734,11 +752,13 @@ int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, c
   if ((rc = encode_weight_map(&L->tmB, w, C_out_pad * L->n_par, k_total, bn / L->cta_group, bk))) return rc;
   // TMA-store epilogue: dense bf16 NHWC outputs with 32-channel chunks; an epilogue warp's 32 tile rows are a (bw, bh, bn) pixel box
   L->tmO = L->tmB;
-  L->tma_store = (out_mode == CONV_OUT_BF16_NHWC && bn >= 32 && geom.out_scale == 1 && !fuse && g_tma_store_enabled &&
-                  (reinterpret_cast<uintptr_t>(out) & 15u) == 0) ? 1 : 0;
+  L->tma_store = (out_mode == CONV_OUT_BF16_NHWC && bn >= 32 && !fuse && g_tma_store_enabled && (reinterpret_cast<uintptr_t>(out) & 15u) == 0 &&
+                  B * H_out < (1ll << 31)) ? 1 : 0;
   if (L->tma_store) {
     const int bw = L->Wb < 32 ? L->Wb : 32, bh = L->Hb < 32 / bw ? L->Hb : 32 / bw, bi = 32 / (bw * bh);
-    if ((rc = encode_out_map(&L->tmO, out, B, H_out, W_out, C_out, bw, bh, bi))) return rc;
+    if (geom.out_scale == 2) rc = encode_out_map_up(&L->tmO, out, B, H_out, W_out, C_out, bw, bh * bi);
+    else rc = encode_out_map(&L->tmO, out, B, H_out, W_out, C_out, bw, bh, bi);
+    if (rc) return rc;
   }
   return DLPM_OK;
 }
