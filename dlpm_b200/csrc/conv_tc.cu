@@ -76,6 +76,23 @@ struct ConvKParams {
 // be the virtual concatenation of two tensors (tmA | tmA2).  Barrier chain per stage:
 //   TMA(A) -> fullA (local) -> transform warps -> xf (leader, 8 x CG arrivals) -+-> MMA -> empty
 //   TMA(B) -> full (leader) ----------------------------------------------------+
+// Order of the pipeline stages of a "tall" work item: 3 * cin_blocks main stages (activation box + three weight tiles, 12..24
+// MMAs each) and the 1x1 skip-conv stages (one K block, 4..8 MMAs each).  Run back to back, the skip stages leave the
+// three-stage ring with less MMA work in flight than a TMA round trip takes; spread evenly between the main stages
+// (Bresenham) every window of three stages carries enough.  Stage 0 is always a main stage.
+__device__ __forceinline__ void tall_slot(int sb, int n_main, int n_skip, bool interleave, bool& main_part, int& idx) {
+  if (!interleave || n_skip == 0) {
+    main_part = sb < n_main;
+    idx = main_part ? sb : sb - n_main;
+    return;
+  }
+  const int n_sb = n_main + n_skip;
+  const int before = (sb * n_skip) / n_sb;
+  const bool is_skip = ((sb + 1) * n_skip) / n_sb > before;
+  main_part = !is_skip;
+  idx = is_skip ? before : sb - before;
+}
+
 template <int BLOCK_N, bool XF>
 __host__ __device__ constexpr int conv_epi_groups() { return (BLOCK_N >= 64 && !XF) ? 2 : 1; }
 template <int BLOCK_N, bool XF>
@@ -192,7 +209,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             mbar_wait(empty_bar + stage, phase ^ 1);
             uint8_t* a_dst = smem + stage * STAGE_BYTES;
             uint8_t* b_dst = a_dst + a_tall_bytes;
-            const bool main_part = sb < 3 * p.cin_blocks;
+            bool main_part; int slot_idx;
+            tall_slot(sb, 3 * p.cin_blocks, p.s0_blocks + p.s1_blocks, !XF, main_part, slot_idx);
             const int a_bytes = main_part ? a_tall_bytes : msub * A_BYTES, b_bytes = main_part ? 3 * B_BYTES : B_BYTES;
             // XF: activations complete on this CTA's own fullA barrier (its transform warps wait there), weights on full
             const int bytes = XF ? b_bytes : a_bytes + b_bytes;
@@ -206,7 +224,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             if (XF) mbar_expect_tx_e(elected, fullA_bar + stage, a_bytes);
             const int brow = brow0;
             if (main_part) {
-              const int cblk = sb / 3, dxi = sb - cblk * 3;
+              const int cblk = slot_idx / 3, dxi = slot_idx - cblk * 3;
               if (XF) {
                 const bool src0 = cblk < p.c0_blocks;
                 tma_load_4d_e(elected, src0 ? &tmA : &tmA2, fullA_bar + stage, a_dst, (src0 ? cblk : cblk - p.c0_blocks) * BLOCK_K, dxi - 1, h0 - 1, n0);
@@ -219,7 +237,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 else tma_load_2d_e(elected, &tmB, full_bar + stage, b_dst + j * B_BYTES, kcol, brow);
               }
             } else {
-              const int e = sb - 3 * p.cin_blocks;
+              const int e = slot_idx;
               const CUtensorMap* map = e < p.s0_blocks ? &tmS0 : &tmS1;
               const int c_a = (e < p.s0_blocks ? e : e - p.s0_blocks) * BLOCK_K;
               const int kcol = (main_blocks + e) * BLOCK_K;
@@ -294,7 +312,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             tc_fence_after();
             const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
             const uint32_t b_addr = a_addr + a_tall_bytes;
-            const bool main_part = sb < 3 * p.cin_blocks;
+            bool main_part; int slot_idx;
+            tall_slot(sb, 3 * p.cin_blocks, p.s0_blocks + p.s1_blocks, !XF, main_part, slot_idx);
             const int n_j = main_part ? 3 : 1;
             for (int j = 0; j < n_j; ++j) {
               for (int sub = 0; sub < msub; ++sub) {
