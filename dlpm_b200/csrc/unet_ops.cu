@@ -470,6 +470,130 @@ __global__ void __launch_bounds__(256) k_attention(__nv_bfloat16* __restrict__ o
   }
 }
 
+// Tensor-core form of K7 for head dims 16 / 32 / 64 and L a multiple of 16 (every attention block of the shipped configs:
+// MNIST L = 256 / 64 with d = 16 -- 58 % of that network's forward with the FMA kernel above -- and CIFAR L = 16, d = 64).
+// Flash-attention dataflow on mma.sync.m16n8k16 (bf16 in, fp32 accumulate): a warp owns 16 query rows, walks the keys in
+// blocks of 64 with an online softmax in the exp2 domain, and feeds the S accumulator fragments straight back as the A
+// operand of P.V (the m16n8 accumulator layout of two adjacent key tiles IS the m16k16 A layout).  K sits in shared memory
+// row-major with (D+8)-element rows, V transposed with (L+8)-element rows: both B-fragment reads are conflict-free 32-bit
+// loads.  The contraction dims here (d = 16..64, 16..256 keys) are far below a tcgen05 tile (M = 128 per CTA, operands via
+// TMA descriptors); the warp-level MMA is the right granularity for this 0.3 % of the FLOPs.
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+template <int D>
+__global__ void __launch_bounds__(128) k_attention_mma(__nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ qkv, int L,
+                                                       int C, int heads, int q_blocks) {
+  constexpr int KSTR = D + 8;
+  extern __shared__ __align__(16) uint8_t att_smem[];
+  pdl_launch_dependents();
+  pdl_wait();
+  __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(att_smem);  // [L][KSTR]
+  __nv_bfloat16* Vt = Ks + (size_t)L * KSTR;                        // [D][L + 8]
+  const int VSTR = L + 8;
+  const int qb = blockIdx.x % q_blocks, nh = blockIdx.x / q_blocks;
+  const int n = nh / heads, h = nh % heads;
+  const __nv_bfloat16* base = qkv + (int64_t)n * L * 3 * C + h * 3 * D;  // per head: q | k | v blocks of D channels
+  const int64_t rs = (int64_t)3 * C;                                      // row stride of qkv in elements
+  for (int i = threadIdx.x; i < L * (D / 8); i += blockDim.x) {
+    const int s = i / (D / 8), d8 = (i - s * (D / 8)) * 8;
+    const uint4 kr = __ldg(reinterpret_cast<const uint4*>(base + s * rs + D + d8));
+    const uint4 vr = __ldg(reinterpret_cast<const uint4*>(base + s * rs + 2 * D + d8));
+    *reinterpret_cast<uint4*>(Ks + s * KSTR + d8) = kr;
+    const __nv_bfloat16* ve = reinterpret_cast<const __nv_bfloat16*>(&vr);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) Vt[(d8 + e) * VSTR + s] = ve[e];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int r0 = qb * 64 + warp * 16;
+  if (r0 >= L) return;
+  uint32_t qa[D / 16][4];
+#pragma unroll
+  for (int kk = 0; kk < D / 16; ++kk) {
+    const __nv_bfloat16* q0 = base + (r0 + g) * rs + kk * 16 + 2 * t;
+    qa[kk][0] = __ldg(reinterpret_cast<const uint32_t*>(q0));
+    qa[kk][1] = __ldg(reinterpret_cast<const uint32_t*>(q0 + 8 * rs));
+    qa[kk][2] = __ldg(reinterpret_cast<const uint32_t*>(q0 + 8));
+    qa[kk][3] = __ldg(reinterpret_cast<const uint32_t*>(q0 + 8 * rs + 8));
+  }
+  // softmax(q.k / sqrt(d)) (unet.py:244-247: q and k are each scaled by d^-1/4), evaluated as exp2((s - m) * log2 e / sqrt(d))
+  const float sl2 = rsqrtf((float)D) * 1.4426950408889634f;
+  float o[D / 8][4];
+#pragma unroll
+  for (int nd = 0; nd < D / 8; ++nd) { o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f; }
+  float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
+  for (int kb = 0; kb < L; kb += 64) {
+    const int nkt = (L - kb) >= 64 ? 8 : (L - kb) / 8;  // valid 8-key tiles of this block (L is a multiple of 16)
+    float sc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+      if (j < nkt) {
+        const __nv_bfloat16* kr = Ks + (kb + j * 8 + g) * KSTR + 2 * t;
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk)
+          mma_bf16_16816(sc[j], qa[kk], *reinterpret_cast<const uint32_t*>(kr + kk * 16), *reinterpret_cast<const uint32_t*>(kr + kk * 16 + 8));
+#pragma unroll
+        for (int e = 0; e < 4; ++e) sc[j][e] *= sl2;
+      } else {
+        sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = -INFINITY;
+      }
+    }
+    float mx_lo = m_lo, mx_hi = m_hi;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      mx_lo = fmaxf(mx_lo, fmaxf(sc[j][0], sc[j][1]));
+      mx_hi = fmaxf(mx_hi, fmaxf(sc[j][2], sc[j][3]));
+    }
+    mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1)); mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
+    mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1)); mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
+    const float c_lo = exp2f(m_lo - mx_lo), c_hi = exp2f(m_hi - mx_hi);
+    m_lo = mx_lo; m_hi = mx_hi;
+    l_lo *= c_lo; l_hi *= c_hi;
+#pragma unroll
+    for (int nd = 0; nd < D / 8; ++nd) { o[nd][0] *= c_lo; o[nd][1] *= c_lo; o[nd][2] *= c_hi; o[nd][3] *= c_hi; }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sc[j][0] = exp2f(sc[j][0] - m_lo); sc[j][1] = exp2f(sc[j][1] - m_lo);
+      sc[j][2] = exp2f(sc[j][2] - m_hi); sc[j][3] = exp2f(sc[j][3] - m_hi);
+      l_lo += sc[j][0] + sc[j][1];
+      l_hi += sc[j][2] + sc[j][3];
+    }
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      if (2 * ks < nkt) {
+        uint32_t pa[4];
+        pa[0] = pack_bf16(sc[2 * ks][0], sc[2 * ks][1]);
+        pa[1] = pack_bf16(sc[2 * ks][2], sc[2 * ks][3]);
+        pa[2] = pack_bf16(sc[2 * ks + 1][0], sc[2 * ks + 1][1]);
+        pa[3] = pack_bf16(sc[2 * ks + 1][2], sc[2 * ks + 1][3]);
+        const __nv_bfloat16* vr = Vt + g * VSTR + kb + ks * 16 + 2 * t;
+#pragma unroll
+        for (int nd = 0; nd < D / 8; ++nd)
+          mma_bf16_16816(o[nd], pa, *reinterpret_cast<const uint32_t*>(vr + nd * 8 * VSTR), *reinterpret_cast<const uint32_t*>(vr + nd * 8 * VSTR + 8));
+      }
+    }
+  }
+  l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1); l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
+  l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1); l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
+  const float i_lo = 1.0f / l_lo, i_hi = 1.0f / l_hi;
+  __nv_bfloat16* d_lo = out + ((int64_t)n * L + r0 + g) * C + h * D + 2 * t;
+  __nv_bfloat16* d_hi = d_lo + (int64_t)8 * C;
+#pragma unroll
+  for (int nd = 0; nd < D / 8; ++nd) {
+    *reinterpret_cast<uint32_t*>(d_lo + nd * 8) = pack_bf16(o[nd][0] * i_lo, o[nd][1] * i_lo);
+    *reinterpret_cast<uint32_t*>(d_hi + nd * 8) = pack_bf16(o[nd][2] * i_hi, o[nd][3] * i_hi);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Network input for the tensor-core input conv: NCHW fp32 [B, C, H, W] -> NHWC bf16 [B, H, W, 32] holding the bf16
 // SPLIT of every value, x = hi + lo (+ O(2^-17 |x|)):  channels [0,C) = hi, [C,2C) = lo, [2C,3C) = hi, rest 0.
@@ -768,19 +892,41 @@ int dlpm_b200_groupnorm_fold(float* ab, int C0, const float* stats0, int parts0,
   return DLPM_OK;
 }
 
+static int g_attention_mma = 1;  // dlpm_b200_set_option("attention_mma", 0): FMA kernel (A/B and fallback for other shapes)
+namespace dlpm { void attention_set_mma(int on) { g_attention_mma = on; } }
+
 int dlpm_b200_attention(void* out, const void* qkv, int64_t B, int L, int C, int heads, void* stream) {
   DLPM_REQUIRE(out && qkv, "attention: NULL tensor");
   DLPM_REQUIRE(heads >= 1 && C % heads == 0 && L >= 1 && L <= 1024, "attention: bad shape");
   const int D = C / heads;
   DLPM_REQUIRE(B * heads < (1ll << 31), "attention: batch too large");
   if (B == 0) return DLPM_OK;
+  auto* o = reinterpret_cast<__nv_bfloat16*>(out);
+  auto* q = reinterpret_cast<const __nv_bfloat16*>(qkv);
+  cudaStream_t s = (cudaStream_t)stream;
+  {  // tensor-core path
+    const size_t msmem = ((size_t)L * (D + 8) + (size_t)D * (L + 8)) * 2;
+    const int q_blocks = (L + 63) / 64;
+    if ((D == 16 || D == 32 || D == 64) && L % 16 == 0 && msmem <= 200 * 1024 && B * heads * q_blocks < (1ll << 31) && g_attention_mma) {
+      const int mthreads = L >= 64 ? 128 : (L / 16) * 32;
+      const unsigned mgrid = (unsigned)(B * heads * q_blocks);
+#define ATTM(DD)                                                                                                     \
+  case DD: {                                                                                                         \
+    cudaError_t e = cudaFuncSetAttribute(k_attention_mma<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem); \
+    if (e != cudaSuccess) return cuda_fail(e, "attention smem attribute");                                           \
+    cudaError_t e2 = launch_ex(k_attention_mma<DD>, dim3(mgrid), dim3(mthreads), msmem, s, 1, o, q, L, C, heads, q_blocks); \
+    if (e2 != cudaSuccess) return cuda_fail(e2, "attention launch");                                                 \
+  } break
+      switch (D) { ATTM(16); ATTM(32); ATTM(64); }
+#undef ATTM
+      DLPM_CHECK_LAUNCH("attention");
+      return DLPM_OK;
+    }
+  }
   const size_t smem = (size_t)2 * L * D * sizeof(float);
   DLPM_REQUIRE(smem <= 200 * 1024, "attention: K/V of one head do not fit in shared memory");
   int threads = L * (D / 8);  // D/8 lanes per query row
   threads = threads < 32 ? 32 : (threads > 256 ? 256 : (threads + 31) / 32 * 32);
-  auto* o = reinterpret_cast<__nv_bfloat16*>(out);
-  auto* q = reinterpret_cast<const __nv_bfloat16*>(qkv);
-  cudaStream_t s = (cudaStream_t)stream;
   const unsigned grid = (unsigned)(B * heads);
 #define ATT(DD)                                                                                            \
   case DD: {                                                                                               \

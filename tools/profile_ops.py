@@ -20,16 +20,20 @@ ap.add_argument("--batch", type=int, default=512)
 ap.add_argument("--opt", action="append", default=[])
 ap.add_argument("--summary", action="store_true")
 ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--config", default="cifar", choices=["cifar", "mnist"])
 args = ap.parse_args()
 for o in args.opt:
     k, v = o.split("=")
     _lib.call("dlpm_b200_set_option", k.encode(), int(v))
-m = UNetModel(3, 128, 3, 2, (16,), channel_mult=(1, 2, 2, 2), num_heads=4, use_scale_shift_norm=True)
+if args.config == "mnist":  # mnist.yml:50-58: ch 32, attention at ds 2 and 4 (16x16 and 8x8)
+    m = UNetModel(1, 32, 1, 2, (2, 4), channel_mult=(1, 2, 2, 2), num_heads=4, use_scale_shift_norm=True)
+else:
+    m = UNetModel(3, 128, 3, 2, (16,), channel_mult=(1, 2, 2, 2), num_heads=4, use_scale_shift_norm=True)
 randomize_parameters_(m, 0)
 m = m.cuda().eval()
 B = args.batch
 eng = m.engine(32, 32, B)
-x = torch.randn(B, 3, 32, 32, device="cuda")
+x = torch.randn(B, 1 if args.config == "mnist" else 3, 32, 32, device="cuda")
 t = torch.full((1,), 0.5, device="cuda")
 out = torch.empty_like(x)
 eng.profile(x, t, out, B)
