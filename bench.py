@@ -273,9 +273,14 @@ def run_ours(args, rank, local_rank, world):
     ms_k1 = time_kernel(lambda: _lib.call("dlpm_b200_sas", _lib.ptr(nbuf), None, n_noise // 3072, 3072, 1, ALPHA, 200.0, 1.0, 1, 2, 0,
                                           _lib.stream_ptr()), reps=5)
     hbm_peak = float(pk["hbm_gbs"])
-    hbm["reverse_step"] = {"bytes_per_launch": 12 * n_el, "ms": ms_k3, "GB/s": 12 * n_el / ms_k3 / 1e6, "frac": 12 * n_el / ms_k3 / 1e6 / hbm_peak}
+    # a library elementwise kernel with exactly the same traffic (2 reads + 1 write of the same tensors, no RNG): what a
+    # 151 MB launch can reach on this box, next to the copy peak measured on multi-GB buffers
+    ms_add = time_kernel(lambda: torch.add(xw, eps, out=xw))
+    hbm["reverse_step"] = {"bytes_per_launch": 12 * n_el, "ms": ms_k3, "GB/s": 12 * n_el / ms_k3 / 1e6, "frac": 12 * n_el / ms_k3 / 1e6 / hbm_peak,
+                           "same_traffic_torch_add_GB/s": 12 * n_el / ms_add / 1e6}
     nn = (n_noise // 3072) * 3072
-    hbm["sas_noise_isotropic"] = {"bytes_per_launch": 4 * nn, "ms": ms_k1, "GB/s": 4 * nn / ms_k1 / 1e6, "frac": 4 * nn / ms_k1 / 1e6 / hbm_peak}
+    hbm["sas_noise_isotropic"] = {"bytes_per_launch": 4 * nn, "ms": ms_k1, "GB/s": 4 * nn / ms_k1 / 1e6, "frac": 4 * nn / ms_k1 / 1e6 / hbm_peak,
+                                  "limiter": "fmaheavy (Philox4x32-10: 20 IMAD.WIDE per 4 normals) + XU (Box-Muller: 2 MUFU per normal), see profiles/r01_ncu_stream.md"}
 
     launches_per_pass = (T - 1) * (eng.num_launches() + 2) + 3
     if rank == 0:
