@@ -27,6 +27,15 @@ UNET = dict(model_channels=128, channel_mult=(1, 2, 2, 2), num_res_blocks=2, att
 GFLOP_PER_SAMPLE_STEP = 11.44  # SURVEY.md section 6 (2*MAC of conv/linear/bmm, torch flop counter on the reference UNet)
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
@@ -127,7 +136,7 @@ def run_reference(args, rank):
             "config": workload_config(args, args.cpu_batch, 1),
             "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, batch_per_gpu, n):
@@ -185,32 +194,41 @@ def run_ours(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(n, e2e):
+    each = {}  # per-step device times of this rank (diagnostic: shows clock / power-cap drift across the run)
+
+    def timed(n, e2e, tag=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [e0]
         w0 = time.perf_counter()
         e0.record()
-        for _ in range(n):
+        for i in range(n):
             step(e2e)
-        e1.record()
+            m = e1 if i == n - 1 else torch.cuda.Event(enable_timing=True)
+            m.record()
+            marks.append(m)
+        if n == 0:
+            e1.record()
         barrier()
         wall = time.perf_counter() - w0
+        if tag:
+            each[tag] = [round(marks[i].elapsed_time(marks[i + 1]), 1) for i in range(len(marks) - 1)]
         ms = torch.tensor([e0.elapsed_time(e1), wall * 1000.0], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms[0]), float(ms[1])
 
-    for _ in range(args.warmup):
-        step()
+    if args.warmup > 0:
+        timed(args.warmup, e2e=False, tag="warmup")
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    ms_dev, _ = timed(args.steps, e2e=False)
+    ms_dev, _ = timed(args.steps, e2e=False, tag="timed")
     clk = clocks.stop() if rank == 0 else None
-    _, ms_e2e_wall = timed(args.e2e_steps, e2e=True)
+    _, ms_e2e_wall = timed(args.e2e_steps, e2e=True, tag="e2e") if args.e2e_steps > 0 else (0.0, float("nan"))
     ms_per_step = ms_dev / args.steps
     value = world * B / (ms_per_step / 1000.0)
-    e2e_value = world * B / (ms_e2e_wall / args.e2e_steps / 1000.0)
+    e2e_value = world * B / (ms_e2e_wall / args.e2e_steps / 1000.0) if args.e2e_steps > 0 else None
 
     # ---- roofline of the dominant kernel (tcgen05 implicit-GEMM conv), measured live with CUDA events per op
     eng = model.engine(IMG, IMG, B)
@@ -286,7 +304,7 @@ def run_ours(args, rank, local_rank, world):
     if rank == 0:
         cpu_val, _, cpu_desc = cpu_reference_step(args.cpu_batch, args.cpu_substeps)
         line = {"metric": "DLPM samples/sec (1000 reverse steps, CIFAR-10 shape)", "value": value, "unit": "samples/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "ms_each_step": each, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, B, world),
                 "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(host_sched.numel() * 4 * world),
                         "d2h_bytes_per_step": int(host_out.numel() * 4 * world), "steps": args.e2e_steps,
@@ -295,7 +313,7 @@ def run_ours(args, rank, local_rank, world):
                 "hbm_kernels": hbm,
                 "cpu_baseline": {"value": cpu_val, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port", "sample": cpu_desc},
                 "workspace_gb": eng.workspace_bytes / 1e9}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -312,7 +330,13 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=8)
     ap.add_argument("--cpu-substeps", type=int, default=3)
     args = ap.parse_args()
-    # stdout carries exactly one JSON line: NCCL's own banner / debug output ("NCCL version ...") goes to stderr
+    # stdout carries exactly one JSON line.  NCCL prints its version banner to the process's fd 1 at communicator creation
+    # (NCCL_DEBUG_FILE does not redirect it), so fd 1 is pointed at stderr for the whole run and the JSON line is written
+    # to a duplicate of the original stdout.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -324,7 +348,7 @@ def main():
         # not launched through torchrun: re-exec under it (one process per GPU)
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus), "--master-addr",
                "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
-        sys.exit(subprocess.call(cmd))
+        sys.exit(subprocess.call(cmd, stdout=_JSON_OUT))
     run_ours(args, rank, local_rank, world)
 
 
