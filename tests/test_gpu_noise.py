@@ -104,6 +104,40 @@ def test_determinism_and_shard_invariance(dl):
     assert not torch.equal(other, full)
 
 
+def test_full_size_properties(dl):
+    """BASELINE.json sizes (C3: 4096 x 3 x 32 x 32 per call; C5: 2^28 draws): size-independent properties instead of an
+    oracle comparison -- shard invariance (8 'ranks' of 512 samples reproduce the single 4096-sample call bit for bit),
+    determinism, the isotropic structure (eps / sqrt(A) is a standard normal field sharing one A per sample) and moments."""
+    from dlpm_b200 import rng
+    shape = (4096, 3, 32, 32)
+    full = dl.gen_sas(1.7, shape, device="cuda", isotropic=True, clamp_eps=200.0, state=rng.PhiloxState(seed=11, offset=5))
+    parts = [dl.gen_sas(1.7, (512, 3, 32, 32), device="cuda", isotropic=True, clamp_eps=200.0,
+                        state=rng.PhiloxState(seed=11, offset=5, sample_base=512 * r)) for r in range(8)]
+    assert torch.equal(torch.cat(parts), full)
+    del parts
+    assert torch.isfinite(full).all() and float(full.abs().max()) <= 200.0
+    # isotropic structure: inside one sample the 3072 values are Gaussian (common scale sqrt(A_b)): per-sample kurtosis ~ 3,
+    # while the pooled marginal is heavy-tailed (SaS: pooled kurtosis is orders of magnitude larger)
+    x = full.double().reshape(4096, -1)
+    m2, m4 = x.pow(2).mean(1), x.pow(4).mean(1)
+    kurt = (m4 / m2.pow(2))
+    assert abs(float(kurt.median()) - 3.0) < 0.05
+    pooled = float(x.pow(4).mean() / x.pow(2).mean() ** 2)
+    assert pooled > 30.0
+    del full
+    # C5-sized flat fill: 2^28 draws in one launch; determinism + normal moments of the G field
+    n = (1 << 28) // 3072
+    from dlpm_b200 import _lib
+    buf = torch.empty(n * 3072, device="cuda")
+    _lib.call("dlpm_b200_normal", _lib.ptr(buf), n, 3072, 3, 9, 0, _lib.stream_ptr())
+    s1 = float(buf.double().sum()), float(buf.double().pow(2).sum())
+    chk = buf[:: 65537].clone()
+    _lib.call("dlpm_b200_normal", _lib.ptr(buf), n, 3072, 3, 9, 0, _lib.stream_ptr())
+    assert torch.equal(buf[:: 65537], chk)
+    N = buf.numel()
+    assert abs(s1[0] / N) < 3e-4 and abs(s1[1] / N - 1.0) < 3e-4  # mean 0 +- 5 sigma, variance 1
+
+
 def test_error_behaviour(dl):
     with pytest.raises(Exception, match="Wrong value of alpha"):
         dl.gen_skewed_levy(2.5, (4, 4), device="cuda")
