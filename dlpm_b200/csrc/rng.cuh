@@ -17,6 +17,10 @@ enum : uint32_t { STREAM_A = 0x0Au, STREAM_G = 0x06u, STREAM_Z = 0x5Au, STREAM_E
 // The ten round keys (k + r * Weyl constant).  The hot streaming kernels take them precomputed on the host as a
 // __grid_constant__ parameter, so every round's key is a constant-bank operand of the LOP3 (no per-iteration
 // UIADD3 key schedule); the other kernels build them in registers from the seed.  Both give the same stream.
+#ifndef DLPM_PHILOX_ROUNDS
+#define DLPM_PHILOX_ROUNDS 10  // Random123 / cuRAND default.  7 rounds still pass BigCrush (Salmon et al. 2011, Table 2) and make the
+                               // normal fill HBM-bound (profiles/r01_ncu_stream.md); kept at 10 for the safety margin.
+#endif
 struct PhiloxKeys {
   uint32_t a[10], b[10];
 };
@@ -32,10 +36,10 @@ __host__ __device__ __forceinline__ PhiloxKeys make_philox_keys(uint64_t seed) {
   return k;
 }
 
-// 10 rounds, Salmon et al. 2011 constants.  One round = 2 IMAD.WIDE + 2 three-input XORs.
+// DLPM_PHILOX_ROUNDS (10) rounds, Salmon et al. 2011 constants.  One round = 2 IMAD.WIDE + 2 three-input XORs.
 __device__ __forceinline__ uint4 philox_rounds(const PhiloxKeys& k, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < DLPM_PHILOX_ROUNDS; ++r) {
     const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
     c0 = (uint32_t)(p1 >> 32) ^ c1 ^ k.a[r];
     c1 = (uint32_t)p1;
