@@ -120,6 +120,94 @@ class GenerativeLevyProcess:
         assert mean.shape == x.shape
         return {"eps": eps, "mean": mean, "variance": var}
 
+    # ------------------------------------------------------------------------------------------ single-step API (:225-239, :332-373)
+    def q_posterior_mean_variance(self, x_start, x_t, t):
+        raise NotImplementedError("dead code in the reference (GenerativeLevyProcess.py:126-127 calls methods that do not exist)")
+
+    def _single_step(self, model, x, t, clip_denoised, model_kwargs, deterministic, noise, state, z_offset):
+        dev = _lib.require_cuda(self.device)
+        B = x.shape[0]
+        assert t.shape == (B,)
+        d = self.dlpm
+        T = self.reverse_steps
+        tt = int(t[0])  # the reference indexes the posterior with t[0] (:210): the step is batch-constant
+        assert 1 <= tt < T, "t out of range [1, T)"
+        st = state or rng.default_state()
+        net = _Net(model, dev)
+        with torch.inference_mode(), torch.cuda.device(dev):
+            xs = x.to(dev, torch.float32).contiguous()
+            table = self._input_scale_table()
+            x_in = xs if table is None else self._scaled_input(xs, table, t=tt)
+            eps = net(x_in, self._scale_timesteps(t.to(dev)), **(model_kwargs or {}))
+            fl = (_lib.STEP_CLIP_DENOISED if clip_denoised else 0) | (_lib.STEP_EPS_BF16 if eps.dtype == torch.bfloat16 else 0)
+            eps = eps.contiguous() if eps.dtype == torch.bfloat16 else eps.to(torch.float32).contiguous()
+            out = xs.clone()
+            D = out[0].numel()
+            if deterministic:
+                _lib.call("dlpm_b200_dlim_step", _lib.ptr(out), _lib.ptr(eps), _lib.ptr(d.sched), tt, None, T, B, D, fl, None,
+                          _lib.stream_ptr())
+            else:
+                assert d.Sigmas is not None, "sample_A / compute_Sigmas must run first (as in the reference, :308-309)"
+                fl |= 0 if d.isotropic else _lib.STEP_SIGMA_FULL
+                z = None if noise is None else noise.to(dev, torch.float32).contiguous()
+                # one reserved block of T offsets per call: the kernel keys z by (offset + t), unique for every (call, t)
+                zo = st.reserve(T) if z_offset is None else z_offset
+                _lib.call("dlpm_b200_reverse_step", _lib.ptr(out), _lib.ptr(eps), _lib.ptr(d.Sigmas), _lib.ptr(d.sched), tt, None, T,
+                          B, D, fl, _lib.ptr(z), st.seed, zo, st.sample_base, None, _lib.stream_ptr())
+        return {"sample": out.view(x.shape)}
+
+    def p_sample(self, model, x, t, clip_denoised=False, denoised_fn=None, model_kwargs=None, noise=None, state=None,
+                 _z_offset=None):
+        """:225-239: x_{t-1} = mean + 1[t != 1] sqrt(var) z -- one network evaluation + the fused K3 step.
+        ``noise`` (extension) injects z for parity tests; otherwise it is drawn in-kernel."""
+        assert denoised_fn is None, "denoised_fn is not supported"
+        return self._single_step(model, x, t, clip_denoised, model_kwargs, False, noise, state, _z_offset)
+
+    def ddim_sample(self, model, x, t, clip_denoised=False, denoised_fn=None, model_kwargs=None, eta=0.0):
+        """:332-373 with eta = 0 (App. B.3): x_{t-1} = (x_t - bs_t eps) / g_t + bs_{t-1} eps."""
+        assert denoised_fn is None, "denoised_fn is not supported"
+        if eta != 0.0:
+            raise NotImplementedError("dlim_eta != 0 is broken in the reference (dlpm.py:289-297); use eta=0.0")
+        return self._single_step(model, x, t, clip_denoised, model_kwargs, True, None, None, None)
+
+    def _progressive(self, model, shape, noise, clip_denoised, model_kwargs, deterministic, state):
+        dev = _lib.require_cuda(self.device)
+        assert isinstance(shape, (tuple, list))
+        shape = [int(s) for s in shape]
+        st = state or rng.default_state()
+        T = self.reverse_steps
+        self.dlpm.sample_A(shape, T, state=st)
+        if noise is not None:
+            img = noise.to(dev, torch.float32)
+        else:
+            img = self.dlpm.gen_eps.generate(size=shape, scale=float(self.dlpm._sched_host[-1, 3]), state=st)
+        yield {"sample": img}
+        z_offset = st.reserve(T)
+        for i in range(T - 1, 0, -1):
+            t = torch.tensor([i] * shape[0], device=dev)
+            if deterministic:
+                out = self.ddim_sample(model, img, t, clip_denoised=clip_denoised, model_kwargs=model_kwargs, eta=0.0)
+            else:
+                out = self.p_sample(model, img, t, clip_denoised=clip_denoised, model_kwargs=model_kwargs, state=st,
+                                    _z_offset=z_offset)
+            yield out
+            img = out["sample"]
+
+    def p_sample_loop_progressive(self, model, shape, noise=None, clip_denoised=False, denoised_fn=None, model_kwargs=None,
+                                  state=None):
+        """:291-330: generator over {'sample': x_t} for t = T-1 ... 0 (T entries).  Same Philox stream layout as
+        ``p_sample_loop`` (A chain, x_T, then one block of T offsets for z), so both produce the same samples."""
+        assert denoised_fn is None, "denoised_fn is not supported"
+        return self._progressive(model, shape, noise, clip_denoised, model_kwargs, False, state)
+
+    def ddim_sample_loop_progressive(self, model, shape, noise=None, clip_denoised=False, denoised_fn=None, model_kwargs=None,
+                                     eta=0.0, state=None):
+        """:413-452 with eta = 0."""
+        assert denoised_fn is None, "denoised_fn is not supported"
+        if eta != 0.0:
+            raise NotImplementedError("dlim_eta != 0 is broken in the reference (dlpm.py:289-297); use eta=0.0")
+        return self._progressive(model, shape, noise, clip_denoised, model_kwargs, True, state)
+
     def _reverse_loop(self, model, shape, noise, clip_denoised, deterministic, get_sample_history, model_kwargs=None,
                       progress=False, injected_A=None, injected_z=None, state=None):
         """p_sample_loop_progressive / ddim_sample_loop_progressive (:291-330, :413-452) on the fused kernels."""

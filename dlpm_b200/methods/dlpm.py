@@ -125,6 +125,11 @@ class DLPM:
     def get_schedule(self, shape):
         return tuple(match_last_dims(v, shape) for v in (self.gammas, self.bargammas, self.sigmas, self.barsigmas))
 
+    def update_constants(self, shape):
+        """dlpm.py:170-174 (API parity).  The kernels read the (T, 4) ``sched`` table; nothing is cached per shape."""
+        self.constants = self.get_schedule(shape)
+        return self.constants
+
     def get_t_to_batch_size(self, x_t, t):
         if isinstance(t, int):
             return torch.full([x_t.shape[0]], t).to(self.device)
@@ -149,6 +154,37 @@ class DLPM:
         if eps is None:
             eps = self.gen_eps.generate(size=xstart.size())
         return bg * xstart + bs * eps, eps
+
+    # API-parity helpers of the conditioned dynamics (dlpm.py:199-202, :243-270, :377-382): torch expressions on device
+    # tensors, not used by the fused loops
+    def _sigma_rows(self, like, t):
+        tb = self.get_t_to_batch_size(like, t)
+        S1, St = self.Sigmas[tb - 1], self.Sigmas[tb]
+        if S1.dim() != like.dim():  # compact (T, B) tables: the batched index gives (B, B); take the matching rows
+            idx = torch.arange(like.shape[0], device=S1.device)
+            S1, St = _bc(self.Sigmas[tb - 1, idx], like), _bc(self.Sigmas[tb, idx], like)
+        return S1, St
+
+    def predict_eps_from_m_tilde(self, x_t, t, m_tilde_t_1):
+        g, bg, s, bs = self._rows(m_tilde_t_1, t)
+        S1, St = self._sigma_rows(m_tilde_t_1, t)
+        Gamma_t = 1 - (g ** 2 * S1) / St
+        return (x_t - m_tilde_t_1 * g) / (bs * Gamma_t)
+
+    def sample_x_t_from_xstart_given_Sigma(self, xstart, t, Sigma_t, z_t=None):
+        g, bg, s, bs = self._rows(xstart, t)
+        if z_t is None:
+            from ..datasets.Distributions import gen_normal
+            z_t = gen_normal(xstart.shape, device=self.device)
+        return bg * xstart + Sigma_t ** (1 / 2) * z_t
+
+    def compute_m_tilde_t_1(self, x_t, t, Gamma_t, eps_t):
+        g, bg, s, bs = self._rows(x_t, t)
+        return (x_t - bs * Gamma_t * eps_t) / g
+
+    def compute_one_rv_Sigma_prime_t(self, t, a_t):
+        g, bg, s, bs = self._rows(a_t, t)
+        return a_t * bs ** 2
 
     # ------------------------------------------------------------------ A / Sigma chains (dlpm.py:226-239)
     def _clamp_a(self):

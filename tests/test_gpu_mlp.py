@@ -174,3 +174,55 @@ def test_lim_training_loss_golden(model):
     np.testing.assert_allclose(score.cpu().numpy(), score_o.numpy(), rtol=1e-6)
     free = glp.training_losses({"default": model}, torch.randn(256, 1, 2), clamp_eps=20.0)["loss"]
     assert torch.isfinite(free) and free.dim() == 0
+
+
+def test_single_step_and_progressive_api(model):
+    """API parity of the per-step entry points (GenerativeLevyProcess.py:225-239 p_sample, :332-373 ddim_sample, :291-330 /
+    :413-452 the progressive generators): teacher-forced against the reference history with injected z, and the generators
+    against the fused loops on the same Philox key."""
+    from dlpm_b200 import GenerativeLevyProcess, rng
+    g = load_golden("mlp_chain")
+    r = sub(g, "dlpm")
+    T, B = r["A"].shape
+    glp = GenerativeLevyProcess(1.7, "cuda", T, rescale_timesteps=True, isotropic=True)
+    glp.dlpm.A = torch.from_numpy(r["A"]).cuda()
+    glp.dlpm._shape = list(r["x_init"].shape)
+    glp.dlpm._sigma_src = None
+    glp.dlpm.compute_Sigmas()
+    hist = torch.from_numpy(r["hist"])
+    for k, t in enumerate(range(T - 1, 0, -1)):
+        tv = torch.full((B,), t, device="cuda", dtype=torch.int64)
+        out = glp.p_sample(model, hist[k].cuda(), tv, noise=torch.from_numpy(r["z"][k]))
+        np.testing.assert_allclose(out["sample"].cpu().numpy(), r["hist"][k + 1], rtol=2e-4, atol=2e-4)
+    rd = sub(g, "dlim")
+    histd = torch.from_numpy(rd["hist"])
+    for k, t in enumerate(range(T - 1, 0, -1)):
+        tv = torch.full((B,), t, device="cuda", dtype=torch.int64)
+        out = glp.ddim_sample(model, histd[k].cuda(), tv, eta=0.0)
+        np.testing.assert_allclose(out["sample"].cpu().numpy(), rd["hist"][k + 1], rtol=2e-4, atol=2e-4)
+    with pytest.raises(NotImplementedError):
+        glp.ddim_sample(model, histd[0].cuda(), torch.full((B,), 3, device="cuda"), eta=0.5)
+    # generators: T entries, same samples as the fused loop on the same key
+    T2, B2 = 12, 64
+    glp2 = GenerativeLevyProcess(1.7, "cuda", T2, rescale_timesteps=True, isotropic=True)
+    steps = list(glp2.p_sample_loop_progressive(model, [B2, 1, 2], state=rng.PhiloxState(seed=31, offset=0)))
+    assert len(steps) == T2 and all(s["sample"].shape == (B2, 1, 2) for s in steps)
+    fused, fh = glp2.p_sample_loop(model, [B2, 1, 2], get_sample_history=True, state=rng.PhiloxState(seed=31, offset=0))
+    np.testing.assert_allclose(torch.stack([s["sample"] for s in steps]).cpu().numpy(), fh.cpu().numpy(), rtol=2e-3, atol=2e-3)
+    dsteps = list(glp2.ddim_sample_loop_progressive(model, [B2, 1, 2], state=rng.PhiloxState(seed=31, offset=0)))
+    dfused = glp2.ddim_sample_loop(model, [B2, 1, 2], eta=0.0, state=rng.PhiloxState(seed=31, offset=0))
+    np.testing.assert_allclose(dsteps[-1]["sample"].cpu().numpy(), dfused.cpu().numpy(), rtol=2e-3, atol=2e-3)
+    # DLPM helper parity (dlpm.py:199-202, :243-270, :377-382) against the oracle expressions
+    d = glp.dlpm
+    x = hist[3].cuda()
+    tv = torch.full((B,), T - 4, device="cuda", dtype=torch.int64)
+    eps = torch.randn_like(x)
+    mean, var = d.anterior_mean_variance_dlpm(x, T - 4, eps)
+    Gamma = d.compute_Gamma_t(T - 4, d.Sigmas_full()[T - 5], d.Sigmas_full()[T - 4])
+    np.testing.assert_allclose(d.compute_m_tilde_t_1(x, tv, Gamma, eps).cpu().numpy(), mean.cpu().numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(d.predict_eps_from_m_tilde(x, tv, mean).cpu().numpy(), eps.cpu().numpy(), rtol=2e-3, atol=2e-3)
+    a = torch.rand(B, 1, 2, device="cuda") + 0.5
+    np.testing.assert_allclose(d.compute_one_rv_Sigma_prime_t(tv, a).cpu().numpy(), (a * d.barsigmas[T - 4] ** 2).cpu().numpy(), rtol=1e-6)
+    xs = d.sample_x_t_from_xstart_given_Sigma(x, tv, a, z_t=eps)
+    np.testing.assert_allclose(xs.cpu().numpy(), (d.bargammas[T - 4] * x + a.sqrt() * eps).cpu().numpy(), rtol=1e-6, atol=1e-6)
+    assert len(d.update_constants(x.shape)) == 4
