@@ -63,10 +63,21 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def mark(self):
+        """Rows logged so far belong to the warm-up: only later ones are reported."""
+        self.first = len(self.rows)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
+        self.rows = self.rows[getattr(self, "first", 0):]
+        try:  # diagnostic trace of the timed region (scratch, not tracked)
+            if os.path.isdir(os.path.join(ROOT, "gpurun_out")):
+                with open(os.path.join(ROOT, "gpurun_out", "clock_rows.csv"), "w") as fh:
+                    fh.write(self.Q + "\n" + "\n".join(",".join(r) for r in self.rows) + "\n")
+        except OSError:
+            pass
         sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
         mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -218,11 +229,17 @@ def run_ours(args, rank, local_rank, world):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms[0]), float(ms[1])
 
-    if args.warmup > 0:
-        timed(args.warmup, e2e=False, tag="warmup")
+    # nvidia-smi needs ~1 s to initialise NVML and briefly contends with kernel launches while it does: start it before
+    # the last warm-up step so that only its steady 200 ms polling runs during the timed region; rows logged before the
+    # timed region starts are dropped.
     clocks = ClockSampler(local_rank)
+    if args.warmup > 1:
+        timed(args.warmup - 1, e2e=False, tag="warmup")
     if rank == 0:
         clocks.start()
+    if args.warmup > 0:
+        timed(1, e2e=False, tag="warmup_last")
+    clocks.mark()
     ms_dev, _ = timed(args.steps, e2e=False, tag="timed")
     clk = clocks.stop() if rank == 0 else None
     _, ms_e2e_wall = timed(args.e2e_steps, e2e=True, tag="e2e") if args.e2e_steps > 0 else (0.0, float("nan"))
