@@ -132,7 +132,6 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);  // 16-byte aligned (the barrier block is a multiple of 16 bytes)
-  for (int i = threadIdx.x; i < p.c_out_pad; i += blockDim.x) s_bias[i] = __ldg(p.bias + i);  // weights: safe before pdl_wait
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // provably warp-uniform (see tc::elect_one)
   const int lane = threadIdx.x & 31;
@@ -420,6 +419,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     }
   } else if (warp >= 4 && warp < 4 + 4 * EG) {
     // ===================== epilogue =====================
+    // the bias vector is only needed here: loaded by the epilogue warps and published with a named barrier among them, so
+    // that its L2 round trip is off the path of the TMA producer / MMA issuer (the first accumulator is microseconds away)
+    for (int i = (int)threadIdx.x - 128; i < p.c_out_pad; i += 128 * EG) s_bias[i] = __ldg(p.bias + i);
+    asm volatile("bar.sync 1, %0;" ::"n"(128 * EG) : "memory");
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     const int eg = (warp - 4) >> 2;  // which half of the column chunks (EG == 2)
     const int m = q * 32 + lane;
@@ -595,7 +598,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       }
     }
   }
-  if (p.tma_store && warp >= 4 && warp < 4 + 4 * EG && lane == 0) bulk_wait0();  // this thread's TMA stores have completed
+  // the staging buffers must outlive the TMA engine's reads; the writes themselves are flushed by grid completion
+  if (p.tma_store && warp >= 4 && warp < 4 + 4 * EG && lane == 0) bulk_wait_read0();
   tc_fence_before();
   __syncwarp();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
