@@ -16,7 +16,7 @@ from dlpm_b200 import GenerativeLevyProcess  # noqa: E402
 from dlpm_b200.init_utils import randomize_parameters_  # noqa: E402
 from dlpm_b200.score_nets import UNetModel  # noqa: E402
 
-steps = int(sys.argv[1]) if len(sys.argv) > 1 else 12
+steps = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 12
 dev = torch.device("cuda", 0)
 dlpm_b200.manual_seed(1)
 m = UNetModel(3, 128, 3, 2, (16,), channel_mult=(1, 2, 2, 2), num_heads=4, use_scale_shift_norm=True)
@@ -52,3 +52,10 @@ print("steps %d  kernels/step %.1f  span/step %.1f us  busy/step %.1f us  idle/s
     sum(gaps) / len(gaps)))
 for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print("%-42s %6.1f launches/step %9.1f us/step" % (k, c / n_steps, t / n_steps))
+
+if "--sequence" in sys.argv:  # kernel sequence of one steady step with in-loop durations (us), averaged over the steps
+    per = len(seg) // n_steps
+    print("--- per-kernel in-loop duration (mean over %d steps) ---" % n_steps)
+    for i in range(per):
+        d = [seg[s * per + i][2] - seg[s * per + i][1] for s in range(n_steps)]
+        print("%3d %-40s %8.1f" % (i, seg[i][0].split("(")[0].replace("void ", "").replace("dlpm::", "")[:40], sum(d) / len(d)))
