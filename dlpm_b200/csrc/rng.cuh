@@ -107,19 +107,39 @@ __device__ __forceinline__ float4 normal4(uint4 r) {
   return make_float4(a.x, a.y, b.x, b.y);
 }
 
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // Exp(1) variate from 32 bits, accurate in the W -> 0 tail (which drives the heavy tail of A):
-// W = -log(1 - d), d in (0,1); series for small d, MUFU lg2 otherwise.
+// W = -log(1 - d), d in (0,1) on the centred 32-bit lattice; series for small d, MUFU lg2 otherwise.
 __device__ __forceinline__ float exp1(uint32_t x) {
-  const float d = fminf(((float)x + 0.5f) * 2.3283064365386963e-10f, 0.99999994f);
+  const float d = fminf(fmaf((float)x, 2.3283064365386963e-10f, 1.1641532182693481e-10f), 0.99999994f);
   const float series = d * (1.0f + d * (0.5f + d * (0.33333334f + d * 0.25f)));
   const float full = -0.6931471805599453f * lg2_ftz(1.0f - d);
   return d < 0.03125f ? series : full;
 }
 
-// sin on (0, pi) with relative accuracy near 0 (MUFU.SIN only promises absolute error).
-__device__ __forceinline__ float sin_0_pi(float x) {
-  const float small = x * (1.0f - x * x * 0.16666667f);
-  return x < 0.0625f ? small : __sinf(x);
+// SCALE * sin(pi v) for v in [0, 1/2] on the FMA pipes: odd minimax polynomial of degree 9 (relative error 5.3e-9 before
+// rounding, so sin keeps RELATIVE accuracy as v -> 0, which MUFU.SIN does not promise).  Replaces MUFU.SIN + range scaling
+// + a small-argument branch: fewer instructions and no XU-pipe slot.  (Throughput note, profiles/r01_ncu_stream.md: the
+// per-element draw is bound by instruction dispatch with IMAD.WIDE costing 4 slots, not by the XU pipe.)
+template <int SCALE>
+__device__ __forceinline__ float sinpi_half(float v) {
+  const float z = v * v;
+  float p = SCALE * 0.07756038554456743f;
+  p = fmaf(p, z, SCALE * -0.5982421256741446f);
+  p = fmaf(p, z, SCALE * 2.5500697262138807f);
+  p = fmaf(p, z, SCALE * -5.167709684792514f);
+  p = fmaf(p, z, SCALE * 3.14159263689534f);
+  return v * p;
 }
 
 // Parameters of the Kanter / CMS transform for alpha' = alpha/2 (precomputed on the host).
@@ -131,25 +151,31 @@ struct StableParams {
   int gaussian;    // alpha == 2  ->  A == 2 exactly (Distributions.py:40-42)
 };
 
-// A = 2 K,  K = sin(a'U)/sin(U)^(1/a') * (sin((1-a')U)/W)^((1-a')/a'),  U ~ Unif(0,pi), W ~ Exp(1)
+// A = 2 K,  K = sin(a'U)/sin(U)^(1/a') * (sin((1-a')U)/W)^((1-a')/a'),  U = pi u ~ Unif(0,pi), W ~ Exp(1)
 // (identical pointwise to scipy's _rvs_Z1 'otherwise' branch with beta=1
 //  times scale 2 cos(pi alpha/4)^(2/alpha), see oracle/stable.py).
-// Evaluated in log2 space so that the heavy tail (U -> pi, W -> 0) neither overflows nor
-// loses precision: sin(U) is evaluated on the reflected argument min(u, 1-u) built from the
-// integer so that U -> pi keeps full relative precision.
+// Evaluated in log2 space with the logarithms merged (1/a' = 1 + r):
+//   lg2 A = lg2( 2 sin(a'U) / sin U ) + r lg2( sin((1-a')U) / (sin U * W) )
+// = one MUFU.RCP + two MUFU.LG2 instead of four LG2; the heavy tail (U -> pi, W -> 0) neither overflows (sin U * W >= 2e-17)
+// nor loses precision: sin(U) is evaluated on the reflected argument min(u, 1-u) built from the integer so that U -> pi keeps
+// full relative precision.  MUFU ops per draw: LG2 (W), RCP, 2 LG2, EX2 = 5 (was 9: + 3 SIN, + 1 LG2).
+// Checked pointwise against oracle/stable.py::kanter_A on the same lattice variates (max relative error 3e-6 incl. both tails).
 __device__ __forceinline__ float stable_A(const StableParams& p, uint32_t xu, uint32_t xw) {
   if (p.gaussian) return 2.0f;
   // u in (0,1) on the centred 32-bit lattice; v = min(u, 1-u) is built from the integer so both ends are exact.
-  const uint32_t xr = (xu & 0x80000000u) ? ~xu : xu;            // reflect the upper half
-  const float v = ((float)xr + 0.5f) * 2.3283064365386963e-10f;  // (0, 0.5]
-  const float u = (xu & 0x80000000u) ? 1.0f - v : v;
-  const float PI = 3.14159265358979323846f;
-  const float sinU = sin_0_pi(PI * v);  // sin(pi u) = sin(pi (1-u))
-  const float s1 = sin_0_pi(p.ap * PI * u);
-  const float s2 = sin_0_pi(p.one_m_ap * PI * u);
+  const uint32_t xr = xu ^ (uint32_t)((int32_t)xu >> 31);                      // reflect the upper half (~xu)
+  const float v = fmaf((float)xr, 2.3283064365386963e-10f, 1.1641532182693481e-10f);  // (0, 0.5]
+  const float u = (int32_t)xu < 0 ? 1.0f - v : v;
+  const float sinU = sinpi_half<1>(v);  // sin(pi u) = sin(pi (1-u))
+  const float a1 = p.ap * u;            // (0, a') with a' < 1
+  const float s1 = sinpi_half<2>(fminf(a1, 1.0f - a1));
+  float a2 = p.one_m_ap * u;            // (0, 1/2] for alpha >= 1
+  if (p.one_m_ap > 0.5f) a2 = fminf(a2, 1.0f - a2);
+  const float s2 = sinpi_half<1>(a2);
   const float w = exp1(xw);
-  const float l2 = lg2_ftz(s1) - p.inv_ap * lg2_ftz(sinU) + p.r * (lg2_ftz(s2) - lg2_ftz(w));
-  return 2.0f * exp2f(l2);
+  const float q = rcp_ftz(sinU * w);
+  const float l2 = lg2_ftz((s1 * q) * w) + p.r * lg2_ftz(s2 * q);
+  return ex2_ftz(l2);
 }
 
 }  // namespace dlpm

@@ -138,6 +138,53 @@ def test_full_size_properties(dl):
     assert abs(s1[0] / N) < 3e-4 and abs(s1[1] / N - 1.0) < 3e-4  # mean 0 +- 5 sigma, variance 1
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# Pointwise parity: the kernels' draws against the REFERENCE formulas (scipy's CMS branch, Box-Muller) evaluated in float64
+# on the very same Philox words (oracle/philox.py: Philox4x32-10 pinned by the Random123 known-answer vectors)
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("alpha", ALPHAS + (1.2,))
+def test_pointwise_A_against_oracle_on_same_words(dl, alpha):
+    from dlpm_b200 import rng
+    from oracle import philox
+    seed, off, base, n = 0x1234_5678_9ABC_DEF0, 1000, 77, 200000
+    Ac = dl.gen_skewed_levy(alpha, (n,), device="cuda", isotropic=True, compact=True,
+                            state=rng.PhiloxState(seed=seed, offset=off, sample_base=base)).cpu().numpy().astype(np.float64)
+    ref = philox.sample_A(alpha, seed, off, base + np.arange(n))
+    np.testing.assert_allclose(Ac, ref, rtol=3e-5)  # MUFU lg2 / ex2 / rcp approximations; observed ~3e-6
+    # broadcast layout, clamped: same draws
+    Ab = dl.gen_skewed_levy(alpha, (512, 3, 8, 8), device="cuda", isotropic=True, clamp_a=20.0,
+                            state=rng.PhiloxState(seed=seed, offset=off, sample_base=base))
+    np.testing.assert_allclose(Ab[:, 0, 0, 0].cpu().numpy(), np.minimum(ref[:512], 20.0), rtol=3e-5)
+    # per-element draws (vector kernel: inner % 4 == 0; scalar kernel: odd inner), positions 2q+1 / 2q+2 of each sample
+    Ae = dl.gen_skewed_levy(alpha, (300, 64), device="cuda", isotropic=False,
+                            state=rng.PhiloxState(seed=seed, offset=off + 1, sample_base=base)).cpu().numpy().astype(np.float64)
+    refe = philox.element_A(alpha, seed, off + 1, base + np.arange(300), 64)
+    np.testing.assert_allclose(Ae, refe, rtol=3e-5)
+    Ao = dl.gen_skewed_levy(alpha, (300, 7), device="cuda", isotropic=False,
+                            state=rng.PhiloxState(seed=seed, offset=off + 1, sample_base=base)).cpu().numpy().astype(np.float64)
+    np.testing.assert_allclose(Ao, philox.element_A(alpha, seed, off + 1, base + np.arange(300), 8)[:, :7], rtol=3e-5)
+
+
+def test_pointwise_normal_and_sas_against_oracle_on_same_words(dl):
+    from dlpm_b200 import rng
+    from oracle import philox
+    seed, off, base = 99, 5, 1 << 33  # a sample index beyond 32 bits exercises the high counter bits
+    z = dl.gen_normal((256, 3072), device="cuda", state=rng.PhiloxState(seed=seed, offset=off, sample_base=base)).cpu().numpy().astype(np.float64)
+    ref = philox.normal(seed, off, base + np.arange(256), 3072)
+    err = np.abs(z - ref)
+    # MUFU.SIN / COS: absolute error ~5e-7 x radius; lg2.approx has an ABSOLUTE error of 2^-22 near u = 1, i.e. on the
+    # few draws with a radius below ~1e-2 the radius itself is off by up to ~1e-4
+    assert np.quantile(err, 0.9999) < 1e-5 and err.max() < 2e-3, (np.quantile(err, 0.9999), err.max())
+    e = dl.gen_sas(1.7, (256, 3, 32, 32), device="cuda", isotropic=True, clamp_eps=200.0,
+                   state=rng.PhiloxState(seed=seed, offset=off, sample_base=base)).cpu().numpy().astype(np.float64).reshape(256, -1)
+    refe = philox.sas_isotropic(1.7, seed, off, base + np.arange(256), 3072, clamp_eps=200.0)
+    # in units of the sample's scale sqrt(A_b): the normal tolerances above plus A's relative error (3e-5) times |G|
+    sa = np.sqrt(philox.sample_A(1.7, seed, off, base + np.arange(256), stream=philox.STREAM_EPS_A))[:, None]
+    err = np.abs(e - refe) / sa
+    assert np.quantile(err, 0.9999) < 3e-4 and err.max() < 3e-3, (np.quantile(err, 0.9999), err.max())
+    assert np.abs(e).max() <= 200.0
+
+
 def test_error_behaviour(dl):
     with pytest.raises(Exception, match="Wrong value of alpha"):
         dl.gen_skewed_levy(2.5, (4, 4), device="cuda")

@@ -214,3 +214,84 @@ def test_oracle_against_live_reference():
     t = torch.linspace(0.9946, 1e-5, 11)
     assert torch.equal(sde_ref.marginal_std(t), sde.marginal_std(t))
     assert torch.equal(sde_ref.diffusion_coeff(t), sde.diffusion_coeff(t))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Counter-based variates (oracle/philox.py): Philox known-answer vectors, and the fp32 evaluation order of the CUDA
+# transform (rng.cuh::stable_A, restated in numpy float32) against the reference formula on identical lattice variates
+# ------------------------------------------------------------------------------------------------------------------
+def test_philox4x32_known_answers():
+    """Random123 kat_vectors, philox4x32-10 (Salmon et al. 2011)."""
+    from oracle import philox
+    kat = [((0, 0), (0, 0, 0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff, 0xffffffff), (0xffffffff,) * 4, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0xa4093822, 0x299f31d0), (0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for key, ctr, exp in kat:
+        out = philox.philox4x32(key, *[np.array([c]) for c in ctr])
+        assert [int(o[0]) for o in out] == list(exp)
+    # counter layout: distinct (sample, position, offset, stream) never share a block
+    w = philox.words(1234, philox.STREAM_A, 7, np.arange(4), 0)
+    assert len({tuple(int(c[i]) for c in w) for i in range(4)}) == 4
+    assert not np.array_equal(w[0], philox.words(1234, philox.STREAM_G, 7, np.arange(4), 0)[0])
+    assert not np.array_equal(w[0], philox.words(1234, philox.STREAM_A, 8, np.arange(4), 0)[0])
+
+
+def _device_stable_A_f32(alpha, xu, xw):
+    """rng.cuh::stable_A operation by operation in numpy float32 (exact log2 / reciprocal in place of the MUFU approximations)."""
+    f32 = np.float32
+    C = [f32(c) for c in (3.14159263689534, -5.167709684792514, 2.5500697262138807, -0.5982421256741446, 0.07756038554456743)]
+
+    def sinpi_half(v, scale):
+        z = (v * v).astype(f32)
+        p = np.full(v.shape, C[4] * scale, dtype=f32)
+        for c in C[3::-1]:
+            p = (p.astype(np.float64) * z + np.float64(c * scale)).astype(f32)  # fmaf: one rounding
+        return (v * p).astype(f32)
+
+    ap, r, om = f32(alpha / 2), f32((1 - alpha / 2) / (alpha / 2)), f32(1 - alpha / 2)
+    top = (xu >> np.uint32(31)).astype(bool)
+    xr = np.where(top, ~xu, xu).astype(np.uint32)
+    v = (xr.astype(f32).astype(np.float64) * 2.0 ** -32 + 2.0 ** -33).astype(f32)
+    u = np.where(top, (f32(1) - v).astype(f32), v)
+    sinU = sinpi_half(v, f32(1))
+    a1 = (ap * u).astype(f32)
+    s1 = sinpi_half(np.minimum(a1, (f32(1) - a1).astype(f32)), f32(2))
+    a2 = (om * u).astype(f32)
+    if om > 0.5:
+        a2 = np.minimum(a2, (f32(1) - a2).astype(f32))
+    s2 = sinpi_half(a2, f32(1))
+    d = np.minimum((xw.astype(f32).astype(np.float64) * 2.0 ** -32 + 2.0 ** -33).astype(f32), f32(0.99999994))
+    series = (d * (f32(1) + d * (f32(0.5) + d * (f32(0.33333334) + d * f32(0.25))))).astype(f32)
+    full = (f32(-0.6931471805599453) * np.log2((f32(1) - d).astype(f32)).astype(f32)).astype(f32)
+    w = np.where(d < f32(0.03125), series, full).astype(f32)
+    q = (f32(1) / (sinU * w).astype(f32)).astype(f32)
+    l2 = (np.log2(((s1 * q).astype(f32) * w).astype(f32)).astype(f32) + r * np.log2((s2 * q).astype(f32)).astype(f32)).astype(f32)
+    return np.exp2(l2).astype(f32)
+
+
+@pytest.mark.parametrize("alpha", [0.8, 1.2, 1.5, 1.7, 1.9, 1.99])
+def test_device_stable_formula_matches_reference_formula(alpha):
+    """The kernel's merged-logarithm / polynomial-sine evaluation (fp32) against scipy's CMS branch restated in float64
+    (oracle/stable.py::kanter_A through oracle/philox.py) on the same words, including both ends of both lattices."""
+    from oracle import philox
+    rs = np.random.RandomState(0)
+    n = 400000
+    xu = rs.randint(0, 2 ** 32, size=n, dtype=np.uint64).astype(np.uint32)
+    xw = rs.randint(0, 2 ** 32, size=n, dtype=np.uint64).astype(np.uint32)
+    k = np.arange(1000, dtype=np.uint32)
+    xu[:1000], xu[1000:2000] = k, np.uint32(2 ** 32 - 1) - k          # U -> 0 and U -> pi (the heavy tail)
+    xw[2000:3000], xw[3000:4000] = k, np.uint32(2 ** 32 - 1) - k      # W -> 0 and W -> max
+    xu[4000:5000], xw[4000:5000] = np.uint32(2 ** 32 - 1) - k, k      # both tails at once
+    with np.errstate(over="ignore"):
+        A = _device_stable_A_f32(alpha, xu, xw).astype(np.float64)
+    ref = philox.stable_A_from_words(alpha, xu, xw)
+    ok = ref < 1e38  # alpha < 1: the joint tail exceeds the fp32 range (inf, like the reference's float32 cast)
+    assert ok.all() or alpha < 1.0
+    assert np.all(np.isfinite(A[ok])) and A.min() > 0 and np.all(A[~ok] > 1e38)
+    np.testing.assert_allclose(A[ok], ref[ok], rtol=2e-5 if alpha < 1.95 else 5e-5)
+    # and the lattice restatement is the published formula: same as kanter_A on U = pi u, W
+    top = (xu >> np.uint32(31)).astype(bool)
+    v = philox._lattice(np.where(top, ~xu, xu))
+    d = np.minimum(philox._lattice(xw), np.float64(np.float32(0.99999994)))
+    lo = ~top  # on the lower half u == v exactly, so the two restatements must agree to rounding
+    np.testing.assert_allclose(ref[lo], stable.kanter_A(alpha, np.pi * v[lo], -np.log1p(-d[lo])), rtol=1e-9)
