@@ -204,3 +204,64 @@ def test_non_isotropic_sigma_chain_and_step(L):
     d.A = (A * 0.5).cuda()
     d.compute_Sigmas()
     assert torch.equal(d.Sigmas.cpu(), process.compute_Sigmas(A * 0.5, sched[0], sched[2]))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# In-kernel noise paths (the production mode): the variates each kernel draws are the documented Philox words
+# (oracle/philox.py), so the kernel's result must equal the ORACLE step fed with the oracle's own evaluation of those variates.
+# ------------------------------------------------------------------------------------------------------------------
+def test_in_kernel_noise_is_the_documented_stream(L):
+    from oracle import philox
+    alpha, T, B, D = 1.7, 20, 37, 48
+    seed, off, base = 0xABCDEF0123, 11, 3
+    sched = process.gen_noise_schedule(alpha, T)
+    _, sd = sched_dev(alpha, T)
+    samples = base + np.arange(B)
+
+    # K2: A_t drawn in-kernel at call offset off + t, clamped; Sigma follows dlpm.py:230-239 on those draws bit for bit
+    Sig, A_out = torch.empty(T, B).cuda(), torch.empty(T, B).cuda()
+    L.call("dlpm_b200_sigma_scan", L.ptr(Sig), None, L.ptr(A_out), L.ptr(sd), T, B, 1, 0, alpha, 20.0, seed, off, base, L.stream_ptr())
+    A_ref = np.stack([philox.sample_A(alpha, seed, off + t, samples, clamp_a=20.0) for t in range(T)])
+    np.testing.assert_allclose(A_out.cpu().numpy(), A_ref, rtol=3e-5)
+    want_S = process.compute_Sigmas(A_out.cpu()[:, :, None], sched[0], sched[2])[:, :, 0]
+    assert np.array_equal(Sig.cpu().numpy(), want_S.numpy())
+
+    # K3 (vector fast path and scalar path): z = N(0,1) of stream Z at call offset off + t
+    torch.manual_seed(1)
+    x0, eps = torch.randn(B, D), torch.randn(B, D)
+    for t in (7, 1):
+        for Dd in (D, D - 1):
+            x = x0[:, :Dd].contiguous().cuda()
+            e = eps[:, :Dd].contiguous().cuda()
+            L.call("dlpm_b200_reverse_step", L.ptr(x), L.ptr(e), L.ptr(Sig), L.ptr(sd), t, None, T, B, Dd, 0, None, seed, off, base, None,
+                   L.stream_ptr())
+            z = torch.from_numpy(philox.normal(seed, off + t, samples, D, stream=philox.STREAM_Z)[:, :Dd]).float()
+            want = process.dlpm_step(x0[:, :Dd], eps[:, :Dd], z, t, Sig.cpu()[:, :, None], sched)
+            np.testing.assert_allclose(x.cpu().numpy(), want.numpy(), rtol=2e-5, atol=2e-5)
+
+    # LIM SDE step: eps_L = sqrt(A_b) G with A from stream EPS_A and G from stream G at call offset off + step
+    coef = torch.tensor([[1.3, 0.97, -0.02, 0.11]] * 4).cuda()
+    step = 2
+    x = x0.clone().cuda()
+    mo = eps.clone().cuda()
+    L.call("dlpm_b200_lim_step", L.ptr(x), L.ptr(mo), L.ptr(coef), step, None, B, D, 0, 0, 1, alpha, 200.0, None, seed, off, base, None,
+           L.stream_ptr())
+    eL = philox.sas_isotropic(alpha, seed, off + step, samples, D, clamp_eps=200.0)
+    sc, a, c_score, c_noise = 1.3, 0.97, -0.02, 0.11
+    want = a * x0.numpy().astype(np.float64) + c_score * (sc * eps.numpy().astype(np.float64)) + c_noise * eL
+    np.testing.assert_allclose(x.cpu().numpy(), want, rtol=1e-4, atol=1e-4 * np.sqrt(np.abs(eL).max()))
+
+    # training elements (dlpm.py:384-401): A from stream A, z from stream Z, both at the call offset
+    tt = torch.randint(1, T, (B,), dtype=torch.int64)
+    xs = torch.rand(B, D) * 2 - 1
+    x_t, e_t = torch.empty(B, D).cuda(), torch.empty(B, D).cuda()
+    xs_d, tt_d = xs.cuda(), tt.cuda()  # keep both alive: a freed temporary's block is handed to the next allocation
+    L.call("dlpm_b200_training_elements", L.ptr(x_t), L.ptr(e_t), L.ptr(xs_d), L.ptr(tt_d), None, None, L.ptr(sd), T, B, D, alpha,
+           20.0, seed, off, base, L.stream_ptr())
+    A_tr = philox.sample_A(alpha, seed, off, samples, clamp_a=20.0)
+    z_tr = philox.normal(seed, off, samples, D, stream=philox.STREAM_Z)
+    bg, bs = sched[1].numpy().astype(np.float64)[tt.numpy()], sched[3].numpy().astype(np.float64)[tt.numpy()]
+    want_eps = np.sqrt(A_tr)[:, None] * z_tr
+    want_xt = bg[:, None] * xs.numpy() + bs[:, None] * want_eps
+    np.testing.assert_allclose(x_t.cpu().numpy(), want_xt, rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(e_t.cpu().numpy(), want_eps, rtol=1e-4, atol=2e-4)
