@@ -488,8 +488,27 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<const uint32_t*>(&v);
 }
 
-template <int D>
-__global__ void __launch_bounds__(128) k_attention_mma(__nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ qkv, int L,
+__device__ __forceinline__ float att_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// 2^x for x <= 0 on the FMA / ALU pipes: round-to-nearest split x = n + f (magic-number add), cubic minimax of 2^f on
+// [-1/2, 1/2] (relative error 7.5e-5, far below the 2^-9 rounding of the bf16 probability it feeds), exponent added to the bits.
+// x < -125 (incl. -inf of masked keys) returns 0.
+__device__ __forceinline__ float att_ex2_poly(float x) {
+  const float xc = fmaxf(x, -125.0f);
+  const float tt = xc + 12582912.0f;          // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float f = xc - (tt - 12582912.0f);    // [-1/2, 1/2]
+  float p = fmaf(f, 0.05517163f, 0.24261112f);
+  p = fmaf(p, f, 0.69326099f);
+  p = fmaf(p, f, 0.99992807f);
+  const float r = __int_as_float(__float_as_int(p) + (__float_as_int(tt) << 23));
+  return x < -125.0f ? 0.0f : r;
+}
+
+template <int D, bool POLY>
+__global__ void __launch_bounds__(256) k_attention_mma(__nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ qkv, int L,
                                                        int C, int heads, int q_blocks) {
   constexpr int KSTR = D + 8;
   extern __shared__ __align__(16) uint8_t att_smem[];
@@ -513,7 +532,7 @@ __global__ void __launch_bounds__(128) k_attention_mma(__nv_bfloat16* __restrict
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int r0 = qb * 64 + warp * 16;
+  const int r0 = qb * (int)(blockDim.x >> 5) * 16 + warp * 16;  // a CTA of w warps owns 16 w query rows of one head
   if (r0 >= L) return;
   uint32_t qa[D / 16][4];
 #pragma unroll
@@ -524,7 +543,11 @@ __global__ void __launch_bounds__(128) k_attention_mma(__nv_bfloat16* __restrict
     qa[kk][2] = __ldg(reinterpret_cast<const uint32_t*>(q0 + 8));
     qa[kk][3] = __ldg(reinterpret_cast<const uint32_t*>(q0 + 8 * rs + 8));
   }
-  // softmax(q.k / sqrt(d)) (unet.py:244-247: q and k are each scaled by d^-1/4), evaluated as exp2((s - m) * log2 e / sqrt(d))
+  // softmax(q.k / sqrt(d)) (unet.py:244-247: q and k are each scaled by d^-1/4), evaluated as exp2(s * c - m * c) with
+  // c = log2 e / sqrt(d): the running maximum is kept on the RAW scores (c > 0), so an element costs one FFMA + one MUFU.EX2
+  // + one FADD (row sum) -- at d = 16 the softmax, not the MMAs, is the bulk of this kernel (L^2 exponentials per head against
+  // 4 d L^2 tensor FLOPs).  POLY evaluates a quarter of the exponentials on the FMA pipes (att_ex2_poly); measured slower
+  // (the kernel is issue-bound, the XU pipe is not the limiter), so it is off unless "attention_poly" = 1.
   const float sl2 = rsqrtf((float)D) * 1.4426950408889634f;
   float o[D / 8][4];
 #pragma unroll
@@ -541,8 +564,6 @@ __global__ void __launch_bounds__(128) k_attention_mma(__nv_bfloat16* __restrict
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk)
           mma_bf16_16816(sc[j], qa[kk], *reinterpret_cast<const uint32_t*>(kr + kk * 16), *reinterpret_cast<const uint32_t*>(kr + kk * 16 + 8));
-#pragma unroll
-        for (int e = 0; e < 4; ++e) sc[j][e] *= sl2;
       } else {
         sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = -INFINITY;
       }
@@ -555,15 +576,17 @@ __global__ void __launch_bounds__(128) k_attention_mma(__nv_bfloat16* __restrict
     }
     mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1)); mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
     mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1)); mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
-    const float c_lo = exp2f(m_lo - mx_lo), c_hi = exp2f(m_hi - mx_hi);
+    const float c_lo = att_ex2((m_lo - mx_lo) * sl2), c_hi = att_ex2((m_hi - mx_hi) * sl2);  // first block: ex2(-inf) = 0
     m_lo = mx_lo; m_hi = mx_hi;
+    const float ms_lo = -m_lo * sl2, ms_hi = -m_hi * sl2;
     l_lo *= c_lo; l_hi *= c_hi;
 #pragma unroll
     for (int nd = 0; nd < D / 8; ++nd) { o[nd][0] *= c_lo; o[nd][1] *= c_lo; o[nd][2] *= c_hi; o[nd][3] *= c_hi; }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      sc[j][0] = exp2f(sc[j][0] - m_lo); sc[j][1] = exp2f(sc[j][1] - m_lo);
-      sc[j][2] = exp2f(sc[j][2] - m_hi); sc[j][3] = exp2f(sc[j][3] - m_hi);
+      sc[j][0] = att_ex2(fmaf(sc[j][0], sl2, ms_lo)); sc[j][1] = att_ex2(fmaf(sc[j][1], sl2, ms_lo));
+      sc[j][2] = att_ex2(fmaf(sc[j][2], sl2, ms_hi));
+      sc[j][3] = POLY ? att_ex2_poly(fmaf(sc[j][3], sl2, ms_hi)) : att_ex2(fmaf(sc[j][3], sl2, ms_hi));
       l_lo += sc[j][0] + sc[j][1];
       l_hi += sc[j][2] + sc[j][3];
     }
@@ -893,7 +916,9 @@ int dlpm_b200_groupnorm_fold(float* ab, int C0, const float* stats0, int parts0,
 }
 
 static int g_attention_mma = 1;  // dlpm_b200_set_option("attention_mma", 0): FMA kernel (A/B and fallback for other shapes)
-namespace dlpm { void attention_set_mma(int on) { g_attention_mma = on; } }
+static int g_attention_poly = -1;  // -1 = auto = off: measured slower (MNIST forward, 5 + 6 attention blocks: 1.65 vs 1.53 ms) -- the kernel is
+                                    // issue / latency-bound, not XU-bound; 1 forces the polynomial variant ("attention_poly")
+namespace dlpm { void attention_set_mma(int on) { g_attention_mma = on; } void attention_set_poly(int v) { g_attention_poly = v; } }
 
 int dlpm_b200_attention(void* out, const void* qkv, int64_t B, int L, int C, int heads, void* stream) {
   DLPM_REQUIRE(out && qkv, "attention: NULL tensor");
@@ -906,15 +931,19 @@ int dlpm_b200_attention(void* out, const void* qkv, int64_t B, int L, int C, int
   cudaStream_t s = (cudaStream_t)stream;
   {  // tensor-core path
     const size_t msmem = ((size_t)L * (D + 8) + (size_t)D * (L + 8)) * 2;
-    const int q_blocks = (L + 63) / 64;
+    // 8 warps (128 query rows) per CTA when the head has them: K / V of the head are staged half as often as with 4
+    const int rows_per_cta = L >= 128 ? 128 : 64;
+    const int q_blocks = (L + rows_per_cta - 1) / rows_per_cta;
     if ((D == 16 || D == 32 || D == 64) && L % 16 == 0 && msmem <= 200 * 1024 && B * heads * q_blocks < (1ll << 31) && g_attention_mma) {
-      const int mthreads = L >= 64 ? 128 : (L / 16) * 32;
+      const int mthreads = L >= 128 ? 256 : (L >= 64 ? 128 : (L / 16) * 32);
       const unsigned mgrid = (unsigned)(B * heads * q_blocks);
+      const bool poly = g_attention_poly > 0;
 #define ATTM(DD)                                                                                                     \
   case DD: {                                                                                                         \
-    cudaError_t e = cudaFuncSetAttribute(k_attention_mma<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem); \
+    auto kern = poly ? k_attention_mma<DD, true> : k_attention_mma<DD, false>;                                       \
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem);             \
     if (e != cudaSuccess) return cuda_fail(e, "attention smem attribute");                                           \
-    cudaError_t e2 = launch_ex(k_attention_mma<DD>, dim3(mgrid), dim3(mthreads), msmem, s, 1, o, q, L, C, heads, q_blocks); \
+    cudaError_t e2 = launch_ex(kern, dim3(mgrid), dim3(mthreads), msmem, s, 1, o, q, L, C, heads, q_blocks);         \
     if (e2 != cudaSuccess) return cuda_fail(e2, "attention launch");                                                 \
   } break
       switch (D) { ATTM(16); ATTM(32); ATTM(64); }

@@ -150,13 +150,19 @@ def test_groupnorm_silu(L, C0, C1, HW, ss, silu):
         np.testing.assert_allclose(from_nhwc(out).numpy(), want.numpy(), rtol=1.5e-2, atol=1.5e-2)
 
 
-@pytest.mark.parametrize("L_,C,heads", [(16, 256, 4), (256, 64, 4), (64, 64, 4), (16, 64, 4)])
-def test_attention(L, L_, C, heads):
+@pytest.mark.parametrize("poly", [-1, 0, 1])  # softmax exponentials: auto / all MUFU.EX2 / a quarter on the FMA pipes
+@pytest.mark.parametrize("L_,C,heads", [(16, 256, 4), (256, 64, 4), (64, 64, 4), (16, 64, 4), (1024, 128, 4)])
+def test_attention(L, L_, C, heads, poly):
     B = 3
-    qkv = rnd(B, 3 * C, L_, seed=7)
+    qkv = rnd(B, 3 * C, L_, seed=7) * (3.0 if L_ == 1024 else 1.0)  # wide score range: exercises the running-maximum rescale
     qd = bf(qkv.permute(0, 2, 1).contiguous()).cuda()  # [B, L, 3C]
+    qkv = qd.float().cpu().permute(0, 2, 1).contiguous()  # the reference sees the same bf16-rounded operands
     out = torch.zeros(B, L_, C, device="cuda", dtype=torch.bfloat16)
-    L.call("dlpm_b200_attention", L.ptr(out), L.ptr(qd), B, L_, C, heads, L.stream_ptr())
+    L.call("dlpm_b200_set_option", b"attention_poly", poly)
+    try:
+        L.call("dlpm_b200_attention", L.ptr(out), L.ptr(qd), B, L_, C, heads, L.stream_ptr())
+    finally:
+        L.call("dlpm_b200_set_option", b"attention_poly", -1)
     q = qkv.reshape(B * heads, -1, L_)
     ch = q.shape[1] // 3
     qq, kk, vv = torch.split(q, ch, dim=1)
