@@ -305,6 +305,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (p.tall) {
           const int a_tall_bytes = (msub * p.Hb + 2) * p.Wb * BLOCK_K * 2;
           const int n_sb = 3 * p.cin_blocks + p.s0_blocks + p.s1_blocks;
+          const int row_units = (p.Wb * BLOCK_K * 2) >> 4, sub_units = p.Hb * row_units;  // descriptor address units (16 bytes)
           for (int sb = 0; sb < n_sb; ++sb) {
             mbar_wait(full_bar + stage, phase);
             if (XF) mbar_wait(xf_bar + stage, phase);  // activation boxes of both CTAs normalised in place
@@ -313,18 +314,42 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const uint32_t b_addr = a_addr + a_tall_bytes;
             bool main_part; int slot_idx;
             tall_slot(sb, 3 * p.cin_blocks, p.s0_blocks + p.s1_blocks, !XF, main_part, slot_idx);
-            const int n_j = main_part ? 3 : 1;
-            for (int j = 0; j < n_j; ++j) {
-              for (int sub = 0; sub < msub; ++sub) {
-                // dy = j - 1: shift by Wb rows (whole swizzle atoms); sub-tile `sub` starts Hb image rows further down
-                const uint32_t a_j = main_part ? a_addr + (uint32_t)((sub * p.Hb + j) * p.Wb * BLOCK_K * 2) : a_addr + (uint32_t)(sub * A_BYTES);
-                const uint32_t d_sub = d_tmem + (uint32_t)(sub * BLOCK_N);
-                // a K step of 16 elements = 32 bytes inside the swizzled row: the descriptor's address field (>> 4) moves by 2
-                const uint64_t da0 = make_smem_desc<SWZ>(a_j), db0 = make_smem_desc<SWZ>(b_addr + j * B_BYTES);
+            // One descriptor pair per stage; every (dy, sub-tile, K step) operand is that descriptor plus a loop-invariant
+            // offset in its 16-byte address field (dy = j - 1 shifts by Wb rows = whole swizzle atoms, sub-tile `sub` starts Hb
+            // image rows further down, tap j's weight tile follows tap j-1's, a K step of 16 elements is 32 bytes inside the
+            // swizzled row).  Fully unrolled: the issue loop costs a 64-bit add per operand instead of re-deriving addresses
+            // and descriptors per MMA (ncu on the N = 32 layers: 24 warp instructions = 109 clk per MMA in the issuing warp
+            // against 16 clk of tensor work; the MMA issuer, not TMA or the epilogue, set the pace).
+            const uint64_t da_s = make_smem_desc<SWZ>(a_addr), db_s = make_smem_desc<SWZ>(b_addr);
+            if (main_part) {
 #pragma unroll
-                for (int k = 0; k < BLOCK_K / 16; ++k) {
-                  if (CG == 2) umma_bf16_pair_e(elected, d_sub, da0 + 2 * k, db0 + 2 * k, IDESC, (sb | j | k) != 0);
-                  else umma_bf16_e(elected, d_sub, da0 + 2 * k, db0 + 2 * k, IDESC, (sb | j | k) != 0);
+              for (int j = 0; j < 3; ++j) {
+#pragma unroll
+                for (int sub = 0; sub < MS_MAX; ++sub) {
+                  if (sub < msub) {
+                    const uint64_t da0 = da_s + (uint64_t)(uint32_t)(sub * sub_units + j * row_units);
+                    const uint64_t db0 = db_s + (uint64_t)(j * (B_BYTES >> 4));
+                    const uint32_t d_sub = d_tmem + (uint32_t)(sub * BLOCK_N);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / 16; ++k) {
+                      const uint32_t accum = (j | k) != 0 ? 1u : (uint32_t)(sb != 0);
+                      if (CG == 2) umma_bf16_pair_e(elected, d_sub, da0 + 2 * k, db0 + 2 * k, IDESC, accum);
+                      else umma_bf16_e(elected, d_sub, da0 + 2 * k, db0 + 2 * k, IDESC, accum);
+                    }
+                  }
+                }
+              }
+            } else {  // fused 1x1 skip-conv stage: plain 128-row A tiles, one weight tile
+#pragma unroll
+              for (int sub = 0; sub < MS_MAX; ++sub) {
+                if (sub < msub) {
+                  const uint64_t da0 = da_s + (uint64_t)(sub * (A_BYTES >> 4));
+                  const uint32_t d_sub = d_tmem + (uint32_t)(sub * BLOCK_N);
+#pragma unroll
+                  for (int k = 0; k < BLOCK_K / 16; ++k) {
+                    if (CG == 2) umma_bf16_pair_e(elected, d_sub, da0 + 2 * k, db_s + 2 * k, IDESC, (sb | k) != 0);
+                    else umma_bf16_e(elected, d_sub, da0 + 2 * k, db_s + 2 * k, IDESC, (sb | k) != 0);
+                  }
                 }
               }
             }
