@@ -29,7 +29,8 @@ using namespace tc;
 
 constexpr int kMaxStages = 8;
 constexpr int kConvThreads = 256;
-constexpr int kConvThreadsEpi2 = 384;  // + warps 8-11: a second epilogue warp per TMEM lane quadrant (tiles with >= 2 column chunks)
+constexpr int kConvThreadsEpi2 = 384;  // + warps 8-11: a second epilogue warp per TMEM lane quadrant (they split the tile's column chunks, or --
+                                       // one-chunk tiles, N <= 32 -- the two sub-tiles of the work item)
 constexpr int kConvThreadsXF = 512;  // + warps 8-15: the eight transform warps (two per SM sub-partition)
 constexpr int kXfWarps = 8;
 constexpr int kSmemBudget = 204 * 1024;  // operand ring; epilogue staging, barriers, bias and alignment slack come on top (227 KB per CTA)
@@ -94,7 +95,7 @@ __device__ __forceinline__ void tall_slot(int sb, int n_main, int n_skip, bool i
 }
 
 template <int BLOCK_N, bool XF>
-__host__ __device__ constexpr int conv_epi_groups() { return (BLOCK_N >= 64 && !XF) ? 2 : 1; }
+__host__ __device__ constexpr int conv_epi_groups() { return XF ? 1 : 2; }
 template <int BLOCK_N, bool XF>
 __host__ __device__ constexpr int conv_threads() { return XF ? kConvThreadsXF : (conv_epi_groups<BLOCK_N, XF>() == 2 ? kConvThreadsEpi2 : kConvThreads); }
 
@@ -118,7 +119,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   constexpr uint32_t TMEM_COLS = ACC_COLS <= 32 ? 32 : (ACC_COLS <= 64 ? 64 : (ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512)));
   constexpr uint32_t IDESC = make_idesc_bf16(128 * CG, BLOCK_N);
   // short-K layers are epilogue-bound with one warp per quadrant (TMEM load -> bias/residual/statistics -> store is a long
-  // dependent chain): two warps per quadrant split the tile's column chunks and interleave on the same sub-partition
+  // dependent chain): two warps per quadrant split the tile's column chunks and interleave on the same sub-partition.
+  // Tiles with a single chunk (N <= 32: the 32-channel layers of the MNIST network, the final conv) split the work item's
+  // two SUB-TILES instead.
   constexpr int EG = conv_epi_groups<BLOCK_N, XF>();
 
   extern __shared__ uint8_t smem_raw[];
@@ -478,18 +481,20 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         // identity-skip rows are fetched BEFORE waiting for the accumulator so their HBM latency hides behind the MMAs
         constexpr bool RES_PREFETCH = !XF;  // XF kernels run 512 threads (128 registers each): residual rows are read in place
         constexpr int NCH = BLOCK_N / CH;  // column chunks of the tile; this warp owns chunks eg, eg + EG, ...
-        uint4 resv[RES_PREFETCH ? MS_MAX : 1][RES_PREFETCH ? BLOCK_N / 8 / EG : 1];
+        constexpr bool SPLIT_SUB = NCH < EG;            // ... or, one-chunk tiles: sub-tiles eg, eg + EG, ... of the work item
+        constexpr int CPW = SPLIT_SUB ? NCH : NCH / EG;  // chunks per warp
+        uint4 resv[RES_PREFETCH ? MS_MAX : 1][RES_PREFETCH ? CPW * (CH / 8) : 1];
         const bool has_res = p.residual != nullptr && valid;
         if (RES_PREFETCH && has_res) {
 #pragma unroll
           for (int sub = 0; sub < MS_MAX; ++sub) {
-            if (sub < msub) {
+            if (sub < msub && (!SPLIT_SUB || (sub & (EG - 1)) == eg)) {
               const int64_t pix = (nn * p.H_full + p.out_scale * (h0 + sub * p.Hb + h_in) + out_oy) * p.W_full + p.out_scale * w_in + out_ox;
               const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.C_out + nt * BLOCK_N);
 #pragma unroll
-              for (int ci = 0; ci < NCH / EG; ++ci)
+              for (int ci = 0; ci < CPW; ++ci)
 #pragma unroll
-                for (int j = 0; j < CH / 8; ++j) resv[sub][ci * (CH / 8) + j] = __ldg(rp + (ci * EG + eg) * (CH / 8) + j);
+                for (int j = 0; j < CH / 8; ++j) resv[sub][ci * (CH / 8) + j] = __ldg(rp + (SPLIT_SUB ? ci : ci * EG + eg) * (CH / 8) + j);
             }
           }
         }
@@ -501,16 +506,16 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           pixs[sub] = (nn * p.H_full + p.out_scale * (h0 + sub * p.Hb + h_in) + out_oy) * p.W_full + p.out_scale * w_in + out_ox;
         // GroupNorm statistics of the tensor being written (consumed by k_gn_apply / the fold kernel): per warp, per
         // channel QUAD, (sum, sum of squares) over the warp's 32 pixels (x msub sub-tiles) -- no second pass over the output
-        const bool do_stats = CH == 32 && p.stats != nullptr && valid;
+        const bool do_stats = CH == 32 && !SPLIT_SUB && p.stats != nullptr && valid;  // (N >= 64 only: conv_stats_parts)
 #pragma unroll
-        for (int ci = 0; ci < NCH / EG; ++ci) {
-          const int c0 = (ci * EG + eg) * CH;
+        for (int ci = 0; ci < CPW; ++ci) {
+          const int c0 = (SPLIT_SUB ? ci : ci * EG + eg) * CH;
           float st[CH / 2];
 #pragma unroll
           for (int i = 0; i < CH / 2; ++i) st[i] = 0.f;
 #pragma unroll
           for (int sub = 0; sub < MS_MAX; ++sub) {
-            if (sub < msub) {
+            if (sub < msub && (!SPLIT_SUB || (sub & (EG - 1)) == eg)) {
               const uint32_t t_row = t_row0 + (uint32_t)(sub * BLOCK_N);
               uint32_t r[CH];
               if constexpr (CH == 32) tmem_ld_x32(t_row + c0, r);
@@ -571,7 +576,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
           }
           if constexpr (CH == 32) {
-            if (p.stats != nullptr) {  // warp-uniform (so is valid: a warp's 32 pixels belong to one image)
+            if (!SPLIT_SUB && p.stats != nullptr) {  // warp-uniform (so is valid: a warp's 32 pixels belong to one image)
               // transposing butterfly: 16 values over 32 lanes in 8+4+2+1+1 shuffles; lane l ends with the total of value l>>1
 #pragma unroll
               for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
@@ -598,7 +603,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         tc_fence_after();
 #pragma unroll
         for (int sub = 0; sub < MS_MAX; ++sub) {
-          if (sub < msub) {
+          if (sub < msub && (sub & (EG - 1)) == eg) {  // N = 16: one chunk, the quadrant's two warps take one sub-tile each
             uint32_t r[16];
             tmem_ld_x16(t_row0 + (uint32_t)(sub * BLOCK_N), r);
             tmem_ld_wait();
@@ -814,7 +819,7 @@ int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, c
 // Partial-statistics rows per image this conv can emit for the GroupNorm that consumes its output (0 = not supported):
 // one row per epilogue warp (4) per work unit of the image per output parity.
 int conv_stats_parts(const ConvLaunch& L) {
-  if (L.out_mode != CONV_OUT_BF16_NHWC || L.block_n < 32 || L.C_out % 4) return 0;
+  if (L.out_mode != CONV_OUT_BF16_NHWC || L.block_n < 64 || L.C_out % 4) return 0;  // one-chunk tiles split sub-tiles over the epilogue warps
   if (L.Nb == 1) return 4 * (L.tiles_per_img / L.msub) * L.n_par;
   // several images per tile: every epilogue warp (32 pixels) must lie inside one image
   return (L.Wb * L.Hb) % 32 == 0 ? ((L.Wb * L.Hb) / 32) * L.n_par : 0;
