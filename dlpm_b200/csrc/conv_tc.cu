@@ -61,6 +61,8 @@ struct ConvKParams {
   int c0_blocks, c_in_total;  // XF: channel blocks served by the first main source (tmA), the rest come from tmA2
   float* stats;           // GroupNorm partial sums of the output [B][stats_parts][C_out/4][2], or nullptr
   int stats_parts, units_per_img, stats_wpi;  // rows per image, work units per image, epilogue warps per image and unit
+  FastDiv fd_ipp, fd_nnt, fd_tpi;  // multiply-high division by items_per_par / n_n_tiles / tiles_per_img: the per-item index math of
+                                   // the producer and epilogue warps sits on the critical path of short-K work items
 };
 
 // CG = 1: one CTA per 128-pixel tile.  CG = 2: a CTA PAIR (cluster of 2 on one TPC) computes two adjacent 128-pixel
@@ -185,12 +187,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const bool elected = elect_one();
       int stage = 0; uint32_t phase = 0;
       for (int item = first_item; item < n_items; item += item_stride) {
-        const int par = item / items_per_par, it_in = item - par * items_per_par;
-        const int nt = it_in % p.n_n_tiles, mt = ((it_in / p.n_n_tiles) * CG + (int)cta_rank) * msub;
+        const int par = (int)p.fd_ipp.div((uint32_t)item), it_in = item - par * items_per_par;
+        const int mg = (int)p.fd_nnt.div((uint32_t)it_in), nt = it_in - mg * p.n_n_tiles, mt = (mg * CG + (int)cta_rank) * msub;
         const int dy_base = p.dy0 + (p.n_par == 4 ? (par >> 1) : 0), dx_base = p.dx0 + (p.n_par == 4 ? (par & 1) : 0);
         const int brow0 = par * p.c_out_pad + nt * BLOCK_N + (int)cta_rank * B_ROWS;
         int n0, h0;
-        if (p.Nb == 1) { n0 = mt / p.tiles_per_img; h0 = (mt - n0 * p.tiles_per_img) * p.Hb; }
+        if (p.Nb == 1) { n0 = (int)p.fd_tpi.div((uint32_t)mt); h0 = (mt - n0 * p.tiles_per_img) * p.Hb; }
         else { n0 = mt * p.Nb; h0 = 0; }
         if (p.tall) {
           const int a_tall_bytes = (msub * p.Hb + 2) * p.Wb * BLOCK_K * 2;
@@ -465,11 +467,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int w_box = m0 % p.Wb, h_box = (m0 / p.Wb) % p.Hb, n_box = m0 / (p.Wb * p.Hb);
     int it = 0;
     for (int item = first_item; item < n_items; item += item_stride, ++it) {
-      const int par = item / items_per_par, it_in = item - par * items_per_par;
-      const int nt = it_in % p.n_n_tiles, mt = ((it_in / p.n_n_tiles) * CG + (int)cta_rank) * msub;
+      const int par = (int)p.fd_ipp.div((uint32_t)item), it_in = item - par * items_per_par;
+      const int mg = (int)p.fd_nnt.div((uint32_t)it_in), nt = it_in - mg * p.n_n_tiles, mt = (mg * CG + (int)cta_rank) * msub;
       const int out_oy = p.n_par == 4 ? (par >> 1) : p.out_oy, out_ox = p.n_par == 4 ? (par & 1) : p.out_ox;
       int n0, h0;
-      if (p.Nb == 1) { n0 = mt / p.tiles_per_img; h0 = (mt - n0 * p.tiles_per_img) * p.Hb; }
+      if (p.Nb == 1) { n0 = (int)p.fd_tpi.div((uint32_t)mt); h0 = (mt - n0 * p.tiles_per_img) * p.Hb; }
       else { n0 = mt * p.Nb; h0 = 0; }
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -867,6 +869,12 @@ static int launch_t(const ConvLaunch& L, cudaStream_t stream) {
   p.ab = reinterpret_cast<const float2*>(L.ab); p.c0_blocks = L.c0_blocks; p.c_in_total = L.cin_blocks * BK;
   p.stats = L.stats; p.stats_parts = conv_stats_parts(L); p.units_per_img = L.tiles_per_img > 0 ? L.tiles_per_img / L.msub : 1;
   p.stats_wpi = L.Nb == 1 ? 4 : (L.Wb * L.Hb) / 32;
+  {
+    const int ipp = ((L.n_m_tiles / L.msub + CG - 1) / CG) * L.n_n_tiles;
+    p.fd_ipp = FastDiv((uint32_t)(ipp > 0 ? ipp : 1));
+    p.fd_nnt = FastDiv((uint32_t)(L.n_n_tiles > 0 ? L.n_n_tiles : 1));
+    p.fd_tpi = FastDiv((uint32_t)(L.tiles_per_img > 0 ? L.tiles_per_img : 1));
+  }
   const int n_items = ((L.n_m_tiles / L.msub + CG - 1) / CG) * L.n_n_tiles * L.n_par;
   const int max_groups = kNumSMs / CG;
   const int grid = (n_items < max_groups ? n_items : max_groups) * CG;
