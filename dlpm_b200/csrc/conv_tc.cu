@@ -522,11 +522,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               uint32_t r[CH];
               if constexpr (CH == 32) tmem_ld_x32(t_row + c0, r);
               else tmem_ld_x16(t_row + c0, r);
-              tmem_ld_wait();
               if (CH == 32 && p.tma_store) {  // the staging buffer is free once the previous box has been read out
-                if (lane == 0) bulk_wait_read0();
+                if (lane == 0) bulk_wait_read0();  // (waited for while the TMEM load is in flight)
                 __syncwarp();
               }
+              tmem_ld_wait();
               if (valid) {
                 const int col = nt * BLOCK_N + c0;
                 const uint32_t bias_s = smem_u32(s_bias) + (uint32_t)col * 4u;  // explicit shared-space address: LDS.128
