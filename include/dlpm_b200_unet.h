@@ -45,7 +45,9 @@ int dlpm_b200_conv2d_stats(const void* in, const void* w, const float* bias, con
 /* Tuning / debugging knobs.  "conv_cta_group": 0 = automatic (CTA pairs with tcgen05 cta_group::2 when the problem has
  * enough tiles), 1 = always single-CTA MMAs, 2 = always CTA pairs.  "conv_tall": 1 (default) lets 3x3 stride-1 convs with
  * narrow output tiles load one (rows+2)-tall activation box per horizontal tap and reuse it for the three vertical taps,
- * 0 loads one box per tap.  Takes effect for descriptors built afterwards. */
+ * 0 loads one box per tap.  "attention_mma": 1 (default) = tensor-core attention kernel, 0 = FMA kernel.  "attention_poly":
+ * 1 evaluates a quarter of the softmax exponentials on the FMA pipes (measured slower; default -1 / 0 = all on MUFU.EX2).
+ * Takes effect for descriptors built afterwards. */
 int dlpm_b200_set_option(const char* name, int value);
 
 /* K6. GroupNorm(min(32,C) groups, eps 1e-5) over the virtual concatenation [in0 | in1] of two NHWC bf16
