@@ -912,7 +912,7 @@ int conv_launch(const ConvLaunch& L, cudaStream_t stream) {
 
 }  // namespace dlpm
 
-namespace dlpm { void attention_set_mma(int on); void attention_set_poly(int v); void engine_set_gn_stats(bool on); void engine_set_gn_fuse(int mode); bool process_set_option(const char* name, int value); }
+namespace dlpm { void attention_set_mma(int on); void attention_set_poly(int v); void gn_apply_set_min_elems(int v); void engine_set_gn_stats(bool on); void engine_set_gn_fuse(int mode); bool process_set_option(const char* name, int value); }
 using namespace dlpm;
 
 int dlpm_b200_set_option(const char* name, int value) {
@@ -943,6 +943,10 @@ int dlpm_b200_set_option(const char* name, int value) {
   }
   if (std::string(name) == "attention_mma") {
     attention_set_mma(value);
+    return DLPM_OK;
+  }
+  if (std::string(name) == "gn_apply_min_elems") {
+    gn_apply_set_min_elems(value);
     return DLPM_OK;
   }
   if (std::string(name) == "attention_poly") {
