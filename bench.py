@@ -343,7 +343,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch-per-gpu", type=int, default=512)
     ap.add_argument("--reverse-steps", type=int, default=T_STEPS)
-    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--e2e-steps", type=int, default=2)  # two passes: one pass alone carries the +-3 % power-cap jitter
     ap.add_argument("--cpu-batch", type=int, default=8)
     ap.add_argument("--cpu-substeps", type=int, default=3)
     args = ap.parse_args()
