@@ -1,0 +1,37 @@
+"""CPU: the bench.py contract that can be checked without a GPU -- the reference arm (oracle port on the host cores) prints
+ONE JSON line with the required keys, and the product arm refuses to run without CUDA (no CPU fallback)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def run_bench(*args, timeout=600):
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", ""))
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True, timeout=timeout, env=env)
+
+
+def test_reference_arm_json_line():
+    r = run_bench("--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-batch", "2", "--cpu-substeps", "1")
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, "stdout must carry exactly one JSON line"
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "samples/s" and d["higher_is_better"] is True
+    assert d["metric"].startswith("DLPM samples/sec") and d["value"] > 0 and d["vs_baseline"] is None
+    assert d["config"]["workload"].startswith("CIFAR-10-LT") and d["config"]["reverse_steps"] == 1000
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the behaviour on a machine without a GPU")
+def test_product_arm_needs_cuda():
+    r = run_bench("--steps", "1", "--warmup", "0", "--e2e-steps", "0", timeout=300)
+    assert r.returncode != 0, "the product arm must fail loudly without CUDA, not fall back to the CPU"
+    assert not [l for l in r.stdout.splitlines() if l.strip().startswith("{")]
