@@ -295,3 +295,49 @@ def test_device_stable_formula_matches_reference_formula(alpha):
     d = np.minimum(philox._lattice(xw), np.float64(np.float32(0.99999994)))
     lo = ~top  # on the lower half u == v exactly, so the two restatements must agree to rounding
     np.testing.assert_allclose(ref[lo], stable.kanter_A(alpha, np.pi * v[lo], -np.log1p(-d[lo])), rtol=1e-9)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The caller of the boundary (bem/GenerationManager.generate) restated in oracle/caller.py, against the real one
+# ------------------------------------------------------------------------------------------------------------------
+class _RecordingMethod:
+    """Stands in for GenerativeLevyProcess: records what the caller passes to sample() and returns fixed tensors."""
+
+    def __init__(self, T=5):
+        self.calls, self.T = [], T
+
+    def sample(self, **kw):
+        self.calls.append({k: (v if not isinstance(v, dict) else sorted(v)) for k, v in kw.items()})
+        g = torch.Generator().manual_seed(3)
+        shape = kw["shape"]
+        x = torch.randn(*shape, generator=g) * 2.0
+        if kw.get("get_sample_history"):
+            hist = torch.randn(self.T, *shape, generator=g) * 2.0
+            return x, hist
+        return x
+
+
+@pytest.mark.parametrize("is_image,shape", [(True, (4, 3, 8, 8)), (False, (4, 1, 2))])
+@pytest.mark.parametrize("history", [False, True])
+def test_restated_caller_matches_generation_manager(is_image, shape, history):
+    from oracle import caller, ref_import
+    if not ref_import.available():
+        pytest.skip("reference tree not present (GPU box)")
+    ref_import.load()
+    import importlib
+    GM = importlib.import_module("bem.GenerationManager").GenerationManager
+    loader = [(torch.zeros(*shape), torch.zeros(shape[0]))]
+    mgr_kwargs = dict(reverse_steps=5, clamp_a=20, clamp_eps=200, deterministic=False)
+    m_ref, m_new = _RecordingMethod(), _RecordingMethod()
+    gm = GM(m_ref, loader, is_image, **mgr_kwargs)
+    gm.generate({"default": None}, 7, get_sample_history=history, reverse_steps=3)
+    samples, hist = caller.generation_manager_generate(m_new, {"default": None}, shape, 7, is_image, manager_kwargs=mgr_kwargs,
+                                                       get_sample_history=history, reverse_steps=3)
+    assert m_ref.calls == m_new.calls and m_new.calls[0]["shape"] == [7] + list(shape[1:]) and m_new.calls[0]["reverse_steps"] == 3
+    assert torch.equal(gm.samples, samples)
+    if history:
+        assert torch.equal(gm.history, hist)
+    else:
+        assert len(gm.history) == 0 and len(hist) == 0
+    if is_image:
+        assert float(samples.min()) >= 0.0 and float(samples.max()) <= 1.0
