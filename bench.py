@@ -315,7 +315,7 @@ def run_ours(args, rank, local_rank, world):
                            "same_traffic_torch_add_GB/s": 12 * n_el / ms_add / 1e6}
     nn = (n_noise // 3072) * 3072
     hbm["sas_noise_isotropic"] = {"bytes_per_launch": 4 * nn, "ms": ms_k1, "GB/s": 4 * nn / ms_k1 / 1e6, "frac": 4 * nn / ms_k1 / 1e6 / hbm_peak,
-                                  "limiter": "fmaheavy (Philox4x32-10: 20 IMAD.WIDE per 4 normals) + XU (Box-Muller: 2 MUFU per normal), see profiles/r01_ncu_stream.md"}
+                                  "limiter": "instruction dispatch: each of the 20 IMAD.WIDE of Philox4x32-10 per 4 normals holds the port 4 cycles (+ Box-Muller: 2 MUFU per normal), see profiles/r01_ncu_stream.md"}
 
     launches_per_pass = (T - 1) * (eng.num_launches() + 2) + 3
     if rank == 0:
