@@ -87,12 +87,30 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference's PyTorch path (the reference itself cannot travel to the GPU box)
+# CPU arm: the UNMODIFIED reference (oracle/_ref = verbatim copy installed by oracle/install_ref.py; /root/reference in
+# the build container) on the box's host cores; the oracle port only if no copy of the reference is present
 # ------------------------------------------------------------------------------------------------------------------
 def cpu_reference_step(b_cpu, n_sub, seed=0):
-    """One bounded sample of the workload on the host cores: the full A/Sigma set-up for T=1000 at batch b_cpu, then
-    n_sub reverse steps (UNet forward + posterior update), extrapolated linearly to the 999 steps of a full pass.
-    Returns (samples_per_sec, seconds_spent, description)."""
+    """One bounded sample of the workload on the host cores.  Returns (samples_per_sec, seconds_spent, description, kind)."""
+    from oracle import ref_import
+    if ref_import.available():
+        from oracle import ref_driver
+        v, spent, desc, _ = ref_driver.cpu_arm(b_cpu, n_sub, T=T_STEPS, alpha=ALPHA, img=IMG, ch=CH, seed=seed)
+        # contract vocabulary: "reference" = the reference's own code "port" = the oracle restatement
+        return v, spent, desc, "reference"
+    v, spent, desc = cpu_port_step(b_cpu, n_sub, seed)
+    return v, spent, desc, "port"
+
+
+def reference_source():
+    """Where the reference arm's code comes from: '/root/reference', 'oracle/_ref' (verbatim installed copy) or 'oracle port'."""
+    from oracle import ref_import
+    return {"reference": "/root/reference", "_ref": "oracle/_ref"}.get(ref_import.kind(), "oracle port")
+
+
+def cpu_port_step(b_cpu, n_sub, seed=0):
+    """Fallback when neither /root/reference nor oracle/_ref exists: the oracle port of the reference CPU path --
+    the full A/Sigma set-up for T=1000 at batch b_cpu, then n_sub reverse steps, extrapolated linearly."""
     import numpy as np
     import torch
     from dlpm_b200.init_utils import randomize_parameters_
@@ -131,9 +149,9 @@ def run_reference(args, rank):
     if rank != 0:
         return
     vals, spent = [], 0.0
-    desc = ""
+    desc, kind = "", "port"
     for i in range(args.warmup + args.steps):
-        v, s, desc = cpu_reference_step(args.cpu_batch, args.cpu_substeps, seed=i)
+        v, s, desc, kind = cpu_reference_step(args.cpu_batch, args.cpu_substeps, seed=i)
         spent += s
         if i >= args.warmup:
             vals.append(v)
@@ -145,7 +163,7 @@ def run_reference(args, rank):
             "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup, "ms_per_step": 1000.0 * args.cpu_batch / value,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, args.cpu_batch, 1),
-            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": desc},
+            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": kind, "source": reference_source(), "sample": desc},
             "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     emit(line)
 
@@ -318,8 +336,26 @@ def run_ours(args, rank, local_rank, world):
                                   "limiter": "instruction dispatch: each of the 20 IMAD.WIDE of Philox4x32-10 per 4 normals holds the port 4 cycles (+ Box-Muller: 2 MUFU per normal), see profiles/r01_ncu_stream.md"}
 
     launches_per_pass = (T - 1) * (eng.num_launches() + 2) + 3
+    # ---- same-box GPU baseline: the UNMODIFIED reference with device='cuda' (PyTorch eager + cuDNN, TF32 convs), in the
+    # chunk size its own eval config uses (64, dlpm/configs/cifar10_lt.yml:35) and at 256 (its (T,B,C,H,W) tables: 6 GB)
+    gpu_eager = None
+    if rank == 0 and world == 1 and args.gpu_eager:
+        try:
+            from oracle import ref_import
+            if ref_import.available():
+                from oracle import ref_driver
+                del xs, out, eps, xw, nbuf, big
+                torch.cuda.empty_cache()
+                runs = [ref_driver.gpu_eager_arm(dev, b, n_steps=20, T=T, alpha=ALPHA, img=IMG, ch=CH) for b in (64, 256)]
+                best = max(runs, key=lambda r: r["value"])
+                gpu_eager = dict(best, runs=[{"batch": r["batch"], "value": r["value"], "ms_per_reverse_step": r["ms_per_reverse_step"],
+                                              "setup_s": r["setup_s"]} for r in runs])
+            else:
+                gpu_eager = {"unavailable": "no copy of the reference on this box (oracle/_ref missing)"}
+        except Exception as e:  # the baseline must never take the bench line down
+            gpu_eager = {"unavailable": "%s: %s" % (type(e).__name__, e)}
     if rank == 0:
-        cpu_val, _, cpu_desc = cpu_reference_step(args.cpu_batch, args.cpu_substeps)
+        cpu_val, _, cpu_desc, cpu_kind = cpu_reference_step(args.cpu_batch, args.cpu_substeps)
         line = {"metric": "DLPM samples/sec (1000 reverse steps, CIFAR-10 shape)", "value": value, "unit": "samples/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "ms_each_step": each, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, B, world),
@@ -327,8 +363,8 @@ def run_ours(args, rank, local_rank, world):
                         "d2h_bytes_per_step": int(host_out.numel() * 4 * world), "steps": args.e2e_steps,
                         "api": "GenerativeLevyProcess.sample() + GenerationManager post-processing + pinned D2H"},
                 "gpu_launches": int(launches_per_pass * (args.steps + args.e2e_steps)), "clocks": clk, "roofline": roofline,
-                "hbm_kernels": hbm,
-                "cpu_baseline": {"value": cpu_val, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port", "sample": cpu_desc},
+                "hbm_kernels": hbm, "gpu_eager_baseline": gpu_eager,
+                "cpu_baseline": {"value": cpu_val, "unit": "samples/s", "cores": os.cpu_count(), "kind": cpu_kind, "source": reference_source(), "sample": cpu_desc},
                 "workspace_gb": eng.workspace_bytes / 1e9}
         emit(line)
     if world > 1:
@@ -344,8 +380,9 @@ def main():
     ap.add_argument("--batch-per-gpu", type=int, default=512)
     ap.add_argument("--reverse-steps", type=int, default=T_STEPS)
     ap.add_argument("--e2e-steps", type=int, default=2)  # two passes: one pass alone carries the +-3 % power-cap jitter
-    ap.add_argument("--cpu-batch", type=int, default=8)
+    ap.add_argument("--cpu-batch", type=int, default=16)
     ap.add_argument("--cpu-substeps", type=int, default=3)
+    ap.add_argument("--gpu-eager", type=int, default=1)  # 0 skips the reference-on-GPU (PyTorch eager) baseline
     args = ap.parse_args()
     # stdout carries exactly one JSON line.  NCCL prints its version banner to the process's fd 1 at communicator creation
     # (NCCL_DEBUG_FILE does not redirect it), so fd 1 is pointed at stderr for the whole run and the JSON line is written

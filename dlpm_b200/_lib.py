@@ -25,7 +25,13 @@ SIGNATURES = {
     "dlpm_b200_dlim_step": [c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_i64, c_i64, c_int, c_vp, c_vp],
     "dlpm_b200_lim_step": [c_vp, c_vp, c_vp, c_int, c_vp, c_i64, c_i64, c_int, c_int, c_int, c_f32, c_f32, c_vp, c_u64,
                            c_u64, c_i64, c_vp, c_vp],
+    "dlpm_b200_reverse_step_post": [c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_i64, c_i64, c_int, c_vp, c_u64, c_u64,
+                                    c_i64, c_vp, c_vp, c_vp],
+    "dlpm_b200_dlim_step_post": [c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_i64, c_i64, c_int, c_vp, c_vp, c_vp],
+    "dlpm_b200_lim_step_post": [c_vp, c_vp, c_vp, c_int, c_vp, c_i64, c_i64, c_int, c_int, c_int, c_f32, c_f32, c_vp, c_u64,
+                                c_u64, c_i64, c_vp, c_vp, c_int, c_vp],
     "dlpm_b200_advance_counter": [c_vp, c_int, c_vp],
+    "dlpm_b200_set_counter": [c_vp, c_int, c_vp],
     "dlpm_b200_training_elements": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_i64, c_f32, c_f32, c_u64,
                                     c_u64, c_i64, c_vp],
     "dlpm_b200_scale_by_step": [c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_i64, c_i64, c_vp],
@@ -37,6 +43,21 @@ SIGNATURES = {
     "dlpm_b200_mlp_sample_chain": [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_vp,
                                    c_vp, c_u64, c_u64, c_i64, c_vp],
 }
+
+class Post(ctypes.Structure):
+    """``dlpm_b200_post_t``: post-processing of the final sample fused into the last step (bem/GenerationManager.py:50-63)."""
+    _fields_ = [("out", c_vp), ("clamp", c_f32), ("mode", c_int), ("channels", c_int)]
+
+
+POST_NONE, POST_F32, POST_F32_IMAGE, POST_U8_NHWC = 0, 1, 2, 3
+
+
+def make_post(out, clamp, mode, channels=1):
+    """ctypes pointer to a ``dlpm_b200_post_t`` (or None): ``out`` is a CUDA tensor that receives the processed x_0."""
+    if out is None or mode == POST_NONE:
+        return None
+    return ctypes.byref(Post(ptr(out), float(clamp), int(mode), int(channels)))
+
 
 A_COMPACT, A_ISOTROPIC, A_FULL = 0, 1, 2
 STEP_CLIP_DENOISED, STEP_EPS_BF16, STEP_SIGMA_FULL = 1, 2, 4
@@ -59,6 +80,7 @@ def load():
             "(there is no CPU / PyTorch fallback for the DLPM hot path)" % LIB_PATH)
     lib = ctypes.CDLL(LIB_PATH)
     lib.dlpm_b200_abi_version.restype = c_int
+    lib.dlpm_b200_philox_rounds.restype = c_int
     lib.dlpm_b200_last_error.restype = ctypes.c_char_p
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)

@@ -30,6 +30,9 @@ UNET_SIGNATURES = {
     "dlpm_b200_unet_create": [ctypes.POINTER(c_vp), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), c_vp,
                               c_i64, c_vp, c_i64, c_i64],
     "dlpm_b200_unet_forward": [c_vp, c_vp, c_vp, c_int, c_vp, c_f32, c_vp, c_i64, c_vp],
+    "dlpm_b200_graph_sample": [c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_int, c_f32, c_f32, ctypes.c_uint64,
+                               ctypes.c_uint64, c_i64, c_vp, c_vp],
+    "dlpm_b200_graph_sample_stats": [c_vp, ctypes.POINTER(c_int), ctypes.POINTER(c_int)],
     "dlpm_b200_unet_copy_buffer": [c_vp, c_int, c_vp, c_i64, c_vp],
     "dlpm_b200_unet_profile": [c_vp, c_vp, c_vp, c_int, c_vp, c_i64, ctypes.POINTER(c_f32), ctypes.POINTER(ctypes.c_double), c_vp],
     "dlpm_b200_unet_num_launches": [c_vp],
@@ -106,95 +109,72 @@ class Engine:
             pass
 
 
+LOOP_DLPM, LOOP_DLIM, LOOP_LIM_SDE, LOOP_LIM_ODE = 0, 1, 2, 3
+
+
+def graph_stats(eng):
+    """(instantiations, in-place updates) of the engine's cached executable graph (dlpm_b200_graph_sample_stats)."""
+    a, b = c_int(), c_int()
+    _lib.call("dlpm_b200_graph_sample_stats", eng.handle, ctypes.byref(a), ctypes.byref(b))
+    return a.value, b.value
+
+
 def run_lim_loop(model, x, coef_d, t_table, steps, ode, isotropic, alpha, clamp_eps, hist, seed, offset, sample_base,
-                 use_graph=True):
+                 use_graph=True, post=None):
     """LIM reverse loop (sampler.py:218-258) for the image net: per step UNet forward at the continuous time
-    t_table[step] (device table, device step counter) + fused LIM update; one CUDA graph replayed `steps` times."""
+    t_table[step] (device table, device step counter) + fused LIM update.  Without history the whole loop is ONE call of
+    ``dlpm_b200_graph_sample`` (capture + cached executable graph inside the library); ``post`` = ctypes pointer from
+    ``_lib.make_post`` fuses the GenerationManager post-processing into the last step."""
     dev = x.device
     B, C, H, W = x.shape
     D = C * H * W
     eng = model.engine(H, W, B)
+    ce = -1.0 if clamp_eps is None else float(clamp_eps)
+    if hist is None and use_graph:
+        _lib.call("dlpm_b200_graph_sample", eng.handle, LOOP_LIM_ODE if ode else LOOP_LIM_SDE, _lib.ptr(x), None, _lib.ptr(coef_d),
+                  _lib.ptr(t_table), int(steps), B, 0, 1 if isotropic else 0, float(alpha), ce, seed, offset, sample_base, post,
+                  _lib.stream_ptr())
+        return
     out = torch.empty((B, model.out_channels, H, W), device=dev, dtype=torch.float32)
     step_dev = torch.zeros((1,), device=dev, dtype=torch.int32)
-    stream = torch.cuda.current_stream()
-
-    def one_step(h_ptr):
+    for k in range(steps):
         eng.forward(x, t_table, step_dev, 0.0, out, B)
-        _lib.call("dlpm_b200_lim_step", _lib.ptr(x), _lib.ptr(out), _lib.ptr(coef_d), 0, _lib.ptr(step_dev), B, D, 0, 1 if ode else 0,
-                  1 if isotropic else 0, float(alpha), -1.0 if clamp_eps is None else float(clamp_eps), None, seed, offset,
-                  sample_base, h_ptr, _lib.stream_ptr())
+        _lib.call("dlpm_b200_lim_step_post", _lib.ptr(x), _lib.ptr(out), _lib.ptr(coef_d), 0, _lib.ptr(step_dev), B, D, 0, 1 if ode else 0,
+                  1 if isotropic else 0, float(alpha), ce, None, seed, offset, sample_base,
+                  _lib.ptr(hist[k + 1]) if hist is not None else None, post, steps - 1, _lib.stream_ptr())
         _lib.call("dlpm_b200_advance_counter", _lib.ptr(step_dev), 1, _lib.stream_ptr())
 
-    if hist is not None or not use_graph:
-        for k in range(steps):
-            one_step(_lib.ptr(hist[k + 1]) if hist is not None else None)
-        return
-    x_save = x.clone()
-    one_step(None)  # builds the per-batch plan outside capture
-    x.copy_(x_save)
-    step_dev.zero_()
-    torch.cuda.synchronize()
-    g = torch.cuda.CUDAGraph()
-    side = torch.cuda.Stream()
-    side.wait_stream(stream)
-    with torch.cuda.stream(side):
-        with torch.cuda.graph(g, stream=side):
-            one_step(None)
-    stream.wait_stream(side)
-    for _ in range(steps):
-        g.replay()
-    torch.cuda.synchronize()
-    del g
 
-
-def run_sample_loop(model, x, dlpm, T, mode, flags, hist, seed, z_offset, sample_base, graph_cache=None, progress=False,
-                    use_graph=True, input_scale=None):
+def run_sample_loop(model, x, dlpm, T, mode, flags, hist, seed, z_offset, sample_base, progress=False,
+                    use_graph=True, input_scale=None, post=None):
     """x: (B, C, H, W) fp32, updated in place to x_0.  One step = UNet forward (t from the device counter) + fused
-    update + counter decrement; captured once as a CUDA graph and replayed T-1 times."""
+    update + counter decrement.  Without history the whole loop is ONE call of ``dlpm_b200_graph_sample``: the library
+    captures the step on the current stream, updates its cached executable graph in place and replays it T-1 times
+    (nothing is re-instantiated from the second call on; ``graph_stats``).  With history every step needs its own
+    destination, so the launches are issued directly."""
     dev = x.device
     B, C, H, W = x.shape
     D = C * H * W
     eng = model.engine(H, W, B)
+    if hist is None and use_graph:
+        _lib.call("dlpm_b200_graph_sample", eng.handle, LOOP_DLIM if mode == 1 else LOOP_DLPM, _lib.ptr(x),
+                  _lib.ptr(dlpm.Sigmas) if mode != 1 else None, _lib.ptr(dlpm.sched), _lib.ptr(input_scale), int(T), B, int(flags), 1,
+                  0.0, -1.0, seed, z_offset, sample_base, post, _lib.stream_ptr())
+        return
     eps = torch.empty((B, model.out_channels, H, W), device=dev, dtype=torch.float32)
     t_dev = torch.full((1,), T - 1, device=dev, dtype=torch.int32)
     inv_T = float(torch.tensor(1.0 / T, dtype=torch.float32))
-    stream = torch.cuda.current_stream()
-
     x_in = x if input_scale is None else torch.empty_like(x)  # scale_exploding + input_scaling: net sees x / (1 + barsigma_t)
-
-    def one_step(h_ptr):
+    for k in range(T - 1):
+        h_ptr = _lib.ptr(hist[k + 1]) if hist is not None else None
         if input_scale is not None:
             _lib.call("dlpm_b200_scale_by_step", _lib.ptr(x_in), _lib.ptr(x), _lib.ptr(input_scale), None, 0, _lib.ptr(t_dev), T, B, D,
                       _lib.stream_ptr())
         eng.forward(x_in, None, t_dev, inv_T, eps, B)
         if mode == 1:
-            _lib.call("dlpm_b200_dlim_step", _lib.ptr(x), _lib.ptr(eps), _lib.ptr(dlpm.sched), 0, _lib.ptr(t_dev), T, B, D, flags,
-                      h_ptr, _lib.stream_ptr())
+            _lib.call("dlpm_b200_dlim_step_post", _lib.ptr(x), _lib.ptr(eps), _lib.ptr(dlpm.sched), 0, _lib.ptr(t_dev), T, B, D, flags,
+                      h_ptr, post, _lib.stream_ptr())
         else:
-            _lib.call("dlpm_b200_reverse_step", _lib.ptr(x), _lib.ptr(eps), _lib.ptr(dlpm.Sigmas), _lib.ptr(dlpm.sched), 0,
-                      _lib.ptr(t_dev), T, B, D, flags, None, seed, z_offset, sample_base, h_ptr, _lib.stream_ptr())
+            _lib.call("dlpm_b200_reverse_step_post", _lib.ptr(x), _lib.ptr(eps), _lib.ptr(dlpm.Sigmas), _lib.ptr(dlpm.sched), 0,
+                      _lib.ptr(t_dev), T, B, D, flags, None, seed, z_offset, sample_base, h_ptr, post, _lib.stream_ptr())
         _lib.call("dlpm_b200_advance_counter", _lib.ptr(t_dev), -1, _lib.stream_ptr())
-
-    if hist is not None or not use_graph:
-        # history needs a different destination every step: run the launches directly
-        for k in range(T - 1):
-            one_step(_lib.ptr(hist[k + 1]) if hist is not None else None)
-        return
-    # warm-up step outside capture builds the per-batch plan (TMA descriptors) -- then rewind
-    x_save = x.clone()
-    one_step(None)
-    x.copy_(x_save)
-    t_dev.fill_(T - 1)
-    torch.cuda.synchronize()
-    g = torch.cuda.CUDAGraph()
-    side = torch.cuda.Stream()
-    side.wait_stream(stream)
-    with torch.cuda.stream(side):
-        with torch.cuda.graph(g, stream=side):
-            one_step(None)
-    stream.wait_stream(side)
-    # capture does not execute: state is still (x_{T-1}, t = T-1)
-    for _ in range(T - 1):
-        g.replay()
-    torch.cuda.synchronize()
-    del g

@@ -398,6 +398,36 @@ __device__ __forceinline__ float dlpm_update1_fast(float x, float e, float z, co
   return fmaf(c.sd, z, fmaf(-c.c1, e, x) * inv_g);
 }
 
+// GenerationManager.generate post-processing (bem/GenerationManager.py:50-63) fused into the LAST step's store: when the
+// step being executed is `at`, the new x_0 is also written to `out` clamped to +-clamp, mapped to (x+1)/2 for images, and
+// optionally quantised like torchvision.utils.save_image (x*255 + 0.5, clamp, truncate) into uint8 NHWC -- no extra pass
+// over x_0 and nothing to wait for before the device -> host copy.
+struct StepPost {
+  void* out;   // nullptr = off
+  float clamp;
+  int mode;    // DLPM_POST_F32 (clamp), DLPM_POST_F32_IMAGE (clamp, (x+1)/2), DLPM_POST_U8_NHWC
+  int at;      // step index whose result is final (DLPM / DLIM: 1; LIM: n_steps - 1)
+  int C, HW;   // sample layout (C, H*W) for the NHWC mode; D = C * HW
+};
+__device__ __forceinline__ float post_val(const StepPost& p, float v) {
+  v = fminf(fmaxf(v, -p.clamp), p.clamp);
+  return p.mode == DLPM_POST_F32 ? v : __fdiv_rn(__fadd_rn(v, 1.0f), 2.0f);
+}
+__device__ __forceinline__ void post_store1(const StepPost& p, int64_t b, int64_t i, float v) {
+  v = post_val(p, v);
+  if (p.mode != DLPM_POST_U8_NHWC) { reinterpret_cast<float*>(p.out)[b * ((int64_t)p.C * p.HW) + i] = v; return; }
+  const int c = (int)(i / p.HW), pix = (int)(i - (int64_t)c * p.HW);
+  reinterpret_cast<uint8_t*>(p.out)[(b * p.HW + pix) * p.C + c] = (uint8_t)fminf(fmaxf(fmaf(v, 255.0f, 0.5f), 0.0f), 255.0f);
+}
+__device__ __forceinline__ void post_store4(const StepPost& p, int64_t q, int64_t b, uint32_t pos, const float4& v) {
+  if (p.mode != DLPM_POST_U8_NHWC) {
+    st_stream(reinterpret_cast<float4*>(p.out) + q, make_float4(post_val(p, v.x), post_val(p, v.y), post_val(p, v.z), post_val(p, v.w)));
+    return;
+  }
+  const int64_t i = (int64_t)pos * 4;
+  post_store1(p, b, i, v.x); post_store1(p, b, i + 1, v.y); post_store1(p, b, i + 2, v.z); post_store1(p, b, i + 3, v.w);
+}
+
 template <bool VEC, bool EPS_BF16>
 __device__ __forceinline__ float4 load_eps4(const void* eps, int64_t q) {
   if (EPS_BF16) return bf16x4_to_float4(__ldg(reinterpret_cast<const uint2*>(eps) + q));
@@ -416,11 +446,12 @@ __global__ void __launch_bounds__(256) k_reverse_step(float* __restrict__ x, con
                                                       int t_imm, const int* __restrict__ t_dev, int T, int64_t B,
                                                       int64_t D, int flags, const float* __restrict__ z,
                                                       uint64_t seed, uint64_t offset, int64_t sample_base,
-                                                      float* __restrict__ hist, FastDiv fd) {
+                                                      float* __restrict__ hist, FastDiv fd, const StepPost post) {
   pdl_launch_dependents();
   pdl_wait();
   const int t = t_dev ? *t_dev : t_imm;
   if (t < 1 || t >= T) return;
+  const bool do_post = post.out != nullptr && t == post.at;
   const Philox ph(seed);
   const float4 row = __ldg(reinterpret_cast<const float4*>(sched) + t);
   const float bs_prev = __ldg(sched + 4 * (t - 1) + 3);
@@ -472,6 +503,7 @@ __global__ void __launch_bounds__(256) k_reverse_step(float* __restrict__ x, con
       }
       reinterpret_cast<float4*>(x)[q] = o;
       if (hist) st_stream(reinterpret_cast<float4*>(hist) + q, o);
+      if (do_post) post_store4(post, q, b, pos, o);
     }
   } else {
     const int64_t n = B * D;
@@ -491,6 +523,7 @@ __global__ void __launch_bounds__(256) k_reverse_step(float* __restrict__ x, con
       }
       x[e] = o;
       if (hist) hist[e] = o;
+      if (do_post) post_store1(post, b, i, o);
     }
   }
 }
@@ -504,11 +537,13 @@ __global__ void __launch_bounds__(256, OCC) k_reverse_step_fast(float* __restric
                                                               const float* __restrict__ Sigma, const float* __restrict__ sched,
                                                               int t_imm, const int* __restrict__ t_dev, int T, int64_t B,
                                                               const QuadSpan span, const __grid_constant__ PhiloxKeys keys,
-                                                              uint64_t offset, int64_t sample_base, float* __restrict__ hist) {
+                                                              uint64_t offset, int64_t sample_base, float* __restrict__ hist,
+                                                              const StepPost post) {
   pdl_launch_dependents();
   pdl_wait();
   const int t = t_dev ? *t_dev : t_imm;
   if (t < 1 || t >= T) return;
+  const bool do_post = post.out != nullptr && t == post.at;
   const PhiloxRef ph(keys);
   const float4 row = __ldg(reinterpret_cast<const float4*>(sched) + t);
   const float inv_g = __frcp_rn(row.x);
@@ -551,6 +586,7 @@ __global__ void __launch_bounds__(256, OCC) k_reverse_step_fast(float* __restric
           r.w = fmaf(cf.y, zv.w, fmaf(-cf.x, ev[u].w, xv[u].w) * inv_g);
           reinterpret_cast<float4*>(x)[q] = r;
           if (hist) st_stream(reinterpret_cast<float4*>(hist) + q, r);
+          if (do_post) post_store4(post, q, o, pos, r);
         }
         span_advance(span, o, pos);
       }
@@ -565,8 +601,10 @@ __global__ void __launch_bounds__(256) k_lim_step(float* __restrict__ x, const v
                                                   const int* __restrict__ step_dev, int64_t B, int64_t D, int ode,
                                                   int isotropic, StableParams sp, float clamp_eps,
                                                   const float* __restrict__ e_L, uint64_t seed, uint64_t offset,
-                                                  int64_t sample_base, float* __restrict__ hist, FastDiv fd, int chunk) {
+                                                  int64_t sample_base, float* __restrict__ hist, FastDiv fd, int chunk,
+                                                  const StepPost post) {
   const int step = step_dev ? *step_dev : step_imm;
+  const bool do_post = post.out != nullptr && step == post.at;
   const Philox ph(seed);
   const float4 cf = __ldg(reinterpret_cast<const float4*>(coef) + step);  // (score_scale, a, c_score, c_noise)
   const uint64_t off_s = offset + (uint64_t)step;
@@ -620,6 +658,7 @@ __global__ void __launch_bounds__(256) k_lim_step(float* __restrict__ x, const v
         }
         reinterpret_cast<float4*>(x)[q] = o;
         if (hist) st_stream(reinterpret_cast<float4*>(hist) + q, o);
+        if (do_post) post_store4(post, q, b, pos, o);
       }
     }
   } else {
@@ -644,6 +683,7 @@ __global__ void __launch_bounds__(256) k_lim_step(float* __restrict__ x, const v
       }
       x[e] = o;
       if (hist) hist[e] = o;
+      if (do_post) post_store1(post, b, i, o);
     }
   }
 }
@@ -655,8 +695,10 @@ __global__ void __launch_bounds__(256) k_lim_step_vec(float* __restrict__ x, con
                                                       const int* __restrict__ step_dev, const QuadSpan span, int ode,
                                                       int isotropic, StableParams sp, float clamp_eps,
                                                       const float* __restrict__ e_L, const __grid_constant__ PhiloxKeys keys,
-                                                      uint64_t offset, int64_t sample_base, float* __restrict__ hist) {
+                                                      uint64_t offset, int64_t sample_base, float* __restrict__ hist,
+                                                      const StepPost post) {
   const int step = step_dev ? *step_dev : step_imm;
+  const bool do_post = post.out != nullptr && step == post.at;
   const PhiloxRef ph(keys);
   const float4 cf = __ldg(reinterpret_cast<const float4*>(coef) + step);  // (score_scale, a, c_score, c_noise)
   const uint64_t off_s = offset + (uint64_t)step;
@@ -706,6 +748,7 @@ __global__ void __launch_bounds__(256) k_lim_step_vec(float* __restrict__ x, con
       }
       reinterpret_cast<float4*>(x)[q] = o;
       if (hist) st_stream(reinterpret_cast<float4*>(hist) + q, o);
+      if (do_post) post_store4(post, q, b, pos, o);
       span_advance(span, b, pos);
     }
   }
@@ -952,7 +995,7 @@ int dlpm_b200_sigma_scan(float* Sigma, const float* A_in, float* A_out, const fl
 template <int MODE>
 static int launch_step(float* x, const void* eps, const float* Sigma, const float* sched, int t, const int* t_dev, int T,
                        int64_t B, int64_t D, int flags, const float* z, uint64_t seed, uint64_t offset, int64_t sample_base,
-                       float* hist, void* stream) {
+                       float* hist, const StepPost& post, void* stream) {
   const bool bf16 = flags & DLPM_STEP_EPS_BF16;
   const bool vec = (D % 4 == 0) && aligned16(x) && (reinterpret_cast<uintptr_t>(eps) % (bf16 ? 8 : 16) == 0) &&
                    (!z || aligned16(z)) && (!hist || aligned16(hist)) &&
@@ -966,8 +1009,8 @@ static int launch_step(float* x, const void* eps, const float* Sigma, const floa
 #define LF(U, O)                                                                                                              \
   do {                                                                                                                        \
     const int fgrid = span_grid(span, g_stream_ctas > 0 ? g_stream_ctas : O);                                                 \
-    if (bf16) launch_ex(k_reverse_step_fast<true, U, O>, dim3(fgrid), dim3(256), 0, s, 1, x, eps, Sigma, sched, t, t_dev, T, B, span, keys, offset, sample_base, hist); \
-    else launch_ex(k_reverse_step_fast<false, U, O>, dim3(fgrid), dim3(256), 0, s, 1, x, eps, Sigma, sched, t, t_dev, T, B, span, keys, offset, sample_base, hist);     \
+    if (bf16) launch_ex(k_reverse_step_fast<true, U, O>, dim3(fgrid), dim3(256), 0, s, 1, x, eps, Sigma, sched, t, t_dev, T, B, span, keys, offset, sample_base, hist, post); \
+    else launch_ex(k_reverse_step_fast<false, U, O>, dim3(fgrid), dim3(256), 0, s, 1, x, eps, Sigma, sched, t, t_dev, T, B, span, keys, offset, sample_base, hist, post);     \
   } while (0)
     switch (g_k3_variant) {  // measured within 4 % of each other at B = 4096 (tools/bench_stream.py); (2, 6) is the default
       case 1: LF(4, 4); break;
@@ -979,7 +1022,7 @@ static int launch_step(float* x, const void* eps, const float* Sigma, const floa
     DLPM_CHECK_LAUNCH("reverse_step");
     return DLPM_OK;
   }
-#define L(V, H) launch_ex(k_reverse_step<V, H, MODE>, dim3(grid), dim3(256), 0, s, 1, x, eps, Sigma, sched, t, t_dev, T, B, D, flags, z, seed, offset, sample_base, hist, fd)
+#define L(V, H) launch_ex(k_reverse_step<V, H, MODE>, dim3(grid), dim3(256), 0, s, 1, x, eps, Sigma, sched, t, t_dev, T, B, D, flags, z, seed, offset, sample_base, hist, fd, post)
   if (vec) { if (bf16) L(true, true); else L(true, false); }
   else { if (bf16) L(false, true); else L(false, false); }
 #undef L
@@ -987,33 +1030,72 @@ static int launch_step(float* x, const void* eps, const float* Sigma, const floa
   return DLPM_OK;
 }
 
-int dlpm_b200_reverse_step(float* x, const void* eps, const float* Sigma, const float* sched, int t, const int* t_dev,
-                           int T, int64_t B, int64_t D, int flags, const float* z, uint64_t seed, uint64_t offset,
-                           int64_t sample_base, float* hist_out, void* stream) {
+// host form of dlpm_b200_post_t -> StepPost (validated)
+static int make_post(const dlpm_b200_post_t* post, int at, int64_t D, StepPost* out) {
+  StepPost p;
+  p.out = nullptr; p.clamp = 0.f; p.mode = 0; p.at = at; p.C = 1; p.HW = (int)D;
+  if (post && post->out && post->mode != DLPM_POST_NONE) {
+    DLPM_REQUIRE(post->mode == DLPM_POST_F32 || post->mode == DLPM_POST_F32_IMAGE || post->mode == DLPM_POST_U8_NHWC,
+                 "post: unknown mode");
+    DLPM_REQUIRE(post->clamp > 0.f, "post: clamp must be positive");
+    p.out = post->out; p.clamp = post->clamp; p.mode = post->mode;
+    if (post->mode == DLPM_POST_U8_NHWC) {
+      DLPM_REQUIRE(post->channels >= 1 && D % post->channels == 0 && D < (1ll << 31), "post: channels must divide D");
+      p.C = post->channels; p.HW = (int)(D / post->channels);
+    } else {
+      DLPM_REQUIRE((reinterpret_cast<uintptr_t>(post->out) & 15u) == 0, "post: fp32 output must be 16-byte aligned");
+    }
+  }
+  *out = p;
+  return DLPM_OK;
+}
+
+int dlpm_b200_reverse_step_post(float* x, const void* eps, const float* Sigma, const float* sched, int t, const int* t_dev,
+                                int T, int64_t B, int64_t D, int flags, const float* z, uint64_t seed, uint64_t offset,
+                                int64_t sample_base, float* hist_out, const dlpm_b200_post_t* post, void* stream) {
   DLPM_REQUIRE(x && eps && Sigma && sched, "reverse_step: NULL tensor");
   DLPM_REQUIRE(T >= 2 && B >= 0 && D >= 1, "reverse_step: bad sizes");
   DLPM_REQUIRE(t_dev || (t >= 1 && t < T), "reverse_step: t out of range [1, T)");
   if (B == 0) return DLPM_OK;
-  return launch_step<0>(x, eps, Sigma, sched, t, t_dev, T, B, D, flags, z, seed, offset, sample_base, hist_out, stream);
+  StepPost sp;
+  if (int rc = make_post(post, 1, D, &sp)) return rc;
+  return launch_step<0>(x, eps, Sigma, sched, t, t_dev, T, B, D, flags, z, seed, offset, sample_base, hist_out, sp, stream);
 }
 
-int dlpm_b200_dlim_step(float* x, const void* eps, const float* sched, int t, const int* t_dev, int T, int64_t B,
-                        int64_t D, int flags, float* hist_out, void* stream) {
+int dlpm_b200_reverse_step(float* x, const void* eps, const float* Sigma, const float* sched, int t, const int* t_dev,
+                           int T, int64_t B, int64_t D, int flags, const float* z, uint64_t seed, uint64_t offset,
+                           int64_t sample_base, float* hist_out, void* stream) {
+  return dlpm_b200_reverse_step_post(x, eps, Sigma, sched, t, t_dev, T, B, D, flags, z, seed, offset, sample_base, hist_out,
+                                     nullptr, stream);
+}
+
+int dlpm_b200_dlim_step_post(float* x, const void* eps, const float* sched, int t, const int* t_dev, int T, int64_t B,
+                             int64_t D, int flags, float* hist_out, const dlpm_b200_post_t* post, void* stream) {
   DLPM_REQUIRE(x && eps && sched, "dlim_step: NULL tensor");
   DLPM_REQUIRE(T >= 2 && B >= 0 && D >= 1, "dlim_step: bad sizes");
   DLPM_REQUIRE(t_dev || (t >= 1 && t < T), "dlim_step: t out of range [1, T)");
   if (B == 0) return DLPM_OK;
+  StepPost sp;
+  if (int rc = make_post(post, 1, D, &sp)) return rc;
   return launch_step<1>(x, eps, sched /*unused Sigma*/, sched, t, t_dev, T, B, D, flags & ~DLPM_STEP_SIGMA_FULL, nullptr, 0, 0, 0,
-                        hist_out, stream);
+                        hist_out, sp, stream);
 }
 
-int dlpm_b200_lim_step(float* x, const void* model_out, const float* coef, int step, const int* step_dev, int64_t B,
-                       int64_t D, int flags, int ode, int isotropic, float alpha, float clamp_eps, const float* e_L,
-                       uint64_t seed, uint64_t offset, int64_t sample_base, float* hist_out, void* stream) {
+int dlpm_b200_dlim_step(float* x, const void* eps, const float* sched, int t, const int* t_dev, int T, int64_t B,
+                        int64_t D, int flags, float* hist_out, void* stream) {
+  return dlpm_b200_dlim_step_post(x, eps, sched, t, t_dev, T, B, D, flags, hist_out, nullptr, stream);
+}
+
+int dlpm_b200_lim_step_post(float* x, const void* model_out, const float* coef, int step, const int* step_dev, int64_t B,
+                            int64_t D, int flags, int ode, int isotropic, float alpha, float clamp_eps, const float* e_L,
+                            uint64_t seed, uint64_t offset, int64_t sample_base, float* hist_out, const dlpm_b200_post_t* post,
+                            int last_step, void* stream) {
   DLPM_REQUIRE(x && model_out && coef, "lim_step: NULL tensor");
   DLPM_REQUIRE(B >= 0 && D >= 1 && (step_dev || step >= 0), "lim_step: bad sizes");
   DLPM_REQUIRE(alpha > 0.f && alpha < 2.f, "lim_step: heavy-tailed branch only (0 < alpha < 2)");
   if (B == 0) return DLPM_OK;
+  StepPost pp;
+  if (int rc = make_post(post, last_step, D, &pp)) return rc;
   const StableParams sp = make_params(alpha);
   const bool bf16 = flags & DLPM_STEP_EPS_BF16;
   const bool vec = (D % 4 == 0) && aligned16(x) && (reinterpret_cast<uintptr_t>(model_out) % (bf16 ? 8 : 16) == 0) &&
@@ -1022,19 +1104,36 @@ int dlpm_b200_lim_step(float* x, const void* model_out, const float* coef, int s
   if (vec) chunk_grid(B * D / 4, &chunk, &grid);
   cudaStream_t s = (cudaStream_t)stream;
   const FastDiv fd((uint32_t)(vec ? D / 4 : 1));
-#define L(V, H) k_lim_step<V, H><<<grid, 256, 0, s>>>(x, model_out, coef, step, step_dev, B, D, ode, isotropic, sp, clamp_eps, e_L, seed, offset, sample_base, hist_out, fd, chunk)
+#define L(V, H) k_lim_step<V, H><<<grid, 256, 0, s>>>(x, model_out, coef, step, step_dev, B, D, ode, isotropic, sp, clamp_eps, e_L, seed, offset, sample_base, hist_out, fd, chunk, pp)
   if (vec && span_ok(B, D)) {
     const QuadSpan span = make_span(B, D);
     const PhiloxKeys keys = make_philox_keys(seed);
     const int g = span_grid(span, 6);
-    if (bf16) k_lim_step_vec<true><<<g, 256, 0, s>>>(x, model_out, coef, step, step_dev, span, ode, isotropic, sp, clamp_eps, e_L, keys, offset, sample_base, hist_out);
-    else k_lim_step_vec<false><<<g, 256, 0, s>>>(x, model_out, coef, step, step_dev, span, ode, isotropic, sp, clamp_eps, e_L, keys, offset, sample_base, hist_out);
+    if (bf16) k_lim_step_vec<true><<<g, 256, 0, s>>>(x, model_out, coef, step, step_dev, span, ode, isotropic, sp, clamp_eps, e_L, keys, offset, sample_base, hist_out, pp);
+    else k_lim_step_vec<false><<<g, 256, 0, s>>>(x, model_out, coef, step, step_dev, span, ode, isotropic, sp, clamp_eps, e_L, keys, offset, sample_base, hist_out, pp);
   } else if (vec) { if (bf16) L(true, true); else L(true, false); }
   else { if (bf16) L(false, true); else L(false, false); }
 #undef L
   DLPM_CHECK_LAUNCH("lim_step");
   return DLPM_OK;
 }
+
+int dlpm_b200_lim_step(float* x, const void* model_out, const float* coef, int step, const int* step_dev, int64_t B,
+                       int64_t D, int flags, int ode, int isotropic, float alpha, float clamp_eps, const float* e_L,
+                       uint64_t seed, uint64_t offset, int64_t sample_base, float* hist_out, void* stream) {
+  return dlpm_b200_lim_step_post(x, model_out, coef, step, step_dev, B, D, flags, ode, isotropic, alpha, clamp_eps, e_L, seed, offset,
+                                 sample_base, hist_out, nullptr, 0, stream);
+}
+
+__global__ void k_set_counter(int* t, int value) { *t = value; }
+int dlpm_b200_set_counter(int* t_dev, int value, void* stream) {
+  DLPM_REQUIRE(t_dev, "set_counter: NULL");
+  k_set_counter<<<1, 1, 0, (cudaStream_t)stream>>>(t_dev, value);
+  DLPM_CHECK_LAUNCH("set_counter");
+  return DLPM_OK;
+}
+
+int dlpm_b200_philox_rounds(void) { return DLPM_PHILOX_ROUNDS; }
 
 int dlpm_b200_advance_counter(int* t_dev, int delta, void* stream) {
   DLPM_REQUIRE(t_dev, "advance_counter: NULL");

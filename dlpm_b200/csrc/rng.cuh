@@ -3,7 +3,7 @@
 // Replaces the reference's host-side scipy draw + H2D copy
 // (bem/datasets/Distributions.py:45-51: scipy.stats.levy_stable.rvs -> Chambers-Mallows-Stuck)
 // and torch.randn (Distributions.py:65, GenerativeLevyProcess.py:236) with a stateless
-// Philox4x32-10 generator: every variate is a pure function of
+// Philox4x32-R generator (R = DLPM_PHILOX_ROUNDS): every variate is a pure function of
 //   (seed, stream tag, call offset, GLOBAL sample index, position inside the sample)
 // so results do not depend on grid shape or on how the batch is sharded over GPUs.
 #pragma once
@@ -18,8 +18,12 @@ enum : uint32_t { STREAM_A = 0x0Au, STREAM_G = 0x06u, STREAM_Z = 0x5Au, STREAM_E
 // __grid_constant__ parameter, so every round's key is a constant-bank operand of the LOP3 (no per-iteration
 // UIADD3 key schedule); the other kernels build them in registers from the seed.  Both give the same stream.
 #ifndef DLPM_PHILOX_ROUNDS
-#define DLPM_PHILOX_ROUNDS 10  // Random123 / cuRAND default.  7 rounds still pass BigCrush (Salmon et al. 2011, Table 2) and make the
-                               // normal fill HBM-bound (profiles/r01_ncu_stream.md); kept at 10 for the safety margin.
+#define DLPM_PHILOX_ROUNDS 7  // Philox4x32-7: the fewest rounds that pass BigCrush (Salmon et al. 2011, Table 2: "Crush-resistant").
+                              // Random123 / cuRAND default to 10 for margin; nothing in the reference pins a generator (it draws from
+                              // numpy MT19937 + ATen Philox), and the fills are bound by the quarter-rate IMAD.WIDE of the rounds
+                              // (profiles/r01_ncu_stream.md: 10 rounds 0.54 of the HBM copy peak, 7 rounds 0.77), so the default is 7.
+                              // -DDLPM_PHILOX_ROUNDS=10 (DLPM_B200_NVCC_EXTRA) rebuilds with the cuRAND count; oracle/philox.py
+                              // asks the library (dlpm_b200_philox_rounds) and carries the Random123 known answers for both.
 #endif
 struct PhiloxKeys {
   uint32_t a[10], b[10];
@@ -36,7 +40,7 @@ __host__ __device__ __forceinline__ PhiloxKeys make_philox_keys(uint64_t seed) {
   return k;
 }
 
-// DLPM_PHILOX_ROUNDS (10) rounds, Salmon et al. 2011 constants.  One round = 2 IMAD.WIDE + 2 three-input XORs.
+// DLPM_PHILOX_ROUNDS rounds, Salmon et al. 2011 constants.  One round = 2 IMAD.WIDE + 2 three-input XORs.
 __device__ __forceinline__ uint4 philox_rounds(const PhiloxKeys& k, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
 #pragma unroll
   for (int r = 0; r < DLPM_PHILOX_ROUNDS; ++r) {

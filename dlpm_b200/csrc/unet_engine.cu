@@ -47,6 +47,16 @@ struct UNetEngine {
   float* semb = nullptr;  // [max_batch][4*mc]
   int64_t workspace_bytes = 0;
   std::map<int64_t, Plan> plans;
+  // captured sampling loop (dlpm_b200_graph_sample): engine-owned step counter / network output / scaled-input scratch
+  // and ONE executable graph that is re-parameterised in place (cudaGraphExecUpdate) on every call
+  int* loop_counter = nullptr;
+  float* loop_eps = nullptr;
+  float* loop_xin = nullptr;
+  cudaGraphExec_t loop_exec = nullptr;
+  cudaStream_t loop_stream = nullptr;  // stands in for the legacy default stream, which cannot be captured
+  cudaEvent_t loop_ev = nullptr;
+  std::map<int64_t, bool> warmed;  // batch sizes whose kernels have run once outside capture
+  int loop_instantiations = 0, loop_updates = 0;
   int n_launches = 0;
   std::vector<cudaEvent_t> prof;  // when non-empty: one event recorded before the first op and after every op
 
@@ -328,6 +338,133 @@ int dlpm_b200_unet_profile(void* handle, const float* x, const float* t, int t_r
   return DLPM_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// The whole reverse loop behind one call (SURVEY.md section 8b `dlpm_b200_graph_sample`): p_sample_loop_progressive /
+// ddim_sample_loop_progressive (GenerativeLevyProcess.py:291-330, :413-452) and LIM_sampler (LIM/functions/sampler.py:218-258)
+// for the image net.  One step = [x * 1/(1+barsigma_t)] -> UNet forward (time read through the device counter) -> fused
+// update (K3 / K3' / K3'') -> counter +-1.  The step is captured ONCE per call into a CUDA graph with
+// cudaStreamBeginCapture on the caller's stream; the engine keeps one executable graph and re-parameterises it in place
+// with cudaGraphExecUpdate (same topology, new pointers / seed / offsets: microseconds), instantiating only when the
+// topology changes (other batch size or mode).  Everything is asynchronous on `stream`.
+// ------------------------------------------------------------------------------------------------
+static int loop_alloc(UNetEngine* E) {
+  const int64_t* h = E->header;
+  cudaError_t e;
+  if (!E->loop_counter) {
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&E->loop_counter), 16)) != cudaSuccess) return cuda_fail(e, "graph_sample: counter");
+  }
+  if (!E->loop_eps) {
+    const int64_t bytes = E->max_batch * h[3] * h[4] * h[5] * 4;
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&E->loop_eps), (size_t)bytes)) != cudaSuccess) return cuda_fail(e, "graph_sample: eps buffer");
+    E->workspace_bytes += bytes;
+  }
+  return DLPM_OK;
+}
+
+int dlpm_b200_graph_sample(void* handle, int mode, float* x, const float* Sigma, const float* sched, const float* aux, int T,
+                           int64_t B, int flags, int isotropic, float alpha, float clamp_eps, uint64_t seed, uint64_t offset,
+                           int64_t sample_base, const dlpm_b200_post_t* post, void* stream) {
+  DLPM_REQUIRE(handle && x && sched, "graph_sample: NULL argument");
+  DLPM_REQUIRE(mode >= DLPM_LOOP_DLPM && mode <= DLPM_LOOP_LIM_ODE, "graph_sample: unknown mode");
+  UNetEngine* E = reinterpret_cast<UNetEngine*>(handle);
+  DLPM_REQUIRE(B >= 1 && B <= E->max_batch, "graph_sample: batch exceeds the engine's max_batch");
+  const bool lim = mode == DLPM_LOOP_LIM_SDE || mode == DLPM_LOOP_LIM_ODE;
+  DLPM_REQUIRE(lim ? T >= 1 : T >= 2, "graph_sample: too few steps");
+  DLPM_REQUIRE(mode != DLPM_LOOP_DLPM || Sigma, "graph_sample: the stochastic DLPM loop needs the Sigma table");
+  DLPM_REQUIRE(!lim || aux, "graph_sample: the LIM loops need the table of continuous times");
+  DLPM_REQUIRE(E->header[2] == E->header[3], "graph_sample: the score net must map x to a tensor of the same shape");
+  const int64_t* h = E->header;
+  const int64_t D = h[2] * h[4] * h[5];
+  cudaStream_t caller = (cudaStream_t)stream, s = caller;
+  cudaError_t e;
+  if (int rc = loop_alloc(E)) return rc;
+  const bool legacy = caller == nullptr || caller == cudaStreamLegacy;
+  if (legacy) {  // run the loop on an engine-owned stream, fenced against the default stream on both sides
+    if (!E->loop_stream) {
+      if ((e = cudaStreamCreateWithFlags(&E->loop_stream, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "graph_sample: stream");
+      if ((e = cudaEventCreateWithFlags(&E->loop_ev, cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "graph_sample: event");
+    }
+    s = E->loop_stream;
+    stream = (void*)s;
+    if ((e = cudaEventRecord(E->loop_ev, caller)) != cudaSuccess || (e = cudaStreamWaitEvent(s, E->loop_ev, 0)) != cudaSuccess)
+      return cuda_fail(e, "graph_sample: stream fence");
+  }
+  const bool scaled = !lim && aux != nullptr;  // scale_exploding + input_scaling: the net sees x / (1 + barsigma_t)
+  if (scaled && !E->loop_xin) {
+    const int64_t bytes = E->max_batch * D * 4;
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&E->loop_xin), (size_t)bytes)) != cudaSuccess) return cuda_fail(e, "graph_sample: scaled input");
+    E->workspace_bytes += bytes;
+  }
+  const int n_steps = lim ? T : T - 1;
+  const int first = lim ? 0 : T - 1, delta = lim ? 1 : -1;
+  const float inv_T = lim ? 0.f : (float)(1.0 / (double)T);
+  if (int rc = dlpm_b200_set_counter(E->loop_counter, first, stream)) return rc;
+  // first use of this batch size: one forward outside capture builds the plan (cudaMalloc, tensor maps) and lets every
+  // kernel set its shared-memory attribute; it only writes the engine's own eps buffer
+  if (!E->warmed[B]) {
+    if (int rc = dlpm_b200_unet_forward(handle, x, lim ? aux : nullptr, 0, E->loop_counter, inv_T, E->loop_eps, B, stream)) return rc;
+    E->warmed[B] = true;
+  }
+  auto one_step = [&]() -> int {
+    const float* xin = x;
+    if (scaled) {
+      if (int rc = dlpm_b200_scale_by_step(E->loop_xin, x, aux, nullptr, 0, E->loop_counter, T, B, D, stream)) return rc;
+      xin = E->loop_xin;
+    }
+    if (int rc = dlpm_b200_unet_forward(handle, xin, lim ? aux : nullptr, 0, E->loop_counter, inv_T, E->loop_eps, B, stream)) return rc;
+    int rc;
+    if (mode == DLPM_LOOP_DLPM)
+      rc = dlpm_b200_reverse_step_post(x, E->loop_eps, Sigma, sched, 0, E->loop_counter, T, B, D, flags, nullptr, seed, offset,
+                                       sample_base, nullptr, post, stream);
+    else if (mode == DLPM_LOOP_DLIM)
+      rc = dlpm_b200_dlim_step_post(x, E->loop_eps, sched, 0, E->loop_counter, T, B, D, flags, nullptr, post, stream);
+    else
+      rc = dlpm_b200_lim_step_post(x, E->loop_eps, sched, 0, E->loop_counter, B, D, 0, mode == DLPM_LOOP_LIM_ODE ? 1 : 0, isotropic,
+                                   alpha, clamp_eps, nullptr, seed, offset, sample_base, nullptr, post, n_steps - 1, stream);
+    if (rc) return rc;
+    return dlpm_b200_advance_counter(E->loop_counter, delta, stream);
+  };
+  if ((e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal)) != cudaSuccess) return cuda_fail(e, "graph_sample: begin capture");
+  const int rc_step = one_step();
+  cudaGraph_t graph = nullptr;
+  e = cudaStreamEndCapture(s, &graph);
+  if (rc_step) { if (graph) cudaGraphDestroy(graph); return rc_step; }
+  if (e != cudaSuccess || !graph) return cuda_fail(e, "graph_sample: end capture");
+  bool have = false;
+  if (E->loop_exec) {
+    cudaGraphExecUpdateResultInfo info;
+    if (cudaGraphExecUpdate(E->loop_exec, graph, &info) == cudaSuccess) {
+      have = true;
+      ++E->loop_updates;
+    } else {
+      cudaGetLastError();  // topology changed: clear the sticky-free error and re-instantiate
+      cudaGraphExecDestroy(E->loop_exec);
+      E->loop_exec = nullptr;
+    }
+  }
+  if (!have) {
+    e = cudaGraphInstantiate(&E->loop_exec, graph, 0);
+    if (e != cudaSuccess) { cudaGraphDestroy(graph); E->loop_exec = nullptr; return cuda_fail(e, "graph_sample: instantiate"); }
+    ++E->loop_instantiations;
+  }
+  cudaGraphDestroy(graph);
+  for (int k = 0; k < n_steps; ++k)
+    if ((e = cudaGraphLaunch(E->loop_exec, s)) != cudaSuccess) return cuda_fail(e, "graph_sample: launch");
+  if (legacy) {
+    if ((e = cudaEventRecord(E->loop_ev, s)) != cudaSuccess || (e = cudaStreamWaitEvent(caller, E->loop_ev, 0)) != cudaSuccess)
+      return cuda_fail(e, "graph_sample: stream fence");
+  }
+  return DLPM_OK;
+}
+
+int dlpm_b200_graph_sample_stats(void* handle, int* instantiations, int* updates) {
+  DLPM_REQUIRE(handle, "graph_sample_stats: NULL handle");
+  UNetEngine* E = reinterpret_cast<UNetEngine*>(handle);
+  if (instantiations) *instantiations = E->loop_instantiations;
+  if (updates) *updates = E->loop_updates;
+  return DLPM_OK;
+}
+
 int64_t dlpm_b200_unet_workspace_bytes(void* handle) { return handle ? reinterpret_cast<UNetEngine*>(handle)->workspace_bytes : 0; }
 int dlpm_b200_unet_num_launches(void* handle) { return handle ? reinterpret_cast<UNetEngine*>(handle)->n_launches : 0; }
 
@@ -335,6 +472,10 @@ int dlpm_b200_unet_destroy(void* handle) {
   if (!handle) return DLPM_OK;
   UNetEngine* E = reinterpret_cast<UNetEngine*>(handle);
   cudaFree(E->wb); cudaFree(E->wf); cudaFree(E->slab); cudaFree(E->ss); cudaFree(E->semb);
+  cudaFree(E->loop_counter); cudaFree(E->loop_eps); cudaFree(E->loop_xin);
+  if (E->loop_exec) cudaGraphExecDestroy(E->loop_exec);
+  if (E->loop_ev) cudaEventDestroy(E->loop_ev);
+  if (E->loop_stream) cudaStreamDestroy(E->loop_stream);
   for (auto& kv : E->plans)
     for (float* st : kv.second.stats_bufs) cudaFree(st);
   delete E;

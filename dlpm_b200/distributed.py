@@ -60,11 +60,22 @@ def sample_sharded(method, models, shape, group=None, **sample_kwargs):
     state = rng.default_state()
     old = state.sample_base
     state.sample_base = start
-    try:
-        local = method.sample(models, [count] + [int(s) for s in shape[1:]], **sample_kwargs)
-    finally:
-        state.sample_base = old
     hist = None
+    if count == 0:
+        # more ranks than samples: this rank owns nothing (the kernels reject empty batches) but still takes part in the
+        # gather with an empty slice of the right trailing shape / dtype / device
+        dev = getattr(method, "device", "cpu")
+        local = torch.empty([0] + [int(s) for s in shape[1:]], dtype=torch.float32, device=dev)
+        if sample_kwargs.get("get_sample_history", False):
+            steps = int(sample_kwargs.get("reverse_steps", getattr(method, "reverse_steps", 1)))
+            n_hist = steps + 1 if getattr(method, "LIM", False) else steps
+            hist = torch.empty([n_hist, 0] + [int(s) for s in shape[1:]], dtype=torch.float32, device=dev)
+    else:
+        try:
+            local = method.sample(models, [count] + [int(s) for s in shape[1:]], **sample_kwargs)
+        finally:
+            state.sample_base = old
+    state.sample_base = old
     if isinstance(local, tuple):
         local, hist = local
     out = gather_samples(local, total, group)

@@ -38,12 +38,43 @@ def compute_loss_terms(x, y, lploss):
     return out
 
 
+def _torch_loss_terms(x, y, lploss):
+    """GenerativeLevyProcess.py:19-31 in torch ops (differentiable): used when the model output carries an autograd graph."""
+    dims = list(range(1, x.dim()))
+    if lploss == 2.0:
+        return torch.sqrt(torch.nn.functional.mse_loss(x, y, reduction="none").mean(dim=dims))
+    if lploss == 1.0:
+        return torch.nn.functional.smooth_l1_loss(x, y, beta=1, reduction="none").mean(dim=dims)
+    if lploss == -1:
+        return torch.nn.functional.mse_loss(x, y, reduction="none").mean(dim=dims)
+    raise NotImplementedError("lploss must be 2., 1. or -1 (generic p-norm is not on the hot path)")
+
+
+def _wants_grad(model):
+    """True when the caller is TRAINING this module: grad mode on, module in train() mode, trainable parameters
+    (bem/TrainingManager.py:111-120 calls ``loss.backward()`` right after ``training_losses``)."""
+    return (torch.is_grad_enabled() and isinstance(model, torch.nn.Module) and model.training
+            and any(p.requires_grad for p in model.parameters()))
+
+
 class _Net:
     """Adapter around ``models['default']``: picks the native engine for this package's score nets (or
-    reference modules that can be ingested), otherwise calls the user's module on the device."""
+    reference modules that can be ingested), otherwise calls the user's module on the device.
 
-    def __init__(self, model, device):
+    ``train=True`` (training_losses under autograd): a torch module -- the reference's ``UNetModel`` / ``MLPModel``
+    included -- is called as is so that the loss keeps its graph; this package's own mirrors are parameter containers
+    without a torch forward and there are no backward kernels in this tier, so they raise."""
+
+    def __init__(self, model, device, train=False):
         from .. import score_nets
+        if train:
+            if getattr(model, "native_kind", None) is not None:
+                raise NotImplementedError(
+                    "dlpm_b200's %s runs forward-only CUDA kernels (no backward in this tier, dropout ignored): call "
+                    "training_losses under torch.no_grad() / model.eval() for the loss value, or train a torch module "
+                    "(e.g. the reference's own model class) -- its weights are ingested for sampling" % type(model).__name__)
+            self.model, self.kind = model, "module"
+            return
         self.model = score_nets.as_native(model, device)
         self.kind = getattr(self.model, "native_kind", "module")
 
@@ -74,7 +105,6 @@ class GenerativeLevyProcess:
             self.levy = None  # the reference instantiates torchlevy.LevyStable here but never calls it
         self.dlpm = DLPM(alpha, device, diffusion_steps=reverse_steps, time_spacing=time_spacing, isotropic=isotropic,
                          scale=scale)
-        self.graph_cache = {}
 
     def _scale_timesteps(self, t):
         if self.rescale_timesteps:
@@ -209,7 +239,7 @@ class GenerativeLevyProcess:
         return self._progressive(model, shape, noise, clip_denoised, model_kwargs, True, state)
 
     def _reverse_loop(self, model, shape, noise, clip_denoised, deterministic, get_sample_history, model_kwargs=None,
-                      progress=False, injected_A=None, injected_z=None, state=None):
+                      progress=False, injected_A=None, injected_z=None, state=None, postprocess=None):
         """p_sample_loop_progressive / ddim_sample_loop_progressive (:291-330, :413-452) on the fused kernels."""
         dev = _lib.require_cuda(self.device)
         assert isinstance(shape, (tuple, list))
@@ -227,6 +257,11 @@ class GenerativeLevyProcess:
         with torch.inference_mode(), torch.cuda.device(dev):
             # (a)+(b) A_{0:T-1} and the Sigma recursion (dlpm.py:226-239), one scan kernel
             if injected_A is not None:
+                want = (T, B) if d.isotropic else (T, *shape)
+                if tuple(injected_A.shape) == (T, *shape) and d.isotropic:
+                    # the reference's full-shape layout (dlpm.py:227): isotropic A is constant per sample -> compact (T, B)
+                    injected_A = injected_A.reshape(T, B, -1)[:, :, 0]
+                assert tuple(injected_A.shape) == want, "injected_A must have shape %s (got %s)" % (want, tuple(injected_A.shape))
                 d.A = injected_A.to(dev, torch.float32).contiguous()
                 d._shape = shape
                 d._sigma_src = None
@@ -247,6 +282,7 @@ class GenerativeLevyProcess:
             z_offset = st.reserve(T)
             mode = 1 if deterministic else 0
             in_scale = self._input_scale_table()
+            post = None if postprocess is None else postprocess.bind(shape, dev)  # fused into the LAST step's store
             # (d) the hot loop
             if net.kind == "mlp" and not model_kwargs and d.isotropic and self.rescale_timesteps and in_scale is None:
                 m = net.model
@@ -254,9 +290,11 @@ class GenerativeLevyProcess:
                           _lib.ptr(d.sched), T, B, m.nfeatures, m.nunits, m.time_emb_size, m.nblocks_total, mode,
                           flags & _lib.STEP_CLIP_DENOISED, _lib.ptr(z), _lib.ptr(hist), st.seed, z_offset,
                           st.sample_base, _lib.stream_ptr())
+                if postprocess is not None:  # the persistent 2-D chain kernel keeps x in registers: one tiny extra launch
+                    postprocess.run_standalone(x)
             elif net.kind == "unet" and not model_kwargs and z is None and self.rescale_timesteps:
                 net.model.sample_loop(x, d, T, mode, flags, hist, st.seed, z_offset, st.sample_base,
-                                      graph_cache=self.graph_cache, progress=progress, input_scale=in_scale)
+                                      progress=progress, input_scale=in_scale, post=post)
             else:
                 bar = None
                 if progress:
@@ -270,12 +308,12 @@ class GenerativeLevyProcess:
                     eps = eps.contiguous() if eps.dtype == torch.bfloat16 else eps.to(torch.float32).contiguous()
                     h = _lib.ptr(hist[k + 1]) if hist is not None else None
                     if deterministic:
-                        _lib.call("dlpm_b200_dlim_step", _lib.ptr(x), _lib.ptr(eps), _lib.ptr(d.sched), t, None, T, B, D,
-                                  fl, h, _lib.stream_ptr())
+                        _lib.call("dlpm_b200_dlim_step_post", _lib.ptr(x), _lib.ptr(eps), _lib.ptr(d.sched), t, None, T, B, D,
+                                  fl, h, post, _lib.stream_ptr())
                     else:
-                        _lib.call("dlpm_b200_reverse_step", _lib.ptr(x), _lib.ptr(eps), _lib.ptr(d.Sigmas),
+                        _lib.call("dlpm_b200_reverse_step_post", _lib.ptr(x), _lib.ptr(eps), _lib.ptr(d.Sigmas),
                                   _lib.ptr(d.sched), t, None, T, B, D, fl, _lib.ptr(z[k]) if z is not None else None,
-                                  st.seed, z_offset, st.sample_base, h, _lib.stream_ptr())
+                                  st.seed, z_offset, st.sample_base, h, post, _lib.stream_ptr())
                     if bar is not None:
                         bar.update(1)
                 if bar is not None:
@@ -286,23 +324,24 @@ class GenerativeLevyProcess:
         return x
 
     def p_sample_loop(self, model, shape, noise=None, clip_denoised=False, denoised_fn=None, model_kwargs=None,
-                      progress=False, get_sample_history=False, injected_A=None, injected_z=None, state=None):
-        """:241-289 (+ ``injected_A`` (T,B) / ``injected_z`` (T-1,*shape) for parity tests)."""
+                      progress=False, get_sample_history=False, injected_A=None, injected_z=None, state=None,
+                      postprocess=None):
+        """:241-289 (+ ``injected_A`` (T,B) / ``injected_z`` (T-1,*shape) for parity tests; ``postprocess``: see ``sample``)."""
         assert denoised_fn is None, "denoised_fn is not supported"
         return self._reverse_loop(model, shape, noise, clip_denoised, False, get_sample_history, model_kwargs, progress,
-                                  injected_A, injected_z, state)
+                                  injected_A, injected_z, state, postprocess)
 
     def ddim_sample_loop(self, model, shape, noise=None, clip_denoised=False, denoised_fn=None, model_kwargs=None,
-                         progress=False, eta=0.0, get_sample_history=False, injected_A=None, state=None):
+                         progress=False, eta=0.0, get_sample_history=False, injected_A=None, state=None, postprocess=None):
         """:375-411.  eta must be 0."""
         assert denoised_fn is None, "denoised_fn is not supported"
         if eta != 0.0:
             raise NotImplementedError("dlim_eta != 0 is broken in the reference (dlpm.py:289-297); use dlim_eta=0.0")
         return self._reverse_loop(model, shape, noise, clip_denoised, True, get_sample_history, model_kwargs, progress,
-                                  injected_A, None, state)
+                                  injected_A, None, state, postprocess)
 
     def lim_sample(self, model, shape, ddim=False, get_sample_history=False, clip_denoised=False, injected_x=None,
-                   injected_noise=None, state=None):
+                   injected_noise=None, state=None, postprocess=None):
         """:454-506.  x_T ~ SaS is NOT scaled by barsigma (:464)."""
         dev = _lib.require_cuda(self.device)
         st = state or rng.default_state()
@@ -312,43 +351,55 @@ class GenerativeLevyProcess:
         return LIM_sampler(ddim=ddim, x=x, y=None, model=net.model, sde=self.sde, levy=self.levy,
                            isotropic=self.isotropic, steps=self.reverse_steps, gen_a=self.dlpm.gen_a,
                            gen_eps=self.dlpm.gen_eps, device=dev, get_sample_history=get_sample_history,
-                           injected_noise=injected_noise, net_call=lambda xx, tt: net(xx.view(shape), tt), state=st)
+                           injected_noise=injected_noise, net_call=lambda xx, tt: net(xx.view(shape), tt), state=st,
+                           postprocess=postprocess)
 
     def sample(self, models, shape, reverse_steps, time_spacing=None, initial_data=None, clip_denoised=False,
                deterministic=False, dlim_eta=1.0, print_progression=False, get_sample_history=False, clamp_a=None,
-               clamp_eps=None):
-        """Boundary entry point (:512-569); called by ``bem/GenerationManager.py:43-47``."""
+               clamp_eps=None, postprocess=None):
+        """Boundary entry point (:512-569); called by ``bem/GenerationManager.py:43-47``.
+
+        ``postprocess`` (extension, default None = reference behaviour): a ``dlpm_b200.generation.FusedPost``; the
+        caller's clamp / (x+1)/2 / uint8 quantisation (bem/GenerationManager.py:50-63) is then written by the LAST step
+        kernel into ``postprocess.out`` while the returned tensor still holds the unprocessed x_0."""
         self.dlpm.gen_a.setParams(clamp_a=clamp_a)
         self.dlpm.gen_eps.setParams(clamp_eps=clamp_eps)
         model = models["default"]
         assert time_spacing is None, "Specific time spacing is not yet supported for diffusion reverse sampling"
         default_reverse_steps = self.reverse_steps
-        default_time_spacing = self.time_spacing
         rescaled = self.reverse_steps != reverse_steps
         if rescaled:
             assert self.rescale_timesteps, "Rescaling only works when rescale_timesteps is True"
+            snapshot = self.dlpm.snapshot_schedule()
+            # like the reference (dlpm.py:176-185, App. B.5) the rescaled schedule is always the cosine 'scale_preserving'
+            # one, whatever self.dlpm.scale says (and input_scaling, if on, then uses the cosine barsigma: same quirk)
             self.dlpm.rescale_diffusion(reverse_steps, time_spacing=time_spacing)
             self.reverse_steps = reverse_steps
         try:
             if self.LIM:
                 x = self.lim_sample(model, shape=shape, ddim=deterministic, get_sample_history=get_sample_history,
-                                    clip_denoised=clip_denoised)
+                                    clip_denoised=clip_denoised, postprocess=postprocess)
             elif deterministic:
                 x = self.ddim_sample_loop(model, shape=initial_data.shape if initial_data is not None else shape,
                                           noise=initial_data, eta=dlim_eta, progress=print_progression,
-                                          get_sample_history=get_sample_history, clip_denoised=clip_denoised)
+                                          get_sample_history=get_sample_history, clip_denoised=clip_denoised,
+                                          postprocess=postprocess)
             else:
                 x = self.p_sample_loop(model, shape=shape, progress=print_progression,
-                                       get_sample_history=get_sample_history, clip_denoised=clip_denoised)
+                                       get_sample_history=get_sample_history, clip_denoised=clip_denoised,
+                                       postprocess=postprocess)
         finally:
-            if rescaled:  # the reference's restore guard never fires (App. B.4); we do restore
-                self.dlpm.rescale_diffusion(default_reverse_steps, default_time_spacing)
+            if rescaled:  # the reference's restore guard never fires (App. B.4); we do restore -- the exact tables, whatever
+                self.dlpm.restore_schedule(snapshot)  # their family ('scale_exploding' included)
                 self.reverse_steps = default_reverse_steps
         return x
 
     # ------------------------------------------------------------------------------------------ training (forward + loss)
     def training_losses(self, models, x_start, model_kwargs=None, **kwargs):
-        """:581-609.  Forward + loss only: backward kernels are out of this tier."""
+        """:581-609.  The noise / x_t / eps_t elements always come from the fused kernels.  A torch module in train()
+        mode under autograd (the reference's TrainingManager, bem/TrainingManager.py:111-120) is evaluated by torch and
+        the loss is differentiable; this package's native nets are forward-only (no backward kernels in
+        this tier) and raise NotImplementedError when asked to train."""
         model = models["default"]
         x_start = x_start.to(self.device)
         if model_kwargs is None:
@@ -386,11 +437,15 @@ class GenerativeLevyProcess:
                                 compact=True, state=st)
             A_ext = A.repeat(monte_carlo_inner)
         x_t, eps_t = self.dlpm.get_one_rv_loss_elements(t_ext, x_ext, A_ext, inj.get("z"), state=st)
-        net = _Net(model, dev)
+        train = _wants_grad(model)
+        net = _Net(model, dev, train=train)
         table = self._input_scale_table()
         x_in = x_t if table is None else self._scaled_input(x_t, table, t_vec=t_ext)
         model_eps = net(x_in, self._scale_timesteps(t_ext), **model_kwargs)
-        losses = compute_loss_terms(model_eps.reshape(x_t.shape), eps_t, lploss)
+        if model_eps.requires_grad:  # a torch module under autograd: differentiable loss terms, as the reference computes them
+            losses = _torch_loss_terms(model_eps.reshape(x_t.shape), eps_t, lploss)
+        else:
+            losses = compute_loss_terms(model_eps.reshape(x_t.shape), eps_t, lploss)
         assert not torch.isnan(losses).any(), "Nan in losses"
         if loss_monte_carlo == "mean":
             return losses.mean()
@@ -425,8 +480,11 @@ class GenerativeLevyProcess:
             _lib.call("dlpm_b200_lim_training_elements", _lib.ptr(x_t), _lib.ptr(score), _lib.ptr(x0), _lib.ptr(t), _lib.ptr(e), n, D,
                       float(self.sde.alpha), 1 if self.isotropic else 0, -1.0 if clamp_eps is None else float(clamp_eps), st.seed,
                       st.reserve(1), st.sample_base, _lib.stream_ptr())
-        net = _Net(model, dev)
+        net = _Net(model, dev, train=_wants_grad(model))
         output = net(x_t, t)
-        losses = compute_loss_terms(output.reshape(x_t.shape), score, 1.0)  # per-sample mean smooth-L1 (beta = 1)
+        if output.requires_grad:
+            losses = _torch_loss_terms(output.reshape(x_t.shape), score, 1.0)
+        else:
+            losses = compute_loss_terms(output.reshape(x_t.shape), score, 1.0)  # per-sample mean smooth-L1 (beta = 1)
         assert not torch.isnan(losses).any(), "Nan in losses"
         return losses.mean()  # all samples have D elements: mean of per-sample means == F.smooth_l1_loss(..., 'mean')

@@ -122,6 +122,17 @@ class DLPM:
         self._set_schedule(diffusion_steps, "scale_preserving")
         self.constants = None
 
+    def snapshot_schedule(self):
+        """Everything ``rescale_diffusion`` overwrites, so that ``sample(reverse_steps != train steps)`` can put the
+        TRAINING schedule back afterwards -- including a 'scale_exploding' one, which ``rescale_diffusion`` (like the
+        reference, dlpm.py:183) would silently replace by the cosine schedule."""
+        return (self._sched_host, self.sched, self.gammas, self.bargammas, self.sigmas, self.barsigmas, self.diffusion_steps,
+                self.time_spacing, self.constants)
+
+    def restore_schedule(self, snap):
+        (self._sched_host, self.sched, self.gammas, self.bargammas, self.sigmas, self.barsigmas, self.diffusion_steps,
+         self.time_spacing, self.constants) = snap
+
     def get_schedule(self, shape):
         return tuple(match_last_dims(v, shape) for v in (self.gammas, self.bargammas, self.sigmas, self.barsigmas))
 

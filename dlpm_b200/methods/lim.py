@@ -64,7 +64,7 @@ def lim_step_table(sde, steps, ode):
 
 def LIM_sampler(ddim, x, y, model, sde, levy, isotropic, steps, gen_a, gen_eps, sde_clamp=None, masked_data=None,
                 mask=None, t0=None, device="cuda", get_sample_history=False, injected_noise=None, net_call=None,
-                state=None):
+                state=None, postprocess=None):
     """Same signature as sampler.py:15-33 (+ ``injected_noise`` (steps, *x.shape) for parity tests).
     Heavy-tailed branch only (alpha != 2), 'sde' / 'ode' methods (imputation is not on the hot path)."""
     if sde.alpha == 2:
@@ -83,12 +83,13 @@ def LIM_sampler(ddim, x, y, model, sde, levy, isotropic, steps, gen_a, gen_eps, 
         hist = torch.empty((steps + 1, *x.shape), device=dev, dtype=torch.float32)
         hist[0].copy_(x)
     call = net_call or (lambda xx, tt: model(xx, tt))
+    post = None if postprocess is None else postprocess.bind(list(x.shape), dev)
     if getattr(model, "native_kind", None) == "unet" and injected_noise is None and x.dim() == 4:
         # image nets: one CUDA graph per step, replayed `steps` times (times come from a device table)
         from .. import _unet_lib
         with torch.no_grad(), torch.cuda.device(dev):
             _unet_lib.run_lim_loop(model, x, coef_d, timesteps[:-1].contiguous().to(dev), steps, bool(ddim), bool(isotropic),
-                                   float(sde.alpha), clamp_eps, hist, st.seed, offset, st.sample_base)
+                                   float(sde.alpha), clamp_eps, hist, st.seed, offset, st.sample_base, post=post)
         return (x, hist) if get_sample_history else x
     with torch.no_grad(), torch.cuda.device(dev):
         for i in range(steps):
@@ -97,10 +98,10 @@ def LIM_sampler(ddim, x, y, model, sde, levy, isotropic, steps, gen_a, gen_eps, 
             flags = _lib.STEP_EPS_BF16 if out.dtype == torch.bfloat16 else 0
             out = out.contiguous() if out.dtype == torch.bfloat16 else out.to(torch.float32).contiguous()
             e_L = None if injected_noise is None else injected_noise[i].to(dev, torch.float32).contiguous()
-            _lib.call("dlpm_b200_lim_step", _lib.ptr(x), _lib.ptr(out), _lib.ptr(coef_d), i, None, B, D, flags,
+            _lib.call("dlpm_b200_lim_step_post", _lib.ptr(x), _lib.ptr(out), _lib.ptr(coef_d), i, None, B, D, flags,
                       1 if ddim else 0, 1 if isotropic else 0, float(sde.alpha),
                       -1.0 if clamp_eps is None else float(clamp_eps), _lib.ptr(e_L), st.seed, offset, st.sample_base,
-                      _lib.ptr(hist[i + 1]) if hist is not None else None, _lib.stream_ptr())
+                      _lib.ptr(hist[i + 1]) if hist is not None else None, post, steps - 1, _lib.stream_ptr())
     if get_sample_history:
         return x, hist
     return x

@@ -25,18 +25,50 @@ class PhiloxState:
 
 
 _default = PhiloxState()
+_follow_torch = True     # until dlpm_b200.manual_seed() is called, the default stream is keyed by torch's seed
+_torch_seed_seen = None
+
+
+def _mix(seed):
+    """splitmix64 finaliser: decorrelates our Philox key from the raw user seed (torch's own generator uses it as is)."""
+    z = (int(seed) + 0x9E3779B97F4A7C15) & (2 ** 64 - 1)
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & (2 ** 64 - 1)
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & (2 ** 64 - 1)
+    return z ^ (z >> 31)
 
 
 def default_state():
+    """The process-wide state.  Unless ``dlpm_b200.manual_seed`` has been called it FOLLOWS ``torch.manual_seed``: the
+    reference seeds its noise through ``torch.manual_seed`` / ``np.random.seed`` (bem/Experiments.py:58-63), so a run that
+    only does that must not silently reuse one fixed stream -- whenever ``torch.initial_seed()`` changes, the Philox key
+    is re-derived from it and the call offset restarts at 0."""
+    global _torch_seed_seen
+    if _follow_torch:
+        import torch
+        ts = int(torch.initial_seed())
+        if ts != _torch_seed_seen:
+            _torch_seed_seen = ts
+            _default.seed = _mix(ts)
+            _default.offset = 0
     return _default
 
 
 def manual_seed(seed, offset=0):
-    """Seed the noise generator (mirrors ``torch.manual_seed`` / ``np.random.seed`` in the reference)."""
+    """Seed the noise generator explicitly (from here on ``torch.manual_seed`` no longer re-keys it)."""
+    global _follow_torch
+    _follow_torch = False
     _default.seed = int(seed) & (2 ** 64 - 1)
     _default.offset = int(offset)
 
 
+def follow_torch_seed(on=True):
+    """Return to (or leave) the default behaviour of keying the noise stream by ``torch.initial_seed()``."""
+    global _follow_torch, _torch_seed_seen
+    _follow_torch = bool(on)
+    _torch_seed_seen = None
+
+
 def set_sample_base(base):
-    """Global index of this process's first sample (batch sharding over GPUs)."""
+    """Global index of this process's first sample (batch sharding over GPUs / over generation processes: two processes
+    with the same seed and the same sample base draw the SAME samples)."""
     _default.sample_base = int(base)

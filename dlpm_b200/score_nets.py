@@ -152,31 +152,101 @@ def _mlp_from_reference(ref, device):
     return m.to(device).eval()
 
 
+def parameter_fingerprint(module):
+    """Content fingerprint of a module's parameters: (data_ptr, shape) of every tensor + per-tensor L2 norms + the sum and
+    a fixed-stride subsample of the flattened parameters, all reduced on the parameters' own device (one multi-tensor norm,
+    one concatenation, one D2H of ~300 floats).  Unlike ``Tensor._version`` it also sees writes made through ``.data`` --
+    ``EMAHelper._ema`` (bem/utils_ema.py:34-39) and ``load_state_dict`` overwrite the weights of ONE persistent module
+    that way between two ``sample()`` calls."""
+    ps = [p.detach() for p in module.parameters()]
+    if not ps:
+        return ()
+    with torch.no_grad():
+        flat = torch.cat([p.reshape(-1).float() for p in ps])
+        norms = torch.stack(torch._foreach_norm(ps)).float()
+        stride = max(1, flat.numel() // 61)
+        probe = torch.cat([norms, flat.sum().reshape(1), flat[::stride]]).cpu()
+    return tuple((p.data_ptr(), tuple(p.shape)) for p in ps) + (tuple(probe.tolist()),)
+
+
+def _invalidate_packed(model):
+    if hasattr(model, "_cache"):
+        model._cache.key = None
+    for ent in getattr(model, "_engines", {}).values():
+        ent.version = None
+
+
+def _refresh_native(model, fp):
+    """A native net whose parameters were rewritten behind ``Tensor._version``'s back: drop the packed copies."""
+    if getattr(model, "_fingerprint", None) not in (None, fp):
+        _invalidate_packed(model)
+    try:
+        object.__setattr__(model, "_fingerprint", fp)
+    except Exception:
+        pass
+
+
 def as_native(model, device):
     """Return a module whose forward runs on the CUDA engine when ``model`` is one of the hot-path
     score nets (this package's classes, or the reference's ``MLPModel`` / ``UNetModel`` which are
     ingested through their ``state_dict``); any other ``nn.Module`` is returned unchanged and is simply
-    called on the device by the sampling loop."""
+    called on the device by the sampling loop.
+
+    The ingested copy is cached on the source object together with a content fingerprint of the source's parameters
+    (``parameter_fingerprint``); every call re-checks it and re-copies the ``state_dict`` when the source has changed --
+    the reference mutates weights in place on one persistent object (EMA evaluation, checkpoint load, training between
+    two evaluations; bem/utils_ema.py:52-54, bem/TrainingManager.py:240-264)."""
     if getattr(model, "native_kind", None) is not None:
+        _refresh_native(model, parameter_fingerprint(model))
         return model
+    name = type(model).__name__
+    is_mlp = name == "MLPModel" and hasattr(model, "midblocks") and hasattr(model, "outblocks_mean")
+    is_unet = name == "UNetModel" and hasattr(model, "input_blocks") and hasattr(model, "output_blocks")
+    if not (is_mlp or is_unet):
+        return model
+    fp = parameter_fingerprint(model)
     cached = getattr(model, "_dlpm_b200_native", None)
     if cached is not None:
-        return cached
-    name = type(model).__name__
-    native = None
-    if name == "MLPModel" and hasattr(model, "midblocks") and hasattr(model, "outblocks_mean"):
-        native = _mlp_from_reference(model, device)
-    elif name == "UNetModel" and hasattr(model, "input_blocks") and hasattr(model, "output_blocks"):
-        native = _unet_from_reference(model, device)
-    if native is None:
-        return model
+        native, old_fp = cached
+        if old_fp != fp or next(native.parameters()).device != torch.device(device):
+            native.load_state_dict(model.state_dict(), strict=True)
+            native.to(device)
+            _invalidate_packed(native)  # (version counters are not bumped for copies made under inference_mode)
+            object.__setattr__(model, "_dlpm_b200_native", (native, fp))
+        return native
+    native = _mlp_from_reference(model, device) if is_mlp else _unet_from_reference(model, device)
     try:
-        object.__setattr__(model, "_dlpm_b200_native", native)
+        object.__setattr__(model, "_dlpm_b200_native", (native, fp))
     except Exception:
         pass
     return native
 
 
+def load_checkpoint(path_or_dict, model, ema=None, map_location=None):
+    """Load the weights of ``models['default']`` from a checkpoint in the reference's on-disk format
+    (bem/TrainingManager.py:267-285: ``torch.save`` of a dict with ``model_parameters`` = ``state_dict()`` and, when EMA
+    is on, ``ema_models`` = list of ``EMAHelper.state_dict()`` = ``{parameter name: shadow tensor}`` in the order of the
+    run's ``ema_rates``; loaded at :240-264).  ``ema`` = None takes the raw model, an int selects that EMA entry (what
+    ``EMAHelper.get_ema_model`` would copy into the model, bem/utils_ema.py:34-54).  ``model`` may be one of this package's
+    mirrors or a reference ``MLPModel`` / ``UNetModel``; returns it (weights replaced in place)."""
+    ckpt = path_or_dict
+    if not isinstance(ckpt, dict):
+        ckpt = torch.load(path_or_dict, map_location=map_location or "cpu", weights_only=False)
+    if "model_parameters" not in ckpt:
+        raise KeyError("not a bem checkpoint: no 'model_parameters' entry (keys: %s)" % sorted(ckpt.keys()))
+    sd = dict(ckpt["model_parameters"])
+    if ema is not None:
+        emas = ckpt.get("ema_models")
+        assert emas is not None, "no ema model in checkpoint"
+        if not 0 <= int(ema) < len(emas):
+            raise IndexError("checkpoint holds %d EMA models, asked for %d" % (len(emas), ema))
+        shadow = emas[int(ema)]
+        missing = [k for k, _ in model.named_parameters() if k not in shadow and _.requires_grad]
+        if missing:
+            raise KeyError("EMA state lacks parameters %s ..." % missing[:3])
+        sd.update({k: v for k, v in shadow.items()})  # shadow covers the trainable parameters; buffers come from the model
+    model.load_state_dict(sd, strict=True)
+    return model
 
 
 # ------------------------------------------------------------------------------------------------
@@ -510,13 +580,13 @@ class UNetModel(nn.Module):
             eng.forward(xin, t[:1].contiguous() if uniform else t, None, 0.0, out, B)
         return out
 
-    def sample_loop(self, x, dlpm, T, mode, flags, hist, seed, z_offset, sample_base, graph_cache=None, progress=False,
-                    input_scale=None):
+    def sample_loop(self, x, dlpm, T, mode, flags, hist, seed, z_offset, sample_base, progress=False,
+                    input_scale=None, post=None):
         """The image-config hot loop: per step  eps = UNet(x, t/T)  then the fused update (K3), with the step index
         in a device counter so ONE captured CUDA graph is replayed T-1 times."""
         from . import _unet_lib
-        _unet_lib.run_sample_loop(self, x, dlpm, T, mode, flags, hist, seed, z_offset, sample_base, graph_cache, progress,
-                                  input_scale=input_scale)
+        _unet_lib.run_sample_loop(self, x, dlpm, T, mode, flags, hist, seed, z_offset, sample_base, progress,
+                                  input_scale=input_scale, post=post)
 
 
 def _unet_from_reference(ref, device):

@@ -7,9 +7,12 @@
  * The Python host (dlpm_b200/_lib.py, ctypes) mirrors the reference's `dlpm/methods` API on top.
  * `file:line` citations are relative to the reference tree (darioShar/DLPM).
  *
- * RNG contract: Philox4x32-10; a variate is a pure function of (seed, stream tag, offset, GLOBAL
- * sample index = sample_base + local index, position in sample), so any sharding of the batch
- * over GPUs reproduces the same numbers.
+ * RNG contract: Philox4x32-R (Salmon et al. 2011) with R = dlpm_b200_philox_rounds() = 7 in the default build (the fewest
+ * rounds that pass BigCrush, Table 2 of the paper; -DDLPM_PHILOX_ROUNDS=10 rebuilds with the Random123 / cuRAND default);
+ * a variate is a pure function of (seed, stream tag, offset, GLOBAL sample index = sample_base + local index, position in
+ * sample), so any sharding of the batch over GPUs reproduces the same numbers.  The reference draws from numpy's / torch's
+ * global generators, so no reference stream is pinned by this choice; oracle/philox.py restates the generator with the
+ * Random123 known-answer vectors for both round counts.
  */
 #ifndef DLPM_B200_H_
 #define DLPM_B200_H_
@@ -77,6 +80,32 @@ int dlpm_b200_reverse_step(float* x, const void* eps, const float* Sigma, const 
                            const int* t_dev, int T, int64_t B, int64_t D, int flags, const float* z,
                            uint64_t seed, uint64_t offset, int64_t sample_base, float* hist_out, void* stream);
 
+/* Post-processing of the FINAL sample fused into the last step's store (bem/GenerationManager.py:50-63: clamp to +-1
+ * (images) / +-6 (2-D data), images then mapped by (x+1)/2; DLPM_POST_U8_NHWC additionally quantises like
+ * torchvision.utils.save_image -- x*255 + 0.5, clamp to [0,255], truncate -- into uint8 [B, H*W, C]).  The step kernel
+ * writes `out` only when it executes the step whose result is final (t == 1; LIM: the last step), so the same argument
+ * can be baked into a CUDA graph that is replayed for every step.  x itself always receives the unprocessed x_0. */
+#define DLPM_POST_NONE 0
+#define DLPM_POST_F32 1        /* out fp32 [B, D] = clamp(x, +-clamp)                 (16-byte aligned) */
+#define DLPM_POST_F32_IMAGE 2  /* out fp32 [B, D] = (clamp(x, +-clamp) + 1) / 2 */
+#define DLPM_POST_U8_NHWC 3    /* out uint8 [B, D/channels, channels] of the image form */
+typedef struct dlpm_b200_post {
+  void* out;
+  float clamp;
+  int mode;
+  int channels; /* DLPM_POST_U8_NHWC only: D = channels * H * W */
+} dlpm_b200_post_t;
+int dlpm_b200_reverse_step_post(float* x, const void* eps, const float* Sigma, const float* sched, int t, const int* t_dev,
+                                int T, int64_t B, int64_t D, int flags, const float* z, uint64_t seed, uint64_t offset,
+                                int64_t sample_base, float* hist_out, const dlpm_b200_post_t* post, void* stream);
+int dlpm_b200_dlim_step_post(float* x, const void* eps, const float* sched, int t, const int* t_dev, int T, int64_t B,
+                             int64_t D, int flags, float* hist_out, const dlpm_b200_post_t* post, void* stream);
+/* last_step: the step index whose result is the final sample (n_steps - 1). */
+int dlpm_b200_lim_step_post(float* x, const void* model_out, const float* coef, int step, const int* step_dev, int64_t B,
+                            int64_t D, int flags, int ode, int isotropic, float alpha, float clamp_eps, const float* e_L,
+                            uint64_t seed, uint64_t offset, int64_t sample_base, float* hist_out, const dlpm_b200_post_t* post,
+                            int last_step, void* stream);
+
 /* K3'. Deterministic DLIM step, eta = 0 (anterior_mean_variance_dlim dlpm.py:281-287):
  *   x <- (x - bs_t eps)/g_t + bs_{t-1} eps. */
 int dlpm_b200_dlim_step(float* x, const void* eps, const float* sched, int t, const int* t_dev, int T,
@@ -94,8 +123,12 @@ int dlpm_b200_lim_step(float* x, const void* model_out, const float* coef, int s
                        const float* e_L, uint64_t seed, uint64_t offset, int64_t sample_base, float* hist_out,
                        void* stream);
 
-/* Device-side step counter helper for graph replay: *t_dev += delta (single thread). */
+/* Device-side step counter helpers for graph replay: *t_dev += delta / *t_dev = value (single thread). */
 int dlpm_b200_advance_counter(int* t_dev, int delta, void* stream);
+int dlpm_b200_set_counter(int* t_dev, int value, void* stream);
+
+/* Rounds of the Philox4x32 generator this build uses (compile-time DLPM_PHILOX_ROUNDS; 7 by default, see RNG contract). */
+int dlpm_b200_philox_rounds(void);
 
 /* Training forward elements, Proposition (9) (dlpm.py:384-401, GenerativeLevyProcess.py:634-661):
  *   x_t = bg_t x0 + sqrt(A bs_t^2) z ;  eps_t = (x_t - bg_t x0)/bs_t,   per-sample t (int64, B).

@@ -8,6 +8,8 @@
 #define DLPM_B200_UNET_H_
 #include <stdint.h>
 
+#include "dlpm_b200.h"
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -128,6 +130,28 @@ int dlpm_b200_unet_create(void** handle, const int64_t* header, const int64_t* o
  * t_dev (+ inv_T, or + t as a time table) as above; out fp32 NCHW [B,out_ch,H,W]. */
 int dlpm_b200_unet_forward(void* handle, const float* x, const float* t, int t_rows, const int* t_dev, float inv_T,
                            float* out, int64_t B, void* stream);
+/* The captured reverse loop: the whole of p_sample_loop_progressive / ddim_sample_loop_progressive
+ * (GenerativeLevyProcess.py:291-330, :413-452) or LIM_sampler (LIM/functions/sampler.py:218-258) for the image net in ONE
+ * call.  A step = [optional input scaling] -> UNet forward (time from a device-side counter) -> fused update -> counter
+ * +-1; it is captured with cudaStreamBeginCapture on `stream` into a CUDA graph, the engine's cached executable graph is
+ * updated in place (cudaGraphExecUpdate; instantiated only when the topology changes) and launched once per step.
+ * Asynchronous; x (fp32 [B, C, H, W], in place) holds the final sample when the stream has drained.
+ *   mode DLPM_LOOP_DLPM : x_{T-1} -> x_0, T - 1 steps; Sigma compact (T, B) or full (flag DLPM_STEP_SIGMA_FULL), sched (T, 4),
+ *                         aux = NULL or the device table 1/(1 + barsigma_t) [T] of `input_scaling` (GenerativeLevyProcess.py:177-180)
+ *   mode DLPM_LOOP_DLIM : deterministic eta = 0 steps; Sigma unused
+ *   mode DLPM_LOOP_LIM_SDE / _ODE : T steps; sched = coefficient rows [T][4] of dlpm_b200_lim_step, aux = continuous times [T];
+ *                         isotropic / alpha / clamp_eps as in dlpm_b200_lim_step
+ * flags: DLPM_STEP_CLIP_DENOISED, DLPM_STEP_SIGMA_FULL.  seed / offset / sample_base key the in-kernel noise exactly as
+ * in the step functions (z of step t at offset + t).  post: NULL or the fused post-processing of the final sample. */
+#define DLPM_LOOP_DLPM 0
+#define DLPM_LOOP_DLIM 1
+#define DLPM_LOOP_LIM_SDE 2
+#define DLPM_LOOP_LIM_ODE 3
+int dlpm_b200_graph_sample(void* handle, int mode, float* x, const float* Sigma, const float* sched, const float* aux, int T,
+                           int64_t B, int flags, int isotropic, float alpha, float clamp_eps, uint64_t seed, uint64_t offset,
+                           int64_t sample_base, const dlpm_b200_post_t* post, void* stream);
+/* how often dlpm_b200_graph_sample had to instantiate an executable graph / could update the cached one in place */
+int dlpm_b200_graph_sample_stats(void* handle, int* instantiations, int* updates);
 /* debugging / per-layer parity: copy activation buffer `buf` (bf16, B * elems) of the last forward to dst. */
 int dlpm_b200_unet_copy_buffer(void* handle, int buf, void* dst, int64_t B, void* stream);
 /* measurement: one forward with a CUDA event after every op; ms_per_op / flops_per_op are HOST arrays of n_ops + 1

@@ -4,8 +4,9 @@ The reference draws its noise from numpy's / torch's global generators (``bem/da
 is no reference stream to reproduce bit for bit; what CAN be pinned pointwise is the chain
 ``Philox words -> lattice uniforms -> reference formula``:
 
-* ``philox4x32`` is Philox4x32-10 (Salmon et al. 2011), checked against the Random123 known-answer vectors
-  (``tests/test_oracle_golden.py``);
+* ``philox4x32`` is Philox4x32-R (Salmon et al. 2011), checked against the Random123 known-answer vectors for R = 7
+  (the kernels' default, ``csrc/rng.cuh`` DLPM_PHILOX_ROUNDS) and R = 10 (``tests/test_oracle_golden.py``); ``ROUNDS`` is
+  what ``words`` uses -- the tests set it from the library (``dlpm_b200_philox_rounds``);
 * ``counters`` is the counter layout of ``dlpm_b200/csrc/rng.cuh`` (position, global sample index, call offset, stream tag);
 * ``stable_A_from_words`` / ``normal_from_words`` map the 32-bit words to the exactly representable fp32 lattice points the
   kernels use and then evaluate the REFERENCE formulas in float64 (``oracle/stable.py::kanter_A`` = scipy's CMS branch,
@@ -22,8 +23,12 @@ _W0, _W1 = 0x9E3779B9, 0xBB67AE85
 _MASK = np.uint64(0xFFFFFFFF)
 
 
-def philox4x32(key, c0, c1, c2, c3, rounds=10):
+ROUNDS = 7  # DLPM_PHILOX_ROUNDS of the default build
+
+
+def philox4x32(key, c0, c1, c2, c3, rounds=None):
     """Philox4x32-R on arrays of counters; ``key`` = (k0, k1) 32-bit words.  Returns four uint32 arrays."""
+    rounds = ROUNDS if rounds is None else rounds
     c0, c1, c2, c3 = (np.asarray(c, dtype=np.uint64) & _MASK for c in np.broadcast_arrays(c0, c1, c2, c3))
     k0, k1 = int(key[0]) & 0xFFFFFFFF, int(key[1]) & 0xFFFFFFFF
     for _ in range(rounds):

@@ -29,7 +29,12 @@ def test_library_exports_every_declared_symbol():
         build.build()
     lib = ctypes.CDLL(_lib.LIB_PATH)
     syms = header_symbols()
-    assert len(syms) >= 29
+    assert len(syms) >= 37
+    for new in ("dlpm_b200_graph_sample", "dlpm_b200_graph_sample_stats", "dlpm_b200_reverse_step_post", "dlpm_b200_dlim_step_post",
+                "dlpm_b200_lim_step_post", "dlpm_b200_set_counter", "dlpm_b200_philox_rounds"):
+        assert new in syms, new
+    lib.dlpm_b200_philox_rounds.restype = ctypes.c_int
+    assert lib.dlpm_b200_philox_rounds() in (7, 10)
     for name in syms:
         assert hasattr(lib, name), "missing export: " + name
     lib.dlpm_b200_abi_version.restype = ctypes.c_int
@@ -38,7 +43,7 @@ def test_library_exports_every_declared_symbol():
     table = dict(_lib.SIGNATURES)
     table.update(_unet_lib.UNET_SIGNATURES)
     for name, nargs in syms.items():
-        if name in ("dlpm_b200_abi_version", "dlpm_b200_last_error", "dlpm_b200_unet_workspace_bytes"):
+        if name in ("dlpm_b200_abi_version", "dlpm_b200_last_error", "dlpm_b200_unet_workspace_bytes", "dlpm_b200_philox_rounds"):
             continue
         assert name in table, "no ctypes signature for " + name
         assert len(table[name]) == nargs, (name, len(table[name]), nargs)

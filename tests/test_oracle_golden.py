@@ -221,14 +221,19 @@ def test_oracle_against_live_reference():
 # transform (rng.cuh::stable_A, restated in numpy float32) against the reference formula on identical lattice variates
 # ------------------------------------------------------------------------------------------------------------------
 def test_philox4x32_known_answers():
-    """Random123 kat_vectors, philox4x32-10 (Salmon et al. 2011)."""
+    """Random123 kat_vectors (Salmon et al. 2011): philox4x32-10 and philox4x32-7 (the kernels' default round count)."""
     from oracle import philox
-    kat = [((0, 0), (0, 0, 0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
-           ((0xffffffff, 0xffffffff), (0xffffffff,) * 4, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
-           ((0xa4093822, 0x299f31d0), (0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
-    for key, ctr, exp in kat:
-        out = philox.philox4x32(key, *[np.array([c]) for c in ctr])
-        assert [int(o[0]) for o in out] == list(exp)
+    keys = [((0, 0), (0, 0, 0, 0)), ((0xffffffff, 0xffffffff), (0xffffffff,) * 4),
+            ((0xa4093822, 0x299f31d0), (0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344))]
+    kat = {10: [(0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd),
+                (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)],
+           7: [(0x5f6fb709, 0x0d893f64, 0x4f121f81, 0x4f730a48), (0x5207ddc2, 0x45165e59, 0x4d8ee751, 0x8c52f662),
+               (0x4dfccaba, 0x190a87f0, 0xc47362ba, 0xb6b5242a)]}
+    for rounds, exps in kat.items():
+        for (key, ctr), exp in zip(keys, exps):
+            out = philox.philox4x32(key, *[np.array([c]) for c in ctr], rounds=rounds)
+            assert [int(o.reshape(-1)[0]) for o in out] == list(exp), rounds
+    assert philox.ROUNDS == 7
     # counter layout: distinct (sample, position, offset, stream) never share a block
     w = philox.words(1234, philox.STREAM_A, 7, np.arange(4), 0)
     assert len({tuple(int(c[i]) for c in w) for i in range(4)}) == 4
