@@ -177,6 +177,59 @@ def workload_config(args, batch_per_gpu, n):
                        % (5.1e-3 * batch_per_gpu, batch_per_gpu)}
 
 
+def hbm_kernels(torch, _lib, glp, dev, T, hbm_peak, sets=4, reps=5):
+    """K3 (fused reverse step, 12 B per element) at the full C3 batch 4096 x 3 x 32 x 32 and K1 (isotropic SaS fill,
+    4 B per draw) on 2^28 draws: mean duration of `sets` back-to-back launches on `sets` different buffer sets (K3: 100 MB
+    each, 400 MB together > the 126 MB L2; K1: 1 GB each), CUDA events on the launching stream, best of `reps` rounds.
+    A library kernel with exactly K3's traffic (torch.add, warmed up) is timed the same way beside it."""
+    out = {}
+    Bk = 4096
+    kshape = [Bk, CH, IMG, IMG]
+    n_el = Bk * CH * IMG * IMG
+    d = glp.dlpm
+    d.sample_A(kshape, T)
+    xs = [torch.randn(kshape, device=dev) for _ in range(sets)]
+    es = [torch.randn(kshape, device=dev) for _ in range(sets)]
+
+    def timed(fn_of_set, n_sets):
+        best = float("inf")
+        for _ in range(reps + 1):  # first round = warm-up
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record()
+            for k in range(n_sets):
+                fn_of_set(k)
+            b.record()
+            torch.cuda.synchronize()
+            if _ > 0:
+                best = min(best, a.elapsed_time(b) / n_sets)
+        return best
+    ms_k3 = timed(lambda k: _lib.call("dlpm_b200_reverse_step", _lib.ptr(xs[k]), _lib.ptr(es[k]), _lib.ptr(d.Sigmas), _lib.ptr(d.sched),
+                                      min(500, T - 1), None, T, Bk, CH * IMG * IMG, 0, None, 1, 2, 0, None, _lib.stream_ptr()), sets)
+    ms_add = timed(lambda k: torch.add(xs[k], es[k], out=xs[k]), sets)
+    out["reverse_step"] = {"bytes_per_launch": 12 * n_el, "ms": ms_k3, "GB/s": 12 * n_el / ms_k3 / 1e6, "frac": 12 * n_el / ms_k3 / 1e6 / hbm_peak,
+                           "same_traffic_torch_add_GB/s": 12 * n_el / ms_add / 1e6,
+                           "how": "mean of %d back-to-back launches on %d buffer sets (%.0f MB together), best of %d rounds, before the sampling loop"
+                                  % (sets, sets, sets * 8 * n_el / 1e6, reps)}
+    del xs, es
+    torch.cuda.empty_cache()
+    n_noise = 1 << 28
+    nn = (n_noise // 3072) * 3072
+    bufs = [torch.empty(n_noise, device=dev) for _ in range(2)]
+    for name, iso, per_el in (("sas_noise_isotropic", 1, False), ("sas_noise_per_element", 0, False), ("A_per_element", 0, True)):
+        if per_el:
+            ms = timed(lambda k: _lib.call("dlpm_b200_stable_A", _lib.ptr(bufs[k]), n_noise // 3072, 3072, 2, ALPHA, -1.0, 1, 2, 0,
+                                           _lib.stream_ptr()), 2)
+        else:
+            ms = timed(lambda k: _lib.call("dlpm_b200_sas", _lib.ptr(bufs[k]), None, n_noise // 3072, 3072, iso, ALPHA, 200.0, 1.0, 1, 2, 0,
+                                           _lib.stream_ptr()), 2)
+        out[name] = {"bytes_per_launch": 4 * nn, "ms": ms, "GB/s": 4 * nn / ms / 1e6, "frac": 4 * nn / ms / 1e6 / hbm_peak}
+    out["sas_noise_isotropic"]["generator"] = "Philox4x32-%d" % _lib.load().dlpm_b200_philox_rounds()
+    out["sas_noise_isotropic"]["limiter"] = ("instruction dispatch: 2 quarter-rate IMAD.WIDE per Philox round per 4 normals (+ Box-Muller: 2 MUFU "
+                                             "per normal), see profiles/r01_ncu_stream.md and profiles/r02_noise.md")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------------------
 def run_ours(args, rank, local_rank, world):
     import torch
@@ -203,19 +256,22 @@ def run_ours(args, rank, local_rank, world):
     dlpm_b200.manual_seed(1234)
     dlpm_b200.set_sample_base(rank * B)  # global sample index of this rank's first sample
     gathered = torch.empty((world * B, CH, IMG, IMG), device=dev) if world > 1 else None
-    host_out = torch.empty((B, CH, IMG, IMG), dtype=torch.float32).pin_memory()
     host_sched = glp.dlpm._sched_host.clone().pin_memory()
+    # the caller of the boundary (bem/GenerationManager.py:29-63) with its post-processing fused into the last step kernel
+    # and the device -> host copy of the result into pinned memory issued inside generate()
+    manager = dlpm_b200.GenerationManager(glp, shape, is_image=True, reverse_steps=T, clamp_a=20, clamp_eps=200)
 
     def step(e2e=False):
-        if e2e:  # host -> device: the per-call inputs of sample() are the schedule table and the RNG key/offset
+        if e2e:
+            # host -> device: the per-call inputs of sample() are the schedule table and the RNG key / offset
             glp.dlpm.sched.copy_(host_sched, non_blocking=True)
+            manager.generate(models, B)  # sample() + fused clamp, (x+1)/2 + pinned async D2H + stream sync
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, manager.device_samples)
+            return manager.samples
         x = glp.sample(models, shape, reverse_steps=T, clamp_a=20, clamp_eps=200)
         if world > 1:
             dist.all_gather_into_tensor(gathered, x)  # the path's only collective
-        if e2e:  # GenerationManager.generate post-processing (clamp, (x+1)/2) + device -> host read of the result
-            _lib.call("dlpm_b200_postprocess", _lib.ptr(x), _lib.ptr(x), x.numel(), 1.0, 1, _lib.stream_ptr())
-            host_out.copy_(x, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
         return x
 
     def barrier():
@@ -246,6 +302,15 @@ def run_ours(args, rank, local_rank, world):
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms[0]), float(ms[1])
+
+    # ---- HBM-bound kernels: fused reverse step (12 B/element) and SaS noise (4 B/element).  Timed BEFORE the long loop
+    # (the loop leaves the GPU power-capped at ~1590 MHz; these kernels are quoted against the BURST copy peak of
+    # MEASURED_PEAKS.json, which was taken on a cool GPU), as the mean of back-to-back launches over buffer sets that together
+    # exceed the 126 MB L2 (each launch misses L2; one launch's ~7 us launch latency is not billed to a 25 us kernel)
+    pk, pk_src = peaks()
+    hbm_peak = float(pk["hbm_gbs"])
+    hbm = hbm_kernels(torch, _lib, glp, dev, T, hbm_peak)
+    torch.cuda.empty_cache()
 
     # nvidia-smi needs ~1 s to initialise NVML and briefly contends with kernel launches while it does: start it before
     # the last warm-up step so that only its steady 200 ms polling runs during the timed region; rows logged before the
@@ -284,7 +349,6 @@ def run_ours(args, rank, local_rank, world):
     conv = [(ms, fl) for code, ms, fl in prof if code == 2]
     conv_ms, conv_fl = sum(m for m, _ in conv), sum(f for _, f in conv)
     fwd_ms = sum(ms for _, ms, _ in prof)
-    pk, pk_src = peaks()
     achieved = conv_fl / (conv_ms * 1e-3) / 1e12
     peak = float(pk.get("bf16_tflops_sustained", pk["bf16_tflops"]))
     traffic = None
@@ -299,42 +363,6 @@ def run_ours(args, rank, local_rank, world):
                 "conv_share_of_forward": conv_ms / fwd_ms, "forward_ms_serialised": fwd_ms, "forward_ms_by_op": breakdown,
                 "end_to_end_tflops": GFLOP_PER_SAMPLE_STEP * 1e9 * B * (T - 1) / (ms_per_step * 1e-3) / 1e12}
 
-    # ---- HBM-bound kernels: fused reverse step (12 B/element) and SaS noise (4 B/element), timed alone (burst peak)
-    hbm = {}
-    Bk = 4096  # BASELINE.json configs[2] full batch: 4096 x 3 x 32 x 32 (151 MB per launch, > L2)
-    kshape = [Bk, CH, IMG, IMG]
-    n_el = Bk * CH * IMG * IMG
-    big = torch.empty(64 * 1024 * 1024, device=dev)  # 256 MB > L2: flushes between timed launches
-    d = glp.dlpm
-    d.sample_A(kshape, T)
-    eps = torch.randn(kshape, device=dev)
-    xw = torch.randn(kshape, device=dev)
-
-    def time_kernel(fn, reps=20):
-        t = 0.0
-        for _ in range(reps):
-            big.zero_()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); fn(); b.record()
-            torch.cuda.synchronize()
-            t += a.elapsed_time(b)
-        return t / reps
-    ms_k3 = time_kernel(lambda: _lib.call("dlpm_b200_reverse_step", _lib.ptr(xw), _lib.ptr(eps), _lib.ptr(d.Sigmas), _lib.ptr(d.sched), min(500, T - 1),
-                                          None, T, Bk, CH * IMG * IMG, 0, None, 1, 2, 0, None, _lib.stream_ptr()))
-    n_noise = 1 << 28
-    nbuf = torch.empty(n_noise, device=dev)
-    ms_k1 = time_kernel(lambda: _lib.call("dlpm_b200_sas", _lib.ptr(nbuf), None, n_noise // 3072, 3072, 1, ALPHA, 200.0, 1.0, 1, 2, 0,
-                                          _lib.stream_ptr()), reps=5)
-    hbm_peak = float(pk["hbm_gbs"])
-    # a library elementwise kernel with exactly the same traffic (2 reads + 1 write of the same tensors, no RNG): what a
-    # 151 MB launch can reach on this box, next to the copy peak measured on multi-GB buffers
-    ms_add = time_kernel(lambda: torch.add(xw, eps, out=xw))
-    hbm["reverse_step"] = {"bytes_per_launch": 12 * n_el, "ms": ms_k3, "GB/s": 12 * n_el / ms_k3 / 1e6, "frac": 12 * n_el / ms_k3 / 1e6 / hbm_peak,
-                           "same_traffic_torch_add_GB/s": 12 * n_el / ms_add / 1e6}
-    nn = (n_noise // 3072) * 3072
-    hbm["sas_noise_isotropic"] = {"bytes_per_launch": 4 * nn, "ms": ms_k1, "GB/s": 4 * nn / ms_k1 / 1e6, "frac": 4 * nn / ms_k1 / 1e6 / hbm_peak,
-                                  "limiter": "instruction dispatch: each of the 20 IMAD.WIDE of Philox4x32-10 per 4 normals holds the port 4 cycles (+ Box-Muller: 2 MUFU per normal), see profiles/r01_ncu_stream.md"}
-
     launches_per_pass = (T - 1) * (eng.num_launches() + 2) + 3
     # ---- same-box GPU baseline: the UNMODIFIED reference with device='cuda' (PyTorch eager + cuDNN, TF32 convs), in the
     # chunk size its own eval config uses (64, dlpm/configs/cifar10_lt.yml:35) and at 256 (its (T,B,C,H,W) tables: 6 GB)
@@ -344,7 +372,7 @@ def run_ours(args, rank, local_rank, world):
             from oracle import ref_import
             if ref_import.available():
                 from oracle import ref_driver
-                del xs, out, eps, xw, nbuf, big
+                del xs, out
                 torch.cuda.empty_cache()
                 runs = [ref_driver.gpu_eager_arm(dev, b, n_steps=20, T=T, alpha=ALPHA, img=IMG, ch=CH) for b in (64, 256)]
                 best = max(runs, key=lambda r: r["value"])
@@ -359,14 +387,154 @@ def run_ours(args, rank, local_rank, world):
         line = {"metric": "DLPM samples/sec (1000 reverse steps, CIFAR-10 shape)", "value": value, "unit": "samples/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "ms_each_step": each, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, B, world),
+                "precision": {"ours": "bf16 activations and conv weights, fp32 accumulation / GroupNorm statistics / x_t state / noise",
+                              "reference": "fp32 storage (cuDNN TF32 convolutions when it runs on a GPU)",
+                              "parity": "tests/test_gpu_reference_live.py: T=1000 chains + distribution of 1000-step samples vs the live reference"},
                 "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(host_sched.numel() * 4 * world),
-                        "d2h_bytes_per_step": int(host_out.numel() * 4 * world), "steps": args.e2e_steps,
-                        "api": "GenerativeLevyProcess.sample() + GenerationManager post-processing + pinned D2H"},
+                        "d2h_bytes_per_step": int(B * CH * IMG * IMG * 4 * world), "steps": args.e2e_steps,
+                        "api": "dlpm_b200.GenerationManager.generate() = GenerativeLevyProcess.sample() with the clamp / (x+1)/2 of "
+                               "bem/GenerationManager.py:50-63 fused into the last step kernel + async D2H into pinned memory"},
                 "gpu_launches": int(launches_per_pass * (args.steps + args.e2e_steps)), "clocks": clk, "roofline": roofline,
                 "hbm_kernels": hbm, "gpu_eager_baseline": gpu_eager,
                 "cpu_baseline": {"value": cpu_val, "unit": "samples/s", "cores": os.cpu_count(), "kind": cpu_kind, "source": reference_source(), "sample": cpu_desc},
                 "workspace_gb": eng.workspace_bytes / 1e9}
         emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# --workload noise: BASELINE.json configs[4] (alpha-stable noise sweep, 1M - 1B draws, 1/2/4/8 GPUs vs the HBM roofline)
+# ------------------------------------------------------------------------------------------------------------------
+def run_noise(args, rank, local_rank, world):
+    """Independent shards: rank r fills its own buffer with the variates of the GLOBAL samples [r * n_outer, (r+1) * n_outer)
+    (sample_base), no collective on the data path; every number is the MAX over ranks of the device-timed mean launch."""
+    import torch
+    import torch.distributed as dist
+    import dlpm_b200
+    from dlpm_b200 import _lib
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    pk, pk_src = peaks()
+    hbm_peak = float(pk["hbm_gbs"])
+    inner = 3072
+    seed = 1234
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def fill(buf, mode, alpha, outer, base):
+        if mode == "A_per_element":
+            _lib.call("dlpm_b200_stable_A", _lib.ptr(buf), outer, inner, 2, alpha, -1.0, seed, 2, base, _lib.stream_ptr())
+        else:
+            _lib.call("dlpm_b200_sas", _lib.ptr(buf), None, outer, inner, 1 if mode == "sas_isotropic" else 0, alpha, -1.0, 1.0, seed, 2,
+                      base, _lib.stream_ptr())
+
+    def timed(mode, alpha, logn, launches):
+        outer = (1 << logn) // inner
+        n = outer * inner
+        # two buffers when they fit comfortably (a 2^30 fill is 4 GB: far beyond L2 by itself)
+        bufs = [torch.empty(n, device=dev) for _ in range(2 if logn <= 28 else 1)]
+        flush = torch.empty(64 << 20, device=dev) if logn < 26 else None  # small fills: flush L2 between launches instead
+        base = rank * outer
+        for b in bufs:
+            fill(b, mode, alpha, outer, base)  # warm-up
+        barrier()
+        tot = 0.0
+        if flush is not None:
+            for k in range(launches):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); fill(bufs[k % len(bufs)], mode, alpha, outer, base); b.record()
+                torch.cuda.synchronize()
+                tot += a.elapsed_time(b)
+        else:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for k in range(launches):
+                fill(bufs[k % len(bufs)], mode, alpha, outer, base)
+            b.record()
+            torch.cuda.synchronize()
+            tot = a.elapsed_time(b)
+        ms = torch.tensor([tot / launches], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ok = bool(torch.isfinite(bufs[0][: 1 << 16]).all())
+        del bufs, flush
+        return float(ms[0]), n, ok
+
+    for _ in range(max(args.warmup, 3)):
+        timed("sas_isotropic", ALPHA, 28, 2)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+        time.sleep(1.0)
+    clocks.mark()
+    ms_head, n_head, _ = timed("sas_isotropic", ALPHA, 30, max(args.steps, 5))
+    clk = clocks.stop() if rank == 0 else None
+    sweep = []
+    for alpha in (1.5, 1.7, 1.9, 2.0):
+        for logn in (20, 24, 28, 30):
+            row = {"alpha": alpha, "draws_per_gpu": ((1 << logn) // inner) * inner}
+            for mode in ("A_per_element", "sas_per_element", "sas_isotropic"):
+                ms, n, ok = timed(mode, alpha, logn, 3 if logn == 30 else 5)
+                row[mode] = {"ms": ms, "GB/s": world * 4 * n / ms / 1e6, "frac_per_gpu": 4 * n / ms / 1e6 / hbm_peak, "finite": ok}
+            sweep.append(row)
+    # end to end through the public API with a host destination (the reference's gen_sas returns a device tensor; its caller
+    # moves samples to the host): fill + pinned D2H, 2^26 draws
+    n_e = ((1 << 26) // inner) * inner
+    host = torch.empty(n_e, dtype=torch.float32).pin_memory()
+    dlpm_b200.manual_seed(seed)
+
+    def e2e_once():
+        x = dlpm_b200.gen_sas(ALPHA, (n_e // inner, inner), device=dev, isotropic=True)
+        host.copy_(x.view(-1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e2e_once()
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(3):
+        e2e_once()
+    barrier()
+    e2e_ms = torch.tensor([(time.perf_counter() - w0) / 3 * 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        value = world * 4 * n_head / ms_head / 1e6
+        cpu = None
+        try:
+            from oracle import ref_import
+            if ref_import.available():
+                import numpy as np
+                ns = ref_import.load()
+                np.random.seed(0)
+                t0 = time.perf_counter()
+                n_cpu = 1 << 20
+                ns.Distributions.gen_sas(ALPHA, (n_cpu // inner, inner), device="cpu", isotropic=False)
+                dt = time.perf_counter() - t0
+                cpu = {"value": 4 * n_cpu / dt / 1e9, "unit": "GB/s", "cores": 1, "kind": "reference", "source": reference_source(),
+                       "sample": "bem/datasets/Distributions.py gen_sas(alpha=1.7, isotropic=False) of the unmodified reference, 2^20 draws "
+                                 "(scipy levy_stable.rvs, single-threaded) in %.2f s" % dt}
+        except Exception as e:
+            cpu = {"unavailable": "%s: %s" % (type(e).__name__, e)}
+        emit({"metric": "alpha-stable noise GB/s (isotropic SaS fill, alpha=1.7, 2^30 draws per GPU)", "value": value, "unit": "GB/s",
+              "n_gpus": world, "steps": max(args.steps, 5), "warmup": max(args.warmup, 3), "ms_per_step": ms_head, "higher_is_better": True,
+              "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+              "config": {"workload": "BASELINE.json configs[4]: alpha-stable noise sweep alpha in {1.5,1.7,1.9,2.0}, 2^20..2^30 draws per GPU, "
+                                     "modes A per element / SaS per element / SaS isotropic (inner 3072); independent shards per GPU",
+                         "generator": "Philox4x32-%d" % _lib.load().dlpm_b200_philox_rounds(),
+                         "l2_note": "fills >= 2^26 draws exceed L2 by themselves; smaller fills flush L2 between launches"},
+              "roofline": {"bound": "hbm", "kernel": "k_sas_vec (isotropic SaS fill)", "achieved": 4 * n_head / ms_head / 1e6, "peak": hbm_peak,
+                           "unit": "GB/s", "frac": 4 * n_head / ms_head / 1e6 / hbm_peak, "traffic": None,
+                           "peak_source": "MEASURED_PEAKS.json hbm_gbs (%s)" % pk_src},
+              "e2e": {"value": world * 4 * n_e / float(e2e_ms[0]) / 1e6, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4 * n_e * world,
+                      "api": "dlpm_b200.gen_sas(...) + pinned D2H of the tensor (PCIe-bound)"},
+              "gpu_launches": int(world * (max(args.steps, 5) + 2)), "clocks": clk, "cpu_baseline": cpu, "sweep": sweep})
     if world > 1:
         dist.destroy_process_group()
 
@@ -377,6 +545,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="sampling", choices=["sampling", "noise"])  # noise = BASELINE.json configs[4]
     ap.add_argument("--batch-per-gpu", type=int, default=512)
     ap.add_argument("--reverse-steps", type=int, default=T_STEPS)
     ap.add_argument("--e2e-steps", type=int, default=2)  # two passes: one pass alone carries the +-3 % power-cap jitter
@@ -403,7 +572,10 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus), "--master-addr",
                "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd, stdout=_JSON_OUT))
-    run_ours(args, rank, local_rank, world)
+    if args.workload == "noise":
+        run_noise(args, rank, local_rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
 
 
 if __name__ == "__main__":

@@ -83,6 +83,7 @@ class GenerationManager:
         self.kwargs = kwargs
         self.samples = []
         self.history = []
+        self.device_samples = None  # the post-processed samples on the device (multi-GPU callers gather these)
         self._pinned = None
 
     def _data_shape(self):
@@ -118,6 +119,7 @@ class GenerationManager:
         x = self.method.sample(shape=size, models=models, print_progression=print_progression, get_sample_history=False,
                                postprocess=post, **tmp_kwargs)
         out = post.out if post.out is not None else post.run_standalone(x)
+        self.device_samples = out
         out = out[..., :last]  # "select positions in case of pdmp" (:56); a no-op for the DLPM / LIM methods
         if not out.is_contiguous():
             out = out.contiguous()
