@@ -77,9 +77,10 @@ def test_reference_unet_instance_through_sample_and_in_place_weight_updates():
 
 def test_reference_mlp_instance_through_sample_t1000():
     """C1 at full length: T = 1000 free-running chain of the 2-D MLP (fp32), B = 16, reference MLPModel INSTANCE ingested,
-    against the live reference (CPU fp32) on identical injected noise.  The per-step bar is rtol 1e-3; the final sample of
-    999 amplifying steps is asserted at the measured bound (two fp32 implementations of the reference itself differ by as
-    much, see gpurun_out/chain_growth_mlp.json)."""
+    against the live reference (CPU fp32) on identical injected noise.  The north star's fp32 bar (rtol 1e-3) is asserted on
+    the FINAL sample of the 999 free-running steps and along the way (measured: 6e-8 ... 1.3e-7 of the history's scale at
+    every checkpoint, gpurun_out/chain_growth_mlp.json -- the explicit round-to-nearest arithmetic in the reference's
+    evaluation order does not drift)."""
     from dlpm_b200 import GenerativeLevyProcess
     from oracle import ref_live
     alpha, T, shape = 1.7, 1000, (16, 1, 2)
@@ -94,9 +95,9 @@ def test_reference_mlp_instance_through_sample_t1000():
     growth = {int(k): float((h[k] - hist[k]).abs().max() / hist[k].abs().max()) for k in (1, 10, 50, 200, 500, 999)}
     with open(os.path.join(out_dir(), "chain_growth_mlp.json"), "w") as fh:
         json.dump({"config": "MLP 2-D, alpha 1.7, T 1000, B 16, fp32", "rel_err_vs_reference_history": growth, "scale": scale}, fh)
-    assert growth[1] < 1e-4 and growth[10] < 1e-3, growth
-    np.testing.assert_allclose(h[-1].numpy(), hist[-1].numpy(), rtol=2e-2, atol=2e-3 * scale, err_msg=str(growth))
-    assert growth[999] < 2e-2, growth
+    assert max(growth.values()) < 1e-4, growth
+    np.testing.assert_allclose(h[-1].numpy(), hist[-1].numpy(), rtol=1e-3, atol=1e-5 * scale, err_msg=str(growth))
+    np.testing.assert_allclose(final.cpu().numpy(), hist[-1].numpy(), rtol=1e-3, atol=1e-5 * scale)
 
 
 def test_checkpoint_roundtrip_reference_format(tmp_path):
@@ -263,12 +264,13 @@ def test_graph_sample_caches_the_executable_graph():
     glp.sample({"default": m}, shape, reverse_steps=7, clamp_a=20, clamp_eps=200)
     inst2, _ = _unet_lib.graph_stats(m.engine(32, 32, 4))
     assert inst2 == 1
-    # LIM loops share the engine's cache; the step kernel differs -> one re-instantiation, then updates
+    # LIM loops share the engine's cache: same chain topology, another step kernel -- cudaGraphExecUpdate may swap a kernel
+    # node's function, so even this is an in-place update (measured on B200 / CUDA 12.9; a re-instantiation would be legal)
     lim = GenerativeLevyProcess(1.7, "cuda", 10, rescale_timesteps=True, isotropic=True, LIM=True)
     for _ in range(2):
         lim.sample({"default": m}, shape, reverse_steps=10, clamp_eps=200)
-    inst3, _ = _unet_lib.graph_stats(m.engine(32, 32, 4))
-    assert inst3 == 2, inst3
+    inst3, upd3 = _unet_lib.graph_stats(m.engine(32, 32, 4))
+    assert inst3 in (1, 2) and inst3 + upd3 == 6, (inst3, upd3)
 
 
 # ------------------------------------------------------------------------------------------------------------------
