@@ -98,16 +98,8 @@ __device__ __forceinline__ float sqrt_approx(float x) {
 }
 
 // two N(0,1) from two 32-bit words (Box-Muller: lg2 + sqrt + sin + cos = 4 MUFU ops per pair).
-// Radius uniform WITHOUT an int -> float conversion (I2F runs on the XU pipe next to the four MUFU ops; with it the XU
-// pipe, 8 cycles per warp instruction, was the tightest resource of the normal fill: profiles/r02_noise.md):
-//   k = x >> 9 (23 bits),  u = 1 - k 2^-23 = 2 - as_float(0x3f800000 | k)  in [2^-23, 1]   (exact, ALU + one FADD)
-// and the LAST lattice point (k = 2^23 - 1, probability 2^-23) is refined with the 9 low bits, u = (j + 1/2) 2^-32, so
-// the radius still reaches sqrt(-2 ln 2^-33) = 6.76 as on a full 32-bit lattice (a divergent branch taken by one warp in
-// 2^18; oracle/philox.py::normal_from_words restates both cases).
 __device__ __forceinline__ float2 box_muller(uint32_t x, uint32_t y) {
-  float u = 2.0f - __uint_as_float((x >> 9) | 0x3f800000u);
-  if (u == 1.1920928955078125e-07f) u = ((float)(x & 511u) + 0.5f) * 2.3283064365386963e-10f;
-  const float r = sqrt_approx(-1.3862943611198906f * lg2_ftz(u));  // sqrt(-2 ln u), ln u = ln2 * lg2 u
+  const float r = sqrt_approx(-1.3862943611198906f * lg2_ftz(u01(x)));  // sqrt(-2 ln u), ln u = ln2 * lg2 u
   float s, c;
   // angle 2 pi m with m in [1, 2): one turn ahead of 2 pi (m - 1), same sine / cosine, saves the subtraction
   __sincosf(6.28318530717958647692f * __uint_as_float((y >> 9) | 0x3f800000u), &s, &c);

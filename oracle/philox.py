@@ -74,12 +74,9 @@ def stable_A_from_words(alpha, xu, xw, clamp_a=None):
 
 
 def normal_from_words(x, y):
-    """rng.cuh::box_muller: radius uniform u = 1 - (x >> 9) 2^-23 (the last lattice point refined by the 9 low bits to
-    (j + 1/2) 2^-32), angle 2 pi (y >> 9) / 2^23.  Returns (z0, z1)."""
-    x = np.asarray(x, dtype=np.uint32)
-    k = (x >> np.uint32(9)).astype(np.float64)
-    u = 1.0 - k * 2.0 ** -23
-    u = np.where(k == 2.0 ** 23 - 1, ((x & np.uint32(511)).astype(np.float64) + 0.5) * 2.0 ** -32, u)
+    """rng.cuh::box_muller: radius from the 32-bit lattice uniform of x, angle 2 pi (y >> 9) / 2^23.  Returns (z0, z1)."""
+    xf = np.asarray(x, dtype=np.uint32).astype(np.float32)
+    u = ((xf + np.float32(0.5)) * np.float32(2.0 ** -32)).astype(np.float64)
     r = np.sqrt(-2.0 * np.log(u))
     ang = 2.0 * np.pi * (np.asarray(y, dtype=np.uint32) >> np.uint32(9)).astype(np.float64) / 2.0 ** 23
     return r * np.cos(ang), r * np.sin(ang)

@@ -318,7 +318,8 @@ def test_training_losses_autograd_and_native_guard():
     x0 = torch.randn(64, 1, 2, generator=torch.Generator().manual_seed(0)).cuda()
     ref = ref_live.make_mlp("cuda", seed=0)
     ref.train()
-    loss = glp.training_losses({"default": ref}, x0)["loss"]
+    kw = dict(loss_type="EPS_LOSS")  # p['training']['dlpm'] of every shipped config (dlpm/configs/*.yml: loss_type: EPS_LOSS)
+    loss = glp.training_losses({"default": ref}, x0, **kw)["loss"]
     assert loss.requires_grad
     loss.backward()
     grads = [p.grad for p in ref.parameters() if p.grad is not None]
@@ -327,10 +328,10 @@ def test_training_losses_autograd_and_native_guard():
     inj = dict(t=torch.randint(1, 100, (64,), generator=torch.Generator().manual_seed(1)),
                A=torch.rand(64, generator=torch.Generator().manual_seed(2)) * 3 + 0.1,
                z=torch.randn(64, 1, 2, generator=torch.Generator().manual_seed(3)))
-    l_train = glp.training_losses({"default": ref}, x0, injected=inj)["loss"]
+    l_train = glp.training_losses({"default": ref}, x0, injected=inj, **kw)["loss"]
     ref.eval()
     with torch.no_grad():
-        l_eval = glp.training_losses({"default": ref}, x0, injected=inj)["loss"]
+        l_eval = glp.training_losses({"default": ref}, x0, injected=inj, **kw)["loss"]
     assert not l_eval.requires_grad
     np.testing.assert_allclose(float(l_train), float(l_eval), rtol=1e-4)
     # native mirror in train() mode under autograd: loud, documented error
@@ -338,9 +339,9 @@ def test_training_losses_autograd_and_native_guard():
     native.load_state_dict(ref.state_dict())
     native.train()
     with pytest.raises(NotImplementedError, match="forward-only"):
-        glp.training_losses({"default": native}, x0)
+        glp.training_losses({"default": native}, x0, **kw)
     with torch.no_grad():
-        l_native = glp.training_losses({"default": native}, x0, injected=inj)["loss"]
+        l_native = glp.training_losses({"default": native}, x0, injected=inj, **kw)["loss"]
     np.testing.assert_allclose(float(l_native), float(l_eval), rtol=1e-4)
     # LIM loss through a torch module
     lim = GenerativeLevyProcess(1.7, "cuda", 100, rescale_timesteps=True, isotropic=True, LIM=True)
@@ -358,8 +359,9 @@ def test_unet_t1000_free_running_against_live_reference(name, cfg):
     """C3's length: 999 UNet evaluations, B = 2, identical injected A / x_T / z for (i) the reference in strict fp32 on
     this GPU, (ii) the reference as it really runs on a GPU (cuDNN TF32 convolutions, PyTorch's default), (iii) this
     package (bf16 activations, fp32 accumulation).  The error-growth curve of (ii) and (iii) against (i) is written to
-    gpurun_out/chain_growth_<name>.json; asserted: the first steps meet the per-step bf16 bar, and after 999 free-running
-    steps the bf16 path stays within the MEASURED bound stated in DESIGN.md section 2."""
+    gpurun_out/chain_growth_<name>.json.  Asserted at EVERY checkpoint including the final sample after 999 free-running
+    steps: the north star's bf16 bar, rtol 2e-2 (measured on B200: 2.3e-3 ... 3.1e-3 of the sample's scale from step 1 to
+    step 999 -- the chain contracts perturbations, the error does not grow; the reference's own TF32 path sits at 3e-4)."""
     from dlpm_b200 import GenerativeLevyProcess
     from oracle import ref_live
     alpha, T, shape = 1.7, 1000, (2, 3, 32, 32)
@@ -380,10 +382,11 @@ def test_unet_t1000_free_running_against_live_reference(name, cfg):
         growth["rms_bf16_vs_fp32"][k] = float(((h[k] - h32[k]) ** 2).mean().sqrt() / (h32[k] ** 2).mean().sqrt())
     with open(os.path.join(out_dir(), "chain_growth_%s.json" % name), "w") as fh:
         json.dump({"config": "%s UNet, alpha 1.7, T 1000, B 2, injected noise" % name, "history_index": list(marks), **growth}, fh)
-    assert growth["bf16_vs_fp32"][1] < 2e-2 and growth["bf16_vs_fp32"][10] < 2e-2, growth
     assert torch.isfinite(h).all()
-    assert growth["rms_bf16_vs_fp32"][999] < 0.25, growth
-    np.testing.assert_allclose(h[999].numpy(), h32[999].numpy(), rtol=0.0, atol=0.5 * float(h32[999].abs().max()), err_msg=str(growth))
+    assert max(growth["bf16_vs_fp32"].values()) < 2e-2, growth
+    assert max(growth["rms_bf16_vs_fp32"].values()) < 1e-2, growth
+    for k in marks:
+        np.testing.assert_allclose(h[k].numpy(), h32[k].numpy(), rtol=2e-2, atol=2e-2 * float(h32[k].abs().max()), err_msg="history index %d" % k)
 
 
 def test_full_width_per_sample_t_teacher_forced_chain_and_elementwise():
