@@ -12,6 +12,8 @@ UNET_SIGNATURES = {
                          c_int, c_int, c_vp],
     "dlpm_b200_conv2d_stats": [c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_int, c_i64, c_int, c_int, c_int, c_int,
                                c_int, c_int, c_vp, ctypes.POINTER(c_int), c_vp],
+    "dlpm_b200_conv2d_post": [c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_vp,
+                              ctypes.POINTER(c_int), c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_i64, c_i64, c_int, c_vp],
     "dlpm_b200_groupnorm_from_stats": [c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_int, c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp,
                                        c_int, c_i64, c_i64, c_int, c_vp],
     "dlpm_b200_groupnorm_fold": [c_vp, c_int, c_vp, c_int, c_int, c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_int, c_i64, c_i64,

@@ -33,13 +33,28 @@ constexpr int kConvThreadsEpi2 = 384;  // + warps 8-11: a second epilogue warp p
                                        // one-chunk tiles, N <= 32 -- the two sub-tiles of the work item)
 constexpr int kConvThreadsXF = 512;  // + warps 8-15: the eight transform warps (two per SM sub-partition)
 constexpr int kXfWarps = 8;
+constexpr int kConvThreadsPost = 512;  // POST kernels: warps 12-15 normalise finished samples ("GroupNorm in the producer's tail")
+constexpr int kPostThreads = 128;
+constexpr int kPostSmemBytes = 4 * 8 + 16 + 64 * 2 * 4;  // ready[2] / free[2] barriers + per-quad (sum, sum of squares) of one sample
 constexpr int kSmemBudget = 204 * 1024;  // operand ring; epilogue staging, barriers, bias and alignment slack come on top (227 KB per CTA)
 constexpr int kEpiStageBytes = 2048;     // per epilogue warp: one 32-pixel x 32-channel bf16 chunk (64-byte rows, SWIZZLE_64B) for TMA stores
 constexpr int kEpiStageTotal = 8 * kEpiStageBytes;
 constexpr int kBiasSmemFloats = 1024;    // the layer's bias vector lives in shared memory: with the whole carve-out given to shared
                                          // memory there is no L1 left and every bias load of every chunk went to L2
 constexpr int kSmemExtra = 1024 /*base alignment*/ + 1024 /*staging alignment*/ + kEpiStageTotal + (4 * kMaxStages + 4) * 8 + 16 +
-                           kBiasSmemFloats * 4;
+                           kBiasSmemFloats * 4 + kPostSmemBytes;
+
+// POST: one GroupNorm (+ scale-shift, + SiLU) that consumes this convolution's output, evaluated by the convolution itself.
+// dst is the consumer's NORMALISED input tensor (NHWC bf16, dst_C channels per pixel); this convolution's channel c lands at
+// dst channel c_off + c (c_off > 0: second half of a skip concatenation).  cpg = channels per group of the CONSUMER's
+// GroupNorm ((C0 + C1) / 32); gamma / beta / ss_off index the consumer's channels.
+struct PostTarget {
+  __nv_bfloat16* dst;
+  const float* gamma;
+  const float* beta;
+  int64_t ss_off;   // scale at ss[row][ss_off + ch], shift at ss[row][ss_off + dst_C + ch]; < 0: no scale-shift
+  int dst_C, c_off, cpg, silu;
+};
 
 struct ConvKParams {
   int n_m_tiles, n_n_tiles, stages;
@@ -63,7 +78,48 @@ struct ConvKParams {
   int stats_parts, units_per_img, stats_wpi;  // rows per image, work units per image, epilogue warps per image and unit
   FastDiv fd_ipp, fd_nnt, fd_tpi;  // multiply-high division by items_per_par / n_n_tiles / tiles_per_img: the per-item index math of
                                    // the producer and epilogue warps sits on the critical path of short-K work items
+  // POST kernels
+  int post_n;             // targets (1 or 2)
+  int ipu_log;            // Nb == 1: log2(work items per sample) -- every CTA walks WHOLE samples (unit = CG samples x one N tile)
+  int n_units;            // Nb == 1: ceil(B / CG) * n_n_tiles
+  int stats_half;         // 4x4 maps: a warp's 32 tile rows are two images, statistics are reduced per half warp
+  const float* ss;        // time-embedding scale / shift table [ss_rows][ss_stride] (unet_ops.cu: k_gemv_rows)
+  int ss_rows;
+  int64_t ss_stride;
+  PostTarget post[2];
 };
+
+// Coordinates of the it-th work item of a CTA (pair).  Default walk: item = first + it * stride over (parity, M group, N tile).
+// POST kernels on maps of >= 128 pixels walk sample-major instead: CTA r of a pair owns sample (unit * CG + r) and runs its
+// ipu = tiles_per_img / msub items back to back, so a sample's output (and its GroupNorm statistics) is complete -- and still
+// L2-resident -- on ONE CTA when its last accumulator has been drained.
+struct ItemCoord { int par, nt, mt, n0, h0; };
+template <int CG, bool POST>
+__device__ __forceinline__ bool item_coord(const ConvKParams& p, int it, int first, int stride, int cta_rank, int msub, int items_per_par,
+                                           int n_items, ItemCoord& c) {
+  if (POST && p.Nb == 1) {
+    const int su = it >> p.ipu_log, j = it - (su << p.ipu_log);
+    const int gu = first + su * stride;
+    if (gu >= p.n_units) return false;
+    const int sp = (int)p.fd_nnt.div((uint32_t)gu);
+    c.par = 0;
+    c.nt = gu - sp * p.n_n_tiles;
+    c.n0 = sp * CG + cta_rank;
+    c.h0 = j * msub * p.Hb;
+    c.mt = c.n0 * p.tiles_per_img + j * msub;
+    return true;
+  }
+  const int item = first + it * stride;
+  if (item >= n_items) return false;
+  c.par = (int)p.fd_ipp.div((uint32_t)item);
+  const int it_in = item - c.par * items_per_par;
+  const int mg = (int)p.fd_nnt.div((uint32_t)it_in);
+  c.nt = it_in - mg * p.n_n_tiles;
+  c.mt = (mg * CG + cta_rank) * msub;
+  if (p.Nb == 1) { c.n0 = (int)p.fd_tpi.div((uint32_t)c.mt); c.h0 = (c.mt - c.n0 * p.tiles_per_img) * p.Hb; }
+  else { c.n0 = c.mt * p.Nb; c.h0 = 0; }
+  return true;
+}
 
 // CG = 1: one CTA per 128-pixel tile.  CG = 2: a CTA PAIR (cluster of 2 on one TPC) computes two adjacent 128-pixel
 // tiles with tcgen05.mma.cta_group::2 (M = 256): each CTA stages its own 128 activation rows and only HALF of the weight
@@ -96,13 +152,37 @@ __device__ __forceinline__ void tall_slot(int sb, int n_main, int n_skip, bool i
   idx = is_skip ? before : sb - before;
 }
 
+// y = silu(a x + b) (coefficients pre-halved: silu(y) = h + h tanh(h) with h = y / 2, ONE MUFU op) or a x + b, on eight bf16
+__device__ __forceinline__ uint4 post_apply8(const uint4& raw, const float (&a)[8], const float (&b)[8], int silu) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(&raw);
+  uint4 o;
+  uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float y0 = fmaf(__uint_as_float(w[e] << 16), a[2 * e], b[2 * e]);
+    float y1 = fmaf(__uint_as_float(w[e] & 0xffff0000u), a[2 * e + 1], b[2 * e + 1]);
+    if (silu) {
+      float t0, t1;
+      asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(y0));
+      asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(y1));
+      y0 = fmaf(y0, t0, y0);
+      y1 = fmaf(y1, t1, y1);
+    }
+    const __nv_bfloat162 pk = __floats2bfloat162_rn(y0, y1);
+    ow[e] = *reinterpret_cast<const uint32_t*>(&pk);
+  }
+  return o;
+}
+
 template <int BLOCK_N, bool XF>
 __host__ __device__ constexpr int conv_epi_groups() { return XF ? 1 : 2; }
-template <int BLOCK_N, bool XF>
-__host__ __device__ constexpr int conv_threads() { return XF ? kConvThreadsXF : (conv_epi_groups<BLOCK_N, XF>() == 2 ? kConvThreadsEpi2 : kConvThreads); }
+template <int BLOCK_N, bool XF, bool POST = false>
+__host__ __device__ constexpr int conv_threads() {
+  return XF ? kConvThreadsXF : (POST ? kConvThreadsPost : (conv_epi_groups<BLOCK_N, XF>() == 2 ? kConvThreadsEpi2 : kConvThreads));
+}
 
-template <int BLOCK_N, int BLOCK_K, int CG, int KS, bool XF>
-__global__ void __launch_bounds__(conv_threads<BLOCK_N, XF>(), 1)
+template <int BLOCK_N, int BLOCK_K, int CG, int KS, bool XF, bool POST>
+__global__ void __launch_bounds__(conv_threads<BLOCK_N, XF, POST>(), 1)
 k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmS0,
           const __grid_constant__ CUtensorMap tmS1, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
           const ConvKParams p) {
@@ -125,6 +205,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   // Tiles with a single chunk (N <= 32: the 32-channel layers of the MNIST network, the final conv) split the work item's
   // two SUB-TILES instead.
   constexpr int EG = conv_epi_groups<BLOCK_N, XF>();
+  static_assert(!(XF && POST), "normalise-on-load and the producer-side GroupNorm are alternatives");
+  static_assert(!POST || (BLOCK_N >= 128 && EG == 2), "POST kernels: N tiles of 128 / 256 channels");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -137,6 +219,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);  // 16-byte aligned (the barrier block is a multiple of 16 bytes)
+  uint64_t* ready_bar = reinterpret_cast<uint64_t*>(s_bias + kBiasSmemFloats);  // POST: "sample complete" (epilogue -> post warps), 2 slots
+  uint64_t* free_bar = ready_bar + 2;                                            // POST: slot consumed (post warps -> epilogue)
+  float* s_pq = reinterpret_cast<float*>(free_bar + 2);                          // POST: [BLOCK_N / 4][2] quad sums of the sample in flight
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // provably warp-uniform (see tc::elect_one)
   const int lane = threadIdx.x & 31;
@@ -150,6 +235,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const int items_per_par = m_groups * p.n_n_tiles;
   const int n_items = items_per_par * p.n_par;
   const int first_item = blockIdx.x / CG, item_stride = gridDim.x / CG;
+  // POST: work items per completion unit (a CTA's tile holds whole samples when Nb > 1; else ipu items make one sample)
+  const int ipu_log = (POST && p.Nb == 1) ? p.ipu_log : 0;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -166,6 +253,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       if (XF) { mbar_init(fullA_bar + s, 1); mbar_init(xf_bar + s, kXfWarps * CG); }
     }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar + a, 1); mbar_init(tempty_bar + a, 4 * EG * CG); }
+    if (POST) {
+      for (int a = 0; a < 2; ++a) { mbar_init(ready_bar + a, (uint32_t)(4 * EG) << ipu_log); mbar_init(free_bar + a, 1); }
+    }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -186,18 +276,17 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     {
       const bool elected = elect_one();
       int stage = 0; uint32_t phase = 0;
-      for (int item = first_item; item < n_items; item += item_stride) {
-        const int par = (int)p.fd_ipp.div((uint32_t)item), it_in = item - par * items_per_par;
-        const int mg = (int)p.fd_nnt.div((uint32_t)it_in), nt = it_in - mg * p.n_n_tiles, mt = (mg * CG + (int)cta_rank) * msub;
+      for (int it = 0;; ++it) {
+        ItemCoord ic;
+        if (!item_coord<CG, POST>(p, it, first_item, item_stride, (int)cta_rank, msub, items_per_par, n_items, ic)) break;
+        const int item = first_item + it * item_stride;  // (default walk only: used by the optional L2 prefetch)
+        const int par = ic.par, nt = ic.nt, n0 = ic.n0, h0 = ic.h0;
         const int dy_base = p.dy0 + (p.n_par == 4 ? (par >> 1) : 0), dx_base = p.dx0 + (p.n_par == 4 ? (par & 1) : 0);
         const int brow0 = par * p.c_out_pad + nt * BLOCK_N + (int)cta_rank * B_ROWS;
-        int n0, h0;
-        if (p.Nb == 1) { n0 = (int)p.fd_tpi.div((uint32_t)mt); h0 = (mt - n0 * p.tiles_per_img) * p.Hb; }
-        else { n0 = mt * p.Nb; h0 = 0; }
         if (p.tall) {
           const int a_tall_bytes = (msub * p.Hb + 2) * p.Wb * BLOCK_K * 2;
           const int n_sb = 3 * p.cin_blocks + p.s0_blocks + p.s1_blocks;
-          if (p.l2_prefetch && item + item_stride < n_items) {
+          if (!POST && p.l2_prefetch && item + item_stride < n_items) {
             // pull the NEXT work item's activation boxes from HBM into L2 now: its TMA loads then see L2 latency only
             const int it2 = (item + item_stride) % items_per_par;
             const int mt2 = ((it2 / p.n_n_tiles) * CG + (int)cta_rank) * msub;
@@ -300,8 +389,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     if (leader) {
       const bool elected = elect_one();
       int stage = 0; uint32_t phase = 0;
-      int it = 0;
-      for (int item = first_item; item < n_items; item += item_stride, ++it) {
+      for (int it = 0;; ++it) {
+        ItemCoord ic;
+        if (!item_coord<CG, POST>(p, it, first_item, item_stride, (int)cta_rank, msub, items_per_par, n_items, ic)) break;
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(tempty_bar + acc, acc_phase ^ 1);  // epilogues (of both CTAs) have drained this accumulator stage
@@ -398,10 +488,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int x_base = (rl & (p.Wb - 1)) - 1, y_step = 32 >> wshift;
     const uint32_t row_off = (uint32_t)(rl * 128 + ((chunk ^ (rl & 7)) << 4));
     int stage = 0; uint32_t phase = 0;
-    for (int item = first_item; item < n_items; item += item_stride) {
-      const int it_in = item % items_per_par;
-      const int mt = ((it_in / p.n_n_tiles) * CG + (int)cta_rank) * msub;
-      const int n0 = mt / p.tiles_per_img, h0 = (mt - n0 * p.tiles_per_img) * p.Hb;
+    for (int it = 0;; ++it) {
+      ItemCoord ic;
+      if (!item_coord<CG, false>(p, it, first_item, item_stride, (int)cta_rank, msub, items_per_par, n_items, ic)) break;
+      const int n0 = ic.n0, h0 = ic.h0;
       const float4* ab_row = reinterpret_cast<const float4*>(p.ab + (int64_t)(n0 < p.B ? n0 : p.B - 1) * p.c_in_total);
       const int y_first = h0 - 1 + (rl >> wshift);
       for (int sb = 0; sb < n_sb; ++sb) {
@@ -465,14 +555,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const uint32_t my_row = my_stage + (uint32_t)lane * 64u;
     const int m0 = q * 32;  // first tile row of this warp: coordinates of the store box
     const int w_box = m0 % p.Wb, h_box = (m0 / p.Wb) % p.Hb, n_box = m0 / (p.Wb * p.Hb);
-    int it = 0;
-    for (int item = first_item; item < n_items; item += item_stride, ++it) {
-      const int par = (int)p.fd_ipp.div((uint32_t)item), it_in = item - par * items_per_par;
-      const int mg = (int)p.fd_nnt.div((uint32_t)it_in), nt = it_in - mg * p.n_n_tiles, mt = (mg * CG + (int)cta_rank) * msub;
+    for (int it = 0;; ++it) {
+      ItemCoord ic;
+      if (!item_coord<CG, POST>(p, it, first_item, item_stride, (int)cta_rank, msub, items_per_par, n_items, ic)) break;
+      const int par = ic.par, nt = ic.nt, mt = ic.mt, n0 = ic.n0, h0 = ic.h0;
       const int out_oy = p.n_par == 4 ? (par >> 1) : p.out_oy, out_ox = p.n_par == 4 ? (par & 1) : p.out_ox;
-      int n0, h0;
-      if (p.Nb == 1) { n0 = (int)p.fd_tpi.div((uint32_t)mt); h0 = (mt - n0 * p.tiles_per_img) * p.Hb; }
-      else { n0 = mt * p.Nb; h0 = 0; }
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int64_t nn = (int64_t)n0 + n_in;
@@ -481,7 +568,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       if (p.out_mode == CONV_OUT_BF16_NHWC) {
         constexpr int CH = BLOCK_N >= 32 ? 32 : 16;
         // identity-skip rows are fetched BEFORE waiting for the accumulator so their HBM latency hides behind the MMAs
-        constexpr bool RES_PREFETCH = !XF;  // XF kernels run 512 threads (128 registers each): residual rows are read in place
+        constexpr bool RES_PREFETCH = !XF && !POST;  // XF / POST kernels run 512 threads (128 registers each): residual rows are read in place
         constexpr int NCH = BLOCK_N / CH;  // column chunks of the tile; this warp owns chunks eg, eg + EG, ...
         constexpr bool SPLIT_SUB = NCH < EG;            // ... or, one-chunk tiles: sub-tiles eg, eg + EG, ... of the work item
         constexpr int CPW = SPLIT_SUB ? NCH : NCH / EG;  // chunks per warp
@@ -578,7 +665,24 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
           }
           if constexpr (CH == 32) {
-            if (!SPLIT_SUB && p.stats != nullptr) {  // warp-uniform (so is valid: a warp's 32 pixels belong to one image)
+            if (!SPLIT_SUB && p.stats != nullptr && p.stats_half) {
+              // 4x4 maps: the warp's 32 tile rows are TWO images of 16 pixels -- the same transposing butterfly inside each
+              // half warp (8+4+2+1 shuffles): lane l ends with the total of value l & 15 over its image
+#pragma unroll
+              for (int half = 8, off = 8; half >= 1; half >>= 1, off >>= 1) {
+                const bool up = (lane & off) != 0;
+#pragma unroll
+                for (int k = 0; k < half; ++k) {
+                  const float send = up ? st[k] : st[k + half];
+                  const float keep = up ? st[k + half] : st[k];
+                  st[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+              }
+              if (do_stats) {
+                const int64_t row = nn * p.stats_parts + par;
+                p.stats[(row * (p.C_out >> 2) + ((nt * BLOCK_N + c0) >> 2)) * 2 + (lane & 15)] = st[0];
+              }
+            } else if (!SPLIT_SUB && p.stats != nullptr) {  // warp-uniform (so is valid: a warp's 32 pixels belong to one image)
               // transposing butterfly: 16 values over 32 lanes in 8+4+2+1+1 shuffles; lane l ends with the total of value l>>1
 #pragma unroll
               for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
@@ -628,6 +732,96 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (CG == 2) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(tempty_bar + acc), 0));
         else mbar_arrive(tempty_bar + acc);
       }
+      if (POST) {
+        // this warp's share of the item is in global memory: raw bf16 rows (TMA stores: wait for the bulk group to COMPLETE,
+        // not only for its shared-memory reads) and the statistics rows (plain stores of the lanes, ordered by __syncwarp
+        // above + the release of the arrive).  One arrival per warp and item on the unit's "sample complete" barrier; the
+        // slot is handed back by the post warps (at most two units in flight).
+        const int su = it >> ipu_log, slot = su & 1;
+        if (lane == 0) {
+          if (p.tma_store) { bulk_wait0(); fence_proxy_async_all(); }
+          if ((it & ((1 << ipu_log) - 1)) == 0) mbar_wait(free_bar + slot, ((su >> 1) & 1) ^ 1);
+          mbar_arrive(ready_bar + slot);
+        }
+      }
+    }
+  } else if (POST && warp >= 12) {
+    // ===================== post warps: GroupNorm (+ scale-shift, SiLU) of finished samples =====================
+    // "GroupNorm in the producer's tail": the GroupNorms that consume this convolution's output (unet.py:141,153,188-191,
+    // 212,433) need whole-sample statistics, so they cannot sit in the per-tile epilogue -- but a CTA that walks whole
+    // samples can apply them as soon as the sample's last tile has been stored, while the raw rows are still in L2 and the
+    // tensor cores work on the next sample.  Replaces the separate k_gn_apply / k_groupnorm_cluster launches: the raw tensor
+    // is never re-read from HBM.  Thread t owns one 8-channel octet (fixed coefficients per sample) and every SLOTS-th pixel.
+    constexpr int OCT = BLOCK_N / 8, SLOTS = kPostThreads / OCT, NQ = BLOCK_N / 4;
+    const int pt = (warp - 12) * 32 + lane;
+    const int oct = pt % OCT, pslot = pt / OCT;
+    const int HWs = p.H_full * p.W_full;
+    const int cq = p.C_out >> 2;
+    for (int su = 0;; ++su) {
+      ItemCoord ic;
+      if (!item_coord<CG, POST>(p, su << ipu_log, first_item, item_stride, (int)cta_rank, msub, items_per_par, n_items, ic)) break;
+      mbar_wait(ready_bar + (su & 1), (su >> 1) & 1);
+      fence_proxy_async_all();
+      const int ch0 = ic.nt * BLOCK_N + oct * 8;  // first of this thread's eight conv output channels
+      for (int sI = 0; sI < p.Nb; ++sI) {
+        const int64_t n = (int64_t)ic.n0 + sI;
+        if (n >= p.B) break;
+        // (1) per-quad sums of the sample over its partial-statistics rows
+        asm volatile("bar.sync 2, %0;" ::"n"(kPostThreads) : "memory");
+        for (int qd = pt; qd < NQ; qd += kPostThreads) {
+          const float2* row = reinterpret_cast<const float2*>(p.stats) + (n * p.stats_parts) * cq + ic.nt * NQ + qd;
+          float sA = 0.f, qA = 0.f;
+          for (int r = 0; r < p.stats_parts; ++r) { const float2 v = __ldcg(row + (int64_t)r * cq); sA += v.x; qA += v.y; }
+          s_pq[2 * qd] = sA; s_pq[2 * qd + 1] = qA;
+        }
+        asm volatile("bar.sync 2, %0;" ::"n"(kPostThreads) : "memory");
+        for (int k = 0; k < p.post_n; ++k) {
+          const PostTarget& tg = p.post[k];
+          // (2) y = a x + b for this thread's channels: a = gamma rstd (1 + scale), b = (beta - mean gamma rstd)(1 + scale) + shift
+          float a[8], b[8];
+          const float* ssrow = tg.ss_off >= 0 ? p.ss + (p.ss_rows == 1 ? 0 : n * p.ss_stride) + tg.ss_off : nullptr;
+          const float inv_n = 1.0f / (float)(tg.cpg * HWs);
+          const float osc = tg.silu ? 0.5f : 1.0f;  // silu(y) = h + h tanh(h), h = y / 2
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int ct = tg.c_off + ch0 + 4 * h;             // consumer channel of this quad
+            const int g0 = (ct / tg.cpg) * tg.cpg - tg.c_off;  // first conv channel of its group (inside this N tile: host-checked)
+            const int lq0 = (g0 - ic.nt * BLOCK_N) >> 2;
+            float sA = 0.f, qA = 0.f;
+            for (int j = 0; j < (tg.cpg >> 2); ++j) { sA += s_pq[2 * (lq0 + j)]; qA += s_pq[2 * (lq0 + j) + 1]; }
+            const float mean = sA * inv_n;
+            const float rstd = rsqrtf(fmaxf(qA * inv_n - mean * mean, 0.f) + 1e-5f);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float ga = __ldg(tg.gamma + ct + e) * rstd;
+              float be = __ldg(tg.beta + ct + e) - mean * ga;
+              if (ssrow) {
+                const float sc = 1.0f + __ldg(ssrow + ct + e), sh = __ldg(ssrow + tg.dst_C + ct + e);
+                ga *= sc;
+                be = be * sc + sh;
+              }
+              a[4 * h + e] = ga * osc;
+              b[4 * h + e] = be * osc;
+            }
+          }
+          // (3) stream the sample: raw rows from L2 (ld.global.cg: written by this CTA a moment ago), normalised rows out
+          const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.out) + (n * HWs) * p.C_out + ch0);
+          uint4* dst = reinterpret_cast<uint4*>(tg.dst + (n * HWs) * tg.dst_C + tg.c_off + ch0);
+          const int sstr = p.C_out >> 3, dstr = tg.dst_C >> 3;  // row strides in 16-byte units
+          constexpr int U = 4;
+          int px = pslot;
+          for (; px + (U - 1) * SLOTS < HWs; px += U * SLOTS) {
+            uint4 raw[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) raw[u] = __ldcg(src + (int64_t)(px + u * SLOTS) * sstr);
+#pragma unroll
+            for (int u = 0; u < U; ++u) dst[(int64_t)(px + u * SLOTS) * dstr] = post_apply8(raw[u], a, b, tg.silu);
+          }
+          for (; px < HWs; px += SLOTS) dst[(int64_t)px * dstr] = post_apply8(__ldcg(src + (int64_t)px * sstr), a, b, tg.silu);
+        }
+      }
+      asm volatile("bar.sync 2, %0;" ::"n"(kPostThreads) : "memory");
+      if (pt == 0) mbar_arrive(free_bar + (su & 1));
     }
   }
   // the staging buffers must outlive the TMA engine's reads; the writes themselves are flushed by grid completion
@@ -804,6 +998,8 @@ int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, c
   const int64_t k_total = (int64_t)L->taps * C_in + C_s0 + C_s1;
   L->c_out_pad = C_out_pad;
   L->stats = nullptr;
+  L->post_n = 0;
+  L->ss = nullptr; L->ss_rows = 1; L->ss_stride = 0;
   if ((rc = encode_weight_map(&L->tmB, w, C_out_pad * L->n_par, k_total, bn / L->cta_group, bk))) return rc;
   // TMA-store epilogue: dense bf16 NHWC outputs with 32-channel chunks; an epilogue warp's 32 tile rows are a (bw, bh, bn) pixel box
   L->tmO = L->tmB;
@@ -823,8 +1019,39 @@ int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, c
 int conv_stats_parts(const ConvLaunch& L) {
   if (L.out_mode != CONV_OUT_BF16_NHWC || L.block_n < 64 || L.C_out % 4) return 0;  // one-chunk tiles split sub-tiles over the epilogue warps
   if (L.Nb == 1) return 4 * (L.tiles_per_img / L.msub) * L.n_par;
-  // several images per tile: every epilogue warp (32 pixels) must lie inside one image
+  // several images per tile: every epilogue warp (32 pixels) lies inside one image, or (4x4 maps) holds exactly two images
+  if (L.Wb * L.Hb == 16) return L.n_par;
   return (L.Wb * L.Hb) % 32 == 0 ? ((L.Wb * L.Hb) / 32) * L.n_par : 0;
+}
+
+bool conv_post_capable(const ConvLaunch& L) {
+  if (L.out_mode != CONV_OUT_BF16_NHWC || L.n_par != 1 || L.out_scale != 1 || L.xf || L.block_n < 128) return false;
+  if (conv_stats_parts(L) <= 0 || L.C_out % 8) return false;
+  if (L.Nb == 1) {
+    const int ipu = L.tiles_per_img / L.msub;
+    if (ipu < 1 || (ipu & (ipu - 1)) || ipu * L.msub != L.tiles_per_img) return false;
+  }
+  return true;
+}
+
+int conv_set_post(ConvLaunch* L, int n, const ConvLaunch::Post* targets, const float* ss, int64_t ss_stride) {
+  DLPM_REQUIRE(n >= 1 && n <= 2 && targets, "conv_set_post: 1 or 2 targets");
+  if (!conv_post_capable(*L)) { set_error("conv: this shape cannot apply the consumer's GroupNorm (N tile %d, out mode %d, parities %d)", L->block_n, L->out_mode, L->n_par); return DLPM_ERR_UNSUPPORTED; }
+  for (int k = 0; k < n; ++k) {
+    const ConvLaunch::Post& t = targets[k];
+    DLPM_REQUIRE(t.dst && t.gamma && t.beta, "conv_set_post: NULL target tensor");
+    if (t.cpg < 4 || t.cpg % 4 || L->block_n % t.cpg || t.c_off % t.cpg || t.c_off % 8 || t.dst_C % 8 || t.c_off + L->C_out > t.dst_C ||
+        (reinterpret_cast<uintptr_t>(t.dst) & 15u)) {
+      set_error("conv_set_post: group size %d / channel offset %d / row width %d do not fit N tiles of %d channels", t.cpg, t.c_off, t.dst_C, L->block_n);
+      return DLPM_ERR_UNSUPPORTED;
+    }
+    DLPM_REQUIRE(t.ss_off < 0 || ss != nullptr, "conv_set_post: scale-shift columns without a table");
+    L->post[k] = t;
+  }
+  L->post_n = n;
+  L->ss = ss;
+  L->ss_stride = ss_stride;
+  return DLPM_OK;
 }
 
 static int g_tall_enabled = 1;
@@ -841,7 +1068,7 @@ int conv_cta_group_override() {
 }
 void conv_set_cta_group_override(int v) { g_cta_group_override = v; }
 
-template <int BN, int BK, int CG, bool XF>
+template <int BN, int BK, int CG, bool XF, bool POST = false>
 static int launch_t(const ConvLaunch& L, cudaStream_t stream) {
   constexpr int KS = BN <= 128 ? 2 : 1;
   const int B_BYTES = (BN / CG) * BK * 2;
@@ -851,7 +1078,7 @@ static int launch_t(const ConvLaunch& L, cudaStream_t stream) {
   const size_t smem = (size_t)stages * STAGE + kSmemExtra;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_conv_tc<BN, BK, CG, KS, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemBudget + kSmemExtra));
+    cudaError_t e = cudaFuncSetAttribute(k_conv_tc<BN, BK, CG, KS, XF, POST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemBudget + kSmemExtra));
     if (e != cudaSuccess) return cuda_fail(e, "conv smem attribute");
     attr_set = true;
   }
@@ -875,11 +1102,29 @@ static int launch_t(const ConvLaunch& L, cudaStream_t stream) {
     p.fd_nnt = FastDiv((uint32_t)(L.n_n_tiles > 0 ? L.n_n_tiles : 1));
     p.fd_tpi = FastDiv((uint32_t)(L.tiles_per_img > 0 ? L.tiles_per_img : 1));
   }
-  const int n_items = ((L.n_m_tiles / L.msub + CG - 1) / CG) * L.n_n_tiles * L.n_par;
+  int n_items = ((L.n_m_tiles / L.msub + CG - 1) / CG) * L.n_n_tiles * L.n_par;
+  p.post_n = 0; p.ipu_log = 0; p.n_units = 0; p.ss = L.ss; p.ss_rows = L.ss_rows; p.ss_stride = L.ss_stride;
+  p.stats_half = (L.Nb > 1 && L.Wb * L.Hb == 16) ? 1 : 0;
+  if (POST) {
+    if (L.stats == nullptr || L.post_n < 1) { set_error("conv: POST launch without statistics buffer / targets"); return DLPM_ERR_ARG; }
+    p.post_n = L.post_n;
+    for (int k = 0; k < L.post_n; ++k) {
+      p.post[k].dst = reinterpret_cast<__nv_bfloat16*>(L.post[k].dst); p.post[k].gamma = L.post[k].gamma; p.post[k].beta = L.post[k].beta;
+      p.post[k].ss_off = L.post[k].ss_off; p.post[k].dst_C = L.post[k].dst_C; p.post[k].c_off = L.post[k].c_off;
+      p.post[k].cpg = L.post[k].cpg; p.post[k].silu = L.post[k].silu;
+    }
+    if (L.Nb == 1) {  // sample-major walk: a unit = CG samples x one N tile, ipu items each
+      int ipu = L.tiles_per_img / L.msub, lg = 0;
+      while ((1 << lg) < ipu) ++lg;
+      p.ipu_log = lg;
+      p.n_units = (int)((L.B + CG - 1) / CG) * L.n_n_tiles;
+      n_items = p.n_units;  // (grid sizing below: one CTA group per unit at most)
+    }
+  }
   const int max_groups = kNumSMs / CG;
   const int grid = (n_items < max_groups ? n_items : max_groups) * CG;
-  const int threads = conv_threads<BN, XF>();
-  cudaError_t e = launch_ex(k_conv_tc<BN, BK, CG, KS, XF>, dim3(grid), dim3(threads), smem, stream, CG, L.tmA, L.tmA2, L.tmS0, L.tmS1,
+  const int threads = conv_threads<BN, XF, POST>();
+  cudaError_t e = launch_ex(k_conv_tc<BN, BK, CG, KS, XF, POST>, dim3(grid), dim3(threads), smem, stream, CG, L.tmA, L.tmA2, L.tmS0, L.tmS1,
                             L.tmB, L.tmO, p);
   if (e != cudaSuccess) return cuda_fail(e, CG == 1 ? "conv_tc launch" : "conv_tc pair launch");
   return DLPM_OK;
@@ -896,6 +1141,14 @@ int conv_launch(const ConvLaunch& L, cudaStream_t stream) {
         return launch_t<BN, BK, 1, true>(L, stream);                                \
       }                                                                             \
       set_error("conv: no normalise-on-load kernel for tile N=%d K=%d", BN, BK);   \
+      return DLPM_ERR_UNSUPPORTED;                                                  \
+    }                                                                               \
+    if (L.post_n > 0) {                                                             \
+      if constexpr (BN >= 128) {                                                    \
+        if (L.cta_group == 2) return launch_t<BN, BK, 2, false, true>(L, stream);   \
+        return launch_t<BN, BK, 1, false, true>(L, stream);                         \
+      }                                                                             \
+      set_error("conv: no producer-side GroupNorm kernel for tile N=%d", BN);       \
       return DLPM_ERR_UNSUPPORTED;                                                  \
     }                                                                               \
     if (L.cta_group == 2) {                                                         \
@@ -999,6 +1252,31 @@ int dlpm_b200_conv2d_stats(const void* in, const void* w, const float* bias, con
   if (stats == nullptr) return stats_parts ? DLPM_OK : conv_launch(L, (cudaStream_t)stream);
   DLPM_REQUIRE(parts > 0, "conv2d_stats: this shape cannot emit GroupNorm statistics");
   L.stats = stats;
+  return conv_launch(L, (cudaStream_t)stream);
+}
+
+int dlpm_b200_conv2d_post(const void* in, const void* w, const float* bias, const void* skip0, int C_s0, const void* skip1, int C_s1,
+                          const void* residual, void* out, int64_t B, int H, int W, int C_in, int C_out, int ksize, int stride, float* stats,
+                          int* stats_parts, void* post_dst, int dst_C, int c_off, int cpg, const float* gamma, const float* beta,
+                          const float* ss, int ss_rows, int64_t ss_stride, int64_t ss_off, int apply_silu, void* stream) {
+  DLPM_REQUIRE(ksize == 3 || ksize == 1, "conv: kernel size must be 1 or 3");
+  ConvLaunch L;
+  if (int rc = conv_plan(&L, in, w, bias, skip0, C_s0, skip1, C_s1, residual, out, CONV_OUT_BF16_NHWC, B, H, W, C_in, C_out,
+                         conv_geom_default(ksize), stride, nullptr))
+    return rc;
+  const int parts = conv_stats_parts(L);
+  if (stats_parts) *stats_parts = parts;
+  if (stats == nullptr) {
+    if (stats_parts) return conv_post_capable(L) ? DLPM_OK : DLPM_ERR_UNSUPPORTED;
+    set_error("conv2d_post: the statistics buffer is required");
+    return DLPM_ERR_ARG;
+  }
+  L.stats = stats;
+  ConvLaunch::Post t;
+  t.dst = post_dst; t.gamma = gamma; t.beta = beta; t.ss_off = ss ? ss_off : -1; t.dst_C = dst_C; t.c_off = c_off; t.cpg = cpg;
+  t.silu = apply_silu;
+  if (int rc = conv_set_post(&L, 1, &t, ss, ss_stride)) return rc;
+  L.ss_rows = ss_rows;
   return conv_launch(L, (cudaStream_t)stream);
 }
 

@@ -37,7 +37,26 @@ struct ConvLaunch {
   int xf, c0_blocks;                // normalise-on-load (GroupNorm + SiLU applied to the activation boxes in shared memory)
   const float* ab;                  // its coefficient table [B][C_in][2] = (a/2, b/2)
   float* stats;                     // optional GroupNorm partial sums of the output (see conv_stats_parts), set by the caller
+  // POST ("GroupNorm in the producer's tail", conv_set_post): the GroupNorms that consume this output are applied by the
+  // convolution's own post warps as soon as a sample is complete; needs `stats`
+  int post_n;
+  struct Post {
+    void* dst;            // consumer's normalised input, NHWC bf16 [B, H_out, W_out, dst_C]
+    const float* gamma;   // consumer GroupNorm parameters, indexed by the consumer's channel (c_off + c)
+    const float* beta;
+    int64_t ss_off;       // scale / shift columns of the time-embedding table (scale at ss_off + ch, shift at ss_off + dst_C + ch); < 0: none
+    int dst_C, c_off, cpg, silu;
+  } post[2];
+  const float* ss;                  // time-embedding table [ss_rows][ss_stride]; ss_rows (1 or B) is patched per forward
+  int ss_rows;
+  int64_t ss_stride;
 };
+
+// Attach up to two fused GroupNorm targets to a planned convolution.  DLPM_ERR_UNSUPPORTED when the shape cannot carry them
+// (output not bf16 NHWC, folded-upsample launches, N tiles below 128 channels, groups that are not whole quads of this
+// convolution's channels or straddle an N tile).
+int conv_set_post(ConvLaunch* L, int n, const ConvLaunch::Post* targets, const float* ss, int64_t ss_stride);
+bool conv_post_capable(const ConvLaunch& L);
 
 // Fills geometry + tensor maps.  in: NHWC bf16 [B, H, W, C_in]; w: bf16 [C_out_pad][taps*C_in + C_s0 + C_s1] (K contiguous);
 // skip sources NHWC bf16 [B, H_out, W_out, C_s*].  Returns DLPM_OK or an error code (message via set_error).

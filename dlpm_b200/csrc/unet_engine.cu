@@ -13,7 +13,8 @@ namespace dlpm {
 
 enum OpCode { OP_CONV_IN = 0, OP_GN = 1, OP_CONV = 2, OP_UP = 3, OP_ATTN = 4, OP_SPLIT = 5 };
 
-constexpr int kOpFields = 24;
+constexpr int kOpFields = 40;  // 24.. = two fused GroupNorm targets of an OP_CONV (8 fields each, score_nets.py POST_FIELDS)
+constexpr int kPostFields = 8;
 struct Op { int64_t f[kOpFields]; };
 
 // GroupNorm whose inputs were all written by convolutions that left partial statistics (conv_tc.cu epilogue): no
@@ -165,11 +166,25 @@ static int build_plan(UNetEngine* E, int64_t B, Plan* P) {
     if (!ext) {
       writes(f[2]);
       const int parts = conv_stats_parts(L);
-      if (parts > 0 && g_gn_stats_enabled && L.C_out % 128 == 0) {
+      // fused GroupNorm targets (fields 24..): this convolution applies the GroupNorm(s) of its consumers itself
+      ConvLaunch::Post targets[2];
+      int n_t = 0;
+      for (int k = 0; k < 2; ++k) {
+        const int64_t* tf = f + 24 + kPostFields * k;  // dst buffer, dst_C, c_off, cpg, gamma_off, beta_off, ss_off, silu
+        if (tf[0] < 0) continue;
+        ConvLaunch::Post& t = targets[n_t++];
+        t.dst = E->buf(tf[0], B); t.dst_C = (int)tf[1]; t.c_off = (int)tf[2]; t.cpg = (int)tf[3];
+        t.gamma = E->wf + tf[4]; t.beta = E->wf + tf[5]; t.ss_off = tf[6]; t.silu = (int)tf[7];
+      }
+      if ((parts > 0 && g_gn_stats_enabled && L.C_out % 128 == 0) || n_t > 0) {
+        if (parts <= 0) { set_error("unet plan: a convolution with fused GroupNorm targets cannot emit statistics"); return DLPM_ERR_UNSUPPORTED; }
         float* st = nullptr;
         if (int rc2 = alloc_stats(E, P, B, parts, L.C_out, &st)) return rc2;
         L.stats = st;
         bstats[f[2]].st = st; bstats[f[2]].parts = parts; bstats[f[2]].C = L.C_out;
+      }
+      if (n_t > 0) {
+        if (int rc2 = conv_set_post(&L, n_t, targets, E->ss, E->header[7])) return rc2;
       }
     }
   }
@@ -275,6 +290,7 @@ int dlpm_b200_unet_forward(void* handle, const float* x, const float* t, int t_r
       case OP_CONV: {
         ConvLaunch& L = P.convs[ci++];
         if (f[2] < 0) L.out = out;
+        L.ss_rows = rows;  // scale / shift rows of this forward: 1 (batch-constant step) or B
         rc = conv_launch(L, (cudaStream_t)stream);
       } break;
       case OP_UP:  // 1 in, 2 out, 3 H, 4 W, 5 C

@@ -253,7 +253,8 @@ def load_checkpoint(path_or_dict, model, ema=None, map_location=None):
 # UNet (image configs)
 # ------------------------------------------------------------------------------------------------
 OP_CONV_IN, OP_GN, OP_CONV, OP_UP, OP_ATTN, OP_SPLIT = 0, 1, 2, 3, 4, 5
-OP_FIELDS = 24  # int64 fields per op record (unet_engine.cu: kOpFields)
+OP_FIELDS = 40  # int64 fields per op record (unet_engine.cu: kOpFields); 24.. = two fused GroupNorm targets of a conv
+POST_FIELDS = 8  # per target: dst buffer (-1 = none), dst channels, channel offset, channels per group, gamma, beta, ss offset, silu
 
 
 def _gn(c):
@@ -302,6 +303,7 @@ class UNetModel(nn.Module):
     scale-shift norm -- the only variant ``dlpm_experiment.py:41-56`` builds)."""
 
     native_kind = "unet"
+    fuse_groupnorm = True  # GroupNorm applied by the producing convolution's post warps (False: separate k_gn_apply launches)
 
     def __init__(self, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions, dropout=0,
                  channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2, num_classes=None, use_checkpoint=False,
@@ -356,11 +358,18 @@ class UNetModel(nn.Module):
         self._cache = _PackedCache()
 
     # ------------------------------------------------------------------ architecture walk -> op list
-    def build_program(self, H, W, reuse_scratch=True):
-        """Walk forward() (unet.py:463-492) and emit (header, ops, buffer sizes, bf16 blob, fp32 blob, debug names)."""
+    def build_program(self, H, W, reuse_scratch=True, fuse_gn=True):
+        """Walk forward() (unet.py:463-492) and emit (header, ops, buffer sizes, bf16 blob, fp32 blob, debug names).
+
+        ``fuse_gn``: a GroupNorm (+ scale-shift, SiLU) whose input -- or both halves of whose concatenated input -- was
+        written by tensor-core convolutions is not emitted as an op; it is attached to the producing convolution(s) as a
+        "post target" (fields 24.. of the conv record) and applied by that kernel's post warps as soon as a sample is
+        complete (csrc/conv_tc.cu, POST).  Needs groups of whole channel quads that do not straddle the two halves of a
+        concatenation (C0 + C1 a multiple of 128, C0 a multiple of the group size); everything else stays an OP_GN."""
         dev = next(self.parameters()).device
         mc, nh = self.model_channels, self.num_heads
         ops, bufs, names = [], [], {}
+        producer = {}  # activation buffer -> index of the conv op whose (post-capable) output it currently holds
         wb_parts, wf_parts = [], []
         wb_len, wf_len = [0], [0]
         free_pool = []
@@ -400,7 +409,36 @@ class UNetModel(nn.Module):
 
         def op(*f):
             f = list(f) + [0] * (OP_FIELDS - len(f))
+            f[24], f[24 + POST_FIELDS] = -1, -1  # no fused GroupNorm targets
             ops.append([int(v) for v in f])
+
+        def group_norm(parts, HW, norm, ss_off, silu, tmp=True):
+            """GroupNorm over the concatenation of ``parts`` = [(buffer, channels)]: attached to the producing convolutions
+            when possible, else an OP_GN.  Returns the buffer that holds the normalised tensor."""
+            C = sum(c for _, c in parts)
+            cpg = C // min(32, C)
+            plan = []
+            if fuse_gn and C % 128 == 0 and 128 % cpg == 0:
+                c_off = 0
+                for b, c in parts:
+                    pi = producer.get(b)
+                    slot = None if pi is None else (0 if ops[pi][24] < 0 else (1 if ops[pi][24 + POST_FIELDS] < 0 else None))
+                    if slot is None or c_off % cpg or c % cpg:
+                        plan = []
+                        break
+                    plan.append((pi, slot, c_off))
+                    c_off += c
+            if plan:
+                dst = new_buf(HW * C)  # dedicated: written while the producers run, i.e. before this point of the walk
+                g_off, b_off = add_f(norm.weight), add_f(norm.bias)
+                for pi, slot, c_off in plan:
+                    ops[pi][24 + POST_FIELDS * slot: 24 + POST_FIELDS * (slot + 1)] = [dst, C, c_off, cpg, g_off, b_off, ss_off, silu]
+                return dst
+            p = list(parts) + [(-1, 0)] * (2 - len(parts))
+            dst = new_buf(HW * C, tmp=tmp)
+            producer.pop(dst, None)
+            op(OP_GN, p[0][0], p[1][0], dst, p[0][1], p[1][1], HW, add_f(norm.weight), add_f(norm.bias), ss_off, silu)
+            return dst
 
         def conv(src, C_in, H_, W_, w, b, out_buf, ksize=3, stride=1, skips=(), skip_w=None, skip_b=None, residual=-1,
                  C_out_pad=None, geom=None):
@@ -422,6 +460,13 @@ class UNetModel(nn.Module):
             s = list(skips) + [(-1, 0)] * (2 - len(skips))
             op(OP_CONV, src, out_buf, s[0][0], s[0][1], s[1][0], s[1][1], residual, H_, W_, C_in, C_out, ksize, stride,
                add_b(wk), add_f(bias), *geom)
+            if out_buf >= 0:
+                # bf16 NHWC outputs of >= 128 channels in one launch (not the four-parity folded upsample) can carry the
+                # GroupNorm of their consumers (conv_tc.cu: conv_post_capable)
+                if n_par == 1 and C_out % 128 == 0 and (C_out_pad is None or C_out_pad == C_out):
+                    producer[out_buf] = len(ops) - 1
+                else:
+                    producer.pop(out_buf, None)
 
         ss_off = [0]
         emb_w, emb_b = [], []
@@ -430,14 +475,11 @@ class UNetModel(nn.Module):
             C_in = sum(c for _, c in parts)
             C_out = rb.out_channels
             hw = H_ * W_
-            p = list(parts) + [(-1, 0)] * (2 - len(parts))
-            a1 = new_buf(hw * C_in, tmp=True)
-            op(OP_GN, p[0][0], p[1][0], a1, p[0][1], p[1][1], hw, add_f(rb.in_layers[0].weight), add_f(rb.in_layers[0].bias), -1, 1)
+            a1 = group_norm(parts, hw, rb.in_layers[0], -1, 1)
             h1 = new_buf(hw * C_out, tmp=True)
             conv(a1, C_in, H_, W_, rb.in_layers[2].weight, rb.in_layers[2].bias, h1)
             release(a1)
-            a2 = new_buf(hw * C_out, tmp=True)
-            op(OP_GN, h1, -1, a2, C_out, 0, hw, add_f(rb.out_layers[0].weight), add_f(rb.out_layers[0].bias), ss_off[0], 1)
+            a2 = group_norm([(h1, C_out)], hw, rb.out_layers[0], ss_off[0], 1)
             emb_w.append(rb.emb_layers[1].weight)
             emb_b.append(rb.emb_layers[1].bias)
             ss_off[0] += 2 * C_out
@@ -455,12 +497,12 @@ class UNetModel(nn.Module):
 
         def attention(at, src, C, H_, W_, tag):
             L = H_ * W_
-            xn = new_buf(L * C, tmp=True)
-            op(OP_GN, src, -1, xn, C, 0, L, add_f(at.norm.weight), add_f(at.norm.bias), -1, 0)
+            xn = group_norm([(src, C)], L, at.norm, -1, 0)
             qkv = new_buf(L * 3 * C, tmp=True)
             conv(xn, C, H_, W_, at.qkv.weight, at.qkv.bias, qkv, ksize=1)
             release(xn)
             ao = new_buf(L * C, tmp=True)
+            producer.pop(ao, None)
             op(OP_ATTN, qkv, ao, L, C, nh)
             release(qkv)
             out = new_buf(L * C)
@@ -513,6 +555,7 @@ class UNetModel(nn.Module):
             # tensor-core input conv: x is split into bf16 (hi, lo, hi) channel groups (k_split_input) and the weights into
             # (w_hi, w_hi, w_lo), so the bf16 MMAs sum x_hi*w_hi + x_lo*w_hi + x_hi*w_lo = x*w to 2^-16 relative
             xs = new_buf(H * W * 32, tmp=True)
+            producer.pop(xs, None)
             op(OP_SPLIT, xs, cin, H, W)
             w0 = c0.weight.detach().float()
             w_hi = w0.to(torch.bfloat16).float()
@@ -532,8 +575,7 @@ class UNetModel(nn.Module):
         for i, blk in enumerate(self.output_blocks):
             skip = hs.pop()
             h, C, Hc, Wc = run_block(blk, [(h, C), skip], Hc, Wc, "output_blocks.%d" % i)
-        a = new_buf(Hc * Wc * C, tmp=True)
-        op(OP_GN, h, -1, a, C, 0, Hc * Wc, add_f(self.out[0].weight), add_f(self.out[0].bias), -1, 1)
+        a = group_norm([(h, C)], Hc * Wc, self.out[0], -1, 1)
         conv(a, C, Hc, Wc, self.out[2].weight, self.out[2].bias, -1, C_out_pad=16)
         ss_total = ss_off[0]
         te = self.time_embed
@@ -547,17 +589,19 @@ class UNetModel(nn.Module):
                     names=names)
 
     # ------------------------------------------------------------------ engine
-    def engine(self, H, W, max_batch, reuse_scratch=True):
-        """Create (or fetch) the CUDA engine for this resolution / batch capacity."""
+    def engine(self, H, W, max_batch, reuse_scratch=True, fuse_gn=None):
+        """Create (or fetch) the CUDA engine for this resolution / batch capacity.  ``fuse_gn`` (default: the module
+        attribute ``fuse_groupnorm``, True) attaches GroupNorms to their producing convolutions (``build_program``)."""
         from . import _unet_lib
-        key = (H, W, reuse_scratch)
+        fuse_gn = self.fuse_groupnorm if fuse_gn is None else bool(fuse_gn)
+        key = (H, W, reuse_scratch, fuse_gn)
         version = tuple((p.data_ptr(), _version_of(p)) for p in self.parameters())
         ent = self._engines.get(key)
         if ent is not None and (ent.version != version or ent.max_batch < max_batch):
             ent.close()
             ent = None
         if ent is None:
-            prog = self.build_program(H, W, reuse_scratch)
+            prog = self.build_program(H, W, reuse_scratch, fuse_gn)
             ent = _unet_lib.Engine(prog, max_batch, version)
             self._engines[key] = ent
         return ent

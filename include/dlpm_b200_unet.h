@@ -44,6 +44,21 @@ int dlpm_b200_conv2d_stats(const void* in, const void* w, const float* bias, con
                            int C_s1, const void* residual, void* out, int out_mode, int64_t B, int H, int W, int C_in,
                            int C_out, int ksize, int stride, float* stats, int* stats_parts, void* stream);
 
+/* K5 with the GroupNorm of its CONSUMER applied by the convolution itself ("GroupNorm in the producer's tail"): besides
+ * `out` (raw bf16 NHWC, as dlpm_b200_conv2d) and the statistics rows (as dlpm_b200_conv2d_stats) the kernel's post warps
+ * write  post_dst[b, y, x, c_off + c] = act( GN(out)[b, y, x, c] * (1 + scale) + shift )  as soon as a sample is complete,
+ * reading the raw rows back from L2 -- the separate GroupNorm pass over HBM (unet.py:141,153,188-191,212,433) disappears.
+ *   post_dst   NHWC bf16 [B, H/stride, W/stride, dst_C]; this convolution fills channels [c_off, c_off + C_out) (the two
+ *              halves of a skip concatenation are filled by their two producers)
+ *   cpg        channels per group of the consumer's GroupNorm = its total channels / 32; multiple of 4, divides 128 and c_off
+ *   gamma/beta fp32 [dst_C] of the consumer; ss / ss_rows / ss_stride / ss_off as in dlpm_b200_groupnorm_silu (NULL: none)
+ * C_out must be a multiple of 128.  Call with stats == NULL and stats_parts != NULL to size the statistics buffer
+ * (fp32 [B][*stats_parts][C_out/4][2]); returns DLPM_ERR_UNSUPPORTED for shapes that cannot carry the fusion. */
+int dlpm_b200_conv2d_post(const void* in, const void* w, const float* bias, const void* skip0, int C_s0, const void* skip1, int C_s1,
+                          const void* residual, void* out, int64_t B, int H, int W, int C_in, int C_out, int ksize, int stride, float* stats,
+                          int* stats_parts, void* post_dst, int dst_C, int c_off, int cpg, const float* gamma, const float* beta,
+                          const float* ss, int ss_rows, int64_t ss_stride, int64_t ss_off, int apply_silu, void* stream);
+
 /* Tuning / debugging knobs.  "conv_cta_group": 0 = automatic (CTA pairs with tcgen05 cta_group::2 when the problem has
  * enough tiles), 1 = always single-CTA MMAs, 2 = always CTA pairs.  "conv_tall": 1 (default) lets 3x3 stride-1 convs with
  * narrow output tiles load one (rows+2)-tall activation box per horizontal tap and reuse it for the three vertical taps,

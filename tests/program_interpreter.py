@@ -84,6 +84,28 @@ def interpret(prog, x, t, mc, emulate_bf16=False):
                     out = y
                 elif oscale == 1:
                     bufs[o] = q(y.permute(0, 2, 3, 1))
+                    # fused GroupNorm targets (fields 24..): the consumer's GroupNorm restricted to this conv's channels --
+                    # its groups never straddle the halves of a concatenation -- written at channel offset c_off of dst
+                    for kk in range(2):
+                        dst, dC, c_off, cpg, goff, boff2, ssoff, silu = f[24 + 8 * kk: 32 + 8 * kk]
+                        if dst < 0:
+                            continue
+                        assert cout % cpg == 0 and c_off % cpg == 0
+                        # statistics from the fp32 values the epilogue holds (as the kernel does), applied to the bf16-rounded tensor
+                        yn = F.group_norm(y, cout // cpg, None, None, eps=1e-5)
+                        if emulate_bf16:
+                            mean = y.reshape(B, cout // cpg, -1).mean(-1)
+                            var = y.reshape(B, cout // cpg, -1).var(-1, unbiased=False)
+                            yb = bufs[o].permute(0, 3, 1, 2)
+                            yn = ((yb.reshape(B, cout // cpg, -1) - mean[..., None]) / torch.sqrt(var[..., None] + 1e-5)).reshape(y.shape)
+                        yn = yn * wf[goff + c_off:goff + c_off + cout][None, :, None, None] + wf[boff2 + c_off:boff2 + c_off + cout][None, :, None, None]
+                        if ssoff >= 0:
+                            yn = yn * (1 + ss[:, ssoff + c_off:ssoff + c_off + cout, None, None]) + ss[:, ssoff + dC + c_off:ssoff + dC + c_off + cout, None, None]
+                        if silu:
+                            yn = F.silu(yn)
+                        if dst not in bufs or bufs[dst].shape[-1] != dC or bufs[dst].shape[1] != Ho:
+                            bufs[dst] = torch.zeros(B, Ho, Wo, dC)
+                        bufs[dst][..., c_off:c_off + cout] = q(yn.permute(0, 2, 3, 1))
                 else:
                     if o not in bufs or bufs[o].shape[1] != Ho * oscale or bufs[o].shape[3] != cout:
                         bufs[o] = torch.zeros(B, Ho * oscale, Wo * oscale, cout)

@@ -136,13 +136,26 @@ def test_unet_program_matches_oracle_block_plan():
     from oracle import nets
     for mc, attn in ((128, (16,)), (32, (2, 4))):
         m = UNetModel(3, mc, 3, 2, attn, channel_mult=(1, 2, 2, 2), num_heads=4, use_scale_shift_norm=True)
-        prog = m.build_program(32, 32)
+        prog = m.build_program(32, 32, fuse_gn=False)
         inp, out = nets.unet_block_plan(mc, (1, 2, 2, 2), 2, attn)
         n_res = sum(l.count("res") for l in inp + out) + 2
         n_attn = sum(l.count("attn") for l in inp + out) + 1
         ops = [o[0] for o in prog["ops"]]
         assert ops.count(OP_ATTN) == n_attn
         assert ops.count(OP_GN) == 2 * n_res + n_attn + 1
+        # GroupNorms attached to their producing convolutions (default): every GroupNorm is either an op or a fused target
+        # (a concatenation's GroupNorm counts once but is carried by BOTH producers)
+        fused = m.build_program(32, 32)
+        fops = [o[0] for o in fused["ops"]]
+        dsts = {o[24 + 8 * k] for o in fused["ops"] if o[0] == OP_CONV for k in (0, 1) if o[24 + 8 * k] >= 0}
+        assert fops.count(OP_GN) + len(dsts) == 2 * n_res + n_attn + 1
+        if mc == 128:
+            # benchmark net: only the GroupNorms fed by a folded upsample conv (3) or with 12-channel groups straddling the
+            # 256 | 128 concatenation (1) stay separate launches
+            assert fops.count(OP_GN) == 4, fops.count(OP_GN)
+        else:
+            assert len(dsts) == 0  # 32 / 64 channels: groups smaller than a channel quad
+        assert [o for o in fops if o != OP_GN] == [o for o in ops if o != OP_GN]
         n_up = sum(l.count("up") for l in inp + out)
         n_down = sum(l.count("down") for l in inp + out)
         # an upsample+conv = ONE parity-batched launch; the input conv = bf16 split + ONE tensor-core conv
@@ -172,6 +185,22 @@ def test_mlp_packing_layout():
         bad = dict(p)
         bad["model"] = dict(p["model"], time_emb_type="sinusoidal")
         MLPModel(bad)
+
+
+def test_unet_program_interpreted_full_width_fused_groupnorm():
+    """Benchmark-width op list with the GroupNorms attached to their producing convolutions (fused targets, both halves of
+    the skip concatenations) against the reference output."""
+    from program_interpreter import interpret
+    from dlpm_b200.init_utils import randomize_parameters_
+    from dlpm_b200.score_nets import UNetModel
+    g = load_golden("unet_cifar_full")
+    m = UNetModel(3, 128, 3, 2, (16,), channel_mult=(1, 2, 2, 2), num_heads=4, use_scale_shift_norm=True)
+    randomize_parameters_(m, 21)
+    want = torch.from_numpy(g["y"])
+    for fuse in (True, False):
+        y, _ = interpret(m.build_program(32, 32, fuse_gn=fuse), torch.from_numpy(g["x"]), torch.from_numpy(g["t"]), 128)
+        err = float((y - want).abs().max() / want.abs().max())
+        assert err < 6e-3, (fuse, err)
 
 
 @pytest.mark.parametrize("name", ["mnist", "cifar_half"])

@@ -354,3 +354,83 @@ def test_conv_normalise_on_load(L, B, H, C0, C1, C_out, residual, f32_out):
         want = want + res
     np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=2e-2, atol=3e-2)
     assert (got - want).abs().mean().item() < 5e-3
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# K5 + K6 fused on the PRODUCER side: the convolution's post warps apply the consumer's GroupNorm (+ scale-shift, SiLU)
+# to every finished sample ("GroupNorm in the producer's tail", conv_tc.cu POST kernels)
+# ------------------------------------------------------------------------------------------------------------------
+POST_CASES = [
+    # B, H, C_in, C_out, k, stride, consumer channels (dst_C), c_off, residual, per-sample scale-shift
+    (3, 32, 128, 128, 3, 1, 128, 0, False, False),    # 32x32: a sample = 2 (pairs) / 4 (single CTAs) work items
+    (37, 32, 128, 128, 3, 1, 128, 0, True, True),     # odd batch, CTA pairs with an idle half, identity residual
+    (150, 32, 128, 128, 3, 1, 256, 128, False, False),  # > 148 samples: several units per CTA (slot recycling); second half of a concat
+    (5, 16, 256, 256, 3, 1, 256, 0, False, True),
+    (40, 16, 256, 256, 3, 1, 512, 0, True, False),    # first half of a 512-channel concat (16-channel groups)
+    (2, 32, 128, 128, 3, 2, 256, 128, False, False),  # Downsample output (hs entry) -> second half of a concat
+    (5, 8, 256, 256, 3, 1, 256, 0, False, True),      # two images per tile, odd batch
+    (300, 8, 256, 256, 3, 1, 512, 256, False, False),
+    (11, 4, 256, 256, 3, 1, 256, 0, True, True),      # eight images per tile: statistics per half warp
+    (600, 4, 256, 256, 3, 1, 512, 0, False, False),
+    (9, 4, 256, 256, 1, 1, 256, 0, True, False),      # attention proj_out (1x1, residual)
+    (3, 32, 32, 128, 3, 1, 128, 0, False, False),     # K blocks of 32 channels (the split input conv)
+]
+
+
+@pytest.mark.parametrize("case", POST_CASES, ids=lambda c: "B%d_%dx%d_%d-%d_k%d_s%d_dst%d@%d_res%d_ss%d" % (c[0], c[1], c[1], c[2], c[3], c[4], c[5], c[6], c[7], c[8], c[9]))
+def test_conv_with_producer_side_groupnorm(L, case):
+    import ctypes
+    B, H, C_in, C_out, k, stride, dst_C, c_off, use_res, per_sample = case
+    x = rnd(B, C_in, H, H, seed=1)
+    w = rnd(C_out, C_in, k, k, scale=1.0 / math.sqrt(C_in * k * k), seed=2)
+    b = rnd(C_out, scale=0.1, seed=3)
+    Ho = H // stride
+    res = rnd(B, C_out, Ho, Ho, seed=4) if use_res else None
+    g = torch.Generator().manual_seed(7)
+    gamma, beta = 1 + 0.2 * torch.randn(dst_C, generator=g), 0.2 * torch.randn(dst_C, generator=g)
+    ss_rows = B if per_sample else 1
+    ss = 0.3 * torch.randn(ss_rows, 2 * dst_C + 5, generator=g)
+    ss_off = 3
+    silu = 1
+    cpg = dst_C // 32
+    xd, wd, bd = nhwc(x), bf(w.permute(0, 2, 3, 1).reshape(C_out, -1)).contiguous().cuda(), b.cuda()
+    rd = nhwc(res) if use_res else None
+    out = torch.zeros(B, Ho, Ho, C_out, device="cuda", dtype=torch.bfloat16)
+    dst = torch.full((B, Ho, Ho, dst_C), 7.0, device="cuda", dtype=torch.bfloat16)
+    parts = ctypes.c_int(0)
+    args = lambda st: (L.ptr(xd), L.ptr(wd), L.ptr(bd), None, 0, None, 0, L.ptr(rd), L.ptr(out), B, H, H, C_in, C_out, k, stride, st,
+                       ctypes.byref(parts), L.ptr(dst), dst_C, c_off, cpg, L.ptr(gamma.cuda()), L.ptr(beta.cuda()), L.ptr(ss.cuda()),
+                       ss_rows, ss.shape[1], ss_off, silu, L.stream_ptr())
+    gd, bed, ssd = gamma.cuda(), beta.cuda(), ss.cuda().contiguous()
+    call = lambda st: L.call("dlpm_b200_conv2d_post", L.ptr(xd), L.ptr(wd), L.ptr(bd), None, 0, None, 0, L.ptr(rd), L.ptr(out), B, H, H,
+                             C_in, C_out, k, stride, st, ctypes.byref(parts), L.ptr(dst), dst_C, c_off, cpg, L.ptr(gd), L.ptr(bed),
+                             L.ptr(ssd), ss_rows, ssd.shape[1], ss_off, silu, L.stream_ptr())
+    call(None)
+    assert parts.value > 0
+    stats = torch.zeros(B * parts.value * (C_out // 4) * 2, device="cuda")
+    for rep in range(2):  # second run on a dirty destination: every element must be rewritten
+        dst.fill_(7.0 + rep)
+        call(L.ptr(stats))
+        torch.cuda.synchronize()
+    y = F.conv2d(x, w, b, stride=stride, padding=k // 2)
+    if use_res:
+        y = y + res
+    raw = from_nhwc(out)
+    assert float((raw - y).abs().max() / y.abs().max()) < 2e-2
+    # the consumer's GroupNorm restricted to this conv's channels (statistics of the fp32 values, applied to the bf16 rows)
+    G = C_out // cpg
+    yg = y.reshape(B, G, -1)
+    mean, var = yg.mean(-1), yg.var(-1, unbiased=False)
+    yn = ((raw.reshape(B, G, -1) - mean[..., None]) / torch.sqrt(var[..., None] + 1e-5)).reshape(y.shape)
+    sl = slice(c_off, c_off + C_out)
+    yn = yn * gamma[sl][None, :, None, None] + beta[sl][None, :, None, None]
+    scale = ss[:, ss_off:ss_off + dst_C][:, sl]
+    shift = ss[:, ss_off + dst_C:ss_off + 2 * dst_C][:, sl]
+    yn = F.silu(yn * (1 + scale[:, :, None, None]) + shift[:, :, None, None])
+    got = from_nhwc(dst)
+    np.testing.assert_allclose(got[:, sl].numpy(), yn.numpy(), rtol=2e-2, atol=2e-2 * float(yn.abs().max()))
+    # channels outside [c_off, c_off + C_out) belong to the other producer of the concatenation: untouched
+    other = torch.ones(dst_C, dtype=torch.bool)
+    other[sl] = False
+    if other.any():
+        assert torch.equal(got[:, other], torch.full_like(got[:, other], 8.0))
