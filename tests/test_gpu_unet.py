@@ -43,18 +43,22 @@ def test_unet_forward_golden(name):
         np.testing.assert_allclose(y.numpy(), want.numpy(), rtol=2e-2, atol=2e-2 * float(want.abs().max()))
 
 
-@pytest.mark.parametrize("opts", [{}, {"gn_stats": 0}, {"gn_fuse": 2}, {"gn_fuse": 1}],
-                         ids=["default", "gn_cluster_kernels", "normalise_on_load_everywhere", "normalise_on_load_final_conv"])
+@pytest.mark.parametrize("opts", [{}, {"fuse": 0}, {"fuse": 0, "gn_stats": 0}, {"fuse": 0, "gn_fuse": 2}, {"fuse": 0, "gn_fuse": 1}],
+                         ids=["default_producer_side_groupnorm", "separate_gn_apply", "gn_cluster_kernels", "normalise_on_load_everywhere",
+                              "normalise_on_load_final_conv"])
 def test_unet_forward_full_width_golden(opts):
-    """Benchmark-width UNet against the reference's output, with every GroupNorm strategy of the engine: statistics from
-    the conv epilogues + one streaming pass (default), the stand-alone cluster kernel, and GroupNorm + SiLU applied inside
-    the consuming conv's shared-memory pipeline."""
+    """Benchmark-width UNet against the reference's output, with every GroupNorm strategy of the engine: applied by the
+    producing convolution's post warps (default), statistics from the conv epilogues + one streaming pass, the stand-alone
+    cluster kernel, and GroupNorm + SiLU applied inside the consuming conv's shared-memory pipeline."""
     from dlpm_b200 import _lib
     g = load_golden("unet_cifar_full")
+    opts = dict(opts)
+    fuse = bool(opts.pop("fuse", 1))
     for k, v in opts.items():
         _lib.call("dlpm_b200_set_option", k.encode(), v)
     try:
         m, csum = make("cifar_full")
+        m.fuse_groupnorm = fuse
         assert abs(csum - float(g["weight_checksum"])) < 1e-6 * max(1.0, abs(csum))
         y = m(torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["t"]).cuda()).cpu()
     finally:
