@@ -739,7 +739,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         // slot is handed back by the post warps (at most two units in flight).
         const int su = it >> ipu_log, slot = su & 1;
         if (lane == 0) {
-          if (p.tma_store) { bulk_wait0(); fence_proxy_async_all(); }
+          if (p.tma_store && p.xf_dbg != 3) { bulk_wait0(); fence_proxy_async_all(); }
           if ((it & ((1 << ipu_log) - 1)) == 0) mbar_wait(free_bar + slot, ((su >> 1) & 1) ^ 1);
           mbar_arrive(ready_bar + slot);
         }
@@ -751,73 +751,93 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     // 212,433) need whole-sample statistics, so they cannot sit in the per-tile epilogue -- but a CTA that walks whole
     // samples can apply them as soon as the sample's last tile has been stored, while the raw rows are still in L2 and the
     // tensor cores work on the next sample.  Replaces the separate k_gn_apply / k_groupnorm_cluster launches: the raw tensor
-    // is never re-read from HBM.  Thread t owns one 8-channel octet (fixed coefficients per sample) and every SLOTS-th pixel.
-    constexpr int OCT = BLOCK_N / 8, SLOTS = kPostThreads / OCT, NQ = BLOCK_N / 4;
+    // is never re-read from HBM.
+    // Work decomposition: a "pair" = (sample of the unit, 8-channel octet of the N tile); a thread owns one pair per round
+    // (its affine coefficients live in registers) and every SLOTS-th pixel of it.  Everything a thread needs -- the partial
+    // statistics rows, gamma / beta / scale / shift, the raw rows -- is fetched with independent loads issued together
+    // (the latency of an L2 round trip under the convolution's own operand traffic is ~2 us: it must be paid once per
+    // batch of loads, not once per sample or pixel).
+    constexpr int OCT = BLOCK_N / 8;
     const int pt = (warp - 12) * 32 + lane;
-    const int oct = pt % OCT, pslot = pt / OCT;
     const int HWs = p.H_full * p.W_full;
     const int cq = p.C_out >> 2;
+    const int n_pairs = p.Nb * OCT;
+    const int ppr = n_pairs < kPostThreads ? n_pairs : kPostThreads;  // pairs per round
+    const int SLOTS = kPostThreads / ppr, pslot = pt / ppr;
     for (int su = 0;; ++su) {
       ItemCoord ic;
       if (!item_coord<CG, POST>(p, su << ipu_log, first_item, item_stride, (int)cta_rank, msub, items_per_par, n_items, ic)) break;
       mbar_wait(ready_bar + (su & 1), (su >> 1) & 1);
       fence_proxy_async_all();
-      const int ch0 = ic.nt * BLOCK_N + oct * 8;  // first of this thread's eight conv output channels
-      for (int sI = 0; sI < p.Nb; ++sI) {
+      for (int pair = pt % ppr; pair < n_pairs && p.xf_dbg != 1; pair += ppr) {  // (xf_dbg: timing experiments only)
+        const int sI = pair / OCT, oct = pair - sI * OCT;
         const int64_t n = (int64_t)ic.n0 + sI;
-        if (n >= p.B) break;
-        // (1) per-quad sums of the sample over its partial-statistics rows
-        asm volatile("bar.sync 2, %0;" ::"n"(kPostThreads) : "memory");
-        for (int qd = pt; qd < NQ; qd += kPostThreads) {
-          const float2* row = reinterpret_cast<const float2*>(p.stats) + (n * p.stats_parts) * cq + ic.nt * NQ + qd;
-          float sA = 0.f, qA = 0.f;
-          for (int r = 0; r < p.stats_parts; ++r) { const float2 v = __ldcg(row + (int64_t)r * cq); sA += v.x; qA += v.y; }
-          s_pq[2 * qd] = sA; s_pq[2 * qd + 1] = qA;
-        }
-        asm volatile("bar.sync 2, %0;" ::"n"(kPostThreads) : "memory");
+        if (n >= p.B) continue;
+        const int ch0 = ic.nt * BLOCK_N + oct * 8;  // first of this thread's eight conv output channels
         for (int k = 0; k < p.post_n; ++k) {
           const PostTarget& tg = p.post[k];
-          // (2) y = a x + b for this thread's channels: a = gamma rstd (1 + scale), b = (beta - mean gamma rstd)(1 + scale) + shift
-          float a[8], b[8];
-          const float* ssrow = tg.ss_off >= 0 ? p.ss + (p.ss_rows == 1 ? 0 : n * p.ss_stride) + tg.ss_off : nullptr;
+          // (1) group statistics straight from the partial rows (L2): this octet's two quads belong to one or two groups
+          const int nqg = tg.cpg >> 2;  // quads per group
+          float mean[2], rstd[2];
           const float inv_n = 1.0f / (float)(tg.cpg * HWs);
-          const float osc = tg.silu ? 0.5f : 1.0f;  // silu(y) = h + h tanh(h), h = y / 2
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int ct = tg.c_off + ch0 + 4 * h;             // consumer channel of this quad
             const int g0 = (ct / tg.cpg) * tg.cpg - tg.c_off;  // first conv channel of its group (inside this N tile: host-checked)
-            const int lq0 = (g0 - ic.nt * BLOCK_N) >> 2;
+            if (h == 1 && nqg > 1) { mean[1] = mean[0]; rstd[1] = rstd[0]; break; }  // both quads in the same group
+            const float2* row = reinterpret_cast<const float2*>(p.stats) + (n * p.stats_parts) * cq + (g0 >> 2);
             float sA = 0.f, qA = 0.f;
-            for (int j = 0; j < (tg.cpg >> 2); ++j) { sA += s_pq[2 * (lq0 + j)]; qA += s_pq[2 * (lq0 + j) + 1]; }
-            const float mean = sA * inv_n;
-            const float rstd = rsqrtf(fmaxf(qA * inv_n - mean * mean, 0.f) + 1e-5f);
+            for (int r = 0; r < p.stats_parts; ++r)
+              for (int j = 0; j < nqg; ++j) { const float2 v = __ldcg(row + (int64_t)r * cq + j); sA += v.x; qA += v.y; }
+            mean[h] = sA * inv_n;
+            rstd[h] = rsqrtf(fmaxf(qA * inv_n - mean[h] * mean[h], 0.f) + 1e-5f);
+          }
+          // (2) y = a x + b: a = gamma rstd (1 + scale), b = (beta - mean gamma rstd)(1 + scale) + shift; halved for the SiLU form
+          float a[8], b[8];
+          const float* ssrow = tg.ss_off >= 0 ? p.ss + (p.ss_rows == 1 ? 0 : n * p.ss_stride) + tg.ss_off : nullptr;
+          const float osc = tg.silu ? 0.5f : 1.0f;  // silu(y) = h + h tanh(h), h = y / 2
+          {
+            const int ct = tg.c_off + ch0;
+            const float4 g0v = __ldg(reinterpret_cast<const float4*>(tg.gamma + ct)), g1v = __ldg(reinterpret_cast<const float4*>(tg.gamma + ct) + 1);
+            const float4 b0v = __ldg(reinterpret_cast<const float4*>(tg.beta + ct)), b1v = __ldg(reinterpret_cast<const float4*>(tg.beta + ct) + 1);
+            const float gg[8] = {g0v.x, g0v.y, g0v.z, g0v.w, g1v.x, g1v.y, g1v.z, g1v.w};
+            const float bb[8] = {b0v.x, b0v.y, b0v.z, b0v.w, b1v.x, b1v.y, b1v.z, b1v.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float ga = __ldg(tg.gamma + ct + e) * rstd;
-              float be = __ldg(tg.beta + ct + e) - mean * ga;
+            for (int e = 0; e < 8; ++e) {
+              float ga = gg[e] * rstd[e >> 2];
+              float be = bb[e] - mean[e >> 2] * ga;
               if (ssrow) {
                 const float sc = 1.0f + __ldg(ssrow + ct + e), sh = __ldg(ssrow + tg.dst_C + ct + e);
                 ga *= sc;
                 be = be * sc + sh;
               }
-              a[4 * h + e] = ga * osc;
-              b[4 * h + e] = be * osc;
+              a[e] = ga * osc;
+              b[e] = be * osc;
             }
           }
-          // (3) stream the sample: raw rows from L2 (ld.global.cg: written by this CTA a moment ago), normalised rows out
+          // (3) stream the sample: raw rows from L2 (ld.global.cg: written by this CTA a moment ago), normalised rows out;
+          // software-pipelined, two batches of U loads in flight per thread
           const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.out) + (n * HWs) * p.C_out + ch0);
           uint4* dst = reinterpret_cast<uint4*>(tg.dst + (n * HWs) * tg.dst_C + tg.c_off + ch0);
           const int sstr = p.C_out >> 3, dstr = tg.dst_C >> 3;  // row strides in 16-byte units
-          constexpr int U = 4;
+          constexpr int U = 8;
+          uint4 cur[U], nxt[U];
           int px = pslot;
-          for (; px + (U - 1) * SLOTS < HWs; px += U * SLOTS) {
-            uint4 raw[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) raw[u] = __ldcg(src + (int64_t)(px + u * SLOTS) * sstr);
+          for (int u = 0; u < U; ++u) if (px + u * SLOTS < HWs) cur[u] = __ldcg(src + (int64_t)(px + u * SLOTS) * sstr);
+          for (; px < HWs; px += U * SLOTS) {
+            const int pn = px + U * SLOTS;
 #pragma unroll
-            for (int u = 0; u < U; ++u) dst[(int64_t)(px + u * SLOTS) * dstr] = post_apply8(raw[u], a, b, tg.silu);
+            for (int u = 0; u < U; ++u) if (pn + u * SLOTS < HWs) nxt[u] = __ldcg(src + (int64_t)(pn + u * SLOTS) * sstr);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+              if (px + u * SLOTS < HWs) {
+                const uint4 o = post_apply8(cur[u], a, b, tg.silu);
+                if (p.xf_dbg != 2 || o.x == 0x12345678u) dst[(int64_t)(px + u * SLOTS) * dstr] = o;
+              }
+#pragma unroll
+            for (int u = 0; u < U; ++u) cur[u] = nxt[u];
           }
-          for (; px < HWs; px += SLOTS) dst[(int64_t)px * dstr] = post_apply8(__ldcg(src + (int64_t)px * sstr), a, b, tg.silu);
         }
       }
       asm volatile("bar.sync 2, %0;" ::"n"(kPostThreads) : "memory");

@@ -304,6 +304,7 @@ class UNetModel(nn.Module):
 
     native_kind = "unet"
     fuse_groupnorm = True  # GroupNorm applied by the producing convolution's post warps (False: separate k_gn_apply launches)
+    fuse_groupnorm_max_pixels = 64  # ... on feature maps up to this many pixels (8x8); 1024 = everywhere (slower, see build_program)
 
     def __init__(self, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions, dropout=0,
                  channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2, num_classes=None, use_checkpoint=False,
@@ -418,7 +419,11 @@ class UNetModel(nn.Module):
             C = sum(c for _, c in parts)
             cpg = C // min(32, C)
             plan = []
-            if fuse_gn and C % 128 == 0 and 128 % cpg == 0:
+            # Only maps of <= 64 pixels (whole samples inside one 128-pixel tile): measured on B200, the post warps of a 16x16 or
+            # 32x32 convolution lose -- those layers already move 6x their output through the L2 -> SM fabric (0.88 of its
+            # 12 TB/s), the re-read + write of the normalised rows adds 2x more, and the kernel slows down by more than the
+            # separate HBM-speed pass costs (profiles/r02_groupnorm_producer_side.md).
+            if fuse_gn and C % 128 == 0 and 128 % cpg == 0 and HW <= self.fuse_groupnorm_max_pixels:
                 c_off = 0
                 for b, c in parts:
                     pi = producer.get(b)
@@ -594,7 +599,7 @@ class UNetModel(nn.Module):
         attribute ``fuse_groupnorm``, True) attaches GroupNorms to their producing convolutions (``build_program``)."""
         from . import _unet_lib
         fuse_gn = self.fuse_groupnorm if fuse_gn is None else bool(fuse_gn)
-        key = (H, W, reuse_scratch, fuse_gn)
+        key = (H, W, reuse_scratch, fuse_gn, self.fuse_groupnorm_max_pixels)
         version = tuple((p.data_ptr(), _version_of(p)) for p in self.parameters())
         ent = self._engines.get(key)
         if ent is not None and (ent.version != version or ent.max_batch < max_batch):

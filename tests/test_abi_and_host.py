@@ -145,6 +145,7 @@ def test_unet_program_matches_oracle_block_plan():
         assert ops.count(OP_GN) == 2 * n_res + n_attn + 1
         # GroupNorms attached to their producing convolutions (default): every GroupNorm is either an op or a fused target
         # (a concatenation's GroupNorm counts once but is carried by BOTH producers)
+        m.fuse_groupnorm_max_pixels = 1024
         fused = m.build_program(32, 32)
         fops = [o[0] for o in fused["ops"]]
         dsts = {o[24 + 8 * k] for o in fused["ops"] if o[0] == OP_CONV for k in (0, 1) if o[24 + 8 * k] >= 0}
@@ -156,6 +157,12 @@ def test_unet_program_matches_oracle_block_plan():
         else:
             assert len(dsts) == 0  # 32 / 64 channels: groups smaller than a channel quad
         assert [o for o in fops if o != OP_GN] == [o for o in ops if o != OP_GN]
+        if mc == 128:  # default: only the 8x8 and 4x4 maps (whole samples inside one tile) carry the fusion
+            m.fuse_groupnorm_max_pixels = 64
+            dflt = m.build_program(32, 32)
+            d_dsts = {o[24 + 8 * k] for o in dflt["ops"] if o[0] == OP_CONV for k in (0, 1) if o[24 + 8 * k] >= 0}
+            assert all(o[8] * o[9] // (o[13] * o[13]) <= 64 for o in dflt["ops"] if o[0] == OP_CONV and o[24] >= 0)
+            assert len(d_dsts) == 24 and [o[0] for o in dflt["ops"]].count(OP_GN) + len(d_dsts) == 2 * n_res + n_attn + 1, len(d_dsts)
         n_up = sum(l.count("up") for l in inp + out)
         n_down = sum(l.count("down") for l in inp + out)
         # an upsample+conv = ONE parity-batched launch; the input conv = bf16 split + ONE tensor-core conv
@@ -197,10 +204,11 @@ def test_unet_program_interpreted_full_width_fused_groupnorm():
     m = UNetModel(3, 128, 3, 2, (16,), channel_mult=(1, 2, 2, 2), num_heads=4, use_scale_shift_norm=True)
     randomize_parameters_(m, 21)
     want = torch.from_numpy(g["y"])
-    for fuse in (True, False):
+    for fuse, max_px in ((True, 64), (True, 1024), (False, 64)):
+        m.fuse_groupnorm_max_pixels = max_px
         y, _ = interpret(m.build_program(32, 32, fuse_gn=fuse), torch.from_numpy(g["x"]), torch.from_numpy(g["t"]), 128)
         err = float((y - want).abs().max() / want.abs().max())
-        assert err < 6e-3, (fuse, err)
+        assert err < 6e-3, (fuse, max_px, err)
 
 
 @pytest.mark.parametrize("name", ["mnist", "cifar_half"])

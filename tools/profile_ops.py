@@ -21,6 +21,7 @@ ap.add_argument("--opt", action="append", default=[])
 ap.add_argument("--summary", action="store_true")
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--config", default="cifar", choices=["cifar", "mnist"])
+ap.add_argument("--no-fuse", action="store_true")  # GroupNorm as separate launches (round-1 path) instead of the producers' post warps
 args = ap.parse_args()
 for o in args.opt:
     k, v = o.split("=")
@@ -31,6 +32,7 @@ else:
     m = UNetModel(3, 128, 3, 2, (16,), channel_mult=(1, 2, 2, 2), num_heads=4, use_scale_shift_norm=True)
 randomize_parameters_(m, 0)
 m = m.cuda().eval()
+m.fuse_groupnorm = not args.no_fuse
 B = args.batch
 eng = m.engine(32, 32, B)
 x = torch.randn(B, 1 if args.config == "mnist" else 3, 32, 32, device="cuda")

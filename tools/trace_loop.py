@@ -22,6 +22,7 @@ dlpm_b200.manual_seed(1)
 m = UNetModel(3, 128, 3, 2, (16,), channel_mult=(1, 2, 2, 2), num_heads=4, use_scale_shift_norm=True)
 randomize_parameters_(m, 0)
 m = m.to(dev).eval()
+m.fuse_groupnorm = "--no-fuse" not in sys.argv
 glp = GenerativeLevyProcess(1.7, dev, 1000, rescale_timesteps=True, isotropic=True)
 fn = lambda: glp.sample({"default": m}, [512, 3, 32, 32], reverse_steps=steps, clamp_a=20, clamp_eps=200)
 fn()
