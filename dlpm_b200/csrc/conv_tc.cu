@@ -181,7 +181,7 @@ __host__ __device__ constexpr int conv_threads() {
   return XF ? kConvThreadsXF : (POST ? kConvThreadsPost : (conv_epi_groups<BLOCK_N, XF>() == 2 ? kConvThreadsEpi2 : kConvThreads));
 }
 
-template <int BLOCK_N, int BLOCK_K, int CG, int KS, bool XF, bool POST, bool GNE>
+template <int BLOCK_N, int BLOCK_K, int CG, int KS, bool XF, bool POST>
 __global__ void __launch_bounds__(conv_threads<BLOCK_N, XF, POST>(), 1)
 k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmS0,
           const __grid_constant__ CUtensorMap tmS1, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
@@ -207,10 +207,6 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   constexpr int EG = conv_epi_groups<BLOCK_N, XF>();
   static_assert(!(XF && POST), "normalise-on-load and the producer-side GroupNorm are alternatives");
   static_assert(!POST || (BLOCK_N >= 128 && EG == 2), "POST kernels: N tiles of 128 / 256 channels");
-  // GNE ("GroupNorm in the epilogue"): feature maps of 16 / 64 pixels -- a 128-pixel tile holds whole samples, so the
-  // consumer's GroupNorm statistics are complete inside one warp (4x4) or one pair of quadrant warps (8x8) and the normalised
-  // rows are written straight from the accumulator registers: no second pass at all
-  static_assert(!GNE || (!XF && !POST && BLOCK_N >= 128 && EG == 2), "GNE kernels: N tiles of 128 / 256 channels");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -572,7 +568,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       if (p.out_mode == CONV_OUT_BF16_NHWC) {
         constexpr int CH = BLOCK_N >= 32 ? 32 : 16;
         // identity-skip rows are fetched BEFORE waiting for the accumulator so their HBM latency hides behind the MMAs
-        constexpr bool RES_PREFETCH = !XF && !POST && !GNE;  // XF / POST kernels run 512 threads (128 registers each): residual rows are read in place
+        constexpr bool RES_PREFETCH = !XF && !POST;  // XF / POST kernels run 512 threads (128 registers each): residual rows are read in place
         constexpr int NCH = BLOCK_N / CH;  // column chunks of the tile; this warp owns chunks eg, eg + EG, ...
         constexpr bool SPLIT_SUB = NCH < EG;            // ... or, one-chunk tiles: sub-tiles eg, eg + EG, ... of the work item
         constexpr int CPW = SPLIT_SUB ? NCH : NCH / EG;  // chunks per warp
@@ -599,12 +595,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           pixs[sub] = (nn * p.H_full + p.out_scale * (h0 + sub * p.Hb + h_in) + out_oy) * p.W_full + p.out_scale * w_in + out_ox;
         // GroupNorm statistics of the tensor being written (consumed by k_gn_apply / the fold kernel): per warp, per
         // channel QUAD, (sum, sum of squares) over the warp's 32 pixels (x msub sub-tiles) -- no second pass over the output
-        const bool want_stats = p.stats != nullptr || GNE;
-        const bool do_stats = CH == 32 && !SPLIT_SUB && want_stats && valid;  // (N >= 64 only: conv_stats_parts)
+        const bool do_stats = CH == 32 && !SPLIT_SUB && p.stats != nullptr && valid;  // (N >= 64 only: conv_stats_parts)
 #pragma unroll
         for (int ci = 0; ci < CPW; ++ci) {
           const int c0 = (SPLIT_SUB ? ci : ci * EG + eg) * CH;
-          uint32_t rk[GNE ? CH : 1];  // GNE: the chunk's final fp32 values (bias and residual added) stay in registers
           float st[CH / 2];
 #pragma unroll
           for (int i = 0; i < CH / 2; ++i) st[i] = 0.f;
@@ -644,10 +638,6 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                   __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
                   for (int e = 0; e < 4; ++e) op[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-                  if constexpr (GNE) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) rk[j + e] = __float_as_uint(v[e]);
-                  }
                   if (CH == 32 && p.tma_store) sts_u4(my_row + (uint32_t)(((j >> 3) ^ ((lane >> 1) & 3)) << 4), o);
                   else *reinterpret_cast<uint4*>(dst + j) = o;
                   if (do_stats) {
@@ -675,7 +665,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
           }
           if constexpr (CH == 32) {
-            if (!SPLIT_SUB && want_stats && p.stats_half) {
+            if (!SPLIT_SUB && p.stats != nullptr && p.stats_half) {
               // 4x4 maps: the warp's 32 tile rows are TWO images of 16 pixels -- the same transposing butterfly inside each
               // half warp (8+4+2+1 shuffles): lane l ends with the total of value l & 15 over its image
 #pragma unroll
@@ -688,11 +678,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                   st[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
                 }
               }
-              if (do_stats && p.stats != nullptr) {
+              if (do_stats) {
                 const int64_t row = nn * p.stats_parts + par;
                 p.stats[(row * (p.C_out >> 2) + ((nt * BLOCK_N + c0) >> 2)) * 2 + (lane & 15)] = st[0];
               }
-            } else if (!SPLIT_SUB && want_stats) {  // warp-uniform (so is valid: a warp's 32 pixels belong to one image)
+            } else if (!SPLIT_SUB && p.stats != nullptr) {  // warp-uniform (so is valid: a warp's 32 pixels belong to one image)
               // transposing butterfly: 16 values over 32 lanes in 8+4+2+1+1 shuffles; lane l ends with the total of value l>>1
 #pragma unroll
               for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
@@ -705,84 +695,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 }
               }
               st[0] += __shfl_xor_sync(0xffffffffu, st[0], 1);
-              if (do_stats && p.stats != nullptr && (lane & 1) == 0) {
+              if (do_stats && (lane & 1) == 0) {
                 const int unit = (mt / msub) % p.units_per_img;
                 const int64_t row = (nn * p.stats_parts + (int64_t)(par * p.units_per_img + unit) * p.stats_wpi + (q % p.stats_wpi));
                 p.stats[(row * (p.C_out >> 2) + ((nt * BLOCK_N + c0) >> 2)) * 2 + (lane >> 1)] = st[0];
-              }
-            }
-          }
-          if constexpr (GNE && CH == 32) {
-            // ---- the consumer's GroupNorm (+ scale-shift, SiLU) on the chunk, from registers ----
-            // tot[2k], tot[2k+1] = (sum, sum of squares) of channel quad k of this chunk over the lane's WHOLE image
-            float tot[16];
-            if (p.stats_half) {  // 4x4: value vi of this lane's image sits in lane (lane & 16) + vi after the half-warp butterfly
-#pragma unroll
-              for (int vi = 0; vi < 16; ++vi) tot[vi] = __shfl_sync(0xffffffffu, st[0], (lane & 16) + vi);
-            } else {             // 8x8: the image is this warp's 32 pixels + those of the neighbouring quadrant's warp (q ^ 1, same eg)
-              float* mine = s_pq + (warp - 4) * 16;
-              const float* other = s_pq + ((warp - 4) ^ 1) * 16;
-              if ((lane & 1) == 0) mine[lane >> 1] = st[0];
-              asm volatile("bar.sync %0, 64;" ::"r"(3 + ((warp - 4) >> 1)) : "memory");
-#pragma unroll
-              for (int vi = 0; vi < 16; vi += 4) {
-                const float4 a4 = *reinterpret_cast<const float4*>(mine + vi), b4 = *reinterpret_cast<const float4*>(other + vi);
-                tot[vi] = a4.x + b4.x; tot[vi + 1] = a4.y + b4.y; tot[vi + 2] = a4.z + b4.z; tot[vi + 3] = a4.w + b4.w;
-              }
-              asm volatile("bar.sync %0, 64;" ::"r"(3 + ((warp - 4) >> 1)) : "memory");  // slots may be rewritten by the next chunk
-            }
-            const int HWs = p.H_full * p.W_full;
-            const int col = nt * BLOCK_N + c0;
-            for (int k = 0; k < p.post_n; ++k) {
-              const PostTarget& tg = p.post[k];
-              const int nqg = tg.cpg >> 2;  // quads per group: 1, 2 or 4 (host-checked)
-              const float inv_n = 1.0f / (float)(tg.cpg * HWs);
-              float mq[8], rq[8];           // mean / rstd of the group each of the chunk's eight quads belongs to
-#pragma unroll
-              for (int g = 0; g < 8; ++g) {
-                float sA, qA;
-                if (nqg == 1) { sA = tot[2 * g]; qA = tot[2 * g + 1]; }
-                else if (nqg == 2) { const int b = (g & ~1) * 2; sA = tot[b] + tot[b + 2]; qA = tot[b + 1] + tot[b + 3]; }
-                else { const int b = (g & ~3) * 2; sA = (tot[b] + tot[b + 2]) + (tot[b + 4] + tot[b + 6]); qA = (tot[b + 1] + tot[b + 3]) + (tot[b + 5] + tot[b + 7]); }
-                mq[g] = sA * inv_n;
-                rq[g] = rsqrtf(fmaxf(qA * inv_n - mq[g] * mq[g], 0.f) + 1e-5f);
-              }
-              const int ct = tg.c_off + col;  // consumer channel of the chunk's first column
-              const float* ssrow = tg.ss_off >= 0 ? p.ss + (p.ss_rows == 1 ? 0 : nn * p.ss_stride) + tg.ss_off : nullptr;
-              const float osc = tg.silu ? 0.5f : 1.0f;
-              __nv_bfloat16* drow = tg.dst + pixs[0] * tg.dst_C + ct;
-#pragma unroll
-              for (int j = 0; j < CH; j += 8) {
-                const float4 g0v = __ldg(reinterpret_cast<const float4*>(tg.gamma + ct + j)), g1v = __ldg(reinterpret_cast<const float4*>(tg.gamma + ct + j) + 1);
-                const float4 b0v = __ldg(reinterpret_cast<const float4*>(tg.beta + ct + j)), b1v = __ldg(reinterpret_cast<const float4*>(tg.beta + ct + j) + 1);
-                float ga[8] = {g0v.x, g0v.y, g0v.z, g0v.w, g1v.x, g1v.y, g1v.z, g1v.w};
-                float be[8] = {b0v.x, b0v.y, b0v.z, b0v.w, b1v.x, b1v.y, b1v.z, b1v.w};
-                if (ssrow && valid) {
-                  const float4 s0 = __ldg(reinterpret_cast<const float4*>(ssrow + ct + j)), s1 = __ldg(reinterpret_cast<const float4*>(ssrow + ct + j) + 1);
-                  const float4 h0 = __ldg(reinterpret_cast<const float4*>(ssrow + tg.dst_C + ct + j)), h1 = __ldg(reinterpret_cast<const float4*>(ssrow + tg.dst_C + ct + j) + 1);
-                  const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w}, sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) { ga[e] *= 1.0f + sc[e]; be[e] = be[e] * (1.0f + sc[e]) + sh[e]; }
-                }
-                uint4 o;
-                uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
-#pragma unroll
-                for (int e = 0; e < 8; e += 2) {
-                  float y[2];
-#pragma unroll
-                  for (int d = 0; d < 2; ++d) {
-                    const int qi = (j + e + d) >> 2;
-                    const float a = ga[e + d] * rq[qi] * osc;
-                    // bf16-round the raw value first: the separate GroupNorm pass (and the reference op order) normalises the STORED tensor
-                    const float xr = __bfloat162float(__float2bfloat16_rn(__uint_as_float(rk[j + e + d])));
-                    float yy = fmaf(xr, a, fmaf(-mq[qi], a, be[e + d] * osc));
-                    if (tg.silu) { float t; asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(yy)); yy = fmaf(yy, t, yy); }
-                    y[d] = yy;
-                  }
-                  const __nv_bfloat162 pk = __floats2bfloat162_rn(y[0], y[1]);
-                  ow[e >> 1] = *reinterpret_cast<const uint32_t*>(&pk);
-                }
-                if (valid) *reinterpret_cast<uint4*>(drow + j) = o;
               }
             }
           }
@@ -1103,7 +1019,6 @@ int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, c
   L->c_out_pad = C_out_pad;
   L->stats = nullptr;
   L->post_n = 0;
-  L->gne = 0;
   L->ss = nullptr; L->ss_rows = 1; L->ss_stride = 0;
   if ((rc = encode_weight_map(&L->tmB, w, C_out_pad * L->n_par, k_total, bn / L->cta_group, bk))) return rc;
   // TMA-store epilogue: dense bf16 NHWC outputs with 32-channel chunks; an epilogue warp's 32 tile rows are a (bw, bh, bn) pixel box
@@ -1135,8 +1050,6 @@ bool conv_post_capable(const ConvLaunch& L) {
   if (L.Nb == 1) {
     const int ipu = L.tiles_per_img / L.msub;
     if (ipu < 1 || (ipu & (ipu - 1)) || ipu * L.msub != L.tiles_per_img) return false;
-  } else if (L.Wb * L.Hb != 16 && L.Wb * L.Hb != 64) {
-    return false;  // in-epilogue GroupNorm: an image is half a warp (4x4) or two quadrant warps (8x8)
   }
   return true;
 }
@@ -1147,7 +1060,7 @@ int conv_set_post(ConvLaunch* L, int n, const ConvLaunch::Post* targets, const f
   for (int k = 0; k < n; ++k) {
     const ConvLaunch::Post& t = targets[k];
     DLPM_REQUIRE(t.dst && t.gamma && t.beta, "conv_set_post: NULL target tensor");
-    if (t.cpg < 4 || t.cpg % 4 || t.cpg > 16 || 32 % t.cpg || L->block_n % t.cpg || t.c_off % t.cpg || t.c_off % 8 || t.dst_C % 8 || t.c_off + L->C_out > t.dst_C ||
+    if (t.cpg < 4 || t.cpg % 4 || L->block_n % t.cpg || t.c_off % t.cpg || t.c_off % 8 || t.dst_C % 8 || t.c_off + L->C_out > t.dst_C ||
         (reinterpret_cast<uintptr_t>(t.dst) & 15u)) {
       set_error("conv_set_post: group size %d / channel offset %d / row width %d do not fit N tiles of %d channels", t.cpg, t.c_off, t.dst_C, L->block_n);
       return DLPM_ERR_UNSUPPORTED;
@@ -1156,7 +1069,6 @@ int conv_set_post(ConvLaunch* L, int n, const ConvLaunch::Post* targets, const f
     L->post[k] = t;
   }
   L->post_n = n;
-  L->gne = L->Nb > 1 ? 1 : 0;
   L->ss = ss;
   L->ss_stride = ss_stride;
   return DLPM_OK;
@@ -1176,7 +1088,7 @@ int conv_cta_group_override() {
 }
 void conv_set_cta_group_override(int v) { g_cta_group_override = v; }
 
-template <int BN, int BK, int CG, bool XF, bool POST = false, bool GNE = false>
+template <int BN, int BK, int CG, bool XF, bool POST = false>
 static int launch_t(const ConvLaunch& L, cudaStream_t stream) {
   constexpr int KS = BN <= 128 ? 2 : 1;
   const int B_BYTES = (BN / CG) * BK * 2;
@@ -1186,7 +1098,7 @@ static int launch_t(const ConvLaunch& L, cudaStream_t stream) {
   const size_t smem = (size_t)stages * STAGE + kSmemExtra;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_conv_tc<BN, BK, CG, KS, XF, POST, GNE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemBudget + kSmemExtra));
+    cudaError_t e = cudaFuncSetAttribute(k_conv_tc<BN, BK, CG, KS, XF, POST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemBudget + kSmemExtra));
     if (e != cudaSuccess) return cuda_fail(e, "conv smem attribute");
     attr_set = true;
   }
@@ -1213,15 +1125,15 @@ static int launch_t(const ConvLaunch& L, cudaStream_t stream) {
   int n_items = ((L.n_m_tiles / L.msub + CG - 1) / CG) * L.n_n_tiles * L.n_par;
   p.post_n = 0; p.ipu_log = 0; p.n_units = 0; p.ss = L.ss; p.ss_rows = L.ss_rows; p.ss_stride = L.ss_stride;
   p.stats_half = (L.Nb > 1 && L.Wb * L.Hb == 16) ? 1 : 0;
-  if (POST || GNE) {
-    if ((POST && L.stats == nullptr) || L.post_n < 1) { set_error("conv: POST launch without statistics buffer / targets"); return DLPM_ERR_ARG; }
+  if (POST) {
+    if (L.stats == nullptr || L.post_n < 1) { set_error("conv: POST launch without statistics buffer / targets"); return DLPM_ERR_ARG; }
     p.post_n = L.post_n;
     for (int k = 0; k < L.post_n; ++k) {
       p.post[k].dst = reinterpret_cast<__nv_bfloat16*>(L.post[k].dst); p.post[k].gamma = L.post[k].gamma; p.post[k].beta = L.post[k].beta;
       p.post[k].ss_off = L.post[k].ss_off; p.post[k].dst_C = L.post[k].dst_C; p.post[k].c_off = L.post[k].c_off;
       p.post[k].cpg = L.post[k].cpg; p.post[k].silu = L.post[k].silu;
     }
-    if (POST && L.Nb == 1) {  // sample-major walk: a unit = CG samples x one N tile, ipu items each
+    if (L.Nb == 1) {  // sample-major walk: a unit = CG samples x one N tile, ipu items each
       int ipu = L.tiles_per_img / L.msub, lg = 0;
       while ((1 << lg) < ipu) ++lg;
       p.ipu_log = lg;
@@ -1232,7 +1144,7 @@ static int launch_t(const ConvLaunch& L, cudaStream_t stream) {
   const int max_groups = kNumSMs / CG;
   const int grid = (n_items < max_groups ? n_items : max_groups) * CG;
   const int threads = conv_threads<BN, XF, POST>();
-  cudaError_t e = launch_ex(k_conv_tc<BN, BK, CG, KS, XF, POST, GNE>, dim3(grid), dim3(threads), smem, stream, CG, L.tmA, L.tmA2, L.tmS0, L.tmS1,
+  cudaError_t e = launch_ex(k_conv_tc<BN, BK, CG, KS, XF, POST>, dim3(grid), dim3(threads), smem, stream, CG, L.tmA, L.tmA2, L.tmS0, L.tmS1,
                             L.tmB, L.tmO, p);
   if (e != cudaSuccess) return cuda_fail(e, CG == 1 ? "conv_tc launch" : "conv_tc pair launch");
   return DLPM_OK;
@@ -1253,10 +1165,6 @@ int conv_launch(const ConvLaunch& L, cudaStream_t stream) {
     }                                                                               \
     if (L.post_n > 0) {                                                             \
       if constexpr (BN >= 128) {                                                    \
-        if (L.gne) {                                                                \
-          if (L.cta_group == 2) return launch_t<BN, BK, 2, false, false, true>(L, stream); \
-          return launch_t<BN, BK, 1, false, false, true>(L, stream);                \
-        }                                                                           \
         if (L.cta_group == 2) return launch_t<BN, BK, 2, false, true>(L, stream);   \
         return launch_t<BN, BK, 1, false, true>(L, stream);                         \
       }                                                                             \

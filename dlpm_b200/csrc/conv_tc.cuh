@@ -40,7 +40,6 @@ struct ConvLaunch {
   // POST ("GroupNorm in the producer's tail", conv_set_post): the GroupNorms that consume this output are applied by the
   // convolution's own post warps as soon as a sample is complete; needs `stats`
   int post_n;
-  int gne;                // 1: maps of 16 / 64 pixels -- the GroupNorm runs inside the epilogue, from the accumulator registers
   struct Post {
     void* dst;            // consumer's normalised input, NHWC bf16 [B, H_out, W_out, dst_C]
     const float* gamma;   // consumer GroupNorm parameters, indexed by the consumer's channel (c_off + c)
