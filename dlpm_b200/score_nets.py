@@ -303,8 +303,10 @@ class UNetModel(nn.Module):
     scale-shift norm -- the only variant ``dlpm_experiment.py:41-56`` builds)."""
 
     native_kind = "unet"
-    fuse_groupnorm = True  # GroupNorm applied by the producing convolution's post warps (False: separate k_gn_apply launches)
-    fuse_groupnorm_max_pixels = 64  # ... on feature maps up to this many pixels (8x8); 1024 = everywhere (slower, see build_program)
+    # GroupNorm applied by the producing convolution's post warps instead of separate k_gn_apply launches.  OFF by default:
+    # measured slower inside the graph-replayed loop on B200 at every resolution (DESIGN.md section 5, profiles/r02_groupnorm_producer_side.md)
+    fuse_groupnorm = False
+    fuse_groupnorm_max_pixels = 64  # ... when on: feature maps up to this many pixels (8x8); 1024 = everywhere
 
     def __init__(self, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions, dropout=0,
                  channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2, num_classes=None, use_checkpoint=False,
@@ -419,10 +421,10 @@ class UNetModel(nn.Module):
             C = sum(c for _, c in parts)
             cpg = C // min(32, C)
             plan = []
-            # Only maps of <= 64 pixels (whole samples inside one 128-pixel tile): measured on B200, the post warps of a 16x16 or
-            # 32x32 convolution lose -- those layers already move 6x their output through the L2 -> SM fabric (0.88 of its
-            # 12 TB/s), the re-read + write of the normalised rows adds 2x more, and the kernel slows down by more than the
-            # separate HBM-speed pass costs (profiles/r02_groupnorm_producer_side.md).
+            # Measured on B200 (profiles/r02_groupnorm_producer_side.md): on 16x16 / 32x32 maps the post warps lose clearly --
+            # those convolutions already move 6x their output through the L2 -> SM fabric (0.88 of its ~12 TB/s) and the
+            # re-read + write of the normalised rows adds 2x more; on 4x4 / 8x8 maps the tail of dependent L2 round trips
+            # (store completion -> statistics -> parameters -> rows) costs what the separate 8.7 us kernel costs.
             if fuse_gn and C % 128 == 0 and 128 % cpg == 0 and HW <= self.fuse_groupnorm_max_pixels:
                 c_off = 0
                 for b, c in parts:

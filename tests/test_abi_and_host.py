@@ -146,7 +146,7 @@ def test_unet_program_matches_oracle_block_plan():
         # GroupNorms attached to their producing convolutions (default): every GroupNorm is either an op or a fused target
         # (a concatenation's GroupNorm counts once but is carried by BOTH producers)
         m.fuse_groupnorm_max_pixels = 1024
-        fused = m.build_program(32, 32)
+        fused = m.build_program(32, 32, fuse_gn=True)
         fops = [o[0] for o in fused["ops"]]
         dsts = {o[24 + 8 * k] for o in fused["ops"] if o[0] == OP_CONV for k in (0, 1) if o[24 + 8 * k] >= 0}
         assert fops.count(OP_GN) + len(dsts) == 2 * n_res + n_attn + 1
@@ -157,9 +157,9 @@ def test_unet_program_matches_oracle_block_plan():
         else:
             assert len(dsts) == 0  # 32 / 64 channels: groups smaller than a channel quad
         assert [o for o in fops if o != OP_GN] == [o for o in ops if o != OP_GN]
-        if mc == 128:  # default: only the 8x8 and 4x4 maps (whole samples inside one tile) carry the fusion
+        if mc == 128:  # restricted to the 8x8 and 4x4 maps (whole samples inside one tile)
             m.fuse_groupnorm_max_pixels = 64
-            dflt = m.build_program(32, 32)
+            dflt = m.build_program(32, 32, fuse_gn=True)
             d_dsts = {o[24 + 8 * k] for o in dflt["ops"] if o[0] == OP_CONV for k in (0, 1) if o[24 + 8 * k] >= 0}
             assert all(o[8] * o[9] // (o[13] * o[13]) <= 64 for o in dflt["ops"] if o[0] == OP_CONV and o[24] >= 0)
             assert len(d_dsts) == 24 and [o[0] for o in dflt["ops"]].count(OP_GN) + len(d_dsts) == 2 * n_res + n_attn + 1, len(d_dsts)

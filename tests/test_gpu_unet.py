@@ -43,22 +43,24 @@ def test_unet_forward_golden(name):
         np.testing.assert_allclose(y.numpy(), want.numpy(), rtol=2e-2, atol=2e-2 * float(want.abs().max()))
 
 
-@pytest.mark.parametrize("opts", [{}, {"fuse": 0}, {"fuse": 0, "gn_stats": 0}, {"fuse": 0, "gn_fuse": 2}, {"fuse": 0, "gn_fuse": 1}],
-                         ids=["default_producer_side_groupnorm", "separate_gn_apply", "gn_cluster_kernels", "normalise_on_load_everywhere",
-                              "normalise_on_load_final_conv"])
+@pytest.mark.parametrize("opts", [{}, {"fuse": 1, "max_px": 64}, {"fuse": 1, "max_px": 1024}, {"gn_stats": 0}, {"gn_fuse": 2}, {"gn_fuse": 1}],
+                         ids=["default_separate_gn_apply", "producer_side_groupnorm_up_to_8x8", "producer_side_groupnorm_everywhere",
+                              "gn_cluster_kernels", "normalise_on_load_everywhere", "normalise_on_load_final_conv"])
 def test_unet_forward_full_width_golden(opts):
-    """Benchmark-width UNet against the reference's output, with every GroupNorm strategy of the engine: applied by the
-    producing convolution's post warps (default), statistics from the conv epilogues + one streaming pass, the stand-alone
-    cluster kernel, and GroupNorm + SiLU applied inside the consuming conv's shared-memory pipeline."""
+    """Benchmark-width UNet against the reference's output, with every GroupNorm strategy of the engine: statistics from
+    the conv epilogues + one streaming pass (default), applied by the producing convolution's post warps (option), the
+    stand-alone cluster kernel, and GroupNorm + SiLU applied inside the consuming conv's shared-memory pipeline."""
     from dlpm_b200 import _lib
     g = load_golden("unet_cifar_full")
     opts = dict(opts)
-    fuse = bool(opts.pop("fuse", 1))
+    fuse = bool(opts.pop("fuse", 0))
+    max_px = opts.pop("max_px", 64)
     for k, v in opts.items():
         _lib.call("dlpm_b200_set_option", k.encode(), v)
     try:
         m, csum = make("cifar_full")
         m.fuse_groupnorm = fuse
+        m.fuse_groupnorm_max_pixels = max_px
         assert abs(csum - float(g["weight_checksum"])) < 1e-6 * max(1.0, abs(csum))
         y = m(torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["t"]).cuda()).cpu()
     finally:
