@@ -62,19 +62,49 @@ def c2():
                       "samples_per_s": B / ms * 1e3}), flush=True)
 
 
+def each(fn, reps, warm=1):
+    """Per-call device times (ms) of `reps` calls after `warm` warm-up calls."""
+    for _ in range(warm):
+        fn()
+    out = []
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        out.append(a.elapsed_time(b))
+    return out
+
+
 def c4():
+    """LIM vs DLPM at 25 / 100 / 1000 steps (BASELINE.json configs[3]).  From the second call on the captured loop is an in-place
+    update of the engine's cached executable graph (dlpm_b200_graph_sample), so short loops are not dominated by set-up:
+    every call's time is listed next to steps x the per-step time of the 1000-step run."""
     m = unet(128, 3, (16,))
     B = 512
-    for steps in (25, 100, 1000):
+    rows = []
+    for steps in (1000, 100, 25):
         d = GenerativeLevyProcess(1.7, dev, 1000, rescale_timesteps=True, isotropic=True)
         li = GenerativeLevyProcess(1.7, dev, 1000, rescale_timesteps=True, isotropic=True, LIM=True)
-        reps = 1 if steps == 1000 else 2
-        ms_d = timed(lambda: d.sample({"default": m}, [B, 3, 32, 32], reverse_steps=steps, clamp_a=20, clamp_eps=200), reps=reps)
-        ms_l = timed(lambda: li.sample({"default": m}, [B, 3, 32, 32], reverse_steps=steps, clamp_eps=200), reps=reps)
-        ms_o = timed(lambda: li.sample({"default": m}, [B, 3, 32, 32], reverse_steps=steps, deterministic=True), reps=reps)
-        print(json.dumps({"config": "C4 CIFAR shape, batch 512, UNet ch128", "steps": steps, "dlpm_ms": ms_d, "lim_sde_ms": ms_l,
-                          "lim_ode_ms": ms_o, "dlpm_samples_per_s": B / ms_d * 1e3, "lim_sde_samples_per_s": B / ms_l * 1e3,
-                          "lim_ode_samples_per_s": B / ms_o * 1e3}), flush=True)
+        reps = 2 if steps == 1000 else 6
+        t_d = each(lambda: d.sample({"default": m}, [B, 3, 32, 32], reverse_steps=steps, clamp_a=20, clamp_eps=200), reps)
+        t_l = each(lambda: li.sample({"default": m}, [B, 3, 32, 32], reverse_steps=steps, clamp_eps=200), reps)
+        t_o = each(lambda: li.sample({"default": m}, [B, 3, 32, 32], reverse_steps=steps, deterministic=True), reps)
+        med = lambda v: sorted(v)[len(v) // 2]
+        rows.append({"config": "C4 CIFAR shape, batch 512, UNet ch128", "steps": steps, "reps": reps,
+                     "dlpm_ms": med(t_d), "lim_sde_ms": med(t_l), "lim_ode_ms": med(t_o),
+                     "dlpm_ms_each": [round(v, 1) for v in t_d], "lim_sde_ms_each": [round(v, 1) for v in t_l],
+                     "lim_ode_ms_each": [round(v, 1) for v in t_o],
+                     "dlpm_samples_per_s": B / med(t_d) * 1e3, "lim_sde_samples_per_s": B / med(t_l) * 1e3,
+                     "lim_ode_samples_per_s": B / med(t_o) * 1e3})
+    per_step = rows[0]["dlpm_ms"] / 999.0
+    for r in rows:
+        r["dlpm_ms_per_network_eval"] = r["dlpm_ms"] / max(r["steps"] - 1, 1)
+        r["lim_ms_per_network_eval"] = r["lim_sde_ms"] / r["steps"]
+        r["dlpm_vs_steps_x_per_step"] = r["dlpm_ms"] / (per_step * max(r["steps"] - 1, 1))
+        print(json.dumps(r), flush=True)
 
 
 def c5():
