@@ -17,12 +17,17 @@ from dlpm_b200.init_utils import randomize_parameters_  # noqa: E402
 from dlpm_b200.score_nets import UNetModel  # noqa: E402
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 12
+for a in sys.argv[1:]:  # library options for A/B runs: --opt=name=value
+    if a.startswith("--opt="):
+        from dlpm_b200 import _lib
+        k, v = a[6:].split("=")
+        _lib.call("dlpm_b200_set_option", k.encode(), int(v))
 dev = torch.device("cuda", 0)
 dlpm_b200.manual_seed(1)
 m = UNetModel(3, 128, 3, 2, (16,), channel_mult=(1, 2, 2, 2), num_heads=4, use_scale_shift_norm=True)
 randomize_parameters_(m, 0)
 m = m.to(dev).eval()
-m.fuse_groupnorm = "--no-fuse" not in sys.argv
+m.fuse_groupnorm = "--fuse" in sys.argv  # producer-side GroupNorm (off by default)
 glp = GenerativeLevyProcess(1.7, dev, 1000, rescale_timesteps=True, isotropic=True)
 fn = lambda: glp.sample({"default": m}, [512, 3, 32, 32], reverse_steps=steps, clamp_a=20, clamp_eps=200)
 fn()
