@@ -61,23 +61,28 @@ def sample_sharded(method, models, shape, group=None, **sample_kwargs):
     old = state.sample_base
     state.sample_base = start
     hist = None
+    want_hist = bool(sample_kwargs.get("get_sample_history", False))
+    tail = [int(s) for s in shape[1:]]
     if count == 0:
         # more ranks than samples: this rank owns nothing (the kernels reject empty batches) but still takes part in the
         # gather with an empty slice of the right trailing shape / dtype / device
         dev = getattr(method, "device", "cpu")
-        local = torch.empty([0] + [int(s) for s in shape[1:]], dtype=torch.float32, device=dev)
-        if sample_kwargs.get("get_sample_history", False):
-            steps = int(sample_kwargs.get("reverse_steps", getattr(method, "reverse_steps", 1)))
-            n_hist = steps + 1 if getattr(method, "LIM", False) else steps
-            hist = torch.empty([n_hist, 0] + [int(s) for s in shape[1:]], dtype=torch.float32, device=dev)
+        local = torch.empty([0] + tail, dtype=torch.float32, device=dev)
     else:
         try:
-            local = method.sample(models, [count] + [int(s) for s in shape[1:]], **sample_kwargs)
+            local = method.sample(models, [count] + tail, **sample_kwargs)
         finally:
             state.sample_base = old
     state.sample_base = old
     if isinstance(local, tuple):
         local, hist = local
+    if want_hist and world > 1:
+        # the number of history entries is the sampler's business (T for DLPM / DLIM, steps + 1 for LIM): agree on it so
+        # that a rank without samples contributes an empty history of the same length
+        n_hist = torch.tensor([0 if hist is None else hist.shape[0]], dtype=torch.int64, device=local.device)
+        dist.all_reduce(n_hist, op=dist.ReduceOp.MAX, group=group)
+        if hist is None:
+            hist = torch.empty([int(n_hist[0]), 0] + tail, dtype=local.dtype, device=local.device)
     out = gather_samples(local, total, group)
     if hist is not None:
         hist = gather_samples(hist.transpose(0, 1).contiguous(), total, group).transpose(0, 1).contiguous()

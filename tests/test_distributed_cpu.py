@@ -59,7 +59,29 @@ def _worker(rank, world, port, total, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("total", [8, 7])
+def test_default_noise_stream_follows_torch_seed():
+    """the reference seeds its noise through torch.manual_seed / np.random.seed (bem/Experiments.py:58-63); the
+    default Philox state is re-keyed whenever torch's seed changes, until dlpm_b200.manual_seed pins it."""
+    import dlpm_b200
+    from dlpm_b200 import rng
+    rng.follow_torch_seed(True)
+    try:
+        torch.manual_seed(123)
+        s1 = rng.default_state()
+        k1, o1 = s1.seed, s1.reserve(5)
+        assert o1 == 0 and rng.default_state().offset == 5
+        torch.manual_seed(124)
+        assert rng.default_state().seed != k1 and rng.default_state().offset == 0   # new key, call offset restarts
+        torch.manual_seed(123)
+        assert rng.default_state().seed == k1                                        # same seed -> same stream
+        dlpm_b200.manual_seed(99)
+        torch.manual_seed(5)
+        assert rng.default_state().seed == 99                                        # pinned explicitly: torch no longer re-keys
+    finally:
+        rng.follow_torch_seed(True)
+
+
+@pytest.mark.parametrize("total", [8, 7, 1])
 def test_sharded_sampling_gathers_in_global_order(total):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
