@@ -79,6 +79,7 @@ struct ConvKParams {
   FastDiv fd_ipp, fd_nnt, fd_tpi;  // multiply-high division by items_per_par / n_n_tiles / tiles_per_img: the per-item index math of
                                    // the producer and epilogue warps sits on the critical path of short-K work items
   // POST kernels
+  int reverse;            // walk the work items in DESCENDING order (see ConvLaunch::reverse)
   int post_n;             // targets (1 or 2)
   int ipu_log;            // Nb == 1: log2(work items per sample) -- every CTA walks WHOLE samples (unit = CG samples x one N tile)
   int n_units;            // Nb == 1: ceil(B / CG) * n_n_tiles
@@ -99,8 +100,9 @@ __device__ __forceinline__ bool item_coord(const ConvKParams& p, int it, int fir
                                            int n_items, ItemCoord& c) {
   if (POST && p.Nb == 1) {
     const int su = it >> p.ipu_log, j = it - (su << p.ipu_log);
-    const int gu = first + su * stride;
+    int gu = first + su * stride;
     if (gu >= p.n_units) return false;
+    if (p.reverse) gu = p.n_units - 1 - gu;
     const int sp = (int)p.fd_nnt.div((uint32_t)gu);
     c.par = 0;
     c.nt = gu - sp * p.n_n_tiles;
@@ -109,8 +111,9 @@ __device__ __forceinline__ bool item_coord(const ConvKParams& p, int it, int fir
     c.mt = c.n0 * p.tiles_per_img + j * msub;
     return true;
   }
-  const int item = first + it * stride;
+  int item = first + it * stride;
   if (item >= n_items) return false;
+  if (p.reverse) item = n_items - 1 - item;
   c.par = (int)p.fd_ipp.div((uint32_t)item);
   const int it_in = item - c.par * items_per_par;
   const int mg = (int)p.fd_nnt.div((uint32_t)it_in);
@@ -1019,6 +1022,7 @@ int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, c
   L->c_out_pad = C_out_pad;
   L->stats = nullptr;
   L->post_n = 0;
+  L->reverse = 0;
   L->ss = nullptr; L->ss_rows = 1; L->ss_stride = 0;
   if ((rc = encode_weight_map(&L->tmB, w, C_out_pad * L->n_par, k_total, bn / L->cta_group, bk))) return rc;
   // TMA-store epilogue: dense bf16 NHWC outputs with 32-channel chunks; an epilogue warp's 32 tile rows are a (bw, bh, bn) pixel box
@@ -1123,6 +1127,7 @@ static int launch_t(const ConvLaunch& L, cudaStream_t stream) {
     p.fd_tpi = FastDiv((uint32_t)(L.tiles_per_img > 0 ? L.tiles_per_img : 1));
   }
   int n_items = ((L.n_m_tiles / L.msub + CG - 1) / CG) * L.n_n_tiles * L.n_par;
+  p.reverse = L.reverse;
   p.post_n = 0; p.ipu_log = 0; p.n_units = 0; p.ss = L.ss; p.ss_rows = L.ss_rows; p.ss_stride = L.ss_stride;
   p.stats_half = (L.Nb > 1 && L.Wb * L.Hb == 16) ? 1 : 0;
   if (POST) {
@@ -1185,7 +1190,7 @@ int conv_launch(const ConvLaunch& L, cudaStream_t stream) {
 
 }  // namespace dlpm
 
-namespace dlpm { void attention_set_mma(int on); void attention_set_poly(int v); void gn_apply_set_min_elems(int v); void engine_set_gn_stats(bool on); void engine_set_gn_fuse(int mode); bool process_set_option(const char* name, int value); }
+namespace dlpm { void engine_set_traverse_alternate(bool on); void attention_set_mma(int on); void attention_set_poly(int v); void gn_apply_set_min_elems(int v); void engine_set_gn_stats(bool on); void engine_set_gn_fuse(int mode); bool process_set_option(const char* name, int value); }
 using namespace dlpm;
 
 int dlpm_b200_set_option(const char* name, int value) {
@@ -1196,6 +1201,10 @@ int dlpm_b200_set_option(const char* name, int value) {
   }
   if (std::string(name) == "gn_fuse") {
     engine_set_gn_fuse(value);
+    return DLPM_OK;
+  }
+  if (std::string(name) == "traverse_alternate") {
+    engine_set_traverse_alternate(value != 0);
     return DLPM_OK;
   }
   if (std::string(name) == "gn_stats") {

@@ -37,6 +37,10 @@ struct ConvLaunch {
   int xf, c0_blocks;                // normalise-on-load (GroupNorm + SiLU applied to the activation boxes in shared memory)
   const float* ab;                  // its coefficient table [B][C_in][2] = (a/2, b/2)
   float* stats;                     // optional GroupNorm partial sums of the output (see conv_stats_parts), set by the caller
+  int reverse;                      // 1: walk the work items (samples) in descending order.  Consecutive kernels of the UNet
+                                    // alternate direction so that a consumer starts with the rows its producer wrote LAST -- the
+                                    // part of a > L2-sized tensor that is still resident (an LRU cache walked in the same
+                                    // direction twice hits nothing)
   // POST ("GroupNorm in the producer's tail", conv_set_post): the GroupNorms that consume this output are applied by the
   // convolution's own post warps as soon as a sample is complete; needs `stats`
   int post_n;

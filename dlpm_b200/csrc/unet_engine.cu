@@ -73,6 +73,14 @@ static int alloc_stats(UNetEngine* E, Plan* P, int64_t B, int parts, int C, floa
   return DLPM_OK;
 }
 
+int groupnorm_from_stats_dir(void* out, const void* in0, int C0, const float* stats0, int parts0, const void* in1, int C1,
+                             const float* stats1, int parts1, int64_t B, int HW, const float* gamma, const float* beta,
+                             const float* ss, int ss_rows, int64_t ss_stride, int64_t ss_off, int apply_silu, int reverse, void* stream);
+// "traverse_alternate" (default on): consecutive streaming kernels of the forward (convolutions, GroupNorm passes) walk the
+// batch in opposite directions, so each starts with the samples its producer finished last -- the part of a tensor larger
+// than the 126 MB L2 that is still resident.  Walking the same direction twice hits nothing (LRU).
+static bool g_traverse_alternate = true;
+void engine_set_traverse_alternate(bool on) { g_traverse_alternate = on; }
 static bool g_gn_stats_enabled = true;
 static int g_gn_fuse_mode = 0;  // 0 = never (default, see DESIGN.md: the transform does not hide behind the MMAs yet), 1 = final conv only, 2 = all
 void engine_set_gn_stats(bool on) { g_gn_stats_enabled = on; }
@@ -277,10 +285,10 @@ int dlpm_b200_unet_forward(void* handle, const float* x, const float* t, int t_r
           break;
         }
         if (G.from_stats) {
-          rc = dlpm_b200_groupnorm_from_stats(E->buf(f[3], B), E->buf(f[1], B), (int)f[4], G.st0, G.parts0,
-                                              f[2] >= 0 ? E->buf(f[2], B) : nullptr, (int)f[5], G.st1, G.parts1, B, (int)f[6],
-                                              E->wf + f[7], E->wf + f[8], f[9] >= 0 ? E->ss : nullptr, rows, ss_total,
-                                              f[9] >= 0 ? f[9] : 0, (int)f[10], stream);
+          rc = groupnorm_from_stats_dir(E->buf(f[3], B), E->buf(f[1], B), (int)f[4], G.st0, G.parts0,
+                                        f[2] >= 0 ? E->buf(f[2], B) : nullptr, (int)f[5], G.st1, G.parts1, B, (int)f[6],
+                                        E->wf + f[7], E->wf + f[8], f[9] >= 0 ? E->ss : nullptr, rows, ss_total,
+                                        f[9] >= 0 ? f[9] : 0, (int)f[10], (g_traverse_alternate && (oi & 1)) ? 1 : 0, stream);
           break;
         }
         rc = dlpm_b200_groupnorm_silu(E->buf(f[3], B), E->buf(f[1], B), (int)f[4], f[2] >= 0 ? E->buf(f[2], B) : nullptr, (int)f[5], B,
@@ -291,6 +299,7 @@ int dlpm_b200_unet_forward(void* handle, const float* x, const float* t, int t_r
         ConvLaunch& L = P.convs[ci++];
         if (f[2] < 0) L.out = out;
         L.ss_rows = rows;  // scale / shift rows of this forward: 1 (batch-constant step) or B
+        L.reverse = (g_traverse_alternate && (oi & 1)) ? 1 : 0;
         rc = conv_launch(L, (cudaStream_t)stream);
       } break;
       case OP_UP:  // 1 in, 2 out, 3 H, 4 W, 5 C

@@ -184,12 +184,14 @@ constexpr int kGnApplyThreads = 512;
 
 __global__ void __launch_bounds__(kGnApplyThreads) k_gn_apply(__nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ in0,
                                                               const __nv_bfloat16* __restrict__ in1, GnFoldArgs g, int apply_silu,
-                                                              int pix_per_cta, int slices) {
+                                                              int pix_per_cta, int slices, int reverse) {
   __shared__ float quad[256];
   __shared__ float coef_a[512], coef_b[512];
   pdl_launch_dependents();
   pdl_wait();
-  const int n = blockIdx.x / slices, p0 = (blockIdx.x - n * slices) * pix_per_cta;
+  // reverse: last sample first -- the rows the producing convolution wrote last are the ones still in L2 (see ConvLaunch::reverse)
+  const int bid = reverse ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+  const int n = bid / slices, p0 = (bid - n * slices) * pix_per_cta;
   const int C = g.C0 + g.C1, nvec = C >> 3, nvec0 = g.C0 >> 3;
   const int slots = kGnApplyThreads / nvec;
   const int v = threadIdx.x % nvec, slot = threadIdx.x / nvec;
@@ -883,9 +885,21 @@ int dlpm_b200_groupnorm_silu(void* out, const void* in0, int C0, const void* in1
 static int g_gn_apply_min_elems = 131072;
 namespace dlpm { void gn_apply_set_min_elems(int v) { g_gn_apply_min_elems = v > 0 ? v : 131072; } }
 
+namespace dlpm {
+int groupnorm_from_stats_dir(void* out, const void* in0, int C0, const float* stats0, int parts0, const void* in1, int C1,
+                             const float* stats1, int parts1, int64_t B, int HW, const float* gamma, const float* beta,
+                             const float* ss, int ss_rows, int64_t ss_stride, int64_t ss_off, int apply_silu, int reverse, void* stream);
+}
 int dlpm_b200_groupnorm_from_stats(void* out, const void* in0, int C0, const float* stats0, int parts0, const void* in1, int C1,
                                    const float* stats1, int parts1, int64_t B, int HW, const float* gamma, const float* beta,
                                    const float* ss, int ss_rows, int64_t ss_stride, int64_t ss_off, int apply_silu, void* stream) {
+  return groupnorm_from_stats_dir(out, in0, C0, stats0, parts0, in1, C1, stats1, parts1, B, HW, gamma, beta, ss, ss_rows, ss_stride, ss_off,
+                                  apply_silu, 0, stream);
+}
+
+int dlpm::groupnorm_from_stats_dir(void* out, const void* in0, int C0, const float* stats0, int parts0, const void* in1, int C1,
+                                   const float* stats1, int parts1, int64_t B, int HW, const float* gamma, const float* beta,
+                                   const float* ss, int ss_rows, int64_t ss_stride, int64_t ss_off, int apply_silu, int reverse, void* stream) {
   DLPM_REQUIRE(out && in0 && stats0 && gamma && beta && parts0 >= 1, "groupnorm_from_stats: NULL tensor");
   DLPM_REQUIRE((in1 == nullptr) == (C1 == 0) && (in1 == nullptr) == (stats1 == nullptr), "groupnorm_from_stats: in1 / C1 / stats1 mismatch");
   const int C = C0 + C1;
@@ -905,7 +919,7 @@ int dlpm_b200_groupnorm_from_stats(void* out, const void* in0, int C0, const flo
   GnFoldArgs g{stats0, parts0, C0, stats1, parts1, C1, HW, gamma, beta, ss, ss_rows, ss_stride, ss_off, apply_silu ? 0.5f : 1.0f};
   cudaError_t e = launch_ex(k_gn_apply, dim3((unsigned)(B * slices)), dim3(kGnApplyThreads), 0, (cudaStream_t)stream, 1,
                             reinterpret_cast<__nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(in0),
-                            reinterpret_cast<const __nv_bfloat16*>(in1), g, apply_silu, HW / slices, slices);
+                            reinterpret_cast<const __nv_bfloat16*>(in1), g, apply_silu, HW / slices, slices, reverse);
   if (e != cudaSuccess) return cuda_fail(e, "groupnorm_from_stats launch");
   return DLPM_OK;
 }
