@@ -21,6 +21,7 @@ UNET_SIGNATURES = {
     "dlpm_b200_conv2d_gn": [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_int, c_i64, c_int, c_int,
                             c_int, c_int, c_vp, ctypes.POINTER(c_int), c_vp],
     "dlpm_b200_set_option": [ctypes.c_char_p, c_int],
+    "dlpm_b200_get_stat": [ctypes.c_char_p, ctypes.POINTER(ctypes.c_int64)],
     "dlpm_b200_groupnorm_silu": [c_vp, c_vp, c_int, c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_int, c_i64, c_i64, c_int,
                                  c_vp],
     "dlpm_b200_attention": [c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp],

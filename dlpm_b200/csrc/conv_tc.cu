@@ -43,6 +43,10 @@ constexpr int kBiasSmemFloats = 1024;    // the layer's bias vector lives in sha
                                          // memory there is no L1 left and every bias load of every chunk went to L2
 constexpr int kSmemExtra = 1024 /*base alignment*/ + 1024 /*staging alignment*/ + kEpiStageTotal + (4 * kMaxStages + 4) * 8 + 16 +
                            kBiasSmemFloats * 4 + kPostSmemBytes;
+// GNE kernels ("GroupNorm in the epilogue", below): bias | per-target coefficient tables | exchanged statistics live in the
+// bias region + the POST region (unused there) + the staging-alignment slack (their ring is a multiple of 1024 bytes, so the
+// slack sits at the END of the allocation, right behind the POST region)
+constexpr int kGneRegionBytes = kBiasSmemFloats * 4 + kPostSmemBytes + 1024;
 
 // POST: one GroupNorm (+ scale-shift, + SiLU) that consumes this convolution's output, evaluated by the convolution itself.
 // dst is the consumer's NORMALISED input tensor (NHWC bf16, dst_C channels per pixel); this convolution's channel c lands at
@@ -83,6 +87,7 @@ struct ConvKParams {
   int post_n;             // targets (1 or 2)
   int ipu_log;            // Nb == 1: log2(work items per sample) -- every CTA walks WHOLE samples (unit = CG samples x one N tile)
   int n_units;            // Nb == 1: ceil(B / CG) * n_n_tiles
+  int gne_raw;            // GNE kernels: 1 = the raw (un-normalised) output is stored as well (it has other readers)
   int stats_half;         // 4x4 maps: a warp's 32 tile rows are two images, statistics are reduced per half warp
   const float* ss;        // time-embedding scale / shift table [ss_rows][ss_stride] (unet_ops.cu: k_gemv_rows)
   int ss_rows;
@@ -184,11 +189,18 @@ __host__ __device__ constexpr int conv_threads() {
   return XF ? kConvThreadsXF : (POST ? kConvThreadsPost : (conv_epi_groups<BLOCK_N, XF>() == 2 ? kConvThreadsEpi2 : kConvThreads));
 }
 
-template <int BLOCK_N, int BLOCK_K, int CG, int KS, bool XF, bool POST>
+// GNE = true ("GroupNorm in the epilogue", CTA pairs on maps of 256 pixels): the pair's accumulator stage holds ONE WHOLE SAMPLE
+// (128 pixels x BLOCK_N channels per CTA), so the GroupNorm(s) that consume this convolution's output (unet.py:141,153,188-191)
+// are applied straight from TMEM: pass 1 reads the accumulators, adds bias / residual, (optionally stores the raw rows) and
+// reduces the per-quad statistics; the two CTAs exchange their totals through distributed shared memory; pass 2 reads the
+// accumulators AGAIN and writes silu((v - mean) * rstd * gamma' + beta') into the consumer's input tensor.  No re-read of the
+// output through L2 (the POST variant's loss), no separate k_gn_apply pass; the second stage keeps the MMAs of the next sample
+// running underneath.
+template <int BLOCK_N, int BLOCK_K, int CG, int KS, bool XF, bool POST, bool GNE>
 __global__ void __launch_bounds__(conv_threads<BLOCK_N, XF, POST>(), 1)
 k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmS0,
           const __grid_constant__ CUtensorMap tmS1, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
-          const ConvKParams p) {
+          const __grid_constant__ CUtensorMap tmP0, const __grid_constant__ CUtensorMap tmP1, const ConvKParams p) {
   constexpr int A_BYTES = 128 * BLOCK_K * 2;
   constexpr int B_ROWS = BLOCK_N / CG;
   constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
@@ -210,6 +222,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   constexpr int EG = conv_epi_groups<BLOCK_N, XF>();
   static_assert(!(XF && POST), "normalise-on-load and the producer-side GroupNorm are alternatives");
   static_assert(!POST || (BLOCK_N >= 128 && EG == 2), "POST kernels: N tiles of 128 / 256 channels");
+  static_assert(!GNE || (!XF && !POST && CG == 2 && BLOCK_N >= 128 && EG == 2), "GNE kernels: CTA pairs, N tiles of 128 / 256 channels");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -248,6 +261,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     if (p.s0_blocks) prefetch_tmap(&tmS0);
     if (p.s1_blocks) prefetch_tmap(&tmS1);
     if (p.tma_store) prefetch_tmap(&tmO);
+    if (GNE) { prefetch_tmap(&tmP0); if (p.post_n > 1) prefetch_tmap(&tmP1); }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -259,6 +273,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     if (POST) {
       for (int a = 0; a < 2; ++a) { mbar_init(ready_bar + a, (uint32_t)(4 * EG) << ipu_log); mbar_init(free_bar + a, 1); }
     }
+    if (GNE) { mbar_init(xf_bar, BLOCK_N / 2); mbar_init(xf_bar + 1, BLOCK_N / 2); }  // statistics exchange (one barrier per item parity)
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -545,6 +560,30 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     // the bias vector is only needed here: loaded by the epilogue warps and published with a named barrier among them, so
     // that its L2 round trip is off the path of the TMA producer / MMA issuer (the first accumulator is microseconds away)
     for (int i = (int)threadIdx.x - 128; i < p.c_out_pad; i += 128 * EG) s_bias[i] = __ldg(p.bias + i);
+    // GNE: per-target coefficient tables behind the bias vector, A = gamma (1 + scale), B = beta (1 + scale) + shift (halved for the
+    // one-MUFU SiLU form), so that pass 2 evaluates y = ((v - mean) rstd) A + B.  Batch-constant in sampling (ss_rows == 1): filled
+    // once per kernel; per-sample time steps refill them per item.
+    float* const s_gA = s_bias + BLOCK_N;
+    float* const s_gB = s_gA + p.post_n * BLOCK_N;
+    float* const s_tot = s_gB + p.post_n * BLOCK_N;  // [2 item parities][2 CTA ranks][BLOCK_N / 2] quad (sum, sum of squares) totals
+    float* const s_rn = s_tot + 2 * BLOCK_N;         // [targets][BLOCK_N / 4] (rstd, -mean rstd) of every quad's group, current item
+    auto gne_fill_tables = [&](int64_t n) {
+      for (int i = (int)threadIdx.x - 128; i < p.post_n * BLOCK_N; i += 128 * EG) {
+        const int k = i / BLOCK_N, ch = i - k * BLOCK_N;
+        const PostTarget& tg = p.post[k];
+        const int ct = tg.c_off + ch;
+        float ga = __ldg(tg.gamma + ct), be = __ldg(tg.beta + ct);
+        if (tg.ss_off >= 0) {
+          const float* row = p.ss + (p.ss_rows == 1 ? 0 : n * p.ss_stride) + tg.ss_off;
+          const float sc = 1.0f + __ldg(row + ct), sh = __ldg(row + tg.dst_C + ct);
+          ga *= sc;
+          be = be * sc + sh;
+        }
+        s_gA[i] = ga * 0.5f;  // GNE targets end in SiLU (host-checked): silu(y) = h + h tanh(h) with h = y / 2
+        s_gB[i] = be * 0.5f;
+      }
+    };
+    if (GNE && p.ss_rows == 1) gne_fill_tables(0);
     asm volatile("bar.sync 1, %0;" ::"n"(128 * EG) : "memory");
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     const int eg = (warp - 4) >> 2;  // which half of the column chunks (EG == 2)
@@ -568,7 +607,205 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const int64_t nn = (int64_t)n0 + n_in;
       const bool valid = nn < p.B;
       const uint32_t t_row0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * msub * BLOCK_N);
-      if (p.out_mode == CONV_OUT_BF16_NHWC) {
+      if constexpr (GNE) {
+        // ---------- GroupNorm in the epilogue: the pair's accumulator stage is one whole sample (msub == 1, two tiles per image) ----------
+        constexpr int NCH = BLOCK_N / 32, CPW = NCH / EG, NQV = BLOCK_N / 2;
+        if (p.ss_rows != 1) {  // per-sample time steps: this sample's scale / shift rows (the previous item's pass 2 is over)
+          asm volatile("bar.sync 1, %0;" ::"n"(128 * EG) : "memory");
+          gne_fill_tables(nn);
+          asm volatile("bar.sync 1, %0;" ::"n"(128 * EG) : "memory");
+        }
+        uint4 resv[CPW * 4];
+        const bool has_res = p.residual != nullptr;
+        const int64_t pix = (nn * p.H_full + (h0 + h_in)) * p.W_full + w_in;
+        if (has_res) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.C_out);
+#pragma unroll
+          for (int ci = 0; ci < CPW; ++ci)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) resv[ci * 4 + j] = __ldg(rp + (ci * EG + eg) * 4 + j);
+        }
+        mbar_wait(tfull_bar + acc, acc_phase);
+        tc_fence_after();
+        // v = accumulator + bias (+ identity residual) of eight channels, as four packed pairs (fp32x2 adds: half the issue slots)
+        auto gne_v8 = [&](const uint32_t (&r)[32], int ci, int j, float2 (&v)[4]) {
+          const uint32_t bias_s = smem_u32(s_bias) + (uint32_t)((ci * EG + eg) * 32 + j) * 4u;
+          const float4 b0 = lds_f4(bias_s), b1 = lds_f4(bias_s + 16);
+          v[0] = __fadd2_rn(make_float2(__uint_as_float(r[j + 0]), __uint_as_float(r[j + 1])), make_float2(b0.x, b0.y));
+          v[1] = __fadd2_rn(make_float2(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])), make_float2(b0.z, b0.w));
+          v[2] = __fadd2_rn(make_float2(__uint_as_float(r[j + 4]), __uint_as_float(r[j + 5])), make_float2(b1.x, b1.y));
+          v[3] = __fadd2_rn(make_float2(__uint_as_float(r[j + 6]), __uint_as_float(r[j + 7])), make_float2(b1.z, b1.w));
+          if (has_res) {
+            const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&resv[ci * 4 + j / 8]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = __fadd2_rn(v[e], __bfloat1622float2(rp[e]));
+          }
+        };
+        // ---- pass 1: statistics (and the raw rows when something else reads them)
+        float keep[CPW];  // this lane's share of the warp totals, one value per chunk (lanes 2k, 2k+1 hold quad value k)
+#pragma unroll
+        for (int ci = 0; ci < CPW; ++ci) {
+          const int c0 = (ci * EG + eg) * 32;
+          uint32_t r[32];
+          tmem_ld_x32(t_row0 + c0, r);
+          if (p.gne_raw) {
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+          }
+          tmem_ld_wait();
+          float st[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            float2 v[4];
+            gne_v8(r, ci, j, v);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { r[j + 2 * e] = __float_as_uint(v[e].x); r[j + 2 * e + 1] = __float_as_uint(v[e].y); }
+            if (p.gne_raw) {
+              uint4 o;
+              __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) op[e] = __float22bfloat162_rn(v[e]);
+              sts_u4(my_row + (uint32_t)(((j >> 3) ^ ((lane >> 1) & 3)) << 4), o);
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {  // (sum, sum of squares) of the quad: every quad of the chunk is visited exactly once
+              const int qi = (j / 4 + h) * 2;
+              const float2 s2 = __fadd2_rn(v[2 * h], v[2 * h + 1]);
+              const float2 q2 = __ffma2_rn(v[2 * h + 1], v[2 * h + 1], __fmul2_rn(v[2 * h], v[2 * h]));
+              st[qi] = s2.x + s2.y;
+              st[qi + 1] = q2.x + q2.y;
+            }
+          }
+          // v = accumulator + bias (+ residual) goes back to TMEM: pass 2 reads it as is, and the residual registers are dead from here
+          tmem_st_x32(t_row0 + c0, r);
+          if (p.gne_raw) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d(&tmO, reinterpret_cast<const void*>(epi_stage + (warp - 4) * kEpiStageBytes), c0, w_box, h0 + h_box, n0 + n_box);
+              bulk_commit();
+            }
+          }
+          // transposing butterfly (as in the plain epilogue): lane l ends with the warp total of value l >> 1
+#pragma unroll
+          for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
+            const bool up = (lane & off) != 0;
+#pragma unroll
+            for (int k = 0; k < half; ++k) {
+              const float send = up ? st[k] : st[k + half];
+              const float keepv = up ? st[k + half] : st[k];
+              st[k] = keepv + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+          }
+          st[0] += __shfl_xor_sync(0xffffffffu, st[0], 1);
+          keep[ci] = st[0];
+          if (p.stats != nullptr && (lane & 1) == 0) {  // other (unfused) GroupNorms still read the partial rows
+            const int unit = (mt / msub) % p.units_per_img;
+            const int64_t row = (nn * p.stats_parts + (int64_t)(par * p.units_per_img + unit) * p.stats_wpi + (q % p.stats_wpi));
+            p.stats[(row * (p.C_out >> 2) + ((nt * BLOCK_N + c0) >> 2)) * 2 + (lane >> 1)] = st[0];
+          }
+        }
+        // warp totals -> the warp's staging buffer (free once the raw box has been read out), CTA totals, exchange with the peer CTA
+        if (lane == 0) bulk_wait_read0();  // (raw box of this item, or the previous item's last normalised box)
+        __syncwarp();
+        if ((lane & 1) == 0) {
+#pragma unroll
+          for (int ci = 0; ci < CPW; ++ci) sts_f32(my_stage + (uint32_t)((ci * 16 + (lane >> 1)) * 4), keep[ci]);
+        }
+        tmem_st_wait();
+        asm volatile("bar.sync 1, %0;" ::"n"(128 * EG) : "memory");
+        const int et = (int)threadIdx.x - 128;
+        const uint32_t xpar = (uint32_t)(it & 1);
+        uint64_t* const xbar = xf_bar + xpar;  // one barrier per item parity: the peer's data for item it + 2 cannot arrive before this phase is over
+        if (et < NQV) {
+          const int quad = et >> 1, comp = et & 1, chunk = quad >> 3, egc = chunk & (EG - 1), cic = chunk / EG;
+          const uint32_t off = (uint32_t)((cic * 16 + (((quad & 7) << 1) | comp)) * 4);
+          float tot = 0.f;
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) tot += lds_f32(smem_u32(epi_stage) + (uint32_t)(qq + 4 * egc) * kEpiStageBytes + off);
+          const uint32_t slot = (uint32_t)(((xpar * 2 + cta_rank) * NQV + et) * 4);
+          sts_f32(smem_u32(s_tot) + slot, tot);
+          // the peer's copy travels as an asynchronous DSMEM store that completes transaction bytes on the PEER's barrier: no
+          // release fence (which would wait for this thread's outstanding global stores) on the epilogue's critical path
+          st_async_f32(mapa_u32(smem_u32(s_tot), cta_rank ^ 1u) + slot, tot, mapa_u32(smem_u32(xbar), cta_rank ^ 1u));
+          if (et == 0) mbar_expect_tx(xbar, NQV * 4);  // (counts as this thread's arrival) the peer's NQV values
+          else mbar_arrive(xbar);
+        }
+        mbar_wait(xbar, (uint32_t)((it >> 1) & 1));
+        // group statistics once per item: thread = (target, quad) -> (rstd, -mean rstd) of the quad's group, over both CTAs' totals
+        // (rank 0 first: the same sum in both CTAs)
+        {
+          const float inv_hw = 1.0f / (float)(p.H_full * p.W_full);
+          for (int i = et; i < p.post_n * (BLOCK_N / 4); i += 128 * EG) {
+            const int k = i / (BLOCK_N / 4), quad = i - k * (BLOCK_N / 4);
+            const int nqg = p.post[k].cpg >> 2, g0 = quad & ~(nqg - 1);
+            const float2* t0 = reinterpret_cast<const float2*>(s_tot + xpar * 2 * NQV) + g0;
+            float sA = 0.f, qA = 0.f;
+            for (int j = 0; j < nqg; ++j) { const float2 a = t0[j], b = t0[j + NQV / 2]; sA += a.x + b.x; qA += a.y + b.y; }
+            const float inv_n = inv_hw / (float)p.post[k].cpg;
+            const float mean = sA * inv_n;
+            const float rstd = rsqrtf(fmaxf(qA * inv_n - mean * mean, 0.f) + 1e-5f);
+            reinterpret_cast<float2*>(s_rn)[i] = make_float2(rstd, -mean * rstd);
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(128 * EG) : "memory");
+        // ---- pass 2: v again, normalised rows out
+#pragma unroll
+        for (int ci = 0; ci < CPW; ++ci) {
+          const int c0 = (ci * EG + eg) * 32;
+          uint32_t r[32];
+          tmem_ld_x32(t_row0 + c0, r);
+          if (lane == 0) bulk_wait_read0();  // staging buffer: the previous box has been read out (waited for while the TMEM load is in flight)
+          __syncwarp();
+          tmem_ld_wait();
+#pragma unroll 1
+          for (int k = 0; k < p.post_n; ++k) {  // (not unrolled: the epilogue's code size is what the instruction cache sees)
+            const PostTarget& tg = p.post[k];
+            float2 rn2[8];  // (rstd, -mean rstd) of the chunk's eight quads
+            {
+              const uint32_t rn = smem_u32(s_rn) + (uint32_t)((k * (BLOCK_N / 4) + (c0 >> 2)) * 8);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 a = lds_f4(rn + j * 16);
+                rn2[2 * j] = make_float2(a.x, a.y); rn2[2 * j + 1] = make_float2(a.z, a.w);
+              }
+            }
+            if (k > 0) {
+              if (lane == 0) bulk_wait_read0();  // the first target's box
+              __syncwarp();
+            }
+            const uint32_t tabA = smem_u32(s_gA) + (uint32_t)((k * BLOCK_N + c0) * 4), tabB = smem_u32(s_gB) + (uint32_t)((k * BLOCK_N + c0) * 4);
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const float4 A0 = lds_f4(tabA + j * 4), A1 = lds_f4(tabA + j * 4 + 16), B0 = lds_f4(tabB + j * 4), B1 = lds_f4(tabB + j * 4 + 16);
+              const float2 Aa[4] = {make_float2(A0.x, A0.y), make_float2(A0.z, A0.w), make_float2(A1.x, A1.y), make_float2(A1.z, A1.w)};
+              const float2 Bb[4] = {make_float2(B0.x, B0.y), make_float2(B0.z, B0.w), make_float2(B1.x, B1.y), make_float2(B1.z, B1.w)};
+              uint4 o;
+              __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {  // channel pair j + 2e, j + 2e + 1 (quad j / 4 + e / 2); fp32x2 FMAs
+                const float2 rq = rn2[j / 4 + e / 2];
+                const float2 v2 = make_float2(__uint_as_float(r[j + 2 * e]), __uint_as_float(r[j + 2 * e + 1]));
+                const float2 t2 = __ffma2_rn(v2, make_float2(rq.x, rq.x), make_float2(rq.y, rq.y));
+                float2 y2 = __ffma2_rn(t2, Aa[e], Bb[e]);  // = y / 2 (tables pre-halved): silu(y) = h + h tanh(h)
+                float2 th;
+                asm("tanh.approx.f32 %0, %1;" : "=f"(th.x) : "f"(y2.x));
+                asm("tanh.approx.f32 %0, %1;" : "=f"(th.y) : "f"(y2.y));
+                y2 = __ffma2_rn(y2, th, y2);
+                op[e] = __float22bfloat162_rn(y2);
+              }
+              sts_u4(my_row + (uint32_t)(((j >> 3) ^ ((lane >> 1) & 3)) << 4), o);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d(k == 0 ? &tmP0 : &tmP1, reinterpret_cast<const void*>(epi_stage + (warp - 4) * kEpiStageBytes), tg.c_off + c0, w_box,
+                           h0 + h_box, n0 + n_box);
+              bulk_commit();
+            }
+          }
+        }
+      } else if (p.out_mode == CONV_OUT_BF16_NHWC) {
         constexpr int CH = BLOCK_N >= 32 ? 32 : 16;
         // identity-skip rows are fetched BEFORE waiting for the accumulator so their HBM latency hides behind the MMAs
         constexpr bool RES_PREFETCH = !XF && !POST;  // XF / POST kernels run 512 threads (128 registers each): residual rows are read in place
@@ -941,7 +1178,7 @@ static int g_l2_prefetch = 0;  // measured: no gain (the three-stage ring alread
 
 int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, const void* skip0, int C_s0, const void* skip1,
               int C_s1, const void* residual, void* out, int out_mode, int64_t B, int H, int W, int C_in0, int C_out, ConvGeom geom,
-              int stride, const ConvFuse* fuse) {
+              int stride, const ConvFuse* fuse, bool want_gne) {
   const int C_in2 = fuse ? fuse->C_in2 : 0;
   const int C_in = C_in0 + C_in2;  // K channels per tap: the main input may be the concatenation [in | fuse->in2]
   DLPM_REQUIRE(!fuse || (fuse->ab != nullptr && (fuse->in2 == nullptr) == (C_in2 == 0)), "conv: bad fusion descriptor");
@@ -976,7 +1213,9 @@ int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, c
   L->Nb = 128 / (L->Wb * L->Hb);
   {  // small problems (4x4 / 8x8 feature maps): prefer more, narrower tiles so that every SM gets work
     const int64_t m_tiles = (L->Nb == 1 ? B * (H_out / L->Hb) : (B + L->Nb - 1) / L->Nb) * (geom.n_par == 4 ? 4 : 1);
-    while (bn > 128 && m_tiles * (C_out_pad / bn) < kNumSMs && C_out_pad % (bn / 2) == 0) bn /= 2;
+    // (not when the GroupNorm is to run in the epilogue: a GNE kernel's N tile is the whole channel range)
+    const bool gne_shape = want_gne && L->Nb == 1 && H_out * W_out == 256 && geom.n_par != 4 && C_out_pad <= 256;
+    while (!gne_shape && bn > 128 && m_tiles * (C_out_pad / bn) < kNumSMs && C_out_pad % (bn / 2) == 0) bn /= 2;
   }
   L->block_n = bn;
   L->H_out = H_out; L->W_out = W_out;
@@ -1003,6 +1242,9 @@ int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, c
   L->cta_group = (conv_cta_group_override() == 1) ? 1
                  : ((bn >= 32 && (int64_t)((L->n_m_tiles / L->msub + 1) / 2) * L->n_n_tiles * L->n_par >= 32) ? 2 : 1);
   if (conv_cta_group_override() == 2 && bn >= 32) L->cta_group = 2;
+  // fused GroupNorm targets on a map of 256 pixels: CTA pairs whatever the batch, so that the pair's accumulator stage holds the
+  // whole sample and the GroupNorm runs in the epilogue (GNE) instead of the post warps
+  if (want_gne && conv_cta_group_override() != 1 && L->Nb == 1 && L->tiles_per_img == 2 && L->msub == 1 && bn >= 128 && geom.n_par != 4) L->cta_group = 2;
   L->tall = (tall_geom && (bn <= 128 || (L->cta_group == 2 && g_tall256_enabled))) ? 1 : 0;
   L->xf = fuse ? 1 : 0;
   L->ab = fuse ? fuse->ab : nullptr;
@@ -1022,6 +1264,7 @@ int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, c
   L->c_out_pad = C_out_pad;
   L->stats = nullptr;
   L->post_n = 0;
+  L->gne = 0; L->raw_unused = 0;
   L->reverse = 0;
   L->ss = nullptr; L->ss_rows = 1; L->ss_stride = 0;
   if ((rc = encode_weight_map(&L->tmB, w, C_out_pad * L->n_par, k_total, bn / L->cta_group, bk))) return rc;
@@ -1075,7 +1318,25 @@ int conv_set_post(ConvLaunch* L, int n, const ConvLaunch::Post* targets, const f
   L->post_n = n;
   L->ss = ss;
   L->ss_stride = ss_stride;
+  // GroupNorm in the epilogue (GNE) instead of the post warps when the pair's accumulator stage holds the whole sample
+  L->gne = 0;
+  if (conv_gne_capable(*L, n)) {
+    const int bw = L->Wb < 32 ? L->Wb : 32, bh = L->Hb < 32 / bw ? L->Hb : 32 / bw, bi = 32 / (bw * bh);
+    for (int k = 0; k < n; ++k)
+      if (int rc = encode_out_map(&L->tmP[k], L->post[k].dst, L->B, L->H_out, L->W_out, L->post[k].dst_C, bw, bh, bi)) return rc;
+    L->gne = 1;
+  }
   return DLPM_OK;
+}
+
+static int g_gne_enabled = 1;
+bool conv_gne_capable(const ConvLaunch& L, int n_targets) {
+  if (!g_gne_enabled || !conv_post_capable(L) || !L.tma_store || L.cta_group != 2 || L.Nb != 1 || L.msub != 1 || L.tiles_per_img != 2) return false;
+  if (L.n_n_tiles != 1 || (L.block_n != 128 && L.block_n != 256) || L.block_k != 64) return false;
+  if ((3 + 2 * n_targets) * L.block_n * 4 + n_targets * L.block_n * 2 > kGneRegionBytes) return false;  // bias | A, B per target | exchanged totals | group (rstd, -mean rstd)
+  for (int k = 0; k < n_targets; ++k)
+    if (32 % L.post[k].cpg || L.post[k].c_off % L.post[k].cpg || !L.post[k].silu) return false;
+  return true;
 }
 
 static int g_tall_enabled = 1;
@@ -1092,8 +1353,13 @@ int conv_cta_group_override() {
 }
 void conv_set_cta_group_override(int v) { g_cta_group_override = v; }
 
-template <int BN, int BK, int CG, bool XF, bool POST = false>
+static int64_t g_n_conv = 0, g_n_post = 0, g_n_gne = 0;
+
+template <int BN, int BK, int CG, bool XF, bool POST = false, bool GNE = false>
 static int launch_t(const ConvLaunch& L, cudaStream_t stream) {
+  ++g_n_conv;
+  if (POST) ++g_n_post;
+  if (GNE) ++g_n_gne;
   constexpr int KS = BN <= 128 ? 2 : 1;
   const int B_BYTES = (BN / CG) * BK * 2;
   const int STAGE = L.tall ? (L.msub * L.Hb + 2) * L.Wb * BK * 2 + 3 * B_BYTES : KS * (128 * BK * 2 + B_BYTES);
@@ -1102,7 +1368,7 @@ static int launch_t(const ConvLaunch& L, cudaStream_t stream) {
   const size_t smem = (size_t)stages * STAGE + kSmemExtra;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_conv_tc<BN, BK, CG, KS, XF, POST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemBudget + kSmemExtra));
+    cudaError_t e = cudaFuncSetAttribute(k_conv_tc<BN, BK, CG, KS, XF, POST, GNE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemBudget + kSmemExtra));
     if (e != cudaSuccess) return cuda_fail(e, "conv smem attribute");
     attr_set = true;
   }
@@ -1130,15 +1396,17 @@ static int launch_t(const ConvLaunch& L, cudaStream_t stream) {
   p.reverse = L.reverse;
   p.post_n = 0; p.ipu_log = 0; p.n_units = 0; p.ss = L.ss; p.ss_rows = L.ss_rows; p.ss_stride = L.ss_stride;
   p.stats_half = (L.Nb > 1 && L.Wb * L.Hb == 16) ? 1 : 0;
-  if (POST) {
-    if (L.stats == nullptr || L.post_n < 1) { set_error("conv: POST launch without statistics buffer / targets"); return DLPM_ERR_ARG; }
+  p.gne_raw = L.raw_unused ? 0 : 1;
+  if (GNE && ((stages * STAGE) % 1024 != 0)) { set_error("conv: GNE kernels need an operand ring that is a multiple of 1024 bytes"); return DLPM_ERR_UNSUPPORTED; }
+  if (POST || GNE) {
+    if ((POST && L.stats == nullptr) || L.post_n < 1) { set_error("conv: POST launch without statistics buffer / targets"); return DLPM_ERR_ARG; }
     p.post_n = L.post_n;
     for (int k = 0; k < L.post_n; ++k) {
       p.post[k].dst = reinterpret_cast<__nv_bfloat16*>(L.post[k].dst); p.post[k].gamma = L.post[k].gamma; p.post[k].beta = L.post[k].beta;
       p.post[k].ss_off = L.post[k].ss_off; p.post[k].dst_C = L.post[k].dst_C; p.post[k].c_off = L.post[k].c_off;
       p.post[k].cpg = L.post[k].cpg; p.post[k].silu = L.post[k].silu;
     }
-    if (L.Nb == 1) {  // sample-major walk: a unit = CG samples x one N tile, ipu items each
+    if (POST && L.Nb == 1) {  // sample-major walk: a unit = CG samples x one N tile, ipu items each
       int ipu = L.tiles_per_img / L.msub, lg = 0;
       while ((1 << lg) < ipu) ++lg;
       p.ipu_log = lg;
@@ -1149,8 +1417,8 @@ static int launch_t(const ConvLaunch& L, cudaStream_t stream) {
   const int max_groups = kNumSMs / CG;
   const int grid = (n_items < max_groups ? n_items : max_groups) * CG;
   const int threads = conv_threads<BN, XF, POST>();
-  cudaError_t e = launch_ex(k_conv_tc<BN, BK, CG, KS, XF, POST>, dim3(grid), dim3(threads), smem, stream, CG, L.tmA, L.tmA2, L.tmS0, L.tmS1,
-                            L.tmB, L.tmO, p);
+  cudaError_t e = launch_ex(k_conv_tc<BN, BK, CG, KS, XF, POST, GNE>, dim3(grid), dim3(threads), smem, stream, CG, L.tmA, L.tmA2, L.tmS0, L.tmS1,
+                            L.tmB, L.tmO, L.tmP[0], L.tmP[1], p);
   if (e != cudaSuccess) return cuda_fail(e, CG == 1 ? "conv_tc launch" : "conv_tc pair launch");
   return DLPM_OK;
 }
@@ -1166,6 +1434,11 @@ int conv_launch(const ConvLaunch& L, cudaStream_t stream) {
         return launch_t<BN, BK, 1, true>(L, stream);                                \
       }                                                                             \
       set_error("conv: no normalise-on-load kernel for tile N=%d K=%d", BN, BK);   \
+      return DLPM_ERR_UNSUPPORTED;                                                  \
+    }                                                                               \
+    if (L.post_n > 0 && L.gne) {                                                    \
+      if constexpr (BN >= 128 && BK == 64) return launch_t<BN, BK, 2, false, false, true>(L, stream); \
+      set_error("conv: no GroupNorm-in-the-epilogue kernel for tile N=%d K=%d", BN, BK); \
       return DLPM_ERR_UNSUPPORTED;                                                  \
     }                                                                               \
     if (L.post_n > 0) {                                                             \
@@ -1190,8 +1463,18 @@ int conv_launch(const ConvLaunch& L, cudaStream_t stream) {
 
 }  // namespace dlpm
 
-namespace dlpm { void engine_set_traverse_alternate(bool on); void attention_set_mma(int on); void attention_set_poly(int v); void gn_apply_set_min_elems(int v); void engine_set_gn_stats(bool on); void engine_set_gn_fuse(int mode); bool process_set_option(const char* name, int value); }
+namespace dlpm { void engine_set_gne_skip_raw(bool on); void engine_set_traverse_alternate(bool on); void attention_set_mma(int on); void attention_set_poly(int v); void gn_apply_set_min_elems(int v); void engine_set_gn_stats(bool on); void engine_set_gn_fuse(int mode); bool process_set_option(const char* name, int value); }
 using namespace dlpm;
+
+int dlpm_b200_get_stat(const char* name, int64_t* value) {
+  DLPM_REQUIRE(name != nullptr && value != nullptr, "get_stat: NULL argument");
+  const std::string n(name);
+  if (n == "conv_launches") *value = g_n_conv;
+  else if (n == "conv_post_launches") *value = g_n_post;
+  else if (n == "conv_gne_launches") *value = g_n_gne;
+  else { set_error("get_stat: unknown counter '%s'", name); return DLPM_ERR_ARG; }
+  return DLPM_OK;
+}
 
 int dlpm_b200_set_option(const char* name, int value) {
   DLPM_REQUIRE(name != nullptr, "set_option: NULL name");
@@ -1209,6 +1492,14 @@ int dlpm_b200_set_option(const char* name, int value) {
   }
   if (std::string(name) == "gn_stats") {
     engine_set_gn_stats(value != 0);
+    return DLPM_OK;
+  }
+  if (std::string(name) == "gne_skip_raw") {
+    engine_set_gne_skip_raw(value != 0);
+    return DLPM_OK;
+  }
+  if (std::string(name) == "conv_gne") {  // GroupNorm in the epilogue for fused targets (0: always the post warps)
+    g_gne_enabled = value != 0;
     return DLPM_OK;
   }
   if (std::string(name) == "conv_msub") {
@@ -1291,7 +1582,7 @@ int dlpm_b200_conv2d_post(const void* in, const void* w, const float* bias, cons
   DLPM_REQUIRE(ksize == 3 || ksize == 1, "conv: kernel size must be 1 or 3");
   ConvLaunch L;
   if (int rc = conv_plan(&L, in, w, bias, skip0, C_s0, skip1, C_s1, residual, out, CONV_OUT_BF16_NHWC, B, H, W, C_in, C_out,
-                         conv_geom_default(ksize), stride, nullptr))
+                         conv_geom_default(ksize), stride, nullptr, true))
     return rc;
   const int parts = conv_stats_parts(L);
   if (stats_parts) *stats_parts = parts;

@@ -51,6 +51,11 @@ struct ConvLaunch {
     int64_t ss_off;       // scale / shift columns of the time-embedding table (scale at ss_off + ch, shift at ss_off + dst_C + ch); < 0: none
     int dst_C, c_off, cpg, silu;
   } post[2];
+  // GNE ("GroupNorm in the epilogue"): chosen by conv_set_post when a CTA pair's accumulator stage holds one whole sample (maps of
+  // 256 pixels): the targets are applied straight from TMEM in a second epilogue pass, no post warps, no re-read through L2
+  int gne;
+  int raw_unused;                   // 1: nothing reads the raw output (its only consumer is a fused GroupNorm): GNE kernels skip the store
+  CUtensorMap tmP[2];               // GNE: the targets' tensors, same pixel box as tmO
   const float* ss;                  // time-embedding table [ss_rows][ss_stride]; ss_rows (1 or B) is patched per forward
   int ss_rows;
   int64_t ss_stride;
@@ -61,6 +66,7 @@ struct ConvLaunch {
 // convolution's channels or straddle an N tile).
 int conv_set_post(ConvLaunch* L, int n, const ConvLaunch::Post* targets, const float* ss, int64_t ss_stride);
 bool conv_post_capable(const ConvLaunch& L);
+bool conv_gne_capable(const ConvLaunch& L, int n_targets);
 
 // Fills geometry + tensor maps.  in: NHWC bf16 [B, H, W, C_in]; w: bf16 [C_out_pad][taps*C_in + C_s0 + C_s1] (K contiguous);
 // skip sources NHWC bf16 [B, H_out, W_out, C_s*].  Returns DLPM_OK or an error code (message via set_error).
@@ -85,7 +91,7 @@ struct ConvFuse {
 
 int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, const void* skip0, int C_s0, const void* skip1,
               int C_s1, const void* residual, void* out, int out_mode, int64_t B, int H, int W, int C_in, int C_out, ConvGeom geom,
-              int stride, const ConvFuse* fuse = nullptr);
+              int stride, const ConvFuse* fuse = nullptr, bool want_gne = false);
 int conv_launch(const ConvLaunch& L, cudaStream_t stream);
 int conv_stats_parts(const ConvLaunch& L);
 int conv_cta_group_override();

@@ -81,6 +81,8 @@ int groupnorm_from_stats_dir(void* out, const void* in0, int C0, const float* st
 // than the 126 MB L2 that is still resident.  Walking the same direction twice hits nothing (LRU).
 static bool g_traverse_alternate = true;
 void engine_set_traverse_alternate(bool on) { g_traverse_alternate = on; }
+static bool g_gne_skip_raw = true;  // GNE convolutions whose raw output has no other reader do not store it (debug: 0 keeps the store)
+void engine_set_gne_skip_raw(bool on) { g_gne_skip_raw = on; }
 static bool g_gn_stats_enabled = true;
 static int g_gn_fuse_mode = 0;  // 0 = never (default, see DESIGN.md: the transform does not hide behind the MMAs yet), 1 = final conv only, 2 = all
 void engine_set_gn_stats(bool on) { g_gn_stats_enabled = on; }
@@ -100,7 +102,7 @@ static int plan_conv(UNetEngine* E, const Op& op, int64_t B, const ConvFuse* fus
                    in_override ? C_in0 : (int)op.f[10], (int)op.f[11],
                    ConvGeom{(int)op.f[16], (int)op.f[17], (int)op.f[18], (int)op.f[19], (int)op.f[20], (int)op.f[21], (int)op.f[22],
                             (int)op.f[23]},
-                   (int)op.f[13], fuse);
+                   (int)op.f[13], fuse, op.f[24] >= 0 || op.f[24 + kPostFields] >= 0);
 }
 
 static int build_plan(UNetEngine* E, int64_t B, Plan* P) {
@@ -142,6 +144,7 @@ static int build_plan(UNetEngine* E, int64_t B, Plan* P) {
         if (g_gn_fuse_mode > 0 && f[10] == 1 && oi + 1 < E->ops.size()) {
           const Op& nx = E->ops[oi + 1];
           if (nx.f[0] == OP_CONV && nx.f[1] == f[3] && nx.f[10] == C && nx.f[12] == 3 && nx.f[13] == 1 && nx.f[20] == 1 &&
+              nx.f[24] < 0 && nx.f[24 + kPostFields] < 0 /* a conv that carries fused GroupNorm targets keeps the plain operand path */ &&
               (nx.f[2] < 0 || (nx.f[2] != f[1] && nx.f[2] != f[2])) /* the conv must not overwrite the raw tensors it now reads */ &&
               (g_gn_fuse_mode == 2 || nx.f[11] <= 16) /* measured: only the thin final conv hides the transform */) {
             float* ab = nullptr;
@@ -177,12 +180,15 @@ static int build_plan(UNetEngine* E, int64_t B, Plan* P) {
       // fused GroupNorm targets (fields 24..): this convolution applies the GroupNorm(s) of its consumers itself
       ConvLaunch::Post targets[2];
       int n_t = 0;
+      bool raw_unused = false;
       for (int k = 0; k < 2; ++k) {
-        const int64_t* tf = f + 24 + kPostFields * k;  // dst buffer, dst_C, c_off, cpg, gamma_off, beta_off, ss_off, silu
+        // dst buffer, dst_C, c_off, cpg, gamma_off, beta_off, ss_off, flags (bit 0: SiLU, bit 1: this GroupNorm is the ONLY reader of the raw output)
+        const int64_t* tf = f + 24 + kPostFields * k;
         if (tf[0] < 0) continue;
         ConvLaunch::Post& t = targets[n_t++];
         t.dst = E->buf(tf[0], B); t.dst_C = (int)tf[1]; t.c_off = (int)tf[2]; t.cpg = (int)tf[3];
-        t.gamma = E->wf + tf[4]; t.beta = E->wf + tf[5]; t.ss_off = tf[6]; t.silu = (int)tf[7];
+        t.gamma = E->wf + tf[4]; t.beta = E->wf + tf[5]; t.ss_off = tf[6]; t.silu = (int)(tf[7] & 1);
+        raw_unused = raw_unused || (tf[7] & 2) != 0;
       }
       if ((parts > 0 && g_gn_stats_enabled && L.C_out % 128 == 0) || n_t > 0) {
         if (parts <= 0) { set_error("unet plan: a convolution with fused GroupNorm targets cannot emit statistics"); return DLPM_ERR_UNSUPPORTED; }
@@ -193,6 +199,7 @@ static int build_plan(UNetEngine* E, int64_t B, Plan* P) {
       }
       if (n_t > 0) {
         if (int rc2 = conv_set_post(&L, n_t, targets, E->ss, E->header[7])) return rc2;
+        L.raw_unused = (L.gne && raw_unused && g_gne_skip_raw) ? 1 : 0;
       }
     }
   }

@@ -307,6 +307,9 @@ class UNetModel(nn.Module):
     # measured slower inside the graph-replayed loop on B200 at every resolution (profiles/r02_groupnorm_producer_side.md)
     fuse_groupnorm = False
     fuse_groupnorm_max_pixels = 64  # ... when on: feature maps up to this many pixels (8x8); 1024 = everywhere
+    # GroupNorm applied in the producing convolution's EPILOGUE, straight from the TMEM accumulators (csrc/conv_tc.cu, GNE): maps of
+    # 256 pixels (16x16), where a CTA pair's accumulator stage holds one whole sample.  ON by default.
+    fuse_groupnorm_epilogue = True
 
     def __init__(self, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions, dropout=0,
                  channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2, num_classes=None, use_checkpoint=False,
@@ -361,7 +364,7 @@ class UNetModel(nn.Module):
         self._cache = _PackedCache()
 
     # ------------------------------------------------------------------ architecture walk -> op list
-    def build_program(self, H, W, reuse_scratch=True, fuse_gn=True):
+    def build_program(self, H, W, reuse_scratch=True, fuse_gn=True, fuse_gne=None):
         """Walk forward() (unet.py:463-492) and emit (header, ops, buffer sizes, bf16 blob, fp32 blob, debug names).
 
         ``fuse_gn``: a GroupNorm (+ scale-shift, SiLU) whose input -- or both halves of whose concatenated input -- was
@@ -371,6 +374,7 @@ class UNetModel(nn.Module):
         concatenation (C0 + C1 a multiple of 128, C0 a multiple of the group size); everything else stays an OP_GN."""
         dev = next(self.parameters()).device
         mc, nh = self.model_channels, self.num_heads
+        fuse_gne = self.fuse_groupnorm_epilogue if fuse_gne is None else bool(fuse_gne)
         ops, bufs, names = [], [], {}
         producer = {}  # activation buffer -> index of the conv op whose (post-capable) output it currently holds
         wb_parts, wf_parts = [], []
@@ -415,7 +419,7 @@ class UNetModel(nn.Module):
             f[24], f[24 + POST_FIELDS] = -1, -1  # no fused GroupNorm targets
             ops.append([int(v) for v in f])
 
-        def group_norm(parts, HW, norm, ss_off, silu, tmp=True):
+        def group_norm(parts, HW, norm, ss_off, silu, tmp=True, sole_reader=False):
             """GroupNorm over the concatenation of ``parts`` = [(buffer, channels)]: attached to the producing convolutions
             when possible, else an OP_GN.  Returns the buffer that holds the normalised tensor."""
             C = sum(c for _, c in parts)
@@ -425,11 +429,14 @@ class UNetModel(nn.Module):
             # those convolutions already move 6x their output through the L2 -> SM fabric (0.88 of its ~12 TB/s) and the
             # re-read + write of the normalised rows adds 2x more; on 4x4 / 8x8 maps the tail of dependent L2 round trips
             # (store completion -> statistics -> parameters -> rows) costs what the separate 8.7 us kernel costs.
-            if fuse_gn and C % 128 == 0 and 128 % cpg == 0 and HW <= self.fuse_groupnorm_max_pixels:
+            gne = fuse_gne and HW == 256 and 32 % cpg == 0  # epilogue variant: the group must lie inside a 32-channel chunk
+            if (gne or (fuse_gn and HW <= self.fuse_groupnorm_max_pixels)) and C % 128 == 0 and 128 % cpg == 0:
                 c_off = 0
                 for b, c in parts:
                     pi = producer.get(b)
                     slot = None if pi is None else (0 if ops[pi][24] < 0 else (1 if ops[pi][24 + POST_FIELDS] < 0 else None))
+                    if gne and slot is not None and (c not in (128, 256) or (slot == 1 and c == 256)):
+                        slot = None  # GNE kernels: one N tile of 128 / 256 channels; the shared-memory tables of a 256-channel tile hold one target
                     if slot is None or c_off % cpg or c % cpg:
                         plan = []
                         break
@@ -439,7 +446,9 @@ class UNetModel(nn.Module):
                 dst = new_buf(HW * C)  # dedicated: written while the producers run, i.e. before this point of the walk
                 g_off, b_off = add_f(norm.weight), add_f(norm.bias)
                 for pi, slot, c_off in plan:
-                    ops[pi][24 + POST_FIELDS * slot: 24 + POST_FIELDS * (slot + 1)] = [dst, C, c_off, cpg, g_off, b_off, ss_off, silu]
+                    # flags: bit 0 SiLU, bit 1 "this GroupNorm is the only reader of the producer's raw output" (the GNE kernel then skips that store)
+                    ops[pi][24 + POST_FIELDS * slot: 24 + POST_FIELDS * (slot + 1)] = [dst, C, c_off, cpg, g_off, b_off, ss_off,
+                                                                                      silu | (2 if sole_reader else 0)]
                 return dst
             p = list(parts) + [(-1, 0)] * (2 - len(parts))
             dst = new_buf(HW * C, tmp=tmp)
@@ -486,7 +495,7 @@ class UNetModel(nn.Module):
             h1 = new_buf(hw * C_out, tmp=True)
             conv(a1, C_in, H_, W_, rb.in_layers[2].weight, rb.in_layers[2].bias, h1)
             release(a1)
-            a2 = group_norm([(h1, C_out)], hw, rb.out_layers[0], ss_off[0], 1)
+            a2 = group_norm([(h1, C_out)], hw, rb.out_layers[0], ss_off[0], 1, sole_reader=True)  # h1 is released right below
             emb_w.append(rb.emb_layers[1].weight)
             emb_b.append(rb.emb_layers[1].bias)
             ss_off[0] += 2 * C_out
@@ -601,7 +610,7 @@ class UNetModel(nn.Module):
         attribute ``fuse_groupnorm``, True) attaches GroupNorms to their producing convolutions (``build_program``)."""
         from . import _unet_lib
         fuse_gn = self.fuse_groupnorm if fuse_gn is None else bool(fuse_gn)
-        key = (H, W, reuse_scratch, fuse_gn, self.fuse_groupnorm_max_pixels)
+        key = (H, W, reuse_scratch, fuse_gn, self.fuse_groupnorm_max_pixels, self.fuse_groupnorm_epilogue)
         version = tuple((p.data_ptr(), _version_of(p)) for p in self.parameters())
         ent = self._engines.get(key)
         if ent is not None and (ent.version != version or ent.max_batch < max_batch):

@@ -66,6 +66,9 @@ int dlpm_b200_conv2d_post(const void* in, const void* w, const float* bias, cons
  * 1 evaluates a quarter of the softmax exponentials on the FMA pipes (measured slower; default -1 / 0 = all on MUFU.EX2).
  * Takes effect for descriptors built afterwards. */
 int dlpm_b200_set_option(const char* name, int value);
+/* Launch counters since library load (tests / bench use them to prove which kernel flavour ran): "conv_launches",
+ * "conv_post_launches" (GroupNorm by the post warps), "conv_gne_launches" (GroupNorm in the epilogue, straight from TMEM). */
+int dlpm_b200_get_stat(const char* name, int64_t* value);
 
 /* K6. GroupNorm(min(32,C) groups, eps 1e-5) over the virtual concatenation [in0 | in1] of two NHWC bf16
  * tensors, optional scale-shift conditioning y = GN(x) * (1 + scale) + shift, optional SiLU; bf16 NHWC out

@@ -101,7 +101,7 @@ def interpret(prog, x, t, mc, emulate_bf16=False):
                         yn = yn * wf[goff + c_off:goff + c_off + cout][None, :, None, None] + wf[boff2 + c_off:boff2 + c_off + cout][None, :, None, None]
                         if ssoff >= 0:
                             yn = yn * (1 + ss[:, ssoff + c_off:ssoff + c_off + cout, None, None]) + ss[:, ssoff + dC + c_off:ssoff + dC + c_off + cout, None, None]
-                        if silu:
+                        if silu & 1:  # bit 1: "sole reader of the raw output" (GNE kernels skip the raw store)
                             yn = F.silu(yn)
                         if dst not in bufs or bufs[dst].shape[-1] != dC or bufs[dst].shape[1] != Ho:
                             bufs[dst] = torch.zeros(B, Ho, Wo, dC)

@@ -136,7 +136,7 @@ def test_unet_program_matches_oracle_block_plan():
     from oracle import nets
     for mc, attn in ((128, (16,)), (32, (2, 4))):
         m = UNetModel(3, mc, 3, 2, attn, channel_mult=(1, 2, 2, 2), num_heads=4, use_scale_shift_norm=True)
-        prog = m.build_program(32, 32, fuse_gn=False)
+        prog = m.build_program(32, 32, fuse_gn=False, fuse_gne=False)
         inp, out = nets.unet_block_plan(mc, (1, 2, 2, 2), 2, attn)
         n_res = sum(l.count("res") for l in inp + out) + 2
         n_attn = sum(l.count("attn") for l in inp + out) + 1
@@ -146,7 +146,7 @@ def test_unet_program_matches_oracle_block_plan():
         # GroupNorms attached to their producing convolutions (default): every GroupNorm is either an op or a fused target
         # (a concatenation's GroupNorm counts once but is carried by BOTH producers)
         m.fuse_groupnorm_max_pixels = 1024
-        fused = m.build_program(32, 32, fuse_gn=True)
+        fused = m.build_program(32, 32, fuse_gn=True, fuse_gne=False)
         fops = [o[0] for o in fused["ops"]]
         dsts = {o[24 + 8 * k] for o in fused["ops"] if o[0] == OP_CONV for k in (0, 1) if o[24 + 8 * k] >= 0}
         assert fops.count(OP_GN) + len(dsts) == 2 * n_res + n_attn + 1
@@ -159,10 +159,18 @@ def test_unet_program_matches_oracle_block_plan():
         assert [o for o in fops if o != OP_GN] == [o for o in ops if o != OP_GN]
         if mc == 128:  # restricted to the 8x8 and 4x4 maps (whole samples inside one tile)
             m.fuse_groupnorm_max_pixels = 64
-            dflt = m.build_program(32, 32, fuse_gn=True)
+            dflt = m.build_program(32, 32, fuse_gn=True, fuse_gne=False)
             d_dsts = {o[24 + 8 * k] for o in dflt["ops"] if o[0] == OP_CONV for k in (0, 1) if o[24 + 8 * k] >= 0}
             assert all(o[8] * o[9] // (o[13] * o[13]) <= 64 for o in dflt["ops"] if o[0] == OP_CONV and o[24] >= 0)
             assert len(d_dsts) == 24 and [o[0] for o in dflt["ops"]].count(OP_GN) + len(d_dsts) == 2 * n_res + n_attn + 1, len(d_dsts)
+        if mc == 128:  # the default engine: GroupNorm in the epilogue (GNE) on the 16x16 maps only, one target per 256-channel conv
+            gne = m.build_program(32, 32, fuse_gn=False)
+            g_ops = [o for o in gne["ops"] if o[0] == OP_CONV and o[24] >= 0]
+            assert all(o[8] * o[9] // (o[13] * o[13]) == 256 and o[24 + 8] < 0 for o in g_ops)
+            g_dsts = {o[24] for o in g_ops}
+            assert [o[0] for o in gne["ops"]].count(OP_GN) + len(g_dsts) == 2 * n_res + n_attn + 1
+            # conv1-type outputs (only reader = the fused GroupNorm) carry the "raw output unused" flag
+            assert len(g_dsts) >= 7 and sum(1 for o in g_ops if o[31] & 2) == 5, (len(g_dsts), [o[31] for o in g_ops])
         n_up = sum(l.count("up") for l in inp + out)
         n_down = sum(l.count("down") for l in inp + out)
         # an upsample+conv = ONE parity-batched launch; the input conv = bf16 split + ONE tensor-core conv

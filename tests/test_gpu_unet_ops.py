@@ -377,7 +377,43 @@ POST_CASES = [
 ]
 
 
-@pytest.mark.parametrize("case", POST_CASES, ids=lambda c: "B%d_%dx%d_%d-%d_k%d_s%d_dst%d@%d_res%d_ss%d" % (c[0], c[1], c[1], c[2], c[3], c[4], c[5], c[6], c[7], c[8], c[9]))
+# GroupNorm in the EPILOGUE (conv_tc.cu GNE kernels): maps of 256 pixels with CTA pairs -- the pair's accumulator stage is one
+# whole sample, the statistics are exchanged through distributed shared memory and the normalised rows come straight from TMEM
+GNE_CASES = [
+    (40, 16, 256, 256, 3, 1, 256, 0, False, False),   # conv1-type: batch-constant scale / shift (tables filled once)
+    (33, 16, 128, 256, 3, 1, 256, 0, False, True),    # odd batch, per-sample scale / shift (tables refilled per item)
+    (70, 16, 512, 256, 3, 1, 512, 0, True, False),    # K = 4608, identity residual, first half of a 512-channel concat (16-channel groups)
+    (300, 16, 256, 256, 3, 1, 512, 256, False, False),  # several items per CTA pair (parity double buffer), second half of a concat
+    (40, 32, 128, 128, 3, 2, 128, 0, False, False),   # Downsample output at 16x16: N tile of 128 channels, 4-channel groups
+    (36, 16, 256, 256, 1, 1, 256, 0, True, True),     # 1x1
+]
+
+
+def _stat(L, name):
+    import ctypes
+    v = ctypes.c_int64(0)
+    L.call("dlpm_b200_get_stat", name, ctypes.byref(v))
+    return v.value
+
+
+_CASE_ID = lambda c: "B%d_%dx%d_%d-%d_k%d_s%d_dst%d@%d_res%d_ss%d" % (c[0], c[1], c[1], c[2], c[3], c[4], c[5], c[6], c[7], c[8], c[9])
+
+
+@pytest.mark.parametrize("case", GNE_CASES, ids=_CASE_ID)
+def test_conv_with_groupnorm_in_the_epilogue(L, case):
+    n0 = _stat(L, b"conv_gne_launches")
+    test_conv_with_producer_side_groupnorm(L, case)
+    assert _stat(L, b"conv_gne_launches") > n0, "the GNE kernel did not run for this shape"
+    L.call("dlpm_b200_set_option", b"conv_gne", 0)  # the same case through the post warps: both flavours stay covered
+    try:
+        n1 = _stat(L, b"conv_gne_launches")
+        test_conv_with_producer_side_groupnorm(L, case)
+        assert _stat(L, b"conv_gne_launches") == n1
+    finally:
+        L.call("dlpm_b200_set_option", b"conv_gne", 1)
+
+
+@pytest.mark.parametrize("case", POST_CASES, ids=_CASE_ID)
 def test_conv_with_producer_side_groupnorm(L, case):
     import ctypes
     B, H, C_in, C_out, k, stride, dst_C, c_off, use_res, per_sample = case

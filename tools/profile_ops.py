@@ -22,6 +22,7 @@ ap.add_argument("--summary", action="store_true")
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--config", default="cifar", choices=["cifar", "mnist"])
 ap.add_argument("--no-fuse", action="store_true")  # GroupNorm as separate launches (round-1 path) instead of the producers' post warps
+ap.add_argument("--no-gne", action="store_true")  # ... and no GroupNorm in the epilogue on the 16x16 maps either
 args = ap.parse_args()
 for o in args.opt:
     k, v = o.split("=")
@@ -33,6 +34,7 @@ else:
 randomize_parameters_(m, 0)
 m = m.cuda().eval()
 m.fuse_groupnorm = not args.no_fuse
+m.fuse_groupnorm_epilogue = not args.no_gne
 B = args.batch
 eng = m.engine(32, 32, B)
 x = torch.randn(B, 1 if args.config == "mnist" else 3, 32, 32, device="cuda")
