@@ -70,6 +70,9 @@ struct ConvKParams {
   int n_par, c_out_pad;   // n_par = 4: the four output-parity 2x2 convs of a folded upsample+conv3x3 share one launch
   int l2_prefetch, xf_dbg;
   int tall, stage_bytes;  // tall: one (Hb+2)-row activation box per (channel block, dx) serves the three dy taps
+  int dx_taps;            // 3, or 1 = "dx-stacked" thin convolution (the network's final conv): the three horizontal taps are stacked
+                          // along N (N = 3 x 16), ONE unshifted box per channel block feeds them, and the epilogue adds the three
+                          // partial results of neighbouring pixels (lane shuffles): a third of the MMAs and of the activation traffic
   int tma_store;          // bf16 NHWC output through shared memory + cp.async.bulk.tensor stores (one 32 x 32 box per warp and chunk)
   int64_t B;
   int C_out, C_out_real, out_mode;
@@ -303,7 +306,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const int brow0 = par * p.c_out_pad + nt * BLOCK_N + (int)cta_rank * B_ROWS;
         if (p.tall) {
           const int a_tall_bytes = (msub * p.Hb + 2) * p.Wb * BLOCK_K * 2;
-          const int n_sb = 3 * p.cin_blocks + p.s0_blocks + p.s1_blocks;
+          const int n_sb = p.dx_taps * p.cin_blocks + p.s0_blocks + p.s1_blocks;
           if (!POST && p.l2_prefetch && item + item_stride < n_items) {
             // pull the NEXT work item's activation boxes from HBM into L2 now: its TMA loads then see L2 latency only
             const int it2 = (item + item_stride) % items_per_par;
@@ -321,7 +324,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             uint8_t* a_dst = smem + stage * STAGE_BYTES;
             uint8_t* b_dst = a_dst + a_tall_bytes;
             bool main_part; int slot_idx;
-            tall_slot(sb, 3 * p.cin_blocks, p.s0_blocks + p.s1_blocks, !XF, main_part, slot_idx);
+            tall_slot(sb, p.dx_taps * p.cin_blocks, p.s0_blocks + p.s1_blocks, !XF, main_part, slot_idx);
             const int a_bytes = main_part ? a_tall_bytes : msub * A_BYTES, b_bytes = main_part ? 3 * B_BYTES : B_BYTES;
             // XF: activations complete on this CTA's own fullA barrier (its transform warps wait there), weights on full
             const int bytes = XF ? b_bytes : a_bytes + b_bytes;
@@ -335,7 +338,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             if (XF) mbar_expect_tx_e(elected, fullA_bar + stage, a_bytes);
             const int brow = brow0;
             if (main_part) {
-              const int cblk = slot_idx / 3, dxi = slot_idx - cblk * 3;
+              const int cblk = p.dx_taps == 3 ? slot_idx / 3 : slot_idx, dxi = p.dx_taps == 3 ? slot_idx - cblk * 3 : 1;
               if (XF) {
                 const bool src0 = cblk < p.c0_blocks;
                 tma_load_4d_e(elected, src0 ? &tmA : &tmA2, fullA_bar + stage, a_dst, (src0 ? cblk : cblk - p.c0_blocks) * BLOCK_K, dxi - 1, h0 - 1, n0);
@@ -343,7 +346,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               else tma_load_4d_e(elected, &tmA, full_bar + stage, a_dst, cblk * BLOCK_K, dxi - 1, h0 - 1, n0);
 #pragma unroll
               for (int j = 0; j < 3; ++j) {
-                const int kcol = ((j * 3 + dxi) * p.cin_blocks + cblk) * BLOCK_K;
+                const int kcol = (p.dx_taps == 3 ? (j * 3 + dxi) * p.cin_blocks + cblk : j * p.cin_blocks + cblk) * BLOCK_K;
                 if (CG == 2) tma_load_2d_pair_e(elected, &tmB, lead_full, b_dst + j * B_BYTES, kcol, brow);
                 else tma_load_2d_e(elected, &tmB, full_bar + stage, b_dst + j * B_BYTES, kcol, brow);
               }
@@ -417,7 +420,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * msub * BLOCK_N);
         if (p.tall) {
           const int a_tall_bytes = (msub * p.Hb + 2) * p.Wb * BLOCK_K * 2;
-          const int n_sb = 3 * p.cin_blocks + p.s0_blocks + p.s1_blocks;
+          const int n_sb = p.dx_taps * p.cin_blocks + p.s0_blocks + p.s1_blocks;
           const int row_units = (p.Wb * BLOCK_K * 2) >> 4, sub_units = p.Hb * row_units;  // descriptor address units (16 bytes)
           for (int sb = 0; sb < n_sb; ++sb) {
             mbar_wait(full_bar + stage, phase);
@@ -426,7 +429,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
             const uint32_t b_addr = a_addr + a_tall_bytes;
             bool main_part; int slot_idx;
-            tall_slot(sb, 3 * p.cin_blocks, p.s0_blocks + p.s1_blocks, !XF, main_part, slot_idx);
+            tall_slot(sb, p.dx_taps * p.cin_blocks, p.s0_blocks + p.s1_blocks, !XF, main_part, slot_idx);
             // One descriptor pair per stage; every (dy, sub-tile, K step) operand is that descriptor plus a loop-invariant
             // offset in its 16-byte address field (dy = j - 1 shifts by Wb rows = whole swizzle atoms, sub-tile `sub` starts Hb
             // image rows further down, tap j's weight tile follows tap j-1's, a K step of 16 elements is 32 bytes inside the
@@ -951,8 +954,27 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         for (int sub = 0; sub < MS_MAX; ++sub) {
           if (sub < msub && (sub & (EG - 1)) == eg) {  // N = 16: one chunk, the quadrant's two warps take one sub-tile each
             uint32_t r[16];
-            tmem_ld_x16(t_row0 + (uint32_t)(sub * BLOCK_N), r);
-            tmem_ld_wait();
+            if constexpr (BLOCK_N == 48) {
+              // dx-stacked: columns [0,16) hold tap dx = -1 evaluated AT this pixel, [16,32) dx = 0, [32,48) dx = +1; the output pixel w
+              // needs the dx = -1 partial of pixel w - 1 and the dx = +1 partial of pixel w + 1 (same image row: a warp's lanes are
+              // whole image rows, Wb <= 32), zero beyond the row ends (the horizontal zero padding)
+              uint32_t rl[16], rh[16];
+              tmem_ld_x16(t_row0 + (uint32_t)(sub * BLOCK_N), rl);
+              tmem_ld_x16(t_row0 + (uint32_t)(sub * BLOCK_N + 16), r);
+              tmem_ld_x16(t_row0 + (uint32_t)(sub * BLOCK_N + 32), rh);
+              tmem_ld_wait();
+#pragma unroll
+              for (int c = 0; c < 16; ++c) {
+                if (c < p.C_out_real) {  // (warp-uniform; the padded channels are never stored)
+                  const float lo = __shfl_up_sync(0xffffffffu, __uint_as_float(rl[c]), 1);
+                  const float hi = __shfl_down_sync(0xffffffffu, __uint_as_float(rh[c]), 1);
+                  r[c] = __float_as_uint((w_in == 0 ? 0.f : lo) + __uint_as_float(r[c]) + (w_in == p.Wb - 1 ? 0.f : hi));
+                }
+              }
+            } else {
+              tmem_ld_x16(t_row0 + (uint32_t)(sub * BLOCK_N), r);
+              tmem_ld_wait();
+            }
             if (valid) {
               float* dst = reinterpret_cast<float*>(p.out);
               const int64_t hw = (int64_t)p.H_full * p.W_full;
@@ -1198,9 +1220,16 @@ int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, c
                "conv: output H and W must be powers of two with W <= 128");
   const int bk = (C_in0 % 64 == 0 && C_in2 % 64 == 0 && C_s0 % 64 == 0 && C_s1 % 64 == 0) ? 64 : 32;
   if (C_in % bk || C_s0 % bk || C_s1 % bk) { set_error("conv: channel counts must be multiples of 32 (got %d,%d,%d)", C_in, C_s0, C_s1); return DLPM_ERR_UNSUPPORTED; }
-  const int C_out_pad = out_mode == CONV_OUT_F32_NCHW ? 16 : C_out;
+  // n_par == 3: "dx-stacked" thin convolution (ConvGeom): weights [3 x 16][3 * C_in], one N tile of 48 columns
+  const bool dxs = geom.n_par == 3;
+  DLPM_REQUIRE(!dxs || (out_mode == CONV_OUT_F32_NCHW && geom.tap_rows == 3 && geom.tap_cols == 3 && geom.dy0 == -1 && geom.dx0 == -1 &&
+                        stride == 1 && geom.out_scale == 1 && !skip0 && !skip1 && !residual && !fuse && W <= 32 && W % 8 == 0 && H * W >= 128 &&
+                        conv_tall_enabled()),
+               "conv: the dx-stacked form is for the thin fp32 output conv (3x3, stride 1, rows of <= 32 pixels)");
+  const int C_out_pad = dxs ? 48 : (out_mode == CONV_OUT_F32_NCHW ? 16 : C_out);
   int bn;
-  if (out_mode == CONV_OUT_F32_NCHW) { DLPM_REQUIRE(C_out <= 16, "conv: fp32 NCHW output supports <= 16 channels"); bn = 16; }
+  if (dxs) { DLPM_REQUIRE(C_out <= 16, "conv: fp32 NCHW output supports <= 16 channels"); bn = 48; }
+  else if (out_mode == CONV_OUT_F32_NCHW) { DLPM_REQUIRE(C_out <= 16, "conv: fp32 NCHW output supports <= 16 channels"); bn = 16; }
   else if (C_out % 256 == 0) bn = 256;
   else if (C_out % 128 == 0) bn = 128;
   else if (C_out % 64 == 0) bn = 64;
@@ -1222,11 +1251,13 @@ int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, c
   L->tiles_per_img = L->Nb == 1 ? H_out / L->Hb : 0;
   L->n_m_tiles = L->Nb == 1 ? (int)(B * L->tiles_per_img) : (int)((B + L->Nb - 1) / L->Nb);
   L->n_n_tiles = C_out_pad / bn;
-  L->stride = stride; L->taps = geom.tap_rows * geom.tap_cols;
+  L->stride = stride; L->taps = dxs ? 3 : geom.tap_rows * geom.tap_cols;  // (dx-stacked: K = 3 vertical taps x C_in)
+  L->dx_taps = dxs ? 1 : 3;
   L->tap_cols = geom.tap_cols; L->dy0 = geom.dy0; L->dx0 = geom.dx0;
   L->out_scale = geom.out_scale; L->out_oy = geom.out_oy; L->out_ox = geom.out_ox;
   L->H_full = H_out * geom.out_scale; L->W_full = W_out * geom.out_scale;
   L->n_par = geom.n_par == 4 ? 4 : 1;
+  DLPM_REQUIRE(geom.n_par == 1 || geom.n_par == 3 || geom.n_par == 4, "conv: n_par must be 1, 3 (dx-stacked) or 4 (folded upsample)");
   DLPM_REQUIRE(L->n_par == 1 || (geom.out_scale == 2 && geom.tap_rows == 2 && geom.tap_cols == 2),
                "conv: parity batching is for folded upsample convs (2x2 taps, output scale 2)");
   L->cin_blocks = C_in / bk; L->s0_blocks = C_s0 / bk; L->s1_blocks = C_s1 / bk;
@@ -1242,6 +1273,7 @@ int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, c
   L->cta_group = (conv_cta_group_override() == 1) ? 1
                  : ((bn >= 32 && (int64_t)((L->n_m_tiles / L->msub + 1) / 2) * L->n_n_tiles * L->n_par >= 32) ? 2 : 1);
   if (conv_cta_group_override() == 2 && bn >= 32) L->cta_group = 2;
+  if (dxs) L->cta_group = 1;
   // fused GroupNorm targets on a map of 256 pixels: CTA pairs whatever the batch, so that the pair's accumulator stage holds the
   // whole sample and the GroupNorm runs in the epilogue (GNE) instead of the post warps
   if (want_gne && conv_cta_group_override() != 1 && L->Nb == 1 && L->tiles_per_img == 2 && L->msub == 1 && bn >= 128 && geom.n_par != 4) L->cta_group = 2;
@@ -1380,6 +1412,7 @@ static int launch_t(const ConvLaunch& L, cudaStream_t stream) {
   p.H_full = L.H_full; p.W_full = L.W_full;
   p.l2_prefetch = g_l2_prefetch; p.xf_dbg = g_xf_dbg;
   p.tma_store = L.tma_store;
+  p.dx_taps = L.dx_taps;
   p.tall = L.tall; p.stage_bytes = STAGE; p.n_par = L.n_par; p.c_out_pad = L.c_out_pad; p.msub = L.msub;
   p.B = L.B; p.C_out = L.C_out; p.C_out_real = L.C_out_real; p.out_mode = L.out_mode;
   p.bias = L.bias; p.residual = L.residual; p.out = L.out;
@@ -1456,6 +1489,10 @@ int conv_launch(const ConvLaunch& L, cudaStream_t stream) {
   }
   CASE(256, 64) CASE(128, 64) CASE(64, 64) CASE(32, 64) CASE(16, 64)
   CASE(256, 32) CASE(128, 32) CASE(64, 32) CASE(32, 32) CASE(16, 32)
+  if (L.block_n == 48 && !L.xf && L.post_n == 0 && L.cta_group == 1) {  // dx-stacked thin conv
+    if (L.block_k == 64) return launch_t<48, 64, 1, false>(L, stream);
+    if (L.block_k == 32) return launch_t<48, 32, 1, false>(L, stream);
+  }
 #undef CASE
   set_error("conv: no kernel for tile N=%d K=%d", L.block_n, L.block_k);
   return DLPM_ERR_UNSUPPORTED;
@@ -1463,7 +1500,7 @@ int conv_launch(const ConvLaunch& L, cudaStream_t stream) {
 
 }  // namespace dlpm
 
-namespace dlpm { void engine_set_gne_skip_raw(bool on); void engine_set_traverse_alternate(bool on); void attention_set_mma(int on); void attention_set_poly(int v); void gn_apply_set_min_elems(int v); void engine_set_gn_stats(bool on); void engine_set_gn_fuse(int mode); bool process_set_option(const char* name, int value); }
+namespace dlpm { void engine_set_loop_ss_table(bool on); void engine_set_gne_skip_raw(bool on); void engine_set_traverse_alternate(bool on); void attention_set_mma(int on); void attention_set_poly(int v); void gn_apply_set_min_elems(int v); void engine_set_gn_stats(bool on); void engine_set_gn_fuse(int mode); bool process_set_option(const char* name, int value); }
 using namespace dlpm;
 
 int dlpm_b200_get_stat(const char* name, int64_t* value) {
@@ -1492,6 +1529,10 @@ int dlpm_b200_set_option(const char* name, int value) {
   }
   if (std::string(name) == "gn_stats") {
     engine_set_gn_stats(value != 0);
+    return DLPM_OK;
+  }
+  if (std::string(name) == "loop_ss_table") {  // graph_sample: scale / shift rows of all steps computed once per call (default 1)
+    engine_set_loop_ss_table(value != 0);
     return DLPM_OK;
   }
   if (std::string(name) == "gne_skip_raw") {

@@ -26,6 +26,7 @@ struct ConvLaunch {
   int out_scale, out_oy, out_ox;     // output pixel of tile pixel (h, w): (out_scale*h + out_oy, out_scale*w + out_ox)
   int H_full, W_full;                // spatial size of the output TENSOR (= out_scale * H_out, W_out)
   int n_par, c_out_pad;              // parity batching (folded upsample): 4 weight matrices stacked along rows
+  int dx_taps;                       // 3, or 1 = dx-stacked thin conv (ConvGeom::n_par == 3)
   int cin_blocks, s0_blocks, s1_blocks;
   int64_t B;
   int C_out;       // row stride (channels) of the output / residual tensors
@@ -76,7 +77,10 @@ bool conv_gne_capable(const ConvLaunch& L, int n_targets);
 // upsampled tensor in memory.
 struct ConvGeom {
   int tap_rows, tap_cols, dy0, dx0, out_scale, out_oy, out_ox;
-  int n_par;  // 4: run the four parity convs of a folded upsample in one launch (weights stacked [4][C_out][4*C_in]; parity
+  int n_par;  // 3: "dx-stacked" thin fp32-output conv (<= 16 channels, rows of <= 32 pixels): weights [3 (dx) x 16][3 (dy) x C_in], i.e. row
+              // dx * 16 + co, column dy * C_in + c = w[co][c][dy][dx]; one unshifted activation box per channel block feeds all three
+              // horizontal taps (N = 48) and the epilogue sums the partials of neighbouring pixels;
+              // 4: run the four parity convs of a folded upsample in one launch (weights stacked [4][C_out][4*C_in]; parity
               // (py, px) uses taps (dy0 + py + a, dx0 + px + b) and writes output pixels (2h + py, 2w + px)); else 1
 };
 inline ConvGeom conv_geom_default(int ksize) { return ConvGeom{ksize, ksize, -(ksize / 2), -(ksize / 2), 1, 0, 0, 1}; }

@@ -53,6 +53,12 @@ struct UNetEngine {
   int* loop_counter = nullptr;
   float* loop_eps = nullptr;
   float* loop_xin = nullptr;
+  // time conditioning of the whole loop, computed ONCE per call: the scale / shift rows of every step ([steps][ss_total], the
+  // time embedding only depends on the step index), so that a step copies its row instead of running the three GEMV launches
+  float* loop_ss_all = nullptr;
+  float* loop_semb_all = nullptr;
+  float* loop_times = nullptr;
+  int64_t loop_ss_rows = 0;
   cudaGraphExec_t loop_exec = nullptr;
   cudaStream_t loop_stream = nullptr;  // stands in for the legacy default stream, which cannot be captured
   cudaEvent_t loop_ev = nullptr;
@@ -251,8 +257,33 @@ int dlpm_b200_unet_create(void** handle, const int64_t* header, const int64_t* o
   return DLPM_OK;
 }
 
+namespace dlpm {
+static bool g_loop_ss_table = true;  // graph_sample: per-step scale / shift rows from a table computed once per call
+void engine_set_loop_ss_table(bool on) { g_loop_ss_table = on; }
+
+// rows[i] = i * inv_T (the time value the captured step derives from the device counter), or a copy of ss_all[*counter] into ss
+__global__ void k_fill_times(float* __restrict__ t, int n, float inv_T) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) t[i] = (float)i * inv_T;
+}
+__global__ void __launch_bounds__(256) k_copy_ss_row(float4* __restrict__ ss, const float4* __restrict__ ss_all, const int* __restrict__ counter,
+                                                     int64_t quads) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const float4* src = ss_all + (int64_t)(*counter) * quads;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < quads; i += (int64_t)gridDim.x * blockDim.x) ss[i] = __ldg(src + i);
+}
+static int unet_forward_impl(void* handle, const float* x, const float* t, int t_rows, const int* t_dev, float inv_T, float* out,
+                             int64_t B, void* stream, bool ss_ready);
+}  // namespace dlpm
+
 int dlpm_b200_unet_forward(void* handle, const float* x, const float* t, int t_rows, const int* t_dev, float inv_T, float* out,
                            int64_t B, void* stream) {
+  return unet_forward_impl(handle, x, t, t_rows, t_dev, inv_T, out, B, stream, false);
+}
+
+static int dlpm::unet_forward_impl(void* handle, const float* x, const float* t, int t_rows, const int* t_dev, float inv_T, float* out,
+                                   int64_t B, void* stream, bool ss_ready) {
   DLPM_REQUIRE(handle && x && out && (t || t_dev), "unet_forward: NULL argument");
   UNetEngine* E = reinterpret_cast<UNetEngine*>(handle);
   DLPM_REQUIRE(B >= 1 && B <= E->max_batch, "unet_forward: batch exceeds the engine's max_batch");
@@ -271,10 +302,17 @@ int dlpm_b200_unet_forward(void* handle, const float* x, const float* t, int t_r
   int launches = 0;
   const bool prof = !E->prof.empty();
   if (prof) cudaEventRecord(E->prof[0], (cudaStream_t)stream);
-  int rc = dlpm_b200_time_embedding(E->ss, E->semb, t, t_dev, inv_T, rows, mc, ss_total, E->wf + h[8], E->wf + h[9], E->wf + h[10],
-                                    E->wf + h[11], E->wf + h[12], E->wf + h[13], stream);
-  if (rc) return rc;
-  launches += 2;
+  int rc = DLPM_OK;
+  if (ss_ready) {  // captured loop: this step's row of the table computed once per call (dlpm_b200_graph_sample)
+    cudaError_t e = launch_ex(k_copy_ss_row, dim3(8), dim3(256), 0, (cudaStream_t)stream, 1, reinterpret_cast<float4*>(E->ss),
+                              reinterpret_cast<const float4*>(E->loop_ss_all), t_dev, ss_total / 4);
+    if (e != cudaSuccess) return cuda_fail(e, "unet_forward: scale / shift row");
+  } else {
+    rc = dlpm_b200_time_embedding(E->ss, E->semb, t, t_dev, inv_T, rows, mc, ss_total, E->wf + h[8], E->wf + h[9], E->wf + h[10],
+                                  E->wf + h[11], E->wf + h[12], E->wf + h[13], stream);
+    if (rc) return rc;
+    launches += 2;
+  }
   if (prof) cudaEventRecord(E->prof[1], (cudaStream_t)stream);
   size_t ci = 0, oi = 0, gi = 0, cii = 0;
   for (const Op& op : E->ops) {
@@ -437,13 +475,40 @@ int dlpm_b200_graph_sample(void* handle, int mode, float* x, const float* Sigma,
     if (int rc = dlpm_b200_unet_forward(handle, x, lim ? aux : nullptr, 0, E->loop_counter, inv_T, E->loop_eps, B, stream)) return rc;
     E->warmed[B] = true;
   }
+  // scale / shift rows of every step of this call, indexed by the value of the device counter (DLPM / DLIM: the step index t,
+  // time t / T; LIM: position in the table of continuous times): the same kernels and arithmetic as the per-step embedding
+  const int64_t ss_total = h[7];
+  const int table_rows = T;  // counter values 0 .. T-1
+  const bool ss_table = g_loop_ss_table && ss_total % 4 == 0;
+  if (ss_table) {
+    if (E->loop_ss_rows < table_rows) {
+      cudaFree(E->loop_ss_all); cudaFree(E->loop_semb_all); cudaFree(E->loop_times);
+      E->loop_ss_all = E->loop_semb_all = E->loop_times = nullptr;
+      E->loop_ss_rows = 0;
+      const int64_t b0 = (int64_t)table_rows * ss_total * 4, b1 = (int64_t)table_rows * 4 * h[6] * 4;
+      if ((e = cudaMalloc(reinterpret_cast<void**>(&E->loop_ss_all), (size_t)b0)) != cudaSuccess ||
+          (e = cudaMalloc(reinterpret_cast<void**>(&E->loop_semb_all), (size_t)b1)) != cudaSuccess ||
+          (e = cudaMalloc(reinterpret_cast<void**>(&E->loop_times), (size_t)table_rows * 4)) != cudaSuccess)
+        return cuda_fail(e, "graph_sample: scale / shift table");
+      E->workspace_bytes += b0 + b1 + table_rows * 4;
+      E->loop_ss_rows = table_rows;
+    }
+    const float* times = aux;
+    if (!lim) {
+      k_fill_times<<<(table_rows + 255) / 256, 256, 0, s>>>(E->loop_times, table_rows, inv_T);
+      times = E->loop_times;
+    }
+    if (int rc = dlpm_b200_time_embedding(E->loop_ss_all, E->loop_semb_all, times, nullptr, 0.f, table_rows, (int)h[6], ss_total,
+                                          E->wf + h[8], E->wf + h[9], E->wf + h[10], E->wf + h[11], E->wf + h[12], E->wf + h[13], stream))
+      return rc;
+  }
   auto one_step = [&]() -> int {
     const float* xin = x;
     if (scaled) {
       if (int rc = dlpm_b200_scale_by_step(E->loop_xin, x, aux, nullptr, 0, E->loop_counter, T, B, D, stream)) return rc;
       xin = E->loop_xin;
     }
-    if (int rc = dlpm_b200_unet_forward(handle, xin, lim ? aux : nullptr, 0, E->loop_counter, inv_T, E->loop_eps, B, stream)) return rc;
+    if (int rc = unet_forward_impl(handle, xin, lim ? aux : nullptr, 0, E->loop_counter, inv_T, E->loop_eps, B, stream, ss_table)) return rc;
     int rc;
     if (mode == DLPM_LOOP_DLPM)
       rc = dlpm_b200_reverse_step_post(x, E->loop_eps, Sigma, sched, 0, E->loop_counter, T, B, D, flags, nullptr, seed, offset,
@@ -505,6 +570,7 @@ int dlpm_b200_unet_destroy(void* handle) {
   UNetEngine* E = reinterpret_cast<UNetEngine*>(handle);
   cudaFree(E->wb); cudaFree(E->wf); cudaFree(E->slab); cudaFree(E->ss); cudaFree(E->semb);
   cudaFree(E->loop_counter); cudaFree(E->loop_eps); cudaFree(E->loop_xin);
+  cudaFree(E->loop_ss_all); cudaFree(E->loop_semb_all); cudaFree(E->loop_times);
   if (E->loop_exec) cudaGraphExecDestroy(E->loop_exec);
   if (E->loop_ev) cudaEventDestroy(E->loop_ev);
   if (E->loop_stream) cudaStreamDestroy(E->loop_stream);

@@ -310,6 +310,7 @@ class UNetModel(nn.Module):
     # GroupNorm applied in the producing convolution's EPILOGUE, straight from the TMEM accumulators (csrc/conv_tc.cu, GNE): maps of
     # 256 pixels (16x16), where a CTA pair's accumulator stage holds one whole sample.  ON by default.
     fuse_groupnorm_epilogue = True
+    dx_stacked_out_conv = True  # the final conv's horizontal taps stacked along N (csrc/conv_tc.cuh ConvGeom::n_par == 3)
 
     def __init__(self, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions, dropout=0,
                  channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2, num_classes=None, use_checkpoint=False,
@@ -461,17 +462,26 @@ class UNetModel(nn.Module):
             """geom = (tap_rows, tap_cols, dy0, dx0, out_scale, out_oy, out_ox); default: centred ksize x ksize taps."""
             C_out = w.shape[0]
             wk = w.detach().float()
-            wk = wk.permute(0, 2, 3, 1).reshape(C_out, -1) if wk.dim() == 4 else wk.reshape(C_out, -1)
             if geom is None:
                 geom = (ksize, ksize, -(ksize // 2), -(ksize // 2), 1, 0, 0, 1)
             n_par = geom[7]
-            C_out //= n_par  # parity-stacked weights: rows = n_par * C_out
+            if n_par == 3:
+                # dx-stacked thin conv (conv_tc.cuh ConvGeom): rows dx * 16 + co, columns dy * C_in + c = w[co][c][dy][dx]
+                w48 = torch.zeros(3, 16, 3, wk.shape[1], device=wk.device)
+                w48[:, :C_out] = wk.permute(3, 0, 2, 1)  # [dx][co][dy][c]
+                wk = w48.reshape(48, -1)
+                C_out_pad = 48
+            else:
+                wk = wk.permute(0, 2, 3, 1).reshape(C_out, -1) if wk.dim() == 4 else wk.reshape(C_out, -1)
+            if n_par == 4:
+                C_out //= n_par  # parity-stacked weights: rows = n_par * C_out
             bias = b.detach().float()
             if skips:
                 wk = torch.cat([wk, skip_w.detach().float().reshape(C_out, -1)], dim=1)
                 bias = bias + skip_b.detach().float()
             if C_out_pad and C_out_pad > C_out:
-                wk = torch.cat([wk, torch.zeros(C_out_pad - C_out, wk.shape[1], device=wk.device)], dim=0)
+                if n_par != 3:
+                    wk = torch.cat([wk, torch.zeros(C_out_pad - C_out, wk.shape[1], device=wk.device)], dim=0)
                 bias = torch.cat([bias, torch.zeros(C_out_pad - C_out, device=bias.device)])
             s = list(skips) + [(-1, 0)] * (2 - len(skips))
             op(OP_CONV, src, out_buf, s[0][0], s[0][1], s[1][0], s[1][1], residual, H_, W_, C_in, C_out, ksize, stride,
@@ -479,7 +489,7 @@ class UNetModel(nn.Module):
             if out_buf >= 0:
                 # bf16 NHWC outputs of >= 128 channels in one launch (not the four-parity folded upsample) can carry the
                 # GroupNorm of their consumers (conv_tc.cu: conv_post_capable)
-                if n_par == 1 and C_out % 128 == 0 and (C_out_pad is None or C_out_pad == C_out):
+                if n_par == 1 and C_out % 128 == 0 and (C_out_pad is None or C_out_pad == C_out):  # (n_par 3 / 4 never carry targets)
                     producer[out_buf] = len(ops) - 1
                 else:
                     producer.pop(out_buf, None)
@@ -592,7 +602,11 @@ class UNetModel(nn.Module):
             skip = hs.pop()
             h, C, Hc, Wc = run_block(blk, [(h, C), skip], Hc, Wc, "output_blocks.%d" % i)
         a = group_norm([(h, C)], Hc * Wc, self.out[0], -1, 1)
-        conv(a, C, Hc, Wc, self.out[2].weight, self.out[2].bias, -1, C_out_pad=16)
+        if self.dx_stacked_out_conv and Wc <= 32 and Wc % 8 == 0 and Hc * Wc >= 128 and self.out_channels <= 16 and C % 32 == 0:
+            # the thin output conv with its three horizontal taps stacked along N (a third of the MMAs / activation traffic)
+            conv(a, C, Hc, Wc, self.out[2].weight, self.out[2].bias, -1, geom=(3, 3, -1, -1, 1, 0, 0, 3))
+        else:
+            conv(a, C, Hc, Wc, self.out[2].weight, self.out[2].bias, -1, C_out_pad=16)
         ss_total = ss_off[0]
         te = self.time_embed
         p_w0T, p_b0 = add_f(te[0].weight.detach().float().t().contiguous()), add_f(te[0].bias)
@@ -610,7 +624,7 @@ class UNetModel(nn.Module):
         attribute ``fuse_groupnorm``, True) attaches GroupNorms to their producing convolutions (``build_program``)."""
         from . import _unet_lib
         fuse_gn = self.fuse_groupnorm if fuse_gn is None else bool(fuse_gn)
-        key = (H, W, reuse_scratch, fuse_gn, self.fuse_groupnorm_max_pixels, self.fuse_groupnorm_epilogue)
+        key = (H, W, reuse_scratch, fuse_gn, self.fuse_groupnorm_max_pixels, self.fuse_groupnorm_epilogue, self.dx_stacked_out_conv)
         version = tuple((p.data_ptr(), _version_of(p)) for p in self.parameters())
         ent = self._engines.get(key)
         if ent is not None and (ent.version != version or ent.max_batch < max_batch):

@@ -54,11 +54,16 @@ def interpret(prog, x, t, mc, emulate_bf16=False):
         elif code == OP_CONV:
             _, i, o, s0, C0, s1, C1, res, H, W, cin, cout, k, stride, woff, boff = f[:16]
             tr, tc_, dy0b, dx0b, oscale, oyb, oxb, n_par = f[16:24]
+            dxs = n_par == 3  # dx-stacked thin conv: weights [3 (dx) x 16][3 (dy) x C_in] -> back to the plain [16][(dy, dx, c)] layout
             n_par = 4 if n_par == 4 else 1
             rows = 16 if o < 0 else cout
             ntap = tr * tc_
             K = ntap * cin + C0 + C1
-            wall = wb[woff:woff + n_par * rows * K].reshape(n_par, rows, K)
+            if dxs:
+                w48 = wb[woff:woff + 48 * 3 * cin].reshape(3, 16, 3, cin)          # [dx][co][dy][c]
+                wall = w48.permute(1, 2, 0, 3).reshape(1, 16, 9 * cin)            # [co][(dy, dx, c)]
+            else:
+                wall = wb[woff:woff + n_par * rows * K].reshape(n_par, rows, K)
             bias = wf[boff:boff + cout]
             xin = bufs[i].permute(0, 3, 1, 2)
             Ho, Wo = H // stride, W // stride
