@@ -183,7 +183,9 @@ template <bool VEC, int A_MODE>
 __global__ void __launch_bounds__(256) k_sas(float* __restrict__ out, const float* __restrict__ A_in, int64_t n_outer,
                                              int64_t inner, StableParams sp, float clamp_eps, float scale,
                                              uint32_t g_stream, uint64_t seed, uint64_t offset, int64_t sample_base,
-                                             FastDiv fd, int chunk) {
+                                             FastDiv fd, int chunk, int sext) {
+  // sext: the row layout of the "sextet" scheme (rng.cuh; rows that are multiples of 384 elements, A_MODE 0 / 1 / 3) -- these generic
+  // kernels (unaligned tensors, >= 2^31 quads) then evaluate it quad by quad so that every path gives the same field
   const Philox ph(seed);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   if (VEC) {
@@ -207,11 +209,17 @@ __global__ void __launch_bounds__(256) k_sas(float* __restrict__ out, const floa
         const int64_t o = fast ? (int64_t)o32 : q / qpr;
         if (!fast) pos = (uint32_t)(q - o * qpr);
         const uint64_t sample = (uint64_t)(o + sample_base);
-        float4 g = normal_quad(ph, g_stream, offset, sample, pos);
-        if (A_MODE == 1 || A_MODE == 3) {
-          const float sa_iso = s_sa[o - o_first];
-          g.x *= sa_iso; g.y *= sa_iso; g.z *= sa_iso; g.w *= sa_iso;
-        } else if (A_MODE == 2 || A_MODE == 4) {
+        float4 g;
+        if (sext) {
+          g = normal_sextet_quad(ph, g_stream, offset, sample, pos, (A_MODE == 1 || A_MODE == 3) ? s_sa[o - o_first] : 1.0f);
+        } else {
+          g = normal_quad(ph, g_stream, offset, sample, pos);
+          if (A_MODE == 1 || A_MODE == 3) {
+            const float sa_iso = s_sa[o - o_first];
+            g.x *= sa_iso; g.y *= sa_iso; g.z *= sa_iso; g.w *= sa_iso;
+          }
+        }
+        if (A_MODE == 2 || A_MODE == 4) {
           const float4 a = (A_MODE == 2) ? element_A4(ph, sp, STREAM_EPS_A, offset, sample, pos)
                                          : ld_stream(reinterpret_cast<const float4*>(A_in) + q);
           g.x *= __fsqrt_rn(a.x); g.y *= __fsqrt_rn(a.y); g.z *= __fsqrt_rn(a.z); g.w *= __fsqrt_rn(a.w);
@@ -230,15 +238,15 @@ __global__ void __launch_bounds__(256) k_sas(float* __restrict__ out, const floa
       const int64_t i = e - o * inner;
       const uint64_t sample = (uint64_t)(o + sample_base);
       const uint32_t pos = (uint32_t)(i >> 2);
-      float g = sel4(normal_quad(ph, g_stream, offset, sample, pos), (int)(i & 3));
-      if (A_MODE != 0) {
-        float a;
-        if (A_MODE == 1) a = sample_A(ph, sp, STREAM_EPS_A, offset, sample);
-        else if (A_MODE == 3) a = A_in[o];
-        else if (A_MODE == 2) a = sel4(element_A4(ph, sp, STREAM_EPS_A, offset, sample, pos), (int)(i & 3));
-        else a = A_in[e];
-        g = scale * clamp_sym(g * __fsqrt_rn(a), clamp_eps);
-      }
+      float a = 1.0f;
+      if (A_MODE == 1) a = sample_A(ph, sp, STREAM_EPS_A, offset, sample);
+      else if (A_MODE == 3) a = A_in[o];
+      else if (A_MODE == 2) a = sel4(element_A4(ph, sp, STREAM_EPS_A, offset, sample, pos), (int)(i & 3));
+      else if (A_MODE == 4) a = A_in[e];
+      float g;
+      if (sext) g = sel4(normal_sextet_quad(ph, g_stream, offset, sample, pos, A_MODE != 0 ? __fsqrt_rn(a) : 1.0f), (int)(i & 3));
+      else g = sel4(normal_quad(ph, g_stream, offset, sample, pos), (int)(i & 3)) * (A_MODE != 0 ? __fsqrt_rn(a) : 1.0f);
+      if (A_MODE != 0) g = scale * clamp_sym(g, clamp_eps);
       out[e] = g;
     }
   }
@@ -326,6 +334,91 @@ __global__ void __launch_bounds__(256) k_sas_vec(float* __restrict__ out, const 
       if (SCALED && A_MODE != 0) { g.x *= scale; g.y *= scale; g.z *= scale; g.w *= scale; }
       st_stream(optr, g);
       span_advance(span, o, pos);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 fast fill under the "sextet" scheme (rng.cuh): rows of gps granules of 96 quads; a WARP owns one granule per iteration
+// (lane l draws two Philox blocks = twelve normals and writes quads l, 32 + l, 64 + l of the granule: three coalesced 512-byte
+// segments); every CTA owns one contiguous share of the granules (single wave), the per-sample sqrt(A) of a sub-chunk lives in
+// shared memory as in k_sas_vec.  A_MODE 0 (plain normal), 1 (in-kernel isotropic A), 3 (A_in compact).
+// ------------------------------------------------------------------------------------------------
+struct GranSpan {
+  uint32_t ng, gps;        // granules in total / per sample row
+  uint32_t step_o, step_g; // 8 granules (one CTA iteration) expressed as (samples, granules)
+  uint32_t sub;            // sub-chunk length in granules: touches <= kChunkQuads samples
+  uint32_t qpr;            // quads per row
+  FastDiv fd;              // division by gps
+};
+static GranSpan make_gran_span(int64_t n_outer, int64_t inner) {
+  GranSpan s;
+  s.qpr = (uint32_t)(inner / 4);
+  s.gps = s.qpr / 96u;
+  s.ng = (uint32_t)(n_outer * s.gps);
+  s.step_o = 8u / s.gps;
+  s.step_g = 8u % s.gps;
+  s.fd = FastDiv(s.gps);
+  const uint64_t sub = (uint64_t)(kChunkQuads - 2) * s.gps;
+  s.sub = sub > (1u << 28) ? (1u << 28) : (uint32_t)sub;
+  return s;
+}
+
+template <int A_MODE, bool SCALED>
+__global__ void __launch_bounds__(256) k_fill6(float* __restrict__ out, const float* __restrict__ A_in, const GranSpan span, StableParams sp,
+                                               float clamp_eps, float scale, uint32_t g_stream, const __grid_constant__ PhiloxKeys keys,
+                                               uint64_t offset, int64_t sample_base) {
+  const PhiloxRef ph(keys);
+  __shared__ float s_sa[A_MODE != 0 ? kChunkQuads : 1];
+  const uint32_t g_lo = (uint32_t)(((uint64_t)span.ng * blockIdx.x) / gridDim.x), g_hi = (uint32_t)(((uint64_t)span.ng * (blockIdx.x + 1)) / gridDim.x);
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (uint32_t q0 = g_lo; q0 < g_hi; q0 += span.sub) {
+    const uint32_t q1 = q0 + span.sub < g_hi ? q0 + span.sub : g_hi;
+    const uint32_t o_first = span.fd.div(q0);
+    if (A_MODE != 0) {
+      const uint32_t o_last = span.fd.div(q1 - 1);
+      __syncthreads();
+      for (uint32_t sI = threadIdx.x; sI <= o_last - o_first; sI += 256)
+        s_sa[sI] = __fsqrt_rn(A_MODE == 1 ? sample_A(ph, sp, STREAM_EPS_A, offset, (uint64_t)((int64_t)(o_first + sI) + sample_base))
+                                          : __ldg(A_in + o_first + sI));
+      __syncthreads();
+    }
+    uint32_t G = q0 + warp, o, gi;
+    span.fd.divmod(G, o, gi);
+    float4* optr = reinterpret_cast<float4*>(out) + ((uint64_t)o * span.qpr + gi * 96u + lane);
+    const uint64_t step_ptr = (uint64_t)span.step_o * span.qpr + span.step_g * 96u;  // 8 granules further on (before the row wrap)
+    for (; G < q1; G += 8) {
+      const uint64_t sample = (uint64_t)((int64_t)o + sample_base);
+      const uint32_t g = gi * 32u + lane;
+      float sa = 1.0f;
+      bool may_clamp = false;
+      if (A_MODE != 0) {
+        sa = s_sa[o - o_first];
+        may_clamp = clamp_eps >= 0.f && sa * kSextetMaxAbs > clamp_eps;  // |G| <= 6.23 on this lattice
+        if (SCALED && !may_clamp) sa *= scale;
+      }
+      float z[12];
+      {
+        float h[6];
+        normal6(philox_at(ph, g_stream, offset, sample, 2u * g), sa, h);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) z[i] = h[i];
+        normal6(philox_at(ph, g_stream, offset, sample, 2u * g + 1u), sa, h);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) z[6 + i] = h[i];
+      }
+      if (may_clamp) {  // (rare: only samples whose sqrt(A) is within a factor 6.23 of the clamp)
+#pragma unroll
+        for (int i = 0; i < 12; ++i) { z[i] = clamp_sym(z[i], clamp_eps); if (SCALED) z[i] *= scale; }
+      }
+      st_stream(optr, make_float4(z[0], z[1], z[2], z[3]));
+      st_stream(optr + 32, make_float4(z[4], z[5], z[6], z[7]));
+      st_stream(optr + 64, make_float4(z[8], z[9], z[10], z[11]));
+      // advance by 8 granules: (o, gi) += (step_o, step_g) with the row wrap
+      gi += span.step_g;
+      o += span.step_o;
+      optr += step_ptr;
+      if (gi >= span.gps) { gi -= span.gps; ++o; }  // (the flat quad index is continuous across rows: no pointer correction)
     }
   }
 }
@@ -879,12 +972,14 @@ static inline void chunk_grid(int64_t nq, int* chunk, int* grid) {
   *grid = (int)g;
 }
 
+static int g_sextet_enabled = 1;  // "noise_sextet": 0 = every fill uses the quad scheme (four normals per Philox block)
 static int g_k3_variant = 0;   // experiment switches (dlpm_b200_set_option): K3 unroll/occupancy variant,
 static int g_stream_ctas = 0;  // CTAs per SM override for the QuadSpan kernels (0 = per-kernel default)
 bool process_set_option(const char* name, int value) {
   const std::string n(name);
   if (n == "k3_variant") { g_k3_variant = value; return true; }
   if (n == "stream_ctas") { g_stream_ctas = value; return true; }
+  if (n == "noise_sextet") { g_sextet_enabled = value != 0; return true; }
   return false;
 }
 
@@ -933,12 +1028,24 @@ static void launch_sas(bool vec, int grid, int chunk, cudaStream_t s, float* out
                        const StableParams& sp, float clamp_eps, float scale, uint32_t g_stream, uint64_t seed,
                        uint64_t offset, int64_t sample_base) {
   const FastDiv fd((uint32_t)(vec ? inner / 4 : 1));
-  if (vec && span_ok(n_outer, inner)) {
+  // plain normal / isotropic fields whose rows are multiples of 384 elements use the "sextet" scheme (rng.cuh): a property of
+  // (mode, row length) only, so every kernel path below produces the same field
+  const bool sext = (A_MODE == 0 || A_MODE == 1 || A_MODE == 3) && inner % 384 == 0 && g_sextet_enabled;
+  if (vec && span_ok(n_outer, inner) && sext) {
+    if constexpr (A_MODE == 0 || A_MODE == 1 || A_MODE == 3) {
+      const GranSpan span = make_gran_span(n_outer, inner);
+      int64_t gsz = (int64_t)kNumSMs * (g_stream_ctas > 0 ? g_stream_ctas : 8);
+      if (gsz > ((int64_t)span.ng + 7) / 8) gsz = ((int64_t)span.ng + 7) / 8;
+      if (gsz < 1) gsz = 1;
+      if (scale == 1.0f) k_fill6<A_MODE, false><<<(int)gsz, 256, 0, s>>>(out, A_in, span, sp, clamp_eps, scale, g_stream, make_philox_keys(seed), offset, sample_base);
+      else k_fill6<A_MODE, true><<<(int)gsz, 256, 0, s>>>(out, A_in, span, sp, clamp_eps, scale, g_stream, make_philox_keys(seed), offset, sample_base);
+    }
+  } else if (vec && span_ok(n_outer, inner) && !sext) {
     const QuadSpan span = make_span(n_outer, inner);
     if (scale == 1.0f) k_sas_vec<A_MODE, false><<<span_grid(span, 8), 256, 0, s>>>(out, A_in, span, sp, clamp_eps, scale, g_stream, make_philox_keys(seed), offset, sample_base);
     else k_sas_vec<A_MODE, true><<<span_grid(span, 8), 256, 0, s>>>(out, A_in, span, sp, clamp_eps, scale, g_stream, make_philox_keys(seed), offset, sample_base);
-  } else if (vec) k_sas<true, A_MODE><<<grid, 256, 0, s>>>(out, A_in, n_outer, inner, sp, clamp_eps, scale, g_stream, seed, offset, sample_base, fd, chunk);
-  else k_sas<false, A_MODE><<<grid, 256, 0, s>>>(out, A_in, n_outer, inner, sp, clamp_eps, scale, g_stream, seed, offset, sample_base, fd, chunk);
+  } else if (vec) k_sas<true, A_MODE><<<grid, 256, 0, s>>>(out, A_in, n_outer, inner, sp, clamp_eps, scale, g_stream, seed, offset, sample_base, fd, chunk, sext ? 1 : 0);
+  else k_sas<false, A_MODE><<<grid, 256, 0, s>>>(out, A_in, n_outer, inner, sp, clamp_eps, scale, g_stream, seed, offset, sample_base, fd, chunk, sext ? 1 : 0);
 }
 
 int dlpm_b200_sas(float* out, const float* A_in, int64_t n_outer, int64_t inner, int isotropic, float alpha,

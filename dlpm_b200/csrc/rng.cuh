@@ -111,6 +111,54 @@ __device__ __forceinline__ float4 normal4(uint4 r) {
   return make_float4(a.x, a.y, b.x, b.y);
 }
 
+// ------------------------------------------------------------------------------------------------
+// "Sextet" scheme of the K1 fills (plain normal / isotropic SaS tensors whose rows are multiples of 384 elements): SIX N(0,1)
+// from one Philox block instead of four.  The fills are bound by instruction dispatch, a third of it the 14 IMAD.WIDE of
+// Philox4x32-7 (profiles/r02_noise.md); Box-Muller does not need 32 + 23 random bits per pair:
+//   pair j = 0, 1, 2:  radius uniform u = (k + 1/2) 2^-27 from the TOP 27 bits k of word j  (|z| <= sqrt(2 * 28 ln 2) = 6.23;
+//                      the 32-bit lattice of the quad scheme reaches 6.66 -- 4e-10 of the mass lies beyond 6.23),
+//                      angle 2 pi a / 2^15 with the 15-bit a = (bits [10 j, 10 j + 10) of word 3) << 5 | (low 5 bits of word j):
+//                      32768 directions; the marginal law of r cos(theta) on a lattice of N directions differs from the normal
+//                      law only by Bessel terms J_N(t r), i.e. not at all in fp32 for N = 2^15, and radius and angle use
+//                      disjoint bits.
+// Row layout (pure function of the position, independent of the grid): a row is cut into granules of 96 quads (384 elements);
+// generator g = granule * 32 + lane draws the Philox blocks at positions 2 g and 2 g + 1 = twelve normals n[0..12), and quad
+// granule * 96 + 32 j + lane (j = 0, 1, 2) holds n[4 j .. 4 j + 4): a warp writes three fully coalesced 512-byte segments.
+// oracle/philox.py::normal_sextet restates it; tests/test_gpu_noise.py pins it pointwise.
+// ------------------------------------------------------------------------------------------------
+constexpr float kSextetMaxAbs = 6.24f;
+// pair (z0, z1) of the sextet scheme from word w (radius + 5 angle bits) and the 10 angle bits f10s = (f10 << 13) & 0x7FE000 of word 3,
+// both scaled by `scale` (folded into the radius)
+__device__ __forceinline__ float2 box_muller27(uint32_t w, uint32_t f10s, float scale) {
+  const float u = fmaf((float)(w >> 5), 7.450580596923828125e-9f, 3.7252902984619140625e-9f);  // (k + 1/2) 2^-27
+  const float r = sqrt_approx(-1.3862943611198906f * lg2_ftz(u)) * scale;
+  float s, c;
+  __sincosf(6.28318530717958647692f * __uint_as_float(0x3f800000u | f10s | ((w << 8) & 0x1F00u)), &s, &c);  // angle 2 pi m, m in [1, 2)
+  return make_float2(r * c, r * s);
+}
+__device__ __forceinline__ void normal6(uint4 r, float scale, float (&z)[6]) {
+  const float2 a = box_muller27(r.x, (r.w << 13) & 0x7FE000u, scale);
+  const float2 b = box_muller27(r.y, (r.w << 3) & 0x7FE000u, scale);
+  const float2 c = box_muller27(r.z, (r.w >> 7) & 0x7FE000u, scale);
+  z[0] = a.x; z[1] = a.y; z[2] = b.x; z[3] = b.y; z[4] = c.x; z[5] = c.y;
+}
+// generic (slow) access: the quad at position `pos` of a row under the sextet scheme -- fallback paths only
+template <class P>
+__device__ __forceinline__ float4 normal_sextet_quad(const P& ph, uint32_t stream, uint64_t offset, uint64_t sample, uint32_t pos, float scale) {
+  const uint32_t gran = pos / 96u, rem = pos - gran * 96u, j = rem >> 5, g = gran * 32u + (rem & 31u);
+  float n[12];
+  {
+    float z[6];
+    normal6(philox_at(ph, stream, offset, sample, 2u * g), scale, z);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) n[i] = z[i];
+    normal6(philox_at(ph, stream, offset, sample, 2u * g + 1u), scale, z);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) n[6 + i] = z[i];
+  }
+  return j == 0 ? make_float4(n[0], n[1], n[2], n[3]) : (j == 1 ? make_float4(n[4], n[5], n[6], n[7]) : make_float4(n[8], n[9], n[10], n[11]));
+}
+
 __device__ __forceinline__ float rcp_ftz(float x) {
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

@@ -108,6 +108,56 @@ def normal(seed, offset, samples, inner, stream=STREAM_Z):
     return np.stack([a0, a1, b0, b1], axis=-1).reshape(samples.shape[0], inner)
 
 
+def normal6_from_words(w0, w1, w2, w3):
+    """rng.cuh::normal6 -- the "sextet" scheme of the K1 fills: pair j takes its radius from the top 27 bits of word j
+    (u = (k + 1/2) 2^-27) and its 15-bit angle from bits [10 j, 10 j + 10) of word 3 (high part) and the low 5 bits of word j.
+    Returns six arrays (z0 .. z5)."""
+    w = [np.asarray(x, dtype=np.uint32) for x in (w0, w1, w2)]
+    w3 = np.asarray(w3, dtype=np.uint32)
+    out = []
+    for j in range(3):
+        k = (w[j] >> np.uint32(5)).astype(np.float64)
+        u = (k + 0.5) * 2.0 ** -27  # exact in fp32: k < 2^27 needs 27 bits -> the kernel's fmaf rounds; restate that rounding
+        u = (k.astype(np.float32).astype(np.float64) * 2.0 ** -27 + 2.0 ** -28).astype(np.float32).astype(np.float64)
+        r = np.sqrt(-2.0 * np.log(u))
+        a = (((w3 >> np.uint32(10 * j)) & np.uint32(0x3FF)).astype(np.uint64) << np.uint64(5)) | (w[j] & np.uint32(31)).astype(np.uint64)
+        ang = 2.0 * np.pi * a.astype(np.float64) / 2.0 ** 15
+        out += [r * np.cos(ang), r * np.sin(ang)]
+    return out
+
+
+def normal_sextet(seed, offset, samples, inner, stream=STREAM_Z):
+    """N(0,1) field of the K1 fills for rows of inner % 384 == 0 elements (rng.cuh, "sextet" scheme): a row is cut into granules of
+    96 quads; generator g = granule * 32 + lane draws the Philox blocks at positions 2 g and 2 g + 1 = twelve normals, and quad
+    granule * 96 + 32 j + lane holds normals 4 j .. 4 j + 3."""
+    assert inner % 384 == 0
+    samples = np.asarray(samples, dtype=np.uint64)[:, None]
+    n_gen = inner // 12
+    g = np.arange(n_gen, dtype=np.uint64)[None, :]
+    n12 = normal6_from_words(*words(seed, stream, offset, samples, 2 * g)) + normal6_from_words(*words(seed, stream, offset, samples, 2 * g + 1))
+    n12 = np.stack(n12, axis=-1)  # (samples, generators, 12)
+    out = np.empty((samples.shape[0], inner // 4, 4))
+    gran, lane = np.arange(n_gen) // 32, np.arange(n_gen) % 32
+    for j in range(3):
+        out[:, gran * 96 + 32 * j + lane, :] = n12[:, :, 4 * j:4 * j + 4]
+    return out.reshape(samples.shape[0], inner)
+
+
+def normal_fill(seed, offset, samples, inner, stream=STREAM_Z):
+    """What dlpm_b200_normal / dlpm_b200_sas (isotropic) write: the sextet scheme for rows of inner % 384 == 0 elements, else one
+    Philox block per quad (``normal``).  The in-kernel noise of the step kernels always uses ``normal``."""
+    return normal_sextet(seed, offset, samples, inner, stream) if inner % 384 == 0 else normal(seed, offset, samples, inner, stream)
+
+
+def sas_isotropic_fill(alpha, seed, offset, samples, inner, clamp_eps=None):
+    """dlpm_b200_sas, isotropic (x_T of the samplers, gen_sas): sqrt(A_b) * G with G = ``normal_fill`` of the G stream."""
+    A = sample_A(alpha, seed, offset, samples, stream=STREAM_EPS_A)
+    e = np.sqrt(A)[:, None] * normal_fill(seed, offset, samples, inner, stream=STREAM_G)
+    if clamp_eps is not None and clamp_eps >= 0:
+        e = np.clip(e, -clamp_eps, clamp_eps)
+    return e
+
+
 def sas_isotropic(alpha, seed, offset, samples, inner, clamp_eps=None):
     """gen_sas, isotropic: sqrt(A_b) * G with A_b from the EPS_A stream and G from the G stream of the same call offset."""
     A = sample_A(alpha, seed, offset, samples, stream=STREAM_EPS_A)

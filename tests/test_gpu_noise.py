@@ -170,19 +170,61 @@ def test_pointwise_normal_and_sas_against_oracle_on_same_words(dl):
     from oracle import philox
     seed, off, base = 99, 5, 1 << 33  # a sample index beyond 32 bits exercises the high counter bits
     z = dl.gen_normal((256, 3072), device="cuda", state=rng.PhiloxState(seed=seed, offset=off, sample_base=base)).cpu().numpy().astype(np.float64)
-    ref = philox.normal(seed, off, base + np.arange(256), 3072)
+    ref = philox.normal_fill(seed, off, base + np.arange(256), 3072)  # rows of 8 x 384 elements: the sextet scheme
     err = np.abs(z - ref)
     # MUFU.SIN / COS: absolute error ~5e-7 x radius; lg2.approx has an ABSOLUTE error of 2^-22 near u = 1, i.e. on the
     # few draws with a radius below ~1e-2 the radius itself is off by up to ~1e-4
     assert np.quantile(err, 0.9999) < 1e-5 and err.max() < 2e-3, (np.quantile(err, 0.9999), err.max())
     e = dl.gen_sas(1.7, (256, 3, 32, 32), device="cuda", isotropic=True, clamp_eps=200.0,
                    state=rng.PhiloxState(seed=seed, offset=off, sample_base=base)).cpu().numpy().astype(np.float64).reshape(256, -1)
-    refe = philox.sas_isotropic(1.7, seed, off, base + np.arange(256), 3072, clamp_eps=200.0)
+    refe = philox.sas_isotropic_fill(1.7, seed, off, base + np.arange(256), 3072, clamp_eps=200.0)
     # in units of the sample's scale sqrt(A_b): the normal tolerances above plus A's relative error (3e-5) times |G|
     sa = np.sqrt(philox.sample_A(1.7, seed, off, base + np.arange(256), stream=philox.STREAM_EPS_A))[:, None]
     err = np.abs(e - refe) / sa
     assert np.quantile(err, 0.9999) < 3e-4 and err.max() < 3e-3, (np.quantile(err, 0.9999), err.max())
     assert np.abs(e).max() <= 200.0
+
+
+def test_sextet_and_quad_schemes_and_every_kernel_path(dl):
+    """Rows that are multiples of 384 elements use six normals per Philox block (rng.cuh "sextet" scheme), all other rows one block
+    per quad; the vector fast path, the generic vector kernel and the scalar kernel (unaligned output) write the same field."""
+    import torch
+    from dlpm_b200 import _lib, rng
+    from oracle import philox
+    seed, off, base = 1234, 9, 77
+    # quad scheme (rows of 1024 elements)
+    z = dl.gen_normal((64, 1024), device="cuda", state=rng.PhiloxState(seed=seed, offset=off, sample_base=base)).cpu().numpy().astype(np.float64)
+    assert np.quantile(np.abs(z - philox.normal(seed, off, base + np.arange(64), 1024)), 0.9999) < 1e-5
+    assert np.quantile(np.abs(z - philox.normal_fill(seed, off, base + np.arange(64), 1024)), 0.9999) < 1e-5
+    # sextet scheme, rows of 1 and 3 granules; plain normal and isotropic SaS with a scale; aligned (fast kernel) vs a destination
+    # shifted by one float (scalar kernel)
+    for inner in (384, 1152):
+        n = 70
+        ref = philox.normal_fill(seed, off, base + np.arange(n), inner)
+        assert not np.allclose(ref, philox.normal(seed, off, base + np.arange(n), inner))
+        fast = torch.empty(n * inner, device="cuda")
+        slow = torch.empty(n * inner + 1, device="cuda")
+        _lib.call("dlpm_b200_normal", _lib.ptr(fast), n, inner, seed, off, base, _lib.stream_ptr())
+        _lib.call("dlpm_b200_normal", slow.data_ptr() + 4, n, inner, seed, off, base, _lib.stream_ptr())
+        torch.cuda.synchronize()
+        assert np.quantile(np.abs(fast.cpu().numpy().astype(np.float64).reshape(n, inner) - ref), 0.9999) < 1e-5
+        assert torch.equal(fast, slow[1:]), "fast sextet kernel and scalar kernel disagree"
+        assert float(fast.abs().max()) <= 6.24
+        for scale in (1.0, 0.37):
+            _lib.call("dlpm_b200_sas", _lib.ptr(fast), None, n, inner, 1, 1.7, 5.0, scale, seed, off, base, _lib.stream_ptr())
+            _lib.call("dlpm_b200_sas", slow.data_ptr() + 4, None, n, inner, 1, 1.7, 5.0, scale, seed, off, base, _lib.stream_ptr())
+            torch.cuda.synchronize()
+            want = scale * philox.sas_isotropic_fill(1.7, seed, off, base + np.arange(n), inner, clamp_eps=5.0)
+            got = fast.cpu().numpy().astype(np.float64).reshape(n, inner)
+            assert np.quantile(np.abs(got - want), 0.9999) < 1e-4 and np.abs(got).max() <= 5.0 * scale + 1e-6
+            np.testing.assert_allclose(slow[1:].cpu().numpy(), fast.cpu().numpy(), rtol=2e-6, atol=1e-7)
+    # the option switches every fill back to the quad scheme
+    _lib.call("dlpm_b200_set_option", b"noise_sextet", 0)
+    try:
+        z = dl.gen_normal((8, 384), device="cuda", state=rng.PhiloxState(seed=seed, offset=off, sample_base=base)).cpu().numpy().astype(np.float64)
+        assert np.quantile(np.abs(z - philox.normal(seed, off, base + np.arange(8), 384)), 0.9999) < 1e-5
+    finally:
+        _lib.call("dlpm_b200_set_option", b"noise_sextet", 1)
 
 
 def test_error_behaviour(dl):

@@ -346,3 +346,26 @@ def test_restated_caller_matches_generation_manager(is_image, shape, history):
         assert len(gm.history) == 0 and len(hist) == 0
     if is_image:
         assert float(samples.min()) >= 0.0 and float(samples.max()) <= 1.0
+
+
+def test_sextet_scheme_restatement_is_a_standard_normal_field():
+    """oracle/philox.py::normal_sextet (six normals per Philox block, rng.cuh): every position of a row is written exactly once,
+    the field is N(0,1) (KS, moments, tail bound of the 27-bit radius lattice) and differs from the quad scheme."""
+    from scipy import stats
+    from oracle import philox
+    inner = 1152
+    z = philox.normal_sextet(5, 3, np.arange(400), inner)
+    assert z.shape == (400, inner) and np.isfinite(z).all()
+    assert abs(z.mean()) < 5e-3 and abs(z.var() - 1.0) < 1e-2 and abs(stats.kurtosis(z.ravel())) < 3e-2
+    assert stats.kstest(z.ravel()[:200000], "norm").pvalue > 1e-3
+    assert np.abs(z).max() <= np.sqrt(2 * 28 * np.log(2.0)) + 1e-9
+    # neighbouring elements (a Box-Muller pair, and elements of different pairs) are uncorrelated
+    assert abs(np.corrcoef(z[:, 0::2].ravel(), z[:, 1::2].ravel())[0, 1]) < 5e-3
+    assert abs(np.corrcoef(z[:, :-4].ravel(), z[:, 4:].ravel())[0, 1]) < 5e-3
+    # layout: quad 32 j + lane of granule g comes from generator 32 g + lane, normals 4 j .. 4 j + 3
+    w = philox.words(5, philox.STREAM_Z, 3, np.array([7], dtype=np.uint64), np.array([2 * 33, 2 * 33 + 1], dtype=np.uint64))
+    n12 = philox.normal6_from_words(w[0][0], w[1][0], w[2][0], w[3][0]) + philox.normal6_from_words(w[0][1], w[1][1], w[2][1], w[3][1])
+    row = philox.normal_sextet(5, 3, np.array([7]), inner)[0].reshape(-1, 4)
+    for j in range(3):  # generator 33 = granule 1, lane 1
+        np.testing.assert_allclose(row[96 + 32 * j + 1], [float(v) for v in n12[4 * j:4 * j + 4]])
+    assert not np.allclose(z[:4], philox.normal(5, 3, np.arange(4), inner))
