@@ -199,7 +199,7 @@ __host__ __device__ constexpr int conv_threads() {
 // accumulators AGAIN and writes silu((v - mean) * rstd * gamma' + beta') into the consumer's input tensor.  No re-read of the
 // output through L2 (the POST variant's loss), no separate k_gn_apply pass; the second stage keeps the MMAs of the next sample
 // running underneath.
-template <int BLOCK_N, int BLOCK_K, int CG, int KS, bool XF, bool POST, bool GNE>
+template <int BLOCK_N, int BLOCK_K, int CG, int KS, bool XF, bool POST, int GNE>
 __global__ void __launch_bounds__(conv_threads<BLOCK_N, XF, POST>(), 1)
 k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmS0,
           const __grid_constant__ CUtensorMap tmS1, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
@@ -225,7 +225,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   constexpr int EG = conv_epi_groups<BLOCK_N, XF>();
   static_assert(!(XF && POST), "normalise-on-load and the producer-side GroupNorm are alternatives");
   static_assert(!POST || (BLOCK_N >= 128 && EG == 2), "POST kernels: N tiles of 128 / 256 channels");
-  static_assert(!GNE || (!XF && !POST && CG == 2 && BLOCK_N >= 128 && EG == 2), "GNE kernels: CTA pairs, N tiles of 128 / 256 channels");
+  static_assert(!GNE || (!XF && !POST && BLOCK_N >= 128 && EG == 2), "GNE kernels: N tiles of 128 / 256 channels");
+  static_assert(GNE != 1 || CG == 2, "GNE mode 1 (the pair's accumulator stage = one sample): CTA pairs");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -276,7 +277,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     if (POST) {
       for (int a = 0; a < 2; ++a) { mbar_init(ready_bar + a, (uint32_t)(4 * EG) << ipu_log); mbar_init(free_bar + a, 1); }
     }
-    if (GNE) { mbar_init(xf_bar, BLOCK_N / 2); mbar_init(xf_bar + 1, BLOCK_N / 2); }  // statistics exchange (one barrier per item parity)
+    if (GNE == 1) { mbar_init(xf_bar, BLOCK_N / 2); mbar_init(xf_bar + 1, BLOCK_N / 2); }  // statistics exchange (one barrier per item parity)
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -566,13 +567,14 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     // GNE: per-target coefficient tables behind the bias vector, A = gamma (1 + scale), B = beta (1 + scale) + shift (halved for the
     // one-MUFU SiLU form), so that pass 2 evaluates y = ((v - mean) rstd) A + B.  Batch-constant in sampling (ss_rows == 1): filled
     // once per kernel; per-sample time steps refill them per item.
-    float* const s_gA = s_bias + BLOCK_N;
-    float* const s_gB = s_gA + p.post_n * BLOCK_N;
-    float* const s_tot = s_gB + p.post_n * BLOCK_N;  // [2 item parities][2 CTA ranks][BLOCK_N / 2] quad (sum, sum of squares) totals
-    float* const s_rn = s_tot + 2 * BLOCK_N;         // [targets][BLOCK_N / 4] (rstd, -mean rstd) of every quad's group, current item
+    const int CT = p.c_out_pad;  // table rows cover every output channel (mode 1: one N tile = all channels; mode 2: any number of N tiles)
+    float* const s_gA = s_bias + CT;
+    float* const s_gB = s_gA + p.post_n * CT;
+    float* const s_tot = s_gB + p.post_n * CT;       // mode 1: [2 item parities][2 CTA ranks][BLOCK_N / 2] quad (sum, sum of squares) totals
+    float* const s_rn = s_tot + 2 * BLOCK_N;         // mode 1: [targets][BLOCK_N / 4] (rstd, -mean rstd) of every quad's group, current item
     auto gne_fill_tables = [&](int64_t n) {
-      for (int i = (int)threadIdx.x - 128; i < p.post_n * BLOCK_N; i += 128 * EG) {
-        const int k = i / BLOCK_N, ch = i - k * BLOCK_N;
+      for (int i = (int)threadIdx.x - 128; i < p.post_n * CT; i += 128 * EG) {
+        const int k = i / CT, ch = i - k * CT;
         const PostTarget& tg = p.post[k];
         const int ct = tg.c_off + ch;
         float ga = __ldg(tg.gamma + ct), be = __ldg(tg.beta + ct);
@@ -582,11 +584,13 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           ga *= sc;
           be = be * sc + sh;
         }
-        s_gA[i] = ga * 0.5f;  // GNE targets end in SiLU (host-checked): silu(y) = h + h tanh(h) with h = y / 2
-        s_gB[i] = be * 0.5f;
+        const float osc = tg.silu ? 0.5f : 1.0f;  // silu(y) = h + h tanh(h) with h = y / 2
+        s_gA[i] = ga * osc;
+        s_gB[i] = be * osc;
       }
     };
-    if (GNE && p.ss_rows == 1) gne_fill_tables(0);
+    // (mode 2 only runs with one table per kernel: batch-constant rows, or no target that reads them -- gne2_needs_post_warps)
+    if (GNE == 2 || (GNE == 1 && p.ss_rows == 1)) gne_fill_tables(0);
     asm volatile("bar.sync 1, %0;" ::"n"(128 * EG) : "memory");
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     const int eg = (warp - 4) >> 2;  // which half of the column chunks (EG == 2)
@@ -610,7 +614,155 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const int64_t nn = (int64_t)n0 + n_in;
       const bool valid = nn < p.B;
       const uint32_t t_row0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * msub * BLOCK_N);
-      if constexpr (GNE) {
+      if constexpr (GNE == 2) {
+        // ---------- GroupNorm in the epilogue, 4x4 maps: a warp's 32 tile rows are TWO WHOLE SAMPLES (half warps), so the statistics
+        // never leave the warp and the chunk is normalised from the registers it was loaded into -- one TMEM pass, no exchange ----------
+        constexpr int NCH = BLOCK_N / 32, CPW = NCH / EG;
+        uint4 resv[CPW * 4];
+        const bool has_res = p.residual != nullptr && valid;
+        const int64_t pix = (nn * p.H_full + h_in) * p.W_full + w_in;
+        if (has_res) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.C_out + nt * BLOCK_N);
+#pragma unroll
+          for (int ci = 0; ci < CPW; ++ci)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) resv[ci * 4 + j] = __ldg(rp + (ci * EG + eg) * 4 + j);
+        }
+        mbar_wait(tfull_bar + acc, acc_phase);
+        tc_fence_after();
+        const float inv_hw = 1.0f / (float)(p.H_full * p.W_full);
+#pragma unroll
+        for (int ci = 0; ci < CPW; ++ci) {
+          const int c0 = (ci * EG + eg) * 32, col = nt * BLOCK_N + c0;
+          uint32_t r[32];
+          tmem_ld_x32(t_row0 + c0, r);
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
+          tmem_ld_wait();
+          float2 v[16];
+          float st[16];
+          {
+            const uint32_t bias_s = smem_u32(s_bias) + (uint32_t)col * 4u;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const float4 b0 = lds_f4(bias_s + j * 4), b1 = lds_f4(bias_s + j * 4 + 16);
+              v[j / 2 + 0] = __fadd2_rn(make_float2(__uint_as_float(r[j + 0]), __uint_as_float(r[j + 1])), make_float2(b0.x, b0.y));
+              v[j / 2 + 1] = __fadd2_rn(make_float2(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])), make_float2(b0.z, b0.w));
+              v[j / 2 + 2] = __fadd2_rn(make_float2(__uint_as_float(r[j + 4]), __uint_as_float(r[j + 5])), make_float2(b1.x, b1.y));
+              v[j / 2 + 3] = __fadd2_rn(make_float2(__uint_as_float(r[j + 6]), __uint_as_float(r[j + 7])), make_float2(b1.z, b1.w));
+              if (has_res) {
+                const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&resv[ci * 4 + j / 8]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[j / 2 + e] = __fadd2_rn(v[j / 2 + e], __bfloat1622float2(rp[e]));
+              }
+              if (p.gne_raw) {
+                uint4 o;
+                __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) op[e] = __float22bfloat162_rn(v[j / 2 + e]);
+                sts_u4(my_row + (uint32_t)(((j >> 3) ^ ((lane >> 1) & 3)) << 4), o);
+              }
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int qi = (j / 4 + h) * 2;
+                const float2 s2 = __fadd2_rn(v[j / 2 + 2 * h], v[j / 2 + 2 * h + 1]);
+                const float2 q2 = __ffma2_rn(v[j / 2 + 2 * h + 1], v[j / 2 + 2 * h + 1], __fmul2_rn(v[j / 2 + 2 * h], v[j / 2 + 2 * h]));
+                st[qi] = s2.x + s2.y;
+                st[qi + 1] = q2.x + q2.y;
+              }
+            }
+          }
+          if (p.gne_raw) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d(&tmO, reinterpret_cast<const void*>(epi_stage + (warp - 4) * kEpiStageBytes), col, w_box, h_box, n0 + n_box);
+              bulk_commit();
+            }
+          }
+          // transposing butterfly inside each half warp (8 + 4 + 2 + 1 shuffles): lane l ends with the total of value l & 15 over its sample
+#pragma unroll
+          for (int half = 8, off = 8; half >= 1; half >>= 1, off >>= 1) {
+            const bool up = (lane & off) != 0;
+#pragma unroll
+            for (int k = 0; k < half; ++k) {
+              const float send = up ? st[k] : st[k + half];
+              const float keepv = up ? st[k + half] : st[k];
+              st[k] = keepv + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+          }
+          if (p.stats != nullptr && valid) {  // other (unfused) GroupNorms still read the partial rows
+            const int64_t row = nn * p.stats_parts + par;
+            p.stats[(row * (p.C_out >> 2) + (col >> 2)) * 2 + (lane & 15)] = st[0];
+          }
+          // every lane needs the totals of all eight quads of its sample
+          float qs[8], qq2[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            qs[k] = __shfl_sync(0xffffffffu, st[0], (lane & 16) | (2 * k));
+            qq2[k] = __shfl_sync(0xffffffffu, st[0], (lane & 16) | (2 * k + 1));
+          }
+#pragma unroll 1
+          for (int k = 0; k < p.post_n; ++k) {
+            const PostTarget& tg = p.post[k];
+            const int nqg = tg.cpg >> 2;  // quads per group: 1, 2, 4 or 8 (cpg divides 32) -- xor-butterfly on the static arrays
+            float gs[8], gq[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { gs[j] = qs[j]; gq[j] = qq2[j]; }
+#pragma unroll
+            for (int step = 1; step < 8; step <<= 1) {
+              if (nqg > step) {
+                float ts[8], tq[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { ts[j] = gs[j & ~step] + gs[j | step]; tq[j] = gq[j & ~step] + gq[j | step]; }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { gs[j] = ts[j]; gq[j] = tq[j]; }
+              }
+            }
+            const float inv_n = inv_hw / (float)tg.cpg;
+            float2 rn2[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float mean = gs[j] * inv_n;
+              const float rstd = rsqrtf(fmaxf(gq[j] * inv_n - mean * mean, 0.f) + 1e-5f);
+              rn2[j] = make_float2(rstd, -mean * rstd);
+            }
+            const uint32_t tabA = smem_u32(s_gA) + (uint32_t)((k * CT + col) * 4), tabB = smem_u32(s_gB) + (uint32_t)((k * CT + col) * 4);
+            uint4 o[4];
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const float4 A0 = lds_f4(tabA + j * 4), A1 = lds_f4(tabA + j * 4 + 16), B0 = lds_f4(tabB + j * 4), B1 = lds_f4(tabB + j * 4 + 16);
+              const float2 Aa[4] = {make_float2(A0.x, A0.y), make_float2(A0.z, A0.w), make_float2(A1.x, A1.y), make_float2(A1.z, A1.w)};
+              const float2 Bb[4] = {make_float2(B0.x, B0.y), make_float2(B0.z, B0.w), make_float2(B1.x, B1.y), make_float2(B1.z, B1.w)};
+              __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&o[j >> 3]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 rq = rn2[j / 4 + e / 2];
+                const float2 t2 = __ffma2_rn(v[j / 2 + e], make_float2(rq.x, rq.x), make_float2(rq.y, rq.y));
+                float2 y2 = __ffma2_rn(t2, Aa[e], Bb[e]);
+                if (tg.silu) {  // (warp-uniform) tables pre-halved: silu(y) = h + h tanh(h)
+                  float2 th;
+                  asm("tanh.approx.f32 %0, %1;" : "=f"(th.x) : "f"(y2.x));
+                  asm("tanh.approx.f32 %0, %1;" : "=f"(th.y) : "f"(y2.y));
+                  y2 = __ffma2_rn(y2, th, y2);
+                }
+                op[e] = __float22bfloat162_rn(y2);
+              }
+            }
+            if (lane == 0) bulk_wait_read0();  // the raw box / the previous target's box has been read out
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sts_u4(my_row + (uint32_t)((j ^ ((lane >> 1) & 3)) << 4), o[j]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d(k == 0 ? &tmP0 : &tmP1, reinterpret_cast<const void*>(epi_stage + (warp - 4) * kEpiStageBytes), tg.c_off + col, w_box,
+                           h_box, n0 + n_box);
+              bulk_commit();
+            }
+          }
+        }
+      } else if constexpr (GNE == 1) {
         // ---------- GroupNorm in the epilogue: the pair's accumulator stage is one whole sample (msub == 1, two tiles per image) ----------
         constexpr int NCH = BLOCK_N / 32, CPW = NCH / EG, NQV = BLOCK_N / 2;
         if (p.ss_rows != 1) {  // per-sample time steps: this sample's scale / shift rows (the previous item's pass 2 is over)
@@ -777,7 +929,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               if (lane == 0) bulk_wait_read0();  // the first target's box
               __syncwarp();
             }
-            const uint32_t tabA = smem_u32(s_gA) + (uint32_t)((k * BLOCK_N + c0) * 4), tabB = smem_u32(s_gB) + (uint32_t)((k * BLOCK_N + c0) * 4);
+            const uint32_t tabA = smem_u32(s_gA) + (uint32_t)((k * CT + c0) * 4), tabB = smem_u32(s_gB) + (uint32_t)((k * CT + c0) * 4);
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               const float4 A0 = lds_f4(tabA + j * 4), A1 = lds_f4(tabA + j * 4 + 16), B0 = lds_f4(tabB + j * 4), B1 = lds_f4(tabB + j * 4 + 16);
@@ -1352,23 +1504,32 @@ int conv_set_post(ConvLaunch* L, int n, const ConvLaunch::Post* targets, const f
   L->ss_stride = ss_stride;
   // GroupNorm in the epilogue (GNE) instead of the post warps when the pair's accumulator stage holds the whole sample
   L->gne = 0;
-  if (conv_gne_capable(*L, n)) {
+  if (const int mode = conv_gne_capable(*L, n)) {
     const int bw = L->Wb < 32 ? L->Wb : 32, bh = L->Hb < 32 / bw ? L->Hb : 32 / bw, bi = 32 / (bw * bh);
     for (int k = 0; k < n; ++k)
       if (int rc = encode_out_map(&L->tmP[k], L->post[k].dst, L->B, L->H_out, L->W_out, L->post[k].dst_C, bw, bh, bi)) return rc;
-    L->gne = 1;
+    L->gne = mode;
   }
   return DLPM_OK;
 }
 
-static int g_gne_enabled = 1;
-bool conv_gne_capable(const ConvLaunch& L, int n_targets) {
-  if (!g_gne_enabled || !conv_post_capable(L) || !L.tma_store || L.cta_group != 2 || L.Nb != 1 || L.msub != 1 || L.tiles_per_img != 2) return false;
-  if (L.n_n_tiles != 1 || (L.block_n != 128 && L.block_n != 256) || L.block_k != 64) return false;
-  if ((3 + 2 * n_targets) * L.block_n * 4 + n_targets * L.block_n * 2 > kGneRegionBytes) return false;  // bias | A, B per target | exchanged totals | group (rstd, -mean rstd)
+static int g_gne_enabled = 3;  // bit 0: mode 1 (maps of 256 pixels, CTA pairs), bit 1: mode 2 (4x4 maps)
+// 0 = not capable; 1 = the pair's accumulator stage holds one whole sample (two tiles per image, CTA pairs): two TMEM passes + DSMEM
+// exchange; 2 = 4x4 maps (eight samples per tile, a sample = half a warp): one pass, statistics by half-warp shuffles
+int conv_gne_capable(const ConvLaunch& L, int n_targets) {
+  if (!g_gne_enabled || !conv_post_capable(L) || !L.tma_store || (L.block_n != 128 && L.block_n != 256) || L.block_k != 64) return 0;
   for (int k = 0; k < n_targets; ++k)
-    if (32 % L.post[k].cpg || L.post[k].c_off % L.post[k].cpg || !L.post[k].silu) return false;
-  return true;
+    if (32 % L.post[k].cpg || L.post[k].c_off % L.post[k].cpg) return 0;
+  if ((g_gne_enabled & 2) && L.Nb > 1 && L.Wb * L.Hb == 16) {
+    if ((1 + 2 * n_targets) * L.c_out_pad * 4 > kGneRegionBytes) return 0;  // bias | A, B per target (all N tiles)
+    return 2;
+  }
+  if (!(g_gne_enabled & 1) || L.cta_group != 2 || L.Nb != 1 || L.msub != 1 || L.tiles_per_img != 2 || L.n_n_tiles != 1) return 0;
+  // bias | A, B per target | exchanged totals | group (rstd, -mean rstd)
+  if ((3 + 2 * n_targets) * L.block_n * 4 + n_targets * L.block_n * 2 > kGneRegionBytes) return 0;
+  for (int k = 0; k < n_targets; ++k)
+    if (!L.post[k].silu) return 0;
+  return 1;
 }
 
 static int g_tall_enabled = 1;
@@ -1387,7 +1548,7 @@ void conv_set_cta_group_override(int v) { g_cta_group_override = v; }
 
 static int64_t g_n_conv = 0, g_n_post = 0, g_n_gne = 0;
 
-template <int BN, int BK, int CG, bool XF, bool POST = false, bool GNE = false>
+template <int BN, int BK, int CG, bool XF, bool POST = false, int GNE = 0>
 static int launch_t(const ConvLaunch& L, cudaStream_t stream) {
   ++g_n_conv;
   if (POST) ++g_n_post;
@@ -1456,6 +1617,15 @@ static int launch_t(const ConvLaunch& L, cudaStream_t stream) {
   return DLPM_OK;
 }
 
+// mode-2 GNE keeps ONE scale / shift table per kernel: a forward with per-sample time steps (ss_rows == B: eight samples with
+// different rows in one tile) goes through the post warps, which read the rows per sample
+static bool gne2_needs_post_warps(const ConvLaunch& L) {
+  if (L.ss_rows == 1) return false;
+  for (int k = 0; k < L.post_n; ++k)
+    if (L.post[k].ss_off >= 0) return true;
+  return false;
+}
+
 int conv_launch(const ConvLaunch& L, cudaStream_t stream) {
 #define CASE(BN, BK)                                                                \
   if (L.block_n == BN && L.block_k == BK) {                                         \
@@ -1469,8 +1639,16 @@ int conv_launch(const ConvLaunch& L, cudaStream_t stream) {
       set_error("conv: no normalise-on-load kernel for tile N=%d K=%d", BN, BK);   \
       return DLPM_ERR_UNSUPPORTED;                                                  \
     }                                                                               \
-    if (L.post_n > 0 && L.gne) {                                                    \
-      if constexpr (BN >= 128 && BK == 64) return launch_t<BN, BK, 2, false, false, true>(L, stream); \
+    if (L.post_n > 0 && L.gne == 1) {                                               \
+      if constexpr (BN >= 128 && BK == 64) return launch_t<BN, BK, 2, false, false, 1>(L, stream); \
+      set_error("conv: no GroupNorm-in-the-epilogue kernel for tile N=%d K=%d", BN, BK); \
+      return DLPM_ERR_UNSUPPORTED;                                                  \
+    }                                                                               \
+    if (L.post_n > 0 && L.gne == 2 && !gne2_needs_post_warps(L)) {                  \
+      if constexpr (BN >= 128 && BK == 64) {                                        \
+        if (L.cta_group == 2) return launch_t<BN, BK, 2, false, false, 2>(L, stream); \
+        return launch_t<BN, BK, 1, false, false, 2>(L, stream);                     \
+      }                                                                             \
       set_error("conv: no GroupNorm-in-the-epilogue kernel for tile N=%d K=%d", BN, BK); \
       return DLPM_ERR_UNSUPPORTED;                                                  \
     }                                                                               \
@@ -1539,8 +1717,8 @@ int dlpm_b200_set_option(const char* name, int value) {
     engine_set_gne_skip_raw(value != 0);
     return DLPM_OK;
   }
-  if (std::string(name) == "conv_gne") {  // GroupNorm in the epilogue for fused targets (0: always the post warps)
-    g_gne_enabled = value != 0;
+  if (std::string(name) == "conv_gne") {  // GroupNorm in the epilogue for fused targets: bit 0 = 16x16 maps, bit 1 = 4x4 maps (0: always the post warps)
+    g_gne_enabled = value == 1 ? 3 : value;
     return DLPM_OK;
   }
   if (std::string(name) == "conv_msub") {

@@ -67,7 +67,7 @@ struct ConvLaunch {
 // convolution's channels or straddle an N tile).
 int conv_set_post(ConvLaunch* L, int n, const ConvLaunch::Post* targets, const float* ss, int64_t ss_stride);
 bool conv_post_capable(const ConvLaunch& L);
-bool conv_gne_capable(const ConvLaunch& L, int n_targets);
+int conv_gne_capable(const ConvLaunch& L, int n_targets);  // 0 / mode 1 (16x16, CTA pairs) / mode 2 (4x4)
 
 // Fills geometry + tensor maps.  in: NHWC bf16 [B, H, W, C_in]; w: bf16 [C_out_pad][taps*C_in + C_s0 + C_s1] (K contiguous);
 // skip sources NHWC bf16 [B, H_out, W_out, C_s*].  Returns DLPM_OK or an error code (message via set_error).

@@ -430,14 +430,18 @@ class UNetModel(nn.Module):
             # those convolutions already move 6x their output through the L2 -> SM fabric (0.88 of its ~12 TB/s) and the
             # re-read + write of the normalised rows adds 2x more; on 4x4 / 8x8 maps the tail of dependent L2 round trips
             # (store completion -> statistics -> parameters -> rows) costs what the separate 8.7 us kernel costs.
-            gne = fuse_gne and HW == 256 and 32 % cpg == 0  # epilogue variant: the group must lie inside a 32-channel chunk
+            # epilogue variant (the group must lie inside a 32-channel chunk): 16x16 maps -- a CTA pair's accumulator stage holds one
+            # sample (SiLU targets) -- and 4x4 maps -- a sample is half a warp of the tile
+            gne = fuse_gne and 32 % cpg == 0 and ((HW == 256 and silu) or HW == 16)
             if (gne or (fuse_gn and HW <= self.fuse_groupnorm_max_pixels)) and C % 128 == 0 and 128 % cpg == 0:
                 c_off = 0
                 for b, c in parts:
                     pi = producer.get(b)
                     slot = None if pi is None else (0 if ops[pi][24] < 0 else (1 if ops[pi][24 + POST_FIELDS] < 0 else None))
-                    if gne and slot is not None and (c not in (128, 256) or (slot == 1 and c == 256)):
-                        slot = None  # GNE kernels: one N tile of 128 / 256 channels; the shared-memory tables of a 256-channel tile hold one target
+                    if gne and slot is not None and HW == 256 and (c not in (128, 256) or (slot == 1 and c == 256)):
+                        slot = None  # 16x16: one N tile of 128 / 256 channels; the shared-memory tables of a 256-channel tile hold one target
+                    if gne and slot is not None and HW == 16 and (1 + 2 * (slot + 1)) * c * 4 > 5680:
+                        slot = None  # 4x4: bias + two tables per target for all channels of the conv (conv_tc.cu kGneRegionBytes)
                     if slot is None or c_off % cpg or c % cpg:
                         plan = []
                         break

@@ -163,14 +163,16 @@ def test_unet_program_matches_oracle_block_plan():
             d_dsts = {o[24 + 8 * k] for o in dflt["ops"] if o[0] == OP_CONV for k in (0, 1) if o[24 + 8 * k] >= 0}
             assert all(o[8] * o[9] // (o[13] * o[13]) <= 64 for o in dflt["ops"] if o[0] == OP_CONV and o[24] >= 0)
             assert len(d_dsts) == 24 and [o[0] for o in dflt["ops"]].count(OP_GN) + len(d_dsts) == 2 * n_res + n_attn + 1, len(d_dsts)
-        if mc == 128:  # the default engine: GroupNorm in the epilogue (GNE) on the 16x16 maps only, one target per 256-channel conv
+        if mc == 128:  # the default engine: GroupNorm in the epilogue (GNE) on the 16x16 maps (one target per 256-channel conv) and 4x4 maps
             gne = m.build_program(32, 32, fuse_gn=False)
             g_ops = [o for o in gne["ops"] if o[0] == OP_CONV and o[24] >= 0]
-            assert all(o[8] * o[9] // (o[13] * o[13]) == 256 and o[24 + 8] < 0 for o in g_ops)
-            g_dsts = {o[24] for o in g_ops}
+            hw = lambda o: o[8] * o[9] // (o[13] * o[13])
+            assert all(hw(o) in (16, 256) for o in g_ops) and all(o[24 + 8] < 0 for o in g_ops if hw(o) == 256)
+            g_dsts = {o[24 + 8 * k] for o in g_ops for k in (0, 1) if o[24 + 8 * k] >= 0}
             assert [o[0] for o in gne["ops"]].count(OP_GN) + len(g_dsts) == 2 * n_res + n_attn + 1
+            assert not any(o[0] == OP_GN and o[6] == 16 for o in gne["ops"])  # no GroupNorm launch left on the 4x4 maps
             # conv1-type outputs (only reader = the fused GroupNorm) carry the "raw output unused" flag
-            assert len(g_dsts) >= 7 and sum(1 for o in g_ops if o[31] & 2) == 5, (len(g_dsts), [o[31] for o in g_ops])
+            assert sum(1 for o in g_ops if hw(o) == 256) == 7 and sum(1 for o in g_ops if hw(o) == 256 and o[31] & 2) == 5
         n_up = sum(l.count("up") for l in inp + out)
         n_down = sum(l.count("down") for l in inp + out)
         # an upsample+conv = ONE parity-batched launch; the input conv = bf16 split + ONE tensor-core conv

@@ -386,6 +386,12 @@ GNE_CASES = [
     (300, 16, 256, 256, 3, 1, 512, 256, False, False),  # several items per CTA pair (parity double buffer), second half of a concat
     (40, 32, 128, 128, 3, 2, 128, 0, False, False),   # Downsample output at 16x16: N tile of 128 channels, 4-channel groups
     (36, 16, 256, 256, 1, 1, 256, 0, True, True),     # 1x1
+    # 4x4 maps (mode 2): eight samples per tile, a sample = half a warp, one TMEM pass, statistics by half-warp shuffles
+    (11, 4, 256, 256, 3, 1, 256, 0, True, False),     # odd batch (masked tail), identity residual, single CTAs
+    (600, 4, 256, 256, 3, 1, 512, 0, False, False),   # CTA pairs, several items per CTA, first half of a concat (16-channel groups)
+    (300, 4, 512, 256, 3, 1, 512, 256, False, False), # K = 4608, second half of a concat
+    (9, 4, 256, 256, 1, 1, 256, 0, True, False),      # attention proj_out (1x1, residual)
+    (64, 8, 256, 256, 3, 2, 256, 0, False, False),    # Downsample output at 4x4
 ]
 
 
