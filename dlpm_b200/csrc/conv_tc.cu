@@ -680,27 +680,63 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               bulk_commit();
             }
           }
-          // transposing butterfly inside each half warp (8 + 4 + 2 + 1 shuffles): lane l ends with the total of value l & 15 over its sample
+          float qs[8], qq2[8];  // totals of the chunk's eight quads over this lane's sample
+          if (p.stats_half) {
+            // 4x4: transposing butterfly inside each half warp (8 + 4 + 2 + 1 shuffles): lane l ends with the total of value l & 15 over
+            // its sample; every lane then fetches all sixteen
 #pragma unroll
-          for (int half = 8, off = 8; half >= 1; half >>= 1, off >>= 1) {
-            const bool up = (lane & off) != 0;
+            for (int half = 8, off = 8; half >= 1; half >>= 1, off >>= 1) {
+              const bool up = (lane & off) != 0;
 #pragma unroll
-            for (int k = 0; k < half; ++k) {
-              const float send = up ? st[k] : st[k + half];
-              const float keepv = up ? st[k + half] : st[k];
-              st[k] = keepv + __shfl_xor_sync(0xffffffffu, send, off);
+              for (int k = 0; k < half; ++k) {
+                const float send = up ? st[k] : st[k + half];
+                const float keepv = up ? st[k + half] : st[k];
+                st[k] = keepv + __shfl_xor_sync(0xffffffffu, send, off);
+              }
             }
-          }
-          if (p.stats != nullptr && valid) {  // other (unfused) GroupNorms still read the partial rows
-            const int64_t row = nn * p.stats_parts + par;
-            p.stats[(row * (p.C_out >> 2) + (col >> 2)) * 2 + (lane & 15)] = st[0];
-          }
-          // every lane needs the totals of all eight quads of its sample
-          float qs[8], qq2[8];
+            if (p.stats != nullptr && valid) {  // other (unfused) GroupNorms still read the partial rows
+              const int64_t row = nn * p.stats_parts + par;
+              p.stats[(row * (p.C_out >> 2) + (col >> 2)) * 2 + (lane & 15)] = st[0];
+            }
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            qs[k] = __shfl_sync(0xffffffffu, st[0], (lane & 16) | (2 * k));
-            qq2[k] = __shfl_sync(0xffffffffu, st[0], (lane & 16) | (2 * k + 1));
+            for (int k = 0; k < 8; ++k) {
+              qs[k] = __shfl_sync(0xffffffffu, st[0], (lane & 16) | (2 * k));
+              qq2[k] = __shfl_sync(0xffffffffu, st[0], (lane & 16) | (2 * k + 1));
+            }
+          } else {
+            // 8x8: a sample is the 64 rows of TWO warps (quadrants 2s, 2s + 1, same column chunks): full-warp transposing butterfly
+            // (lane l ends with the warp total of value l >> 1), the two warps swap their sixteen totals through shared memory
+#pragma unroll
+            for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
+              const bool up = (lane & off) != 0;
+#pragma unroll
+              for (int k = 0; k < half; ++k) {
+                const float send = up ? st[k] : st[k + half];
+                const float keepv = up ? st[k + half] : st[k];
+                st[k] = keepv + __shfl_xor_sync(0xffffffffu, send, off);
+              }
+            }
+            st[0] += __shfl_xor_sync(0xffffffffu, st[0], 1);
+            if (p.stats != nullptr && valid && (lane & 1) == 0) {
+              const int64_t row = (nn * p.stats_parts + (int64_t)par * p.stats_wpi + (q % p.stats_wpi));
+              p.stats[(row * (p.C_out >> 2) + (col >> 2)) * 2 + (lane >> 1)] = st[0];
+            }
+            float* const s_x = s_gB + p.post_n * CT;  // [8 epilogue warps][16]
+            const int bar_id = 2 + (q >> 1) * 2 + eg;  // the two warps of a sample that share this chunk column
+            if ((lane & 1) == 0) s_x[(warp - 4) * 16 + (lane >> 1)] = st[0];
+            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+            {
+              const float4* mine = reinterpret_cast<const float4*>(s_x + (warp - 4) * 16);
+              const float4* other = reinterpret_cast<const float4*>(s_x + (((warp - 4) ^ 1)) * 16);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float4 a = mine[k], b = other[k];
+                // (fixed order: the lower quadrant's total first, so both warps of the sample get the same sums)
+                const float4 lo = (q & 1) ? b : a, hi = (q & 1) ? a : b;
+                qs[2 * k] = lo.x + hi.x; qq2[2 * k] = lo.y + hi.y; qs[2 * k + 1] = lo.z + hi.z; qq2[2 * k + 1] = lo.w + hi.w;
+              }
+            }
+            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");  // both have read: the slots may be rewritten (next chunk)
           }
 #pragma unroll 1
           for (int k = 0; k < p.post_n; ++k) {
@@ -1513,15 +1549,16 @@ int conv_set_post(ConvLaunch* L, int n, const ConvLaunch::Post* targets, const f
   return DLPM_OK;
 }
 
-static int g_gne_enabled = 3;  // bit 0: mode 1 (maps of 256 pixels, CTA pairs), bit 1: mode 2 (4x4 maps)
+static int g_gne_enabled = 7;  // bit 0: mode 1 (maps of 256 pixels, CTA pairs), bit 1: mode 2 on 4x4 maps, bit 2: mode 2 on 8x8 maps
 // 0 = not capable; 1 = the pair's accumulator stage holds one whole sample (two tiles per image, CTA pairs): two TMEM passes + DSMEM
 // exchange; 2 = 4x4 maps (eight samples per tile, a sample = half a warp): one pass, statistics by half-warp shuffles
 int conv_gne_capable(const ConvLaunch& L, int n_targets) {
   if (!g_gne_enabled || !conv_post_capable(L) || !L.tma_store || (L.block_n != 128 && L.block_n != 256) || L.block_k != 64) return 0;
   for (int k = 0; k < n_targets; ++k)
     if (32 % L.post[k].cpg || L.post[k].c_off % L.post[k].cpg) return 0;
-  if ((g_gne_enabled & 2) && L.Nb > 1 && L.Wb * L.Hb == 16) {
-    if ((1 + 2 * n_targets) * L.c_out_pad * 4 > kGneRegionBytes) return 0;  // bias | A, B per target (all N tiles)
+  if ((g_gne_enabled & 2) && L.Nb > 1 && (L.Wb * L.Hb == 16 || (L.Wb * L.Hb == 64 && (g_gne_enabled & 4)))) {
+    // bias | A, B per target (all N tiles) | 8x8: the exchange slots of the eight epilogue warps
+    if ((1 + 2 * n_targets) * L.c_out_pad * 4 + (L.Wb * L.Hb == 64 ? 512 : 0) > kGneRegionBytes) return 0;
     return 2;
   }
   if (!(g_gne_enabled & 1) || L.cta_group != 2 || L.Nb != 1 || L.msub != 1 || L.tiles_per_img != 2 || L.n_n_tiles != 1) return 0;
@@ -1717,8 +1754,8 @@ int dlpm_b200_set_option(const char* name, int value) {
     engine_set_gne_skip_raw(value != 0);
     return DLPM_OK;
   }
-  if (std::string(name) == "conv_gne") {  // GroupNorm in the epilogue for fused targets: bit 0 = 16x16 maps, bit 1 = 4x4 maps (0: always the post warps)
-    g_gne_enabled = value == 1 ? 3 : value;
+  if (std::string(name) == "conv_gne") {  // GroupNorm in the epilogue for fused targets: bit 0 = 16x16 maps, bit 1 = 4x4 maps, bit 2 = 8x8 maps (0: always the post warps)
+    g_gne_enabled = value == 1 ? 7 : value;
     return DLPM_OK;
   }
   if (std::string(name) == "conv_msub") {

@@ -310,6 +310,7 @@ class UNetModel(nn.Module):
     # GroupNorm applied in the producing convolution's EPILOGUE, straight from the TMEM accumulators (csrc/conv_tc.cu, GNE): maps of
     # 256 pixels (16x16), where a CTA pair's accumulator stage holds one whole sample.  ON by default.
     fuse_groupnorm_epilogue = True
+    fuse_groupnorm_epilogue_8x8 = True  # ... also on the 8x8 maps (a sample = two warps of the tile)
     dx_stacked_out_conv = True  # the final conv's horizontal taps stacked along N (csrc/conv_tc.cuh ConvGeom::n_par == 3)
 
     def __init__(self, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions, dropout=0,
@@ -432,7 +433,7 @@ class UNetModel(nn.Module):
             # (store completion -> statistics -> parameters -> rows) costs what the separate 8.7 us kernel costs.
             # epilogue variant (the group must lie inside a 32-channel chunk): 16x16 maps -- a CTA pair's accumulator stage holds one
             # sample (SiLU targets) -- and 4x4 maps -- a sample is half a warp of the tile
-            gne = fuse_gne and 32 % cpg == 0 and ((HW == 256 and silu) or HW == 16)
+            gne = fuse_gne and 32 % cpg == 0 and ((HW == 256 and silu) or HW == 16 or (HW == 64 and self.fuse_groupnorm_epilogue_8x8))
             if (gne or (fuse_gn and HW <= self.fuse_groupnorm_max_pixels)) and C % 128 == 0 and 128 % cpg == 0:
                 c_off = 0
                 for b, c in parts:
@@ -440,8 +441,8 @@ class UNetModel(nn.Module):
                     slot = None if pi is None else (0 if ops[pi][24] < 0 else (1 if ops[pi][24 + POST_FIELDS] < 0 else None))
                     if gne and slot is not None and HW == 256 and (c not in (128, 256) or (slot == 1 and c == 256)):
                         slot = None  # 16x16: one N tile of 128 / 256 channels; the shared-memory tables of a 256-channel tile hold one target
-                    if gne and slot is not None and HW == 16 and (1 + 2 * (slot + 1)) * c * 4 > 5680:
-                        slot = None  # 4x4: bias + two tables per target for all channels of the conv (conv_tc.cu kGneRegionBytes)
+                    if gne and slot is not None and HW in (16, 64) and (1 + 2 * (slot + 1)) * c * 4 + (512 if HW == 64 else 0) > 5680:
+                        slot = None  # 4x4 / 8x8: bias + two tables per target for all channels of the conv (conv_tc.cu kGneRegionBytes)
                     if slot is None or c_off % cpg or c % cpg:
                         plan = []
                         break
@@ -628,7 +629,7 @@ class UNetModel(nn.Module):
         attribute ``fuse_groupnorm``, True) attaches GroupNorms to their producing convolutions (``build_program``)."""
         from . import _unet_lib
         fuse_gn = self.fuse_groupnorm if fuse_gn is None else bool(fuse_gn)
-        key = (H, W, reuse_scratch, fuse_gn, self.fuse_groupnorm_max_pixels, self.fuse_groupnorm_epilogue, self.dx_stacked_out_conv)
+        key = (H, W, reuse_scratch, fuse_gn, self.fuse_groupnorm_max_pixels, self.fuse_groupnorm_epilogue, self.fuse_groupnorm_epilogue_8x8, self.dx_stacked_out_conv)
         version = tuple((p.data_ptr(), _version_of(p)) for p in self.parameters())
         ent = self._engines.get(key)
         if ent is not None and (ent.version != version or ent.max_batch < max_batch):

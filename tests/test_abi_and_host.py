@@ -167,10 +167,11 @@ def test_unet_program_matches_oracle_block_plan():
             gne = m.build_program(32, 32, fuse_gn=False)
             g_ops = [o for o in gne["ops"] if o[0] == OP_CONV and o[24] >= 0]
             hw = lambda o: o[8] * o[9] // (o[13] * o[13])
-            assert all(hw(o) in (16, 256) for o in g_ops) and all(o[24 + 8] < 0 for o in g_ops if hw(o) == 256)
+            assert all(hw(o) in (16, 64, 256) for o in g_ops) and all(o[24 + 8] < 0 for o in g_ops if hw(o) == 256)
             g_dsts = {o[24 + 8 * k] for o in g_ops for k in (0, 1) if o[24 + 8 * k] >= 0}
             assert [o[0] for o in gne["ops"]].count(OP_GN) + len(g_dsts) == 2 * n_res + n_attn + 1
             assert not any(o[0] == OP_GN and o[6] == 16 for o in gne["ops"])  # no GroupNorm launch left on the 4x4 maps
+            assert sum(1 for o in gne["ops"] if o[0] == OP_GN and o[6] == 64) == 1  # 8x8: only the one fed by the folded upsample conv
             # conv1-type outputs (only reader = the fused GroupNorm) carry the "raw output unused" flag
             assert sum(1 for o in g_ops if hw(o) == 256) == 7 and sum(1 for o in g_ops if hw(o) == 256 and o[31] & 2) == 5
         n_up = sum(l.count("up") for l in inp + out)

@@ -392,6 +392,11 @@ GNE_CASES = [
     (300, 4, 512, 256, 3, 1, 512, 256, False, False), # K = 4608, second half of a concat
     (9, 4, 256, 256, 1, 1, 256, 0, True, False),      # attention proj_out (1x1, residual)
     (64, 8, 256, 256, 3, 2, 256, 0, False, False),    # Downsample output at 4x4
+    # 8x8 maps (mode 2): two samples per tile, a sample = two warps, which swap their totals through shared memory
+    (5, 8, 256, 256, 3, 1, 256, 0, False, False),     # odd batch: the last tile's second sample is masked
+    (300, 8, 256, 256, 3, 1, 512, 256, False, False), # CTA pairs, several items per CTA, second half of a concat
+    (130, 8, 512, 256, 3, 1, 256, 0, True, False),    # K = 4608, identity residual
+    (64, 16, 256, 256, 3, 2, 256, 0, False, False),   # Downsample output at 8x8
 ]
 
 
