@@ -1051,32 +1051,35 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + pixs[sub] * p.C_out + col;
 #pragma unroll
                 for (int j = 0; j < CH; j += 8) {
-                  float v[8];
+                  // packed fp32x2 arithmetic (sm_100 FADD2 / FFMA2): half the issue slots of the bias / residual / statistics math
+                  float2 v[4];
                   const float4 b0 = lds_f4(bias_s + j * 4), b1 = lds_f4(bias_s + j * 4 + 16);
-                  v[0] = __uint_as_float(r[j + 0]) + b0.x; v[1] = __uint_as_float(r[j + 1]) + b0.y;
-                  v[2] = __uint_as_float(r[j + 2]) + b0.z; v[3] = __uint_as_float(r[j + 3]) + b0.w;
-                  v[4] = __uint_as_float(r[j + 4]) + b1.x; v[5] = __uint_as_float(r[j + 5]) + b1.y;
-                  v[6] = __uint_as_float(r[j + 6]) + b1.z; v[7] = __uint_as_float(r[j + 7]) + b1.w;
+                  v[0] = __fadd2_rn(make_float2(__uint_as_float(r[j + 0]), __uint_as_float(r[j + 1])), make_float2(b0.x, b0.y));
+                  v[1] = __fadd2_rn(make_float2(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])), make_float2(b0.z, b0.w));
+                  v[2] = __fadd2_rn(make_float2(__uint_as_float(r[j + 4]), __uint_as_float(r[j + 5])), make_float2(b1.x, b1.y));
+                  v[3] = __fadd2_rn(make_float2(__uint_as_float(r[j + 6]), __uint_as_float(r[j + 7])), make_float2(b1.z, b1.w));
                   if (has_res) {
                     uint4 rv;
                     if constexpr (RES_PREFETCH) rv = resv[sub][ci * (CH / 8) + j / 8];
                     else rv = __ldg(reinterpret_cast<const uint4*>(p.residual + pixs[sub] * p.C_out + col + j));
                     const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(rp[e]); v[2 * e] += f.x; v[2 * e + 1] += f.y; }
+                    for (int e = 0; e < 4; ++e) v[e] = __fadd2_rn(v[e], __bfloat1622float2(rp[e]));
                   }
                   uint4 o;
                   __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) op[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+                  for (int e = 0; e < 4; ++e) op[e] = __float22bfloat162_rn(v[e]);
                   if (CH == 32 && p.tma_store) sts_u4(my_row + (uint32_t)(((j >> 3) ^ ((lane >> 1) & 3)) << 4), o);
                   else *reinterpret_cast<uint4*>(dst + j) = o;
                   if (do_stats) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                       const int qi = (j / 4 + h) * 2;
-                      st[qi] += (v[4 * h] + v[4 * h + 1]) + (v[4 * h + 2] + v[4 * h + 3]);
-                      st[qi + 1] += fmaf(v[4 * h], v[4 * h], v[4 * h + 1] * v[4 * h + 1]) + fmaf(v[4 * h + 2], v[4 * h + 2], v[4 * h + 3] * v[4 * h + 3]);
+                      const float2 s2 = __fadd2_rn(v[2 * h], v[2 * h + 1]);
+                      const float2 q2 = __ffma2_rn(v[2 * h + 1], v[2 * h + 1], __fmul2_rn(v[2 * h], v[2 * h]));
+                      st[qi] += s2.x + s2.y;
+                      st[qi + 1] += q2.x + q2.y;
                     }
                   }
                 }
