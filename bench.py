@@ -239,8 +239,12 @@ def hbm_kernels(torch, _lib, glp, dev, T, hbm_peak, sets=4, reps=5):
                                            _lib.stream_ptr()), 2)
         out[name] = {"bytes_per_launch": 4 * nn, "ms": ms, "GB/s": 4 * nn / ms / 1e6, "frac": 4 * nn / ms / 1e6 / hbm_peak}
     out["sas_noise_isotropic"]["generator"] = "Philox4x32-%d" % _lib.load().dlpm_b200_philox_rounds()
-    out["sas_noise_isotropic"]["limiter"] = ("instruction dispatch: 2 quarter-rate IMAD.WIDE per Philox round per 4 normals (+ Box-Muller: 2 MUFU "
-                                             "per normal), see profiles/r01_ncu_stream.md and profiles/r02_noise.md")
+    out["sas_noise_isotropic"]["scheme"] = ("sextet: six normals per Philox block (27-bit radius lattice, 15-bit angle), rows of 3072 = 8 x 384 "
+                                            "elements; csrc/rng.cuh, oracle/philox.py::normal_sextet")
+    out["sas_noise_isotropic"]["limiter"] = ("HBM write (the quad scheme -- four normals per block -- was dispatch-bound at 0.66: 2 quarter-rate "
+                                             "IMAD.WIDE per Philox round, profiles/r02_noise.md)")
+    out["sas_noise_per_element"]["limiter"] = out["A_per_element"]["limiter"] = (
+        "instruction dispatch: one CMS / Kanter transform (3 polynomial sines, 2 lg2, rcp, ex2, Exp(1) tail series) and 64 random bits per draw")
     return out
 
 
