@@ -47,6 +47,33 @@ def launches(path):
     print("| **total** | %d | %.1f | 100%% |" % (sum(a[0] for a in agg.values()), tot))
 
 
+def steps(path):
+    """Launch list restricted to the COMPLETE reverse steps found between consecutive k_advance launches (per-step averages)."""
+    hdr, rows = read_rows(path)
+    ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    seq = [(short(r[ki]), to_us(r[vi], r[ui])) for r in rows]
+    cuts = [i for i, (k, _) in enumerate(seq) if k.startswith("k_advance")]
+    segs = [seq[a + 1:b + 1] for a, b in zip(cuts[:-1], cuts[1:])]
+    # a pure step is the SHORTEST segment (the first step of a pass also carries the pass set-up: Sigma scan, x_T fill, ...)
+    n_max = min(len(sg) for sg in segs if any(k.startswith("k_conv_tc") for k, _ in sg))
+    segs = [sg for sg in segs if len(sg) == n_max]
+    agg = collections.OrderedDict()
+    for sg in segs:
+        for k, us in sg:
+            a = agg.setdefault(k, [0, 0.0])
+            a[0] += 1
+            a[1] += us
+    n = len(segs)
+    tot = sum(a[1] for a in agg.values()) / n
+    print("%d complete steps of %d launches\n" % (n, n_max))
+    print("| kernel | launches / step | us / step | share of the step |\n|---|---:|---:|---:|")
+    for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print("| `%s` | %.1f | %.1f | %.1f %% |" % (k[:90], c / n, t / n, 100 * t / n / tot))
+    print("| **total** | %d | %.1f | 100 %% |" % (n_max, tot))
+    conv = sum(t for k, (c, t) in agg.items() if k.startswith("k_conv_tc")) / n
+    print("\nconvolutions: %.1f %% of the step" % (100 * conv / tot))
+
+
 def metrics(path):
     hdr, rows = read_rows(path)
     idx = {h: i for i, h in enumerate(hdr)}
@@ -71,4 +98,4 @@ def metrics(path):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "metrics": metrics}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "metrics": metrics, "steps": steps}[sys.argv[1]](sys.argv[2])
