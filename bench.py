@@ -547,7 +547,7 @@ def run_noise(args, rank, local_rank, world):
                                      "modes A per element / SaS per element / SaS isotropic (inner 3072); independent shards per GPU",
                          "generator": "Philox4x32-%d" % _lib.load().dlpm_b200_philox_rounds(),
                          "l2_note": "fills >= 2^26 draws exceed L2 by themselves; smaller fills flush L2 between launches"},
-              "roofline": {"bound": "hbm", "kernel": "k_sas_vec (isotropic SaS fill)", "achieved": 4 * n_head / ms_head / 1e6, "peak": hbm_peak,
+              "roofline": {"bound": "hbm", "kernel": "k_fill6 (isotropic SaS fill, sextet scheme: six normals per Philox block)", "achieved": 4 * n_head / ms_head / 1e6, "peak": hbm_peak,
                            "unit": "GB/s", "frac": 4 * n_head / ms_head / 1e6 / hbm_peak, "traffic": None,
                            "peak_source": "MEASURED_PEAKS.json hbm_gbs (%s)" % pk_src},
               "e2e": {"value": world * 4 * n_e / float(e2e_ms[0]) / 1e6, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4 * n_e * world,

@@ -1,5 +1,5 @@
 """Launches each streaming kernel (K1 fills, K3 steps) a few times at the bench sizes: the target of the ncu captures in
-profiles/ (`ncu --set full -k regex:"k_sas_vec|k_stable_A_vec|k_reverse_step_fast|k_lim_step_vec" python tools/profile_stream.py`)."""
+profiles/ (`ncu --set full -k regex:"k_fill6|k_sas_vec|k_stable_A_vec|k_reverse_step_fast|k_lim_step_vec" python tools/profile_stream.py`)."""
 import os
 import sys
 
