@@ -16,6 +16,11 @@
 //   * warp-specialised, persistent: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread),
 //     warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld -> +bias (+residual) -> bf16 -> global).
 //     Two accumulator stages in TMEM let the epilogue of tile i overlap the MMAs of tile i+1.
+//   * GroupNorm in the epilogue (GNE, template argument): where the accumulator stage holds WHOLE samples (16x16 maps as CTA
+//     pairs; 8x8 / 4x4 maps inside one tile) the consumer's GroupNorm (+ scale-shift, SiLU; unet.py:141,153,188-191) is applied
+//     straight from TMEM and the normalised rows go to the consumer's input tensor -- no k_gn_apply pass (see the kernel).
+//   * thin fp32 output conv (unet.py:435): horizontal taps stacked along N (ConvGeom::n_par == 3), partials of neighbouring
+//     pixels summed by lane shuffles in the epilogue.
 #include "../../include/dlpm_b200_unet.h"
 #include <cstdlib>
 #include <string>
