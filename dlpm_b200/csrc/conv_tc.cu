@@ -509,7 +509,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int chunk = xt & 7, rl = xt >> 3;  // 16-byte chunk (8 channels) of a 128-byte row; 32 row lanes
     const int box_rows = (msub * p.Hb + 2) * p.Wb;
     const int wshift = 31 - __clz(p.Wb);
-    const int n_sb = 3 * p.cin_blocks + p.s0_blocks + p.s1_blocks;
+    const int n_sb = p.dx_taps * p.cin_blocks + p.s0_blocks + p.s1_blocks;
     const uint32_t xf_remote = CG == 2 ? mapa_u32(smem_u32(xf_bar), 0) : 0u;
     // a thread's rows are rl, rl + 32, ...: Wb divides 32, so its pixel column and its swizzle phase never change
     const int x_base = (rl & (p.Wb - 1)) - 1, y_step = 32 >> wshift;
@@ -522,8 +522,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const float4* ab_row = reinterpret_cast<const float4*>(p.ab + (int64_t)(n0 < p.B ? n0 : p.B - 1) * p.c_in_total);
       const int y_first = h0 - 1 + (rl >> wshift);
       for (int sb = 0; sb < n_sb; ++sb) {
-        const bool main_part = sb < 3 * p.cin_blocks;
-        const int cblk = sb / 3, dxi = sb - cblk * 3;
+        const bool main_part = sb < p.dx_taps * p.cin_blocks;
+        const int cblk = p.dx_taps == 3 ? sb / 3 : sb, dxi = p.dx_taps == 3 ? sb - cblk * 3 : 1;  // (dx-stacked: one unshifted box per block)
         float4 co[4];  // (a, b) of this thread's 8 channels; fetched while the box is still in flight
         if (main_part) {
 #pragma unroll
@@ -1419,7 +1419,7 @@ int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, c
   // n_par == 3: "dx-stacked" thin convolution (ConvGeom): weights [3 x 16][3 * C_in], one N tile of 48 columns
   const bool dxs = geom.n_par == 3;
   DLPM_REQUIRE(!dxs || (out_mode == CONV_OUT_F32_NCHW && geom.tap_rows == 3 && geom.tap_cols == 3 && geom.dy0 == -1 && geom.dx0 == -1 &&
-                        stride == 1 && geom.out_scale == 1 && !skip0 && !skip1 && !residual && !fuse && W <= 32 && W % 8 == 0 && H * W >= 128 &&
+                        stride == 1 && geom.out_scale == 1 && !skip0 && !skip1 && !residual && (!fuse || !fuse->in2) && W <= 32 && W % 8 == 0 && H * W >= 128 &&
                         conv_tall_enabled()),
                "conv: the dx-stacked form is for the thin fp32 output conv (3x3, stride 1, rows of <= 32 pixels)");
   const int C_out_pad = dxs ? 48 : (out_mode == CONV_OUT_F32_NCHW ? 16 : C_out);
@@ -1477,7 +1477,7 @@ int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, c
   L->xf = fuse ? 1 : 0;
   L->ab = fuse ? fuse->ab : nullptr;
   L->c0_blocks = C_in0 / bk;
-  if (fuse && !(L->tall && bk == 64 && (bn == 16 || bn == 128 || bn == 256))) {
+  if (fuse && !(L->tall && bk == 64 && (bn == 16 || bn == 48 || bn == 128 || bn == 256))) {
     set_error("conv: normalise-on-load needs a 3x3 stride-1 conv with one image per tile row block, 64-channel K blocks, N in {16,128,256}");
     return DLPM_ERR_UNSUPPORTED;
   }
@@ -1712,9 +1712,10 @@ int conv_launch(const ConvLaunch& L, cudaStream_t stream) {
   }
   CASE(256, 64) CASE(128, 64) CASE(64, 64) CASE(32, 64) CASE(16, 64)
   CASE(256, 32) CASE(128, 32) CASE(64, 32) CASE(32, 32) CASE(16, 32)
-  if (L.block_n == 48 && !L.xf && L.post_n == 0 && L.cta_group == 1) {  // dx-stacked thin conv
-    if (L.block_k == 64) return launch_t<48, 64, 1, false>(L, stream);
-    if (L.block_k == 32) return launch_t<48, 32, 1, false>(L, stream);
+  if (L.block_n == 48 && L.post_n == 0 && L.cta_group == 1) {  // dx-stacked thin conv (optionally normalising its input on load)
+    if (L.xf && L.block_k == 64) return launch_t<48, 64, 1, true>(L, stream);
+    if (!L.xf && L.block_k == 64) return launch_t<48, 64, 1, false>(L, stream);
+    if (!L.xf && L.block_k == 32) return launch_t<48, 32, 1, false>(L, stream);
   }
 #undef CASE
   set_error("conv: no kernel for tile N=%d K=%d", L.block_n, L.block_k);

@@ -90,7 +90,10 @@ void engine_set_traverse_alternate(bool on) { g_traverse_alternate = on; }
 static bool g_gne_skip_raw = true;  // GNE convolutions whose raw output has no other reader do not store it (debug: 0 keeps the store)
 void engine_set_gne_skip_raw(bool on) { g_gne_skip_raw = on; }
 static bool g_gn_stats_enabled = true;
-static int g_gn_fuse_mode = 0;  // 0 = never (default, see DESIGN.md: the transform does not hide behind the MMAs yet), 1 = final conv only, 2 = all
+// normalise-on-load: 0 = never (default), 1 = the thin final conv only (with its horizontal taps stacked along N every activation box
+// is transformed once: the last 32x32 GroupNorm pass goes from 49 to 8 us (fold only) and the conv from 36 to 77 us -- a wash),
+// 2 = all (measured slower)
+static int g_gn_fuse_mode = 0;
 void engine_set_gn_stats(bool on) { g_gn_stats_enabled = on; }
 void engine_set_gn_fuse(int mode) { g_gn_fuse_mode = mode; }
 

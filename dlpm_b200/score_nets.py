@@ -312,6 +312,10 @@ class UNetModel(nn.Module):
     fuse_groupnorm_epilogue = True
     fuse_groupnorm_epilogue_8x8 = True  # ... also on the 8x8 maps (a sample = two warps of the tile)
     dx_stacked_out_conv = True  # the final conv's horizontal taps stacked along N (csrc/conv_tc.cuh ConvGeom::n_par == 3)
+    # maps of at least this many pixels run a ResBlock's identity skip as a unit-weight 1x1 skip conv in the K loop instead of an epilogue
+    # add (exact).  OFF: measured at 32x32 (the short-K, epilogue-bound layers) 124.9 -> 118.7 us per layer, 5.534 -> 5.511 ms per step
+    # (0.2-0.4 %, at the noise level, and the unit-weight MMAs are not algorithmic FLOPs); no gain at 16x16
+    identity_skip_as_conv_min_pixels = 1 << 30
 
     def __init__(self, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions, dropout=0,
                  channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2, num_classes=None, use_checkpoint=False,
@@ -519,7 +523,14 @@ class UNetModel(nn.Module):
             names[tag] = out
             if isinstance(rb.skip_connection, nn.Identity):
                 assert len(parts) == 1
-                conv(a2, C_out, H_, W_, rb.out_layers[3].weight, rb.out_layers[3].bias, out, residual=parts[0][0])
+                if hw >= self.identity_skip_as_conv_min_pixels and C_out % 64 == 0:
+                    # the identity skip as a 1x1 conv with unit weights appended to the K loop (exact: 1.0 and the bf16 rows are exact
+                    # MMA operands): the short-K 32x32 layers are epilogue-bound and the residual rows cost the epilogue 29 % there
+                    eye = torch.eye(C_out, device=rb.out_layers[3].weight.device)
+                    conv(a2, C_out, H_, W_, rb.out_layers[3].weight, rb.out_layers[3].bias, out, skips=parts,
+                         skip_w=eye, skip_b=torch.zeros(C_out, device=eye.device))
+                else:
+                    conv(a2, C_out, H_, W_, rb.out_layers[3].weight, rb.out_layers[3].bias, out, residual=parts[0][0])
             else:
                 conv(a2, C_out, H_, W_, rb.out_layers[3].weight, rb.out_layers[3].bias, out, skips=parts,
                      skip_w=rb.skip_connection.weight, skip_b=rb.skip_connection.bias)
@@ -629,7 +640,7 @@ class UNetModel(nn.Module):
         attribute ``fuse_groupnorm``, True) attaches GroupNorms to their producing convolutions (``build_program``)."""
         from . import _unet_lib
         fuse_gn = self.fuse_groupnorm if fuse_gn is None else bool(fuse_gn)
-        key = (H, W, reuse_scratch, fuse_gn, self.fuse_groupnorm_max_pixels, self.fuse_groupnorm_epilogue, self.fuse_groupnorm_epilogue_8x8, self.dx_stacked_out_conv)
+        key = (H, W, reuse_scratch, fuse_gn, self.fuse_groupnorm_max_pixels, self.fuse_groupnorm_epilogue, self.fuse_groupnorm_epilogue_8x8, self.dx_stacked_out_conv, self.identity_skip_as_conv_min_pixels)
         version = tuple((p.data_ptr(), _version_of(p)) for p in self.parameters())
         ent = self._engines.get(key)
         if ent is not None and (ent.version != version or ent.max_batch < max_batch):

@@ -43,9 +43,9 @@ def test_unet_forward_golden(name):
         np.testing.assert_allclose(y.numpy(), want.numpy(), rtol=2e-2, atol=2e-2 * float(want.abs().max()))
 
 
-@pytest.mark.parametrize("opts", [{}, {"gne": 0, "dxs": 0}, {"conv_gne": 0}, {"fuse": 1, "max_px": 64}, {"fuse": 1, "max_px": 1024}, {"gn_stats": 0},
+@pytest.mark.parametrize("opts", [{}, {"gne": 0, "dxs": 0, "idskip": 1024}, {"conv_gne": 0}, {"fuse": 1, "max_px": 64}, {"fuse": 1, "max_px": 1024}, {"gn_stats": 0},
                                   {"gn_fuse": 2}, {"gn_fuse": 1}],
-                         ids=["default_groupnorm_in_the_epilogue_16x16_dx_stacked_out_conv", "separate_gn_apply_everywhere_plain_out_conv",
+                         ids=["default_groupnorm_in_the_epilogue_16x16_dx_stacked_out_conv", "separate_gn_apply_everywhere_plain_out_conv_identity_skips_in_the_k_loop",
                               "gne_targets_through_post_warps",
                               "producer_side_groupnorm_up_to_8x8", "producer_side_groupnorm_everywhere",
                               "gn_cluster_kernels", "normalise_on_load_everywhere", "normalise_on_load_final_conv"])
@@ -60,6 +60,7 @@ def test_unet_forward_full_width_golden(opts):
     max_px = opts.pop("max_px", 64)
     gne = bool(opts.pop("gne", 1))
     dxs = bool(opts.pop("dxs", 1))
+    idskip = opts.pop("idskip", None)
     for k, v in opts.items():
         _lib.call("dlpm_b200_set_option", k.encode(), v)
     try:
@@ -68,6 +69,8 @@ def test_unet_forward_full_width_golden(opts):
         m.fuse_groupnorm_max_pixels = max_px
         m.fuse_groupnorm_epilogue = gne
         m.dx_stacked_out_conv = dxs
+        if idskip is not None:
+            m.identity_skip_as_conv_min_pixels = idskip
         assert abs(csum - float(g["weight_checksum"])) < 1e-6 * max(1.0, abs(csum))
         y = m(torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["t"]).cuda()).cpu()
     finally:

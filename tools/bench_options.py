@@ -20,7 +20,7 @@ glp = GenerativeLevyProcess(1.7, dev, 1000, rescale_timesteps=True, isotropic=Tr
 res = {0: [], 1: []}
 for rnd in range(4):
     for on in ((0, 1) if rnd % 2 == 0 else (1, 0)):
-        if name not in ("fuse", "gne", "gne8", "dxs"):  # "fuse=<max pixels>": GroupNorm applied by the producing convolution's post warps (model attribute)
+        if name not in ("fuse", "gne", "gne8", "dxs", "idskip"):  # "fuse=<max pixels>": GroupNorm applied by the producing convolution's post warps (model attribute)
             _lib.call("dlpm_b200_set_option", name.encode(), int(val) if on else (0 if name != "gn_stats" else 1))
         m = UNetModel(3, 128, 3, 2, (16,), channel_mult=(1, 2, 2, 2), num_heads=4, use_scale_shift_norm=True)
         randomize_parameters_(m, 0)
@@ -29,6 +29,8 @@ for rnd in range(4):
             m.fuse_groupnorm, m.fuse_groupnorm_max_pixels = bool(on), int(val)
         if name == "dxs":  # "dxs=1": the final conv with its horizontal taps stacked along N (the default) against the 9-tap form
             m.dx_stacked_out_conv = bool(on)
+        if name == "idskip":  # "idskip=1024": identity skips of maps with >= 1024 pixels as unit-weight 1x1 skip convs in the K loop
+            m.identity_skip_as_conv_min_pixels = int(val) if on else (1 << 30)
         if name == "gne8":  # "gne8=1": GroupNorm in the epilogue on the 8x8 maps too (the default)
             m.fuse_groupnorm_epilogue_8x8 = bool(on)
         if name == "gne":  # "gne=1": GroupNorm in the epilogue on the 16x16 maps (the default) against separate passes
