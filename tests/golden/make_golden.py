@@ -233,6 +233,21 @@ def golden_unet_full():
          nparams=np.int64(sum(p.numel() for p in model.parameters())))
 
 
+def golden_unet_cifar10():
+    """The UNet of the reference's OTHER image config, cifar10.yml:51-59: full width with ``attn_resolutions: [4, 8, 16]`` =
+    AttentionBlocks after every ResBlock of the 8x8 and 4x4 levels (ds 4 and 8; L = 64 and 16, four heads of 64) in both halves of
+    the net, 11 AttentionBlocks in all.  Weights from the seed recipe; x / t / y for a batch-constant and a per-sample t."""
+    cfg = dict(model_channels=128, channel_mult=(1, 2, 2, 2), num_res_blocks=2, attention_resolutions=(4, 8, 16),
+               num_heads=4, in_ch=3, res=32)
+    model = rerandomize_(make_unet(cfg, 3), 21).eval()
+    x = torch.randn(2, 3, 32, 32, generator=torch.Generator().manual_seed(3))
+    t, t2 = torch.tensor([0.37, 0.37]), torch.tensor([0.05, 0.9])
+    with torch.no_grad():
+        y, y2 = model(x, t), model(x, t2)
+    save("unet_cifar10_attn", x=x.numpy(), t=t.numpy(), y=y.numpy(), t2=t2.numpy(), y2=y2.numpy(),
+         weight_checksum=np.float64(parameter_checksum(model)), nparams=np.int64(sum(p.numel() for p in model.parameters())))
+
+
 def golden_next_rows():
     """scale_exploding schedule with input_scaling (sampling chain + training loss) and the LIM
     training loss (GenerativeLevyProcess.py:177-180, :651-654, :680-709; LIM/functions/loss.py)."""
@@ -299,9 +314,13 @@ if __name__ == "__main__":
     if sys.argv[1:] == ["next_rows"]:
         golden_next_rows()
         sys.exit(0)
+    if sys.argv[1:] == ["unet_cifar10"]:
+        golden_unet_cifar10()
+        sys.exit(0)
     golden_noise()
     golden_schedule()
     golden_mlp_chain()
     golden_unet()
     golden_unet_full()
+    golden_unet_cifar10()
     golden_next_rows()

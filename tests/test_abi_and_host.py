@@ -222,6 +222,28 @@ def test_unet_program_interpreted_full_width_fused_groupnorm():
         assert err < 6e-3, (fuse, max_px, err)
 
 
+def test_unet_program_interpreted_cifar10_yml_architecture():
+    """cifar10.yml:51-59 (``attn_resolutions: [4, 8, 16]``: AttentionBlocks after every ResBlock of the 8x8 and 4x4 levels): the op
+    list of every GroupNorm strategy against the reference output, batch-constant and per-sample t."""
+    from program_interpreter import interpret
+    from dlpm_b200.init_utils import parameter_checksum, randomize_parameters_
+    from dlpm_b200.score_nets import OP_ATTN, UNetModel
+    g = load_golden("unet_cifar10_attn")
+    m = UNetModel(3, 128, 3, 2, (4, 8, 16), channel_mult=(1, 2, 2, 2), num_heads=4, use_scale_shift_norm=True)
+    randomize_parameters_(m, 21)
+    assert abs(parameter_checksum(m) - float(g["weight_checksum"])) < 1e-6 * abs(float(g["weight_checksum"]))
+    assert sum(p.numel() for p in m.parameters()) == int(g["nparams"])
+    x = torch.from_numpy(g["x"])
+    for kw in (dict(), dict(fuse_gn=False, fuse_gne=False), dict(fuse_gn=True, fuse_gne=False)):
+        prog = m.build_program(32, 32, **kw)
+        assert [o[0] for o in prog["ops"]].count(OP_ATTN) == 11  # 2 + 2 (input blocks), 1 (middle), 3 + 3 (output blocks)
+        for tk, yk in (("t", "y"), ("t2", "y2")):
+            y, _ = interpret(prog, x, torch.from_numpy(g[tk]), 128)
+            want = torch.from_numpy(g[yk])
+            err = float((y - want).abs().max() / want.abs().max())
+            assert err < 6e-3, (kw, tk, err)
+
+
 @pytest.mark.parametrize("name", ["mnist", "cifar_half"])
 def test_unet_program_interpreted_matches_reference_golden(name):
     """The op list + packed weights, executed by a plain-PyTorch interpreter (fp32 except bf16 conv weights),

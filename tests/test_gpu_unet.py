@@ -12,6 +12,8 @@ CFGS = {
     "mnist": dict(model_channels=32, channel_mult=(1, 2, 2, 2), num_res_blocks=2, attention_resolutions=(2, 4), num_heads=4, in_ch=1),
     "cifar_half": dict(model_channels=64, channel_mult=(1, 2, 2, 2), num_res_blocks=2, attention_resolutions=(16,), num_heads=4, in_ch=3),
     "cifar_full": dict(model_channels=128, channel_mult=(1, 2, 2, 2), num_res_blocks=2, attention_resolutions=(16,), num_heads=4, in_ch=3),
+    # cifar10.yml:51-59: attention after every ResBlock of the 8x8 and 4x4 levels as well (11 AttentionBlocks)
+    "cifar10_attn": dict(model_channels=128, channel_mult=(1, 2, 2, 2), num_res_blocks=2, attention_resolutions=(4, 8, 16), num_heads=4, in_ch=3),
 }
 
 
@@ -79,6 +81,39 @@ def test_unet_forward_full_width_golden(opts):
         _lib.call("dlpm_b200_set_option", b"conv_gne", 1)
     want = torch.from_numpy(g["y"])
     assert rel_err(y, want) < 2e-2, rel_err(y, want)
+
+
+@pytest.mark.parametrize("strategy", ["default", "separate_passes", "post_warps"])
+def test_unet_forward_cifar10_yml_architecture_golden(strategy):
+    """The reference's other image config (cifar10.yml: ``attn_resolutions: [4, 8, 16]`` = AttentionBlocks at 8x8, L = 64, and 4x4,
+    L = 16, in both halves of the net) at full width against the reference's output: GroupNorms of the attention blocks carried by
+    the producing convolutions' epilogues without SiLU (default), as separate passes, and through the post warps."""
+    from dlpm_b200 import _lib
+    g = load_golden("unet_cifar10_attn")
+    m, csum = make("cifar10_attn")
+    assert abs(csum - float(g["weight_checksum"])) < 1e-6 * max(1.0, abs(csum))
+    if strategy == "separate_passes":
+        m.fuse_groupnorm_epilogue, m.dx_stacked_out_conv = False, False
+    if strategy == "post_warps":
+        m.fuse_groupnorm, m.fuse_groupnorm_epilogue, m.fuse_groupnorm_max_pixels = True, False, 64
+    x = torch.from_numpy(g["x"]).cuda()
+    for tk, yk in (("t", "y"), ("t2", "y2")):  # batch-constant t, then per-sample t
+        n0 = ctypes_stat(_lib, b"conv_gne_launches")
+        y = m(x, torch.from_numpy(g[tk]).cuda()).cpu()
+        want = torch.from_numpy(g[yk])
+        assert rel_err(y, want) < 2e-2, (strategy, tk, rel_err(y, want))
+        np.testing.assert_allclose(y.numpy(), want.numpy(), rtol=2e-2, atol=2e-2 * float(want.abs().max()))
+        if strategy == "default":
+            assert ctypes_stat(_lib, b"conv_gne_launches") > n0
+    # a batch that changes the tiling (CTA pairs, several items per CTA): default engine against separate passes
+    if strategy == "default":
+        gen = torch.Generator().manual_seed(5)
+        xb = torch.randn(96, 3, 32, 32, generator=gen).cuda()
+        tb = torch.full((96,), 0.61).cuda()
+        y_fused = m(xb, tb).cpu()
+        m.fuse_groupnorm_epilogue, m.dx_stacked_out_conv = False, False
+        y_plain = m(xb, tb).cpu()
+        assert torch.isfinite(y_fused).all() and rel_err(y_fused, y_plain) < 2e-2, rel_err(y_fused, y_plain)
 
 
 @pytest.mark.parametrize("B", [3, 17, 40, 100, 333])
