@@ -62,6 +62,16 @@ def c2():
                       "samples_per_s": B / ms * 1e3}), flush=True)
 
 
+def c3b():
+    """The reference's other image config, cifar10.yml: the C3 UNet with AttentionBlocks at 8x8 and 4x4 as well (attn_resolutions [4, 8, 16])."""
+    m = unet(128, 3, (4, 8, 16))
+    glp = GenerativeLevyProcess(1.7, dev, 1000, rescale_timesteps=True, isotropic=True)
+    B = 512
+    ms = timed(lambda: glp.sample({"default": m}, [B, 3, 32, 32], reverse_steps=1000, clamp_a=20, clamp_eps=200), reps=1)
+    print(json.dumps({"config": "cifar10.yml UNet (ch128, attention at 8x8 / 4x4 / middle: 11 AttentionBlocks), DLPM alpha=1.7, T=1000, batch 512",
+                      "ms": ms, "samples_per_s": B / ms * 1e3, "ms_per_network_eval": ms / 999.0}), flush=True)
+
+
 def each(fn, reps, warm=1):
     """Per-call device times (ms) of `reps` calls after `warm` warm-up calls."""
     for _ in range(warm):
@@ -137,4 +147,4 @@ def c5():
 if __name__ == "__main__":
     which = sys.argv[1:] or ["c1", "c2", "c4", "c5"]
     for w in which:
-        {"c1": c1, "c2": c2, "c4": c4, "c5": c5}[w]()
+        {"c1": c1, "c2": c2, "c3b": c3b, "c4": c4, "c5": c5}[w]()
