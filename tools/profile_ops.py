@@ -20,7 +20,7 @@ ap.add_argument("--batch", type=int, default=512)
 ap.add_argument("--opt", action="append", default=[])
 ap.add_argument("--summary", action="store_true")
 ap.add_argument("--reps", type=int, default=5)
-ap.add_argument("--config", default="cifar", choices=["cifar", "mnist"])
+ap.add_argument("--config", default="cifar", choices=["cifar", "mnist", "cifar10"])
 ap.add_argument("--no-fuse", action="store_true")  # GroupNorm as separate launches (round-1 path) instead of the producers' post warps
 ap.add_argument("--no-gne", action="store_true")  # ... and no GroupNorm in the epilogue on the 16x16 maps either
 args = ap.parse_args()
@@ -29,6 +29,8 @@ for o in args.opt:
     _lib.call("dlpm_b200_set_option", k.encode(), int(v))
 if args.config == "mnist":  # mnist.yml:50-58: ch 32, attention at ds 2 and 4 (16x16 and 8x8)
     m = UNetModel(1, 32, 1, 2, (2, 4), channel_mult=(1, 2, 2, 2), num_heads=4, use_scale_shift_norm=True)
+elif args.config == "cifar10":  # cifar10.yml:51-59: the benchmark UNet with attention at 8x8 and 4x4 as well
+    m = UNetModel(3, 128, 3, 2, (4, 8, 16), channel_mult=(1, 2, 2, 2), num_heads=4, use_scale_shift_norm=True)
 else:
     m = UNetModel(3, 128, 3, 2, (16,), channel_mult=(1, 2, 2, 2), num_heads=4, use_scale_shift_norm=True)
 randomize_parameters_(m, 0)
