@@ -517,8 +517,7 @@ __global__ void __launch_bounds__(256) k_attention_mma(__nv_bfloat16* __restrict
   pdl_launch_dependents();
   pdl_wait();
   __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(att_smem);  // [L][KSTR]
-  __nv_bfloat16* Vt = Ks + (size_t)L * KSTR;                        // [D][L + 8]
-  const int VSTR = L + 8;
+  __nv_bfloat16* Vs = Ks + (size_t)L * KSTR;                        // [L][KSTR], row-major like K: the P.V B fragments come from ldmatrix.trans
   const int qb = blockIdx.x % q_blocks, nh = blockIdx.x / q_blocks;
   const int n = nh / heads, h = nh % heads;
   const __nv_bfloat16* base = qkv + (int64_t)n * L * 3 * C + h * 3 * D;  // per head: q | k | v blocks of D channels
@@ -528,9 +527,7 @@ __global__ void __launch_bounds__(256) k_attention_mma(__nv_bfloat16* __restrict
     const uint4 kr = __ldg(reinterpret_cast<const uint4*>(base + s * rs + D + d8));
     const uint4 vr = __ldg(reinterpret_cast<const uint4*>(base + s * rs + 2 * D + d8));
     *reinterpret_cast<uint4*>(Ks + s * KSTR + d8) = kr;
-    const __nv_bfloat16* ve = reinterpret_cast<const __nv_bfloat16*>(&vr);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) Vt[(d8 + e) * VSTR + s] = ve[e];
+    *reinterpret_cast<uint4*>(Vs + s * KSTR + d8) = vr;
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -600,10 +597,19 @@ __global__ void __launch_bounds__(256) k_attention_mma(__nv_bfloat16* __restrict
         pa[1] = pack_bf16(sc[2 * ks][2], sc[2 * ks][3]);
         pa[2] = pack_bf16(sc[2 * ks + 1][0], sc[2 * ks + 1][1]);
         pa[3] = pack_bf16(sc[2 * ks + 1][2], sc[2 * ks + 1][3]);
-        const __nv_bfloat16* vr = Vt + g * VSTR + kb + ks * 16 + 2 * t;
+        // B fragments of V (16 keys x 8 channels, "col" operand) straight from the row-major tile: ldmatrix.x4.trans fetches the two
+        // 8-key halves of two adjacent 8-channel blocks (lane l supplies row l & 7 of matrix l >> 3; the 144-byte row pitch keeps the
+        // eight rows of a matrix on distinct banks), thread (g, t) receives V[2t .. 2t+1][g] of each
+        const uint32_t va = (uint32_t)__cvta_generic_to_shared(Vs + (kb + ks * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * KSTR + (lane >> 4) * 8);
 #pragma unroll
-        for (int nd = 0; nd < D / 8; ++nd)
-          mma_bf16_16816(o[nd], pa, *reinterpret_cast<const uint32_t*>(vr + nd * 8 * VSTR), *reinterpret_cast<const uint32_t*>(vr + nd * 8 * VSTR + 8));
+        for (int nd = 0; nd < D / 8; nd += 2) {
+          uint32_t b00, b01, b10, b11;
+          asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(b00), "=r"(b01), "=r"(b10), "=r"(b11)
+                       : "r"(va + (uint32_t)(nd * 16)));
+          mma_bf16_16816(o[nd], pa, b00, b01);
+          mma_bf16_16816(o[nd + 1], pa, b10, b11);
+        }
       }
     }
   }
@@ -954,7 +960,7 @@ int dlpm_b200_attention(void* out, const void* qkv, int64_t B, int L, int C, int
   auto* q = reinterpret_cast<const __nv_bfloat16*>(qkv);
   cudaStream_t s = (cudaStream_t)stream;
   {  // tensor-core path
-    const size_t msmem = ((size_t)L * (D + 8) + (size_t)D * (L + 8)) * 2;
+    const size_t msmem = (size_t)2 * L * (D + 8) * 2;  // K and V tiles of one head, rows of D + 8 bf16
     // 8 warps (128 query rows) per CTA when the head has them: K / V of the head are staged half as often as with 4
     const int rows_per_cta = L >= 128 ? 128 : 64;
     const int q_blocks = (L + rows_per_cta - 1) / rows_per_cta;
