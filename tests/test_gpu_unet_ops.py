@@ -151,7 +151,7 @@ def test_groupnorm_silu(L, C0, C1, HW, ss, silu):
 
 
 @pytest.mark.parametrize("poly", [-1, 0, 1])  # softmax exponentials: auto / all MUFU.EX2 / a quarter on the FMA pipes
-@pytest.mark.parametrize("L_,C,heads", [(16, 256, 4), (256, 64, 4), (64, 64, 4), (16, 64, 4), (1024, 128, 4)])
+@pytest.mark.parametrize("L_,C,heads", [(16, 256, 4), (64, 256, 4), (256, 64, 4), (64, 64, 4), (16, 64, 4), (1024, 128, 4)])
 def test_attention(L, L_, C, heads, poly):
     B = 3
     qkv = rnd(B, 3 * C, L_, seed=7) * (3.0 if L_ == 1024 else 1.0)  # wide score range: exercises the running-maximum rescale
