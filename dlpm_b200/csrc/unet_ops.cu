@@ -528,6 +528,9 @@ __global__ void __launch_bounds__(256) k_attention_mma(__nv_bfloat16* __restrict
     const uint4 vr = __ldg(reinterpret_cast<const uint4*>(base + s * rs + 2 * D + d8));
     *reinterpret_cast<uint4*>(Ks + s * KSTR + d8) = kr;
     *reinterpret_cast<uint4*>(Vs + s * KSTR + d8) = vr;
+    // the eight padding columns of a V row hold (1, 0, ..., 0): a ninth channel block whose P.V product is the ROW SUM of the
+    // probabilities (of the bf16 values the numerator uses) -- four MMAs per 64 keys instead of 32 FADDs per thread
+    if (d8 == 0) *reinterpret_cast<uint4*>(Vs + s * KSTR + D) = make_uint4(0x00003f80u, 0u, 0u, 0u);
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -551,20 +554,30 @@ __global__ void __launch_bounds__(256) k_attention_mma(__nv_bfloat16* __restrict
   float o[D / 8][4];
 #pragma unroll
   for (int nd = 0; nd < D / 8; ++nd) { o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f; }
-  float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
+  float m_lo = -INFINITY, m_hi = -INFINITY;
+  float osum[4] = {0.f, 0.f, 0.f, 0.f};  // P.V against the ones column: [0] / [2] of the lanes with t == 0 are the row sums of rows g / g + 8
   for (int kb = 0; kb < L; kb += 64) {
     const int nkt = (L - kb) >= 64 ? 8 : (L - kb) / 8;  // valid 8-key tiles of this block (L is a multiple of 16)
     float sc[8][4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < 8; j += 2) {  // (nkt is even: L is a multiple of 16)
       sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+      sc[j + 1][0] = sc[j + 1][1] = sc[j + 1][2] = sc[j + 1][3] = 0.f;
       if (j < nkt) {
-        const __nv_bfloat16* kr = Ks + (kb + j * 8 + g) * KSTR + 2 * t;
+        // B fragments of K^T for two 8-key tiles per ldmatrix.x4: matrix l >> 3 = (key tile j + (l >> 4), channel half (l >> 3) & 1)
+        const uint32_t ka = (uint32_t)__cvta_generic_to_shared(Ks + (kb + (j + (lane >> 4)) * 8 + (lane & 7)) * KSTR + ((lane >> 3) & 1) * 8);
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk)
-          mma_bf16_16816(sc[j], qa[kk], *reinterpret_cast<const uint32_t*>(kr + kk * 16), *reinterpret_cast<const uint32_t*>(kr + kk * 16 + 8));
+        for (int kk = 0; kk < D / 16; ++kk) {
+          uint32_t b00, b01, b10, b11;
+          asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(b00), "=r"(b01), "=r"(b10), "=r"(b11)
+                       : "r"(ka + (uint32_t)(kk * 32)));
+          mma_bf16_16816(sc[j], qa[kk], b00, b01);
+          mma_bf16_16816(sc[j + 1], qa[kk], b10, b11);
+        }
       } else {
         sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = -INFINITY;
+        sc[j + 1][0] = sc[j + 1][1] = sc[j + 1][2] = sc[j + 1][3] = -INFINITY;
       }
     }
     float mx_lo = m_lo, mx_hi = m_hi;
@@ -578,7 +591,7 @@ __global__ void __launch_bounds__(256) k_attention_mma(__nv_bfloat16* __restrict
     const float c_lo = att_ex2((m_lo - mx_lo) * sl2), c_hi = att_ex2((m_hi - mx_hi) * sl2);  // first block: ex2(-inf) = 0
     m_lo = mx_lo; m_hi = mx_hi;
     const float ms_lo = -m_lo * sl2, ms_hi = -m_hi * sl2;
-    l_lo *= c_lo; l_hi *= c_hi;
+    osum[0] *= c_lo; osum[2] *= c_hi;
 #pragma unroll
     for (int nd = 0; nd < D / 8; ++nd) { o[nd][0] *= c_lo; o[nd][1] *= c_lo; o[nd][2] *= c_hi; o[nd][3] *= c_hi; }
 #pragma unroll
@@ -586,8 +599,6 @@ __global__ void __launch_bounds__(256) k_attention_mma(__nv_bfloat16* __restrict
       sc[j][0] = att_ex2(fmaf(sc[j][0], sl2, ms_lo)); sc[j][1] = att_ex2(fmaf(sc[j][1], sl2, ms_lo));
       sc[j][2] = att_ex2(fmaf(sc[j][2], sl2, ms_hi));
       sc[j][3] = POLY ? att_ex2_poly(fmaf(sc[j][3], sl2, ms_hi)) : att_ex2(fmaf(sc[j][3], sl2, ms_hi));
-      l_lo += sc[j][0] + sc[j][1];
-      l_hi += sc[j][2] + sc[j][3];
     }
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
@@ -610,11 +621,15 @@ __global__ void __launch_bounds__(256) k_attention_mma(__nv_bfloat16* __restrict
           mma_bf16_16816(o[nd], pa, b00, b01);
           mma_bf16_16816(o[nd + 1], pa, b10, b11);
         }
+        {  // the ones column (lanes 0-15 supply the sixteen row addresses of the two 8-key halves)
+          uint32_t b0, b1;
+          asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(b0), "=r"(b1) : "r"(va + (uint32_t)(D * 2) - (uint32_t)((lane >> 4) * 16)));
+          mma_bf16_16816(osum, pa, b0, b1);
+        }
       }
     }
   }
-  l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1); l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
-  l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1); l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
+  const float l_lo = __shfl_sync(0xffffffffu, osum[0], lane & ~3), l_hi = __shfl_sync(0xffffffffu, osum[2], lane & ~3);
   const float i_lo = 1.0f / l_lo, i_hi = 1.0f / l_hi;
   __nv_bfloat16* d_lo = out + ((int64_t)n * L + r0 + g) * C + h * D + 2 * t;
   __nv_bfloat16* d_hi = d_lo + (int64_t)8 * C;
