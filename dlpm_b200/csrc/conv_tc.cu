@@ -1390,6 +1390,7 @@ static int encode_out_map_up(CUtensorMap* m, void* base, int64_t B, int H_out, i
 }
 
 static int g_tma_store_enabled = 1;
+static int g_single_wave_cg1 = 1;  // "conv_single_wave_cg1"
 static int g_tall256_enabled = 1;
 static int g_xf_dbg = 0;  // timing experiments only: 1 = transform warps skip the math, 2 = skip the proxy fence
 static int g_l2_prefetch = 0;  // measured: no gain (the three-stage ring already covers the HBM latency)
@@ -1469,6 +1470,11 @@ int conv_plan(ConvLaunch* L, const void* in, const void* w, const float* bias, c
   L->cta_group = (conv_cta_group_override() == 1) ? 1
                  : ((bn >= 32 && (int64_t)((L->n_m_tiles / L->msub + 1) / 2) * L->n_n_tiles * L->n_par >= 32) ? 2 : 1);
   if (conv_cta_group_override() == 2 && bn >= 32) L->cta_group = 2;
+  // ... but not when single CTAs already fit one wave with one work item each (4x4 maps at batch 512: 128 tiles): a pair then saves
+  // nothing it could amortise (half the weight tile of ONE item) and pays the cluster launch, the paired TMEM allocation handshake
+  // and the remote barrier hops: measured 20.4 -> 18.3 us per 256 -> 256 layer at 4x4
+  if (g_single_wave_cg1 && conv_cta_group_override() == 0 && (int64_t)(L->n_m_tiles / L->msub) * L->n_n_tiles * L->n_par <= kNumSMs)
+    L->cta_group = 1;
   if (dxs) L->cta_group = 1;
   // fused GroupNorm targets on a map of 256 pixels: CTA pairs whatever the batch, so that the pair's accumulator stage holds the
   // whole sample and the GroupNorm runs in the epilogue (GNE) instead of the post warps
@@ -1789,6 +1795,10 @@ int dlpm_b200_set_option(const char* name, int value) {
   }
   if (std::string(name) == "attention_poly") {
     attention_set_poly(value);
+    return DLPM_OK;
+  }
+  if (std::string(name) == "conv_single_wave_cg1") {
+    g_single_wave_cg1 = value != 0;
     return DLPM_OK;
   }
   if (std::string(name) == "conv_tma_store") {
