@@ -250,6 +250,8 @@ class GenerativeLevyProcess:
             D *= s
         T = self.reverse_steps
         d = self.dlpm
+        if B == 0:  # same error as the reference, which indexes t[0] of the empty batch (GenerativeLevyProcess.py:210)
+            raise IndexError("index 0 is out of bounds for dimension 0 with size 0")
         st = state or rng.default_state()
         net = _Net(model, dev)
         if hasattr(net.model, "eval"):

@@ -74,6 +74,8 @@ def LIM_sampler(ddim, x, y, model, sde, levy, isotropic, steps, gen_a, gen_eps, 
     coef_d = coef.to(dev)
     x = x.to(dev, torch.float32).contiguous().clone()
     B = x.shape[0]
+    if B == 0:  # the reference's LIM loop runs over the empty batch and returns empty tensors (sampler.py:218-258)
+        return (x, torch.empty((steps + 1, *x.shape), device=dev, dtype=torch.float32)) if get_sample_history else x
     D = x[0].numel()
     clamp_eps = gen_eps.kwargs.get("clamp_eps", None)
     st = state or rng.default_state()

@@ -226,3 +226,23 @@ def test_single_step_and_progressive_api(model):
     xs = d.sample_x_t_from_xstart_given_Sigma(x, tv, a, z_t=eps)
     np.testing.assert_allclose(xs.cpu().numpy(), (d.bargammas[T - 4] * x + a.sqrt() * eps).cpu().numpy(), rtol=1e-6, atol=1e-6)
     assert len(d.update_constants(x.shape)) == 4
+
+
+def test_empty_and_single_sample_batches(model):
+    """Batch edge cases through ``sample()``.  An EMPTY batch behaves as in the reference (checked against it on CPU): the DLPM /
+    DLIM loops index ``t[0]`` of the empty batch and raise IndexError (GenerativeLevyProcess.py:210), LIM's loop runs over the
+    empty tensors and returns them (history of steps + 1 entries, sampler.py:218-258).  A single sample runs every loop."""
+    from dlpm_b200 import GenerativeLevyProcess
+    glp = GenerativeLevyProcess(1.7, "cuda", 20, rescale_timesteps=True, isotropic=True)
+    lim = GenerativeLevyProcess(1.7, "cuda", 20, rescale_timesteps=True, isotropic=True, LIM=True)
+    for det in (False, True):
+        with pytest.raises(IndexError):
+            glp.sample({"default": model}, [0, 1, 2], reverse_steps=20, deterministic=det, dlim_eta=0.0)
+    x, h = lim.sample({"default": model}, [0, 1, 2], reverse_steps=5, get_sample_history=True)
+    assert tuple(x.shape) == (0, 1, 2) and tuple(h.shape) == (6, 0, 1, 2)
+    assert tuple(lim.sample({"default": model}, [0, 1, 2], reverse_steps=5).shape) == (0, 1, 2)
+    for proc, steps, n_hist in ((glp, 20, 20), (lim, 5, 6)):
+        for det in (False, True):
+            x, h = proc.sample({"default": model}, [1, 1, 2], reverse_steps=steps, deterministic=det, dlim_eta=0.0, get_sample_history=True)
+            assert tuple(x.shape) == (1, 1, 2) and tuple(h.shape) == (n_hist, 1, 1, 2)
+            assert torch.isfinite(x).all() and torch.equal(h[-1], x)
