@@ -509,3 +509,28 @@ def test_distribution_of_1000_step_samples_matches_reference():
     for name in feats:
         assert stats[name]["p"] > 1e-3, (name, stats[name])
     assert stats["pixel_mean_z"]["rms"] < 1.5 and stats["pixel_mean_z"]["max_abs"] < 6.0, stats["pixel_mean_z"]
+
+
+def test_dlim_from_initial_data_against_reference():
+    """``sample(deterministic=True, dlim_eta=0.0, initial_data=x)`` (GenerativeLevyProcess.py:548-556 -> ddim_sample_loop with
+    ``noise=initial_data``): the DLIM chain started from the caller's tensor instead of barsigma_{T-1} eps.  At eta = 0 the update
+    uses no random variate (the A the reference draws beforehand does not enter it), so the two implementations can be compared
+    directly, history included: MLP in fp32 at the north star's 1e-3, MNIST-size UNet at the bf16 bar."""
+    from dlpm_b200 import GenerativeLevyProcess
+    from oracle import ref_live
+    ns = ref_import.load()
+    alpha, T = 1.7, 25
+    for kind, shape, tol in (("mlp", (16, 1, 2), 1e-3), ("unet", (2, 1, 32, 32), 2e-2)):
+        ref_model = ref_live.make_mlp("cuda", seed=0) if kind == "mlp" else ref_live.make_unet(CFG_MNIST, 1, "cuda", seed=3)
+        x0 = 1.5 * torch.randn(*shape, generator=torch.Generator().manual_seed(11)).cuda()
+        rglp = ns.glp.GenerativeLevyProcess(alpha, "cuda", T, rescale_timesteps=True, isotropic=True)
+        with ref_live.strict_fp32(), torch.no_grad():
+            want, want_h = rglp.sample({"default": ref_model}, list(shape), reverse_steps=T, deterministic=True, dlim_eta=0.0,
+                                       initial_data=x0.clone(), get_sample_history=True)
+        glp = GenerativeLevyProcess(alpha, "cuda", T, rescale_timesteps=True, isotropic=True)
+        got, got_h = glp.sample({"default": ref_model}, list(shape), reverse_steps=T, deterministic=True, dlim_eta=0.0,
+                                initial_data=x0.clone(), get_sample_history=True)
+        assert tuple(got_h.shape) == tuple(want_h.shape)
+        scale = float(want_h.abs().max())
+        np.testing.assert_allclose(got_h.cpu().numpy(), want_h.cpu().numpy(), rtol=tol, atol=tol * scale, err_msg=kind)
+        np.testing.assert_allclose(got.cpu().numpy(), want.cpu().numpy(), rtol=tol, atol=tol * scale, err_msg=kind)
