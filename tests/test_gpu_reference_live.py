@@ -534,3 +534,31 @@ def test_dlim_from_initial_data_against_reference():
         scale = float(want_h.abs().max())
         np.testing.assert_allclose(got_h.cpu().numpy(), want_h.cpu().numpy(), rtol=tol, atol=tol * scale, err_msg=kind)
         np.testing.assert_allclose(got.cpu().numpy(), want.cpu().numpy(), rtol=tol, atol=tol * scale, err_msg=kind)
+
+
+def test_rescaled_schedule_sampling_against_reference():
+    """``sample(reverse_steps != the constructor's)`` (GenerativeLevyProcess.py:535-546 -> dlpm.rescale_diffusion, dlpm.py:176-185):
+    the schedule is rebuilt for the shorter chain and the network sees t / reverse_steps.  Compared on the noise-free DLIM chain from
+    the caller's initial data (MLP, fp32 bar).  Afterwards the reference is left on the short schedule (its restore guard never
+    fires); this package puts the constructor's schedule back -- both facts asserted."""
+    from dlpm_b200 import GenerativeLevyProcess
+    from oracle import ref_live
+    ns = ref_import.load()
+    alpha, T_train, T_run, shape = 1.7, 100, 20, (16, 1, 2)
+    ref_model = ref_live.make_mlp("cuda", seed=0)
+    x0 = 1.5 * torch.randn(*shape, generator=torch.Generator().manual_seed(12)).cuda()
+    rglp = ns.glp.GenerativeLevyProcess(alpha, "cuda", T_train, rescale_timesteps=True, isotropic=True)
+    glp = GenerativeLevyProcess(alpha, "cuda", T_train, rescale_timesteps=True, isotropic=True)
+    before = glp.dlpm.bargammas.clone()
+    assert torch.equal(before.cpu(), rglp.dlpm.bargammas.cpu())
+    with ref_live.strict_fp32(), torch.no_grad():
+        want, want_h = rglp.sample({"default": ref_model}, list(shape), reverse_steps=T_run, deterministic=True, dlim_eta=0.0,
+                                   initial_data=x0.clone(), get_sample_history=True)
+    got, got_h = glp.sample({"default": ref_model}, list(shape), reverse_steps=T_run, deterministic=True, dlim_eta=0.0,
+                            initial_data=x0.clone(), get_sample_history=True)
+    assert tuple(got_h.shape) == tuple(want_h.shape) == (T_run, *shape)
+    scale = float(want_h.abs().max())
+    np.testing.assert_allclose(got_h.cpu().numpy(), want_h.cpu().numpy(), rtol=1e-3, atol=1e-3 * scale)
+    np.testing.assert_allclose(got.cpu().numpy(), want.cpu().numpy(), rtol=1e-3, atol=1e-3 * scale)
+    assert glp.reverse_steps == T_train and torch.equal(glp.dlpm.bargammas, before)  # restored here ...
+    assert rglp.dlpm.bargammas.numel() == T_run                                        # ... not in the reference
