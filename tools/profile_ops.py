@@ -21,7 +21,8 @@ ap.add_argument("--opt", action="append", default=[])
 ap.add_argument("--summary", action="store_true")
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--config", default="cifar", choices=["cifar", "mnist", "cifar10"])
-ap.add_argument("--no-fuse", action="store_true")  # GroupNorm as separate launches (round-1 path) instead of the producers' post warps
+ap.add_argument("--fuse", action="store_true")  # GroupNorms that cannot run in a conv epilogue: the producers' post warps (maps <= 8x8) instead of separate launches
+ap.add_argument("--no-fuse", action="store_true")  # (the default; kept for old command lines)
 ap.add_argument("--no-gne", action="store_true")  # ... and no GroupNorm in the epilogue on the 16x16 maps either
 args = ap.parse_args()
 for o in args.opt:
@@ -35,7 +36,7 @@ else:
     m = UNetModel(3, 128, 3, 2, (16,), channel_mult=(1, 2, 2, 2), num_heads=4, use_scale_shift_norm=True)
 randomize_parameters_(m, 0)
 m = m.cuda().eval()
-m.fuse_groupnorm = not args.no_fuse
+m.fuse_groupnorm = bool(args.fuse) and not args.no_fuse  # default: the product's default engine
 m.fuse_groupnorm_epilogue = not args.no_gne
 B = args.batch
 eng = m.engine(32, 32, B)
